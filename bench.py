@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the DM-VIO photometric BA hot path on B200 (BASELINE.json metric).
+
+One "step" = one Gauss-Newton iteration of the hot path on the 7-keyframe / 2000-point / 640x480 synthetic window
+(SURVEY.md §8d): resubstitute(x) + point step, residual/Jacobian evaluation of every active point-residual, per-pair
+Hessian blocks, per-point Schur complement, fp64 stitch to the dense (8nf+4)^2 system — the dense host solve excluded.
+
+  value      device-resident throughput: all inputs in HBM, CUDA-event time of the kernel sequence, L2 scrubbed between steps
+  e2e        the same step through the C ABI call a DM-VIO host would make (dmv_ba_gn_step + dmv_ba_apply_res):
+             host buffers in, H/b out, H2D + D2H copies and the stream synchronisation inside the timed region
+  roofline   algorithmic bytes of the dominant kernel (ba_point_kernel) / its CUDA-event duration vs measured HBM peak
+  cpu_baseline   the CPU oracle (restatement of the reference's SSE path, 6 worker threads like NUM_THREADS) on this host
+
+N > 1 (torchrun): weak scaling — every rank owns 2000 points of one N*2000-point window (images and tables replicated),
+the stitched system is all-reduced over NCCL inside every step.
+`--impl reference` times the CPU oracle only (rank 0), same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "point-residuals/sec per GN iter (7 KF, 2000 pts, 640x480)"
+UNIT = "point-residuals/s"
+NF, NPTS, W_, H_ = 7, 2000, 640, 480
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md, sampled while the timed region runs."""
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(nres, npts, nf):
+    """B_alg = 436*nres + 112*npts + 8*(8nf+4)(8nf+5)."""
+    N = 8 * nf + 4
+    return 436 * nres + 112 * npts + 8 * N * (N + 1)
+
+
+def shard_window(W, rank, world):
+    """points p with p % world == rank (keeps the host ordering), and their residuals re-indexed."""
+    if world == 1:
+        return W
+    keep = np.arange(len(W["host"])) % world == rank
+    newidx = -np.ones(len(keep), np.int64)
+    newidx[keep] = np.arange(keep.sum())
+    S = dict(W)
+    for k in ("host", "u", "v", "idepth", "idepth_zero", "color", "weights", "hasDepthPrior"):
+        S[k] = W[k][keep]
+    rk = keep[W["res_point"]]
+    S["res_point"] = newidx[W["res_point"][rk]].astype(np.int32)
+    S["res_target"] = W["res_target"][rk]
+    return S
+
+
+def cpu_oracle_rate(W, seconds, threads, x=None):
+    """times the oracle's hot iteration (accumulate+stitch, resubstitute, step, linearizeAll, applyRes); returns (res/s, ms/iter, iters)."""
+    from oracle import orc
+    ow = orc.Window(W, nthreads=threads)
+    ow.linearize_all()
+    ow.apply_res()
+    if x is None:
+        x, _, _ = ow.solve(0, 1e-5, 0)
+    for _ in range(2):
+        ow.hot_iteration(x, 0)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        ow.hot_iteration(x, 0)
+        n += 1
+        if time.perf_counter() - t0 >= seconds:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return ow.nres / dt, dt * 1e3, n, ow
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import dmvio_b200.synth as synth
+    W = synth.make_window(nf=NF, npts=NPTS * world, w=W_, h=H_, seed=1234)
+    threads = min(6, os.cpu_count() or 1)
+    from oracle import orc
+    ow = orc.Window(W, nthreads=threads)
+    ow.linearize_all(); ow.apply_res()
+    x, _, _ = ow.solve(0, 1e-5, 0)
+    for _ in range(args.warmup):
+        ow.hot_iteration(x, 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ow.hot_iteration(x, 0)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = ow.nres / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"sliding window {NF} KF / {NPTS * world} pts / {W_}x{H_}, pattern 8, {ow.nres} point-residuals, one GN iteration "
+                               "of the hot path per step (host solve excluded)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} full GN iterations of the window, oracle built with g++ -O3 (no -march), {threads} worker threads "
+                                   "(reference NUM_THREADS=6); the reference itself cannot be compiled here (Eigen/Boost/GTSAM absent)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunk", type=int, default=0, help="points per thread block (8/16/32, 0 = library default)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.steps < 1:
+        args.steps = 1
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import dmvio_b200.capi as capi
+    import dmvio_b200.hostmath as hm
+    import dmvio_b200.synth as synth
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---------------- workload (identical on every rank: seeded)
+    Wfull = synth.make_window(nf=NF, npts=NPTS * world, w=W_, h=H_, seed=1234)
+    Wr = shard_window(Wfull, rank, world)
+    nres_local = len(Wr["res_point"])
+    nres_total = len(Wfull["res_point"])
+    ba = capi.BA(W_, H_, max_frames=NF, max_points=len(Wr["host"]), device=local_rank, chunk_points=args.chunk)
+    for k in range(NF):
+        ba.upload_frame(k, Wr["dI"][k])
+    ba.set_window(NF)
+    ba.set_points(Wr["host"], Wr["u"], Wr["v"], Wr["idepth"], Wr["idepth_zero"], Wr["color"], Wr["weights"])
+    ba.set_residuals(Wr["res_point"], Wr["res_target"])
+    adH, adT = hm.adjoints(Wr)
+    ba.set_adjoints(adH, adT)
+    k8 = hm.calib8(Wr["K"])
+    precalc = hm.precalc_table(Wr)
+    TH = Wr["frameEnergyTH"].copy()
+    if world > 1:
+        uid = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ba.comm_init(world, rank, uid[0])
+    ba.set_state(k8, precalc, TH)
+    r0 = ba.linearize()
+    ba.apply_res()
+    acc = ba.accumulate()
+    HL, bL = hm.prior_system(Wr)
+    x = hm.solve_reduced(acc["HA"], acc["bA"], acc["Hsc"], acc["bsc"], HL, bL, lam=1e-5)
+    ba.backup_points()
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- warm-up (both paths)
+    for _ in range(max(3, args.warmup)):
+        ba.gn_step(x, k8, precalc, TH)
+        ba.apply_res()
+    ba.bench_device(x, iters=max(3, args.warmup), flush_l2=True)
+
+    launches0 = ba.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---------------- value: device-resident, CUDA events, L2 scrubbed between steps
+    barrier()
+    ms_iter, ms_point = ba.bench_device(x, iters=args.steps, flush_l2=True)
+    barrier()
+    ms_iter = max_over_ranks(ms_iter)
+    launches_value = ba.launch_count() - launches0
+    # ---------------- e2e: the C ABI call with host buffers (H2D + kernels + D2H + sync), wall clock
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ba.gn_step(x, k8, precalc, TH)
+        ba.apply_res()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
+    clocks = sampler.stop() if rank == 0 else None
+    tm = ba.last_timing()
+    h2d, d2h = ba.io_bytes()
+
+    value = nres_total / (ms_iter * 1e-3)
+    e2e_value = nres_total / (e2e_ms * 1e-3)
+    peak, peak_src = measured_peak()
+    balg = algorithmic_bytes(nres_local, len(Wr["host"]), NF)
+    ach = balg / (ms_point * 1e-3) / 1e9
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = min(6, os.cpu_count() or 1)
+        rate, ms_cpu, n_it, _ = cpu_oracle_rate(Wfull, args.cpu_seconds, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_iter": ms_cpu,
+               "sample": f"{n_it} full GN iterations of the same window in ~{args.cpu_seconds:.0f} s, oracle (g++ -O3, no -march), "
+                         f"{threads} worker threads as NUM_THREADS=6; host has {os.cpu_count()} logical cores"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_iter, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"sliding window {NF} KF / {NPTS * world} pts / {W_}x{H_}, pattern 8, {nres_total} point-residuals "
+                                   f"({nres_local}/GPU), one GN iteration of the hot path per step (host solve excluded)",
+                       "parallelism": f"points sharded over {world} GPU(s), images replicated" + (", NCCL all-reduce of H,b per step" if world > 1 else ""),
+                       "l2": "L2 scrubbed (256 MiB write) between timed steps of `value`", "chunk_points": args.chunk or 16,
+                       "n_in": r0["n_in"], "n_oob": r0["n_oob"], "n_outlier": r0["n_outlier"]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "device_ms_last_step": float(tm[0])},
+            "gpu_launches": int(ba.launch_count() - launches0),
+            "roofline": {"bound": "hbm", "kernel": "ba_point_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": balg, "kernel_ms": ms_point,
+                         "note": "working set (7 level-0 planes = 34 MB as float4) is L2-sized; the step is latency-bound, see DESIGN.md"},
+            "clocks": clocks,
+        }
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    ba.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

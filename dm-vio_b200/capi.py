@@ -1,0 +1,333 @@
+"""ctypes binding of the C ABI in include/dmvio_b200.h (libdmvio_b200.so).
+
+This is the only way Python (tests, bench.py, __graft_entry__) reaches the product: there is no Python/torch
+re-implementation of the path and no CPU fallback — loading fails loudly if the CUDA library is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdmvio_b200.so")
+_LIB = None
+
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+vp = C.c_void_p
+
+MAX_FRAMES = 8
+PRECALC_FLOATS = 32
+
+
+class DmvError(RuntimeError):
+    pass
+
+
+class BAConfig(C.Structure):
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("max_frames", C.c_int), ("max_points", C.c_int), ("device", C.c_int), ("chunk_points", C.c_int)]
+
+
+class BAParams(C.Structure):
+    _fields_ = [("huberTH", C.c_float), ("outlierTHSumComponent", C.c_float), ("affineOptModeA", C.c_float), ("affineOptModeB", C.c_float)]
+
+
+class BAState(C.Structure):
+    _fields_ = [("calib", C.c_float * 8), ("precalc", vp), ("frameEnergyTH", vp), ("idepth", vp), ("idepth_zero", vp)]
+
+
+class BALinResult(C.Structure):
+    _fields_ = [("energy", C.c_double), ("n_in", C.c_int), ("n_oob", C.c_int), ("n_outlier", C.c_int)]
+
+
+class CTConfig(C.Structure):
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("levels", C.c_int), ("max_points", C.c_int), ("device", C.c_int)]
+
+
+# every symbol declared in include/dmvio_b200.h (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "dmv_last_error", "dmv_version", "dmv_device_count",
+    "dmv_ba_create", "dmv_ba_destroy", "dmv_ba_set_params", "dmv_ba_default_params", "dmv_ba_upload_frame", "dmv_ba_upload_image",
+    "dmv_ba_set_window", "dmv_ba_set_points", "dmv_ba_set_residuals", "dmv_ba_set_adjoints", "dmv_ba_set_state", "dmv_ba_linearize",
+    "dmv_ba_get_residual_outputs", "dmv_ba_get_target_energies", "dmv_ba_apply_res", "dmv_ba_accumulate", "dmv_ba_get_point_outputs",
+    "dmv_ba_resubstitute", "dmv_ba_backup_points", "dmv_ba_restore_points", "dmv_ba_get_idepth", "dmv_ba_gn_step", "dmv_nccl_unique_id",
+    "dmv_ba_comm_init", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes",
+    "dmv_ct_create", "dmv_ct_destroy", "dmv_ct_set_K", "dmv_ct_set_ref", "dmv_ct_upload_new", "dmv_ct_upload_new_image", "dmv_ct_set_huber",
+    "dmv_ct_calc_res_gs", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count",
+]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise DmvError(f"{LIB_PATH} is missing: build it with `make -C dm-vio_b200` (python -c 'import __graft_entry__ as g; g.build()')")
+        L = C.CDLL(LIB_PATH)
+        L.dmv_last_error.restype = C.c_char_p
+        L.dmv_version.restype = C.c_char_p
+        L.dmv_ba_create.argtypes = [C.POINTER(BAConfig), C.POINTER(vp)]
+        L.dmv_ba_destroy.argtypes = [vp]
+        L.dmv_ba_set_params.argtypes = [vp, C.POINTER(BAParams)]
+        L.dmv_ba_default_params.argtypes = [C.POINTER(BAParams)]
+        L.dmv_ba_upload_frame.argtypes = [vp, C.c_int, f32p]
+        L.dmv_ba_upload_image.argtypes = [vp, C.c_int, f32p]
+        L.dmv_ba_set_window.argtypes = [vp, C.c_int, vp]
+        L.dmv_ba_set_points.argtypes = [vp, C.c_int, i32p, f32p, f32p, f32p, vp, f32p, f32p, vp]
+        L.dmv_ba_set_residuals.argtypes = [vp, C.c_int, i32p, i32p, vp, vp]
+        L.dmv_ba_set_adjoints.argtypes = [vp, f64p, f64p]
+        L.dmv_ba_set_state.argtypes = [vp, C.POINTER(BAState)]
+        L.dmv_ba_linearize.argtypes = [vp, C.POINTER(BALinResult)]
+        L.dmv_ba_get_residual_outputs.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.dmv_ba_get_target_energies.argtypes = [vp, C.c_int, f32p, C.c_int, C.POINTER(C.c_int)]
+        L.dmv_ba_apply_res.argtypes = [vp]
+        L.dmv_ba_accumulate.argtypes = [vp, f64p, f64p, f64p, f64p, C.POINTER(C.c_int)]
+        L.dmv_ba_get_point_outputs.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.dmv_ba_resubstitute.argtypes = [vp, f64p, vp, C.c_int, f64p]
+        L.dmv_ba_backup_points.argtypes = [vp]
+        L.dmv_ba_restore_points.argtypes = [vp]
+        L.dmv_ba_get_idepth.argtypes = [vp, vp, vp]
+        L.dmv_ba_gn_step.argtypes = [vp, vp, C.POINTER(BAState), C.POINTER(BALinResult), f64p]
+        L.dmv_nccl_unique_id.argtypes = [vp]
+        L.dmv_ba_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.dmv_ba_last_timing.argtypes = [vp, f32p]
+        L.dmv_ba_bench_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.dmv_ba_kernel_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
+        L.dmv_ba_io_bytes.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+        L.dmv_ct_create.argtypes = [C.POINTER(CTConfig), C.POINTER(vp)]
+        L.dmv_ct_destroy.argtypes = [vp]
+        L.dmv_ct_set_K.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.dmv_ct_set_ref.argtypes = [vp, C.c_int, C.c_int, f32p, f32p, f32p, f32p]
+        L.dmv_ct_upload_new.argtypes = [vp, C.c_int, f32p]
+        L.dmv_ct_upload_new_image.argtypes = [vp, f32p]
+        L.dmv_ct_set_huber.argtypes = [vp, C.c_float]
+        L.dmv_ct_calc_res_gs.argtypes = [vp, C.c_int, f32p, f32p, f32p, C.c_float, C.c_float, C.c_int, f64p, f64p, f64p, C.POINTER(C.c_int)]
+        L.dmv_ct_last_timing.argtypes = [vp, f32p]
+        L.dmv_ct_kernel_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise DmvError(f"dmvio_b200 error {rc}: {lib().dmv_last_error().decode()}")
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+def _c(a, t):
+    return None if a is None else np.ascontiguousarray(a, t)
+
+
+class BA:
+    """Thin RAII wrapper over a dmv_ba handle; argument names follow include/dmvio_b200.h."""
+
+    def __init__(self, w, h, max_frames=8, max_points=8192, device=0, chunk_points=0):
+        self.L = lib()
+        cfg = BAConfig(w, h, max_frames, max_points, device, chunk_points)
+        self.h = vp()
+        check(self.L.dmv_ba_create(C.byref(cfg), C.byref(self.h)))
+        self.w, self.hh = w, h
+        self.nf = self.npts = self.nres = 0
+        self._keep = {}
+
+    def close(self):
+        if self.h:
+            self.L.dmv_ba_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, huberTH=9.0, outlierTHSumComponent=2500.0, affineOptModeA=1e12, affineOptModeB=1e8):
+        p = BAParams(huberTH, outlierTHSumComponent, affineOptModeA, affineOptModeB)
+        check(self.L.dmv_ba_set_params(self.h, C.byref(p)))
+
+    def upload_frame(self, slot, dI):
+        check(self.L.dmv_ba_upload_frame(self.h, slot, _c(dI, np.float32).reshape(-1)))
+
+    def upload_image(self, slot, img):
+        check(self.L.dmv_ba_upload_image(self.h, slot, _c(img, np.float32).reshape(-1)))
+
+    def set_window(self, nf, slots=None):
+        s = _c(slots, np.int32)
+        check(self.L.dmv_ba_set_window(self.h, nf, _p(s)))
+        self.nf = nf
+        self.N = 8 * nf + 4
+
+    def set_points(self, host, u, v, idepth, idepth_zero, color, weights, priorF=None):
+        self.npts = len(host)
+        iz, pf = _c(idepth_zero, np.float32), _c(priorF, np.float32)
+        check(self.L.dmv_ba_set_points(self.h, self.npts, _c(host, np.int32), _c(u, np.float32), _c(v, np.float32), _c(idepth, np.float32),
+                                       _p(iz), _c(color, np.float32).reshape(-1), _c(weights, np.float32).reshape(-1), _p(pf)))
+
+    def set_residuals(self, point, target, state=None, energy=None):
+        self.nres = len(point)
+        s, e = _c(state, np.int32), _c(energy, np.float32)
+        check(self.L.dmv_ba_set_residuals(self.h, self.nres, _c(point, np.int32), _c(target, np.int32), _p(s), _p(e)))
+
+    def set_adjoints(self, adHost, adTarget):
+        check(self.L.dmv_ba_set_adjoints(self.h, _c(adHost, np.float64).reshape(-1), _c(adTarget, np.float64).reshape(-1)))
+
+    def _state(self, calib8, precalc, TH, idepth=None, idepth_zero=None):
+        st = BAState()
+        k = _c(calib8, np.float32)
+        for i in range(8):
+            st.calib[i] = float(k[i])
+        pc, th, idd, idz = _c(precalc, np.float32), _c(TH, np.float32), _c(idepth, np.float32), _c(idepth_zero, np.float32)
+        self._keep = dict(pc=pc, th=th, idd=idd, idz=idz)
+        st.precalc, st.frameEnergyTH, st.idepth, st.idepth_zero = _p(pc), _p(th), _p(idd), _p(idz)
+        return st
+
+    def set_state(self, calib8, precalc, TH, idepth=None, idepth_zero=None):
+        st = self._state(calib8, precalc, TH, idepth, idepth_zero)
+        check(self.L.dmv_ba_set_state(self.h, C.byref(st)))
+
+    def linearize(self):
+        r = BALinResult()
+        check(self.L.dmv_ba_linearize(self.h, C.byref(r)))
+        return dict(energy=r.energy, n_in=r.n_in, n_oob=r.n_oob, n_outlier=r.n_outlier)
+
+    def gn_step(self, x, calib8, precalc, TH, idepth=None, idepth_zero=None):
+        st = self._state(calib8, precalc, TH, idepth, idepth_zero)
+        r = BALinResult()
+        sums = np.zeros(3)
+        xx = _c(x, np.float64)
+        check(self.L.dmv_ba_gn_step(self.h, _p(xx), C.byref(st), C.byref(r), sums))
+        return dict(energy=r.energy, n_in=r.n_in, n_oob=r.n_oob, n_outlier=r.n_outlier, sums=sums)
+
+    def residual_outputs(self):
+        n = self.nres
+        o = dict(newState=np.zeros(n, np.int32), newEnergy=np.zeros(n, np.float32), newEnergyWithOutlier=np.zeros(n, np.float32),
+                 centerProjectedTo=np.zeros((n, 3), np.float32), JpJdF=np.zeros((n, 8), np.float32))
+        check(self.L.dmv_ba_get_residual_outputs(self.h, _p(o["newState"]), _p(o["newEnergy"]), _p(o["newEnergyWithOutlier"]),
+                                                 _p(o["centerProjectedTo"]), _p(o["JpJdF"])))
+        return o
+
+    def target_energies(self, target):
+        out = np.zeros(max(self.npts, 1), np.float32)
+        n = C.c_int(0)
+        check(self.L.dmv_ba_get_target_energies(self.h, target, out, len(out), C.byref(n)))
+        return out[:n.value]
+
+    def apply_res(self):
+        check(self.L.dmv_ba_apply_res(self.h))
+
+    def accumulate(self):
+        N = self.N
+        o = dict(HA=np.zeros((N, N)), bA=np.zeros(N), Hsc=np.zeros((N, N)), bsc=np.zeros(N))
+        n = C.c_int(0)
+        check(self.L.dmv_ba_accumulate(self.h, o["HA"].reshape(-1), o["bA"], o["Hsc"].reshape(-1), o["bsc"], C.byref(n)))
+        o["resInA"] = n.value
+        return o
+
+    def point_outputs(self):
+        n = self.npts
+        o = dict(Hdd=np.zeros(n, np.float32), bd=np.zeros(n, np.float32), Hcd=np.zeros((n, 4), np.float32), HdiF=np.zeros(n, np.float32),
+                 bdSumF=np.zeros(n, np.float32))
+        check(self.L.dmv_ba_get_point_outputs(self.h, _p(o["Hdd"]), _p(o["bd"]), _p(o["Hcd"]), _p(o["HdiF"]), _p(o["bdSumF"])))
+        return o
+
+    def resubstitute(self, x, apply=False):
+        step = np.zeros(self.npts, np.float32)
+        sums = np.zeros(3)
+        check(self.L.dmv_ba_resubstitute(self.h, _c(x, np.float64), _p(step), int(apply), sums))
+        return step, sums
+
+    def backup_points(self):
+        check(self.L.dmv_ba_backup_points(self.h))
+
+    def restore_points(self):
+        check(self.L.dmv_ba_restore_points(self.h))
+
+    def get_idepth(self):
+        a, b = np.zeros(self.npts, np.float32), np.zeros(self.npts, np.float32)
+        check(self.L.dmv_ba_get_idepth(self.h, _p(a), _p(b)))
+        return a, b
+
+    def last_timing(self):
+        ms = np.zeros(4, np.float32)
+        check(self.L.dmv_ba_last_timing(self.h, ms))
+        return ms
+
+    def bench_device(self, x=None, iters=100, flush_l2=True):
+        a, b = C.c_float(0), C.c_float(0)
+        xx = _c(x, np.float64)
+        check(self.L.dmv_ba_bench_device(self.h, _p(xx), iters, int(flush_l2), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def launch_count(self):
+        n = C.c_longlong(0)
+        check(self.L.dmv_ba_kernel_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def io_bytes(self):
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        check(self.L.dmv_ba_io_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def comm_init(self, nranks, rank, uid_bytes):
+        buf = C.create_string_buffer(bytes(uid_bytes), 128)
+        check(self.L.dmv_ba_comm_init(self.h, nranks, rank, C.cast(buf, vp)))
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    check(lib().dmv_nccl_unique_id(C.cast(buf, vp)))
+    return bytes(buf.raw)
+
+
+class CT:
+    def __init__(self, w, h, levels, max_points=65536, device=0):
+        self.L = lib()
+        cfg = CTConfig(w, h, levels, max_points, device)
+        self.h = vp()
+        check(self.L.dmv_ct_create(C.byref(cfg), C.byref(self.h)))
+        self.levels = levels
+
+    def close(self):
+        if self.h:
+            self.L.dmv_ct_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_K(self, lvl, fx, fy, cx, cy):
+        check(self.L.dmv_ct_set_K(self.h, lvl, fx, fy, cx, cy))
+
+    def set_ref(self, lvl, u, v, idepth, color):
+        check(self.L.dmv_ct_set_ref(self.h, lvl, len(u), _c(u, np.float32), _c(v, np.float32), _c(idepth, np.float32), _c(color, np.float32)))
+
+    def upload_new(self, lvl, dIp):
+        check(self.L.dmv_ct_upload_new(self.h, lvl, _c(dIp, np.float32).reshape(-1)))
+
+    def upload_new_image(self, img):
+        check(self.L.dmv_ct_upload_new_image(self.h, _c(img, np.float32).reshape(-1)))
+
+    def set_huber(self, th):
+        check(self.L.dmv_ct_set_huber(self.h, th))
+
+    def calc_res_gs(self, lvl, RKi, t, affLL, b0, cutoff, want_gs=True):
+        res6 = np.zeros(6); H = np.zeros(64); b = np.zeros(8); n = C.c_int(0)
+        check(self.L.dmv_ct_calc_res_gs(self.h, lvl, _c(RKi, np.float32).reshape(-1), _c(t, np.float32), _c(affLL, np.float32), b0, cutoff,
+                                        int(want_gs), res6, H, b, C.byref(n)))
+        return res6, H.reshape(8, 8), b, n.value
+
+    def last_timing(self):
+        ms = np.zeros(4, np.float32)
+        check(self.L.dmv_ct_last_timing(self.h, ms))
+        return ms
+
+    def launch_count(self):
+        n = C.c_longlong(0)
+        check(self.L.dmv_ct_kernel_launch_count(self.h, C.byref(n)))
+        return n.value

@@ -1,0 +1,685 @@
+// C-ABI of the bundle-adjustment handle (include/dmvio_b200.h).  Host-side plumbing only: buffer ownership, the
+// [target][point] residual-slot layout, tentative/committed double buffering, one stream + pinned staging per handle.
+#include "../../include/dmvio_b200.h"
+#include "ba_device.cuh"
+#include "common_host.h"
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace dmv {
+void launch_point_kernel(const BAWinDev* wins, int nwin, int max_chunks, int P, int nf, cudaStream_t s);
+void launch_reduce_kernel(const BAWinDev* wins, int nwin, int nf, int ntiles, cudaStream_t s);
+void launch_stitch_kernel(const BAWinDev* wins, int nwin, int N, cudaStream_t s);
+void launch_resub_kernel(const BAWinDev* wins, int nwin, int npts, int apply, cudaStream_t s);
+void launch_backup_kernel(const BAWinDev* wins, int nwin, int npts, int restore, cudaStream_t s);
+void launch_repack(const float* src, float4* dst, int n, cudaStream_t s);
+void launch_make_dI(const float* img, float4* dst, int w, int h, cudaStream_t s);
+void launch_l2_flush(float4* buf, size_t n, cudaStream_t s);
+}  // namespace dmv
+
+using namespace dmv;
+
+struct HostUpload {  // one pinned block -> one H2D copy per linearisation
+  BAWinDev win;
+  BAIter it;
+};
+
+struct dmv_ba {
+  dmv_ba_config cfg;
+  dmv_ba_params prm;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int P = 16;
+  int mp = 0;  // point capacity (slot pitch)
+  int nf = 0, npts = 0, nres = 0, nchunks = 0, max_chunks = 0;
+  int N = 0, NW = 0, T = 0, ntiles = 0;
+  int slots[MAXF];
+  // device buffers
+  float4* d_img[MAXF] = {nullptr};
+  float* d_stage_img = nullptr;
+  HostUpload* d_up = nullptr;  // BAWinDev + BAIter
+  BAAdj* d_adj = nullptr;
+  BAChunk* d_chunks = nullptr;
+  float2* d_uv = nullptr;
+  float *d_idepth = nullptr, *d_idepth_zero = nullptr, *d_idepth_backup = nullptr, *d_color = nullptr, *d_weights = nullptr, *d_priorF = nullptr;
+  uint8_t* d_st_in = nullptr;
+  float* d_en_in = nullptr;
+  uint8_t* d_st_new[2] = {nullptr, nullptr};
+  float *d_en_new[2] = {nullptr, nullptr}, *d_en_wo[2] = {nullptr, nullptr}, *d_cpt[2] = {nullptr, nullptr}, *d_jpjd[2] = {nullptr, nullptr},
+        *d_pout[2] = {nullptr, nullptr};
+  double* d_result[2] = {nullptr, nullptr};
+  float* d_step = nullptr;
+  float *d_top_part = nullptr, *d_sc_part = nullptr, *d_misc_part = nullptr;
+  double *d_step_part = nullptr, *d_top_sum = nullptr, *d_sc_sum = nullptr;
+  float4* d_flush = nullptr;
+  size_t flush_n = 0;
+  // pinned host
+  HostUpload* h_up = nullptr;
+  BAAdj* h_adj = nullptr;
+  double* h_result[2] = {nullptr, nullptr};
+  float* h_scratch = nullptr;  // max(mp*8, w*h*3) floats
+  size_t scratch_floats = 0;
+  // host bookkeeping
+  std::vector<BAChunk> chunks;
+  std::vector<int> host_of_point;
+  std::vector<int> res_slot;   // residual index -> slot (t*mp+p)
+  std::vector<uint8_t> h_st_in;
+  std::vector<float> h_en_in;
+  int tent = 0;                // index of the tentative buffer set; committed = 1 - tent
+  bool have_tentative = false, have_committed = false, have_adj = false, have_state = false;
+  long long launches = 0;
+  float last_ms[4] = {0, 0, 0, 0};
+  // NCCL
+  void* nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) return dmv::set_error(DMV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+static int fill_descriptor(dmv_ba* b) {
+  BAWinDev& W = b->h_up->win;
+  std::memset(&W, 0, sizeof(W));
+  W.nf = b->nf; W.npts = b->npts; W.nchunks = b->nchunks; W.w = b->cfg.w; W.h = b->cfg.h;
+  W.N = b->N; W.NW = b->NW; W.T = b->T; W.ntiles = b->ntiles; W.mp = b->mp;
+  W.huberTH = b->prm.huberTH; W.outlierTHSum = b->prm.outlierTHSumComponent;
+  W.zeroA = b->prm.affineOptModeA < 0; W.zeroB = b->prm.affineOptModeB < 0;
+  for (int f = 0; f < b->nf; f++) W.img[f] = b->d_img[b->slots[f]];
+  W.it = &b->d_up->it;
+  W.adj = b->d_adj;
+  W.chunks = b->d_chunks;
+  int c = 0;
+  for (int h = 0; h <= MAXF; h++) {
+    while (c < b->nchunks && b->chunks[c].host < h) c++;
+    W.chunk_beg[h] = c;
+  }
+  W.uv = b->d_uv; W.idepth = b->d_idepth; W.idepth_zero = b->d_idepth_zero; W.idepth_backup = b->d_idepth_backup;
+  W.color = b->d_color; W.weights = b->d_weights; W.priorF = b->d_priorF;
+  W.st_in = b->d_st_in; W.en_in = b->d_en_in;
+  const int t = b->tent, c2 = 1 - b->tent;
+  W.st_new = b->d_st_new[t]; W.en_new = b->d_en_new[t]; W.en_wo = b->d_en_wo[t]; W.cpt = b->d_cpt[t]; W.jpjd = b->d_jpjd[t]; W.pout = b->d_pout[t];
+  W.c_st = b->d_st_new[c2]; W.c_jpjd = b->d_jpjd[c2]; W.c_pout = b->d_pout[c2];
+  W.step = b->d_step;
+  W.top_part = b->d_top_part; W.sc_part = b->d_sc_part; W.misc_part = b->d_misc_part; W.step_part = b->d_step_part;
+  W.top_sum = b->d_top_sum; W.sc_sum = b->d_sc_sum;
+  W.result = b->d_result[t];
+  return DMV_OK;
+}
+
+extern "C" {
+
+void dmv_ba_default_params(dmv_ba_params* p) {
+  p->huberTH = 9.f;
+  p->outlierTHSumComponent = 50.f * 50.f;
+  p->affineOptModeA = 1e12f;
+  p->affineOptModeB = 1e8f;
+}
+
+int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
+  if (!cfg || !out) return set_error(DMV_ERR_INVALID, "null argument");
+  if (cfg->max_frames < 2 || cfg->max_frames > DMV_MAX_FRAMES) return set_error(DMV_ERR_INVALID, "max_frames must be in [2,%d]", DMV_MAX_FRAMES);
+  if (cfg->w < 16 || cfg->h < 16 || cfg->max_points < 1) return set_error(DMV_ERR_INVALID, "bad size");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_error(DMV_ERR_NO_DEVICE, "no CUDA device: dmvio_b200 has no CPU path");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return set_error(DMV_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+  CK(cudaSetDevice(cfg->device));
+  dmv_ba* b = new dmv_ba();
+  b->cfg = *cfg;
+  b->device = cfg->device;
+  dmv_ba_default_params(&b->prm);
+  b->P = (cfg->chunk_points == 8 || cfg->chunk_points == 16 || cfg->chunk_points == 32) ? cfg->chunk_points : 16;
+  b->mp = (cfg->max_points + 31) & ~31;
+  const int MF = MAXF, mp = b->mp;
+  b->max_chunks = (mp + b->P - 1) / b->P + MF;
+  const size_t npx = (size_t)cfg->w * cfg->h;
+  CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; i++) CK(cudaEventCreate(&b->ev[i]));
+  for (int f = 0; f < cfg->max_frames; f++) CK(cudaMalloc(&b->d_img[f], npx * sizeof(float4)));
+  CK(cudaMalloc(&b->d_stage_img, npx * 3 * sizeof(float)));
+  CK(cudaMalloc(&b->d_up, sizeof(HostUpload)));
+  CK(cudaMalloc(&b->d_adj, sizeof(BAAdj)));
+  CK(cudaMalloc(&b->d_chunks, sizeof(BAChunk) * b->max_chunks));
+  CK(cudaMalloc(&b->d_uv, sizeof(float2) * mp));
+  CK(cudaMalloc(&b->d_idepth, sizeof(float) * mp));
+  CK(cudaMalloc(&b->d_idepth_zero, sizeof(float) * mp));
+  CK(cudaMalloc(&b->d_idepth_backup, sizeof(float) * mp));
+  CK(cudaMalloc(&b->d_color, sizeof(float) * mp * 8));
+  CK(cudaMalloc(&b->d_weights, sizeof(float) * mp * 8));
+  CK(cudaMalloc(&b->d_priorF, sizeof(float) * mp));
+  CK(cudaMalloc(&b->d_st_in, (size_t)MF * mp));
+  CK(cudaMalloc(&b->d_en_in, sizeof(float) * MF * mp));
+  for (int k = 0; k < 2; k++) {
+    CK(cudaMalloc(&b->d_st_new[k], (size_t)MF * mp));
+    CK(cudaMemset(b->d_st_new[k], 0xff, (size_t)MF * mp));
+    CK(cudaMalloc(&b->d_en_new[k], sizeof(float) * MF * mp));
+    CK(cudaMalloc(&b->d_en_wo[k], sizeof(float) * MF * mp));
+    CK(cudaMalloc(&b->d_cpt[k], sizeof(float) * 3 * MF * mp));
+    CK(cudaMalloc(&b->d_jpjd[k], sizeof(float) * 8 * MF * mp));
+    CK(cudaMalloc(&b->d_pout[k], sizeof(float) * 8 * mp));
+    CK(cudaMemset(b->d_pout[k], 0, sizeof(float) * 8 * mp));
+    CK(cudaMalloc(&b->d_result[k], sizeof(double) * result_doubles(8 * MF + 4)));
+    CK(cudaMallocHost(&b->h_result[k], sizeof(double) * result_doubles(8 * MF + 4)));
+  }
+  CK(cudaMalloc(&b->d_step, sizeof(float) * mp));
+  CK(cudaMemset(b->d_step, 0, sizeof(float) * mp));
+  const int maxT = (8 * MF + 4 + 1 + 3) / 4, maxTiles = maxT * (maxT + 1) / 2;
+  CK(cudaMalloc(&b->d_top_part, sizeof(float) * (size_t)b->max_chunks * MF * TOP_PART));
+  CK(cudaMalloc(&b->d_sc_part, sizeof(float) * (size_t)b->max_chunks * maxTiles * 16));
+  CK(cudaMalloc(&b->d_misc_part, sizeof(float) * (size_t)b->max_chunks * MF * 4));
+  CK(cudaMalloc(&b->d_step_part, sizeof(double) * 2 * ((mp + 127) / 128 + 1)));
+  CK(cudaMalloc(&b->d_top_sum, sizeof(double) * MF * MF * TOP_PART));
+  CK(cudaMalloc(&b->d_sc_sum, sizeof(double) * maxTiles * 16));
+  CK(cudaMallocHost(&b->h_up, sizeof(HostUpload)));
+  CK(cudaMallocHost(&b->h_adj, sizeof(BAAdj)));
+  std::memset(b->h_up, 0, sizeof(HostUpload));
+  b->scratch_floats = std::max((size_t)mp * 8 * MF, npx * 3);
+  CK(cudaMallocHost(&b->h_scratch, sizeof(float) * b->scratch_floats));
+  for (int f = 0; f < MF; f++) b->slots[f] = f;
+  *out = b;
+  return DMV_OK;
+}
+
+int dmv_ba_destroy(dmv_ba* b) {
+  if (!b) return DMV_OK;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (int f = 0; f < MAXF; f++) cudaFree(b->d_img[f]);
+  cudaFree(b->d_stage_img); cudaFree(b->d_up); cudaFree(b->d_adj); cudaFree(b->d_chunks); cudaFree(b->d_uv); cudaFree(b->d_idepth);
+  cudaFree(b->d_idepth_zero); cudaFree(b->d_idepth_backup); cudaFree(b->d_color); cudaFree(b->d_weights); cudaFree(b->d_priorF);
+  cudaFree(b->d_st_in); cudaFree(b->d_en_in);
+  for (int k = 0; k < 2; k++) {
+    cudaFree(b->d_st_new[k]); cudaFree(b->d_en_new[k]); cudaFree(b->d_en_wo[k]); cudaFree(b->d_cpt[k]); cudaFree(b->d_jpjd[k]);
+    cudaFree(b->d_pout[k]); cudaFree(b->d_result[k]); cudaFreeHost(b->h_result[k]);
+  }
+  cudaFree(b->d_step); cudaFree(b->d_top_part); cudaFree(b->d_sc_part); cudaFree(b->d_misc_part); cudaFree(b->d_step_part);
+  cudaFree(b->d_top_sum); cudaFree(b->d_sc_sum); cudaFree(b->d_flush);
+  cudaFreeHost(b->h_up); cudaFreeHost(b->h_adj); cudaFreeHost(b->h_scratch);
+  for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+  if (b->nccl_comm) dmv::nccl_destroy(b->nccl_comm);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+  return DMV_OK;
+}
+
+int dmv_ba_set_params(dmv_ba* b, const dmv_ba_params* p) {
+  if (!b || !p) return set_error(DMV_ERR_INVALID, "null argument");
+  b->prm = *p;
+  return DMV_OK;
+}
+
+int dmv_ba_upload_frame(dmv_ba* b, int slot, const float* dI) {
+  if (!b || !dI || slot < 0 || slot >= b->cfg.max_frames) return set_error(DMV_ERR_INVALID, "bad slot/pointer");
+  CK(cudaSetDevice(b->device));
+  const size_t npx = (size_t)b->cfg.w * b->cfg.h;
+  std::memcpy(b->h_scratch, dI, npx * 3 * sizeof(float));
+  CK(cudaMemcpyAsync(b->d_stage_img, b->h_scratch, npx * 3 * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+  launch_repack(b->d_stage_img, b->d_img[slot], (int)npx, b->stream);
+  b->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(b->stream));
+  return DMV_OK;
+}
+
+int dmv_ba_upload_image(dmv_ba* b, int slot, const float* image) {
+  if (!b || !image || slot < 0 || slot >= b->cfg.max_frames) return set_error(DMV_ERR_INVALID, "bad slot/pointer");
+  CK(cudaSetDevice(b->device));
+  const size_t npx = (size_t)b->cfg.w * b->cfg.h;
+  std::memcpy(b->h_scratch, image, npx * sizeof(float));
+  CK(cudaMemcpyAsync(b->d_stage_img, b->h_scratch, npx * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+  launch_make_dI(b->d_stage_img, b->d_img[slot], b->cfg.w, b->cfg.h, b->stream);
+  b->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(b->stream));
+  return DMV_OK;
+}
+
+int dmv_ba_set_window(dmv_ba* b, int nf, const int* slots) {
+  if (!b || nf < 2 || nf > b->cfg.max_frames) return set_error(DMV_ERR_INVALID, "nf out of range");
+  for (int f = 0; f < nf; f++) {
+    const int s = slots ? slots[f] : f;
+    if (s < 0 || s >= b->cfg.max_frames) return set_error(DMV_ERR_INVALID, "slot out of range");
+    b->slots[f] = s;
+  }
+  b->nf = nf;
+  b->N = 8 * nf + 4;
+  b->NW = (b->N + 1 + 3) & ~3;
+  b->T = b->NW / 4;
+  b->ntiles = b->T * (b->T + 1) / 2;
+  b->have_adj = b->have_state = b->have_tentative = b->have_committed = false;
+  b->npts = b->nres = b->nchunks = 0;
+  return DMV_OK;
+}
+
+int dmv_ba_set_points(dmv_ba* b, int npts, const int32_t* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
+                      const float* color8, const float* weights8, const float* priorF) {
+  if (!b || !host || !u || !v || !idepth || !color8 || !weights8) return set_error(DMV_ERR_INVALID, "null argument");
+  if (b->nf < 2) return set_error(DMV_ERR_STATE, "dmv_ba_set_window first");
+  if (npts < 1 || npts > b->cfg.max_points) return set_error(DMV_ERR_INVALID, "npts %d exceeds capacity %d", npts, b->cfg.max_points);
+  for (int i = 0; i < npts; i++) {
+    if (host[i] < 0 || host[i] >= b->nf) return set_error(DMV_ERR_INVALID, "point %d: host %d out of range", i, host[i]);
+    if (i > 0 && host[i] < host[i - 1]) return set_error(DMV_ERR_INVALID, "points must be ordered by host frame (EnergyFunctional::allPoints order)");
+  }
+  CK(cudaSetDevice(b->device));
+  b->npts = npts;
+  b->host_of_point.assign(host, host + npts);
+  b->chunks.clear();
+  for (int s = 0; s < npts;) {
+    int e = s;
+    while (e < npts && host[e] == host[s] && e - s < b->P) e++;
+    BAChunk c; c.start = s; c.count = e - s; c.host = host[s]; c.pad = 0;
+    b->chunks.push_back(c);
+    s = e;
+  }
+  b->nchunks = (int)b->chunks.size();
+  if (b->nchunks > b->max_chunks) return set_error(DMV_ERR_INVALID, "too many chunks");
+  float* s = b->h_scratch;
+  CK(cudaMemcpyAsync(b->d_chunks, b->chunks.data(), sizeof(BAChunk) * b->nchunks, cudaMemcpyHostToDevice, b->stream));
+  for (int i = 0; i < npts; i++) { s[2 * i] = u[i]; s[2 * i + 1] = v[i]; }
+  CK(cudaMemcpyAsync(b->d_uv, s, sizeof(float2) * npts, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  CK(cudaMemcpy(b->d_idepth, idepth, sizeof(float) * npts, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b->d_idepth_backup, idepth, sizeof(float) * npts, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b->d_idepth_zero, idepth_zero ? idepth_zero : idepth, sizeof(float) * npts, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b->d_color, color8, sizeof(float) * 8 * npts, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b->d_weights, weights8, sizeof(float) * 8 * npts, cudaMemcpyHostToDevice));
+  if (priorF) CK(cudaMemcpy(b->d_priorF, priorF, sizeof(float) * npts, cudaMemcpyHostToDevice));
+  else CK(cudaMemset(b->d_priorF, 0, sizeof(float) * npts));
+  b->nres = 0;
+  b->have_tentative = b->have_committed = false;
+  return DMV_OK;
+}
+
+int dmv_ba_set_residuals(dmv_ba* b, int nres, const int32_t* point, const int32_t* target, const int32_t* state_state, const float* state_energy) {
+  if (!b || !point || !target || nres < 0) return set_error(DMV_ERR_INVALID, "null argument");
+  if (b->npts < 1) return set_error(DMV_ERR_STATE, "dmv_ba_set_points first");
+  CK(cudaSetDevice(b->device));
+  const size_t ns = (size_t)MAXF * b->mp;
+  b->h_st_in.assign(ns, (uint8_t)RES_NONE);
+  b->h_en_in.assign(ns, 0.f);
+  b->res_slot.resize(nres);
+  for (int i = 0; i < nres; i++) {
+    const int p = point[i], t = target[i];
+    if (p < 0 || p >= b->npts || t < 0 || t >= b->nf) return set_error(DMV_ERR_INVALID, "residual %d out of range", i);
+    if (t == b->host_of_point[p]) return set_error(DMV_ERR_INVALID, "residual %d targets its own host frame", i);
+    const size_t slot = (size_t)t * b->mp + p;
+    if (b->h_st_in[slot] != RES_NONE) return set_error(DMV_ERR_INVALID, "duplicate residual (point %d, target %d)", p, t);
+    const int st = state_state ? state_state[i] : RES_IN;
+    if (st < 0 || st > 2) return set_error(DMV_ERR_INVALID, "residual %d: bad state %d", i, st);
+    b->h_st_in[slot] = (uint8_t)st;
+    b->h_en_in[slot] = state_energy ? state_energy[i] : 0.f;
+    b->res_slot[i] = (int)slot;
+  }
+  b->nres = nres;
+  CK(cudaMemcpy(b->d_st_in, b->h_st_in.data(), ns, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b->d_en_in, b->h_en_in.data(), ns * sizeof(float), cudaMemcpyHostToDevice));
+  for (int k = 0; k < 2; k++) CK(cudaMemset(b->d_st_new[k], 0xff, ns));
+  b->have_tentative = b->have_committed = false;
+  return DMV_OK;
+}
+
+int dmv_ba_set_adjoints(dmv_ba* b, const double* adHost, const double* adTarget) {
+  if (!b || !adHost || !adTarget) return set_error(DMV_ERR_INVALID, "null argument");
+  if (b->nf < 2) return set_error(DMV_ERR_STATE, "dmv_ba_set_window first");
+  CK(cudaSetDevice(b->device));
+  const int nf = b->nf;
+  BAAdj* A = b->h_adj;
+  std::memset(A, 0, sizeof(BAAdj));
+  for (int h = 0; h < nf; h++)
+    for (int t = 0; t < nf; t++) {
+      const double* ah = adHost + (size_t)(h + t * nf) * 64;
+      const double* at = adTarget + (size_t)(h + t * nf) * 64;
+      const int d = h * nf + t;
+      for (int k = 0; k < 64; k++) { A->adHost[d][k] = ah[k]; A->adHostF[d][k] = (float)ah[k]; }
+      for (int k = 0; k < 8; k++) {
+        for (int c = 0; c < 8; c++)
+          if (c != k && at[k * 8 + c] != 0.0) return set_error(DMV_ERR_INVALID, "adTarget[%d,%d] is not diagonal (EnergyFunctional.cpp:L66-84 makes it diagonal)", h, t);
+        A->adTdiag[d][k] = at[k * 8 + k];
+        A->adTdiagF[d][k] = (float)at[k * 8 + k];
+      }
+    }
+  CK(cudaMemcpyAsync(b->d_adj, A, sizeof(BAAdj), cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  b->have_adj = true;
+  return DMV_OK;
+}
+
+static int stage_state(dmv_ba* b, const dmv_ba_state* st) {
+  if (!st->precalc || !st->frameEnergyTH) return set_error(DMV_ERR_INVALID, "precalc / frameEnergyTH required");
+  BAIter& it = b->h_up->it;
+  const int nf = b->nf;
+  std::memcpy(it.calib, st->calib, sizeof(it.calib));
+  for (int f = 0; f < nf; f++) it.TH[f] = st->frameEnergyTH[f];
+  std::memcpy(it.precalc, st->precalc, sizeof(float) * 32 * nf * nf);
+  if (st->idepth) CK(cudaMemcpyAsync(b->d_idepth, st->idepth, sizeof(float) * b->npts, cudaMemcpyHostToDevice, b->stream));
+  if (st->idepth_zero) CK(cudaMemcpyAsync(b->d_idepth_zero, st->idepth_zero, sizeof(float) * b->npts, cudaMemcpyHostToDevice, b->stream));
+  b->have_state = true;
+  return DMV_OK;
+}
+
+int dmv_ba_set_state(dmv_ba* b, const dmv_ba_state* st) {
+  if (!b || !st) return set_error(DMV_ERR_INVALID, "null argument");
+  if (b->npts < 1) return set_error(DMV_ERR_STATE, "dmv_ba_set_points first");
+  CK(cudaSetDevice(b->device));
+  int rc = stage_state(b, st);
+  if (rc != DMV_OK) return rc;
+  // pageable idepth sources: make the async copies complete before returning
+  CK(cudaStreamSynchronize(b->stream));
+  return DMV_OK;
+}
+
+static int enqueue_linearize(dmv_ba* b, bool with_resub) {
+  fill_descriptor(b);
+  CK(cudaMemcpyAsync(b->d_up, b->h_up, sizeof(HostUpload), cudaMemcpyHostToDevice, b->stream));
+  const BAWinDev* dw = &b->d_up->win;
+  CK(cudaEventRecord(b->ev[0], b->stream));
+  if (with_resub) { launch_resub_kernel(dw, 1, b->npts, 1, b->stream); b->launches += 2; }
+  launch_point_kernel(dw, 1, b->nchunks, b->P, b->nf, b->stream);
+  CK(cudaEventRecord(b->ev[1], b->stream));
+  launch_reduce_kernel(dw, 1, b->nf, b->ntiles, b->stream);
+  launch_stitch_kernel(dw, 1, b->N, b->stream);
+  b->launches += 3;
+  CK(cudaEventRecord(b->ev[2], b->stream));
+  CK(cudaGetLastError());
+  if (b->nccl_comm) {
+    int rc = dmv::nccl_allreduce_double(b->nccl_comm, b->d_result[b->tent], result_doubles(b->N), b->stream);
+    if (rc != DMV_OK) return rc;
+  }
+  CK(cudaMemcpyAsync(b->h_result[b->tent], b->d_result[b->tent], sizeof(double) * result_doubles(b->N), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaEventRecord(b->ev[3], b->stream));
+  return DMV_OK;
+}
+
+static int finish_linearize(dmv_ba* b, dmv_ba_lin_result* out, double sums[3]) {
+  CK(cudaStreamSynchronize(b->stream));
+  const double* tail = b->h_result[b->tent] + 2 * (b->N * b->N + b->N);
+  if (out) { out->energy = tail[0]; out->n_in = (int)tail[1]; out->n_oob = (int)tail[2]; out->n_outlier = (int)tail[3]; }
+  if (sums) { sums[0] = tail[4]; sums[1] = tail[5]; sums[2] = tail[6]; }
+  cudaEventElapsedTime(&b->last_ms[0], b->ev[0], b->ev[3]);
+  cudaEventElapsedTime(&b->last_ms[1], b->ev[0], b->ev[1]);
+  cudaEventElapsedTime(&b->last_ms[2], b->ev[1], b->ev[2]);
+  cudaEventElapsedTime(&b->last_ms[3], b->ev[2], b->ev[3]);
+  b->have_tentative = true;
+  return DMV_OK;
+}
+
+static int check_ready(dmv_ba* b) {
+  if (!b) return set_error(DMV_ERR_INVALID, "null handle");
+  if (b->npts < 1 || b->nres < 0) return set_error(DMV_ERR_STATE, "points/residuals not set");
+  if (!b->have_adj) return set_error(DMV_ERR_STATE, "dmv_ba_set_adjoints first");
+  if (!b->have_state) return set_error(DMV_ERR_STATE, "dmv_ba_set_state first");
+  return DMV_OK;
+}
+
+int dmv_ba_linearize(dmv_ba* b, dmv_ba_lin_result* out) {
+  int rc = check_ready(b);
+  if (rc != DMV_OK) return rc;
+  CK(cudaSetDevice(b->device));
+  b->h_up->it.have_x = 0;
+  rc = enqueue_linearize(b, false);
+  if (rc != DMV_OK) return rc;
+  return finish_linearize(b, out, nullptr);
+}
+
+static void stage_x(dmv_ba* b, const double* x) {
+  // EnergyFunctional::resubstituteF_MT (EnergyFunctional.cpp:L272-283): xAd[h*nf+t] = x_h^T adHostF + x_t^T adTargetF in float
+  BAIter& it = b->h_up->it;
+  const int nf = b->nf;
+  const BAAdj* A = b->h_adj;
+  for (int i = 0; i < 4; i++) it.xc[i] = (float)x[i];
+  for (int h = 0; h < nf; h++)
+    for (int t = 0; t < nf; t++) {
+      const int d = h * nf + t;
+      for (int c = 0; c < 8; c++) {
+        float a = 0.f;
+        for (int k = 0; k < 8; k++) a += (float)x[4 + 8 * h + k] * A->adHostF[d][k * 8 + c];
+        const float bb = (float)x[4 + 8 * t + c] * A->adTdiagF[d][c];
+        it.xAd[d][c] = a + bb;
+      }
+    }
+  it.have_x = 1;
+}
+
+int dmv_ba_resubstitute(dmv_ba* b, const double* x, float* step_out, int apply, double sums[3]) {
+  int rc = check_ready(b);
+  if (rc != DMV_OK) return rc;
+  if (!x) return set_error(DMV_ERR_INVALID, "x is null");
+  if (!b->have_committed) return set_error(DMV_ERR_STATE, "no committed linearisation (linearize + apply_res first)");
+  CK(cudaSetDevice(b->device));
+  stage_x(b, x);
+  fill_descriptor(b);
+  CK(cudaMemcpyAsync(b->d_up, b->h_up, sizeof(HostUpload), cudaMemcpyHostToDevice, b->stream));
+  launch_resub_kernel(&b->d_up->win, 1, b->npts, apply, b->stream);
+  b->launches += 2;
+  CK(cudaGetLastError());
+  double* tail_d = b->d_result[b->tent] + 2 * (b->N * b->N + b->N);
+  double tail[8];
+  CK(cudaMemcpyAsync(tail, tail_d, sizeof(double) * 8, cudaMemcpyDeviceToHost, b->stream));
+  if (step_out) CK(cudaMemcpyAsync(step_out, b->d_step, sizeof(float) * b->npts, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  if (sums) { sums[0] = tail[4]; sums[1] = tail[5]; sums[2] = tail[6]; }
+  b->h_up->it.have_x = 0;
+  return DMV_OK;
+}
+
+int dmv_ba_gn_step(dmv_ba* b, const double* x, const dmv_ba_state* st, dmv_ba_lin_result* out, double sums[3]) {
+  if (!b || !st) return set_error(DMV_ERR_INVALID, "null argument");
+  if (b->npts < 1) return set_error(DMV_ERR_STATE, "points not set");
+  if (!b->have_adj) return set_error(DMV_ERR_STATE, "dmv_ba_set_adjoints first");
+  if (x && !b->have_committed) return set_error(DMV_ERR_STATE, "no committed linearisation to resubstitute");
+  CK(cudaSetDevice(b->device));
+  int rc = stage_state(b, st);
+  if (rc != DMV_OK) return rc;
+  if (x) stage_x(b, x); else b->h_up->it.have_x = 0;
+  rc = enqueue_linearize(b, x != nullptr);
+  if (rc != DMV_OK) return rc;
+  rc = finish_linearize(b, out, sums);
+  b->h_up->it.have_x = 0;
+  return rc;
+}
+
+int dmv_ba_backup_points(dmv_ba* b) {
+  if (!b || b->npts < 1) return set_error(DMV_ERR_STATE, "points not set");
+  CK(cudaSetDevice(b->device));
+  CK(cudaMemcpyAsync(b->d_idepth_backup, b->d_idepth, sizeof(float) * b->npts, cudaMemcpyDeviceToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return DMV_OK;
+}
+int dmv_ba_restore_points(dmv_ba* b) {
+  if (!b || b->npts < 1) return set_error(DMV_ERR_STATE, "points not set");
+  CK(cudaSetDevice(b->device));
+  CK(cudaMemcpyAsync(b->d_idepth, b->d_idepth_backup, sizeof(float) * b->npts, cudaMemcpyDeviceToDevice, b->stream));
+  CK(cudaMemcpyAsync(b->d_idepth_zero, b->d_idepth_backup, sizeof(float) * b->npts, cudaMemcpyDeviceToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return DMV_OK;
+}
+int dmv_ba_get_idepth(dmv_ba* b, float* idepth, float* idepth_zero) {
+  if (!b || b->npts < 1) return set_error(DMV_ERR_STATE, "points not set");
+  CK(cudaSetDevice(b->device));
+  if (idepth) CK(cudaMemcpy(idepth, b->d_idepth, sizeof(float) * b->npts, cudaMemcpyDeviceToHost));
+  if (idepth_zero) CK(cudaMemcpy(idepth_zero, b->d_idepth_zero, sizeof(float) * b->npts, cudaMemcpyDeviceToHost));
+  return DMV_OK;
+}
+
+int dmv_ba_apply_res(dmv_ba* b) {
+  if (!b) return set_error(DMV_ERR_INVALID, "null handle");
+  if (!b->have_tentative) return set_error(DMV_ERR_STATE, "no tentative linearisation to commit");
+  b->tent = 1 - b->tent;
+  b->have_committed = true;
+  b->have_tentative = false;
+  return DMV_OK;
+}
+
+int dmv_ba_accumulate(dmv_ba* b, double* H_A, double* b_A, double* H_sc, double* b_sc, int* resInA) {
+  if (!b) return set_error(DMV_ERR_INVALID, "null handle");
+  if (!b->have_committed) return set_error(DMV_ERR_STATE, "no committed linearisation (linearize + apply_res first)");
+  const int N = b->N;
+  const double* r = b->h_result[1 - b->tent];
+  if (H_A) std::memcpy(H_A, r, sizeof(double) * N * N);
+  if (b_A) std::memcpy(b_A, r + (size_t)N * N, sizeof(double) * N);
+  if (H_sc) std::memcpy(H_sc, r + (size_t)N * N + N, sizeof(double) * N * N);
+  if (b_sc) std::memcpy(b_sc, r + 2 * (size_t)N * N + N, sizeof(double) * N);
+  if (resInA) *resInA = (int)r[2 * ((size_t)N * N + N) + 1];
+  return DMV_OK;
+}
+
+static int fetch_f(dmv_ba* b, const float* dsrc, size_t n) {
+  if (n > b->scratch_floats) return set_error(DMV_ERR_INVALID, "scratch too small");
+  CK(cudaMemcpyAsync(b->h_scratch, dsrc, n * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return DMV_OK;
+}
+
+int dmv_ba_get_residual_outputs(dmv_ba* b, int32_t* newState, float* newEnergy, float* newEnergyWithOutlier, float* cpt3, float* JpJdF8) {
+  if (!b) return set_error(DMV_ERR_INVALID, "null handle");
+  if (!b->have_tentative && !b->have_committed) return set_error(DMV_ERR_STATE, "linearize first");
+  CK(cudaSetDevice(b->device));
+  const int k = b->have_tentative ? b->tent : 1 - b->tent;  // most recent linearisation
+  const size_t ns = (size_t)MAXF * b->mp;
+  int rc;
+  if (newState) {
+    std::vector<uint8_t> tmp(ns);
+    CK(cudaMemcpy(tmp.data(), b->d_st_new[k], ns, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < b->nres; i++) newState[i] = tmp[b->res_slot[i]];
+  }
+  if (newEnergy) {
+    if ((rc = fetch_f(b, b->d_en_new[k], ns)) != DMV_OK) return rc;
+    for (int i = 0; i < b->nres; i++) newEnergy[i] = b->h_scratch[b->res_slot[i]];
+  }
+  if (newEnergyWithOutlier) {
+    if ((rc = fetch_f(b, b->d_en_wo[k], ns)) != DMV_OK) return rc;
+    for (int i = 0; i < b->nres; i++) newEnergyWithOutlier[i] = b->h_scratch[b->res_slot[i]];
+  }
+  if (cpt3) {
+    if ((rc = fetch_f(b, b->d_cpt[k], 3 * ns)) != DMV_OK) return rc;
+    for (int i = 0; i < b->nres; i++)
+      for (int c = 0; c < 3; c++) cpt3[3 * i + c] = b->h_scratch[c * ns + b->res_slot[i]];
+  }
+  if (JpJdF8) {
+    if ((rc = fetch_f(b, b->d_jpjd[k], 8 * ns)) != DMV_OK) return rc;
+    for (int i = 0; i < b->nres; i++)
+      for (int c = 0; c < 8; c++) JpJdF8[8 * i + c] = b->h_scratch[(size_t)b->res_slot[i] * 8 + c];
+  }
+  return DMV_OK;
+}
+
+int dmv_ba_get_target_energies(dmv_ba* b, int target, float* out, int cap, int* n) {
+  if (!b || !out || !n || target < 0 || target >= b->nf) return set_error(DMV_ERR_INVALID, "bad argument");
+  if (!b->have_tentative && !b->have_committed) return set_error(DMV_ERR_STATE, "linearize first");
+  CK(cudaSetDevice(b->device));
+  const int k = b->have_tentative ? b->tent : 1 - b->tent;
+  int rc = fetch_f(b, b->d_en_wo[k] + (size_t)target * b->mp, b->npts);
+  if (rc != DMV_OK) return rc;
+  int c = 0;
+  for (int p = 0; p < b->npts && c < cap; p++)
+    if (b->h_st_in[(size_t)target * b->mp + p] != RES_NONE && b->h_scratch[p] >= 0.f) out[c++] = b->h_scratch[p];
+  *n = c;
+  return DMV_OK;
+}
+
+int dmv_ba_get_point_outputs(dmv_ba* b, float* Hdd, float* bd, float* Hcd4, float* HdiF, float* bdSumF) {
+  if (!b) return set_error(DMV_ERR_INVALID, "null handle");
+  if (!b->have_tentative && !b->have_committed) return set_error(DMV_ERR_STATE, "linearize first");
+  CK(cudaSetDevice(b->device));
+  const int k = b->have_tentative ? b->tent : 1 - b->tent;
+  int rc = fetch_f(b, b->d_pout[k], (size_t)8 * b->npts);
+  if (rc != DMV_OK) return rc;
+  for (int p = 0; p < b->npts; p++) {
+    const float* r = b->h_scratch + (size_t)8 * p;
+    if (Hdd) Hdd[p] = r[0];
+    if (bd) bd[p] = r[1];
+    if (Hcd4) { Hcd4[4 * p] = r[2]; Hcd4[4 * p + 1] = r[3]; Hcd4[4 * p + 2] = r[4]; Hcd4[4 * p + 3] = r[5]; }
+    if (HdiF) HdiF[p] = r[6];
+    if (bdSumF) bdSumF[p] = r[7];
+  }
+  return DMV_OK;
+}
+
+int dmv_ba_last_timing(dmv_ba* b, float ms[4]) {
+  if (!b || !ms) return set_error(DMV_ERR_INVALID, "null argument");
+  for (int i = 0; i < 4; i++) ms[i] = b->last_ms[i];
+  return DMV_OK;
+}
+
+int dmv_ba_kernel_launch_count(dmv_ba* b, long long* n) {
+  if (!b || !n) return set_error(DMV_ERR_INVALID, "null argument");
+  *n = b->launches;
+  return DMV_OK;
+}
+
+int dmv_ba_bench_device(dmv_ba* b, const double* x, int iters, int flush_l2, float* ms_per_iter, float* ms_point_kernel) {
+  int rc = check_ready(b);
+  if (rc != DMV_OK) return rc;
+  if (iters < 1 || iters > 4096) return set_error(DMV_ERR_INVALID, "iters out of range");
+  if (x && !b->have_committed) return set_error(DMV_ERR_STATE, "no committed linearisation to resubstitute");
+  CK(cudaSetDevice(b->device));
+  if (flush_l2 && !b->d_flush) {
+    b->flush_n = (size_t)256 * 1024 * 1024 / sizeof(float4);  // 256 MiB > 126 MB L2
+    CK(cudaMalloc(&b->d_flush, b->flush_n * sizeof(float4)));
+    CK(cudaMemset(b->d_flush, 0, b->flush_n * sizeof(float4)));
+  }
+  if (x) stage_x(b, x); else b->h_up->it.have_x = 0;
+  fill_descriptor(b);
+  CK(cudaMemcpyAsync(b->d_up, b->h_up, sizeof(HostUpload), cudaMemcpyHostToDevice, b->stream));
+  const BAWinDev* dw = &b->d_up->win;
+  std::vector<cudaEvent_t> e(3 * (size_t)iters);
+  for (auto& x : e) CK(cudaEventCreate(&x));
+  for (int i = 0; i < iters; i++) {
+    if (flush_l2) launch_l2_flush(b->d_flush, b->flush_n, b->stream);
+    CK(cudaEventRecord(e[3 * i], b->stream));
+    if (x) { launch_resub_kernel(dw, 1, b->npts, 1, b->stream); b->launches += 2; }
+    launch_point_kernel(dw, 1, b->nchunks, b->P, b->nf, b->stream);
+    CK(cudaEventRecord(e[3 * i + 1], b->stream));
+    launch_reduce_kernel(dw, 1, b->nf, b->ntiles, b->stream);
+    launch_stitch_kernel(dw, 1, b->N, b->stream);
+    if (b->nccl_comm) {
+      rc = dmv::nccl_allreduce_double(b->nccl_comm, b->d_result[b->tent], result_doubles(b->N), b->stream);
+      if (rc != DMV_OK) return rc;
+    }
+    CK(cudaEventRecord(e[3 * i + 2], b->stream));
+    b->launches += 3;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(b->stream));
+  double tot = 0, pk = 0;
+  for (int i = 0; i < iters; i++) {
+    float a = 0, c = 0;
+    cudaEventElapsedTime(&a, e[3 * i], e[3 * i + 2]);
+    cudaEventElapsedTime(&c, e[3 * i], e[3 * i + 1]);
+    tot += a; pk += c;
+  }
+  for (auto& x : e) cudaEventDestroy(x);
+  if (ms_per_iter) *ms_per_iter = (float)(tot / iters);
+  if (ms_point_kernel) *ms_point_kernel = (float)(pk / iters);
+  b->h_up->it.have_x = 0;
+  b->have_tentative = true;
+  return DMV_OK;
+}
+
+int dmv_nccl_unique_id(void* id128) { return dmv::nccl_unique_id(id128); }
+
+int dmv_ba_comm_init(dmv_ba* b, int nranks, int rank, const void* id) {
+  if (!b || !id || nranks < 1 || rank < 0 || rank >= nranks) return set_error(DMV_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(b->device));
+  if (nranks == 1) return DMV_OK;
+  int rc = dmv::nccl_init(&b->nccl_comm, nranks, rank, id);
+  if (rc != DMV_OK) return rc;
+  b->nranks = nranks; b->rank = rank;
+  return DMV_OK;
+}
+
+}  // extern "C"
+
+extern "C" int dmv_ba_io_bytes(dmv_ba* b, long long* h2d, long long* d2h) {
+  if (!b || !h2d || !d2h) return set_error(DMV_ERR_INVALID, "null argument");
+  *h2d = (long long)sizeof(HostUpload);                        // descriptor + per-iteration tables, one pinned copy
+  *d2h = (long long)sizeof(double) * result_doubles(b->N);     // H_A, b_A, H_sc, b_sc, energy + counters
+  return DMV_OK;
+}

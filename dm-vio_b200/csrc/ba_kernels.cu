@@ -1,0 +1,653 @@
+// sm_100a kernels of the bundle-adjustment hot path.
+//
+//   ba_point_kernel     one CTA = one chunk of P points of one host frame; warp t = target frame t.
+//                       phase A: 8 lanes per (point,target) residual = the 8 pattern pixels: project, 4-tap float4 gather
+//                                from the L2-resident target plane, Huber-weighted residual, 8-lane butterfly reductions,
+//                                register-resident rows of the pair's 13x13 block      (Residuals.cpp:L78-274 +
+//                                AccumulatedTopHessian.cpp:L39-159 fused; the 304-byte RawResidualJacobian never exists)
+//                       phase B: per-point Hdd/bd/Hcd, HdiF, and the point's Schur vector in ABSOLUTE frame coordinates
+//                                w_p = [Hcd | sum_t adHost v_t | adTarget v_t ... | bdSum]
+//                       phase C: weighted Gram  sum_p HdiF w_p w_p^T  in 4x4 register tiles  (replaces the nf^3 accD blocks of
+//                                AccumulatedSCHessian.cpp:L34-157)
+//   ba_reduce_kernel    deterministic fp64 reduction of the per-chunk partials
+//   ba_stitch_kernel    adjoint products to the dense (8nf+4)^2 system in fp64 (AccumulatedTopHessian.cpp:L241-303)
+//   ba_resub_kernel     EnergyFunctional::resubstituteFPt + point part of doStepFromBackup
+#include "ba_device.cuh"
+#include <math.h>
+
+namespace dmv {
+
+__device__ __constant__ int c_pattern[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {0, 2}};
+
+__device__ __forceinline__ float pick8(const float* v, int j) {
+  float a = (j & 1) ? v[1] : v[0];
+  float b = (j & 1) ? v[3] : v[2];
+  float c = (j & 1) ? v[5] : v[4];
+  float d = (j & 1) ? v[7] : v[6];
+  float e = (j & 2) ? b : a;
+  float f = (j & 2) ? d : c;
+  return (j & 4) ? f : e;
+}
+
+__device__ __forceinline__ float group_sum8(float v) {  // all-reduce inside aligned groups of 8 lanes
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+__device__ __forceinline__ float cross_group_sum(float v) {  // sum over the 4 groups of a warp
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+template <int P>
+__global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __restrict__ wins) {
+  const BAWinDev& W = wins[blockIdx.y];
+  if ((int)blockIdx.x >= W.nchunks) return;
+  const int nf = W.nf;
+  const BAChunk ch = W.chunks[blockIdx.x];
+  const int h = ch.host;
+  const int tid = threadIdx.x;
+  const int nthreads = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int mp = W.mp;
+
+  __shared__ __align__(16) float s_rec[P][MAXF][REC];
+  __shared__ __align__(16) float s_W[P][8 * MAXF + 8];
+  __shared__ float s_hdi[P];
+  __shared__ __align__(16) float s_adH[MAXF][64];
+  __shared__ float s_adT[MAXF][8];
+
+  const BAIter* __restrict__ it = W.it;
+  for (int i = tid; i < nf * 64; i += nthreads) s_adH[i >> 6][i & 63] = W.adj->adHostF[h * nf + (i >> 6)][i & 63];
+  for (int i = tid; i < nf * 8; i += nthreads) s_adT[i >> 3][i & 7] = W.adj->adTdiagF[h * nf + (i >> 3)][i & 7];
+  for (int i = tid; i < P * MAXF * REC; i += nthreads) (&s_rec[0][0][0])[i] = 0.f;
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase A
+  const int t = warp;  // target frame of this warp
+  if (t < nf && t != h) {
+    const int g = lane >> 3, j = lane & 7;
+    const float* __restrict__ pc = it->precalc[h * nf + t];
+    const float fx = it->calib[0], fy = it->calib[1], cx = it->calib[2], cy = it->calib[3];
+    const float fxi = it->calib[4], fyi = it->calib[5], cxi = it->calib[6], cyi = it->calib[7];
+    (void)cxi; (void)cyi;
+    const float TH = fmaxf(it->TH[h], it->TH[t]);
+    const float wM3 = (float)(W.w - 3), hM3 = (float)(W.h - 3);
+    const float4* __restrict__ img = W.img[t];
+    const int iw = W.w;
+    const float huber = W.huberTH, oth = W.outlierTHSum;
+    const float KRKi0 = pc[0], KRKi1 = pc[1], KRKi2 = pc[2], KRKi3 = pc[3], KRKi4 = pc[4], KRKi5 = pc[5], KRKi6 = pc[6], KRKi7 = pc[7],
+                KRKi8 = pc[8];
+    const float Kt0 = pc[9], Kt1 = pc[10], Kt2 = pc[11];
+    const float affa = pc[24], affb = pc[25], b0 = pc[26];
+    const int pdx = c_pattern[j][0], pdy = c_pattern[j][1];
+
+    float acc1[TOP_COLS], acc2[TOP_COLS], br[6];
+#pragma unroll
+    for (int c = 0; c < TOP_COLS; c++) { acc1[c] = 0.f; acc2[c] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < 6; c++) br[c] = 0.f;
+    float e_sum = 0.f;
+    int n_in = 0, n_oob = 0, n_outl = 0;
+
+    for (int base = 0; base < ch.count; base += 4) {
+      const int pl = base + g;
+      const bool valid = pl < ch.count;
+      const int p = ch.start + (valid ? pl : ch.count - 1);
+      const int slot = t * mp + p;
+      const int st = valid ? (int)W.st_in[slot] : RES_NONE;
+      bool live = (st != RES_NONE) && (st != RES_OOB);
+
+      const float2 uv = W.uv[p];
+      const float idepth = W.idepth[p];
+      const float idz = W.idepth_zero[p];
+      const float col = W.color[p * 8 + j];
+      const float wgt = W.weights[p * 8 + j];
+
+      // ---- centre pixel at the FEJ point (ResidualProjections.h:L62-87, Residuals.cpp:L108-157)
+      const float Kl0 = (uv.x - cx) * fxi, Kl1 = (uv.y - cy) * fyi;
+      const float q0 = pc[12] * Kl0 + pc[13] * Kl1 + pc[14] + pc[21] * idz;
+      const float q1 = pc[15] * Kl0 + pc[16] * Kl1 + pc[17] + pc[22] * idz;
+      const float q2 = pc[18] * Kl0 + pc[19] * Kl1 + pc[20] + pc[23] * idz;
+      const float drescale = 1.0f / q2;
+      const float new_idepth = idz * drescale;
+      const float cu = q0 * drescale, cv = q1 * drescale;
+      const float cKu = cu * fx + cx, cKv = cv * fy + cy;
+      const bool centre_ok = (drescale > 0.f) && cKu > 1.1f && cKv > 1.1f && cKu < wM3 && cKv < hM3;
+      live = live && centre_ok;
+
+      // ---- own pattern pixel at the current state (ResidualProjections.h:L47-57)
+      const float pu = uv.x + (float)pdx, pv = uv.y + (float)pdy;
+      const float r0 = KRKi0 * pu + KRKi1 * pv + KRKi2 + Kt0 * idepth;
+      const float r1 = KRKi3 * pu + KRKi4 * pv + KRKi5 + Kt1 * idepth;
+      const float r2 = KRKi6 * pu + KRKi7 * pv + KRKi8 + Kt2 * idepth;
+      const float Ku = r0 / r2, Kv = r1 / r2;
+      const bool px_ok = Ku > 1.1f && Kv > 1.1f && Ku < wM3 && Kv < hM3;
+      unsigned bal = __ballot_sync(0xffffffffu, px_ok);
+      live = live && (((bal >> (g * 8)) & 0xffu) == 0xffu);
+
+      float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+      if (live) {  // getInterpolatedElement33 (util/globalFuncs.h:L103-118)
+        const int ix = (int)Ku, iy = (int)Kv;
+        const float dx = Ku - ix, dy = Kv - iy, dxdy = dx * dy;
+        const float4* bp = img + (size_t)iy * iw + ix;
+        const float4 tl = __ldg(bp), tr = __ldg(bp + 1), bl = __ldg(bp + iw), brr = __ldg(bp + iw + 1);
+        const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+        h0 = w11 * brr.x + w10 * bl.x + w01 * tr.x + w00 * tl.x;
+        h1 = w11 * brr.y + w10 * bl.y + w01 * tr.y + w00 * tl.y;
+        h2 = w11 * brr.z + w10 * bl.z + w01 * tr.z + w00 * tl.z;
+      }
+      bal = __ballot_sync(0xffffffffu, isfinite(h0));
+      live = live && (((bal >> (g * 8)) & 0xffu) == 0xffu);
+
+      // ---- photometric residual, gradient weight, Huber (Residuals.cpp:L194-258)
+      const float residual = h0 - (affa * col + affb);
+      const float drdA = col - b0;
+      float w = sqrtf(oth / (oth + (h1 * h1 + h2 * h2)));
+      w = 0.5f * (w + wgt);
+      const float ar = fabsf(residual);
+      float hw = ar < huber ? 1.f : huber / ar;
+      float e_px = w * w * hw * residual * residual * (2.f - hw);
+      if (hw < 1.f) hw = sqrtf(hw);
+      hw = hw * w;
+      if (!live) { hw = 0.f; e_px = 0.f; }
+      const float gx = h1 * hw, gy = h2 * hw;
+      const float resF = residual * hw;
+      const float ja = drdA * hw, jb = hw;
+      const float jaF = W.zeroA ? 0.f : ja, jbF = W.zeroB ? 0.f : jb;
+
+      const float JI00 = group_sum8(gx * gx), JI11 = group_sum8(gy * gy), JI10 = group_sum8(gx * gy);
+      const float JabJI00 = group_sum8(ja * gx), JabJI01 = group_sum8(ja * gy), JabJI10 = group_sum8(jb * gx), JabJI11 = group_sum8(jb * gy);
+      const float Jab00 = group_sum8(ja * ja), Jab01 = group_sum8(ja * jb), Jab11 = group_sum8(jb * jb);
+      const float JIr0 = group_sum8(resF * gx), JIr1 = group_sum8(resF * gy);
+      const float Jabr0 = group_sum8(resF * jaF), Jabr1 = group_sum8(resF * jbF);
+      const float rr = group_sum8(resF * resF);
+      const float energy = group_sum8(e_px);
+      // the reference sums hw*hw*(hitColor[1]^2+hitColor[2]^2) with hitColor already multiplied by hw (Residuals.cpp:L217-244)
+      const float wJI2_ref = group_sum8(hw * hw * (gx * gx + gy * gy));
+
+      // ---- classification (Residuals.cpp:L260-273) and per-residual outputs
+      int newState;
+      float newEnergy, ret;
+      if (st == RES_NONE) {
+        newState = RES_NONE; newEnergy = 0.f; ret = 0.f;
+      } else if (!live) {
+        newState = RES_OOB; newEnergy = W.en_in[slot]; ret = newEnergy;  // OOB exits return the old state_energy
+      } else if (energy > TH || wJI2_ref < 2.f) {
+        newState = RES_OUTLIER; newEnergy = TH; ret = TH;
+      } else {
+        newState = RES_IN; newEnergy = energy; ret = energy;
+      }
+      const bool in = (newState == RES_IN);
+
+      // geometric Jacobians of the centre pixel (Residuals.cpp:L113-156): x = d(Ku)/d[C4|xi6], y = d(Kv)/d[C4|xi6]
+      float x[10], y[10];
+      {
+        const float R00 = pc[12], R01 = pc[13], R10 = pc[15], R11 = pc[16], R20 = pc[18], R21 = pc[19];
+        float dCx2 = drescale * (R20 * cu - R00);
+        float dCx3 = fx * drescale * (R21 * cu - R01) * fyi;
+        float dCx0 = Kl0 * dCx2;
+        float dCx1 = Kl1 * dCx3;
+        float dCy2 = fy * drescale * (R20 * cv - R10) * fxi;
+        float dCy3 = drescale * (R21 * cv - R11);
+        float dCy0 = Kl0 * dCy2;
+        float dCy1 = Kl1 * dCy3;
+        x[0] = (dCx0 + cu) * 50.0f; x[1] = dCx1 * 50.0f; x[2] = (dCx2 + 1.f) * 50.0f; x[3] = dCx3 * 50.0f;
+        y[0] = dCy0 * 50.0f; y[1] = (dCy1 + cv) * 50.0f; y[2] = dCy2 * 50.0f; y[3] = (dCy3 + 1.f) * 50.0f;
+        x[4] = new_idepth * fx; x[5] = 0.f; x[6] = -new_idepth * cu * fx; x[7] = -cu * cv * fx; x[8] = (1.f + cu * cu) * fx; x[9] = -cv * fx;
+        y[4] = 0.f; y[5] = new_idepth * fy; y[6] = -new_idepth * cv * fy; y[7] = -(1.f + cv * cv) * fy; y[8] = cu * cv * fy; y[9] = cu * fy;
+      }
+      const float ddx = drescale * (pc[21] - pc[23] * cu) * fx;  // Jpdd (SCALE_IDEPTH = 1)
+      const float ddy = drescale * (pc[22] - pc[23] * cv) * fy;
+
+      if (st != RES_NONE) {
+        e_sum += (j == 0) ? ret : 0.f;
+        if (j == 0) { n_in += in; n_oob += (newState == RES_OOB); n_outl += (newState == RES_OUTLIER); }
+      }
+      if (valid && j == 0) {
+        W.st_new[slot] = (uint8_t)newState;
+        W.en_new[slot] = newEnergy;
+        W.en_wo[slot] = (st == RES_NONE || !live) ? -1.f : energy;
+        const size_t plane = (size_t)MAXF * mp;
+        W.cpt[slot] = cKu; W.cpt[plane + slot] = cKv; W.cpt[2 * plane + slot] = new_idepth;
+      }
+
+      if (in) {
+        // EFResidual::takeDataF (EnergyFunctionalStructs.cpp:L39-49) and the per-point terms of addPoint (AccumulatedTopHessian.cpp:L131-135)
+        const float J0 = JI00 * ddx + JI10 * ddy, J1 = JI10 * ddx + JI11 * ddy;  // JIdx2 * Jpdd
+        if (j == 0) {
+          float* rec = s_rec[pl][t];
+          float4 v0, v1, v2, v3;
+          v0.x = x[4] * J0 + y[4] * J1; v0.y = x[5] * J0 + y[5] * J1; v0.z = x[6] * J0 + y[6] * J1; v0.w = x[7] * J0 + y[7] * J1;
+          v1.x = x[8] * J0 + y[8] * J1; v1.y = x[9] * J0 + y[9] * J1;
+          v1.z = JabJI00 * ddx + JabJI01 * ddy; v1.w = JabJI10 * ddx + JabJI11 * ddy;
+          v2.x = J0 * ddx + J1 * ddy;            // Hdd
+          v2.y = JIr0 * ddx + JIr1 * ddy;        // bd
+          v2.z = x[0] * J0 + y[0] * J1; v2.w = x[1] * J0 + y[1] * J1;  // Hcd[0..1]
+          v3.x = x[2] * J0 + y[2] * J1; v3.y = x[3] * J0 + y[3] * J1;  // Hcd[2..3]
+          v3.z = 1.f; v3.w = 0.f;                                      // active flag
+          reinterpret_cast<float4*>(rec)[0] = v0;
+          reinterpret_cast<float4*>(rec)[1] = v1;
+          reinterpret_cast<float4*>(rec)[2] = v2;
+          reinterpret_cast<float4*>(rec)[3] = v3;
+          float4* gj = reinterpret_cast<float4*>(W.jpjd + (size_t)slot * 8);
+          gj[0] = v0; gj[1] = v1;
+        }
+        // rows of the pair's 13x13 block: lane j owns row j, lanes (j&1) own rows 8/9 (AccumulatorApprox::update/updateTopRight)
+        const float xr1 = pick8(x, j), yr1 = pick8(y, j);
+        const float xr2 = (j & 1) ? x[9] : x[8], yr2 = (j & 1) ? y[9] : y[8];
+        const float al1 = JI00 * xr1 + JI10 * yr1, be1 = JI10 * xr1 + JI11 * yr1;
+        const float al2 = JI00 * xr2 + JI10 * yr2, be2 = JI10 * xr2 + JI11 * yr2;
+#pragma unroll
+        for (int c = 0; c < 10; c++) {
+          acc1[c] += al1 * x[c] + be1 * y[c];
+          acc2[c] += al2 * x[c] + be2 * y[c];
+        }
+        acc1[10] += xr1 * JabJI00 + yr1 * JabJI01;
+        acc1[11] += xr1 * JabJI10 + yr1 * JabJI11;
+        acc1[12] += xr1 * JIr0 + yr1 * JIr1;
+        acc2[10] += xr2 * JabJI00 + yr2 * JabJI01;
+        acc2[11] += xr2 * JabJI10 + yr2 * JabJI11;
+        acc2[12] += xr2 * JIr0 + yr2 * JIr1;
+        br[0] += Jab00; br[1] += Jab01; br[2] += Jabr0; br[3] += Jab11; br[4] += Jabr1; br[5] += rr;
+      }
+    }
+    // ---- cross-group reduction and per-(chunk,target) partial store
+    float* tp = W.top_part + ((size_t)blockIdx.x * MAXF + t) * TOP_PART;
+#pragma unroll
+    for (int c = 0; c < TOP_COLS; c++) {
+      const float a1 = cross_group_sum(acc1[c]);
+      const float a2 = cross_group_sum(acc2[c]);
+      if (lane < 8) tp[lane * TOP_COLS + c] = a1;
+      if (lane < 2) tp[(8 + lane) * TOP_COLS + c] = a2;
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      const float b = cross_group_sum(br[c]);
+      if (lane == 0) tp[TOP_ROWS * TOP_COLS + c] = b;
+    }
+    float es = e_sum, fin = (float)n_in, foob = (float)n_oob, fout = (float)n_outl;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+      es += __shfl_xor_sync(0xffffffffu, es, m);
+      fin += __shfl_xor_sync(0xffffffffu, fin, m);
+      foob += __shfl_xor_sync(0xffffffffu, foob, m);
+      fout += __shfl_xor_sync(0xffffffffu, fout, m);
+    }
+    if (lane == 0) {
+      float4 m4; m4.x = es; m4.y = fin; m4.z = foob; m4.w = fout;
+      reinterpret_cast<float4*>(W.misc_part)[(size_t)blockIdx.x * MAXF + t] = m4;
+    }
+  } else {
+    // the host's own warp: zero its partial slot so the reduction needs no masks
+    if (t < MAXF) {
+      float* tp = W.top_part + ((size_t)blockIdx.x * MAXF + t) * TOP_PART;
+      for (int i = lane; i < TOP_PART; i += 32) tp[i] = 0.f;
+      if (lane == 0) reinterpret_cast<float4*>(W.misc_part)[(size_t)blockIdx.x * MAXF + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase B
+  const int N = W.N, NW = W.NW;
+  for (int i = tid; i < P * (8 * MAXF + 8); i += nthreads) (&s_W[0][0])[i] = 0.f;
+  __syncthreads();
+  for (int pl = tid; pl < ch.count; pl += nthreads) {  // AccumulatedSCHessian.cpp:L36-58
+    const int p = ch.start + pl;
+    float Hdd = 0.f, bd = 0.f, Hcd0 = 0.f, Hcd1 = 0.f, Hcd2 = 0.f, Hcd3 = 0.f;
+    int ngood = 0;
+    for (int tt = 0; tt < nf; tt++) {
+      const float* rec = s_rec[pl][tt];
+      if (rec[14] != 0.f) {
+        ngood++;
+        Hdd += rec[8]; bd += rec[9]; Hcd0 += rec[10]; Hcd1 += rec[11]; Hcd2 += rec[12]; Hcd3 += rec[13];
+      }
+    }
+    float HdiF = 0.f, bdSum = 0.f;
+    if (ngood > 0) {
+      const float prior = W.priorF[p];
+      float H = Hdd + prior;
+      if (H < 1e-10f) H = 1e-10f;
+      HdiF = 1.0f / H;
+      bdSum = bd + prior * (W.idepth[p] - W.idepth_zero[p]);
+      s_W[pl][0] = Hcd0; s_W[pl][1] = Hcd1; s_W[pl][2] = Hcd2; s_W[pl][3] = Hcd3;
+      s_W[pl][N] = bdSum;
+    }
+    s_hdi[pl] = HdiF;
+    float4* po = reinterpret_cast<float4*>(W.pout + (size_t)p * 8);
+    po[0] = make_float4(Hdd, bd, Hcd0, Hcd1);
+    po[1] = make_float4(Hcd2, Hcd3, HdiF, bdSum);
+  }
+  for (int idx = tid; idx < ch.count * nf * 8; idx += nthreads) {
+    const int k = idx & 7;
+    const int f = (idx >> 3) % nf;
+    const int pl = (idx >> 3) / nf;
+    float val = 0.f;
+    if (f == h) {
+      for (int tt = 0; tt < nf; tt++) {
+        const float* rec = s_rec[pl][tt];
+        if (rec[14] != 0.f) {
+          const float* A = &s_adH[tt][k * 8];
+#pragma unroll
+          for (int c = 0; c < 8; c++) val += A[c] * rec[c];
+        }
+      }
+    } else {
+      const float* rec = s_rec[pl][f];
+      if (rec[14] != 0.f) val = s_adT[f][k] * rec[k];
+    }
+    s_W[pl][4 + 8 * f + k] = val;
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase C
+  const int T = W.T;
+  float* scp = W.sc_part + (size_t)blockIdx.x * W.ntiles * 16;
+  for (int tile = tid; tile < W.ntiles; tile += nthreads) {
+    int ti = 0, rem = tile;
+    while (rem >= T - ti) { rem -= T - ti; ti++; }
+    const int tj = ti + rem;
+    float a[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) a[r][c] = 0.f;
+    for (int pl = 0; pl < ch.count; pl++) {
+      const float s = s_hdi[pl];
+      const float4 wi = *reinterpret_cast<const float4*>(&s_W[pl][4 * ti]);
+      const float4 wj = *reinterpret_cast<const float4*>(&s_W[pl][4 * tj]);
+      const float si[4] = {s * wi.x, s * wi.y, s * wi.z, s * wi.w};
+      const float vj[4] = {wj.x, wj.y, wj.z, wj.w};
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) a[r][c] += si[r] * vj[c];
+    }
+    float4* o = reinterpret_cast<float4*>(scp + (size_t)tile * 16);
+#pragma unroll
+    for (int r = 0; r < 4; r++) o[r] = make_float4(a[r][0], a[r][1], a[r][2], a[r][3]);
+  }
+  (void)NW;
+}
+
+template __global__ void ba_point_kernel<8>(const BAWinDev*);
+template __global__ void ba_point_kernel<16>(const BAWinDev*);
+template __global__ void ba_point_kernel<32>(const BAWinDev*);
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp64 reduction of the per-chunk partials.  entry space: [nf*nf*TOP_PART | ntiles*16 | 4 misc]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ba_reduce_kernel(const BAWinDev* __restrict__ wins) {
+  const BAWinDev& W = wins[blockIdx.y];
+  const int nf = W.nf;
+  const int nTop = nf * nf * TOP_PART, nSc = W.ntiles * 16;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nTop) {
+    const int pair = e / TOP_PART, k = e - pair * TOP_PART;
+    const int h = pair / nf, t = pair - h * nf;
+    double s = 0.0;
+    const int c0 = W.chunk_beg[h], c1 = W.chunk_beg[h + 1];
+    const float* p = W.top_part + ((size_t)c0 * MAXF + t) * TOP_PART + k;
+    for (int c = c0; c < c1; c++, p += (size_t)MAXF * TOP_PART) s += (double)*p;
+    W.top_sum[e] = s;
+  } else if (e < nTop + nSc) {
+    const int k = e - nTop;
+    double s = 0.0;
+    const float* p = W.sc_part + k;
+    for (int c = 0; c < W.nchunks; c++, p += (size_t)nSc) s += (double)*p;
+    W.sc_sum[k] = s;
+  } else if (e < nTop + nSc + 4) {
+    const int k = e - nTop - nSc;
+    double s = 0.0;
+    for (int c = 0; c < W.nchunks; c++)
+      for (int t = 0; t < nf; t++) s += (double)W.misc_part[((size_t)c * MAXF + t) * 4 + k];
+    W.result[2 * (W.N * W.N + W.N) + k] = s;
+  }
+}
+
+// 13x13 pair block from the 136-float layout (rows 0..9 full, then the 6 bottom-right entries)
+__device__ __forceinline__ double h13(const double* S, int r, int c) {
+  if (r > c) { int tmp = r; r = c; c = tmp; }
+  if (r < TOP_ROWS) return S[r * TOP_COLS + c];
+  const int rr = r - 10, cc = c - 10;  // (0,0)->0 (0,1)->1 (0,2)->2 (1,1)->3 (1,2)->4 (2,2)->5
+  return S[TOP_ROWS * TOP_COLS + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5))];
+}
+
+// One thread per entry of [H_top | b_top] and [H_sc | b_sc]  (AccumulatedTopHessian.cpp:L241-303 in gather form).
+__global__ void __launch_bounds__(256) ba_stitch_kernel(const BAWinDev* __restrict__ wins) {
+  const BAWinDev& W = wins[blockIdx.y];
+  const int nf = W.nf, N = W.N;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * (N + 1)) return;
+  const int I = e / (N + 1), J = e - I * (N + 1);  // J == N : right-hand side b
+  const BAAdj* __restrict__ A = W.adj;
+  const double* __restrict__ TS = W.top_sum;
+  double* __restrict__ R = W.result;
+
+  // ---- Schur part straight from the Gram tiles
+  {
+    int r = I, c = J;
+    if (c < N && r > c) { int tmp = r; r = c; c = tmp; }
+    const int ti = r >> 2, tj = c >> 2;
+    const int tile = ti * W.T - (ti * (ti - 1)) / 2 + (tj - ti);
+    const double v = W.sc_sum[(size_t)tile * 16 + (r & 3) * 4 + (c & 3)];
+    if (J < N) R[(size_t)(N * N + N) + (size_t)I * N + J] = v;
+    else R[(size_t)(N * N + N) + (size_t)N * N + I] = v;
+  }
+
+  // ---- top part
+  const int fa = (I >= 4) ? (I - 4) >> 3 : -1, ia = (I >= 4) ? (I - 4) & 7 : I;
+  double v = 0.0;
+  if (J == N) {  // b_top
+    if (fa < 0) {
+      for (int pr = 0; pr < nf * nf; pr++) v += h13(TS + (size_t)pr * TOP_PART, ia, 12);
+    } else {
+      for (int t = 0; t < nf; t++) {
+        if (t == fa) continue;
+        const double* S = TS + (size_t)(fa * nf + t) * TOP_PART;       // pair (host fa, target t)
+        const double* Ah = A->adHost[fa * nf + t];
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += Ah[ia * 8 + k] * h13(S, 4 + k, 12);
+        v += s;
+        const double* S2 = TS + (size_t)(t * nf + fa) * TOP_PART;      // pair (host t, target fa)
+        v += A->adTdiag[t * nf + fa][ia] * h13(S2, 4 + ia, 12);
+      }
+    }
+    R[(size_t)N * N + I] = v;
+    return;
+  }
+  const int fb = (J >= 4) ? (J - 4) >> 3 : -1, jb = (J >= 4) ? (J - 4) & 7 : J;
+  if (fa < 0 && fb < 0) {  // calib-calib
+    for (int pr = 0; pr < nf * nf; pr++) v += h13(TS + (size_t)pr * TOP_PART, ia, jb);
+  } else if (fa < 0 || fb < 0) {  // frame-calib (and its transpose)
+    const int f = (fa < 0) ? fb : fa, i = (fa < 0) ? jb : ia, c = (fa < 0) ? ia : jb;
+    for (int t = 0; t < nf; t++) {
+      if (t == f) continue;
+      const double* S = TS + (size_t)(f * nf + t) * TOP_PART;
+      const double* Ah = A->adHost[f * nf + t];
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) s += Ah[i * 8 + k] * h13(S, 4 + k, c);
+      v += s;
+      const double* S2 = TS + (size_t)(t * nf + f) * TOP_PART;
+      v += A->adTdiag[t * nf + f][i] * h13(S2, 4 + i, c);
+    }
+  } else if (fa == fb) {  // diagonal frame block
+    for (int t = 0; t < nf; t++) {
+      if (t == fa) continue;
+      const double* S = TS + (size_t)(fa * nf + t) * TOP_PART;
+      const double* Ah = A->adHost[fa * nf + t];
+      double s0 = 0.0, s1 = 0.0;
+      for (int k = 0; k < 8; k++) {
+        double m0 = 0.0, m1 = 0.0;  // (P Ah^T)[k][jb]
+#pragma unroll
+        for (int l = 0; l < 8; l += 2) {
+          m0 += h13(S, 4 + k, 4 + l) * Ah[jb * 8 + l];
+          m1 += h13(S, 4 + k, 4 + l + 1) * Ah[jb * 8 + l + 1];
+        }
+        if (k & 1) s1 += Ah[ia * 8 + k] * (m0 + m1); else s0 += Ah[ia * 8 + k] * (m0 + m1);
+      }
+      v += s0 + s1;
+      const double* S2 = TS + (size_t)(t * nf + fa) * TOP_PART;
+      const double* d = A->adTdiag[t * nf + fa];
+      v += d[ia] * h13(S2, 4 + ia, 4 + jb) * d[jb];
+    }
+  } else {  // off-diagonal frame block: raw[fa,fb](ia,jb) + raw[fb,fa](jb,ia), raw[h,t] = Ah P At^T
+    {
+      const double* S = TS + (size_t)(fa * nf + fb) * TOP_PART;
+      const double* Ah = A->adHost[fa * nf + fb];
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) s += Ah[ia * 8 + k] * h13(S, 4 + k, 4 + jb);
+      v += s * A->adTdiag[fa * nf + fb][jb];
+    }
+    {
+      const double* S = TS + (size_t)(fb * nf + fa) * TOP_PART;
+      const double* Ah = A->adHost[fb * nf + fa];
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) s += Ah[jb * 8 + k] * h13(S, 4 + k, 4 + ia);
+      v += s * A->adTdiag[fb * nf + fa][ia];
+    }
+  }
+  R[(size_t)I * N + J] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:L295-321) + point part of doStepFromBackup (FullSystemOptimize.cpp:L264-272)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ba_resub_kernel(const BAWinDev* __restrict__ wins, int apply) {
+  const BAWinDev& W = wins[blockIdx.y];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nf = W.nf, mp = W.mp;
+  float step2 = 0.f, nid = 0.f;
+  if (p < W.npts && W.it->have_x) {
+    // host frame of p: chunks are host-sorted; find via the chunk table (few chunks per host)
+    int h = 0;
+    {
+      int lo = 0, hi = W.nchunks - 1;
+      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (W.chunks[mid].start <= p) lo = mid; else hi = mid - 1; }
+      h = W.chunks[lo].host;
+    }
+    const float4 po0 = reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8)[0];
+    const float4 po1 = reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8)[1];
+    const float HdiF = po1.z;
+    float step = 0.f;
+    int ngood = 0;
+    float b = po1.w;  // bdSumF
+    const float* xc = W.it->xc;
+    b -= xc[0] * po0.z + xc[1] * po0.w + xc[2] * po1.x + xc[3] * po1.y;
+    for (int t = 0; t < nf; t++) {
+      if (t == h) continue;
+      const int slot = t * mp + p;
+      if (W.c_st[slot] != RES_IN) continue;
+      ngood++;
+      const float4 a0 = reinterpret_cast<const float4*>(W.c_jpjd + (size_t)slot * 8)[0];
+      const float4 a1 = reinterpret_cast<const float4*>(W.c_jpjd + (size_t)slot * 8)[1];
+      const float* xa = W.it->xAd[h * nf + t];
+      b -= xa[0] * a0.x + xa[1] * a0.y + xa[2] * a0.z + xa[3] * a0.w + xa[4] * a1.x + xa[5] * a1.y + xa[6] * a1.z + xa[7] * a1.w;
+    }
+    if (ngood > 0) step = -b * HdiF;
+    W.step[p] = step;
+    const float idb = W.idepth_backup[p];
+    step2 = step * step;
+    nid = fabsf(idb);
+    if (apply) {
+      const float v = idb + step;
+      W.idepth[p] = v;
+      W.idepth_zero[p] = v;  // DM-VIO: setIdepthZero in doStepFromBackup (FullSystemOptimize.cpp:L268)
+    }
+  }
+  // block partial of (sum step^2, sum |idepth_backup|) — deterministic two-level reduction
+  __shared__ float s2[128], sn[128];
+  s2[threadIdx.x] = step2; sn[threadIdx.x] = nid;
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) { s2[threadIdx.x] += s2[threadIdx.x + s]; sn[threadIdx.x] += sn[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { W.step_part[2 * blockIdx.x] = (double)s2[0]; W.step_part[2 * blockIdx.x + 1] = (double)sn[0]; }
+}
+
+__global__ void ba_resub_finish_kernel(const BAWinDev* __restrict__ wins, int nblocks) {
+  const BAWinDev& W = wins[blockIdx.x];
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < nblocks; i++) { a += W.step_part[2 * i]; b += W.step_part[2 * i + 1]; }
+    double* tail = W.result + 2 * (W.N * W.N + W.N);
+    tail[4] = a; tail[5] = b; tail[6] = (double)W.npts;
+  }
+}
+
+__global__ void ba_backup_kernel(const BAWinDev* __restrict__ wins, int restore) {
+  const BAWinDev& W = wins[blockIdx.y];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= W.npts) return;
+  if (restore) { const float v = W.idepth_backup[p]; W.idepth[p] = v; W.idepth_zero[p] = v; }
+  else W.idepth_backup[p] = W.idepth[p];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// image planes: AoS3 -> float4 texels, and level-0 [I,dx,dy] construction (HessianBlocks.cpp:L169-179)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void repack_aos3_kernel(const float* __restrict__ src, float4* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
+}
+
+__global__ void make_dI_kernel(const float* __restrict__ img, float4* __restrict__ dst, int w, int h) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w * h) return;
+  float dx = 0.f, dy = 0.f;
+  if (idx >= w && idx < w * (h - 1)) {  // the reference's flat loop: row ends wrap into the neighbouring rows
+    dx = 0.5f * (img[idx + 1] - img[idx - 1]);
+    dy = 0.5f * (img[idx + w] - img[idx - w]);
+    if (!isfinite(dx)) dx = 0.f;
+    if (!isfinite(dy)) dy = 0.f;
+  }
+  dst[idx] = make_float4(img[idx], dx, dy, 0.f);
+}
+
+// larger-than-L2 scrub used by the bench between timed iterations
+__global__ void l2_flush_kernel(float4* buf, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) { float4 v = buf[i]; v.x += 1.f; buf[i] = v; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launch helpers (called from ba_api.cu)
+// ---------------------------------------------------------------------------------------------------------------
+void launch_point_kernel(const BAWinDev* wins, int nwin, int max_chunks, int P, int nf, cudaStream_t s) {
+  dim3 grid(max_chunks, nwin), block(32 * (nf < 2 ? 2 : nf));
+  if (P == 8) ba_point_kernel<8><<<grid, block, 0, s>>>(wins);
+  else if (P == 16) ba_point_kernel<16><<<grid, block, 0, s>>>(wins);
+  else ba_point_kernel<32><<<grid, block, 0, s>>>(wins);
+}
+void launch_reduce_kernel(const BAWinDev* wins, int nwin, int nf, int ntiles, cudaStream_t s) {
+  const int entries = nf * nf * TOP_PART + ntiles * 16 + 4;
+  dim3 grid((entries + 255) / 256, nwin);
+  ba_reduce_kernel<<<grid, 256, 0, s>>>(wins);
+}
+void launch_stitch_kernel(const BAWinDev* wins, int nwin, int N, cudaStream_t s) {
+  dim3 grid((N * (N + 1) + 255) / 256, nwin);
+  ba_stitch_kernel<<<grid, 256, 0, s>>>(wins);
+}
+void launch_resub_kernel(const BAWinDev* wins, int nwin, int npts, int apply, cudaStream_t s) {
+  const int nb = (npts + 127) / 128;
+  dim3 grid(nb, nwin);
+  ba_resub_kernel<<<grid, 128, 0, s>>>(wins, apply);
+  ba_resub_finish_kernel<<<nwin, 32, 0, s>>>(wins, nb);
+}
+void launch_backup_kernel(const BAWinDev* wins, int nwin, int npts, int restore, cudaStream_t s) {
+  dim3 grid((npts + 255) / 256, nwin);
+  ba_backup_kernel<<<grid, 256, 0, s>>>(wins, restore);
+}
+void launch_repack(const float* src, float4* dst, int n, cudaStream_t s) { repack_aos3_kernel<<<(n + 255) / 256, 256, 0, s>>>(src, dst, n); }
+void launch_make_dI(const float* img, float4* dst, int w, int h, cudaStream_t s) { make_dI_kernel<<<(w * h + 255) / 256, 256, 0, s>>>(img, dst, w, h); }
+void launch_l2_flush(float4* buf, size_t n, cudaStream_t s) { l2_flush_kernel<<<148 * 8, 256, 0, s>>>(buf, n); }
+
+}  // namespace dmv

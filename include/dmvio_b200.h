@@ -1,0 +1,208 @@
+/* dmvio_b200.h — C ABI of the B200-native DM-VIO photometric hot path.
+ *
+ * Drop-in boundary.  Plain C, opaque handles, int status codes, caller-owned host
+ * buffers, one CUDA stream per handle, no global mutable state: a BA handle (mapper thread) and a
+ * coarse-tracker handle (tracker thread) never share anything.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference's src/dso/).
+ *
+ * Conventions shared with the reference:
+ *   - state vector order  [C(4) | frame0: trans3 rot3 a b | frame1 ...],  N = 8*nf + 4
+ *     (OptimizationBackend/EnergyFunctional.cpp:L1019-1024)
+ *   - pair index of adjoint-like tables:  h + t*nf   (AccumulatedTopHessian.cpp:L71)
+ *   - pair index of precalc tables:       h*nf + t   (host->targetPrecalc[target], FullSystem.cpp:L1670-1680)
+ *   - x returned by the solve is -step               (EnergyFunctional.cpp:L975)
+ *   - residual states: 0 = IN, 1 = OOB, 2 = OUTLIER  (FullSystem/Residuals.h:L43); 255 = "no residual in this slot"
+ *
+ * All functions return DMV_OK (0) or a negative dmv_status.  dmv_last_error() gives a message for the
+ * calling thread.  There is NO CPU fallback: without a CUDA device every create() fails with DMV_ERR_NO_DEVICE.
+ */
+#ifndef DMVIO_B200_H
+#define DMVIO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMV_MAX_FRAMES 8      /* setting_maxFrames = 7 (+1 while the new keyframe is being optimised), util/settings.cpp:L100 */
+#define DMV_PATTERN 8         /* patternNum, util/settings.h:L227 */
+#define DMV_PRECALC_FLOATS 32 /* KRKi[9] Kt[3] R0[9] t0[3] aff[2] b0 pad[5] */
+#define DMV_MAX_PYR_LEVELS 6  /* PYR_LEVELS, util/settings.h:L52 */
+
+typedef enum dmv_status {
+  DMV_OK = 0,
+  DMV_ERR_INVALID = -1,   /* bad argument / inconsistent sizes */
+  DMV_ERR_NO_DEVICE = -2, /* no usable CUDA device: the product has no CPU path */
+  DMV_ERR_CUDA = -3,      /* a CUDA runtime call failed (see dmv_last_error) */
+  DMV_ERR_STATE = -4,     /* call order violated (e.g. accumulate before linearize+apply) */
+  DMV_ERR_NCCL = -5
+} dmv_status;
+
+const char* dmv_last_error(void);
+const char* dmv_version(void);
+int dmv_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bundle-adjustment handle  ==  the GPU side of EnergyFunctional + FullSystem::linearizeAll
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dmv_ba dmv_ba;
+
+typedef struct dmv_ba_config {
+  int w, h;           /* level-0 image size (wG[0], hG[0]) */
+  int max_frames;     /* <= DMV_MAX_FRAMES */
+  int max_points;     /* capacity of the active point set */
+  int device;         /* CUDA device ordinal */
+  int chunk_points;   /* points per thread block: 8, 16 or 32; 0 = default */
+} dmv_ba_config;
+
+/* util/settings.cpp values read by the kernels (constant during a run) */
+typedef struct dmv_ba_params {
+  float huberTH;                /* setting_huberTH = 9 */
+  float outlierTHSumComponent;  /* setting_outlierTHSumComponent = 50*50 */
+  float affineOptModeA;         /* <0: JabF[0] is zeroed (Residuals.cpp:L229-242) */
+  float affineOptModeB;
+} dmv_ba_params;
+
+int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out);
+int dmv_ba_destroy(dmv_ba* ba);
+int dmv_ba_set_params(dmv_ba* ba, const dmv_ba_params* p);
+void dmv_ba_default_params(dmv_ba_params* p);
+
+/* FrameHessian::dI (HessianBlocks.h:L122): level-0 [I,dx,dy] AoS, w*h*3 floats, into image slot `slot`
+ * (0 <= slot < max_frames).  Slots let frames stay resident across keyframes while window indices shift. */
+int dmv_ba_upload_frame(dmv_ba* ba, int slot, const float* dI_aos3);
+/* Same, but builds [I,dx,dy] on the device from the raw float image (FrameHessian::makeImages, HessianBlocks.cpp:L128-191, level 0). */
+int dmv_ba_upload_image(dmv_ba* ba, int slot, const float* image_wh);
+
+/* EnergyFunctional::makeIDX (EnergyFunctional.cpp:L998-1016): window frame index -> image slot */
+int dmv_ba_set_window(dmv_ba* ba, int nf, const int* slots);
+
+/* EFPoint/PointHessian fields read on the path (HessianBlocks.h:L413-508, EnergyFunctionalStructs.h:L104-137).
+ * Points must be ordered by host frame index (that is EnergyFunctional::allPoints' order).
+ * color8/weights8: npts*8.  priorF/deltaF may be NULL (zeros). */
+int dmv_ba_set_points(dmv_ba* ba, int npts, const int32_t* host, const float* u, const float* v, const float* idepth,
+                      const float* idepth_zero, const float* color8, const float* weights8, const float* priorF);
+
+/* The active (non-linearised) PointFrameResiduals of the window: (point, target) pairs, at most one per pair,
+ * with PointFrameResidual::state_state / state_energy (Residuals.h:L64-84).  state_state/state_energy may be NULL (all IN / 0). */
+int dmv_ba_set_residuals(dmv_ba* ba, int nres, const int32_t* point, const int32_t* target, const int32_t* state_state,
+                         const float* state_energy);
+
+/* EnergyFunctional::setAdjointsF (EnergyFunctional.cpp:L48-108): adHost/adTarget, nf*nf 8x8 row-major doubles, index h + t*nf */
+int dmv_ba_set_adjoints(dmv_ba* ba, const double* adHost, const double* adTarget);
+
+/* Per-iteration state == FullSystem::setPrecalcValues (FrameFramePrecalc::set, HessianBlocks.cpp:L193-223) + CalibHessian values +
+ * FrameHessian::frameEnergyTH.  idepth (npts) may be NULL: keep the device copy (e.g. after dmv_ba_resubstitute(apply=1)).
+ * idepth_zero likewise.  deltaF (npts) = idepth - idepth_zero for the prior shift (EnergyFunctional.cpp:L194); NULL => recomputed on device. */
+typedef struct dmv_ba_state {
+  float calib[8];          /* fxl fyl cxl cyl fxli fyli cxli cyli (CalibHessian::value_scaledf / value_scaledi) */
+  const float* precalc;    /* nf*nf*DMV_PRECALC_FLOATS, index h*nf + t */
+  const float* frameEnergyTH; /* nf */
+  const float* idepth;     /* npts or NULL */
+  const float* idepth_zero;/* npts or NULL */
+} dmv_ba_state;
+int dmv_ba_set_state(dmv_ba* ba, const dmv_ba_state* st);
+
+/* FullSystem::linearizeAll(false) (FullSystemOptimize.cpp:L150-218) fused with the *tentative* accumulateAF/SCF of the
+ * next solveSystemF: evaluates every active residual at the current state, reduces the per-pair 13x13 blocks, the
+ * per-point Hdd/bd/Hcd and the Schur complement, and stitches the dense system on the device.
+ * Nothing becomes visible to dmv_ba_accumulate / dmv_ba_resubstitute until dmv_ba_apply_res().
+ * out: energy = sum of PointFrameResidual::linearize() return values (stats[0]); n_in = #residuals with state_NewState==IN. */
+typedef struct dmv_ba_lin_result {
+  double energy;
+  int n_in, n_oob, n_outlier;
+} dmv_ba_lin_result;
+int dmv_ba_linearize(dmv_ba* ba, dmv_ba_lin_result* out);
+
+/* Per-residual outputs of the last linearize, in the order given to dmv_ba_set_residuals
+ * (state_NewState, state_NewEnergy, state_NewEnergyWithOutlier, centerProjectedTo; Residuals.h:L64-84). Any pointer may be NULL. */
+int dmv_ba_get_residual_outputs(dmv_ba* ba, int32_t* newState, float* newEnergy, float* newEnergyWithOutlier, float* centerProjectedTo3,
+                                float* JpJdF8);
+
+/* state_NewEnergyWithOutlier of the residuals whose target is frame `target` (input of FullSystem::setNewFrameEnergyTH,
+ * FullSystemOptimize.cpp:L96-149): writes at most cap floats, returns the count in *n. Entries < 0 (not evaluated) are skipped. */
+int dmv_ba_get_target_energies(dmv_ba* ba, int target, float* out, int cap, int* n);
+
+/* PointFrameResidual::applyRes(true) + EFResidual::takeDataF for all active residuals (FullSystemOptimize.cpp:L90-94):
+ * commits the tentative linearisation (buffer swap; no kernel). */
+int dmv_ba_apply_res(dmv_ba* ba);
+
+/* The accumulate half of EnergyFunctional::solveSystemF (EnergyFunctional.cpp:L853-860): accumulateAF_MT + accumulateSCF_MT of the
+ * committed linearisation.  H_A/H_sc: N*N row-major doubles, b_A/b_sc: N.  (accumulateLF_MT's priors are host data; the host adapter adds them.)
+ * resInA = AccumulatedTopHessianSSE::nres[0]. */
+int dmv_ba_accumulate(dmv_ba* ba, double* H_A, double* b_A, double* H_sc, double* b_sc, int* resInA);
+
+/* Per-point results of the committed accumulation: EFPoint::{Hdd_accAF, bd_accAF, Hcd_accAF, HdiF, bdSumF} (EnergyFunctionalStructs.h:L117-135).
+ * Any pointer may be NULL. */
+int dmv_ba_get_point_outputs(dmv_ba* ba, float* Hdd_accAF, float* bd_accAF, float* Hcd_accAF4, float* HdiF, float* bdSumF);
+
+/* EnergyFunctional::resubstituteF_MT (EnergyFunctional.cpp:L267-321): x = N doubles (= -step).  step_out (npts) may be NULL.
+ * apply != 0 additionally performs the point part of FullSystem::doStepFromBackup (FullSystemOptimize.cpp:L264-272):
+ * idepth = idepth_backup + step, idepth_zero likewise (DM-VIO), on the device copy; sums[0] = sum step^2, sums[1] = sum |idepth_backup|, sums[2] = npts. */
+int dmv_ba_resubstitute(dmv_ba* ba, const double* x, float* step_out, int apply, double sums[3]);
+/* FullSystem::backupState / loadSateBackup for the point depths held on the device (FullSystemOptimize.cpp:L322-388) */
+int dmv_ba_backup_points(dmv_ba* ba);
+int dmv_ba_restore_points(dmv_ba* ba);
+int dmv_ba_get_idepth(dmv_ba* ba, float* idepth, float* idepth_zero);
+
+/* Fused GN iteration (one host<->device round trip): resubstitute(x) + point step + set_state + linearize.
+ * x may be NULL (first linearisation).  Equivalent to dmv_ba_resubstitute(x, apply=1) ; dmv_ba_set_state(st) ; dmv_ba_linearize(). */
+int dmv_ba_gn_step(dmv_ba* ba, const double* x, const dmv_ba_state* st, dmv_ba_lin_result* out, double sums[3]);
+
+/* Multi-GPU: points are sharded over ranks, images/tables replicated.  After dmv_ba_comm_init every
+ * dmv_ba_linearize all-reduces the stitched system (and energy/counters) over NCCL so all ranks hold identical H,b.
+ * nccl_unique_id: 128 bytes from ncclGetUniqueId() on rank 0, distributed by the caller. */
+int dmv_nccl_unique_id(void* id128);
+int dmv_ba_comm_init(dmv_ba* ba, int nranks, int rank, const void* nccl_unique_id);
+
+/* timing of the last linearize/gn_step on the handle's stream (CUDA events), milliseconds: [0]=total device time of the call,
+ * [1]=point kernel, [2]=reduce+stitch */
+int dmv_ba_last_timing(dmv_ba* ba, float ms[4]);
+/* raw device access for benchmarking: run the device part of one GN iteration (resubstitute+step if x != NULL, point kernel, reduce,
+ * stitch, all-reduce if a communicator is attached) `iters` times on the handle's stream with all inputs resident, each iteration
+ * bracketed by CUDA events (optionally preceded by an untimed L2 scrub); returns the average device milliseconds per iteration
+ * and the time from the start of the iteration to the end of the point kernel. */
+int dmv_ba_bench_device(dmv_ba* ba, const double* x, int iters, int flush_l2, float* ms_per_iter, float* ms_point_kernel);
+int dmv_ba_kernel_launch_count(dmv_ba* ba, long long* n);
+/* bytes copied host->device and device->host by one dmv_ba_gn_step / dmv_ba_linearize call */
+int dmv_ba_io_bytes(dmv_ba* ba, long long* h2d, long long* d2h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Coarse-tracker handle  ==  the GPU side of CoarseTracker (FullSystem/CoarseTracker.{h,cpp})
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dmv_ct dmv_ct;
+typedef struct dmv_ct_config {
+  int w, h;
+  int levels;      /* pyrLevelsUsed */
+  int max_points;  /* capacity of pc_* per level */
+  int device;
+} dmv_ct_config;
+
+int dmv_ct_create(const dmv_ct_config* cfg, dmv_ct** out);
+int dmv_ct_destroy(dmv_ct* ct);
+/* CoarseTracker::makeK (CoarseTracker.cpp:L105-134): per-level intrinsics */
+int dmv_ct_set_K(dmv_ct* ct, int level, float fx, float fy, float cx, float cy);
+/* pc_u/pc_v/pc_idepth/pc_color of one level (result of makeCoarseDepthL0, CoarseTracker.cpp:L249-293) */
+int dmv_ct_set_ref(dmv_ct* ct, int level, int n, const float* pc_u, const float* pc_v, const float* pc_idepth, const float* pc_color);
+/* newFrame->dIp[level] (w_l*h_l*3 floats AoS) */
+int dmv_ct_upload_new(dmv_ct* ct, int level, const float* dIp_aos3);
+/* builds the whole pyramid of the new frame on the device from the raw image (FrameHessian::makeImages) */
+int dmv_ct_upload_new_image(dmv_ct* ct, const float* image_wh);
+/* settings read by calcRes: setting_huberTH */
+int dmv_ct_set_huber(dmv_ct* ct, float huberTH);
+
+/* CoarseTracker::calcRes (L361-517) fused with calcGSSSE (L299-356) for one pose:
+ *   RKi = R * Ki[lvl] (row-major 3x3 float), t (3), affLL = AffLight::fromToVecExposure(...) (2),
+ *   a_gs = affLL[0] (first argument `a` of calcGSSSE), b0 = lastRef_aff_g2l.b, cutoffTH.
+ * out: res6 = Vec6 of calcRes; if want_gs: H (8x8 row-major) and b (8) exactly as calcGSSSE returns them
+ * (divided by the 4-padded warped count, SCALE_* applied); n_warped = buf_warped_n (padded). */
+int dmv_ct_calc_res_gs(dmv_ct* ct, int level, const float RKi[9], const float t[3], const float affLL[2], float b0, float cutoffTH,
+                       int want_gs, double res6[6], double H[64], double b[8], int* n_warped);
+int dmv_ct_last_timing(dmv_ct* ct, float ms[4]);
+int dmv_ct_kernel_launch_count(dmv_ct* ct, long long* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMVIO_B200_H */

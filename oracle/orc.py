@@ -70,6 +70,8 @@ def _declare(L):
     L.orc_win_get_frame_states.argtypes = [vp, f64p]
     L.orc_win_gn_iteration.restype = C.c_double
     L.orc_win_gn_iteration.argtypes = [vp, C.c_double, C.c_int, C.c_int]
+    L.orc_win_hot_iteration.restype = C.c_double
+    L.orc_win_hot_iteration.argtypes = [vp, f64p, C.c_int]
     L.orc_win_eval_raw_double.argtypes = [vp, C.c_int, f64p, f64p, C.c_double, f64p, f64p]
     L.orc_pyr_levels.argtypes = [C.c_int, C.c_int, C.c_int]
     L.orc_make_images.restype = C.c_int64
@@ -216,6 +218,9 @@ class Window:
 
     def gn_iteration(self, lam=1e-5, precision=0, do_step=True):
         return self.L.orc_win_gn_iteration(self.h, lam, precision, int(do_step))
+
+    def hot_iteration(self, x, precision=0):
+        return self.L.orc_win_hot_iteration(self.h, np.ascontiguousarray(x, np.float64), precision)
 
     def eval_raw(self, ri, dsh=None, dst=None, didepth=0.0, dcalib=None):
         z8 = np.zeros(8)

@@ -703,12 +703,10 @@ static inline void addBlock88(MatX& H, int r0, int c0, const Mat88& M) {
 
 // AccumulatedTopHessian.cpp:L241-303 (stitchDoubleInternal) + AccumulatedTopHessian.h:L91-139 (stitchDoubleMT)
 template <class T>
-static void stitchTop(Window& W, std::vector<AccSet<T>>& accs, MatX& H, VecX& b, bool usePrior, int* nresOut) {
+static void stitchTopRange(Window& W, std::vector<AccSet<T>>& accs, MatX& H, VecX& b, bool usePrior, int kmin, int kmax) {
+  // AccumulatedTopHessian.cpp:L241-303 (stitchDoubleInternal): one worker's share [kmin,kmax) of the nf*nf pair blocks
   const int nf = W.nf();
-  const int N = nf * 8 + CPARS;
-  H = MatX(N, N);
-  b.assign(N, 0.0);
-  for (int k = 0; k < nf * nf; k++) {
+  for (int k = kmin; k < kmax; k++) {
     int h = k % nf, t = k / nf;
     int hIdx = CPARS + h * 8, tIdx = CPARS + t * 8, aidx = h + nf * t;
     Mat<double, 13, 13> accH;
@@ -736,13 +734,32 @@ static void stitchTop(Window& W, std::vector<AccSet<T>>& accs, MatX& H, VecX& b,
     for (int i = 0; i < 8; i++) { b[hIdx + i] += hb[i]; b[tIdx + i] += tb[i]; }
     for (int i = 0; i < 4; i++) b[i] += accH(i, CPARS + 8);
   }
-  if (usePrior) {  // L292-302
+  if (kmin == 0 && usePrior) {  // only do this on one thread (L290-302)
     for (int i = 0; i < 4; i++) { H(i, i) += W.cPrior[i]; b[i] += W.cPrior[i] * (double)W.cDeltaF[i]; }
     for (int h = 0; h < nf; h++)
       for (int i = 0; i < 8; i++) {
         H(CPARS + h * 8 + i, CPARS + h * 8 + i) += W.frames[h].prior[i];
         b[CPARS + h * 8 + i] += W.frames[h].prior[i] * W.frames[h].delta_prior[i];
       }
+  }
+}
+
+template <class T>
+static void stitchTop(Window& W, std::vector<AccSet<T>>& accs, MatX& H, VecX& b, bool usePrior, int* nresOut) {
+  // AccumulatedTopHessian.h:L91-139 (stitchDoubleMT): per-thread H/b summed afterwards
+  const int nf = W.nf();
+  const int N = nf * 8 + CPARS;
+  if (W.nthreads > 1 && W.pool) {
+    const int nt = W.pool->size();
+    std::vector<MatX> Hs(nt, MatX(N, N));
+    std::vector<VecX> bs(nt, VecX(N, 0.0));
+    W.pool->reduce([&](int lo, int hi, double*, int tid) { if (lo != hi) stitchTopRange<T>(W, accs, Hs[tid], bs[tid], usePrior, lo, hi); }, 0, nf * nf, 0);
+    H = Hs[0]; b = bs[0];
+    for (int i = 1; i < nt; i++) { for (size_t a = 0; a < H.d.size(); a++) H.d[a] += Hs[i].d[a]; for (int a = 0; a < N; a++) b[a] += bs[i][a]; }
+  } else {
+    H = MatX(N, N);
+    b.assign(N, 0.0);
+    stitchTopRange<T>(W, accs, H, b, usePrior, 0, nf * nf);
   }
   // make diagonal by copying over parts (AccumulatedTopHessian.h:L125-138)
   for (int h = 0; h < nf; h++) {
@@ -761,13 +778,11 @@ static void stitchTop(Window& W, std::vector<AccSet<T>>& accs, MatX& H, VecX& b,
 
 // AccumulatedSCHessian.cpp:L78-157 + AccumulatedSCHessian.h:L93-133
 template <class T>
-static void stitchSC(Window& W, std::vector<AccSet<T>>& accs, MatX& H, VecX& b) {
+static void stitchSCRange(Window& W, std::vector<AccSet<T>>& accs, MatX& H, VecX& b, int kmin, int kmax) {
+  // AccumulatedSCHessian.cpp:L78-157 (stitchDoubleInternal)
   const int nf = W.nf();
-  const int N = nf * 8 + CPARS;
   const int nframes2 = nf * nf;
-  H = MatX(N, N);
-  b.assign(N, 0.0);
-  for (int k0 = 0; k0 < nf * nf; k0++) {
+  for (int k0 = kmin; k0 < kmax; k0++) {
     int i = k0 % nf, j = k0 / nf;
     int iIdx = CPARS + i * 8, jIdx = CPARS + j * 8, ijIdx = i + nf * j;
     Mat<double, 8, 4> Hpc; Vec8 bp;
@@ -795,11 +810,32 @@ static void stitchSC(Window& W, std::vector<AccSet<T>>& accs, MatX& H, VecX& b) 
       addBlock88(H, iIdx, kIdx, W.adHost[ijIdx] * accDM * W.adTarget[ikIdx].transpose());
     }
   }
-  for (auto& as : accs) {
-    as.accHcc.finish();
-    as.accbc.finish();
-    for (int a = 0; a < 4; a++) for (int c = 0; c < 4; c++) H(a, c) += (double)as.accHcc.A1m[a * 4 + c];
-    for (int a = 0; a < 4; a++) b[a] += (double)as.accbc.A1m[a];
+  if (kmin == 0) {
+    for (auto& as : accs) {
+      as.accHcc.finish();
+      as.accbc.finish();
+      for (int a = 0; a < 4; a++) for (int c = 0; c < 4; c++) H(a, c) += (double)as.accHcc.A1m[a * 4 + c];
+      for (int a = 0; a < 4; a++) b[a] += (double)as.accbc.A1m[a];
+    }
+  }
+}
+
+template <class T>
+static void stitchSC(Window& W, std::vector<AccSet<T>>& accs, MatX& H, VecX& b) {
+  // AccumulatedSCHessian.h:L93-133 (stitchDoubleMT)
+  const int nf = W.nf();
+  const int N = nf * 8 + CPARS;
+  if (W.nthreads > 1 && W.pool) {
+    const int nt = W.pool->size();
+    std::vector<MatX> Hs(nt, MatX(N, N));
+    std::vector<VecX> bs(nt, VecX(N, 0.0));
+    W.pool->reduce([&](int lo, int hi, double*, int tid) { if (lo != hi) stitchSCRange<T>(W, accs, Hs[tid], bs[tid], lo, hi); }, 0, nf * nf, 0);
+    H = Hs[0]; b = bs[0];
+    for (int i = 1; i < nt; i++) { for (size_t a = 0; a < H.d.size(); a++) H.d[a] += Hs[i].d[a]; for (int a = 0; a < N; a++) b[a] += bs[i][a]; }
+  } else {
+    H = MatX(N, N);
+    b.assign(N, 0.0);
+    stitchSCRange<T>(W, accs, H, b, 0, nf * nf);
   }
   for (int h = 0; h < nf; h++) {
     int hIdx = CPARS + h * 8;
@@ -922,9 +958,7 @@ void Window::solveSystem(int iteration, double lambda, int precision, ReducedSys
     bFinal[i] = sys.bL[i] + bM_top[i] + sys.bA[i] - sys.bsc[i];
   }
   for (int i = 0; i < N; i++) HFinal(i, i) *= (1 + lambda);
-  const double f = (double)(1.0f / (float)(1 + lambda));  // H_sc * (1.0f/(1+lambda)) : float literal promoted to double
-  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) HFinal(i, j) -= sys.Hsc(i, j) * (1.0 / (1 + lambda));
-  (void)f;
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) HFinal(i, j) -= sys.Hsc(i, j) * (1.0 / (1 + lambda));  // L916: (1.0f/(1+lambda)) is a double division
   if (sysOut) *sysOut = sys;
   if (HFinalOut) *HFinalOut = HFinal;
   if (bFinalOut) *bFinalOut = bFinal;

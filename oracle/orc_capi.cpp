@@ -243,6 +243,22 @@ double orc_win_gn_iteration(OrcWin* o, double lambda, int precision, int do_step
   return e;
 }
 
+double orc_win_hot_iteration(OrcWin* o, const double* x, int precision) {
+  // the measured path of one GN iteration WITHOUT the dense host solve: accumulate A/L/SC + stitch,
+  // resubstitute(x), doStepFromBackup (incl. setPrecalcValues), linearizeAll, applyRes; the window is restored afterwards.
+  Window& W = o->W;
+  const int N = W.nf() * 8 + CPARS;
+  W.backupState();
+  W.accumulate(o->lastSys, precision);
+  VecX xv(x, x + N);
+  W.resubstitute(xv);
+  W.doStepFromBackup();
+  double e = W.linearizeAll(false, nullptr);
+  W.applyResAll();
+  W.loadStateBackup();
+  return e;
+}
+
 int orc_win_eval_raw_double(OrcWin* o, int ri, const double dsh[8], const double dst[8], double didepth, const double dcalib[4], double r_raw[8]) {
   // independent first-principles evaluation in double: r_i = I_t(pi(K T_th pi^-1(p_i, idepth))) - (a * color_i + b)
   Window& W = o->W;

@@ -54,6 +54,9 @@ void orc_win_get_frame_states(OrcWin*, double* state10);
 /* one full GN iteration as timed by the bench: solveSystem (accumulate A/L/SC + stitch + solve + resubstitute) + doStep + linearizeAll */
 double orc_win_gn_iteration(OrcWin*, double lambda, int precision, int do_step);
 
+/* the measured path of one GN iteration without the dense solve: accumulate+stitch, resubstitute(x), step, linearizeAll, applyRes */
+double orc_win_hot_iteration(OrcWin*, const double* x, int precision);
+
 /* finite-difference helper: raw (un-weighted) residuals of one residual, evaluated from first principles in double,
  * after adding dstate (unscaled, 8) to the host / target frame state, didepth to the point and dcalib (unscaled) to the calib */
 int orc_win_eval_raw_double(OrcWin*, int res_idx, const double dstate_host[8], const double dstate_target[8], double didepth,

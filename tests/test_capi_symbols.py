@@ -1,0 +1,43 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol declared in
+include/dmvio_b200.h, and fails loudly (no CPU fallback) when there is no CUDA device."""
+import os
+import re
+
+import pytest
+
+
+def _header_symbols():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "include", "dmvio_b200.h")).read()
+    return sorted(set(re.findall(r"\b(dmv_[A-Za-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import dmvio_b200.capi as c
+    L = c.lib()
+    syms = _header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(L, s), f"libdmvio_b200.so lacks {s}"
+    assert sorted(c.SYMBOLS) == syms
+    assert b"sm_100a" in L.dmv_version()
+
+
+def test_no_cpu_fallback():
+    import dmvio_b200.capi as c
+    if c.lib().dmv_device_count() > 0:
+        pytest.skip("a GPU is visible; the failure path is exercised on the CPU-only box")
+    with pytest.raises(c.DmvError, match="no CUDA device"):
+        c.BA(640, 480)
+    with pytest.raises(c.DmvError, match="no CUDA device"):
+        c.CT(640, 480, 4)
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "dm-vio_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, fn), errors="ignore").read()
+                assert "liborc" not in txt and "from oracle" not in txt and "import oracle" not in txt and "orc_" not in txt, fn
