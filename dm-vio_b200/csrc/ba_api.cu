@@ -8,11 +8,9 @@
 #include <vector>
 
 namespace dmv {
-void launch_point_kernel(const BAWinDev* wins, int nwin, int max_chunks, int P, int nf, cudaStream_t s);
-void launch_reduce_kernel(const BAWinDev* wins, int nwin, int nf, int ntiles, cudaStream_t s);
-void launch_stitch_kernel(const BAWinDev* wins, int nwin, int N, cudaStream_t s);
-void launch_resub_kernel(const BAWinDev* wins, int nwin, int npts, int apply, cudaStream_t s);
-void launch_backup_kernel(const BAWinDev* wins, int nwin, int npts, int restore, cudaStream_t s);
+void launch_point_kernel(const BAWinDev& W, const BAIter& it, cudaStream_t s);
+void launch_stitch_kernel(const BAWinDev& W, cudaStream_t s);
+void launch_resub_kernel(const BAWinDev& W, const BAIter& it, int apply, double* sums, cudaStream_t s);
 void launch_repack(const float* src, float4* dst, int n, cudaStream_t s);
 void launch_make_dI(const float* img, float4* dst, int w, int h, cudaStream_t s);
 void launch_l2_flush(float4* buf, size_t n, cudaStream_t s);
@@ -20,7 +18,7 @@ void launch_l2_flush(float4* buf, size_t n, cudaStream_t s);
 
 using namespace dmv;
 
-struct HostUpload {  // one pinned block -> one H2D copy per linearisation
+struct HostUpload {  // descriptor + per-iteration tables: passed BY VALUE as __grid_constant__ kernel parameters (no H2D copy)
   BAWinDev win;
   BAIter it;
 };
@@ -39,9 +37,7 @@ struct dmv_ba {
   // device buffers
   float4* d_img[MAXF] = {nullptr};
   float* d_stage_img = nullptr;
-  HostUpload* d_up = nullptr;  // BAWinDev + BAIter
   BAAdj* d_adj = nullptr;
-  BAChunk* d_chunks = nullptr;
   float2* d_uv = nullptr;
   float *d_idepth = nullptr, *d_idepth_zero = nullptr, *d_idepth_backup = nullptr, *d_color = nullptr, *d_weights = nullptr, *d_priorF = nullptr;
   uint8_t* d_st_in = nullptr;
@@ -51,8 +47,10 @@ struct dmv_ba {
         *d_pout[2] = {nullptr, nullptr};
   double* d_result[2] = {nullptr, nullptr};
   float* d_step = nullptr;
-  float *d_top_part = nullptr, *d_sc_part = nullptr, *d_misc_part = nullptr;
-  double *d_step_part = nullptr, *d_top_sum = nullptr, *d_sc_sum = nullptr;
+  double* d_acc[2] = {nullptr, nullptr};  // fp64 accumulator sets (current / being zeroed for the next iteration)
+  int acc_cur = 0;
+  size_t acc_cap = 0;
+  double* d_resub_sums = nullptr;
   float4* d_flush = nullptr;
   size_t flush_n = 0;
   // pinned host
@@ -62,7 +60,8 @@ struct dmv_ba {
   float* h_scratch = nullptr;  // max(mp*8, w*h*3) floats
   size_t scratch_floats = 0;
   // host bookkeeping
-  std::vector<BAChunk> chunks;
+  int host_start[MAXF + 1];
+  int chunk_beg[MAXF + 1];
   std::vector<int> host_of_point;
   std::vector<int> res_slot;   // residual index -> slot (t*mp+p)
   std::vector<uint8_t> h_st_in;
@@ -86,18 +85,12 @@ static int fill_descriptor(dmv_ba* b) {
   BAWinDev& W = b->h_up->win;
   std::memset(&W, 0, sizeof(W));
   W.nf = b->nf; W.npts = b->npts; W.nchunks = b->nchunks; W.w = b->cfg.w; W.h = b->cfg.h;
-  W.N = b->N; W.NW = b->NW; W.T = b->T; W.ntiles = b->ntiles; W.mp = b->mp;
+  W.N = b->N; W.NW = b->NW; W.T = b->T; W.ntiles = b->ntiles; W.mp = b->mp; W.P = b->P;
   W.huberTH = b->prm.huberTH; W.outlierTHSum = b->prm.outlierTHSumComponent;
   W.zeroA = b->prm.affineOptModeA < 0; W.zeroB = b->prm.affineOptModeB < 0;
+  for (int h = 0; h <= MAXF; h++) { W.host_start[h] = b->host_start[h]; W.chunk_beg[h] = b->chunk_beg[h]; }
   for (int f = 0; f < b->nf; f++) W.img[f] = b->d_img[b->slots[f]];
-  W.it = &b->d_up->it;
   W.adj = b->d_adj;
-  W.chunks = b->d_chunks;
-  int c = 0;
-  for (int h = 0; h <= MAXF; h++) {
-    while (c < b->nchunks && b->chunks[c].host < h) c++;
-    W.chunk_beg[h] = c;
-  }
   W.uv = b->d_uv; W.idepth = b->d_idepth; W.idepth_zero = b->d_idepth_zero; W.idepth_backup = b->d_idepth_backup;
   W.color = b->d_color; W.weights = b->d_weights; W.priorF = b->d_priorF;
   W.st_in = b->d_st_in; W.en_in = b->d_en_in;
@@ -105,8 +98,8 @@ static int fill_descriptor(dmv_ba* b) {
   W.st_new = b->d_st_new[t]; W.en_new = b->d_en_new[t]; W.en_wo = b->d_en_wo[t]; W.cpt = b->d_cpt[t]; W.jpjd = b->d_jpjd[t]; W.pout = b->d_pout[t];
   W.c_st = b->d_st_new[c2]; W.c_jpjd = b->d_jpjd[c2]; W.c_pout = b->d_pout[c2];
   W.step = b->d_step;
-  W.top_part = b->d_top_part; W.sc_part = b->d_sc_part; W.misc_part = b->d_misc_part; W.step_part = b->d_step_part;
-  W.top_sum = b->d_top_sum; W.sc_sum = b->d_sc_sum;
+  W.acc = b->d_acc[b->acc_cur];
+  W.acc_next = b->d_acc[1 - b->acc_cur];
   W.result = b->d_result[t];
   return DMV_OK;
 }
@@ -144,9 +137,7 @@ int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
   for (int i = 0; i < 4; i++) CK(cudaEventCreate(&b->ev[i]));
   for (int f = 0; f < cfg->max_frames; f++) CK(cudaMalloc(&b->d_img[f], npx * sizeof(float4)));
   CK(cudaMalloc(&b->d_stage_img, npx * 3 * sizeof(float)));
-  CK(cudaMalloc(&b->d_up, sizeof(HostUpload)));
   CK(cudaMalloc(&b->d_adj, sizeof(BAAdj)));
-  CK(cudaMalloc(&b->d_chunks, sizeof(BAChunk) * b->max_chunks));
   CK(cudaMalloc(&b->d_uv, sizeof(float2) * mp));
   CK(cudaMalloc(&b->d_idepth, sizeof(float) * mp));
   CK(cudaMalloc(&b->d_idepth_zero, sizeof(float) * mp));
@@ -171,12 +162,12 @@ int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
   CK(cudaMalloc(&b->d_step, sizeof(float) * mp));
   CK(cudaMemset(b->d_step, 0, sizeof(float) * mp));
   const int maxT = (8 * MF + 4 + 1 + 3) / 4, maxTiles = maxT * (maxT + 1) / 2;
-  CK(cudaMalloc(&b->d_top_part, sizeof(float) * (size_t)b->max_chunks * MF * TOP_PART));
-  CK(cudaMalloc(&b->d_sc_part, sizeof(float) * (size_t)b->max_chunks * maxTiles * 16));
-  CK(cudaMalloc(&b->d_misc_part, sizeof(float) * (size_t)b->max_chunks * MF * 4));
-  CK(cudaMalloc(&b->d_step_part, sizeof(double) * 2 * ((mp + 127) / 128 + 1)));
-  CK(cudaMalloc(&b->d_top_sum, sizeof(double) * MF * MF * TOP_PART));
-  CK(cudaMalloc(&b->d_sc_sum, sizeof(double) * maxTiles * 16));
+  b->acc_cap = (size_t)acc_doubles(MF, maxTiles);
+  for (int k = 0; k < 2; k++) {
+    CK(cudaMalloc(&b->d_acc[k], sizeof(double) * b->acc_cap));
+    CK(cudaMemset(b->d_acc[k], 0, sizeof(double) * b->acc_cap));
+  }
+  CK(cudaMalloc(&b->d_resub_sums, sizeof(double) * 4));
   CK(cudaMallocHost(&b->h_up, sizeof(HostUpload)));
   CK(cudaMallocHost(&b->h_adj, sizeof(BAAdj)));
   std::memset(b->h_up, 0, sizeof(HostUpload));
@@ -192,15 +183,14 @@ int dmv_ba_destroy(dmv_ba* b) {
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (int f = 0; f < MAXF; f++) cudaFree(b->d_img[f]);
-  cudaFree(b->d_stage_img); cudaFree(b->d_up); cudaFree(b->d_adj); cudaFree(b->d_chunks); cudaFree(b->d_uv); cudaFree(b->d_idepth);
+  cudaFree(b->d_stage_img); cudaFree(b->d_adj); cudaFree(b->d_uv); cudaFree(b->d_idepth);
   cudaFree(b->d_idepth_zero); cudaFree(b->d_idepth_backup); cudaFree(b->d_color); cudaFree(b->d_weights); cudaFree(b->d_priorF);
   cudaFree(b->d_st_in); cudaFree(b->d_en_in);
   for (int k = 0; k < 2; k++) {
     cudaFree(b->d_st_new[k]); cudaFree(b->d_en_new[k]); cudaFree(b->d_en_wo[k]); cudaFree(b->d_cpt[k]); cudaFree(b->d_jpjd[k]);
     cudaFree(b->d_pout[k]); cudaFree(b->d_result[k]); cudaFreeHost(b->h_result[k]);
   }
-  cudaFree(b->d_step); cudaFree(b->d_top_part); cudaFree(b->d_sc_part); cudaFree(b->d_misc_part); cudaFree(b->d_step_part);
-  cudaFree(b->d_top_sum); cudaFree(b->d_sc_sum); cudaFree(b->d_flush);
+  cudaFree(b->d_step); cudaFree(b->d_acc[0]); cudaFree(b->d_acc[1]); cudaFree(b->d_resub_sums); cudaFree(b->d_flush);
   cudaFreeHost(b->h_up); cudaFreeHost(b->h_adj); cudaFreeHost(b->h_scratch);
   for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   if (b->nccl_comm) dmv::nccl_destroy(b->nccl_comm);
@@ -255,6 +245,9 @@ int dmv_ba_set_window(dmv_ba* b, int nf, const int* slots) {
   b->ntiles = b->T * (b->T + 1) / 2;
   b->have_adj = b->have_state = b->have_tentative = b->have_committed = false;
   b->npts = b->nres = b->nchunks = 0;
+  CK(cudaSetDevice(b->device));
+  CK(cudaStreamSynchronize(b->stream));
+  for (int k = 0; k < 2; k++) CK(cudaMemset(b->d_acc[k], 0, sizeof(double) * b->acc_cap));  // accumulator layout depends on nf
   return DMV_OK;
 }
 
@@ -270,18 +263,21 @@ int dmv_ba_set_points(dmv_ba* b, int npts, const int32_t* host, const float* u, 
   CK(cudaSetDevice(b->device));
   b->npts = npts;
   b->host_of_point.assign(host, host + npts);
-  b->chunks.clear();
-  for (int s = 0; s < npts;) {
-    int e = s;
-    while (e < npts && host[e] == host[s] && e - s < b->P) e++;
-    BAChunk c; c.start = s; c.count = e - s; c.host = host[s]; c.pad = 0;
-    b->chunks.push_back(c);
-    s = e;
+  {
+    int p = 0, c = 0;
+    for (int h = 0; h < MAXF; h++) {
+      b->host_start[h] = p;
+      b->chunk_beg[h] = c;
+      int cnt = 0;
+      while (p < npts && host[p] == h) { p++; cnt++; }
+      c += (cnt + b->P - 1) / b->P;
+    }
+    b->host_start[MAXF] = npts;
+    b->chunk_beg[MAXF] = c;
+    b->nchunks = c;
   }
-  b->nchunks = (int)b->chunks.size();
   if (b->nchunks > b->max_chunks) return set_error(DMV_ERR_INVALID, "too many chunks");
   float* s = b->h_scratch;
-  CK(cudaMemcpyAsync(b->d_chunks, b->chunks.data(), sizeof(BAChunk) * b->nchunks, cudaMemcpyHostToDevice, b->stream));
   for (int i = 0; i < npts; i++) { s[2 * i] = u[i]; s[2 * i + 1] = v[i]; }
   CK(cudaMemcpyAsync(b->d_uv, s, sizeof(float2) * npts, cudaMemcpyHostToDevice, b->stream));
   CK(cudaStreamSynchronize(b->stream));
@@ -376,16 +372,15 @@ int dmv_ba_set_state(dmv_ba* b, const dmv_ba_state* st) {
 }
 
 static int enqueue_linearize(dmv_ba* b, bool with_resub) {
+  (void)with_resub;  // the resubstitute + step prologue is fused into the point kernel (it.have_x)
   fill_descriptor(b);
-  CK(cudaMemcpyAsync(b->d_up, b->h_up, sizeof(HostUpload), cudaMemcpyHostToDevice, b->stream));
-  const BAWinDev* dw = &b->d_up->win;
+  const HostUpload& U = *b->h_up;
   CK(cudaEventRecord(b->ev[0], b->stream));
-  if (with_resub) { launch_resub_kernel(dw, 1, b->npts, 1, b->stream); b->launches += 2; }
-  launch_point_kernel(dw, 1, b->nchunks, b->P, b->nf, b->stream);
+  launch_point_kernel(U.win, U.it, b->stream);
   CK(cudaEventRecord(b->ev[1], b->stream));
-  launch_reduce_kernel(dw, 1, b->nf, b->ntiles, b->stream);
-  launch_stitch_kernel(dw, 1, b->N, b->stream);
-  b->launches += 3;
+  launch_stitch_kernel(U.win, b->stream);
+  b->launches += 2;
+  b->acc_cur = 1 - b->acc_cur;
   CK(cudaEventRecord(b->ev[2], b->stream));
   CK(cudaGetLastError());
   if (b->nccl_comm) {
@@ -455,13 +450,12 @@ int dmv_ba_resubstitute(dmv_ba* b, const double* x, float* step_out, int apply, 
   CK(cudaSetDevice(b->device));
   stage_x(b, x);
   fill_descriptor(b);
-  CK(cudaMemcpyAsync(b->d_up, b->h_up, sizeof(HostUpload), cudaMemcpyHostToDevice, b->stream));
-  launch_resub_kernel(&b->d_up->win, 1, b->npts, apply, b->stream);
-  b->launches += 2;
+  CK(cudaMemsetAsync(b->d_resub_sums, 0, sizeof(double) * 4, b->stream));
+  launch_resub_kernel(b->h_up->win, b->h_up->it, apply, b->d_resub_sums, b->stream);
+  b->launches += 1;
   CK(cudaGetLastError());
-  double* tail_d = b->d_result[b->tent] + 2 * (b->N * b->N + b->N);
-  double tail[8];
-  CK(cudaMemcpyAsync(tail, tail_d, sizeof(double) * 8, cudaMemcpyDeviceToHost, b->stream));
+  double tail[8] = {0};
+  CK(cudaMemcpyAsync(tail + 4, b->d_resub_sums, sizeof(double) * 3, cudaMemcpyDeviceToHost, b->stream));
   if (step_out) CK(cudaMemcpyAsync(step_out, b->d_step, sizeof(float) * b->npts, cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   if (sums) { sums[0] = tail[4]; sums[1] = tail[5]; sums[2] = tail[6]; }
@@ -626,25 +620,23 @@ int dmv_ba_bench_device(dmv_ba* b, const double* x, int iters, int flush_l2, flo
     CK(cudaMemset(b->d_flush, 0, b->flush_n * sizeof(float4)));
   }
   if (x) stage_x(b, x); else b->h_up->it.have_x = 0;
-  fill_descriptor(b);
-  CK(cudaMemcpyAsync(b->d_up, b->h_up, sizeof(HostUpload), cudaMemcpyHostToDevice, b->stream));
-  const BAWinDev* dw = &b->d_up->win;
   std::vector<cudaEvent_t> e(3 * (size_t)iters);
-  for (auto& x : e) CK(cudaEventCreate(&x));
+  for (auto& ev : e) CK(cudaEventCreate(&ev));
   for (int i = 0; i < iters; i++) {
     if (flush_l2) launch_l2_flush(b->d_flush, b->flush_n, b->stream);
+    fill_descriptor(b);
+    const HostUpload& U = *b->h_up;
     CK(cudaEventRecord(e[3 * i], b->stream));
-    if (x) { launch_resub_kernel(dw, 1, b->npts, 1, b->stream); b->launches += 2; }
-    launch_point_kernel(dw, 1, b->nchunks, b->P, b->nf, b->stream);
+    launch_point_kernel(U.win, U.it, b->stream);
     CK(cudaEventRecord(e[3 * i + 1], b->stream));
-    launch_reduce_kernel(dw, 1, b->nf, b->ntiles, b->stream);
-    launch_stitch_kernel(dw, 1, b->N, b->stream);
+    launch_stitch_kernel(U.win, b->stream);
+    b->acc_cur = 1 - b->acc_cur;
     if (b->nccl_comm) {
       rc = dmv::nccl_allreduce_double(b->nccl_comm, b->d_result[b->tent], result_doubles(b->N), b->stream);
       if (rc != DMV_OK) return rc;
     }
     CK(cudaEventRecord(e[3 * i + 2], b->stream));
-    b->launches += 3;
+    b->launches += 2;
   }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(b->stream));
@@ -679,7 +671,7 @@ int dmv_ba_comm_init(dmv_ba* b, int nranks, int rank, const void* id) {
 
 extern "C" int dmv_ba_io_bytes(dmv_ba* b, long long* h2d, long long* d2h) {
   if (!b || !h2d || !d2h) return set_error(DMV_ERR_INVALID, "null argument");
-  *h2d = (long long)sizeof(HostUpload);                        // descriptor + per-iteration tables, one pinned copy
+  *h2d = (long long)sizeof(HostUpload);                        // descriptor + per-iteration tables, carried as kernel parameters
   *d2h = (long long)sizeof(double) * result_doubles(b->N);     // H_A, b_A, H_sc, b_sc, energy + counters
   return DMV_OK;
 }

@@ -1,6 +1,6 @@
-// Device-side data layout of one sliding window.  Everything the BA kernels touch is reachable from
-// one BAWinDev descriptor that lives in device memory, so that (a) a CUDA graph can be replayed without patching
-// kernel arguments and (b) several independent windows can be processed by one launch (blockIdx.y = window).
+// Device-side data layout of one sliding window.
+// The window descriptor (BAWinDev, ~0.5 KB) and the per-iteration tables (BAIter, ~10.6 KB) travel as
+// __grid_constant__ kernel parameters: no H2D copy node, no dependent global load before the first useful load.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -10,11 +10,12 @@ namespace dmv {
 constexpr int MAXF = 8;             // DMV_MAX_FRAMES
 constexpr int TOP_ROWS = 10;        // geometric rows [C4 | xi6] of the 13x13 pair block
 constexpr int TOP_COLS = 13;
-constexpr int TOP_PART = TOP_ROWS * TOP_COLS + 6;  // 136 floats: 10 full rows + 6 bottom-right (a,b,r) entries
+constexpr int TOP_PART = TOP_ROWS * TOP_COLS + 6;  // 136: 10 full rows + 6 bottom-right (a,b,r) entries
 constexpr int REC = 16;             // per (point,target) record kept in shared memory
 constexpr int RES_NONE = 255, RES_IN = 0, RES_OOB = 1, RES_OUTLIER = 2;
+constexpr int ACC_MISC = 8;         // energy, n_in, n_oob, n_outlier, sum step^2, sum |idepth_backup|, npts, pad
 
-// per-iteration parameter block (host -> device every GN iteration; ~11 KB at nf = 8)
+// per-iteration parameter block
 struct BAIter {
   float calib[8];                 // fxl fyl cxl cyl fxli fyli cxli cyli
   float TH[MAXF];                 // frameEnergyTH
@@ -33,22 +34,19 @@ struct BAAdj {
   double adTdiag[MAXF * MAXF][8];
 };
 
-struct BAChunk { int start, count, host, pad; };
-
 struct BAWinDev {
-  int nf, npts, nchunks, w, h, N, NW, T, ntiles, mp;  // mp = capacity (row pitch of the [target][point] slot arrays)
+  int nf, npts, nchunks, w, h, N, NW, T, ntiles, mp, P;  // mp = capacity (row pitch of the [target][point] slot arrays)
   float huberTH, outlierTHSum;
   int zeroA, zeroB;
+  int host_start[MAXF + 1];  // points of host h are [host_start[h], host_start[h+1])
+  int chunk_beg[MAXF + 1];   // chunks (CTAs) of host h are [chunk_beg[h], chunk_beg[h+1]); chunk c covers P consecutive points
   const float4* img[MAXF];   // per window frame index: level-0 texels (I, dx, dy, 0)
-  const BAIter* it;
   const BAAdj* adj;
-  const BAChunk* chunks;
-  int chunk_beg[MAXF + 1];   // chunks of host h are [chunk_beg[h], chunk_beg[h+1])
   // points
   const float2* uv;
   float* idepth;
   float* idepth_zero;
-  float* idepth_backup;
+  const float* idepth_backup;
   const float* color;        // [p][8]
   const float* weights;      // [p][8]
   const float* priorF;
@@ -58,7 +56,7 @@ struct BAWinDev {
   uint8_t* st_new;           // tentative outputs of this linearisation
   float* en_new;
   float* en_wo;
-  float* cpt;                // [slot][3]  (stored as 3 planes: [k][slot])
+  float* cpt;                // 3 planes [k][slot]
   float* jpjd;               // [slot][8]
   float* pout;               // [p][8]: Hdd bd Hcd[4] HdiF bdSum
   // committed copies (read by resubstitute)
@@ -66,16 +64,13 @@ struct BAWinDev {
   const float* c_jpjd;
   const float* c_pout;
   float* step;               // [p]
-  // partials / sums / result
-  float* top_part;           // [chunk][t][TOP_PART]
-  float* sc_part;            // [chunk][tile][16]
-  float* misc_part;          // [chunk][t][4] : energy, n_in, n_oob, n_outlier
-  double* step_part;         // [chunk][2] : sum step^2, sum |idepth_backup|
-  double* top_sum;           // [h*nf + t][TOP_PART]
-  double* sc_sum;            // [tile][16]
-  double* result;            // H_top N*N | b_top N | H_sc N*N | b_sc N | energy, n_in, n_oob, n_outl, sum step^2, sum |id_backup|, npts, pad
+  // fp64 accumulators: [nf*nf*TOP_PART top | ntiles*16 schur tiles | ACC_MISC]
+  double* acc;               // accumulated into by this iteration's point kernel, consumed by its stitch kernel
+  double* acc_next;          // zeroed by this iteration's stitch kernel for the next iteration
+  double* result;            // H_top N*N | b_top N | H_sc N*N | b_sc N | ACC_MISC tail
 };
 
-inline __host__ __device__ int result_doubles(int N) { return 2 * (N * N + N) + 8; }
+inline __host__ __device__ int result_doubles(int N) { return 2 * (N * N + N) + ACC_MISC; }
+inline __host__ __device__ int acc_doubles(int nf, int ntiles) { return nf * nf * TOP_PART + ntiles * 16 + ACC_MISC; }
 
 }  // namespace dmv

@@ -1,17 +1,20 @@
 // sm_100a kernels of the bundle-adjustment hot path.
 //
 //   ba_point_kernel     one CTA = one chunk of P points of one host frame; warp t = target frame t.
+//                       prologue: cp.async staging of the chunk's point records, residual states and the host's adjoint
+//                                 blocks into shared memory; optional fused EnergyFunctional::resubstituteFPt + point step
 //                       phase A: 8 lanes per (point,target) residual = the 8 pattern pixels: project, 4-tap float4 gather
-//                                from the L2-resident target plane, Huber-weighted residual, 8-lane butterfly reductions,
+//                                from the target plane, Huber-weighted residual, 8-lane butterfly reductions,
 //                                register-resident rows of the pair's 13x13 block      (Residuals.cpp:L78-274 +
 //                                AccumulatedTopHessian.cpp:L39-159 fused; the 304-byte RawResidualJacobian never exists)
 //                       phase B: per-point Hdd/bd/Hcd, HdiF, and the point's Schur vector in ABSOLUTE frame coordinates
 //                                w_p = [Hcd | sum_t adHost v_t | adTarget v_t ... | bdSum]
 //                       phase C: weighted Gram  sum_p HdiF w_p w_p^T  in 4x4 register tiles  (replaces the nf^3 accD blocks of
 //                                AccumulatedSCHessian.cpp:L34-157)
-//   ba_reduce_kernel    deterministic fp64 reduction of the per-chunk partials
-//   ba_stitch_kernel    adjoint products to the dense (8nf+4)^2 system in fp64 (AccumulatedTopHessian.cpp:L241-303)
-//   ba_resub_kernel     EnergyFunctional::resubstituteFPt + point part of doStepFromBackup
+//                       all block results go to fp64 global accumulators with red.global.add.f64 (no partial buffers)
+//   ba_stitch_kernel    adjoint products to the dense (8nf+4)^2 system in fp64 (AccumulatedTopHessian.cpp:L241-303, gather form);
+//                       also zeroes the accumulator set of the next iteration
+//   ba_resub_kernel     stand-alone EnergyFunctional::resubstituteFPt + point part of doStepFromBackup
 #include "ba_device.cuh"
 #include <math.h>
 
@@ -28,7 +31,6 @@ __device__ __forceinline__ float pick8(const float* v, int j) {
   float f = (j & 2) ? d : c;
   return (j & 4) ? f : e;
 }
-
 __device__ __forceinline__ float group_sum8(float v) {  // all-reduce inside aligned groups of 8 lanes
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -40,40 +42,130 @@ __device__ __forceinline__ float cross_group_sum(float v) {  // sum over the 4 g
   v += __shfl_xor_sync(0xffffffffu, v, 16);
   return v;
 }
+__device__ __forceinline__ void cp_async4(void* smem, const void* g) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(g));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); }  // result unused -> RED.E.ADD.F64
+
+// EnergyFunctional::resubstituteFPt for one point (EnergyFunctional.cpp:L295-321)
+__device__ __forceinline__ float resub_point(const BAWinDev& W, const BAIter& it, int p, int h) {
+  const int nf = W.nf, mp = W.mp;
+  const float4 po0 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8));
+  const float4 po1 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8) + 1);
+  float b = po1.w;  // bdSumF
+  b -= it.xc[0] * po0.z + it.xc[1] * po0.w + it.xc[2] * po1.x + it.xc[3] * po1.y;
+  int ngood = 0;
+  for (int t = 0; t < nf; t++) {
+    if (t == h) continue;
+    const int slot = t * mp + p;
+    if (W.c_st[slot] != RES_IN) continue;
+    ngood++;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)slot * 8));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)slot * 8) + 1);
+    const float* xa = it.xAd[h * nf + t];
+    b -= xa[0] * a0.x + xa[1] * a0.y + xa[2] * a0.z + xa[3] * a0.w + xa[4] * a1.x + xa[5] * a1.y + xa[6] * a1.z + xa[7] * a1.w;
+  }
+  return ngood > 0 ? -b * po1.z : 0.f;  // step = -b * HdiF
+}
 
 template <int P>
-__global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __restrict__ wins) {
-  const BAWinDev& W = wins[blockIdx.y];
-  if ((int)blockIdx.x >= W.nchunks) return;
+__global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const __grid_constant__ BAWinDev W, const __grid_constant__ BAIter it) {
   const int nf = W.nf;
-  const BAChunk ch = W.chunks[blockIdx.x];
-  const int h = ch.host;
+  int h = 0;
+  while (h < nf - 1 && (int)blockIdx.x >= W.chunk_beg[h + 1]) h++;
+  const int ch_start = W.host_start[h] + ((int)blockIdx.x - W.chunk_beg[h]) * P;
+  const int ch_count = min(P, W.host_start[h + 1] - ch_start);
   const int tid = threadIdx.x;
   const int nthreads = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int mp = W.mp;
+  double* __restrict__ acc = W.acc;
 
   __shared__ __align__(16) float s_rec[P][MAXF][REC];
   __shared__ __align__(16) float s_W[P][8 * MAXF + 8];
   __shared__ float s_hdi[P];
   __shared__ __align__(16) float s_adH[MAXF][64];
-  __shared__ float s_adT[MAXF][8];
+  __shared__ __align__(16) float s_adT[MAXF][8];
+  __shared__ __align__(16) float2 s_uv[P];
+  __shared__ float s_id[P], s_idz[P], s_prior[P];
+  __shared__ __align__(16) float s_col[P][8];
+  __shared__ __align__(16) float s_wgt[P][8];
+  __shared__ float s_en[MAXF][P];
+  __shared__ uint8_t s_st[MAXF][P];
+  __shared__ float s_misc[MAXF][4];
 
-  const BAIter* __restrict__ it = W.it;
-  for (int i = tid; i < nf * 64; i += nthreads) s_adH[i >> 6][i & 63] = W.adj->adHostF[h * nf + (i >> 6)][i & 63];
-  for (int i = tid; i < nf * 8; i += nthreads) s_adT[i >> 3][i & 7] = W.adj->adTdiagF[h * nf + (i >> 3)][i & 7];
-  for (int i = tid; i < P * MAXF * REC; i += nthreads) (&s_rec[0][0][0])[i] = 0.f;
+  // ---------------------------------------------------------------- prologue: stage inputs (one DRAM round trip)
+  {
+    const BAAdj* __restrict__ A = W.adj;
+    for (int i = tid; i < nf * 16; i += nthreads) cp_async16(&s_adH[i >> 4][(i & 15) * 4], &A->adHostF[h * nf + (i >> 4)][(i & 15) * 4]);
+    for (int i = tid; i < nf * 2; i += nthreads) cp_async16(&s_adT[i >> 1][(i & 1) * 4], &A->adTdiagF[h * nf + (i >> 1)][(i & 1) * 4]);
+    for (int i = tid; i < ch_count * 2; i += nthreads) cp_async4(reinterpret_cast<float*>(s_uv) + i, reinterpret_cast<const float*>(W.uv + ch_start) + i);
+    for (int i = tid; i < ch_count * 8; i += nthreads) {
+      cp_async4(&s_col[0][0] + i, W.color + (size_t)ch_start * 8 + i);
+      cp_async4(&s_wgt[0][0] + i, W.weights + (size_t)ch_start * 8 + i);
+    }
+    for (int i = tid; i < ch_count; i += nthreads) cp_async4(&s_prior[i], W.priorF + ch_start + i);
+    if (!it.have_x)
+      for (int i = tid; i < ch_count; i += nthreads) {
+        cp_async4(&s_id[i], W.idepth + ch_start + i);
+        cp_async4(&s_idz[i], W.idepth_zero + ch_start + i);
+      }
+    for (int i = tid; i < nf * ch_count; i += nthreads) {
+      const int tt = i / ch_count, pl = i - tt * ch_count;
+      cp_async4(&s_en[tt][pl], W.en_in + (size_t)tt * mp + ch_start + pl);
+      s_st[tt][pl] = W.st_in[(size_t)tt * mp + ch_start + pl];
+    }
+    for (int i = tid; i < P * MAXF * REC; i += nthreads) (&s_rec[0][0][0])[i] = 0.f;
+    for (int i = tid; i < P * (8 * MAXF + 8); i += nthreads) (&s_W[0][0])[i] = 0.f;
+    if (tid < MAXF * 4) (&s_misc[0][0])[tid] = 0.f;
+    if (it.have_x && warp == 0) {
+      // fused resubstitute + point part of doStepFromBackup (FullSystemOptimize.cpp:L264-272; DM-VIO also moves idepth_zero)
+      float step2 = 0.f, nid = 0.f;
+      if (tid < ch_count) {
+        const int p = ch_start + tid;
+        const float step = resub_point(W, it, p, h);
+        const float idb = __ldg(W.idepth_backup + p);
+        const float v = idb + step;
+        W.step[p] = step;
+        W.idepth[p] = v;
+        W.idepth_zero[p] = v;
+        s_id[tid] = v;
+        s_idz[tid] = v;
+        step2 = step * step;
+        nid = fabsf(idb);
+      }
+#pragma unroll
+      for (int m = 1; m < 32; m <<= 1) {
+        step2 += __shfl_xor_sync(0xffffffffu, step2, m);
+        nid += __shfl_xor_sync(0xffffffffu, nid, m);
+      }
+      if (lane == 0) {  // the sums feed only the convergence test of doStepFromBackup
+        double* m = acc + (size_t)nf * nf * TOP_PART + (size_t)W.ntiles * 16;
+        red_add(m + 4, (double)step2);
+        red_add(m + 5, (double)nid);
+        red_add(m + 6, (double)ch_count);
+      }
+    }
+    cp_async_wait_all();
+  }
   __syncthreads();
 
   // ---------------------------------------------------------------- phase A
   const int t = warp;  // target frame of this warp
   if (t < nf && t != h) {
     const int g = lane >> 3, j = lane & 7;
-    const float* __restrict__ pc = it->precalc[h * nf + t];
-    const float fx = it->calib[0], fy = it->calib[1], cx = it->calib[2], cy = it->calib[3];
-    const float fxi = it->calib[4], fyi = it->calib[5], cxi = it->calib[6], cyi = it->calib[7];
-    (void)cxi; (void)cyi;
-    const float TH = fmaxf(it->TH[h], it->TH[t]);
+    const float* pc = it.precalc[h * nf + t];
+    const float fx = it.calib[0], fy = it.calib[1], cx = it.calib[2], cy = it.calib[3];
+    const float fxi = it.calib[4], fyi = it.calib[5];
+    const float TH = fmaxf(it.TH[h], it.TH[t]);
     const float wM3 = (float)(W.w - 3), hM3 = (float)(W.h - 3);
     const float4* __restrict__ img = W.img[t];
     const int iw = W.w;
@@ -81,6 +173,8 @@ __global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __r
     const float KRKi0 = pc[0], KRKi1 = pc[1], KRKi2 = pc[2], KRKi3 = pc[3], KRKi4 = pc[4], KRKi5 = pc[5], KRKi6 = pc[6], KRKi7 = pc[7],
                 KRKi8 = pc[8];
     const float Kt0 = pc[9], Kt1 = pc[10], Kt2 = pc[11];
+    const float R00 = pc[12], R01 = pc[13], R02 = pc[14], R10 = pc[15], R11 = pc[16], R12 = pc[17], R20 = pc[18], R21 = pc[19], R22 = pc[20];
+    const float t00 = pc[21], t01 = pc[22], t02 = pc[23];
     const float affa = pc[24], affb = pc[25], b0 = pc[26];
     const int pdx = c_pattern[j][0], pdy = c_pattern[j][1];
 
@@ -92,25 +186,24 @@ __global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __r
     float e_sum = 0.f;
     int n_in = 0, n_oob = 0, n_outl = 0;
 
-    for (int base = 0; base < ch.count; base += 4) {
-      const int pl = base + g;
-      const bool valid = pl < ch.count;
-      const int p = ch.start + (valid ? pl : ch.count - 1);
-      const int slot = t * mp + p;
-      const int st = valid ? (int)W.st_in[slot] : RES_NONE;
+    for (int base = 0; base < ch_count; base += 4) {
+      const int pl = min(base + g, ch_count - 1);
+      const bool valid = base + g < ch_count;
+      const int slot = t * mp + ch_start + pl;
+      const int st = valid ? (int)s_st[t][pl] : RES_NONE;
       bool live = (st != RES_NONE) && (st != RES_OOB);
 
-      const float2 uv = W.uv[p];
-      const float idepth = W.idepth[p];
-      const float idz = W.idepth_zero[p];
-      const float col = W.color[p * 8 + j];
-      const float wgt = W.weights[p * 8 + j];
+      const float2 uv = s_uv[pl];
+      const float idepth = s_id[pl];
+      const float idz = s_idz[pl];
+      const float col = s_col[pl][j];
+      const float wgt = s_wgt[pl][j];
 
       // ---- centre pixel at the FEJ point (ResidualProjections.h:L62-87, Residuals.cpp:L108-157)
       const float Kl0 = (uv.x - cx) * fxi, Kl1 = (uv.y - cy) * fyi;
-      const float q0 = pc[12] * Kl0 + pc[13] * Kl1 + pc[14] + pc[21] * idz;
-      const float q1 = pc[15] * Kl0 + pc[16] * Kl1 + pc[17] + pc[22] * idz;
-      const float q2 = pc[18] * Kl0 + pc[19] * Kl1 + pc[20] + pc[23] * idz;
+      const float q0 = R00 * Kl0 + R01 * Kl1 + R02 + t00 * idz;
+      const float q1 = R10 * Kl0 + R11 * Kl1 + R12 + t01 * idz;
+      const float q2 = R20 * Kl0 + R21 * Kl1 + R22 + t02 * idz;
       const float drescale = 1.0f / q2;
       const float new_idepth = idz * drescale;
       const float cu = q0 * drescale, cv = q1 * drescale;
@@ -154,7 +247,7 @@ __global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __r
       hw = hw * w;
       if (!live) { hw = 0.f; e_px = 0.f; }
       const float gx = h1 * hw, gy = h2 * hw;
-      const float resF = residual * hw;
+      const float resF = live ? residual * hw : 0.f;
       const float ja = drdA * hw, jb = hw;
       const float jaF = W.zeroA ? 0.f : ja, jbF = W.zeroB ? 0.f : jb;
 
@@ -166,45 +259,24 @@ __global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __r
       const float rr = group_sum8(resF * resF);
       const float energy = group_sum8(e_px);
       // the reference sums hw*hw*(hitColor[1]^2+hitColor[2]^2) with hitColor already multiplied by hw (Residuals.cpp:L217-244)
-      const float wJI2_ref = group_sum8(hw * hw * (gx * gx + gy * gy));
+      const float wJI2 = group_sum8(hw * hw * (gx * gx + gy * gy));
 
       // ---- classification (Residuals.cpp:L260-273) and per-residual outputs
       int newState;
-      float newEnergy, ret;
+      float newEnergy;
       if (st == RES_NONE) {
-        newState = RES_NONE; newEnergy = 0.f; ret = 0.f;
+        newState = RES_NONE; newEnergy = 0.f;
       } else if (!live) {
-        newState = RES_OOB; newEnergy = W.en_in[slot]; ret = newEnergy;  // OOB exits return the old state_energy
-      } else if (energy > TH || wJI2_ref < 2.f) {
-        newState = RES_OUTLIER; newEnergy = TH; ret = TH;
+        newState = RES_OOB; newEnergy = s_en[t][pl];  // OOB exits return the old state_energy
+      } else if (energy > TH || wJI2 < 2.f) {
+        newState = RES_OUTLIER; newEnergy = TH;
       } else {
-        newState = RES_IN; newEnergy = energy; ret = energy;
+        newState = RES_IN; newEnergy = energy;
       }
       const bool in = (newState == RES_IN);
-
-      // geometric Jacobians of the centre pixel (Residuals.cpp:L113-156): x = d(Ku)/d[C4|xi6], y = d(Kv)/d[C4|xi6]
-      float x[10], y[10];
-      {
-        const float R00 = pc[12], R01 = pc[13], R10 = pc[15], R11 = pc[16], R20 = pc[18], R21 = pc[19];
-        float dCx2 = drescale * (R20 * cu - R00);
-        float dCx3 = fx * drescale * (R21 * cu - R01) * fyi;
-        float dCx0 = Kl0 * dCx2;
-        float dCx1 = Kl1 * dCx3;
-        float dCy2 = fy * drescale * (R20 * cv - R10) * fxi;
-        float dCy3 = drescale * (R21 * cv - R11);
-        float dCy0 = Kl0 * dCy2;
-        float dCy1 = Kl1 * dCy3;
-        x[0] = (dCx0 + cu) * 50.0f; x[1] = dCx1 * 50.0f; x[2] = (dCx2 + 1.f) * 50.0f; x[3] = dCx3 * 50.0f;
-        y[0] = dCy0 * 50.0f; y[1] = (dCy1 + cv) * 50.0f; y[2] = dCy2 * 50.0f; y[3] = (dCy3 + 1.f) * 50.0f;
-        x[4] = new_idepth * fx; x[5] = 0.f; x[6] = -new_idepth * cu * fx; x[7] = -cu * cv * fx; x[8] = (1.f + cu * cu) * fx; x[9] = -cv * fx;
-        y[4] = 0.f; y[5] = new_idepth * fy; y[6] = -new_idepth * cv * fy; y[7] = -(1.f + cv * cv) * fy; y[8] = cu * cv * fy; y[9] = cu * fy;
-      }
-      const float ddx = drescale * (pc[21] - pc[23] * cu) * fx;  // Jpdd (SCALE_IDEPTH = 1)
-      const float ddy = drescale * (pc[22] - pc[23] * cv) * fy;
-
-      if (st != RES_NONE) {
-        e_sum += (j == 0) ? ret : 0.f;
-        if (j == 0) { n_in += in; n_oob += (newState == RES_OOB); n_outl += (newState == RES_OUTLIER); }
+      if (j == 0 && st != RES_NONE) {
+        e_sum += newEnergy;
+        n_in += in; n_oob += (newState == RES_OOB); n_outl += (newState == RES_OUTLIER);
       }
       if (valid && j == 0) {
         W.st_new[slot] = (uint8_t)newState;
@@ -215,6 +287,20 @@ __global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __r
       }
 
       if (in) {
+        // geometric Jacobians of the centre pixel (Residuals.cpp:L113-156): x = d(Ku)/d[C4|xi6], y = d(Kv)/d[C4|xi6]
+        float x[10], y[10];
+        {
+          const float dCx2 = drescale * (R20 * cu - R00);
+          const float dCx3 = fx * drescale * (R21 * cu - R01) * fyi;
+          const float dCy2 = fy * drescale * (R20 * cv - R10) * fxi;
+          const float dCy3 = drescale * (R21 * cv - R11);
+          x[0] = (Kl0 * dCx2 + cu) * 50.0f; x[1] = (Kl1 * dCx3) * 50.0f; x[2] = (dCx2 + 1.f) * 50.0f; x[3] = dCx3 * 50.0f;
+          y[0] = (Kl0 * dCy2) * 50.0f; y[1] = (Kl1 * dCy3 + cv) * 50.0f; y[2] = dCy2 * 50.0f; y[3] = (dCy3 + 1.f) * 50.0f;
+          x[4] = new_idepth * fx; x[5] = 0.f; x[6] = -new_idepth * cu * fx; x[7] = -cu * cv * fx; x[8] = (1.f + cu * cu) * fx; x[9] = -cv * fx;
+          y[4] = 0.f; y[5] = new_idepth * fy; y[6] = -new_idepth * cv * fy; y[7] = -(1.f + cv * cv) * fy; y[8] = cu * cv * fy; y[9] = cu * fy;
+        }
+        const float ddx = drescale * (t00 - t02 * cu) * fx;  // Jpdd (SCALE_IDEPTH = 1)
+        const float ddy = drescale * (t01 - t02 * cv) * fy;
         // EFResidual::takeDataF (EnergyFunctionalStructs.cpp:L39-49) and the per-point terms of addPoint (AccumulatedTopHessian.cpp:L131-135)
         const float J0 = JI00 * ddx + JI10 * ddy, J1 = JI10 * ddx + JI11 * ddy;  // JIdx2 * Jpdd
         if (j == 0) {
@@ -254,19 +340,19 @@ __global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __r
         br[0] += Jab00; br[1] += Jab01; br[2] += Jabr0; br[3] += Jab11; br[4] += Jabr1; br[5] += rr;
       }
     }
-    // ---- cross-group reduction and per-(chunk,target) partial store
-    float* tp = W.top_part + ((size_t)blockIdx.x * MAXF + t) * TOP_PART;
+    // ---- cross-group reduction, then fp64 reductions into the pair's global accumulator
+    double* tp = acc + (size_t)(h * nf + t) * TOP_PART;
 #pragma unroll
     for (int c = 0; c < TOP_COLS; c++) {
       const float a1 = cross_group_sum(acc1[c]);
       const float a2 = cross_group_sum(acc2[c]);
-      if (lane < 8) tp[lane * TOP_COLS + c] = a1;
-      if (lane < 2) tp[(8 + lane) * TOP_COLS + c] = a2;
+      if (lane < 8) red_add(tp + lane * TOP_COLS + c, (double)a1);
+      if (lane < 2) red_add(tp + (8 + lane) * TOP_COLS + c, (double)a2);
     }
 #pragma unroll
     for (int c = 0; c < 6; c++) {
       const float b = cross_group_sum(br[c]);
-      if (lane == 0) tp[TOP_ROWS * TOP_COLS + c] = b;
+      if (lane == 0) red_add(tp + TOP_ROWS * TOP_COLS + c, (double)b);
     }
     float es = e_sum, fin = (float)n_in, foob = (float)n_oob, fout = (float)n_outl;
 #pragma unroll
@@ -276,26 +362,19 @@ __global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __r
       foob += __shfl_xor_sync(0xffffffffu, foob, m);
       fout += __shfl_xor_sync(0xffffffffu, fout, m);
     }
-    if (lane == 0) {
-      float4 m4; m4.x = es; m4.y = fin; m4.z = foob; m4.w = fout;
-      reinterpret_cast<float4*>(W.misc_part)[(size_t)blockIdx.x * MAXF + t] = m4;
-    }
-  } else {
-    // the host's own warp: zero its partial slot so the reduction needs no masks
-    if (t < MAXF) {
-      float* tp = W.top_part + ((size_t)blockIdx.x * MAXF + t) * TOP_PART;
-      for (int i = lane; i < TOP_PART; i += 32) tp[i] = 0.f;
-      if (lane == 0) reinterpret_cast<float4*>(W.misc_part)[(size_t)blockIdx.x * MAXF + t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    if (lane == 0) { s_misc[t][0] = es; s_misc[t][1] = fin; s_misc[t][2] = foob; s_misc[t][3] = fout; }
   }
   __syncthreads();
+  if (tid < 4) {
+    double s = 0.0;
+    for (int tt = 0; tt < nf; tt++) s += (double)s_misc[tt][tid];
+    red_add(acc + (size_t)nf * nf * TOP_PART + (size_t)W.ntiles * 16 + tid, s);
+  }
 
   // ---------------------------------------------------------------- phase B
-  const int N = W.N, NW = W.NW;
-  for (int i = tid; i < P * (8 * MAXF + 8); i += nthreads) (&s_W[0][0])[i] = 0.f;
-  __syncthreads();
-  for (int pl = tid; pl < ch.count; pl += nthreads) {  // AccumulatedSCHessian.cpp:L36-58
-    const int p = ch.start + pl;
+  const int N = W.N;
+  for (int pl = tid; pl < ch_count; pl += nthreads) {  // AccumulatedSCHessian.cpp:L36-58
+    const int p = ch_start + pl;
     float Hdd = 0.f, bd = 0.f, Hcd0 = 0.f, Hcd1 = 0.f, Hcd2 = 0.f, Hcd3 = 0.f;
     int ngood = 0;
     for (int tt = 0; tt < nf; tt++) {
@@ -307,11 +386,11 @@ __global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __r
     }
     float HdiF = 0.f, bdSum = 0.f;
     if (ngood > 0) {
-      const float prior = W.priorF[p];
+      const float prior = s_prior[pl];
       float H = Hdd + prior;
       if (H < 1e-10f) H = 1e-10f;
       HdiF = 1.0f / H;
-      bdSum = bd + prior * (W.idepth[p] - W.idepth_zero[p]);
+      bdSum = bd + prior * (s_id[pl] - s_idz[pl]);
       s_W[pl][0] = Hcd0; s_W[pl][1] = Hcd1; s_W[pl][2] = Hcd2; s_W[pl][3] = Hcd3;
       s_W[pl][N] = bdSum;
     }
@@ -320,7 +399,7 @@ __global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __r
     po[0] = make_float4(Hdd, bd, Hcd0, Hcd1);
     po[1] = make_float4(Hcd2, Hcd3, HdiF, bdSum);
   }
-  for (int idx = tid; idx < ch.count * nf * 8; idx += nthreads) {
+  for (int idx = tid; idx < ch_count * nf * 8; idx += nthreads) {
     const int k = idx & 7;
     const int f = (idx >> 3) % nf;
     const int pl = (idx >> 3) / nf;
@@ -344,7 +423,7 @@ __global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __r
 
   // ---------------------------------------------------------------- phase C
   const int T = W.T;
-  float* scp = W.sc_part + (size_t)blockIdx.x * W.ntiles * 16;
+  double* scp = acc + (size_t)nf * nf * TOP_PART;
   for (int tile = tid; tile < W.ntiles; tile += nthreads) {
     int ti = 0, rem = tile;
     while (rem >= T - ti) { rem -= T - ti; ti++; }
@@ -354,7 +433,7 @@ __global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __r
     for (int r = 0; r < 4; r++)
 #pragma unroll
       for (int c = 0; c < 4; c++) a[r][c] = 0.f;
-    for (int pl = 0; pl < ch.count; pl++) {
+    for (int pl = 0; pl < ch_count; pl++) {
       const float s = s_hdi[pl];
       const float4 wi = *reinterpret_cast<const float4*>(&s_W[pl][4 * ti]);
       const float4 wj = *reinterpret_cast<const float4*>(&s_W[pl][4 * tj]);
@@ -365,49 +444,16 @@ __global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const BAWinDev* __r
 #pragma unroll
         for (int c = 0; c < 4; c++) a[r][c] += si[r] * vj[c];
     }
-    float4* o = reinterpret_cast<float4*>(scp + (size_t)tile * 16);
+    double* o = scp + (size_t)tile * 16;
 #pragma unroll
-    for (int r = 0; r < 4; r++) o[r] = make_float4(a[r][0], a[r][1], a[r][2], a[r][3]);
-  }
-  (void)NW;
-}
-
-template __global__ void ba_point_kernel<8>(const BAWinDev*);
-template __global__ void ba_point_kernel<16>(const BAWinDev*);
-template __global__ void ba_point_kernel<32>(const BAWinDev*);
-
-// ---------------------------------------------------------------------------------------------------------------
-// fp64 reduction of the per-chunk partials.  entry space: [nf*nf*TOP_PART | ntiles*16 | 4 misc]
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ba_reduce_kernel(const BAWinDev* __restrict__ wins) {
-  const BAWinDev& W = wins[blockIdx.y];
-  const int nf = W.nf;
-  const int nTop = nf * nf * TOP_PART, nSc = W.ntiles * 16;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < nTop) {
-    const int pair = e / TOP_PART, k = e - pair * TOP_PART;
-    const int h = pair / nf, t = pair - h * nf;
-    double s = 0.0;
-    const int c0 = W.chunk_beg[h], c1 = W.chunk_beg[h + 1];
-    const float* p = W.top_part + ((size_t)c0 * MAXF + t) * TOP_PART + k;
-    for (int c = c0; c < c1; c++, p += (size_t)MAXF * TOP_PART) s += (double)*p;
-    W.top_sum[e] = s;
-  } else if (e < nTop + nSc) {
-    const int k = e - nTop;
-    double s = 0.0;
-    const float* p = W.sc_part + k;
-    for (int c = 0; c < W.nchunks; c++, p += (size_t)nSc) s += (double)*p;
-    W.sc_sum[k] = s;
-  } else if (e < nTop + nSc + 4) {
-    const int k = e - nTop - nSc;
-    double s = 0.0;
-    for (int c = 0; c < W.nchunks; c++)
-      for (int t = 0; t < nf; t++) s += (double)W.misc_part[((size_t)c * MAXF + t) * 4 + k];
-    W.result[2 * (W.N * W.N + W.N) + k] = s;
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) red_add(o + r * 4 + c, (double)a[r][c]);
   }
 }
 
-// 13x13 pair block from the 136-float layout (rows 0..9 full, then the 6 bottom-right entries)
+
+// 13x13 pair block from the 136-double layout (rows 0..9 full, then the 6 bottom-right entries)
 __device__ __forceinline__ double h13(const double* S, int r, int c) {
   if (r > c) { int tmp = r; r = c; c = tmp; }
   if (r < TOP_ROWS) return S[r * TOP_COLS + c];
@@ -415,142 +461,144 @@ __device__ __forceinline__ double h13(const double* S, int r, int c) {
   return S[TOP_ROWS * TOP_COLS + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5))];
 }
 
-// One thread per entry of [H_top | b_top] and [H_sc | b_sc]  (AccumulatedTopHessian.cpp:L241-303 in gather form).
-__global__ void __launch_bounds__(256) ba_stitch_kernel(const BAWinDev* __restrict__ wins) {
-  const BAWinDev& W = wins[blockIdx.y];
+// Stitch to the dense system (AccumulatedTopHessian.cpp:L241-303 in gather form).  One CTA per block-row of the
+// (8nf+4)^2 matrix: CTA a < nf owns the 8 rows of frame a, CTA nf owns the 4 calibration rows.  All operands of a
+// block-row (the 2(nf-1) pair blocks touching frame a and their adjoints) are staged in shared memory with one
+// coalesced pass, the 8x8 triple products are formed cooperatively as  Ah * (P * Ah^T), everything in fp64.
+constexpr int ST_THREADS = 256;
+__global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_constant__ BAWinDev W) {
   const int nf = W.nf, N = W.N;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= N * (N + 1)) return;
-  const int I = e / (N + 1), J = e - I * (N + 1);  // J == N : right-hand side b
-  const BAAdj* __restrict__ A = W.adj;
-  const double* __restrict__ TS = W.top_sum;
+  const int tid = threadIdx.x;
+  const int a = blockIdx.x;  // frame index, or nf for the calibration rows
+  const int gt = blockIdx.x * blockDim.x + tid, gthreads = gridDim.x * blockDim.x;
+  const int nacc = acc_doubles(nf, W.ntiles);
+  for (int i = gt; i < nacc; i += gthreads) W.acc_next[i] = 0.0;  // accumulators of the next iteration
+  const double* __restrict__ TS = W.acc;
+  const double* __restrict__ SC = W.acc + (size_t)nf * nf * TOP_PART;
   double* __restrict__ R = W.result;
+  double* __restrict__ Rsc = R + (size_t)(N * N + N);
+  if (gt < ACC_MISC) R[2 * (size_t)(N * N + N) + gt] = SC[(size_t)W.ntiles * 16 + gt];
+  const BAAdj* __restrict__ A = W.adj;
 
-  // ---- Schur part straight from the Gram tiles
+  // ---- Schur part: rows of this CTA straight from the Gram tiles
   {
-    int r = I, c = J;
-    if (c < N && r > c) { int tmp = r; r = c; c = tmp; }
-    const int ti = r >> 2, tj = c >> 2;
-    const int tile = ti * W.T - (ti * (ti - 1)) / 2 + (tj - ti);
-    const double v = W.sc_sum[(size_t)tile * 16 + (r & 3) * 4 + (c & 3)];
-    if (J < N) R[(size_t)(N * N + N) + (size_t)I * N + J] = v;
-    else R[(size_t)(N * N + N) + (size_t)N * N + I] = v;
+    const int r0 = (a < nf) ? 4 + 8 * a : 0, nr = (a < nf) ? 8 : 4;
+    for (int e = tid; e < nr * (N + 1); e += ST_THREADS) {
+      const int I = r0 + e / (N + 1), J = e % (N + 1);
+      int r = I, c = J;
+      if (c < N && r > c) { int tmp = r; r = c; c = tmp; }
+      const int ti = r >> 2, tj = c >> 2;
+      const int tile = ti * W.T - (ti * (ti - 1)) / 2 + (tj - ti);
+      const double v = SC[(size_t)tile * 16 + (r & 3) * 4 + (c & 3)];
+      if (J < N) Rsc[(size_t)I * N + J] = v; else Rsc[(size_t)N * N + I] = v;
+    }
   }
 
-  // ---- top part
-  const int fa = (I >= 4) ? (I - 4) >> 3 : -1, ia = (I >= 4) ? (I - 4) & 7 : I;
-  double v = 0.0;
-  if (J == N) {  // b_top
-    if (fa < 0) {
-      for (int pr = 0; pr < nf * nf; pr++) v += h13(TS + (size_t)pr * TOP_PART, ia, 12);
-    } else {
-      for (int t = 0; t < nf; t++) {
-        if (t == fa) continue;
-        const double* S = TS + (size_t)(fa * nf + t) * TOP_PART;       // pair (host fa, target t)
-        const double* Ah = A->adHost[fa * nf + t];
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) s += Ah[ia * 8 + k] * h13(S, 4 + k, 12);
-        v += s;
-        const double* S2 = TS + (size_t)(t * nf + fa) * TOP_PART;      // pair (host t, target fa)
-        v += A->adTdiag[t * nf + fa][ia] * h13(S2, 4 + ia, 12);
-      }
+  __shared__ double s_S[2][MAXF][TOP_PART];  // [0][t] = pair (a,t) (a is host), [1][t] = pair (t,a) (a is target)
+  __shared__ double s_Ah[2][MAXF][64];       // [0][t] = adHost(a,t), [1][t] = adHost(t,a)
+  __shared__ double s_d[2][MAXF][8];         // [0][t] = adTdiag(a,t), [1][t] = adTdiag(t,a)
+  __shared__ double s_M[MAXF][64];           // P(a,t) * Ah(a,t)^T
+
+  if (a == nf) {
+    // calibration rows: H[C,C] = sum R ; b[C] = sum q ; H[C, frame] is written (transposed) by the frame CTAs
+    for (int e = tid; e < 4 * 5; e += ST_THREADS) {
+      const int i = e / 5, j = e % 5;
+      double v = 0.0;
+      for (int pr = 0; pr < nf * nf; pr++) v += h13(TS + (size_t)pr * TOP_PART, i, j < 4 ? j : 12);
+      if (j < 4) R[(size_t)i * N + j] = v; else R[(size_t)N * N + i] = v;
     }
-    R[(size_t)N * N + I] = v;
     return;
   }
-  const int fb = (J >= 4) ? (J - 4) >> 3 : -1, jb = (J >= 4) ? (J - 4) & 7 : J;
-  if (fa < 0 && fb < 0) {  // calib-calib
-    for (int pr = 0; pr < nf * nf; pr++) v += h13(TS + (size_t)pr * TOP_PART, ia, jb);
-  } else if (fa < 0 || fb < 0) {  // frame-calib (and its transpose)
-    const int f = (fa < 0) ? fb : fa, i = (fa < 0) ? jb : ia, c = (fa < 0) ? ia : jb;
-    for (int t = 0; t < nf; t++) {
-      if (t == f) continue;
-      const double* S = TS + (size_t)(f * nf + t) * TOP_PART;
-      const double* Ah = A->adHost[f * nf + t];
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) s += Ah[i * 8 + k] * h13(S, 4 + k, c);
-      v += s;
-      const double* S2 = TS + (size_t)(t * nf + f) * TOP_PART;
-      v += A->adTdiag[t * nf + f][i] * h13(S2, 4 + i, c);
-    }
-  } else if (fa == fb) {  // diagonal frame block
-    for (int t = 0; t < nf; t++) {
-      if (t == fa) continue;
-      const double* S = TS + (size_t)(fa * nf + t) * TOP_PART;
-      const double* Ah = A->adHost[fa * nf + t];
-      double s0 = 0.0, s1 = 0.0;
-      for (int k = 0; k < 8; k++) {
-        double m0 = 0.0, m1 = 0.0;  // (P Ah^T)[k][jb]
-#pragma unroll
-        for (int l = 0; l < 8; l += 2) {
-          m0 += h13(S, 4 + k, 4 + l) * Ah[jb * 8 + l];
-          m1 += h13(S, 4 + k, 4 + l + 1) * Ah[jb * 8 + l + 1];
-        }
-        if (k & 1) s1 += Ah[ia * 8 + k] * (m0 + m1); else s0 += Ah[ia * 8 + k] * (m0 + m1);
-      }
-      v += s0 + s1;
-      const double* S2 = TS + (size_t)(t * nf + fa) * TOP_PART;
-      const double* d = A->adTdiag[t * nf + fa];
-      v += d[ia] * h13(S2, 4 + ia, 4 + jb) * d[jb];
-    }
-  } else {  // off-diagonal frame block: raw[fa,fb](ia,jb) + raw[fb,fa](jb,ia), raw[h,t] = Ah P At^T
-    {
-      const double* S = TS + (size_t)(fa * nf + fb) * TOP_PART;
-      const double* Ah = A->adHost[fa * nf + fb];
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) s += Ah[ia * 8 + k] * h13(S, 4 + k, 4 + jb);
-      v += s * A->adTdiag[fa * nf + fb][jb];
-    }
-    {
-      const double* S = TS + (size_t)(fb * nf + fa) * TOP_PART;
-      const double* Ah = A->adHost[fb * nf + fa];
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) s += Ah[jb * 8 + k] * h13(S, 4 + k, 4 + ia);
-      v += s * A->adTdiag[fb * nf + fa][ia];
-    }
+  for (int e = tid; e < nf * TOP_PART; e += ST_THREADS) {
+    const int t = e / TOP_PART, k = e - t * TOP_PART;
+    s_S[0][t][k] = TS[(size_t)(a * nf + t) * TOP_PART + k];
+    s_S[1][t][k] = TS[(size_t)(t * nf + a) * TOP_PART + k];
   }
-  R[(size_t)I * N + J] = v;
+  for (int e = tid; e < nf * 64; e += ST_THREADS) {
+    const int t = e >> 6, k = e & 63;
+    s_Ah[0][t][k] = A->adHost[a * nf + t][k];
+    s_Ah[1][t][k] = A->adHost[t * nf + a][k];
+  }
+  for (int e = tid; e < nf * 8; e += ST_THREADS) {
+    const int t = e >> 3, k = e & 7;
+    s_d[0][t][k] = A->adTdiag[a * nf + t][k];
+    s_d[1][t][k] = A->adTdiag[t * nf + a][k];
+  }
+  __syncthreads();
+  // M[t] = P(a,t) * Ah(a,t)^T   (8x8 each)
+  for (int e = tid; e < nf * 64; e += ST_THREADS) {
+    const int t = e >> 6, k = (e >> 3) & 7, j = e & 7;
+    double m = 0.0;
+    if (t != a) {
+#pragma unroll
+      for (int l = 0; l < 8; l++) m += h13(s_S[0][t], 4 + k, 4 + l) * s_Ah[0][t][j * 8 + l];
+    }
+    s_M[t][e & 63] = m;
+  }
+  __syncthreads();
+  // outputs of this block-row: 8 rows x (N+1) columns
+  const int r0 = 4 + 8 * a;
+  for (int e = tid; e < 8 * (N + 1); e += ST_THREADS) {
+    const int ia = e / (N + 1), J = e % (N + 1);
+    double v = 0.0;
+    if (J == N) {  // b[a] = sum_t Ah(a,t) p(a,t) + At(t,a) p(t,a)
+      for (int t = 0; t < nf; t++) {
+        if (t == a) continue;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += s_Ah[0][t][ia * 8 + k] * h13(s_S[0][t], 4 + k, 12);
+        v += s + s_d[1][t][ia] * h13(s_S[1][t], 4 + ia, 12);
+      }
+      R[(size_t)N * N + r0 + ia] = v;
+      continue;
+    }
+    if (J < 4) {  // H[a,C] = sum_t Ah(a,t) Q(a,t) + At(t,a) Q(t,a) ; mirrored into H[C,a]
+      for (int t = 0; t < nf; t++) {
+        if (t == a) continue;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += s_Ah[0][t][ia * 8 + k] * h13(s_S[0][t], 4 + k, J);
+        v += s + s_d[1][t][ia] * h13(s_S[1][t], 4 + ia, J);
+      }
+      R[(size_t)(r0 + ia) * N + J] = v;
+      R[(size_t)J * N + r0 + ia] = v;
+      continue;
+    }
+    const int fb = (J - 4) >> 3, jb = (J - 4) & 7;
+    if (fb == a) {  // diagonal block: sum_t Ah M[t] + At(t,a) P(t,a) At(t,a)
+      for (int t = 0; t < nf; t++) {
+        if (t == a) continue;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += s_Ah[0][t][ia * 8 + k] * s_M[t][k * 8 + jb];
+        v += s + s_d[1][t][ia] * h13(s_S[1][t], 4 + ia, 4 + jb) * s_d[1][t][jb];
+      }
+    } else {  // off-diagonal: raw[a,fb](ia,jb) + raw[fb,a](jb,ia), raw[h,t] = Ah P At^T
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) s += s_Ah[0][fb][ia * 8 + k] * h13(s_S[0][fb], 4 + k, 4 + jb);
+      v = s * s_d[0][fb][jb];
+      double s2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) s2 += s_Ah[1][fb][jb * 8 + k] * h13(s_S[1][fb], 4 + k, 4 + ia);
+      v += s2 * s_d[1][fb][ia];
+    }
+    R[(size_t)(r0 + ia) * N + J] = v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:L295-321) + point part of doStepFromBackup (FullSystemOptimize.cpp:L264-272)
+// stand-alone EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:L295-321) + point part of doStepFromBackup
+// sums[0..2] += sum step^2, sum |idepth_backup|, npts   (caller zeroes sums)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) ba_resub_kernel(const BAWinDev* __restrict__ wins, int apply) {
-  const BAWinDev& W = wins[blockIdx.y];
+__global__ void __launch_bounds__(128) ba_resub_kernel(const __grid_constant__ BAWinDev W, const __grid_constant__ BAIter it, int apply,
+                                                       double* __restrict__ sums) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nf = W.nf, mp = W.mp;
   float step2 = 0.f, nid = 0.f;
-  if (p < W.npts && W.it->have_x) {
-    // host frame of p: chunks are host-sorted; find via the chunk table (few chunks per host)
+  if (p < W.npts) {
     int h = 0;
-    {
-      int lo = 0, hi = W.nchunks - 1;
-      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (W.chunks[mid].start <= p) lo = mid; else hi = mid - 1; }
-      h = W.chunks[lo].host;
-    }
-    const float4 po0 = reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8)[0];
-    const float4 po1 = reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8)[1];
-    const float HdiF = po1.z;
-    float step = 0.f;
-    int ngood = 0;
-    float b = po1.w;  // bdSumF
-    const float* xc = W.it->xc;
-    b -= xc[0] * po0.z + xc[1] * po0.w + xc[2] * po1.x + xc[3] * po1.y;
-    for (int t = 0; t < nf; t++) {
-      if (t == h) continue;
-      const int slot = t * mp + p;
-      if (W.c_st[slot] != RES_IN) continue;
-      ngood++;
-      const float4 a0 = reinterpret_cast<const float4*>(W.c_jpjd + (size_t)slot * 8)[0];
-      const float4 a1 = reinterpret_cast<const float4*>(W.c_jpjd + (size_t)slot * 8)[1];
-      const float* xa = W.it->xAd[h * nf + t];
-      b -= xa[0] * a0.x + xa[1] * a0.y + xa[2] * a0.z + xa[3] * a0.w + xa[4] * a1.x + xa[5] * a1.y + xa[6] * a1.z + xa[7] * a1.w;
-    }
-    if (ngood > 0) step = -b * HdiF;
+    while (h < W.nf - 1 && p >= W.host_start[h + 1]) h++;
+    const float step = resub_point(W, it, p, h);
     W.step[p] = step;
     const float idb = W.idepth_backup[p];
     step2 = step * step;
@@ -561,7 +609,6 @@ __global__ void __launch_bounds__(128) ba_resub_kernel(const BAWinDev* __restric
       W.idepth_zero[p] = v;  // DM-VIO: setIdepthZero in doStepFromBackup (FullSystemOptimize.cpp:L268)
     }
   }
-  // block partial of (sum step^2, sum |idepth_backup|) — deterministic two-level reduction
   __shared__ float s2[128], sn[128];
   s2[threadIdx.x] = step2; sn[threadIdx.x] = nid;
   __syncthreads();
@@ -569,25 +616,11 @@ __global__ void __launch_bounds__(128) ba_resub_kernel(const BAWinDev* __restric
     if ((int)threadIdx.x < s) { s2[threadIdx.x] += s2[threadIdx.x + s]; sn[threadIdx.x] += sn[threadIdx.x + s]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { W.step_part[2 * blockIdx.x] = (double)s2[0]; W.step_part[2 * blockIdx.x + 1] = (double)sn[0]; }
-}
-
-__global__ void ba_resub_finish_kernel(const BAWinDev* __restrict__ wins, int nblocks) {
-  const BAWinDev& W = wins[blockIdx.x];
   if (threadIdx.x == 0) {
-    double a = 0, b = 0;
-    for (int i = 0; i < nblocks; i++) { a += W.step_part[2 * i]; b += W.step_part[2 * i + 1]; }
-    double* tail = W.result + 2 * (W.N * W.N + W.N);
-    tail[4] = a; tail[5] = b; tail[6] = (double)W.npts;
+    atomicAdd(sums, (double)s2[0]);
+    atomicAdd(sums + 1, (double)sn[0]);
+    atomicAdd(sums + 2, (double)min(128, W.npts - (int)blockIdx.x * 128));
   }
-}
-
-__global__ void ba_backup_kernel(const BAWinDev* __restrict__ wins, int restore) {
-  const BAWinDev& W = wins[blockIdx.y];
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= W.npts) return;
-  if (restore) { const float v = W.idepth_backup[p]; W.idepth[p] = v; W.idepth_zero[p] = v; }
-  else W.idepth_backup[p] = W.idepth[p];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -621,30 +654,15 @@ __global__ void l2_flush_kernel(float4* buf, size_t n) {
 // ---------------------------------------------------------------------------------------------------------------
 // launch helpers (called from ba_api.cu)
 // ---------------------------------------------------------------------------------------------------------------
-void launch_point_kernel(const BAWinDev* wins, int nwin, int max_chunks, int P, int nf, cudaStream_t s) {
-  dim3 grid(max_chunks, nwin), block(32 * (nf < 2 ? 2 : nf));
-  if (P == 8) ba_point_kernel<8><<<grid, block, 0, s>>>(wins);
-  else if (P == 16) ba_point_kernel<16><<<grid, block, 0, s>>>(wins);
-  else ba_point_kernel<32><<<grid, block, 0, s>>>(wins);
+void launch_point_kernel(const BAWinDev& W, const BAIter& it, cudaStream_t s) {
+  dim3 grid(W.nchunks), block(32 * (W.nf < 2 ? 2 : W.nf));
+  if (W.P == 8) ba_point_kernel<8><<<grid, block, 0, s>>>(W, it);
+  else if (W.P == 16) ba_point_kernel<16><<<grid, block, 0, s>>>(W, it);
+  else ba_point_kernel<32><<<grid, block, 0, s>>>(W, it);
 }
-void launch_reduce_kernel(const BAWinDev* wins, int nwin, int nf, int ntiles, cudaStream_t s) {
-  const int entries = nf * nf * TOP_PART + ntiles * 16 + 4;
-  dim3 grid((entries + 255) / 256, nwin);
-  ba_reduce_kernel<<<grid, 256, 0, s>>>(wins);
-}
-void launch_stitch_kernel(const BAWinDev* wins, int nwin, int N, cudaStream_t s) {
-  dim3 grid((N * (N + 1) + 255) / 256, nwin);
-  ba_stitch_kernel<<<grid, 256, 0, s>>>(wins);
-}
-void launch_resub_kernel(const BAWinDev* wins, int nwin, int npts, int apply, cudaStream_t s) {
-  const int nb = (npts + 127) / 128;
-  dim3 grid(nb, nwin);
-  ba_resub_kernel<<<grid, 128, 0, s>>>(wins, apply);
-  ba_resub_finish_kernel<<<nwin, 32, 0, s>>>(wins, nb);
-}
-void launch_backup_kernel(const BAWinDev* wins, int nwin, int npts, int restore, cudaStream_t s) {
-  dim3 grid((npts + 255) / 256, nwin);
-  ba_backup_kernel<<<grid, 256, 0, s>>>(wins, restore);
+void launch_stitch_kernel(const BAWinDev& W, cudaStream_t s) { ba_stitch_kernel<<<W.nf + 1, ST_THREADS, 0, s>>>(W); }
+void launch_resub_kernel(const BAWinDev& W, const BAIter& it, int apply, double* sums, cudaStream_t s) {
+  ba_resub_kernel<<<(W.npts + 127) / 128, 128, 0, s>>>(W, it, apply, sums);
 }
 void launch_repack(const float* src, float4* dst, int n, cudaStream_t s) { repack_aos3_kernel<<<(n + 255) / 256, 256, 0, s>>>(src, dst, n); }
 void launch_make_dI(const float* img, float4* dst, int w, int h, cudaStream_t s) { make_dI_kernel<<<(w * h + 255) / 256, 256, 0, s>>>(img, dst, w, h); }
