@@ -4,6 +4,7 @@
 #include "ba_device.cuh"
 #include "common_host.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -51,6 +52,9 @@ struct dmv_ba {
   int acc_cur = 0;
   size_t acc_cap = 0;
   double* d_resub_sums = nullptr;
+  unsigned long long* d_dbg_clk = nullptr;
+  unsigned int* d_ticket = nullptr;
+  double* d_stage = nullptr;
   float4* d_flush = nullptr;
   size_t flush_n = 0;
   // pinned host
@@ -66,6 +70,9 @@ struct dmv_ba {
   std::vector<int> res_slot;   // residual index -> slot (t*mp+p)
   std::vector<uint8_t> h_st_in;
   std::vector<float> h_en_in;
+  bool timing = false;         // record CUDA events around the kernels of every call (dmv_ba_set_timing)
+  int iter2 = 0;
+  int dbg = 0;                 // DMV_DBG experiment mask (see ba_device.cuh); never set in production
   int tent = 0;                // index of the tentative buffer set; committed = 1 - tent
   bool have_tentative = false, have_committed = false, have_adj = false, have_state = false;
   long long launches = 0;
@@ -88,6 +95,8 @@ static int fill_descriptor(dmv_ba* b) {
   W.N = b->N; W.NW = b->NW; W.T = b->T; W.ntiles = b->ntiles; W.mp = b->mp; W.P = b->P;
   W.huberTH = b->prm.huberTH; W.outlierTHSum = b->prm.outlierTHSumComponent;
   W.zeroA = b->prm.affineOptModeA < 0; W.zeroB = b->prm.affineOptModeB < 0;
+  W.dbg = b->dbg;
+  W.iter2 = b->iter2;
   for (int h = 0; h <= MAXF; h++) { W.host_start[h] = b->host_start[h]; W.chunk_beg[h] = b->chunk_beg[h]; }
   for (int f = 0; f < b->nf; f++) W.img[f] = b->d_img[b->slots[f]];
   W.adj = b->d_adj;
@@ -100,6 +109,9 @@ static int fill_descriptor(dmv_ba* b) {
   W.step = b->d_step;
   W.acc = b->d_acc[b->acc_cur];
   W.acc_next = b->d_acc[1 - b->acc_cur];
+  W.dbg_clk = b->d_dbg_clk;
+  W.ticket = b->d_ticket;
+  W.stage = b->d_stage;
   W.result = b->d_result[t];
   return DMV_OK;
 }
@@ -128,6 +140,8 @@ int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
   b->cfg = *cfg;
   b->device = cfg->device;
   dmv_ba_default_params(&b->prm);
+  if (const char* e = getenv("DMV_DBG")) b->dbg = atoi(e);
+  if (const char* e = getenv("DMV_ITER2")) b->iter2 = atoi(e);
   b->P = (cfg->chunk_points == 8 || cfg->chunk_points == 16 || cfg->chunk_points == 32) ? cfg->chunk_points : 16;
   b->mp = (cfg->max_points + 31) & ~31;
   const int MF = MAXF, mp = b->mp;
@@ -147,6 +161,7 @@ int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
   CK(cudaMalloc(&b->d_priorF, sizeof(float) * mp));
   CK(cudaMalloc(&b->d_st_in, (size_t)MF * mp));
   CK(cudaMalloc(&b->d_en_in, sizeof(float) * MF * mp));
+  const int maxT0 = (8 * MF + 4 + 1 + 3) / 4, maxTiles0 = maxT0 * (maxT0 + 1) / 2;
   for (int k = 0; k < 2; k++) {
     CK(cudaMalloc(&b->d_st_new[k], (size_t)MF * mp));
     CK(cudaMemset(b->d_st_new[k], 0xff, (size_t)MF * mp));
@@ -156,8 +171,8 @@ int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
     CK(cudaMalloc(&b->d_jpjd[k], sizeof(float) * 8 * MF * mp));
     CK(cudaMalloc(&b->d_pout[k], sizeof(float) * 8 * mp));
     CK(cudaMemset(b->d_pout[k], 0, sizeof(float) * 8 * mp));
-    CK(cudaMalloc(&b->d_result[k], sizeof(double) * result_doubles(8 * MF + 4)));
-    CK(cudaMallocHost(&b->h_result[k], sizeof(double) * result_doubles(8 * MF + 4)));
+    CK(cudaMalloc(&b->d_result[k], sizeof(double) * result_doubles(8 * MF + 4, maxTiles0)));
+    CK(cudaMallocHost(&b->h_result[k], sizeof(double) * result_doubles(8 * MF + 4, maxTiles0)));
   }
   CK(cudaMalloc(&b->d_step, sizeof(float) * mp));
   CK(cudaMemset(b->d_step, 0, sizeof(float) * mp));
@@ -168,6 +183,12 @@ int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
     CK(cudaMemset(b->d_acc[k], 0, sizeof(double) * b->acc_cap));
   }
   CK(cudaMalloc(&b->d_resub_sums, sizeof(double) * 4));
+  CK(cudaMalloc(&b->d_ticket, sizeof(unsigned int) * 16));
+  CK(cudaMemset(b->d_ticket, 0, sizeof(unsigned int) * 16));
+  CK(cudaMalloc(&b->d_stage, sizeof(double) * (MF * MF * 272 + MF * 20)));
+  CK(cudaMemset(b->d_stage, 0, sizeof(double) * (MF * MF * 272 + MF * 20)));
+  CK(cudaMalloc(&b->d_dbg_clk, sizeof(unsigned long long) * 16 * b->max_chunks));
+  CK(cudaMemset(b->d_dbg_clk, 0, sizeof(unsigned long long) * 16 * b->max_chunks));
   CK(cudaMallocHost(&b->h_up, sizeof(HostUpload)));
   CK(cudaMallocHost(&b->h_adj, sizeof(BAAdj)));
   std::memset(b->h_up, 0, sizeof(HostUpload));
@@ -375,32 +396,34 @@ static int enqueue_linearize(dmv_ba* b, bool with_resub) {
   (void)with_resub;  // the resubstitute + step prologue is fused into the point kernel (it.have_x)
   fill_descriptor(b);
   const HostUpload& U = *b->h_up;
-  CK(cudaEventRecord(b->ev[0], b->stream));
-  launch_point_kernel(U.win, U.it, b->stream);
-  CK(cudaEventRecord(b->ev[1], b->stream));
-  launch_stitch_kernel(U.win, b->stream);
+  if (b->timing) CK(cudaEventRecord(b->ev[0], b->stream));
+  launch_point_kernel(U.win, U.it, b->stream);   // residuals + Hessian blocks + Schur Gram -> fp64 accumulators
+  if (b->timing) CK(cudaEventRecord(b->ev[1], b->stream));
+  launch_stitch_kernel(U.win, b->stream);         // programmatic dependent launch: resident early, waits on the grid dependency
   b->launches += 2;
   b->acc_cur = 1 - b->acc_cur;
-  CK(cudaEventRecord(b->ev[2], b->stream));
+  if (b->timing) CK(cudaEventRecord(b->ev[2], b->stream));
   CK(cudaGetLastError());
   if (b->nccl_comm) {
-    int rc = dmv::nccl_allreduce_double(b->nccl_comm, b->d_result[b->tent], result_doubles(b->N), b->stream);
+    int rc = dmv::nccl_allreduce_double(b->nccl_comm, b->d_result[b->tent], result_doubles(b->N, b->ntiles), b->stream);
     if (rc != DMV_OK) return rc;
   }
-  CK(cudaMemcpyAsync(b->h_result[b->tent], b->d_result[b->tent], sizeof(double) * result_doubles(b->N), cudaMemcpyDeviceToHost, b->stream));
-  CK(cudaEventRecord(b->ev[3], b->stream));
+  CK(cudaMemcpyAsync(b->h_result[b->tent], b->d_result[b->tent], sizeof(double) * result_doubles(b->N, b->ntiles), cudaMemcpyDeviceToHost, b->stream));
+  if (b->timing) CK(cudaEventRecord(b->ev[3], b->stream));
   return DMV_OK;
 }
 
 static int finish_linearize(dmv_ba* b, dmv_ba_lin_result* out, double sums[3]) {
   CK(cudaStreamSynchronize(b->stream));
-  const double* tail = b->h_result[b->tent] + 2 * (b->N * b->N + b->N);
+  const double* tail = b->h_result[b->tent] + (b->N * b->N + b->N) + b->ntiles * 16;
   if (out) { out->energy = tail[0]; out->n_in = (int)tail[1]; out->n_oob = (int)tail[2]; out->n_outlier = (int)tail[3]; }
   if (sums) { sums[0] = tail[4]; sums[1] = tail[5]; sums[2] = tail[6]; }
-  cudaEventElapsedTime(&b->last_ms[0], b->ev[0], b->ev[3]);
-  cudaEventElapsedTime(&b->last_ms[1], b->ev[0], b->ev[1]);
-  cudaEventElapsedTime(&b->last_ms[2], b->ev[1], b->ev[2]);
-  cudaEventElapsedTime(&b->last_ms[3], b->ev[2], b->ev[3]);
+  if (b->timing) {
+    cudaEventElapsedTime(&b->last_ms[0], b->ev[0], b->ev[3]);
+    cudaEventElapsedTime(&b->last_ms[1], b->ev[0], b->ev[1]);
+    cudaEventElapsedTime(&b->last_ms[2], b->ev[1], b->ev[2]);
+    cudaEventElapsedTime(&b->last_ms[3], b->ev[2], b->ev[3]);
+  }
   b->have_tentative = true;
   return DMV_OK;
 }
@@ -514,13 +537,27 @@ int dmv_ba_apply_res(dmv_ba* b) {
 int dmv_ba_accumulate(dmv_ba* b, double* H_A, double* b_A, double* H_sc, double* b_sc, int* resInA) {
   if (!b) return set_error(DMV_ERR_INVALID, "null handle");
   if (!b->have_committed) return set_error(DMV_ERR_STATE, "no committed linearisation (linearize + apply_res first)");
-  const int N = b->N;
+  const int N = b->N, T = b->T;
   const double* r = b->h_result[1 - b->tent];
-  if (H_A) std::memcpy(H_A, r, sizeof(double) * N * N);
+  if (H_A) {
+    std::memcpy(H_A, r, sizeof(double) * N * N);
+    for (int i = 4; i < N; i++)  // the device fills H[frame,C]; mirror into H[C,frame] (AccumulatedTopHessian.h:L127-130)
+      for (int c = 0; c < 4; c++) H_A[(size_t)c * N + i] = H_A[(size_t)i * N + c];
+  }
   if (b_A) std::memcpy(b_A, r + (size_t)N * N, sizeof(double) * N);
-  if (H_sc) std::memcpy(H_sc, r + (size_t)N * N + N, sizeof(double) * N * N);
-  if (b_sc) std::memcpy(b_sc, r + 2 * (size_t)N * N + N, sizeof(double) * N);
-  if (resInA) *resInA = (int)r[2 * ((size_t)N * N + N) + 1];
+  const double* sc = r + (size_t)N * N + N;  // raw upper-triangular 4x4 Gram tiles of [H_sc | b_sc] (ba_point.cu, phase C)
+  auto gram = [&](int rr, int cc) {
+    if (cc < N && rr > cc) std::swap(rr, cc);
+    const int ti = rr >> 2, tj = cc >> 2;
+    const int tile = ti * T - (ti * (ti - 1)) / 2 + (tj - ti);
+    return sc[(size_t)tile * 16 + (rr & 3) * 4 + (cc & 3)];
+  };
+  if (H_sc)
+    for (int i = 0; i < N; i++)
+      for (int j = 0; j < N; j++) H_sc[(size_t)i * N + j] = gram(i, j);
+  if (b_sc)
+    for (int i = 0; i < N; i++) b_sc[i] = gram(i, N);
+  if (resInA) *resInA = (int)sc[(size_t)b->ntiles * 16 + 1];
   return DMV_OK;
 }
 
@@ -628,11 +665,11 @@ int dmv_ba_bench_device(dmv_ba* b, const double* x, int iters, int flush_l2, flo
     const HostUpload& U = *b->h_up;
     CK(cudaEventRecord(e[3 * i], b->stream));
     launch_point_kernel(U.win, U.it, b->stream);
-    CK(cudaEventRecord(e[3 * i + 1], b->stream));
     launch_stitch_kernel(U.win, b->stream);
+    CK(cudaEventRecord(e[3 * i + 1], b->stream));
     b->acc_cur = 1 - b->acc_cur;
     if (b->nccl_comm) {
-      rc = dmv::nccl_allreduce_double(b->nccl_comm, b->d_result[b->tent], result_doubles(b->N), b->stream);
+      rc = dmv::nccl_allreduce_double(b->nccl_comm, b->d_result[b->tent], result_doubles(b->N, b->ntiles), b->stream);
       if (rc != DMV_OK) return rc;
     }
     CK(cudaEventRecord(e[3 * i + 2], b->stream));
@@ -672,6 +709,41 @@ int dmv_ba_comm_init(dmv_ba* b, int nranks, int rank, const void* id) {
 extern "C" int dmv_ba_io_bytes(dmv_ba* b, long long* h2d, long long* d2h) {
   if (!b || !h2d || !d2h) return set_error(DMV_ERR_INVALID, "null argument");
   *h2d = (long long)sizeof(HostUpload);                        // descriptor + per-iteration tables, carried as kernel parameters
-  *d2h = (long long)sizeof(double) * result_doubles(b->N);     // H_A, b_A, H_sc, b_sc, energy + counters
+  *d2h = (long long)sizeof(double) * result_doubles(b->N, b->ntiles);     // H_A, b_A, H_sc, b_sc, energy + counters
+  return DMV_OK;
+}
+
+extern "C" int dmv_ba_debug_clocks(dmv_ba* b, unsigned long long* out, int cap) {
+  if (!b || !out) return set_error(DMV_ERR_INVALID, "null argument");
+  const int n = std::min(cap, 16 * b->nchunks);
+  CK(cudaSetDevice(b->device));
+  CK(cudaMemcpy(out, b->d_dbg_clk, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+  return n;
+}
+
+extern "C" int dmv_ba_set_timing(dmv_ba* b, int enable) {
+  if (!b) return set_error(DMV_ERR_INVALID, "null handle");
+  b->timing = enable != 0;
+  return DMV_OK;
+}
+
+// End-to-end timing of the public call sequence a DM-VIO host makes per GN iteration, from C (no interpreter in the loop):
+// iters x { dmv_ba_gn_step(x, st) ; dmv_ba_apply_res() } with host buffers in and H/b out, wall clock (steady_clock).
+#include <chrono>
+extern "C" int dmv_ba_bench_e2e(dmv_ba* b, const double* x, const dmv_ba_state* st, int iters, double* ms_per_iter) {
+  if (!b || !st || !ms_per_iter || iters < 1) return set_error(DMV_ERR_INVALID, "bad argument");
+  dmv_ba_lin_result r;
+  double sums[3];
+  CK(cudaSetDevice(b->device));
+  CK(cudaStreamSynchronize(b->stream));
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < iters; i++) {
+    int rc = dmv_ba_gn_step(b, x, st, &r, sums);
+    if (rc != DMV_OK) return rc;
+    rc = dmv_ba_apply_res(b);
+    if (rc != DMV_OK) return rc;
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  *ms_per_iter = std::chrono::duration<double, std::milli>(t1 - t0).count() / iters;
   return DMV_OK;
 }

@@ -38,6 +38,8 @@ struct BAWinDev {
   int nf, npts, nchunks, w, h, N, NW, T, ntiles, mp, P;  // mp = capacity (row pitch of the [target][point] slot arrays)
   float huberTH, outlierTHSum;
   int zeroA, zeroB;
+  int iter2;                 // experiment: 2 quads per warp (half the warps) for P = 16
+  int dbg;                   // DMV_DBG experiment mask (bit0: skip global REDs, bit1: skip phase C, bit2: skip image gathers); 0 in production
   int host_start[MAXF + 1];  // points of host h are [host_start[h], host_start[h+1])
   int chunk_beg[MAXF + 1];   // chunks (CTAs) of host h are [chunk_beg[h], chunk_beg[h+1]); chunk c covers P consecutive points
   const float4* img[MAXF];   // per window frame index: level-0 texels (I, dx, dy, 0)
@@ -64,13 +66,18 @@ struct BAWinDev {
   const float* c_jpjd;
   const float* c_pout;
   float* step;               // [p]
-  // fp64 accumulators: [nf*nf*TOP_PART top | ntiles*16 schur tiles | ACC_MISC]
+  // fp64 accumulators: [nf*nf*TOP_PART top | ntiles*16 schur tiles | ACC_MISC | dense H N*N | b N]
   double* acc;               // accumulated into by this iteration's point kernel, consumed by its stitch kernel
   double* acc_next;          // zeroed by this iteration's stitch kernel for the next iteration
-  double* result;            // H_top N*N | b_top N | H_sc N*N | b_sc N | ACC_MISC tail
+  unsigned long long* dbg_clk; // [chunk][8] phase timestamps (globaltimer ns) when dbg & 16
+  unsigned int* ticket;      // [0] CTA completion counter, [1+h] per-host counters (last CTA of a host / overall stitches); self-resetting
+  double* stage;             // scratch of the stitch: per pair B|G|GA (272 doubles) + per host 20 calibration sums
+  double* result;            // H_top N*N | b_top N | Schur tiles ntiles*16 | ACC_MISC tail
 };
 
-inline __host__ __device__ int result_doubles(int N) { return 2 * (N * N + N) + ACC_MISC; }
+// result blob: H_top N*N | b_top N | raw Schur Gram tiles ntiles*16 | ACC_MISC counters
+inline __host__ __device__ int result_doubles(int N, int ntiles) { return N * N + N + ntiles * 16 + ACC_MISC; }
+// accumulators: pair blocks nf*nf*TOP_PART | Schur tiles ntiles*16 | ACC_MISC | dense H (N*N) | b (N)
 inline __host__ __device__ int acc_doubles(int nf, int ntiles) { return nf * nf * TOP_PART + ntiles * 16 + ACC_MISC; }
 
 }  // namespace dmv

@@ -15,443 +15,9 @@
 //   ba_stitch_kernel    adjoint products to the dense (8nf+4)^2 system in fp64 (AccumulatedTopHessian.cpp:L241-303, gather form);
 //                       also zeroes the accumulator set of the next iteration
 //   ba_resub_kernel     stand-alone EnergyFunctional::resubstituteFPt + point part of doStepFromBackup
-#include "ba_device.cuh"
-#include <math.h>
+#include "ba_common.cuh"
 
 namespace dmv {
-
-__device__ __constant__ int c_pattern[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {0, 2}};
-
-__device__ __forceinline__ float pick8(const float* v, int j) {
-  float a = (j & 1) ? v[1] : v[0];
-  float b = (j & 1) ? v[3] : v[2];
-  float c = (j & 1) ? v[5] : v[4];
-  float d = (j & 1) ? v[7] : v[6];
-  float e = (j & 2) ? b : a;
-  float f = (j & 2) ? d : c;
-  return (j & 4) ? f : e;
-}
-__device__ __forceinline__ float group_sum8(float v) {  // all-reduce inside aligned groups of 8 lanes
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
-  return v;
-}
-__device__ __forceinline__ float cross_group_sum(float v) {  // sum over the 4 groups of a warp
-  v += __shfl_xor_sync(0xffffffffu, v, 8);
-  v += __shfl_xor_sync(0xffffffffu, v, 16);
-  return v;
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* g) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(g));
-}
-__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g));
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); }  // result unused -> RED.E.ADD.F64
-
-// EnergyFunctional::resubstituteFPt for one point (EnergyFunctional.cpp:L295-321)
-__device__ __forceinline__ float resub_point(const BAWinDev& W, const BAIter& it, int p, int h) {
-  const int nf = W.nf, mp = W.mp;
-  const float4 po0 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8));
-  const float4 po1 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8) + 1);
-  float b = po1.w;  // bdSumF
-  b -= it.xc[0] * po0.z + it.xc[1] * po0.w + it.xc[2] * po1.x + it.xc[3] * po1.y;
-  int ngood = 0;
-  for (int t = 0; t < nf; t++) {
-    if (t == h) continue;
-    const int slot = t * mp + p;
-    if (W.c_st[slot] != RES_IN) continue;
-    ngood++;
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)slot * 8));
-    const float4 a1 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)slot * 8) + 1);
-    const float* xa = it.xAd[h * nf + t];
-    b -= xa[0] * a0.x + xa[1] * a0.y + xa[2] * a0.z + xa[3] * a0.w + xa[4] * a1.x + xa[5] * a1.y + xa[6] * a1.z + xa[7] * a1.w;
-  }
-  return ngood > 0 ? -b * po1.z : 0.f;  // step = -b * HdiF
-}
-
-template <int P>
-__global__ void __launch_bounds__(32 * MAXF) ba_point_kernel(const __grid_constant__ BAWinDev W, const __grid_constant__ BAIter it) {
-  const int nf = W.nf;
-  int h = 0;
-  while (h < nf - 1 && (int)blockIdx.x >= W.chunk_beg[h + 1]) h++;
-  const int ch_start = W.host_start[h] + ((int)blockIdx.x - W.chunk_beg[h]) * P;
-  const int ch_count = min(P, W.host_start[h + 1] - ch_start);
-  const int tid = threadIdx.x;
-  const int nthreads = blockDim.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int mp = W.mp;
-  double* __restrict__ acc = W.acc;
-
-  __shared__ __align__(16) float s_rec[P][MAXF][REC];
-  __shared__ __align__(16) float s_W[P][8 * MAXF + 8];
-  __shared__ float s_hdi[P];
-  __shared__ __align__(16) float s_adH[MAXF][64];
-  __shared__ __align__(16) float s_adT[MAXF][8];
-  __shared__ __align__(16) float2 s_uv[P];
-  __shared__ float s_id[P], s_idz[P], s_prior[P];
-  __shared__ __align__(16) float s_col[P][8];
-  __shared__ __align__(16) float s_wgt[P][8];
-  __shared__ float s_en[MAXF][P];
-  __shared__ uint8_t s_st[MAXF][P];
-  __shared__ float s_misc[MAXF][4];
-
-  // ---------------------------------------------------------------- prologue: stage inputs (one DRAM round trip)
-  {
-    const BAAdj* __restrict__ A = W.adj;
-    for (int i = tid; i < nf * 16; i += nthreads) cp_async16(&s_adH[i >> 4][(i & 15) * 4], &A->adHostF[h * nf + (i >> 4)][(i & 15) * 4]);
-    for (int i = tid; i < nf * 2; i += nthreads) cp_async16(&s_adT[i >> 1][(i & 1) * 4], &A->adTdiagF[h * nf + (i >> 1)][(i & 1) * 4]);
-    for (int i = tid; i < ch_count * 2; i += nthreads) cp_async4(reinterpret_cast<float*>(s_uv) + i, reinterpret_cast<const float*>(W.uv + ch_start) + i);
-    for (int i = tid; i < ch_count * 8; i += nthreads) {
-      cp_async4(&s_col[0][0] + i, W.color + (size_t)ch_start * 8 + i);
-      cp_async4(&s_wgt[0][0] + i, W.weights + (size_t)ch_start * 8 + i);
-    }
-    for (int i = tid; i < ch_count; i += nthreads) cp_async4(&s_prior[i], W.priorF + ch_start + i);
-    if (!it.have_x)
-      for (int i = tid; i < ch_count; i += nthreads) {
-        cp_async4(&s_id[i], W.idepth + ch_start + i);
-        cp_async4(&s_idz[i], W.idepth_zero + ch_start + i);
-      }
-    for (int i = tid; i < nf * ch_count; i += nthreads) {
-      const int tt = i / ch_count, pl = i - tt * ch_count;
-      cp_async4(&s_en[tt][pl], W.en_in + (size_t)tt * mp + ch_start + pl);
-      s_st[tt][pl] = W.st_in[(size_t)tt * mp + ch_start + pl];
-    }
-    for (int i = tid; i < P * MAXF * REC; i += nthreads) (&s_rec[0][0][0])[i] = 0.f;
-    for (int i = tid; i < P * (8 * MAXF + 8); i += nthreads) (&s_W[0][0])[i] = 0.f;
-    if (tid < MAXF * 4) (&s_misc[0][0])[tid] = 0.f;
-    if (it.have_x && warp == 0) {
-      // fused resubstitute + point part of doStepFromBackup (FullSystemOptimize.cpp:L264-272; DM-VIO also moves idepth_zero)
-      float step2 = 0.f, nid = 0.f;
-      if (tid < ch_count) {
-        const int p = ch_start + tid;
-        const float step = resub_point(W, it, p, h);
-        const float idb = __ldg(W.idepth_backup + p);
-        const float v = idb + step;
-        W.step[p] = step;
-        W.idepth[p] = v;
-        W.idepth_zero[p] = v;
-        s_id[tid] = v;
-        s_idz[tid] = v;
-        step2 = step * step;
-        nid = fabsf(idb);
-      }
-#pragma unroll
-      for (int m = 1; m < 32; m <<= 1) {
-        step2 += __shfl_xor_sync(0xffffffffu, step2, m);
-        nid += __shfl_xor_sync(0xffffffffu, nid, m);
-      }
-      if (lane == 0) {  // the sums feed only the convergence test of doStepFromBackup
-        double* m = acc + (size_t)nf * nf * TOP_PART + (size_t)W.ntiles * 16;
-        red_add(m + 4, (double)step2);
-        red_add(m + 5, (double)nid);
-        red_add(m + 6, (double)ch_count);
-      }
-    }
-    cp_async_wait_all();
-  }
-  __syncthreads();
-
-  // ---------------------------------------------------------------- phase A
-  const int t = warp;  // target frame of this warp
-  if (t < nf && t != h) {
-    const int g = lane >> 3, j = lane & 7;
-    const float* pc = it.precalc[h * nf + t];
-    const float fx = it.calib[0], fy = it.calib[1], cx = it.calib[2], cy = it.calib[3];
-    const float fxi = it.calib[4], fyi = it.calib[5];
-    const float TH = fmaxf(it.TH[h], it.TH[t]);
-    const float wM3 = (float)(W.w - 3), hM3 = (float)(W.h - 3);
-    const float4* __restrict__ img = W.img[t];
-    const int iw = W.w;
-    const float huber = W.huberTH, oth = W.outlierTHSum;
-    const float KRKi0 = pc[0], KRKi1 = pc[1], KRKi2 = pc[2], KRKi3 = pc[3], KRKi4 = pc[4], KRKi5 = pc[5], KRKi6 = pc[6], KRKi7 = pc[7],
-                KRKi8 = pc[8];
-    const float Kt0 = pc[9], Kt1 = pc[10], Kt2 = pc[11];
-    const float R00 = pc[12], R01 = pc[13], R02 = pc[14], R10 = pc[15], R11 = pc[16], R12 = pc[17], R20 = pc[18], R21 = pc[19], R22 = pc[20];
-    const float t00 = pc[21], t01 = pc[22], t02 = pc[23];
-    const float affa = pc[24], affb = pc[25], b0 = pc[26];
-    const int pdx = c_pattern[j][0], pdy = c_pattern[j][1];
-
-    float acc1[TOP_COLS], acc2[TOP_COLS], br[6];
-#pragma unroll
-    for (int c = 0; c < TOP_COLS; c++) { acc1[c] = 0.f; acc2[c] = 0.f; }
-#pragma unroll
-    for (int c = 0; c < 6; c++) br[c] = 0.f;
-    float e_sum = 0.f;
-    int n_in = 0, n_oob = 0, n_outl = 0;
-
-    for (int base = 0; base < ch_count; base += 4) {
-      const int pl = min(base + g, ch_count - 1);
-      const bool valid = base + g < ch_count;
-      const int slot = t * mp + ch_start + pl;
-      const int st = valid ? (int)s_st[t][pl] : RES_NONE;
-      bool live = (st != RES_NONE) && (st != RES_OOB);
-
-      const float2 uv = s_uv[pl];
-      const float idepth = s_id[pl];
-      const float idz = s_idz[pl];
-      const float col = s_col[pl][j];
-      const float wgt = s_wgt[pl][j];
-
-      // ---- centre pixel at the FEJ point (ResidualProjections.h:L62-87, Residuals.cpp:L108-157)
-      const float Kl0 = (uv.x - cx) * fxi, Kl1 = (uv.y - cy) * fyi;
-      const float q0 = R00 * Kl0 + R01 * Kl1 + R02 + t00 * idz;
-      const float q1 = R10 * Kl0 + R11 * Kl1 + R12 + t01 * idz;
-      const float q2 = R20 * Kl0 + R21 * Kl1 + R22 + t02 * idz;
-      const float drescale = 1.0f / q2;
-      const float new_idepth = idz * drescale;
-      const float cu = q0 * drescale, cv = q1 * drescale;
-      const float cKu = cu * fx + cx, cKv = cv * fy + cy;
-      const bool centre_ok = (drescale > 0.f) && cKu > 1.1f && cKv > 1.1f && cKu < wM3 && cKv < hM3;
-      live = live && centre_ok;
-
-      // ---- own pattern pixel at the current state (ResidualProjections.h:L47-57)
-      const float pu = uv.x + (float)pdx, pv = uv.y + (float)pdy;
-      const float r0 = KRKi0 * pu + KRKi1 * pv + KRKi2 + Kt0 * idepth;
-      const float r1 = KRKi3 * pu + KRKi4 * pv + KRKi5 + Kt1 * idepth;
-      const float r2 = KRKi6 * pu + KRKi7 * pv + KRKi8 + Kt2 * idepth;
-      const float Ku = r0 / r2, Kv = r1 / r2;
-      const bool px_ok = Ku > 1.1f && Kv > 1.1f && Ku < wM3 && Kv < hM3;
-      unsigned bal = __ballot_sync(0xffffffffu, px_ok);
-      live = live && (((bal >> (g * 8)) & 0xffu) == 0xffu);
-
-      float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-      if (live) {  // getInterpolatedElement33 (util/globalFuncs.h:L103-118)
-        const int ix = (int)Ku, iy = (int)Kv;
-        const float dx = Ku - ix, dy = Kv - iy, dxdy = dx * dy;
-        const float4* bp = img + (size_t)iy * iw + ix;
-        const float4 tl = __ldg(bp), tr = __ldg(bp + 1), bl = __ldg(bp + iw), brr = __ldg(bp + iw + 1);
-        const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
-        h0 = w11 * brr.x + w10 * bl.x + w01 * tr.x + w00 * tl.x;
-        h1 = w11 * brr.y + w10 * bl.y + w01 * tr.y + w00 * tl.y;
-        h2 = w11 * brr.z + w10 * bl.z + w01 * tr.z + w00 * tl.z;
-      }
-      bal = __ballot_sync(0xffffffffu, isfinite(h0));
-      live = live && (((bal >> (g * 8)) & 0xffu) == 0xffu);
-
-      // ---- photometric residual, gradient weight, Huber (Residuals.cpp:L194-258)
-      const float residual = h0 - (affa * col + affb);
-      const float drdA = col - b0;
-      float w = sqrtf(oth / (oth + (h1 * h1 + h2 * h2)));
-      w = 0.5f * (w + wgt);
-      const float ar = fabsf(residual);
-      float hw = ar < huber ? 1.f : huber / ar;
-      float e_px = w * w * hw * residual * residual * (2.f - hw);
-      if (hw < 1.f) hw = sqrtf(hw);
-      hw = hw * w;
-      if (!live) { hw = 0.f; e_px = 0.f; }
-      const float gx = h1 * hw, gy = h2 * hw;
-      const float resF = live ? residual * hw : 0.f;
-      const float ja = drdA * hw, jb = hw;
-      const float jaF = W.zeroA ? 0.f : ja, jbF = W.zeroB ? 0.f : jb;
-
-      const float JI00 = group_sum8(gx * gx), JI11 = group_sum8(gy * gy), JI10 = group_sum8(gx * gy);
-      const float JabJI00 = group_sum8(ja * gx), JabJI01 = group_sum8(ja * gy), JabJI10 = group_sum8(jb * gx), JabJI11 = group_sum8(jb * gy);
-      const float Jab00 = group_sum8(ja * ja), Jab01 = group_sum8(ja * jb), Jab11 = group_sum8(jb * jb);
-      const float JIr0 = group_sum8(resF * gx), JIr1 = group_sum8(resF * gy);
-      const float Jabr0 = group_sum8(resF * jaF), Jabr1 = group_sum8(resF * jbF);
-      const float rr = group_sum8(resF * resF);
-      const float energy = group_sum8(e_px);
-      // the reference sums hw*hw*(hitColor[1]^2+hitColor[2]^2) with hitColor already multiplied by hw (Residuals.cpp:L217-244)
-      const float wJI2 = group_sum8(hw * hw * (gx * gx + gy * gy));
-
-      // ---- classification (Residuals.cpp:L260-273) and per-residual outputs
-      int newState;
-      float newEnergy;
-      if (st == RES_NONE) {
-        newState = RES_NONE; newEnergy = 0.f;
-      } else if (!live) {
-        newState = RES_OOB; newEnergy = s_en[t][pl];  // OOB exits return the old state_energy
-      } else if (energy > TH || wJI2 < 2.f) {
-        newState = RES_OUTLIER; newEnergy = TH;
-      } else {
-        newState = RES_IN; newEnergy = energy;
-      }
-      const bool in = (newState == RES_IN);
-      if (j == 0 && st != RES_NONE) {
-        e_sum += newEnergy;
-        n_in += in; n_oob += (newState == RES_OOB); n_outl += (newState == RES_OUTLIER);
-      }
-      if (valid && j == 0) {
-        W.st_new[slot] = (uint8_t)newState;
-        W.en_new[slot] = newEnergy;
-        W.en_wo[slot] = (st == RES_NONE || !live) ? -1.f : energy;
-        const size_t plane = (size_t)MAXF * mp;
-        W.cpt[slot] = cKu; W.cpt[plane + slot] = cKv; W.cpt[2 * plane + slot] = new_idepth;
-      }
-
-      if (in) {
-        // geometric Jacobians of the centre pixel (Residuals.cpp:L113-156): x = d(Ku)/d[C4|xi6], y = d(Kv)/d[C4|xi6]
-        float x[10], y[10];
-        {
-          const float dCx2 = drescale * (R20 * cu - R00);
-          const float dCx3 = fx * drescale * (R21 * cu - R01) * fyi;
-          const float dCy2 = fy * drescale * (R20 * cv - R10) * fxi;
-          const float dCy3 = drescale * (R21 * cv - R11);
-          x[0] = (Kl0 * dCx2 + cu) * 50.0f; x[1] = (Kl1 * dCx3) * 50.0f; x[2] = (dCx2 + 1.f) * 50.0f; x[3] = dCx3 * 50.0f;
-          y[0] = (Kl0 * dCy2) * 50.0f; y[1] = (Kl1 * dCy3 + cv) * 50.0f; y[2] = dCy2 * 50.0f; y[3] = (dCy3 + 1.f) * 50.0f;
-          x[4] = new_idepth * fx; x[5] = 0.f; x[6] = -new_idepth * cu * fx; x[7] = -cu * cv * fx; x[8] = (1.f + cu * cu) * fx; x[9] = -cv * fx;
-          y[4] = 0.f; y[5] = new_idepth * fy; y[6] = -new_idepth * cv * fy; y[7] = -(1.f + cv * cv) * fy; y[8] = cu * cv * fy; y[9] = cu * fy;
-        }
-        const float ddx = drescale * (t00 - t02 * cu) * fx;  // Jpdd (SCALE_IDEPTH = 1)
-        const float ddy = drescale * (t01 - t02 * cv) * fy;
-        // EFResidual::takeDataF (EnergyFunctionalStructs.cpp:L39-49) and the per-point terms of addPoint (AccumulatedTopHessian.cpp:L131-135)
-        const float J0 = JI00 * ddx + JI10 * ddy, J1 = JI10 * ddx + JI11 * ddy;  // JIdx2 * Jpdd
-        if (j == 0) {
-          float* rec = s_rec[pl][t];
-          float4 v0, v1, v2, v3;
-          v0.x = x[4] * J0 + y[4] * J1; v0.y = x[5] * J0 + y[5] * J1; v0.z = x[6] * J0 + y[6] * J1; v0.w = x[7] * J0 + y[7] * J1;
-          v1.x = x[8] * J0 + y[8] * J1; v1.y = x[9] * J0 + y[9] * J1;
-          v1.z = JabJI00 * ddx + JabJI01 * ddy; v1.w = JabJI10 * ddx + JabJI11 * ddy;
-          v2.x = J0 * ddx + J1 * ddy;            // Hdd
-          v2.y = JIr0 * ddx + JIr1 * ddy;        // bd
-          v2.z = x[0] * J0 + y[0] * J1; v2.w = x[1] * J0 + y[1] * J1;  // Hcd[0..1]
-          v3.x = x[2] * J0 + y[2] * J1; v3.y = x[3] * J0 + y[3] * J1;  // Hcd[2..3]
-          v3.z = 1.f; v3.w = 0.f;                                      // active flag
-          reinterpret_cast<float4*>(rec)[0] = v0;
-          reinterpret_cast<float4*>(rec)[1] = v1;
-          reinterpret_cast<float4*>(rec)[2] = v2;
-          reinterpret_cast<float4*>(rec)[3] = v3;
-          float4* gj = reinterpret_cast<float4*>(W.jpjd + (size_t)slot * 8);
-          gj[0] = v0; gj[1] = v1;
-        }
-        // rows of the pair's 13x13 block: lane j owns row j, lanes (j&1) own rows 8/9 (AccumulatorApprox::update/updateTopRight)
-        const float xr1 = pick8(x, j), yr1 = pick8(y, j);
-        const float xr2 = (j & 1) ? x[9] : x[8], yr2 = (j & 1) ? y[9] : y[8];
-        const float al1 = JI00 * xr1 + JI10 * yr1, be1 = JI10 * xr1 + JI11 * yr1;
-        const float al2 = JI00 * xr2 + JI10 * yr2, be2 = JI10 * xr2 + JI11 * yr2;
-#pragma unroll
-        for (int c = 0; c < 10; c++) {
-          acc1[c] += al1 * x[c] + be1 * y[c];
-          acc2[c] += al2 * x[c] + be2 * y[c];
-        }
-        acc1[10] += xr1 * JabJI00 + yr1 * JabJI01;
-        acc1[11] += xr1 * JabJI10 + yr1 * JabJI11;
-        acc1[12] += xr1 * JIr0 + yr1 * JIr1;
-        acc2[10] += xr2 * JabJI00 + yr2 * JabJI01;
-        acc2[11] += xr2 * JabJI10 + yr2 * JabJI11;
-        acc2[12] += xr2 * JIr0 + yr2 * JIr1;
-        br[0] += Jab00; br[1] += Jab01; br[2] += Jabr0; br[3] += Jab11; br[4] += Jabr1; br[5] += rr;
-      }
-    }
-    // ---- cross-group reduction, then fp64 reductions into the pair's global accumulator
-    double* tp = acc + (size_t)(h * nf + t) * TOP_PART;
-#pragma unroll
-    for (int c = 0; c < TOP_COLS; c++) {
-      const float a1 = cross_group_sum(acc1[c]);
-      const float a2 = cross_group_sum(acc2[c]);
-      if (lane < 8) red_add(tp + lane * TOP_COLS + c, (double)a1);
-      if (lane < 2) red_add(tp + (8 + lane) * TOP_COLS + c, (double)a2);
-    }
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-      const float b = cross_group_sum(br[c]);
-      if (lane == 0) red_add(tp + TOP_ROWS * TOP_COLS + c, (double)b);
-    }
-    float es = e_sum, fin = (float)n_in, foob = (float)n_oob, fout = (float)n_outl;
-#pragma unroll
-    for (int m = 1; m < 32; m <<= 1) {
-      es += __shfl_xor_sync(0xffffffffu, es, m);
-      fin += __shfl_xor_sync(0xffffffffu, fin, m);
-      foob += __shfl_xor_sync(0xffffffffu, foob, m);
-      fout += __shfl_xor_sync(0xffffffffu, fout, m);
-    }
-    if (lane == 0) { s_misc[t][0] = es; s_misc[t][1] = fin; s_misc[t][2] = foob; s_misc[t][3] = fout; }
-  }
-  __syncthreads();
-  if (tid < 4) {
-    double s = 0.0;
-    for (int tt = 0; tt < nf; tt++) s += (double)s_misc[tt][tid];
-    red_add(acc + (size_t)nf * nf * TOP_PART + (size_t)W.ntiles * 16 + tid, s);
-  }
-
-  // ---------------------------------------------------------------- phase B
-  const int N = W.N;
-  for (int pl = tid; pl < ch_count; pl += nthreads) {  // AccumulatedSCHessian.cpp:L36-58
-    const int p = ch_start + pl;
-    float Hdd = 0.f, bd = 0.f, Hcd0 = 0.f, Hcd1 = 0.f, Hcd2 = 0.f, Hcd3 = 0.f;
-    int ngood = 0;
-    for (int tt = 0; tt < nf; tt++) {
-      const float* rec = s_rec[pl][tt];
-      if (rec[14] != 0.f) {
-        ngood++;
-        Hdd += rec[8]; bd += rec[9]; Hcd0 += rec[10]; Hcd1 += rec[11]; Hcd2 += rec[12]; Hcd3 += rec[13];
-      }
-    }
-    float HdiF = 0.f, bdSum = 0.f;
-    if (ngood > 0) {
-      const float prior = s_prior[pl];
-      float H = Hdd + prior;
-      if (H < 1e-10f) H = 1e-10f;
-      HdiF = 1.0f / H;
-      bdSum = bd + prior * (s_id[pl] - s_idz[pl]);
-      s_W[pl][0] = Hcd0; s_W[pl][1] = Hcd1; s_W[pl][2] = Hcd2; s_W[pl][3] = Hcd3;
-      s_W[pl][N] = bdSum;
-    }
-    s_hdi[pl] = HdiF;
-    float4* po = reinterpret_cast<float4*>(W.pout + (size_t)p * 8);
-    po[0] = make_float4(Hdd, bd, Hcd0, Hcd1);
-    po[1] = make_float4(Hcd2, Hcd3, HdiF, bdSum);
-  }
-  for (int idx = tid; idx < ch_count * nf * 8; idx += nthreads) {
-    const int k = idx & 7;
-    const int f = (idx >> 3) % nf;
-    const int pl = (idx >> 3) / nf;
-    float val = 0.f;
-    if (f == h) {
-      for (int tt = 0; tt < nf; tt++) {
-        const float* rec = s_rec[pl][tt];
-        if (rec[14] != 0.f) {
-          const float* A = &s_adH[tt][k * 8];
-#pragma unroll
-          for (int c = 0; c < 8; c++) val += A[c] * rec[c];
-        }
-      }
-    } else {
-      const float* rec = s_rec[pl][f];
-      if (rec[14] != 0.f) val = s_adT[f][k] * rec[k];
-    }
-    s_W[pl][4 + 8 * f + k] = val;
-  }
-  __syncthreads();
-
-  // ---------------------------------------------------------------- phase C
-  const int T = W.T;
-  double* scp = acc + (size_t)nf * nf * TOP_PART;
-  for (int tile = tid; tile < W.ntiles; tile += nthreads) {
-    int ti = 0, rem = tile;
-    while (rem >= T - ti) { rem -= T - ti; ti++; }
-    const int tj = ti + rem;
-    float a[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-      for (int c = 0; c < 4; c++) a[r][c] = 0.f;
-    for (int pl = 0; pl < ch_count; pl++) {
-      const float s = s_hdi[pl];
-      const float4 wi = *reinterpret_cast<const float4*>(&s_W[pl][4 * ti]);
-      const float4 wj = *reinterpret_cast<const float4*>(&s_W[pl][4 * tj]);
-      const float si[4] = {s * wi.x, s * wi.y, s * wi.z, s * wi.w};
-      const float vj[4] = {wj.x, wj.y, wj.z, wj.w};
-#pragma unroll
-      for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) a[r][c] += si[r] * vj[c];
-    }
-    double* o = scp + (size_t)tile * 16;
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-      for (int c = 0; c < 4; c++) red_add(o + r * 4 + c, (double)a[r][c]);
-  }
-}
-
 
 // 13x13 pair block from the 136-double layout (rows 0..9 full, then the 6 bottom-right entries)
 __device__ __forceinline__ double h13(const double* S, int r, int c) {
@@ -461,127 +27,113 @@ __device__ __forceinline__ double h13(const double* S, int r, int c) {
   return S[TOP_ROWS * TOP_COLS + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5))];
 }
 
-// Stitch to the dense system (AccumulatedTopHessian.cpp:L241-303 in gather form).  One CTA per block-row of the
-// (8nf+4)^2 matrix: CTA a < nf owns the 8 rows of frame a, CTA nf owns the 4 calibration rows.  All operands of a
-// block-row (the 2(nf-1) pair blocks touching frame a and their adjoints) are staged in shared memory with one
-// coalesced pass, the 8x8 triple products are formed cooperatively as  Ah * (P * Ah^T), everything in fp64.
-constexpr int ST_THREADS = 256;
+// ---------------------------------------------------------------------------------------------------------------
+// ba_stitch_kernel — AccumulatedTopHessian.cpp:L241-303 (stitchDoubleInternal + symmetrisation) in gather form, fp64.
+// Launched with programmatic stream serialisation right behind ba_point_kernel: its CTAs are resident early and wait in
+// griddepcontrol.wait.  CTA a < nf owns the 8 rows of frame a, CTA nf the 4 calibration rows + the Schur tiles + counters
+// + the zeroing of the next iteration's accumulators.  Per block row: one wave of 16-byte cp.async copies stages the
+// 2(nf-1) pair blocks touching frame a with their adjoints; B = [P|Q|p] is expanded from the symmetric storage,
+// G = adHost*B and GA = (adHost P) adHost^T are formed once; every output entry is then a short sum (adTarget is diagonal).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int ST_THREADS = 512;
+struct alignas(16) StitchSmem {
+  double raw[2][MAXF][TOP_PART];  // [0][t] pair (a,t) (a hosts), [1][t] pair (t,a) (a is target)
+  double Ah[2][MAXF][64];
+  double d[2][MAXF][8];
+  double B[2][MAXF][8][13];       // [P | Q | p] rows 4..11 of the pair block
+  double G[2][MAXF][8][13];       // adHost * B   ([1]: only the P part is used)
+  double GA[MAXF][64];            // (adHost P) adHost^T for the pairs hosted by a
+};
+
 __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_constant__ BAWinDev W) {
+  extern __shared__ __align__(16) unsigned char st_smem[];
+  StitchSmem& Q = *reinterpret_cast<StitchSmem*>(st_smem);
   const int nf = W.nf, N = W.N;
   const int tid = threadIdx.x;
-  const int a = blockIdx.x;  // frame index, or nf for the calibration rows
-  const int gt = blockIdx.x * blockDim.x + tid, gthreads = gridDim.x * blockDim.x;
-  const int nacc = acc_doubles(nf, W.ntiles);
-  for (int i = gt; i < nacc; i += gthreads) W.acc_next[i] = 0.0;  // accumulators of the next iteration
+  const int a = blockIdx.x;
+  const BAAdj* __restrict__ A = W.adj;
+  // adjoints do not depend on the point kernel: prefetch them before waiting on the grid dependency
+  if (a < nf) {
+    for (int e = tid; e < nf * 32; e += ST_THREADS) {
+      const int t = e >> 5, k = (e & 31) * 2;
+      cp_async16(&Q.Ah[0][t][k], &A->adHost[a * nf + t][k]);
+      cp_async16(&Q.Ah[1][t][k], &A->adHost[t * nf + a][k]);
+    }
+    for (int e = tid; e < nf * 4; e += ST_THREADS) {
+      const int t = e >> 2, k = (e & 3) * 2;
+      cp_async16(&Q.d[0][t][k], &A->adTdiag[a * nf + t][k]);
+      cp_async16(&Q.d[1][t][k], &A->adTdiag[t * nf + a][k]);
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (W.dbg & 8) return;
   const double* __restrict__ TS = W.acc;
   const double* __restrict__ SC = W.acc + (size_t)nf * nf * TOP_PART;
   double* __restrict__ R = W.result;
-  double* __restrict__ Rsc = R + (size_t)(N * N + N);
-  if (gt < ACC_MISC) R[2 * (size_t)(N * N + N) + gt] = SC[(size_t)W.ntiles * 16 + gt];
-  const BAAdj* __restrict__ A = W.adj;
-
-  // ---- Schur part: rows of this CTA straight from the Gram tiles
-  {
-    const int r0 = (a < nf) ? 4 + 8 * a : 0, nr = (a < nf) ? 8 : 4;
-    for (int e = tid; e < nr * (N + 1); e += ST_THREADS) {
-      const int I = r0 + e / (N + 1), J = e % (N + 1);
-      int r = I, c = J;
-      if (c < N && r > c) { int tmp = r; r = c; c = tmp; }
-      const int ti = r >> 2, tj = c >> 2;
-      const int tile = ti * W.T - (ti * (ti - 1)) / 2 + (tj - ti);
-      const double v = SC[(size_t)tile * 16 + (r & 3) * 4 + (c & 3)];
-      if (J < N) Rsc[(size_t)I * N + J] = v; else Rsc[(size_t)N * N + I] = v;
-    }
-  }
-
-  __shared__ double s_S[2][MAXF][TOP_PART];  // [0][t] = pair (a,t) (a is host), [1][t] = pair (t,a) (a is target)
-  __shared__ double s_Ah[2][MAXF][64];       // [0][t] = adHost(a,t), [1][t] = adHost(t,a)
-  __shared__ double s_d[2][MAXF][8];         // [0][t] = adTdiag(a,t), [1][t] = adTdiag(t,a)
-  __shared__ double s_M[MAXF][64];           // P(a,t) * Ah(a,t)^T
+  const int nH = N * N + N;
 
   if (a == nf) {
-    // calibration rows: H[C,C] = sum R ; b[C] = sum q ; H[C, frame] is written (transposed) by the frame CTAs
-    for (int e = tid; e < 4 * 5; e += ST_THREADS) {
-      const int i = e / 5, j = e % 5;
+    // calibration rows, raw Schur tiles + counters, and the next iteration's accumulators
+    const int nsc = W.ntiles * 16 + ACC_MISC;
+    for (int e = tid; e < nsc; e += ST_THREADS) R[nH + e] = __ldcg(SC + e);
+    const int nacc = acc_doubles(nf, W.ntiles);
+    for (int i = tid; i < nacc; i += ST_THREADS) W.acc_next[i] = 0.0;
+    if (tid < 20) {
+      const int i = tid / 5, j = tid - i * 5;
       double v = 0.0;
-      for (int pr = 0; pr < nf * nf; pr++) v += h13(TS + (size_t)pr * TOP_PART, i, j < 4 ? j : 12);
+      const int c = (j < 4) ? j : 12;
+      const int rr = i < c ? i : c, cc = i < c ? c : i;  // rows 0..3 are stored in full: entry (rr, cc) with rr <= cc
+      for (int pr = 0; pr < nf * nf; pr++) v += __ldcg(TS + (size_t)pr * TOP_PART + rr * TOP_COLS + cc);
       if (j < 4) R[(size_t)i * N + j] = v; else R[(size_t)N * N + i] = v;
     }
     return;
   }
-  for (int e = tid; e < nf * TOP_PART; e += ST_THREADS) {
-    const int t = e / TOP_PART, k = e - t * TOP_PART;
-    s_S[0][t][k] = TS[(size_t)(a * nf + t) * TOP_PART + k];
-    s_S[1][t][k] = TS[(size_t)(t * nf + a) * TOP_PART + k];
+  for (int e = tid; e < nf * (TOP_PART / 2); e += ST_THREADS) {
+    const int t = e / (TOP_PART / 2), k = (e - t * (TOP_PART / 2)) * 2;
+    cp_async16(&Q.raw[0][t][k], TS + (size_t)(a * nf + t) * TOP_PART + k);
+    cp_async16(&Q.raw[1][t][k], TS + (size_t)(t * nf + a) * TOP_PART + k);
   }
-  for (int e = tid; e < nf * 64; e += ST_THREADS) {
-    const int t = e >> 6, k = e & 63;
-    s_Ah[0][t][k] = A->adHost[a * nf + t][k];
-    s_Ah[1][t][k] = A->adHost[t * nf + a][k];
-  }
-  for (int e = tid; e < nf * 8; e += ST_THREADS) {
-    const int t = e >> 3, k = e & 7;
-    s_d[0][t][k] = A->adTdiag[a * nf + t][k];
-    s_d[1][t][k] = A->adTdiag[t * nf + a][k];
+  cp_async_wait_all();
+  __syncthreads();
+  for (int e = tid; e < 2 * nf * 104; e += ST_THREADS) {  // B[s][t][k][c] = H13[4+k][col(c)], col = 4..11, 0..3, 12
+    const int s2 = e / (nf * 104), e1 = e - s2 * nf * 104, t = e1 / 104, r = e1 - t * 104, k = r / 13, c = r - k * 13;
+    const int col = (c < 8) ? 4 + c : (c < 12 ? c - 8 : 12);
+    (&Q.B[s2][t][0][0])[r] = (t == a) ? 0.0 : h13(Q.raw[s2][t], 4 + k, col);
   }
   __syncthreads();
-  // M[t] = P(a,t) * Ah(a,t)^T   (8x8 each)
-  for (int e = tid; e < nf * 64; e += ST_THREADS) {
-    const int t = e >> 6, k = (e >> 3) & 7, j = e & 7;
+  for (int e = tid; e < 2 * nf * 104; e += ST_THREADS) {  // G = Ah (8x8) * B (8x13)
+    const int s2 = e / (nf * 104), e1 = e - s2 * nf * 104, t = e1 / 104, r = e1 - t * 104, i = r / 13, c = r - i * 13;
+    if (s2 == 1 && c >= 8) continue;
     double m = 0.0;
-    if (t != a) {
 #pragma unroll
-      for (int l = 0; l < 8; l++) m += h13(s_S[0][t], 4 + k, 4 + l) * s_Ah[0][t][j * 8 + l];
-    }
-    s_M[t][e & 63] = m;
+    for (int k = 0; k < 8; k++) m += Q.Ah[s2][t][i * 8 + k] * Q.B[s2][t][k][c];
+    (&Q.G[s2][t][0][0])[r] = m;
   }
   __syncthreads();
-  // outputs of this block-row: 8 rows x (N+1) columns
+  for (int e = tid; e < nf * 64; e += ST_THREADS) {  // GA = G[0][:, 0:8] * Ah[0]^T
+    const int t = e >> 6, i = (e >> 3) & 7, j = e & 7;
+    double m = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) m += Q.G[0][t][i][k] * Q.Ah[0][t][j * 8 + k];
+    Q.GA[t][e & 63] = m;
+  }
+  __syncthreads();
   const int r0 = 4 + 8 * a;
   for (int e = tid; e < 8 * (N + 1); e += ST_THREADS) {
-    const int ia = e / (N + 1), J = e % (N + 1);
+    const int ia = e / (N + 1), J = e - ia * (N + 1);
     double v = 0.0;
-    if (J == N) {  // b[a] = sum_t Ah(a,t) p(a,t) + At(t,a) p(t,a)
-      for (int t = 0; t < nf; t++) {
-        if (t == a) continue;
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) s += s_Ah[0][t][ia * 8 + k] * h13(s_S[0][t], 4 + k, 12);
-        v += s + s_d[1][t][ia] * h13(s_S[1][t], 4 + ia, 12);
-      }
-      R[(size_t)N * N + r0 + ia] = v;
-      continue;
-    }
-    if (J < 4) {  // H[a,C] = sum_t Ah(a,t) Q(a,t) + At(t,a) Q(t,a) ; mirrored into H[C,a]
-      for (int t = 0; t < nf; t++) {
-        if (t == a) continue;
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) s += s_Ah[0][t][ia * 8 + k] * h13(s_S[0][t], 4 + k, J);
-        v += s + s_d[1][t][ia] * h13(s_S[1][t], 4 + ia, J);
-      }
-      R[(size_t)(r0 + ia) * N + J] = v;
-      R[(size_t)J * N + r0 + ia] = v;
+    if (J == N || J < 4) {  // b[a] / H[a,C] = sum_t Ah(a,t) (p|Q)(a,t) + At(t,a) (p|Q)(t,a)
+      const int c = (J == N) ? 12 : 8 + J;
+      for (int t = 0; t < nf; t++) v += Q.G[0][t][ia][c] + Q.d[1][t][ia] * Q.B[1][t][ia][c];
+      if (J == N) R[(size_t)N * N + r0 + ia] = v;
+      else { R[(size_t)(r0 + ia) * N + J] = v; R[(size_t)J * N + r0 + ia] = v; }
       continue;
     }
     const int fb = (J - 4) >> 3, jb = (J - 4) & 7;
-    if (fb == a) {  // diagonal block: sum_t Ah M[t] + At(t,a) P(t,a) At(t,a)
-      for (int t = 0; t < nf; t++) {
-        if (t == a) continue;
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) s += s_Ah[0][t][ia * 8 + k] * s_M[t][k * 8 + jb];
-        v += s + s_d[1][t][ia] * h13(s_S[1][t], 4 + ia, 4 + jb) * s_d[1][t][jb];
-      }
-    } else {  // off-diagonal: raw[a,fb](ia,jb) + raw[fb,a](jb,ia), raw[h,t] = Ah P At^T
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) s += s_Ah[0][fb][ia * 8 + k] * h13(s_S[0][fb], 4 + k, 4 + jb);
-      v = s * s_d[0][fb][jb];
-      double s2 = 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) s2 += s_Ah[1][fb][jb * 8 + k] * h13(s_S[1][fb], 4 + k, 4 + ia);
-      v += s2 * s_d[1][fb][ia];
+    if (fb == a) {  // diagonal block: sum_t (Ah P Ah^T)(a,t) + At(t,a) P(t,a) At(t,a)
+      for (int t = 0; t < nf; t++) v += Q.GA[t][ia * 8 + jb] + Q.d[1][t][ia] * Q.B[1][t][ia][jb] * Q.d[1][t][jb];
+    } else {  // raw[a,b](ia,jb) + raw[b,a](jb,ia), raw[h,t] = (Ah P) At^T
+      v = Q.G[0][fb][ia][jb] * Q.d[0][fb][jb] + Q.G[1][fb][jb][ia] * Q.d[1][fb][ia];
     }
     R[(size_t)(r0 + ia) * N + J] = v;
   }
@@ -654,13 +206,24 @@ __global__ void l2_flush_kernel(float4* buf, size_t n) {
 // ---------------------------------------------------------------------------------------------------------------
 // launch helpers (called from ba_api.cu)
 // ---------------------------------------------------------------------------------------------------------------
-void launch_point_kernel(const BAWinDev& W, const BAIter& it, cudaStream_t s) {
-  dim3 grid(W.nchunks), block(32 * (W.nf < 2 ? 2 : W.nf));
-  if (W.P == 8) ba_point_kernel<8><<<grid, block, 0, s>>>(W, it);
-  else if (W.P == 16) ba_point_kernel<16><<<grid, block, 0, s>>>(W, it);
-  else ba_point_kernel<32><<<grid, block, 0, s>>>(W, it);
+void launch_stitch_kernel(const BAWinDev& W, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(ba_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StitchSmem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(W.nf + 1);
+  cfg.blockDim = dim3(ST_THREADS);
+  cfg.dynamicSmemBytes = sizeof(StitchSmem);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, ba_stitch_kernel, W);
 }
-void launch_stitch_kernel(const BAWinDev& W, cudaStream_t s) { ba_stitch_kernel<<<W.nf + 1, ST_THREADS, 0, s>>>(W); }
 void launch_resub_kernel(const BAWinDev& W, const BAIter& it, int apply, double* sums, cudaStream_t s) {
   ba_resub_kernel<<<(W.npts + 127) / 128, 128, 0, s>>>(W, it, apply, sums);
 }

@@ -165,6 +165,12 @@ int dmv_ba_last_timing(dmv_ba* ba, float ms[4]);
  * and the time from the start of the iteration to the end of the point kernel. */
 int dmv_ba_bench_device(dmv_ba* ba, const double* x, int iters, int flush_l2, float* ms_per_iter, float* ms_point_kernel);
 int dmv_ba_kernel_launch_count(dmv_ba* ba, long long* n);
+/* enable/disable the CUDA-event timing of dmv_ba_linearize / dmv_ba_gn_step (off by default: 4 event records per call) */
+int dmv_ba_set_timing(dmv_ba* ba, int enable);
+/* wall-clock time of `iters` x { dmv_ba_gn_step(x, st) ; dmv_ba_apply_res() } issued from C, milliseconds per iteration */
+int dmv_ba_bench_e2e(dmv_ba* ba, const double* x, const dmv_ba_state* st, int iters, double* ms_per_iter);
+/* phase timestamps of the point kernel (DMV_DBG=16 experiments only) */
+int dmv_ba_debug_clocks(dmv_ba* ba, unsigned long long* out, int cap);
 /* bytes copied host->device and device->host by one dmv_ba_gn_step / dmv_ba_linearize call */
 int dmv_ba_io_bytes(dmv_ba* ba, long long* h2d, long long* d2h);
 
