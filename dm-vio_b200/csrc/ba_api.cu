@@ -40,7 +40,10 @@ struct dmv_ba {
   float* d_stage_img = nullptr;
   BAAdj* d_adj = nullptr;
   float2* d_uv = nullptr;
-  float *d_idepth = nullptr, *d_idepth_zero = nullptr, *d_idepth_backup = nullptr, *d_color = nullptr, *d_weights = nullptr, *d_priorF = nullptr;
+  float* d_idepth[2] = {nullptr, nullptr};  // ping-pong: [cur] current depths, [bak] FullSystem::backupState copy
+  int id_cur = 0, id_bak = 0;
+  bool zero_alias = false;                  // idepth_zero == idepth (true after any step / restore)
+  float *d_idepth_zero = nullptr, *d_color = nullptr, *d_weights = nullptr, *d_priorF = nullptr;
   uint8_t* d_st_in = nullptr;
   float* d_en_in = nullptr;
   uint8_t* d_st_new[2] = {nullptr, nullptr};
@@ -100,10 +103,17 @@ static int fill_descriptor(dmv_ba* b) {
   for (int h = 0; h <= MAXF; h++) { W.host_start[h] = b->host_start[h]; W.chunk_beg[h] = b->chunk_beg[h]; }
   for (int f = 0; f < b->nf; f++) W.img[f] = b->d_img[b->slots[f]];
   W.adj = b->d_adj;
-  W.uv = b->d_uv; W.idepth = b->d_idepth; W.idepth_zero = b->d_idepth_zero; W.idepth_backup = b->d_idepth_backup;
+  W.uv = b->d_uv;
+  W.idepth = b->d_idepth[b->id_cur];
+  W.idepth_zero = b->zero_alias ? b->d_idepth[b->id_cur] : b->d_idepth_zero;
+  W.idepth_backup = b->d_idepth[b->id_bak];
+  W.idepth_out = b->d_idepth[1 - b->id_bak];
   W.color = b->d_color; W.weights = b->d_weights; W.priorF = b->d_priorF;
-  W.st_in = b->d_st_in; W.en_in = b->d_en_in;
   const int t = b->tent, c2 = 1 - b->tent;
+  // PointFrameResidual::applyRes made state_NewState / state_NewEnergy the residual's state (Residuals.cpp:L325-326): once a
+  // linearisation has been committed, the committed outputs ARE the input states (OOB stays OOB, its energy is returned)
+  W.st_in = b->have_committed ? b->d_st_new[c2] : b->d_st_in;
+  W.en_in = b->have_committed ? b->d_en_new[c2] : b->d_en_in;
   W.st_new = b->d_st_new[t]; W.en_new = b->d_en_new[t]; W.en_wo = b->d_en_wo[t]; W.cpt = b->d_cpt[t]; W.jpjd = b->d_jpjd[t]; W.pout = b->d_pout[t];
   W.c_st = b->d_st_new[c2]; W.c_jpjd = b->d_jpjd[c2]; W.c_pout = b->d_pout[c2];
   W.step = b->d_step;
@@ -153,9 +163,9 @@ int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
   CK(cudaMalloc(&b->d_stage_img, npx * 3 * sizeof(float)));
   CK(cudaMalloc(&b->d_adj, sizeof(BAAdj)));
   CK(cudaMalloc(&b->d_uv, sizeof(float2) * mp));
-  CK(cudaMalloc(&b->d_idepth, sizeof(float) * mp));
+  CK(cudaMalloc(&b->d_idepth[0], sizeof(float) * mp));
+  CK(cudaMalloc(&b->d_idepth[1], sizeof(float) * mp));
   CK(cudaMalloc(&b->d_idepth_zero, sizeof(float) * mp));
-  CK(cudaMalloc(&b->d_idepth_backup, sizeof(float) * mp));
   CK(cudaMalloc(&b->d_color, sizeof(float) * mp * 8));
   CK(cudaMalloc(&b->d_weights, sizeof(float) * mp * 8));
   CK(cudaMalloc(&b->d_priorF, sizeof(float) * mp));
@@ -204,8 +214,8 @@ int dmv_ba_destroy(dmv_ba* b) {
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (int f = 0; f < MAXF; f++) cudaFree(b->d_img[f]);
-  cudaFree(b->d_stage_img); cudaFree(b->d_adj); cudaFree(b->d_uv); cudaFree(b->d_idepth);
-  cudaFree(b->d_idepth_zero); cudaFree(b->d_idepth_backup); cudaFree(b->d_color); cudaFree(b->d_weights); cudaFree(b->d_priorF);
+  cudaFree(b->d_stage_img); cudaFree(b->d_adj); cudaFree(b->d_uv); cudaFree(b->d_idepth[0]); cudaFree(b->d_idepth[1]);
+  cudaFree(b->d_idepth_zero); cudaFree(b->d_color); cudaFree(b->d_weights); cudaFree(b->d_priorF);
   cudaFree(b->d_st_in); cudaFree(b->d_en_in);
   for (int k = 0; k < 2; k++) {
     cudaFree(b->d_st_new[k]); cudaFree(b->d_en_new[k]); cudaFree(b->d_en_wo[k]); cudaFree(b->d_cpt[k]); cudaFree(b->d_jpjd[k]);
@@ -302,9 +312,10 @@ int dmv_ba_set_points(dmv_ba* b, int npts, const int32_t* host, const float* u, 
   for (int i = 0; i < npts; i++) { s[2 * i] = u[i]; s[2 * i + 1] = v[i]; }
   CK(cudaMemcpyAsync(b->d_uv, s, sizeof(float2) * npts, cudaMemcpyHostToDevice, b->stream));
   CK(cudaStreamSynchronize(b->stream));
-  CK(cudaMemcpy(b->d_idepth, idepth, sizeof(float) * npts, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(b->d_idepth_backup, idepth, sizeof(float) * npts, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(b->d_idepth_zero, idepth_zero ? idepth_zero : idepth, sizeof(float) * npts, cudaMemcpyHostToDevice));
+  b->id_cur = b->id_bak = 0;
+  CK(cudaMemcpy(b->d_idepth[0], idepth, sizeof(float) * npts, cudaMemcpyHostToDevice));
+  b->zero_alias = (idepth_zero == nullptr);
+  if (idepth_zero) CK(cudaMemcpy(b->d_idepth_zero, idepth_zero, sizeof(float) * npts, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(b->d_color, color8, sizeof(float) * 8 * npts, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(b->d_weights, weights8, sizeof(float) * 8 * npts, cudaMemcpyHostToDevice));
   if (priorF) CK(cudaMemcpy(b->d_priorF, priorF, sizeof(float) * npts, cudaMemcpyHostToDevice));
@@ -375,8 +386,11 @@ static int stage_state(dmv_ba* b, const dmv_ba_state* st) {
   std::memcpy(it.calib, st->calib, sizeof(it.calib));
   for (int f = 0; f < nf; f++) it.TH[f] = st->frameEnergyTH[f];
   std::memcpy(it.precalc, st->precalc, sizeof(float) * 32 * nf * nf);
-  if (st->idepth) CK(cudaMemcpyAsync(b->d_idepth, st->idepth, sizeof(float) * b->npts, cudaMemcpyHostToDevice, b->stream));
-  if (st->idepth_zero) CK(cudaMemcpyAsync(b->d_idepth_zero, st->idepth_zero, sizeof(float) * b->npts, cudaMemcpyHostToDevice, b->stream));
+  if (st->idepth) CK(cudaMemcpyAsync(b->d_idepth[b->id_cur], st->idepth, sizeof(float) * b->npts, cudaMemcpyHostToDevice, b->stream));
+  if (st->idepth_zero) {
+    CK(cudaMemcpyAsync(b->d_idepth_zero, st->idepth_zero, sizeof(float) * b->npts, cudaMemcpyHostToDevice, b->stream));
+    b->zero_alias = false;
+  }
   b->have_state = true;
   return DMV_OK;
 }
@@ -414,6 +428,7 @@ static int enqueue_linearize(dmv_ba* b, bool with_resub) {
 }
 
 static int finish_linearize(dmv_ba* b, dmv_ba_lin_result* out, double sums[3]) {
+  if (b->h_up->it.have_x) { b->id_cur = 1 - b->id_bak; b->zero_alias = true; }  // the fused step wrote idepth_backup + step
   CK(cudaStreamSynchronize(b->stream));
   const double* tail = b->h_result[b->tent] + (b->N * b->N + b->N) + b->ntiles * 16;
   if (out) { out->energy = tail[0]; out->n_in = (int)tail[1]; out->n_oob = (int)tail[2]; out->n_outlier = (int)tail[3]; }
@@ -482,6 +497,7 @@ int dmv_ba_resubstitute(dmv_ba* b, const double* x, float* step_out, int apply, 
   if (step_out) CK(cudaMemcpyAsync(step_out, b->d_step, sizeof(float) * b->npts, cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   if (sums) { sums[0] = tail[4]; sums[1] = tail[5]; sums[2] = tail[6]; }
+  if (apply) { b->id_cur = 1 - b->id_bak; b->zero_alias = true; }
   b->h_up->it.have_x = 0;
   return DMV_OK;
 }
@@ -504,24 +520,21 @@ int dmv_ba_gn_step(dmv_ba* b, const double* x, const dmv_ba_state* st, dmv_ba_li
 
 int dmv_ba_backup_points(dmv_ba* b) {
   if (!b || b->npts < 1) return set_error(DMV_ERR_STATE, "points not set");
-  CK(cudaSetDevice(b->device));
-  CK(cudaMemcpyAsync(b->d_idepth_backup, b->d_idepth, sizeof(float) * b->npts, cudaMemcpyDeviceToDevice, b->stream));
-  CK(cudaStreamSynchronize(b->stream));
+  b->id_bak = b->id_cur;  // ping-pong: the next step writes the other buffer, nothing is copied
   return DMV_OK;
 }
 int dmv_ba_restore_points(dmv_ba* b) {
   if (!b || b->npts < 1) return set_error(DMV_ERR_STATE, "points not set");
-  CK(cudaSetDevice(b->device));
-  CK(cudaMemcpyAsync(b->d_idepth, b->d_idepth_backup, sizeof(float) * b->npts, cudaMemcpyDeviceToDevice, b->stream));
-  CK(cudaMemcpyAsync(b->d_idepth_zero, b->d_idepth_backup, sizeof(float) * b->npts, cudaMemcpyDeviceToDevice, b->stream));
-  CK(cudaStreamSynchronize(b->stream));
+  b->id_cur = b->id_bak;
+  b->zero_alias = true;   // loadSateBackup: setIdepthZero(idepth_backup) (FullSystemOptimize.cpp:L380)
   return DMV_OK;
 }
 int dmv_ba_get_idepth(dmv_ba* b, float* idepth, float* idepth_zero) {
   if (!b || b->npts < 1) return set_error(DMV_ERR_STATE, "points not set");
   CK(cudaSetDevice(b->device));
-  if (idepth) CK(cudaMemcpy(idepth, b->d_idepth, sizeof(float) * b->npts, cudaMemcpyDeviceToHost));
-  if (idepth_zero) CK(cudaMemcpy(idepth_zero, b->d_idepth_zero, sizeof(float) * b->npts, cudaMemcpyDeviceToHost));
+  CK(cudaStreamSynchronize(b->stream));
+  if (idepth) CK(cudaMemcpy(idepth, b->d_idepth[b->id_cur], sizeof(float) * b->npts, cudaMemcpyDeviceToHost));
+  if (idepth_zero) CK(cudaMemcpy(idepth_zero, b->zero_alias ? b->d_idepth[b->id_cur] : b->d_idepth_zero, sizeof(float) * b->npts, cudaMemcpyDeviceToHost));
   return DMV_OK;
 }
 

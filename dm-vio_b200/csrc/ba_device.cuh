@@ -46,9 +46,10 @@ struct BAWinDev {
   const BAAdj* adj;
   // points
   const float2* uv;
-  float* idepth;
-  float* idepth_zero;
-  const float* idepth_backup;
+  const float* idepth;        // current inverse depths (read when no step is fused)
+  const float* idepth_zero;   // FEJ inverse depths (aliases idepth after the first step / restore: DM-VIO keeps them equal)
+  const float* idepth_backup; // FullSystem::backupState copy: ping-pong buffer, no copy kernel
+  float* idepth_out;          // where a fused / stand-alone step writes idepth_backup + step
   const float* color;        // [p][8]
   const float* weights;      // [p][8]
   const float* priorF;

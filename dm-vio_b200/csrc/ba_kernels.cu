@@ -157,8 +157,7 @@ __global__ void __launch_bounds__(128) ba_resub_kernel(const __grid_constant__ B
     nid = fabsf(idb);
     if (apply) {
       const float v = idb + step;
-      W.idepth[p] = v;
-      W.idepth_zero[p] = v;  // DM-VIO: setIdepthZero in doStepFromBackup (FullSystemOptimize.cpp:L268)
+      W.idepth_out[p] = v;  // DM-VIO: idepth_zero follows (FullSystemOptimize.cpp:L268); the host aliases the pointers
     }
   }
   __shared__ float s2[128], sn[128];

@@ -132,8 +132,7 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
           const float step = ngood > 0 ? -bsum * rs_po1.z : 0.f;
           const float v = rs_idb + step;
           W.step[p] = step;
-          W.idepth[p] = v;
-          W.idepth_zero[p] = v;  // DM-VIO: setIdepthZero in doStepFromBackup
+          W.idepth_out[p] = v;  // DM-VIO: idepth_zero follows (setIdepthZero in doStepFromBackup); the host aliases the pointers
           S.id[tid] = v;
           S.idz[tid] = v;
           step2 = step * step;

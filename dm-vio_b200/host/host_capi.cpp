@@ -1,0 +1,123 @@
+#include "host_capi.h"
+#include "coarse_tracker.h"
+#include "window_ba.h"
+#include <cstring>
+
+using namespace dmvio_b200;
+
+static SE3 mkSE3(const double R[9], const double t[3]) {
+  SE3 T;
+  for (int i = 0; i < 9; i++) T.R[i] = R[i];
+  for (int i = 0; i < 3; i++) T.t[i] = t[i];
+  return T;
+}
+static void initCalib(CalibHessian& C, const double vs[4]) {
+  const double v[4] = {vs[0] / SCALE_F, vs[1] / SCALE_F, vs[2] / SCALE_C, vs[3] / SCALE_C};
+  for (int i = 0; i < 4; i++) { C.value_zero[i] = v[i]; C.step[i] = 0; C.value_backup[i] = v[i]; }
+  C.setValueScaled(vs);
+}
+
+extern "C" {
+
+void* dmvh_window_create(int w, int h, int max_frames, int max_points, int device, const double cvs[4]) {
+  WindowBA* W = new WindowBA(w, h, max_frames, max_points, device);
+  initCalib(W->Hcalib, cvs);
+  return W;
+}
+void dmvh_window_destroy(void* p) { delete static_cast<WindowBA*>(p); }
+const char* dmvh_window_error(void* p) { return static_cast<WindowBA*>(p)->error().c_str(); }
+
+int dmvh_window_add_frame(void* p, const float* data, int is_image, const double R[9], const double t[3], const double state[10],
+                          const double state_zero[10], float ab_exposure, int frameID) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  if (!W->ok()) return -1;
+  const SE3 T = mkSE3(R, t);
+  return is_image ? W->insertFrame(data, T, state, state_zero, ab_exposure, frameID) : W->insertFrameDI(data, T, state, state_zero, ab_exposure, frameID);
+}
+int dmvh_window_set_points(void* p, int n, const int32_t* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
+                           const float* color8, const float* weights8, const uint8_t* hdp) {
+  static_cast<WindowBA*>(p)->insertPoints(n, host, u, v, idepth, idepth_zero, color8, weights8, hdp);
+  return 0;
+}
+int dmvh_window_set_residuals(void* p, int n, const int32_t* point, const int32_t* target) {
+  static_cast<WindowBA*>(p)->insertResiduals(n, point, target);
+  return 0;
+}
+int dmvh_window_prepare(void* p) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  if (!W->makeIDX()) return -1;
+  W->setAdjointsF();
+  W->setPrecalcValues();
+  return W->error().empty() ? 0 : -1;
+}
+double dmvh_window_linearize(void* p, int fix) { return static_cast<WindowBA*>(p)->linearizeAll(fix != 0); }
+void dmvh_window_apply(void* p) { static_cast<WindowBA*>(p)->applyRes_Reductor(); }
+int dmvh_window_solve(void* p, int iteration, double lambda, double* x) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  W->solveSystemF(iteration, lambda);
+  if (x) std::memcpy(x, W->lastX.data(), sizeof(double) * W->lastX.size());
+  return (int)W->lastX.size();
+}
+int dmvh_window_optimize(void* p, int its, double* log, int cap) {
+  std::vector<double> e;
+  const int n = static_cast<WindowBA*>(p)->optimize(its, &e);
+  for (int i = 0; i < cap; i++) log[i] = i < (int)e.size() ? e[i] : -1.0;
+  return n;
+}
+void dmvh_window_get_tables(void* p, float* precalc, double* adH, double* adT) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  if (precalc) std::memcpy(precalc, W->precalc.data(), sizeof(float) * W->precalc.size());
+  if (adH) std::memcpy(adH, W->adHost.data(), sizeof(double) * W->adHost.size());
+  if (adT) std::memcpy(adT, W->adTarget.data(), sizeof(double) * W->adTarget.size());
+}
+void dmvh_window_get_system(void* p, double* HA, double* bA, double* Hsc, double* bsc, double* HS, double* bS) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  auto cp = [](const std::vector<double>& v, double* o) { if (o && !v.empty()) std::memcpy(o, v.data(), sizeof(double) * v.size()); };
+  cp(W->last_HA, HA); cp(W->last_bA, bA); cp(W->last_Hsc, Hsc); cp(W->last_bsc, bsc); cp(W->lastHS, HS); cp(W->lastbS, bS);
+}
+void dmvh_window_get_states(void* p, double* st, float* idepth, float* th) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  if (st) W->getFrameStates(st);
+  if (idepth) W->getIdepths(idepth);
+  if (th) for (size_t f = 0; f < W->frameHessians.size(); f++) th[f] = W->frameHessians[f].frameEnergyTH;
+}
+double dmvh_window_energy_L(void* p) { return static_cast<WindowBA*>(p)->calcLEnergyF_MT(); }
+
+void* dmvh_ct_create(int w, int h, int levels, int max_points, int device, const double cvs[4]) {
+  CoarseTracker* C = new CoarseTracker(w, h, levels, max_points, device);
+  CalibHessian H;
+  initCalib(H, cvs);
+  C->makeK(H);
+  return C;
+}
+void dmvh_ct_destroy(void* p) { delete static_cast<CoarseTracker*>(p); }
+int dmvh_ct_set_ref(void* p, int n, const float* Ku, const float* Kv, const float* nid, const float* HdiF, const float* ref, double ra, double rb,
+                    float rexp) {
+  CoarseTracker* C = static_cast<CoarseTracker*>(p);
+  if (!C->ok()) return -1;
+  const float* lv[DMV_MAX_PYR_LEVELS];
+  size_t off = 0;
+  for (int l = 0; l < C->levels(); l++) { lv[l] = ref + off; off += (size_t)C->levelPixels(l) * 3; }
+  AffLight a; a.a = ra; a.b = rb;
+  C->setCoarseTrackingRef(n, Ku, Kv, nid, HdiF, lv, a, rexp);
+  return C->error().empty() ? 0 : -1;
+}
+int dmvh_ct_pc_n(void* p, int lvl) { return static_cast<CoarseTracker*>(p)->pc_n[lvl]; }
+int dmvh_ct_set_new_image(void* p, const float* image, float exposure) { return static_cast<CoarseTracker*>(p)->setNewFrame(image, exposure) ? 0 : -1; }
+int dmvh_ct_track(void* p, double R[9], double t[3], double* a, double* b, int coarsestLvl, const double minRes[5], double lastRes[5], double flow[3],
+                  int* iterations, long long* evaluations) {
+  CoarseTracker* C = static_cast<CoarseTracker*>(p);
+  SE3 T = mkSE3(R, t);
+  AffLight aff; aff.a = *a; aff.b = *b;
+  const bool good = C->trackNewestCoarse(T, aff, coarsestLvl, minRes);
+  for (int i = 0; i < 9; i++) R[i] = T.R[i];
+  for (int i = 0; i < 3; i++) t[i] = T.t[i];
+  *a = aff.a; *b = aff.b;
+  for (int i = 0; i < 5; i++) lastRes[i] = C->lastResiduals[i];
+  for (int i = 0; i < 3; i++) flow[i] = C->lastFlowIndicators[i];
+  if (iterations) *iterations = C->iterations;
+  if (evaluations) *evaluations = C->evaluations;
+  return good ? 1 : 0;
+}
+
+}  // extern "C"

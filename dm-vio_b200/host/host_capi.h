@@ -1,0 +1,37 @@
+/* C glue over the C++ host adapters (WindowBA, CoarseTracker) so that the Python tests and bench can drive them through
+ * ctypes.  Not part of the drop-in boundary (that is include/dmvio_b200.h); a C++ host links the classes directly. */
+#pragma once
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+void* dmvh_window_create(int w, int h, int max_frames, int max_points, int device, const double calib_value_scaled[4]);
+void dmvh_window_destroy(void* win);
+const char* dmvh_window_error(void* win);
+/* is_image: 1 = raw w*h float image (level-0 [I,dx,dy] built on the device), 0 = w*h*3 dI AoS */
+int dmvh_window_add_frame(void* win, const float* data, int is_image, const double R[9], const double t[3], const double state[10],
+                          const double state_zero[10], float ab_exposure, int frameID);
+int dmvh_window_set_points(void* win, int n, const int32_t* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
+                           const float* color8, const float* weights8, const uint8_t* hasDepthPrior);
+int dmvh_window_set_residuals(void* win, int n, const int32_t* point, const int32_t* target);
+int dmvh_window_prepare(void* win); /* makeIDX + setAdjointsF + setPrecalcValues */
+double dmvh_window_linearize(void* win, int fix);
+void dmvh_window_apply(void* win);
+int dmvh_window_solve(void* win, int iteration, double lambda, double* x_out);
+int dmvh_window_optimize(void* win, int its, double* energyLog, int cap);
+void dmvh_window_get_tables(void* win, float* precalc, double* adHost, double* adTarget);
+void dmvh_window_get_system(void* win, double* HA, double* bA, double* Hsc, double* bsc, double* lastHS, double* lastbS);
+void dmvh_window_get_states(void* win, double* states10, float* idepth, float* frameEnergyTH);
+double dmvh_window_energy_L(void* win);
+
+void* dmvh_ct_create(int w, int h, int levels, int max_points, int device, const double calib_value_scaled[4]);
+void dmvh_ct_destroy(void* ct);
+int dmvh_ct_set_ref(void* ct, int n, const float* Ku, const float* Kv, const float* new_idepth, const float* HdiF, const float* ref_dIp_concat,
+                    double ref_a, double ref_b, float ref_exposure);
+int dmvh_ct_pc_n(void* ct, int lvl);
+int dmvh_ct_set_new_image(void* ct, const float* image, float exposure);
+int dmvh_ct_track(void* ct, double R[9], double t[3], double* a, double* b, int coarsestLvl, const double minResForAbort[5],
+                  double lastResiduals[5], double flow[3], int* iterations, long long* evaluations);
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,421 @@
+// Host-side C++ mirror of FullSystem::optimize / EnergyFunctional on top of the C ABI — see window_ba.h.
+#include "window_ba.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+namespace dmvio_b200 {
+
+void AffLight::fromToVecExposure(float exposureF, float exposureT, AffLight g2F, AffLight g2T, double out[2]) {
+  if (exposureF == 0 || exposureT == 0) exposureT = exposureF = 1;  // util/NumType.h:L174-186
+  const double a = std::exp(g2T.a - g2F.a) * exposureT / exposureF;
+  out[0] = a;
+  out[1] = g2T.b - a * g2F.b;
+}
+
+void CalibHessian::setValue(const double v[4]) {  // HessianBlocks.h:L356-371
+  for (int i = 0; i < 4; i++) value[i] = v[i];
+  value_scaled[0] = SCALE_F * value[0]; value_scaled[1] = SCALE_F * value[1];
+  value_scaled[2] = SCALE_C * value[2]; value_scaled[3] = SCALE_C * value[3];
+  for (int i = 0; i < 4; i++) value_scaledf[i] = (float)value_scaled[i];
+  value_scaledi[0] = 1.0f / value_scaledf[0];
+  value_scaledi[1] = 1.0f / value_scaledf[1];
+  value_scaledi[2] = -value_scaledf[2] / value_scaledf[0];
+  value_scaledi[3] = -value_scaledf[3] / value_scaledf[1];
+  for (int i = 0; i < 4; i++) value_minus_value_zero[i] = value[i] - value_zero[i];
+}
+void CalibHessian::setValueScaled(const double vs[4]) {  // HessianBlocks.h:L373-387
+  const double v[4] = {vs[0] / SCALE_F, vs[1] / SCALE_F, vs[2] / SCALE_C, vs[3] / SCALE_C};
+  setValue(v);
+  for (int i = 0; i < 4; i++) { value_scaled[i] = vs[i]; value_scaledf[i] = (float)vs[i]; }
+  value_scaledi[0] = 1.0f / value_scaledf[0];
+  value_scaledi[1] = 1.0f / value_scaledf[1];
+  value_scaledi[2] = -value_scaledf[2] / value_scaledf[0];
+  value_scaledi[3] = -value_scaledf[3] / value_scaledf[1];
+}
+
+void FrameHessian::setState(const double s[10]) {  // HessianBlocks.h:L172-186
+  for (int i = 0; i < 10; i++) state[i] = s[i];
+  for (int i = 0; i < 3; i++) state_scaled[i] = SCALE_XI_TRANS * s[i];
+  for (int i = 3; i < 6; i++) state_scaled[i] = SCALE_XI_ROT * s[i];
+  state_scaled[6] = SCALE_A * s[6]; state_scaled[7] = SCALE_B * s[7];
+  state_scaled[8] = SCALE_A * s[8]; state_scaled[9] = SCALE_B * s[9];
+  PRE_worldToCam = SE3::exp(state_scaled) * worldToCam_evalPT;
+  PRE_camToWorld = PRE_worldToCam.inverse();
+}
+
+WindowBA::WindowBA(int w, int h, int max_frames, int max_points, int device) : w_(w), h_(h), max_frames_(max_frames), max_points_(max_points) {
+  dmv_ba_config cfg = {w, h, max_frames, max_points, device, 0};
+  if (dmv_ba_create(&cfg, &ba_) != DMV_OK) { err_ = dmv_last_error(); ba_ = nullptr; }
+  for (int i = 0; i < 4; i++) { Hcalib.value_zero[i] = 0; Hcalib.step[i] = 0; Hcalib.value_backup[i] = 0; }
+}
+WindowBA::~WindowBA() { if (ba_) dmv_ba_destroy(ba_); }
+
+bool WindowBA::fail(const char* what) {
+  err_ = std::string(what) + ": " + dmv_last_error();
+  return false;
+}
+
+int WindowBA::insertFrame(const float* image, const SE3& evalPT, const double state[10], const double state_zero[10], float ab_exposure, int frameID) {
+  if (!ba_ || nf() >= max_frames_) return -1;
+  FrameHessian f;
+  f.worldToCam_evalPT = evalPT;
+  for (int i = 0; i < 10; i++) { f.state_zero[i] = state_zero[i]; f.step[i] = 0; f.state_backup[i] = state[i]; }
+  f.ab_exposure = ab_exposure;
+  f.frameID = frameID;
+  f.slot = nf();
+  f.setState(state);
+  if (image && dmv_ba_upload_image(ba_, f.slot, image) != DMV_OK) { fail("dmv_ba_upload_image"); return -1; }
+  frameHessians.push_back(f);
+  return nf() - 1;
+}
+int WindowBA::insertFrameDI(const float* dI, const SE3& evalPT, const double state[10], const double state_zero[10], float ab_exposure, int frameID) {
+  const int idx = insertFrame(nullptr, evalPT, state, state_zero, ab_exposure, frameID);
+  if (idx < 0) return idx;
+  if (dmv_ba_upload_frame(ba_, frameHessians[idx].slot, dI) != DMV_OK) { fail("dmv_ba_upload_frame"); return -1; }
+  return idx;
+}
+
+void WindowBA::insertPoints(int n, const int* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
+                            const float* color8, const float* weights8, const unsigned char* hasDepthPrior) {
+  points.resize(n);
+  for (int i = 0; i < n; i++) {
+    PointHessian& p = points[i];
+    p.host = host[i]; p.u = u[i]; p.v = v[i]; p.idepth = idepth[i]; p.idepth_zero = idepth_zero ? idepth_zero[i] : idepth[i];
+    p.idepth_backup = p.idepth; p.step = 0;
+    for (int k = 0; k < 8; k++) { p.color[k] = color8[8 * i + k]; p.weights[k] = weights8[8 * i + k]; }
+    p.hasDepthPrior = hasDepthPrior && hasDepthPrior[i];
+    p.priorF = p.hasDepthPrior ? s.setting_idepthFixPrior * SCALE_IDEPTH * SCALE_IDEPTH : 0;  // EFPoint::takeData
+  }
+}
+void WindowBA::insertResiduals(int n, const int* point, const int* target) {
+  activeResiduals.resize(n);
+  for (int i = 0; i < n; i++) { activeResiduals[i] = PointFrameResidual(); activeResiduals[i].point = point[i]; activeResiduals[i].target = target[i]; }
+}
+
+bool WindowBA::makeIDX() {
+  if (!ba_) return false;
+  const int n = nf(), np = (int)points.size(), nr = (int)activeResiduals.size();
+  std::vector<int> slots(n);
+  for (int f = 0; f < n; f++) slots[f] = frameHessians[f].slot;
+  if (dmv_ba_set_window(ba_, n, slots.data()) != DMV_OK) return fail("dmv_ba_set_window");
+  dmv_ba_params prm;
+  prm.huberTH = s.setting_huberTH; prm.outlierTHSumComponent = s.setting_outlierTHSumComponent;
+  prm.affineOptModeA = s.setting_affineOptModeA; prm.affineOptModeB = s.setting_affineOptModeB;
+  dmv_ba_set_params(ba_, &prm);
+  std::vector<int32_t> host(np);
+  std::vector<float> u(np), v(np), id(np), idz(np), col((size_t)np * 8), wgt((size_t)np * 8), prior(np);
+  for (int i = 0; i < np; i++) {
+    const PointHessian& p = points[i];
+    host[i] = p.host; u[i] = p.u; v[i] = p.v; id[i] = p.idepth; idz[i] = p.idepth_zero; prior[i] = p.priorF;
+    for (int k = 0; k < 8; k++) { col[(size_t)8 * i + k] = p.color[k]; wgt[(size_t)8 * i + k] = p.weights[k]; }
+  }
+  if (dmv_ba_set_points(ba_, np, host.data(), u.data(), v.data(), id.data(), idz.data(), col.data(), wgt.data(), prior.data()) != DMV_OK)
+    return fail("dmv_ba_set_points");
+  std::vector<int32_t> rp(nr), rt(nr), rs(nr);
+  std::vector<float> re(nr);
+  for (int i = 0; i < nr; i++) { rp[i] = activeResiduals[i].point; rt[i] = activeResiduals[i].target; rs[i] = activeResiduals[i].state_state; re[i] = activeResiduals[i].state_energy; }
+  if (dmv_ba_set_residuals(ba_, nr, rp.data(), rt.data(), rs.data(), re.data()) != DMV_OK) return fail("dmv_ba_set_residuals");
+  const int N = 8 * n + CPARS;
+  if ((int)HM.size() != N * N) { HM.assign((size_t)N * N, 0.0); bM.assign(N, 0.0); }
+  have_pending_x_ = false;
+  return true;
+}
+
+void WindowBA::framePrior(const FrameHessian& f, double p[10]) const {  // HessianBlocks.h:L262-298 (getPrior)
+  for (int i = 0; i < 10; i++) p[i] = 0;
+  if (f.frameID == 0) {
+    for (int i = 0; i < 3; i++) p[i] = s.setting_initialTransPrior;
+    for (int i = 3; i < 6; i++) p[i] = s.setting_initialRotPrior;
+    p[6] = s.setting_initialAffAPrior; p[7] = s.setting_initialAffBPrior;
+  } else {
+    p[6] = (s.setting_affineOptModeA < 0) ? s.setting_initialAffAPrior : s.setting_affineOptModeA;
+    p[7] = (s.setting_affineOptModeB < 0) ? s.setting_initialAffBPrior : s.setting_affineOptModeB;
+  }
+  p[8] = s.setting_initialAffAPrior; p[9] = s.setting_initialAffBPrior;
+  if (f.addCamPrior) {
+    for (int i = 0; i < 3; i++) p[i] = s.setting_initialTransPrior;
+    for (int i = 3; i < 6; i++) p[i] = s.setting_initialRotPrior;
+  }
+}
+
+void WindowBA::setAdjointsF() {  // EnergyFunctional.cpp:L48-108
+  const int n = nf();
+  adHost.assign((size_t)n * n * 64, 0.0);
+  adTarget.assign((size_t)n * n * 64, 0.0);
+  for (int h = 0; h < n; h++)
+    for (int t = 0; t < n; t++) {
+      const FrameHessian& host = frameHessians[h];
+      const FrameHessian& target = frameHessians[t];
+      const SE3 hostToTarget = target.worldToCam_evalPT * host.worldToCam_evalPT.inverse();
+      double Adj[36];
+      hostToTarget.Adj(Adj);
+      double* AH = &adHost[(size_t)(h + t * n) * 64];
+      double* AT = &adTarget[(size_t)(h + t * n) * 64];
+      for (int i = 0; i < 8; i++) { AH[i * 8 + i] = 1; AT[i * 8 + i] = 1; }
+      for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) AH[i * 8 + j] = -Adj[j * 6 + i];
+      double aff[2];
+      AffLight::fromToVecExposure(host.ab_exposure, target.ab_exposure, host.aff_g2l_0(), target.aff_g2l_0(), aff);
+      const float a0 = (float)aff[0];
+      AT[6 * 8 + 6] = -a0; AH[6 * 8 + 6] = a0; AT[7 * 8 + 7] = -1; AH[7 * 8 + 7] = a0;
+      const double sc[8] = {SCALE_XI_TRANS, SCALE_XI_TRANS, SCALE_XI_TRANS, SCALE_XI_ROT, SCALE_XI_ROT, SCALE_XI_ROT, SCALE_A, SCALE_B};
+      for (int r = 0; r < 8; r++)
+        for (int c = 0; c < 8; c++) { AH[r * 8 + c] *= sc[r]; AT[r * 8 + c] *= sc[r]; }
+    }
+  for (FrameHessian& f : frameHessians) {  // EFFrame::takeData
+    double p[10];
+    framePrior(f, p);
+    for (int i = 0; i < 8; i++) f.prior[i] = p[i];
+  }
+  if (ba_ && dmv_ba_set_adjoints(ba_, adHost.data(), adTarget.data()) != DMV_OK) fail("dmv_ba_set_adjoints");
+}
+
+void WindowBA::setPrecalcValues() {  // FullSystem.cpp:L1670-1680 -> FrameFramePrecalc::set (HessianBlocks.cpp:L193-223) + setDeltaF
+  const int n = nf();
+  precalc.assign((size_t)n * n * DMV_PRECALC_FLOATS, 0.f);
+  const float fx = Hcalib.value_scaledf[0], fy = Hcalib.value_scaledf[1], cx = Hcalib.value_scaledf[2], cy = Hcalib.value_scaledf[3];
+  const float K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+  const float Ki[9] = {1.0f / fx, 0, -cx / fx, 0, 1.0f / fy, -cy / fy, 0, 0, 1};
+  for (int h = 0; h < n; h++)
+    for (int t = 0; t < n; t++) {
+      const FrameHessian& host = frameHessians[h];
+      const FrameHessian& target = frameHessians[t];
+      float* q = &precalc[(size_t)(h * n + t) * DMV_PRECALC_FLOATS];
+      const SE3 l0 = target.worldToCam_evalPT * host.worldToCam_evalPT.inverse();
+      const SE3 l = target.PRE_worldToCam * host.PRE_camToWorld;
+      float R[9], tt[3];
+      for (int i = 0; i < 9; i++) { R[i] = (float)l.R[i]; q[12 + i] = (float)l0.R[i]; }
+      for (int i = 0; i < 3; i++) { tt[i] = (float)l.t[i]; q[21 + i] = (float)l0.t[i]; }
+      float KR[9];
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) KR[i * 3 + j] = K[i * 3] * R[j] + K[i * 3 + 1] * R[3 + j] + K[i * 3 + 2] * R[6 + j];
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) q[i * 3 + j] = KR[i * 3] * Ki[j] + KR[i * 3 + 1] * Ki[3 + j] + KR[i * 3 + 2] * Ki[6 + j];
+      for (int i = 0; i < 3; i++) q[9 + i] = K[i * 3] * tt[0] + K[i * 3 + 1] * tt[1] + K[i * 3 + 2] * tt[2];
+      double aff[2];
+      AffLight::fromToVecExposure(host.ab_exposure, target.ab_exposure, host.aff_g2l(), target.aff_g2l(), aff);
+      q[24] = (float)aff[0]; q[25] = (float)aff[1];
+      q[26] = (float)host.aff_g2l_0().b;
+    }
+  for (FrameHessian& f : frameHessians)  // EnergyFunctional::setDeltaF (EnergyFunctional.cpp:L188-192)
+    for (int i = 0; i < 8; i++) { f.delta[i] = f.state[i] - f.state_zero[i]; f.delta_prior[i] = f.state[i]; }
+}
+
+void WindowBA::fillState(dmv_ba_state* st, float* th) const {
+  for (int i = 0; i < 4; i++) { st->calib[i] = Hcalib.value_scaledf[i]; st->calib[4 + i] = Hcalib.value_scaledi[i]; }
+  for (int f = 0; f < nf(); f++) th[f] = frameHessians[f].frameEnergyTH;
+  st->precalc = precalc.data();
+  st->frameEnergyTH = th;
+  st->idepth = nullptr;
+  st->idepth_zero = nullptr;
+}
+
+double WindowBA::linearizeAll(bool fixLinearization) {
+  // FullSystemOptimize.cpp:L150-218.  One C-ABI call: a pending resubstitute + point step (from the last solveSystemF /
+  // doStepFromBackup) rides along, fused on the device.
+  (void)fixLinearization;  // the applyRes / bookkeeping half of fixLinearization is syncResidualStates() + applyRes_Reductor()
+  dmv_ba_state st;
+  float th[DMV_MAX_FRAMES];
+  fillState(&st, th);
+  dmv_ba_lin_result r;
+  const double* x = have_pending_x_ ? pending_x_.data() : nullptr;
+  if (dmv_ba_gn_step(ba_, x, &st, &r, step_sums_) != DMV_OK) { fail("dmv_ba_gn_step"); return NAN; }
+  have_pending_x_ = false;
+  setNewFrameEnergyTH();
+  return r.energy;
+}
+
+void WindowBA::setNewFrameEnergyTH() {  // FullSystemOptimize.cpp:L96-149 (no IMU cap)
+  std::vector<float> allResVec(points.size() + 1);
+  int n = 0;
+  if (dmv_ba_get_target_energies(ba_, nf() - 1, allResVec.data(), (int)allResVec.size(), &n) != DMV_OK) { fail("dmv_ba_get_target_energies"); return; }
+  FrameHessian& newFrame = frameHessians.back();
+  if (n == 0) { newFrame.frameEnergyTH = 12 * 12 * patternNum; return; }
+  allResVec.resize(n);
+  const int nthIdx = (int)(s.setting_frameEnergyTHN * n);
+  std::nth_element(allResVec.begin(), allResVec.begin() + nthIdx, allResVec.end());
+  const float nthElement = sqrtf(allResVec[nthIdx]);
+  float th = nthElement * s.setting_frameEnergyTHFacMedian;
+  th = 26.0f * s.setting_frameEnergyTHConstWeight + th * (1 - s.setting_frameEnergyTHConstWeight);
+  th = th * th;
+  th *= s.setting_overallEnergyTHWeight * s.setting_overallEnergyTHWeight;
+  newFrame.frameEnergyTH = th;
+}
+
+void WindowBA::applyRes_Reductor() {
+  if (dmv_ba_apply_res(ba_) != DMV_OK) fail("dmv_ba_apply_res");
+}
+
+double WindowBA::calcLEnergyF_MT() {  // EnergyFunctional.cpp:L411-431 (no linearised residuals; idepth priors: deltaF == 0 in DM-VIO)
+  double E = 0;
+  for (const FrameHessian& f : frameHessians)
+    for (int i = 0; i < 8; i++) E += f.delta_prior[i] * f.prior[i] * f.delta_prior[i];
+  float ec = 0;
+  for (int i = 0; i < 4; i++) { const float d = (float)Hcalib.value_minus_value_zero[i]; ec += d * s.setting_initialCalibHessian * d; }
+  return E + ec;
+}
+
+double WindowBA::calcMEnergyF() {  // EnergyFunctional.cpp:L324-346
+  const int n = nf(), N = 8 * n + CPARS;
+  if ((int)HM.size() != N * N) return 0;
+  std::vector<double> delta(N);
+  for (int i = 0; i < 4; i++) delta[i] = (double)(float)Hcalib.value_minus_value_zero[i];
+  for (int h = 0; h < n; h++) for (int i = 0; i < 8; i++) delta[CPARS + 8 * h + i] = frameHessians[h].delta[i];
+  double v = 0;
+  for (int i = 0; i < N; i++) {
+    double sacc = 2 * bM[i];
+    for (int j = 0; j < N; j++) sacc += HM[(size_t)i * N + j] * delta[j];
+    v += delta[i] * sacc;
+  }
+  return v;
+}
+
+void WindowBA::solveSystemF(int iteration, double lambda) {
+  // EnergyFunctional.cpp:L841-996, default solver mode, no-GTSAM branch (L971-973)
+  (void)iteration;
+  const int n = nf(), N = 8 * n + CPARS;
+  last_HA.assign((size_t)N * N, 0.0); last_bA.assign(N, 0.0); last_Hsc.assign((size_t)N * N, 0.0); last_bsc.assign(N, 0.0);
+  if (dmv_ba_accumulate(ba_, last_HA.data(), last_bA.data(), last_Hsc.data(), last_bsc.data(), &resInA) != DMV_OK) { fail("dmv_ba_accumulate"); return; }
+  std::vector<double> delta(N);
+  for (int i = 0; i < 4; i++) delta[i] = (double)(float)Hcalib.value_minus_value_zero[i];
+  for (int h = 0; h < n; h++) for (int i = 0; i < 8; i++) delta[CPARS + 8 * h + i] = frameHessians[h].delta[i];
+  std::vector<double> HFinal((size_t)N * N), bFinal(N);
+  for (int i = 0; i < N; i++) {
+    double bm = bM[i];
+    for (int j = 0; j < N; j++) bm += HM[(size_t)i * N + j] * delta[j];
+    for (int j = 0; j < N; j++) HFinal[(size_t)i * N + j] = HM[(size_t)i * N + j] + last_HA[(size_t)i * N + j];
+    bFinal[i] = bm + last_bA[i] - last_bsc[i];
+  }
+  // accumulateLF_MT with no linearised residuals == priors (AccumulatedTopHessian.cpp:L292-302)
+  for (int i = 0; i < 4; i++) { HFinal[(size_t)i * N + i] += s.setting_initialCalibHessian; bFinal[i] += s.setting_initialCalibHessian * delta[i]; }
+  for (int h = 0; h < n; h++)
+    for (int i = 0; i < 8; i++) {
+      const int k = CPARS + 8 * h + i;
+      HFinal[(size_t)k * N + k] += frameHessians[h].prior[i];
+      bFinal[k] += frameHessians[h].prior[i] * frameHessians[h].delta_prior[i];
+    }
+  lastHS.assign((size_t)N * N, 0.0);
+  for (size_t i = 0; i < (size_t)N * N; i++) lastHS[i] = HFinal[i] - last_Hsc[i];
+  lastbS = bFinal;
+  for (int i = 0; i < N; i++) HFinal[(size_t)i * N + i] *= (1 + lambda);
+  for (size_t i = 0; i < (size_t)N * N; i++) HFinal[i] -= last_Hsc[i] * (1.0 / (1 + lambda));
+  std::vector<double> SVecI(N), Hs((size_t)N * N), bs(N), xs(N);
+  for (int i = 0; i < N; i++) SVecI[i] = 1.0 / std::sqrt(HFinal[(size_t)i * N + i] + 10);
+  for (int i = 0; i < N; i++) {
+    for (int j = 0; j < N; j++) Hs[(size_t)i * N + j] = SVecI[i] * HFinal[(size_t)i * N + j] * SVecI[j];
+    bs[i] = SVecI[i] * bFinal[i];
+  }
+  ldlt_solve(N, Hs.data(), bs.data(), xs.data());
+  lastX.resize(N);
+  for (int i = 0; i < N; i++) lastX[i] = SVecI[i] * xs[i];
+  // resubstituteF_MT (EnergyFunctional.cpp:L267-289): frame / calib steps here, the per-point half is fused into the next linearizeAll
+  for (int i = 0; i < 4; i++) Hcalib.step[i] = -lastX[i];
+  for (int h = 0; h < n; h++) {
+    for (int i = 0; i < 8; i++) frameHessians[h].step[i] = -lastX[CPARS + 8 * h + i];
+    frameHessians[h].step[8] = frameHessians[h].step[9] = 0;
+  }
+  pending_x_ = lastX;
+  have_pending_x_ = true;
+}
+
+void WindowBA::backupState() {  // FullSystemOptimize.cpp:L322-370 (no momentum)
+  for (int i = 0; i < 4; i++) Hcalib.value_backup[i] = Hcalib.value[i];
+  for (FrameHessian& f : frameHessians) for (int i = 0; i < 10; i++) f.state_backup[i] = f.state[i];
+  dmv_ba_backup_points(ba_);
+}
+
+bool WindowBA::doStepFromBackup() {  // FullSystemOptimize.cpp:L224-317, stepfac = 1
+  float sumA = 0, sumB = 0, sumT = 0, sumR = 0;
+  double nv[4];
+  for (int i = 0; i < 4; i++) nv[i] = Hcalib.value_backup[i] + Hcalib.step[i];
+  Hcalib.setValue(nv);
+  for (FrameHessian& f : frameHessians) {
+    double ns[10];
+    for (int i = 0; i < 10; i++) ns[i] = f.state_backup[i] + f.step[i];
+    f.setState(ns);
+    sumA += f.step[6] * f.step[6];
+    sumB += f.step[7] * f.step[7];
+    sumT += f.step[0] * f.step[0] + f.step[1] * f.step[1] + f.step[2] * f.step[2];
+    sumR += f.step[3] * f.step[3] + f.step[4] * f.step[4] + f.step[5] * f.step[5];
+  }
+  const float nfr = (float)frameHessians.size();
+  canbreak_frames_[0] = sumA / nfr; canbreak_frames_[1] = sumB / nfr; canbreak_frames_[2] = sumR / nfr; canbreak_frames_[3] = sumT / nfr;
+  setPrecalcValues();
+  return true;  // the convergence test needs sum |idepth_backup| of the points: evaluated after the fused linearizeAll
+}
+
+void WindowBA::loadSateBackup() {  // FullSystemOptimize.cpp:L371-388
+  Hcalib.setValue(Hcalib.value_backup);
+  for (FrameHessian& f : frameHessians) f.setState(f.state_backup);
+  dmv_ba_restore_points(ba_);
+  have_pending_x_ = false;
+  setPrecalcValues();
+}
+
+int WindowBA::optimize(int mnumOptIts, std::vector<double>* energyLog) {
+  // FullSystemOptimize.cpp:L417-647 without IMU / GTSAM / logging
+  if (nf() < 2) return 0;
+  if (nf() < 3) mnumOptIts = 20;
+  if (nf() < 4) mnumOptIts = 15;
+  double lastEnergy = linearizeAll(false);
+  double lastEnergyL = calcLEnergyF_MT();
+  double lastEnergyM = calcMEnergyF();
+  applyRes_Reductor();
+  if (energyLog) energyLog->push_back(lastEnergy);
+  double lambda = 1e-5;
+  const double minLambda = 1e-5;
+  int numIterations = 0;
+  const float savedTH = frameHessians.back().frameEnergyTH;
+  (void)savedTH;
+  for (int iteration = 0; iteration < mnumOptIts; iteration++) {
+    backupState();
+    const float th_before = frameHessians.back().frameEnergyTH;
+    solveSystemF(iteration, lambda);
+    doStepFromBackup();
+    const double newEnergy = linearizeAll(false);
+    const double newEnergyL = calcLEnergyF_MT();
+    const double newEnergyM = calcMEnergyF();
+    // doStepFromBackup's return value (L311-314), now that the device reported sum |idepth_backup|
+    const float sumNID = step_sums_[2] > 0 ? (float)(step_sums_[1] / step_sums_[2]) : 0.f;
+    bool canbreak = sqrtf(canbreak_frames_[0]) < 0.0005 * s.setting_thOptIterations && sqrtf(canbreak_frames_[1]) < 0.00005 * s.setting_thOptIterations &&
+                    sqrtf(canbreak_frames_[2]) < 0.00005 * s.setting_thOptIterations &&
+                    sqrtf(canbreak_frames_[3]) * sumNID < 0.00005 * s.setting_thOptIterations;
+    if (newEnergy + newEnergyL + newEnergyM < lastEnergy + lastEnergyL + lastEnergyM) {
+      applyRes_Reductor();
+      lastEnergy = newEnergy; lastEnergyL = newEnergyL; lastEnergyM = newEnergyM;
+      lambda *= 0.25;
+      lambda = std::max(lambda, minLambda);
+    } else {
+      // the reference restores the state and re-linearises; the committed linearisation is still on the device, so only the
+      // state (and the energy threshold that re-linearising would have recomputed) is restored
+      loadSateBackup();
+      frameHessians.back().frameEnergyTH = th_before;
+      lambda *= 1e2;
+    }
+    if (energyLog) energyLog->push_back(lastEnergy);
+    numIterations++;
+    if (canbreak && iteration >= s.setting_minOptIterations) break;
+  }
+  lastEnergyTotal = lastEnergy;
+  return numIterations;
+}
+
+void WindowBA::syncResidualStates() {
+  const int nr = (int)activeResiduals.size();
+  std::vector<int32_t> ns(nr);
+  std::vector<float> ne(nr), nw(nr), cp((size_t)nr * 3);
+  if (dmv_ba_get_residual_outputs(ba_, ns.data(), ne.data(), nw.data(), cp.data(), nullptr) != DMV_OK) { fail("dmv_ba_get_residual_outputs"); return; }
+  for (int i = 0; i < nr; i++) {
+    PointFrameResidual& r = activeResiduals[i];
+    r.state_NewState = ns[i]; r.state_NewEnergy = ne[i]; r.state_NewEnergyWithOutlier = nw[i];
+    for (int k = 0; k < 3; k++) r.centerProjectedTo[k] = cp[(size_t)3 * i + k];
+  }
+}
+void WindowBA::getIdepths(float* idepth) { dmv_ba_get_idepth(ba_, idepth, nullptr); }
+void WindowBA::getFrameStates(double* st) const {
+  for (int f = 0; f < nf(); f++) for (int i = 0; i < 10; i++) st[10 * f + i] = frameHessians[f].state[i];
+}
+double WindowBA::lastGpuMs() const { float ms[4] = {0, 0, 0, 0}; dmv_ba_last_timing(ba_, ms); return ms[0]; }
+
+}  // namespace dmvio_b200

@@ -1,0 +1,139 @@
+// Host-side C++ mirror of the reference's BA surface (FullSystem::optimize + EnergyFunctional), driving the CUDA hot
+// path through the C ABI (include/dmvio_b200.h).  Names, argument meaning and call order follow the reference so that a
+// DM-VIO checkout can forward its own methods 1:1:
+//     FullSystem::setPrecalcValues / linearizeAll / applyRes_Reductor / setNewFrameEnergyTH / backupState /
+//     doStepFromBackup / loadSateBackup / optimize                 (src/dso/FullSystem/FullSystemOptimize.cpp, FullSystem.cpp:L1670-1680)
+//     EnergyFunctional::setAdjointsF / setDeltaF / solveSystemF / resubstituteF_MT / calcLEnergyF_MT / calcMEnergyF
+//                                                                  (src/dso/OptimizationBackend/EnergyFunctional.cpp)
+// The pointer graph of the reference (FrameHessian* / PointHessian* / PointFrameResidual*) is flattened to index-based
+// vectors; everything numerical on the per-point path happens on the GPU, the O(nf^2) tables and the dense solve stay here.
+#pragma once
+#include "../../include/dmvio_b200.h"
+#include "se3.h"
+#include <string>
+#include <vector>
+
+namespace dmvio_b200 {
+
+// FullSystem/HessianBlocks.h:L60-68
+constexpr float SCALE_IDEPTH = 1.0f, SCALE_XI_ROT = 1.0f, SCALE_XI_TRANS = 1.0f, SCALE_F = 50.0f, SCALE_C = 50.0f, SCALE_A = 10.0f, SCALE_B = 1000.0f;
+constexpr int CPARS = 4, patternNum = 8;
+
+struct Settings {  // util/settings.cpp:L60-160
+  float setting_huberTH = 9, setting_outlierTH = 12 * 12, setting_outlierTHSumComponent = 50 * 50, setting_overallEnergyTHWeight = 1;
+  float setting_coarseCutoffTH = 20, setting_affineOptModeA = 1e12f, setting_affineOptModeB = 1e8f;
+  float setting_idepthFixPrior = 50 * 50, setting_initialRotPrior = 1e11f, setting_initialTransPrior = 1e10f;
+  float setting_initialAffAPrior = 1e14f, setting_initialAffBPrior = 1e14f, setting_initialCalibHessian = 5e9f;
+  float setting_frameEnergyTHConstWeight = 0.5f, setting_frameEnergyTHN = 0.7f, setting_frameEnergyTHFacMedian = 1.5f;
+  float setting_thOptIterations = 1.2f;
+  int setting_minOptIterations = 1;
+};
+
+struct AffLight {  // util/NumType.h:L166-192
+  double a = 0, b = 0;
+  static void fromToVecExposure(float exposureF, float exposureT, AffLight g2F, AffLight g2T, double out[2]);
+};
+
+struct CalibHessian {  // FullSystem/HessianBlocks.h:L309-409
+  double value[4], value_zero[4], value_scaled[4], value_backup[4], step[4], value_minus_value_zero[4];
+  float value_scaledf[4], value_scaledi[4];
+  void setValue(const double v[4]);
+  void setValueScaled(const double vs[4]);
+};
+
+struct FrameHessian {  // FullSystem/HessianBlocks.h:L113-307 (+ EFFrame: prior, delta, delta_prior)
+  SE3 worldToCam_evalPT, PRE_worldToCam, PRE_camToWorld;
+  double state_zero[10], state_scaled[10], state[10], step[10], state_backup[10];
+  float frameEnergyTH = 8 * 8 * patternNum, ab_exposure = 1;
+  int frameID = 0, slot = 0;
+  bool addCamPrior = false;
+  double prior[8], delta_prior[8], delta[8];
+  void setState(const double s[10]);
+  AffLight aff_g2l() const { AffLight l; l.a = state_scaled[6]; l.b = state_scaled[7]; return l; }
+  AffLight aff_g2l_0() const { AffLight l; l.a = state_zero[6] * SCALE_A; l.b = state_zero[7] * SCALE_B; return l; }
+};
+
+struct PointHessian {  // FullSystem/HessianBlocks.h:L413-508 (+ EFPoint)
+  int host = 0;
+  float u = 0, v = 0, idepth = 0, idepth_zero = 0, idepth_backup = 0, step = 0;
+  float color[8], weights[8];
+  bool hasDepthPrior = false;
+  float priorF = 0;
+};
+
+struct PointFrameResidual {  // FullSystem/Residuals.h:L53-110
+  int point = 0, target = 0;
+  int state_state = 0, state_NewState = 2;
+  float state_energy = 0, state_NewEnergy = 0, state_NewEnergyWithOutlier = -1;
+  float centerProjectedTo[3] = {0, 0, 0};
+};
+
+class WindowBA {
+ public:
+  WindowBA(int w, int h, int max_frames, int max_points, int device = 0);
+  ~WindowBA();
+  WindowBA(const WindowBA&) = delete;
+  WindowBA& operator=(const WindowBA&) = delete;
+  bool ok() const { return ba_ != nullptr; }
+  const std::string& error() const { return err_; }
+
+  Settings s;
+  CalibHessian Hcalib;
+  std::vector<FrameHessian> frameHessians;
+  std::vector<PointHessian> points;            // EnergyFunctional::allPoints order (by host frame)
+  std::vector<PointFrameResidual> activeResiduals;
+  std::vector<double> HM, bM;                  // marginalisation prior (EnergyFunctional::HM / bM), N*N / N
+  std::vector<double> lastHS, lastbS, lastX;   // EnergyFunctional.h:L113-116
+  int resInA = 0;
+  double lastEnergyTotal = 0;
+
+  // ---- construction (EnergyFunctional::insertFrame / insertPoint / insertResidual + FrameHessian::makeImages on the device)
+  int insertFrame(const float* image_wh, const SE3& worldToCam_evalPT, const double state[10], const double state_zero[10], float ab_exposure,
+                  int frameID);
+  int insertFrameDI(const float* dI_aos3, const SE3& worldToCam_evalPT, const double state[10], const double state_zero[10], float ab_exposure,
+                    int frameID);
+  void insertPoints(int n, const int* host, const float* u, const float* v, const float* idepth, const float* idepth_zero, const float* color8,
+                    const float* weights8, const unsigned char* hasDepthPrior);
+  void insertResiduals(int n, const int* point, const int* target);
+  bool makeIDX();  // uploads points/residuals (EnergyFunctional::makeIDX, EnergyFunctional.cpp:L998-1016)
+
+  // ---- reference surface
+  void setAdjointsF();                 // EnergyFunctional.cpp:L48-108
+  void setPrecalcValues();             // FullSystem.cpp:L1670-1680 (+ setDeltaF)
+  double linearizeAll(bool fixLinearization);  // FullSystemOptimize.cpp:L150-218 (energy = Vec3[0])
+  void applyRes_Reductor();            // FullSystemOptimize.cpp:L90-94
+  void setNewFrameEnergyTH();          // FullSystemOptimize.cpp:L96-149
+  void solveSystemF(int iteration, double lambda);  // EnergyFunctional.cpp:L841-996, no-GTSAM branch
+  double calcLEnergyF_MT();            // EnergyFunctional.cpp:L411-431 (priors; no linearised residuals in the active set)
+  double calcMEnergyF();               // EnergyFunctional.cpp:L324-346
+  void backupState();                  // FullSystemOptimize.cpp:L322-370
+  bool doStepFromBackup();             // FullSystemOptimize.cpp:L224-317 (point part deferred to the next linearizeAll: fused on the GPU)
+  void loadSateBackup();               // FullSystemOptimize.cpp:L371-388
+  int optimize(int mnumOptIts, std::vector<double>* energyLog = nullptr);  // FullSystemOptimize.cpp:L417-647 (no IMU); returns #iterations
+
+  // ---- results
+  void syncResidualStates();           // pulls state_NewState / energies / centerProjectedTo of the last linearisation from the device
+  void getIdepths(float* idepth);      // current device depths
+  void getFrameStates(double* state10) const;
+  double lastGpuMs() const;
+
+  // tables (exposed for tests)
+  std::vector<float> precalc;          // nf*nf*32, [h*nf+t]
+  std::vector<double> adHost, adTarget;  // nf*nf*64, [h+t*nf]
+  std::vector<double> last_HA, last_bA, last_Hsc, last_bsc;
+
+ private:
+  bool fail(const char* what);
+  void framePrior(const FrameHessian& f, double p[10]) const;
+  int nf() const { return (int)frameHessians.size(); }
+  void fillState(dmv_ba_state* st, float* th) const;
+  dmv_ba* ba_ = nullptr;
+  int w_, h_, max_frames_, max_points_;
+  std::string err_;
+  bool have_pending_x_ = false;      // resubstitute + point step are fused into the next linearizeAll
+  std::vector<double> pending_x_;
+  double step_sums_[3] = {0, 0, 0};
+  float canbreak_frames_[4] = {0, 0, 0, 0};
+};
+
+}  // namespace dmvio_b200

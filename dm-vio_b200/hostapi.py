@@ -1,0 +1,156 @@
+"""ctypes binding of the C glue (host/host_capi.h) over the C++ host adapters WindowBA / CoarseTracker — the classes a
+DM-VIO checkout would link directly.  Python only marshals arrays here; all logic is C++ + CUDA."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+vp = C.c_void_p
+_L = None
+
+
+def lib():
+    global _L
+    if _L is None:
+        L = capi.lib()
+        L.dmvh_window_create.restype = vp
+        L.dmvh_window_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64p]
+        L.dmvh_window_destroy.argtypes = [vp]
+        L.dmvh_window_error.restype = C.c_char_p
+        L.dmvh_window_error.argtypes = [vp]
+        L.dmvh_window_add_frame.argtypes = [vp, f32p, C.c_int, f64p, f64p, f64p, f64p, C.c_float, C.c_int]
+        L.dmvh_window_set_points.argtypes = [vp, C.c_int, i32p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
+        L.dmvh_window_set_residuals.argtypes = [vp, C.c_int, i32p, i32p]
+        L.dmvh_window_prepare.argtypes = [vp]
+        L.dmvh_window_linearize.restype = C.c_double
+        L.dmvh_window_linearize.argtypes = [vp, C.c_int]
+        L.dmvh_window_apply.argtypes = [vp]
+        L.dmvh_window_solve.argtypes = [vp, C.c_int, C.c_double, f64p]
+        L.dmvh_window_optimize.argtypes = [vp, C.c_int, f64p, C.c_int]
+        L.dmvh_window_get_tables.argtypes = [vp, f32p, f64p, f64p]
+        L.dmvh_window_get_system.argtypes = [vp, f64p, f64p, f64p, f64p, f64p, f64p]
+        L.dmvh_window_get_states.argtypes = [vp, f64p, f32p, f32p]
+        L.dmvh_window_energy_L.restype = C.c_double
+        L.dmvh_window_energy_L.argtypes = [vp]
+        L.dmvh_ct_create.restype = vp
+        L.dmvh_ct_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64p]
+        L.dmvh_ct_destroy.argtypes = [vp]
+        L.dmvh_ct_set_ref.argtypes = [vp, C.c_int, f32p, f32p, f32p, f32p, f32p, C.c_double, C.c_double, C.c_float]
+        L.dmvh_ct_pc_n.argtypes = [vp, C.c_int]
+        L.dmvh_ct_set_new_image.argtypes = [vp, f32p, C.c_float]
+        L.dmvh_ct_track.argtypes = [vp, f64p, f64p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, f64p, f64p, f64p, C.POINTER(C.c_int),
+                                    C.POINTER(C.c_longlong)]
+        _L = L
+    return _L
+
+
+def _c(a, t):
+    return np.ascontiguousarray(a, t)
+
+
+class WindowBA:
+    """dmvio_b200::WindowBA loaded from a synth.make_window() dict."""
+
+    def __init__(self, W, device=0, use_device_pyramid=False):
+        self.L = lib()
+        self.nf, self.npts = W["nf"], len(W["host"])
+        self.N = 8 * self.nf + 4
+        self.h = self.L.dmvh_window_create(W["w"], W["h"], max(2, self.nf), self.npts, device, _c(W["K"], np.float64))
+        for k in range(self.nf):
+            data = _c(W["images"][k], np.float32).reshape(-1) if use_device_pyramid else _c(W["dI"][k], np.float32).reshape(-1)
+            rc = self.L.dmvh_window_add_frame(self.h, data, int(use_device_pyramid), _c(W["R_eval"][k], np.float64).reshape(-1), _c(W["t_eval"][k], np.float64),
+                                              _c(W["state"][k], np.float64), _c(W["state_zero"][k], np.float64), float(W["exposure"][k]), int(W["frameID"][k]))
+            if rc < 0:
+                raise capi.DmvError(self.L.dmvh_window_error(self.h).decode())
+        self.L.dmvh_window_set_points(self.h, self.npts, _c(W["host"], np.int32), _c(W["u"], np.float32), _c(W["v"], np.float32), _c(W["idepth"], np.float32),
+                                      _c(W["idepth_zero"], np.float32), _c(W["color"], np.float32).reshape(-1), _c(W["weights"], np.float32).reshape(-1), None)
+        self.L.dmvh_window_set_residuals(self.h, len(W["res_point"]), _c(W["res_point"], np.int32), _c(W["res_target"], np.int32))
+        if self.L.dmvh_window_prepare(self.h) != 0:
+            raise capi.DmvError(self.L.dmvh_window_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.L.dmvh_window_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def tables(self):
+        pc = np.zeros((self.nf * self.nf, 32), np.float32); a = np.zeros((self.nf * self.nf, 8, 8)); b = np.zeros((self.nf * self.nf, 8, 8))
+        self.L.dmvh_window_get_tables(self.h, pc.reshape(-1), a.reshape(-1), b.reshape(-1))
+        return pc, a, b
+
+    def linearize(self, fix=False):
+        return self.L.dmvh_window_linearize(self.h, int(fix))
+
+    def apply(self):
+        self.L.dmvh_window_apply(self.h)
+
+    def solve(self, iteration=0, lam=1e-5):
+        x = np.zeros(self.N)
+        self.L.dmvh_window_solve(self.h, iteration, lam, x)
+        return x
+
+    def system(self):
+        N = self.N
+        o = [np.zeros(N * N), np.zeros(N), np.zeros(N * N), np.zeros(N), np.zeros(N * N), np.zeros(N)]
+        self.L.dmvh_window_get_system(self.h, *o)
+        return dict(HA=o[0].reshape(N, N), bA=o[1], Hsc=o[2].reshape(N, N), bsc=o[3], lastHS=o[4].reshape(N, N), lastbS=o[5])
+
+    def optimize(self, its=6):
+        log = np.zeros(64)
+        n = self.L.dmvh_window_optimize(self.h, its, log, 64)
+        return n, log[log >= 0]
+
+    def states(self):
+        st = np.zeros((self.nf, 10)); idd = np.zeros(self.npts, np.float32); th = np.zeros(self.nf, np.float32)
+        self.L.dmvh_window_get_states(self.h, st.reshape(-1), idd, th)
+        return st, idd, th
+
+
+class CoarseTracker:
+    def __init__(self, w, h, K, levels, max_points=65536, device=0):
+        self.L = lib()
+        self.levels = levels
+        self.h = self.L.dmvh_ct_create(w, h, levels, max_points, device, _c(K, np.float64))
+
+    def close(self):
+        if self.h:
+            self.L.dmvh_ct_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_ref(self, Ku, Kv, nid, HdiF, pyr_ref, ref_a=0.0, ref_b=0.0, ref_exposure=1.0):
+        ref = _c(np.concatenate([p.reshape(-1) for p in pyr_ref]), np.float32)
+        rc = self.L.dmvh_ct_set_ref(self.h, len(Ku), _c(Ku, np.float32), _c(Kv, np.float32), _c(nid, np.float32), _c(HdiF, np.float32), ref, ref_a, ref_b, ref_exposure)
+        if rc != 0:
+            raise capi.DmvError("dmvh_ct_set_ref failed")
+        return [self.L.dmvh_ct_pc_n(self.h, l) for l in range(self.levels)]
+
+    def set_new_image(self, img, exposure=1.0):
+        if self.L.dmvh_ct_set_new_image(self.h, _c(img, np.float32).reshape(-1), exposure) != 0:
+            raise capi.DmvError("dmvh_ct_set_new_image failed")
+
+    def track(self, R, t, a, b, coarsest=None, minRes=None):
+        R = _c(R, np.float64).reshape(-1).copy(); t = _c(t, np.float64).copy()
+        ca, cb = C.c_double(a), C.c_double(b)
+        its, ev = C.c_int(0), C.c_longlong(0)
+        lastRes, flow = np.zeros(5), np.zeros(3)
+        mr = np.full(5, np.nan) if minRes is None else _c(minRes, np.float64)
+        good = self.L.dmvh_ct_track(self.h, R, t, C.byref(ca), C.byref(cb), self.levels - 1 if coarsest is None else coarsest, mr, lastRes, flow,
+                                    C.byref(its), C.byref(ev))
+        return dict(good=bool(good), R=R.reshape(3, 3), t=t, a=ca.value, b=cb.value, lastResiduals=lastRes, flow=flow, iterations=its.value,
+                    evaluations=ev.value)

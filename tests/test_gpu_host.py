@@ -1,0 +1,83 @@
+"""GPU tests of the C++ host adapters (dmvio_b200::WindowBA / CoarseTracker) that mirror the reference's C++ surface:
+the whole FullSystem::optimize GN/LM loop and CoarseTracker::trackNewestCoarse against the CPU oracle."""
+import numpy as np
+import pytest
+
+from helpers import rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hostapi():
+    import dmvio_b200.capi as c
+    if c.lib().dmv_device_count() < 1:
+        pytest.fail("no CUDA device visible: GPU tests must run on the B200 box")
+    import dmvio_b200.hostapi as h
+    return h
+
+
+def test_host_tables_match_oracle(hostapi, orc, synth):
+    W = synth.make_window(nf=5, npts=300, seed=3)
+    ow = orc.Window(W)
+    hw = hostapi.WindowBA(W)
+    pc, adH, adT = hw.tables()
+    np.testing.assert_allclose(pc, ow.precalc(), rtol=2e-6, atol=1e-4)
+    a_o, t_o = ow.adjoints()
+    np.testing.assert_allclose(adH, a_o, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(adT, t_o, rtol=1e-12, atol=1e-12)
+    hw.close()
+
+
+@pytest.mark.parametrize("cfg", [dict(nf=4, npts=600, seed=13), dict(nf=7, npts=2000, seed=1234)], ids=["nf4", "nf7"])
+def test_optimize_matches_oracle(hostapi, orc, synth, cfg):
+    """FullSystem::optimize on the GPU (fused gn_step per iteration) vs the oracle's optimize: same accept/reject sequence,
+    energies within 1e-4 relative, final frame states within 1e-5 absolute (unscaled state units), depths within 1e-4 relative."""
+    W = synth.make_window(state_noise=2e-3, **cfg)
+    ow = orc.Window(W)
+    n_o, log_o = ow.optimize(6, precision=1)
+    hw = hostapi.WindowBA(W)
+    n_g, log_g = hw.optimize(6)
+    assert n_g == n_o
+    assert len(log_g) == len(log_o)
+    np.testing.assert_allclose(log_g, log_o, rtol=2e-4)
+    st_g, id_g, th_g = hw.states()
+    st_o = ow.frame_states()
+    assert np.abs(st_g - st_o).max() < 2e-5
+    id_o = ow.point_outputs()["idepth"]
+    np.testing.assert_allclose(id_g, id_o, rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(th_g, ow.frame_tables()["frameEnergyTH"], rtol=2e-3)
+    assert log_g[-1] < 0.6 * log_g[0]
+    hw.close()
+
+
+def test_device_pyramid_frames(hostapi, orc, synth):
+    """frames uploaded as raw images (level-0 [I,dx,dy] built on the device) give the same linearisation as host-built dI."""
+    W = synth.make_window(nf=3, npts=300, seed=8)
+    a = hostapi.WindowBA(W, use_device_pyramid=False)
+    b = hostapi.WindowBA(W, use_device_pyramid=True)
+    ea, eb = a.linearize(), b.linearize()
+    assert abs(ea - eb) <= 1e-6 * abs(ea)
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("levels", [4, 5])
+def test_track_newest_coarse(hostapi, orc, synth, levels):
+    T = synth.make_tracking_pair(seed=4321, levels=levels if levels == 5 else 0)
+    oct_ = orc.CoarseTracker(T["w"], T["h"], T["K"], levels if levels == 5 else 0)
+    oct_.make_coarse_depth(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
+    oct_.set_new_frame(T["pyr_new"])
+    r_o = oct_.track(np.eye(3), np.zeros(3), 0.0, 0.0)
+    g = hostapi.CoarseTracker(T["w"], T["h"], T["K"], levels)
+    counts = g.set_ref(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
+    assert counts == [len(oct_.ref_points(l)["u"]) for l in range(levels)]
+    g.set_new_image(T["img_new"])
+    r_g = g.track(np.eye(3), np.zeros(3), 0.0, 0.0)
+    assert r_g["good"] == r_o["good"]
+    assert np.abs(r_g["R"] - r_o["R"]).max() < 2e-5
+    assert np.abs(r_g["t"] - r_o["t"]).max() < 2e-5
+    assert abs(r_g["a"] - r_o["a"]) < 1e-3 and abs(r_g["b"] - r_o["b"]) < 5e-2
+    np.testing.assert_allclose(r_g["lastResiduals"][:levels], r_o["lastResiduals"][:levels], rtol=2e-3)
+    assert abs(r_g["iterations"] - r_o["iterations"]) <= 2
+    assert np.linalg.norm(r_g["t"] - T["t_true"]) < 5e-4
+    g.close()
