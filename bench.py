@@ -98,22 +98,6 @@ def algorithmic_bytes(nres, npts, nf):
     return 436 * nres + 112 * npts + 8 * N * (N + 1)
 
 
-def shard_window(W, rank, world):
-    """points p with p % world == rank (keeps the host ordering), and their residuals re-indexed."""
-    if world == 1:
-        return W
-    keep = np.arange(len(W["host"])) % world == rank
-    newidx = -np.ones(len(keep), np.int64)
-    newidx[keep] = np.arange(keep.sum())
-    S = dict(W)
-    for k in ("host", "u", "v", "idepth", "idepth_zero", "color", "weights", "hasDepthPrior"):
-        S[k] = W[k][keep]
-    rk = keep[W["res_point"]]
-    S["res_point"] = newidx[W["res_point"][rk]].astype(np.int32)
-    S["res_target"] = W["res_target"][rk]
-    return S
-
-
 def cpu_oracle_rate(W, seconds, threads, x=None):
     """times the oracle's hot iteration (accumulate+stitch, resubstitute, step, linearizeAll, applyRes); returns (res/s, ms/iter, iters)."""
     from oracle import orc
@@ -188,6 +172,7 @@ def main():
     import dmvio_b200.capi as capi
     import dmvio_b200.hostmath as hm
     import dmvio_b200.synth as synth
+    from dmvio_b200.sharding import shard_window
 
     dist = None
     if world > 1:

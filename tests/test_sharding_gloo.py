@@ -1,0 +1,102 @@
+"""Multi-rank logic of the BA path on CPU (gloo, world_size 2): point sharding + the single all-reduce of the stitched system.
+
+What is checked (the CUDA kernels are not involved; the per-shard systems come from the oracle, used here as the checker):
+  * shards partition the points and residuals, each shard stays ordered by host frame;
+  * sum over ranks of the per-shard [H_A b_A H_sc b_sc energy counters] == the unsharded window's (the shard-sum invariance that
+    makes a plain ncclAllReduce(sum, double) the whole exchange step);
+  * after the all-reduce every rank holds the identical system, hence solves to the identical x.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import rel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, cfg, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import dmvio_b200.synth as synth
+    import dmvio_b200.hostmath as hm
+    from dmvio_b200.sharding import shard_window, pack_system, unpack_system
+    from oracle import orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    W = synth.make_window(**cfg)
+    S = shard_window(W, rank, world)
+    ow = orc.Window(S)
+    E = ow.linearize_all(update_th=False)
+    st = ow.res_outputs(False)["newState"]
+    ow.apply_res()
+    a = ow.accumulate(1)
+    buf = torch.from_numpy(pack_system(a["HA"], a["bA"], a["Hsc"], a["bsc"], E, [(st == 0).sum(), (st == 1).sum(), (st == 2).sum()]))
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    N = 8 * W["nf"] + 4
+    tot = unpack_system(buf.numpy(), N)
+    HL, bL = hm.prior_system(W)
+    x = hm.solve_reduced(tot["HA"], tot["bA"], tot["Hsc"], tot["bsc"], HL, bL, lam=1e-5)
+    q.put((rank, len(S["host"]), len(S["res_point"]), bool(np.all(np.diff(S["host"]) >= 0)), buf.numpy().copy(), x))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cfg", [dict(nf=4, npts=301, seed=5, w=160, h=120)], ids=["nf4_n301"])
+def test_shard_allreduce_matches_unsharded(orc, synth, cfg):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    W = synth.make_window(**cfg)
+    assert sum(r[1] for r in res) == len(W["host"])
+    assert sum(r[2] for r in res) == len(W["res_point"])
+    assert all(r[3] for r in res)
+    np.testing.assert_array_equal(res[0][4], res[1][4])  # identical on every rank after the all-reduce
+    np.testing.assert_array_equal(res[0][5], res[1][5])
+    ow = orc.Window(W)
+    E = ow.linearize_all(update_th=False)
+    st = ow.res_outputs(False)["newState"]
+    ow.apply_res()
+    a = ow.accumulate(1)
+    from dmvio_b200.sharding import unpack_system
+    tot = unpack_system(res[0][4], 8 * W["nf"] + 4)
+    for k in ("HA", "bA", "Hsc", "bsc"):
+        assert rel(tot[k], a[k]) < 1e-12, k
+    assert abs(tot["energy"] - E) <= 1e-9 * abs(E)
+    np.testing.assert_array_equal(tot["counts"], [(st == 0).sum(), (st == 1).sum(), (st == 2).sum()])
+
+
+def test_shard_edge_cases(synth):
+    from dmvio_b200.sharding import shard_window, shard_points
+    W = synth.make_window(nf=3, npts=5, seed=2, w=96, h=64, hosts="all")
+    # more ranks than points of some host; a rank may own zero points
+    seen = np.zeros(5, int)
+    for r in range(8):
+        m = shard_points(W["host"], r, 8)
+        seen += m
+        S = shard_window(W, r, 8)
+        assert len(S["res_point"]) == (len(S["host"]) * 2)
+        if len(S["host"]):
+            assert S["res_point"].max() < len(S["host"])
+    np.testing.assert_array_equal(seen, 1)
+    assert shard_window(W, 0, 1) is W
