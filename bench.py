@@ -193,6 +193,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="points per thread block (8/16/32, 0 = library default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: all-reduce of the stitched system by the peer-memory kernel (NVLink, CUDA IPC) or by NCCL")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,10 +233,32 @@ def main():
     k8 = hm.calib8(Wr["K"])
     precalc = hm.precalc_table(Wr)
     TH = Wr["frameEnergyTH"].copy()
+    exchange = "none"
     if world > 1:
-        uid = [capi.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ba.comm_init(world, rank, uid[0])
+        exchange = args.exchange
+        if exchange == "p2p":
+            try:
+                mine = ba.p2p_export()
+                handles = [None] * world
+                dist.all_gather_object(handles, mine)   # doubles as the barrier after every inbox has been zeroed
+                ba.p2p_import(world, rank, handles)
+                ok = 1
+            except Exception as e:  # no peer access between these GPUs: fall back to NCCL on ALL ranks
+                sys.stderr.write(f"[rank {rank}] peer-memory exchange unavailable ({e}); using NCCL\n")
+                ok = 0
+            import torch
+            t_ok = torch.tensor([ok], device="cuda")
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            if int(t_ok.item()) == 0:
+                exchange = "nccl"
+                try:
+                    ba.p2p_import(1, 0, [mine])  # nranks = 1 switches the peer exchange off again
+                except Exception:
+                    pass
+        if exchange == "nccl":
+            uid = [capi.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ba.comm_init(world, rank, uid[0])
     ba.set_state(k8, precalc, TH)
     r0 = ba.linearize()
     ba.apply_res()
@@ -324,7 +348,7 @@ def main():
             "ms_per_step": ms_iter, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"sliding window {NF} KF / {NPTS * world} pts / {W_}x{H_}, pattern 8, {nres_total} point-residuals "
                                    f"({nres_local}/GPU), one GN iteration of the hot path per step (host solve excluded)",
-                       "parallelism": f"points sharded over {world} GPU(s), images replicated" + (", NCCL all-reduce of H,b per step" if world > 1 else ""),
+                       "parallelism": f"points sharded over {world} GPU(s), images replicated" + ({"p2p": ", all-reduce of H,b per step by ba_xchg_kernel over NVLink peer memory", "nccl": ", NCCL all-reduce of H,b per step", "none": ""}[exchange]),
                        "l2": "L2 scrubbed (256 MiB write) between timed steps of `value`", "chunk_points": args.chunk or 16,
                        "n_in": r0["n_in"], "n_oob": r0["n_oob"], "n_outlier": r0["n_outlier"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

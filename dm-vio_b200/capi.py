@@ -52,7 +52,7 @@ SYMBOLS = [
     "dmv_ba_set_window", "dmv_ba_set_points", "dmv_ba_set_residuals", "dmv_ba_set_adjoints", "dmv_ba_set_state", "dmv_ba_linearize",
     "dmv_ba_get_residual_outputs", "dmv_ba_get_target_energies", "dmv_ba_apply_res", "dmv_ba_accumulate", "dmv_ba_get_point_outputs",
     "dmv_ba_resubstitute", "dmv_ba_backup_points", "dmv_ba_restore_points", "dmv_ba_get_idepth", "dmv_ba_gn_step", "dmv_nccl_unique_id",
-    "dmv_ba_comm_init", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e", "dmv_ba_debug_clocks",
+    "dmv_ba_comm_init", "dmv_ba_p2p_export", "dmv_ba_p2p_import", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e", "dmv_ba_debug_clocks",
     "dmv_ct_create", "dmv_ct_destroy", "dmv_ct_set_K", "dmv_ct_set_ref", "dmv_ct_upload_new", "dmv_ct_upload_new_image", "dmv_ct_set_huber",
     "dmv_ct_calc_res_gs", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count",
 ]
@@ -90,6 +90,8 @@ def lib():
         L.dmv_ba_gn_step.argtypes = [vp, vp, C.POINTER(BAState), C.POINTER(BALinResult), f64p]
         L.dmv_nccl_unique_id.argtypes = [vp]
         L.dmv_ba_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.dmv_ba_p2p_export.argtypes = [vp, vp]
+        L.dmv_ba_p2p_import.argtypes = [vp, C.c_int, C.c_int, vp]
         L.dmv_ba_last_timing.argtypes = [vp, f32p]
         L.dmv_ba_bench_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.dmv_ba_kernel_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
@@ -287,6 +289,19 @@ class BA:
     def comm_init(self, nranks, rank, uid_bytes):
         buf = C.create_string_buffer(bytes(uid_bytes), 128)
         check(self.L.dmv_ba_comm_init(self.h, nranks, rank, C.cast(buf, vp)))
+
+
+    def p2p_export(self):
+        """64-byte CUDA IPC handle of this rank's exchange inbox (all-gather it, then p2p_import)."""
+        buf = C.create_string_buffer(64)
+        check(self.L.dmv_ba_p2p_export(self.h, C.cast(buf, vp)))
+        return bytes(buf.raw)
+
+    def p2p_import(self, nranks, rank, handles):
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * nranks
+        buf = C.create_string_buffer(blob, len(blob))
+        check(self.L.dmv_ba_p2p_import(self.h, nranks, rank, C.cast(buf, vp)))
 
 
 def nccl_unique_id():

@@ -15,6 +15,7 @@ void launch_resub_kernel(const BAWinDev& W, const BAIter& it, int apply, double*
 void launch_repack(const float* src, float4* dst, int n, cudaStream_t s);
 void launch_make_dI(const float* img, float4* dst, int w, int h, cudaStream_t s);
 void launch_l2_flush(float4* buf, size_t n, cudaStream_t s);
+void launch_xchg_kernel(const XchgDev& X, cudaStream_t s);
 }  // namespace dmv
 
 using namespace dmv;
@@ -83,7 +84,36 @@ struct dmv_ba {
   // NCCL
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  // peer-memory exchange (ba_xchg.cu)
+  void* xchg_own = nullptr;                 // this rank's inbox (cudaMalloc, exported through CUDA IPC)
+  void* xchg_map[XCHG_MAXR] = {nullptr};    // every rank's inbox as mapped here ([rank] == xchg_own)
+  int xchg_pitch = 0;
+  bool xchg_on = false;
+  unsigned long long xchg_seq = 0;
 };
+
+// all-reduce of the stitched result blob across ranks, on the handle's stream, behind the stitch kernel
+static int enqueue_exchange(dmv_ba* b) {
+  if (b->xchg_on) {
+    XchgDev X;
+    std::memset(&X, 0, sizeof(X));
+    X.nranks = b->nranks; X.rank = b->rank;
+    X.nvec = result_doubles(b->N, b->ntiles) / 2;
+    X.pitch = b->xchg_pitch;
+    X.seq = ++b->xchg_seq;
+    for (int r = 0; r < b->nranks; r++) {
+      X.flags[r] = reinterpret_cast<unsigned long long*>(b->xchg_map[r]);
+      X.inbox[r] = reinterpret_cast<double2*>(reinterpret_cast<char*>(b->xchg_map[r]) + XCHG_FLAG_BYTES);
+    }
+    X.buf = reinterpret_cast<double2*>(b->d_result[b->tent]);
+    launch_xchg_kernel(X, b->stream);
+    b->launches += 1;
+    if (cudaGetLastError() != cudaSuccess) return dmv::set_error(DMV_ERR_CUDA, "ba_xchg_kernel launch failed");
+    return DMV_OK;
+  }
+  if (b->nccl_comm) return dmv::nccl_allreduce_double(b->nccl_comm, b->d_result[b->tent], result_doubles(b->N, b->ntiles), b->stream);
+  return DMV_OK;
+}
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -197,8 +227,8 @@ int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
   CK(cudaMemset(b->d_ticket, 0, sizeof(unsigned int) * 16));
   CK(cudaMalloc(&b->d_stage, sizeof(double) * (MF * MF * 272 + MF * 20)));
   CK(cudaMemset(b->d_stage, 0, sizeof(double) * (MF * MF * 272 + MF * 20)));
-  CK(cudaMalloc(&b->d_dbg_clk, sizeof(unsigned long long) * 16 * b->max_chunks));
-  CK(cudaMemset(b->d_dbg_clk, 0, sizeof(unsigned long long) * 16 * b->max_chunks));
+  CK(cudaMalloc(&b->d_dbg_clk, sizeof(unsigned long long) * 16 * (b->max_chunks + MAXF + 1)));
+  CK(cudaMemset(b->d_dbg_clk, 0, sizeof(unsigned long long) * 16 * (b->max_chunks + MAXF + 1)));
   CK(cudaMallocHost(&b->h_up, sizeof(HostUpload)));
   CK(cudaMallocHost(&b->h_adj, sizeof(BAAdj)));
   std::memset(b->h_up, 0, sizeof(HostUpload));
@@ -225,6 +255,9 @@ int dmv_ba_destroy(dmv_ba* b) {
   cudaFreeHost(b->h_up); cudaFreeHost(b->h_adj); cudaFreeHost(b->h_scratch);
   for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   if (b->nccl_comm) dmv::nccl_destroy(b->nccl_comm);
+  for (int r = 0; r < XCHG_MAXR; r++)
+    if (b->xchg_map[r] && b->xchg_map[r] != b->xchg_own) cudaIpcCloseMemHandle(b->xchg_map[r]);
+  cudaFree(b->xchg_own);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
   return DMV_OK;
@@ -418,8 +451,8 @@ static int enqueue_linearize(dmv_ba* b, bool with_resub) {
   b->acc_cur = 1 - b->acc_cur;
   if (b->timing) CK(cudaEventRecord(b->ev[2], b->stream));
   CK(cudaGetLastError());
-  if (b->nccl_comm) {
-    int rc = dmv::nccl_allreduce_double(b->nccl_comm, b->d_result[b->tent], result_doubles(b->N, b->ntiles), b->stream);
+  {
+    int rc = enqueue_exchange(b);
     if (rc != DMV_OK) return rc;
   }
   CK(cudaMemcpyAsync(b->h_result[b->tent], b->d_result[b->tent], sizeof(double) * result_doubles(b->N, b->ntiles), cudaMemcpyDeviceToHost, b->stream));
@@ -681,10 +714,8 @@ int dmv_ba_bench_device(dmv_ba* b, const double* x, int iters, int flush_l2, flo
     launch_stitch_kernel(U.win, b->stream);
     CK(cudaEventRecord(e[3 * i + 1], b->stream));
     b->acc_cur = 1 - b->acc_cur;
-    if (b->nccl_comm) {
-      rc = dmv::nccl_allreduce_double(b->nccl_comm, b->d_result[b->tent], result_doubles(b->N, b->ntiles), b->stream);
-      if (rc != DMV_OK) return rc;
-    }
+    rc = enqueue_exchange(b);
+    if (rc != DMV_OK) return rc;
     CK(cudaEventRecord(e[3 * i + 2], b->stream));
     b->launches += 2;
   }
@@ -719,6 +750,42 @@ int dmv_ba_comm_init(dmv_ba* b, int nranks, int rank, const void* id) {
 
 }  // extern "C"
 
+// ---- peer-memory exchange set-up (CUDA IPC): export this rank's inbox, import everybody's
+extern "C" int dmv_ba_p2p_export(dmv_ba* b, void* ipc_handle64) {
+  if (!b || !ipc_handle64) return set_error(DMV_ERR_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CK(cudaSetDevice(b->device));
+  if (!b->xchg_own) {
+    const int maxT = (8 * MAXF + 4 + 1 + 3) / 4, maxTiles = maxT * (maxT + 1) / 2;
+    b->xchg_pitch = (result_doubles(8 * MAXF + 4, maxTiles) / 2 + 7) & ~7;
+    if ((b->xchg_pitch + XCHG_CTAS - 1) / XCHG_CTAS > XCHG_THREADS) return set_error(DMV_ERR_INVALID, "result blob too large for the exchange kernel");
+    const size_t bytes = XCHG_FLAG_BYTES + (size_t)2 * XCHG_MAXR * b->xchg_pitch * sizeof(double2);
+    CK(cudaMalloc(&b->xchg_own, bytes));
+    CK(cudaMemset(b->xchg_own, 0, bytes));
+    CK(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t hdl;
+  CK(cudaIpcGetMemHandle(&hdl, b->xchg_own));
+  std::memcpy(ipc_handle64, &hdl, 64);
+  return DMV_OK;
+}
+
+extern "C" int dmv_ba_p2p_import(dmv_ba* b, int nranks, int rank, const void* ipc_handles) {
+  if (!b || !ipc_handles || nranks < 1 || nranks > XCHG_MAXR || rank < 0 || rank >= nranks) return set_error(DMV_ERR_INVALID, "bad argument (1..%d ranks)", XCHG_MAXR);
+  if (!b->xchg_own) return set_error(DMV_ERR_STATE, "dmv_ba_p2p_export first");
+  CK(cudaSetDevice(b->device));
+  for (int r = 0; r < nranks; r++) {
+    if (r == rank) { b->xchg_map[r] = b->xchg_own; continue; }
+    cudaIpcMemHandle_t hdl;
+    std::memcpy(&hdl, static_cast<const char*>(ipc_handles) + (size_t)r * 64, 64);
+    CK(cudaIpcOpenMemHandle(&b->xchg_map[r], hdl, cudaIpcMemLazyEnablePeerAccess));
+  }
+  b->nranks = nranks; b->rank = rank;
+  b->xchg_on = nranks > 1;
+  b->xchg_seq = 0;
+  return DMV_OK;
+}
+
 extern "C" int dmv_ba_io_bytes(dmv_ba* b, long long* h2d, long long* d2h) {
   if (!b || !h2d || !d2h) return set_error(DMV_ERR_INVALID, "null argument");
   *h2d = (long long)sizeof(HostUpload);                        // descriptor + per-iteration tables, carried as kernel parameters
@@ -728,7 +795,7 @@ extern "C" int dmv_ba_io_bytes(dmv_ba* b, long long* h2d, long long* d2h) {
 
 extern "C" int dmv_ba_debug_clocks(dmv_ba* b, unsigned long long* out, int cap) {
   if (!b || !out) return set_error(DMV_ERR_INVALID, "null argument");
-  const int n = std::min(cap, 16 * b->nchunks);
+  const int n = std::min(cap, 16 * (b->nchunks + b->nf + 1));  // point-kernel CTAs, then the stitch CTAs
   CK(cudaSetDevice(b->device));
   CK(cudaMemcpy(out, b->d_dbg_clk, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
   return n;

@@ -76,6 +76,17 @@ struct BAWinDev {
   double* result;            // H_top N*N | b_top N | Schur tiles ntiles*16 | ACC_MISC tail
 };
 
+// peer-memory exchange (ba_xchg.cu): inbox of one rank = flags [2][XCHG_MAXR][XCHG_CTAS] u64, then data [2][XCHG_MAXR][pitch] double2
+constexpr int XCHG_MAXR = 8, XCHG_CTAS = 8, XCHG_THREADS = 512;
+constexpr size_t XCHG_FLAG_BYTES = 2 * XCHG_MAXR * XCHG_CTAS * sizeof(unsigned long long);
+struct XchgDev {
+  int nranks, rank, nvec, pitch;      // nvec = 16-byte vectors in the result blob, pitch = slot stride in vectors
+  unsigned long long seq;             // exchange number, 1, 2, ... (identical on every rank)
+  double2* inbox[XCHG_MAXR];          // data area of rank r's inbox as mapped in THIS process
+  unsigned long long* flags[XCHG_MAXR];
+  double2* buf;                       // local stitched result, all-reduced in place
+};
+
 // result blob: H_top N*N | b_top N | raw Schur Gram tiles ntiles*16 | ACC_MISC counters
 inline __host__ __device__ int result_doubles(int N, int ntiles) { return N * N + N + ntiles * 16 + ACC_MISC; }
 // accumulators: pair blocks nf*nf*TOP_PART | Schur tiles ntiles*16 | ACC_MISC | dense H (N*N) | b (N)

@@ -36,6 +36,7 @@ __device__ __forceinline__ double h13(const double* S, int r, int c) {
 // G = adHost*B and GA = (adHost P) adHost^T are formed once; every output entry is then a short sum (adTarget is diagonal).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int ST_THREADS = 512;
+#define STAMP_ST(k) do { if ((W.dbg & 16) && threadIdx.x == 0) W.dbg_clk[(size_t)(W.nchunks + blockIdx.x) * 16 + (k)] = gtime(); } while (0)
 struct alignas(16) StitchSmem {
   double raw[2][MAXF][TOP_PART];  // [0][t] pair (a,t) (a hosts), [1][t] pair (t,a) (a is target)
   double Ah[2][MAXF][64];
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
   const int tid = threadIdx.x;
   const int a = blockIdx.x;
   const BAAdj* __restrict__ A = W.adj;
+  STAMP_ST(0);
   // adjoints do not depend on the point kernel: prefetch them before waiting on the grid dependency
   if (a < nf) {
     for (int e = tid; e < nf * 32; e += ST_THREADS) {
@@ -66,6 +68,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
     }
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  STAMP_ST(1);
   if (W.dbg & 8) return;
   const double* __restrict__ TS = W.acc;
   const double* __restrict__ SC = W.acc + (size_t)nf * nf * TOP_PART;
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
   }
   cp_async_wait_all();
   __syncthreads();
+  STAMP_ST(2);
   for (int e = tid; e < 2 * nf * 104; e += ST_THREADS) {  // B[s][t][k][c] = H13[4+k][col(c)], col = 4..11, 0..3, 12
     const int s2 = e / (nf * 104), e1 = e - s2 * nf * 104, t = e1 / 104, r = e1 - t * 104, k = r / 13, c = r - k * 13;
     const int col = (c < 8) ? 4 + c : (c < 12 ? c - 8 : 12);
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
     Q.GA[t][e & 63] = m;
   }
   __syncthreads();
+  STAMP_ST(3);
   const int r0 = 4 + 8 * a;
   for (int e = tid; e < 8 * (N + 1); e += ST_THREADS) {
     const int ia = e / (N + 1), J = e - ia * (N + 1);
@@ -137,6 +142,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
     }
     R[(size_t)(r0 + ia) * N + J] = v;
   }
+  STAMP_ST(4);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

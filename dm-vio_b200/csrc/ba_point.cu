@@ -26,15 +26,8 @@ struct PointSmem {
   float hdi[P];
   float adH[MAXF][64];
   float adT[MAXF][8];
-  float2 uv[P];
-  float id[P], idz[P], prior[P];
-  float col[P][8];
-  float wgt[P][8];
-  float en[MAXF][P];
-  float rsb[MAXF][P];
+  float id[P], idz[P];                   // inverse depths the residuals were evaluated at (written by the first target's groups)
   float misc[MAXF * (P / 4)][4];
-  uint8_t st[MAXF][P];
-  uint8_t rgood[MAXF][P];
 };
 
 template <int P, int ITER>
@@ -50,8 +43,10 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
   PointSmem<P>& S = *reinterpret_cast<PointSmem<P>*>(smem_raw);
 
   const int nf = W.nf;
-  int h = 0;
-  while (h < nf - 1 && (int)blockIdx.x >= W.chunk_beg[h + 1]) h++;
+  int h = 0;  // host frame of this chunk: branch-free so that the 7 constant-bank loads are independent
+#pragma unroll
+  for (int k = 1; k < MAXF; k++) h += ((int)blockIdx.x >= W.chunk_beg[k]) ? 1 : 0;
+  h = min(h, nf - 1);
   const int ch_start = W.host_start[h] + ((int)blockIdx.x - W.chunk_beg[h]) * P;
   const int ch_count = min(P, W.host_start[h + 1] - ch_start);
   STAMP(8);
@@ -62,99 +57,20 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
   double* __restrict__ acc = W.acc;
   double* __restrict__ acc_misc = acc + (size_t)nf * nf * TOP_PART + (size_t)W.ntiles * 16;
 
-  // ---------------------------------------------------------------- prologue: stage inputs (one memory round trip)
+  // ---------------------------------------------------------------- prologue: only the adjoint blocks are staged (needed from
+  // phase B on); everything phase A needs is loaded straight into the registers of the lanes that use it, so the first
+  // block-wide barrier comes after phase A
   {
     const BAAdj* __restrict__ A = W.adj;
     for (int i = tid; i < nf * 16; i += nthreads) cp_async16(&S.adH[i >> 4][(i & 15) * 4], &A->adHostF[h * nf + (i >> 4)][(i & 15) * 4]);
     for (int i = tid; i < nf * 2; i += nthreads) cp_async16(&S.adT[i >> 1][(i & 1) * 4], &A->adTdiagF[h * nf + (i >> 1)][(i & 1) * 4]);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     STAMP(9);
-    for (int i = tid; i < ch_count * 2; i += nthreads) cp_async4(reinterpret_cast<float*>(S.uv) + i, reinterpret_cast<const float*>(W.uv + ch_start) + i);
-    for (int i = tid; i < ch_count * 8; i += nthreads) {
-      cp_async4(&S.col[0][0] + i, W.color + (size_t)ch_start * 8 + i);
-      cp_async4(&S.wgt[0][0] + i, W.weights + (size_t)ch_start * 8 + i);
-    }
-    STAMP(10);
-    for (int i = tid; i < ch_count; i += nthreads) cp_async4(&S.prior[i], W.priorF + ch_start + i);
-    if (!it.have_x)
-      for (int i = tid; i < ch_count; i += nthreads) {
-        cp_async4(&S.id[i], W.idepth + ch_start + i);
-        cp_async4(&S.idz[i], W.idepth_zero + ch_start + i);
-      }
-    for (int i = tid; i < nf * ch_count; i += nthreads) {
-      const int tt = i / ch_count, pl = i - tt * ch_count;
-      cp_async4(&S.en[tt][pl], W.en_in + (size_t)tt * mp + ch_start + pl);
-    }
-    STAMP(6);
-    float4 rs_po0 = make_float4(0.f, 0.f, 0.f, 0.f), rs_po1 = rs_po0;
-    float rs_idb = 0.f;
-    if (it.have_x) {
-      // fused resubstitute: one thread per (point,target) slot; all loads independent
-      for (int i = tid; i < nf * ch_count; i += nthreads) {
-        const int tt = i / ch_count, pl = i - tt * ch_count;
-        const int slot = tt * mp + ch_start + pl;
-        float d = 0.f;
-        uint8_t good = 0;
-        if (tt != h) {
-          const int stc = W.c_st[slot];
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)slot * 8));
-          const float4 a1 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)slot * 8) + 1);
-          const float* xa = it.xAd[h * nf + tt];
-          const float dot = xa[0] * a0.x + xa[1] * a0.y + xa[2] * a0.z + xa[3] * a0.w + xa[4] * a1.x + xa[5] * a1.y + xa[6] * a1.z + xa[7] * a1.w;
-          good = (stc == RES_IN);
-          d = good ? dot : 0.f;
-        }
-        S.rsb[tt][pl] = d;
-        S.rgood[tt][pl] = good;
-      }
-      if (tid < ch_count) {
-        rs_po0 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)(ch_start + tid) * 8));
-        rs_po1 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)(ch_start + tid) * 8) + 1);
-        rs_idb = __ldg(W.idepth_backup + ch_start + tid);
-      }
-    }
-    STAMP(7);
-    for (int i = tid; i < nf * ch_count; i += nthreads) {
-      const int tt = i / ch_count, pl = i - tt * ch_count;
-      S.st[tt][pl] = W.st_in[(size_t)tt * mp + ch_start + pl];
-    }
-    for (int i = tid; i < P * MAXF * REC; i += nthreads) (&S.rec[0][0][0])[i] = 0.f;
-    for (int i = tid; i < P * (8 * MAXF + 8); i += nthreads) (&S.Wv[0][0])[i] = 0.f;
-    for (int i = tid; i < MAXF * (P / 4) * 4; i += nthreads) (&S.misc[0][0])[i] = 0.f;
-    if (it.have_x) {
-      __syncthreads();
-      if (warp == 0) {
-        float step2 = 0.f, nid = 0.f;
-        if (tid < ch_count) {
-          const int p = ch_start + tid;
-          float bsum = rs_po1.w - (it.xc[0] * rs_po0.z + it.xc[1] * rs_po0.w + it.xc[2] * rs_po1.x + it.xc[3] * rs_po1.y);
-          int ngood = 0;
-          for (int tt = 0; tt < nf; tt++) { bsum -= S.rsb[tt][tid]; ngood += S.rgood[tt][tid]; }
-          const float step = ngood > 0 ? -bsum * rs_po1.z : 0.f;
-          const float v = rs_idb + step;
-          W.step[p] = step;
-          W.idepth_out[p] = v;  // DM-VIO: idepth_zero follows (setIdepthZero in doStepFromBackup); the host aliases the pointers
-          S.id[tid] = v;
-          S.idz[tid] = v;
-          step2 = step * step;
-          nid = fabsf(rs_idb);
-        }
-#pragma unroll
-        for (int m = 1; m < 32; m <<= 1) {
-          step2 += __shfl_xor_sync(0xffffffffu, step2, m);
-          nid += __shfl_xor_sync(0xffffffffu, nid, m);
-        }
-        if (lane == 0) {  // the sums feed only the convergence test of doStepFromBackup
-          RED_ADD(acc_misc + 4, (double)step2);
-          RED_ADD(acc_misc + 5, (double)nid);
-          RED_ADD(acc_misc + 6, (double)ch_count);
-        }
-      }
-    }
-    STAMP(1);
-    cp_async_wait_all();
   }
-  __syncthreads();
-  STAMP(2);
+  // the thread that finalises point pl_b in phase B fetches its prior now
+  const int pl_b = nthreads - 1 - tid;
+  const float prior_b = (pl_b < ch_count) ? __ldg(W.priorF + ch_start + pl_b) : 0.f;
+  STAMP(6);
 
   // ---------------------------------------------------------------- phase A
   const int t = warp / WQ;  // target frame of this warp
@@ -172,6 +88,8 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
     const int pdx = c_pattern[j][0], pdy = c_pattern[j][1];
     float e_sum = 0.f;
     int n_in = 0, n_oob = 0, n_outl = 0;
+    const int t0 = (h == 0) ? 1 : 0;  // first target frame: its groups publish the per-point step / depths
+    float rs_step2 = 0.f, rs_nid = 0.f, rs_cnt = 0.f;
 
 #pragma unroll 1
     for (int pass = 0; pass < ITER; pass++) {
@@ -183,15 +101,54 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
       }
       const int pl = min(quad * 4 + g, ch_count - 1);
       const bool valid = quad * 4 + g < ch_count;
-      const int slot = t * mp + ch_start + pl;
-      const int st = valid ? (int)S.st[t][pl] : RES_NONE;
+      const int p = ch_start + pl;
+      const int slot = t * mp + p;
+      // ---- direct loads (all independent: one memory round trip)
+      const int st = valid ? (int)__ldg(W.st_in + slot) : RES_NONE;
+      const float en_old = __ldg(W.en_in + slot);
+      const float2 uv = __ldg(W.uv + p);
+      const float col = __ldg(W.color + (size_t)p * 8 + j);
+      const float wgt = __ldg(W.weights + (size_t)p * 8 + j);
+      float idepth, idz;
+      if (it.have_x) {
+        // fused EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:L295-321) + point step (FullSystemOptimize.cpp:L264-272):
+        // lane j of the group takes target frame j of the point's committed residuals; every group of the point recomputes the
+        // same step (the loads hit L1/L2), the group of the FIRST target publishes it
+        float d = 0.f;
+        bool good = false;
+        if (j < nf && j != h) {
+          const int cs = j * mp + p;
+          const int stc = __ldg(W.c_st + cs);
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8) + 1);
+          const float* xa = it.xAd[h * nf + j];
+          const float dot = xa[0] * a0.x + xa[1] * a0.y + xa[2] * a0.z + xa[3] * a0.w + xa[4] * a1.x + xa[5] * a1.y + xa[6] * a1.z + xa[7] * a1.w;
+          good = (stc == RES_IN);
+          d = good ? dot : 0.f;
+        }
+        const float4 po0 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8));
+        const float4 po1 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8) + 1);
+        const float idb = __ldg(W.idepth_backup + p);
+        const unsigned gb = __ballot_sync(0xffffffffu, good);
+        const int ngood = __popc((gb >> (g * 8)) & 0xffu);
+        const float dsum = group_sum8(d);
+        const float bsum = po1.w - (it.xc[0] * po0.z + it.xc[1] * po0.w + it.xc[2] * po1.x + it.xc[3] * po1.y) - dsum;
+        const float step = ngood > 0 ? -bsum * po1.z : 0.f;
+        idepth = idb + step;
+        idz = idepth;  // DM-VIO: idepth_zero follows (setIdepthZero in doStepFromBackup); the host aliases the pointers
+        if (t == t0 && j == 0 && valid) {
+          W.step[p] = step;
+          W.idepth_out[p] = idepth;
+          rs_step2 += step * step;
+          rs_nid += fabsf(idb);
+          rs_cnt += 1.f;
+        }
+      } else {
+        idepth = __ldg(W.idepth + p);
+        idz = __ldg(W.idepth_zero + p);
+      }
+      if (t == t0 && j == 0 && valid) { S.id[pl] = idepth; S.idz[pl] = idz; }
       bool live = (st != RES_NONE) && (st != RES_OOB);
-
-      const float2 uv = S.uv[pl];
-      const float idepth = S.id[pl];
-      const float idz = S.idz[pl];
-      const float col = S.col[pl][j];
-      const float wgt = S.wgt[pl][j];
 
       // ---- centre pixel at the FEJ point (ResidualProjections.h:L62-87, Residuals.cpp:L108-157)
       const float Kl0 = (uv.x - cx) * fxi, Kl1 = (uv.y - cy) * fyi;
@@ -258,7 +215,7 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
       if (st == RES_NONE) {
         newState = RES_NONE; newEnergy = 0.f;
       } else if (!live) {
-        newState = RES_OOB; newEnergy = S.en[t][pl];  // OOB exits return the old state_energy
+        newState = RES_OOB; newEnergy = en_old;  // OOB exits return the old state_energy
       } else if (energy > TH || wJI2 < 2.f) {
         newState = RES_OUTLIER; newEnergy = TH;
       } else {
@@ -335,6 +292,7 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
         if (j < 6) part[TOP_ROWS * TOP_COLS + j] = (j == 0) ? Jab00 : (j == 1) ? Jab01 : (j == 2) ? Jabr0 : (j == 3) ? Jab11 : (j == 4) ? Jabr1 : rr;
       } else {
         for (int c = j; c < TOP_PART; c += 8) part[c] = 0.f;
+        if (j == 0 && valid) S.rec[pl][t][14] = 0.f;  // "no active residual" flag (shared memory is not pre-zeroed)
       }
     }
     float es = e_sum, fin = (float)n_in, foob = (float)n_oob, fout = (float)n_outl;
@@ -346,7 +304,20 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
       fout += __shfl_xor_sync(0xffffffffu, fout, m);
     }
     if (lane == 0) { S.misc[warp][0] = es; S.misc[warp][1] = fin; S.misc[warp][2] = foob; S.misc[warp][3] = fout; }
+    if (it.have_x && t == t0) {  // sum step^2, sum |idepth_backup|, #points: feed only the convergence test of doStepFromBackup
+      rs_step2 += __shfl_xor_sync(0xffffffffu, rs_step2, 8); rs_step2 += __shfl_xor_sync(0xffffffffu, rs_step2, 16);
+      rs_nid += __shfl_xor_sync(0xffffffffu, rs_nid, 8); rs_nid += __shfl_xor_sync(0xffffffffu, rs_nid, 16);
+      rs_cnt += __shfl_xor_sync(0xffffffffu, rs_cnt, 8); rs_cnt += __shfl_xor_sync(0xffffffffu, rs_cnt, 16);
+      if (lane == 0) {
+        RED_ADD(acc_misc + 4, (double)rs_step2);
+        RED_ADD(acc_misc + 5, (double)rs_nid);
+        RED_ADD(acc_misc + 6, (double)rs_cnt);
+      }
+    }
+  } else if (lane < 4) {
+    S.misc[warp][lane] = 0.f;  // idle warps (t == h or t >= nf) still own a counter slot
   }
+  cp_async_wait_all();  // the adjoint blocks staged in the prologue
   __syncthreads();
   STAMP(3);
 
@@ -372,12 +343,13 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
   const int N = W.N;
   // (a) the point finalisation (AccumulatedSCHessian.cpp:L36-58) runs on the LAST warps' lanes so that it overlaps the vector tasks
   {
-    const int pl = nthreads - 1 - tid;
+    const int pl = pl_b;
     if (pl < ch_count) {
       const int p = ch_start + pl;
       float Hdd = 0.f, bd = 0.f, Hcd0 = 0.f, Hcd1 = 0.f, Hcd2 = 0.f, Hcd3 = 0.f;
       int ngood = 0;
       for (int tt = 0; tt < nf; tt++) {
+        if (tt == h) continue;
         const float* rec = S.rec[pl][tt];
         if (rec[14] != 0.f) {
           ngood++;
@@ -385,15 +357,18 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
         }
       }
       float HdiF = 0.f, bdSum = 0.f;
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
       if (ngood > 0) {
-        const float prior = S.prior[pl];
+        const float prior = prior_b;
         float H = Hdd + prior;
         if (H < 1e-10f) H = 1e-10f;
         HdiF = 1.0f / H;
         bdSum = bd + prior * (S.id[pl] - S.idz[pl]);
-        S.Wv[pl][0] = Hcd0; S.Wv[pl][1] = Hcd1; S.Wv[pl][2] = Hcd2; S.Wv[pl][3] = Hcd3;
-        S.Wv[pl][N] = bdSum;
+        w0 = Hcd0; w1 = Hcd1; w2 = Hcd2; w3 = Hcd3;
       }
+      S.Wv[pl][0] = w0; S.Wv[pl][1] = w1; S.Wv[pl][2] = w2; S.Wv[pl][3] = w3;
+      S.Wv[pl][N] = bdSum;
+      for (int c = N + 1; c < W.NW; c++) S.Wv[pl][c] = 0.f;  // padding columns of the last 4x4 tiles
       S.hdi[pl] = HdiF;
       float4* po = reinterpret_cast<float4*>(W.pout + (size_t)p * 8);
       po[0] = make_float4(Hdd, bd, Hcd0, Hcd1);
@@ -408,6 +383,7 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
     float val = 0.f;
     if (f == h) {
       for (int tt = 0; tt < nf; tt++) {
+        if (tt == h) continue;
         const float* rec = S.rec[pl][tt];
         if (rec[14] != 0.f) {
           const float* A = &S.adH[tt][k * 8];

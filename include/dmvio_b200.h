@@ -156,6 +156,14 @@ int dmv_ba_gn_step(dmv_ba* ba, const double* x, const dmv_ba_state* st, dmv_ba_l
 int dmv_nccl_unique_id(void* id128);
 int dmv_ba_comm_init(dmv_ba* ba, int nranks, int rank, const void* nccl_unique_id);
 
+/* The same exchange without NCCL, over NVLink/NVSwitch peer memory (CUDA IPC, one process per GPU of one node, <= 8 ranks):
+ * every rank exports its inbox (64-byte cudaIpcMemHandle_t), the caller all-gathers the handles (any transport: MPI,
+ * torch.distributed, a file) and every rank imports all of them.  From then on the all-reduce is one kernel chained behind the
+ * stitch (push to all peers, flag, wait, sum in rank order => bit-identical H,b on all ranks).  Takes precedence over a NCCL
+ * communicator if both are set.  No reference counterpart (the reference is single-node CPU). */
+int dmv_ba_p2p_export(dmv_ba* ba, void* ipc_handle64);
+int dmv_ba_p2p_import(dmv_ba* ba, int nranks, int rank, const void* ipc_handles /* nranks*64 bytes, rank order */);
+
 /* timing of the last linearize/gn_step on the handle's stream (CUDA events), milliseconds: [0]=total device time of the call,
  * [1]=point kernel, [2]=reduce+stitch */
 int dmv_ba_last_timing(dmv_ba* ba, float ms[4]);

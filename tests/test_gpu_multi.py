@@ -1,0 +1,106 @@
+"""Two-rank GPU test of the sharded BA path (needs >= 2 GPUs; skipped on a single-GPU box): one process per GPU, points
+sharded (dmvio_b200.sharding), stitched systems all-reduced by (a) ba_xchg_kernel over NVLink peer memory and (b) NCCL.
+Checks: every rank ends with the bit-identical system; it equals the unsharded oracle system within the single-GPU tolerances."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, cfg, mode, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    import dmvio_b200.capi as capi
+    import dmvio_b200.hostmath as hm
+    import dmvio_b200.synth as synth
+    from dmvio_b200.sharding import shard_window
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    W = synth.make_window(**cfg)
+    S = shard_window(W, rank, world)
+    ba = capi.BA(W["w"], W["h"], max_frames=W["nf"], max_points=len(S["host"]), device=rank)
+    for k in range(W["nf"]):
+        ba.upload_frame(k, S["dI"][k])
+    ba.set_window(W["nf"])
+    ba.set_points(S["host"], S["u"], S["v"], S["idepth"], S["idepth_zero"], S["color"], S["weights"])
+    ba.set_residuals(S["res_point"], S["res_target"])
+    ba.set_adjoints(*hm.adjoints(S))
+    k8, pc, TH = hm.calib8(S["K"]), hm.precalc_table(S), S["frameEnergyTH"]
+    if mode == "p2p":
+        handles = [None] * world
+        dist.all_gather_object(handles, ba.p2p_export())
+        ba.p2p_import(world, rank, handles)
+    else:
+        uid = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ba.comm_init(world, rank, uid[0])
+    ba.set_state(k8, pc, TH)
+    out = []
+    r = ba.linearize()
+    ba.apply_res()
+    a = ba.accumulate()
+    out.append((r["energy"], r["n_in"], a["HA"].copy(), a["bA"].copy(), a["Hsc"].copy(), a["bsc"].copy()))
+    # a few fused GN steps: exercises the parity double-buffering of the inbox
+    HL, bL = hm.prior_system(W)
+    ba.backup_points()
+    for _ in range(5):
+        x = hm.solve_reduced(a["HA"], a["bA"], a["Hsc"], a["bsc"], HL, bL, lam=1e-5)
+        r = ba.gn_step(x, k8, pc, TH)
+        ba.apply_res()
+        a = ba.accumulate()
+        ba.backup_points()
+    out.append((r["energy"], r["n_in"], a["HA"].copy(), a["bA"].copy(), a["Hsc"].copy(), a["bsc"].copy()))
+    q.put((rank, out))
+    dist.barrier()
+    ba.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_two_rank_exchange(orc, synth, mode):
+    import dmvio_b200.capi as capi
+    if capi.lib().dmv_device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    cfg = dict(nf=5, npts=901, seed=17)
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for it in range(2):
+        e0, n0, *m0 = res[0][it]
+        e1, n1, *m1 = res[1][it]
+        assert e0 == e1 and n0 == n1
+        for a, b in zip(m0, m1):
+            np.testing.assert_array_equal(a, b)  # bit-identical on both ranks
+    W = synth.make_window(**cfg)
+    ow = orc.Window(W)
+    E = ow.linearize_all(update_th=False)
+    ow.apply_res()
+    a = ow.accumulate(1)
+    e0, n0, HA, bA, Hsc, bsc = res[0][0]
+    assert abs(e0 - E) <= 2e-5 * abs(E)
+    assert rel(HA, a["HA"]) < 1e-5 and rel(Hsc, a["Hsc"]) < 1e-5
+    assert rel(bA, a["bA"]) < 1e-4 and rel(bsc, a["bsc"]) < 1e-4

@@ -20,19 +20,18 @@ L = capi.lib(); L.dmv_ba_debug_clocks.argtypes = [C.c_void_p, C.c_void_p, C.c_in
 HAVE_X = int(os.environ.get('HAVE_X', '1'))
 for flush in (True, False):
     ba.bench_device(x if HAVE_X else None, iters=5, flush_l2=flush)
-    buf = np.zeros(16 * 400, np.uint64)
+    buf = np.zeros(16 * 600, np.uint64)
     n = L.dmv_ba_debug_clocks(ba.h, buf.ctypes.data_as(C.c_void_p), len(buf))
     t = buf[:n].reshape(-1, 16).astype(np.int64)
+    ts = t[-8:]  # the nf+1 = 8 stitch CTAs
+    t = t[:-8]
     t0 = t[:, 0].min()
-    order = [0, 8, 9, 10, 6, 7, 1, 2, 3, 4, 5]
-    names = {8: "chunk_known", 9: "adj_issued", 10: "uvcolwgt_issued", 0: "start", 6: "cpasync_issued", 7: "resub_loads_used", 1: "resub_done", 2: "staged+sync", 3: "phaseA", 4: "phaseB", 5: "end"}
+    order = [0, 8, 9, 6, 3, 4, 5]
+    names = {8: "chunk_known", 9: "adj_issued", 0: "start", 6: "prior_issued", 3: "phaseA+sync", 4: "phaseB", 5: "end"}
     print(f"P={P} flush={flush} have_x={HAVE_X} blocks={len(t)}  (ns relative to first CTA start; mean / max over CTAs)")
     prev = 0
     for k in order:
         print(f"  {names[k]:17s} mean {np.mean(t[:, k] - t0):9.0f}  max {np.max(t[:, k] - t0):9.0f}   dt_mean {np.mean(t[:, k] - t[:, prev]):8.0f}")
         prev = k
-    last = t[:, 11] > t[:, 5]
-    print(f"  tail (all CTAs, mean ns): fence+sync {np.mean(t[:,12]-t[:,5]):.0f}, host ticket {np.mean(t[:,13]-t[:,12]):.0f}, host stitch {np.mean(t[:,14]-t[:,13]):.0f} (max {np.max(t[:,14]-t[:,13])}), final ticket {np.mean(t[:,15]-t[:,14]):.0f}")
-    if last.any():
-        i = np.argmax(t[:, 11] * last)
-        print(f"  last CTA {i}: phaseC end {t[i,5]-t0}, fence+sync {t[i,12]-t[i,5]}, host ticket {t[i,13]-t[i,12]}, host stitch {t[i,14]-t[i,13]}, final ticket {t[i,15]-t[i,14]}, final {t[i,11]-t[i,15]}; end {t[i,11]-t0}; all CTAs' phaseC end max {np.max(t[:,5]-t0)}, stamp15 max {np.max(t[:,15]-t0)}")
+    print(f"  stitch (ns rel. to first point-CTA start, mean/max over {len(ts)} CTAs): resident {np.mean(ts[:,0]-t0):.0f}/{np.max(ts[:,0]-t0)}, dependency released {np.mean(ts[:,1]-t0):.0f}/{np.max(ts[:,1]-t0)}, "
+          f"staged {np.mean(ts[:-1,2]-t0):.0f}/{np.max(ts[:-1,2]-t0)}, products done {np.mean(ts[:-1,3]-t0):.0f}/{np.max(ts[:-1,3]-t0)}, written {np.mean(ts[:-1,4]-t0):.0f}/{np.max(ts[:-1,4]-t0)}")
