@@ -9,6 +9,7 @@
 //   pyr_down_kernel / grad_kernel   FrameHessian::makeImages (HessianBlocks.cpp:L128-191) on the device.
 #include "../../include/dmvio_b200.h"
 #include "common_host.h"
+#include "inv3.h"
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -326,8 +327,10 @@ int dmv_ct_calc_res_gs(dmv_ct* c, int l, const float RKi[9], const float t[3], c
   std::memcpy(P.RKi, RKi, sizeof(P.RKi));
   std::memcpy(P.t, t, sizeof(P.t));
   // Ki[lvl] = K^-1 (CoarseTracker.cpp:L126-133)
-  std::memset(P.Ki, 0, sizeof(P.Ki));
-  P.Ki[0] = 1.0f / c->fx[l]; P.Ki[4] = 1.0f / c->fy[l]; P.Ki[8] = 1.f; P.Ki[2] = -c->cx[l] / c->fx[l]; P.Ki[5] = -c->cy[l] / c->fy[l];
+  {
+    const float Kl[9] = {c->fx[l], 0.f, c->cx[l], 0.f, c->fy[l], c->cy[l], 0.f, 0.f, 1.f};
+    inv3_cofactor(Kl, P.Ki);
+  }
   P.fx = c->fx[l]; P.fy = c->fy[l]; P.cx = c->cx[l]; P.cy = c->cy[l];
   P.affa = affLL[0]; P.affb = affLL[1]; P.a_gs = affLL[0]; P.b0 = b0;
   P.cutoff = cutoffTH; P.huber = c->huber;

@@ -1,5 +1,6 @@
 // Host-side C++ mirror of CoarseTracker on top of the C ABI — see coarse_tracker.h.
 #include "coarse_tracker.h"
+#include "../csrc/inv3.h"
 #include <algorithm>
 #include <cmath>
 
@@ -101,7 +102,9 @@ bool CoarseTracker::eval(int lvl, const SE3& refToNew, AffLight aff_g2l, float c
   float R[9], t[3], RKi[9];
   for (int i = 0; i < 9; i++) R[i] = (float)refToNew.R[i];
   for (int i = 0; i < 3; i++) t[i] = (float)refToNew.t[i];
-  const float Ki[9] = {1.0f / fx_[lvl], 0, -cx_[lvl] / fx_[lvl], 0, 1.0f / fy_[lvl], -cy_[lvl] / fy_[lvl], 0, 0, 1};
+  const float Kl[9] = {fx_[lvl], 0.f, cx_[lvl], 0.f, fy_[lvl], cy_[lvl], 0.f, 0.f, 1.f};
+  float Ki[9];
+  dmv::inv3_cofactor(Kl, Ki);  // Ki[lvl] = K[lvl].inverse() with the reference's rounding (CoarseTracker.cpp:L128)
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) RKi[i * 3 + j] = R[i * 3] * Ki[j] + R[i * 3 + 1] * Ki[3 + j] + R[i * 3 + 2] * Ki[6 + j];
   double aff[2];

@@ -1,5 +1,6 @@
 // Host-side C++ mirror of FullSystem::optimize / EnergyFunctional on top of the C ABI — see window_ba.h.
 #include "window_ba.h"
+#include "../csrc/inv3.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -176,7 +177,8 @@ void WindowBA::setPrecalcValues() {  // FullSystem.cpp:L1670-1680 -> FrameFrameP
   precalc.assign((size_t)n * n * DMV_PRECALC_FLOATS, 0.f);
   const float fx = Hcalib.value_scaledf[0], fy = Hcalib.value_scaledf[1], cx = Hcalib.value_scaledf[2], cy = Hcalib.value_scaledf[3];
   const float K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
-  const float Ki[9] = {1.0f / fx, 0, -cx / fx, 0, 1.0f / fy, -cy / fy, 0, 0, 1};
+  float Ki[9];
+  dmv::inv3_cofactor(K, Ki);  // K.inverse() with the reference's rounding (FrameFramePrecalc::set, HessianBlocks.cpp:L217)
   for (int h = 0; h < n; h++)
     for (int t = 0; t < n; t++) {
       const FrameHessian& host = frameHessians[h];

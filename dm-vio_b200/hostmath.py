@@ -32,6 +32,33 @@ def aff_from_to(expF, expT, aF, bF, aT, bT):
     return a, bT - a * bF
 
 
+def inv3_cofactor_f32(M):
+    """3x3 float32 inverse the way Eigen evaluates it for fixed sizes: cofactors times one reciprocal of the determinant
+    (FrameFramePrecalc::set computes K.inverse() like this, HessianBlocks.cpp:L217); every step rounded to float32."""
+    M = np.asarray(M, np.float32)
+    f = np.float32
+
+    def cof(i, j):
+        i1, i2, j1, j2 = (i + 1) % 3, (i + 2) % 3, (j + 1) % 3, (j + 2) % 3
+        return f(f(M[i1, j1] * M[i2, j2]) - f(M[i1, j2] * M[i2, j1]))
+
+    c0, c1, c2 = cof(0, 0), cof(1, 0), cof(2, 0)
+    det = f(f(f(c0 * M[0, 0]) + f(c1 * M[1, 0])) + f(c2 * M[2, 0]))
+    invdet = f(f(1.0) / det)
+    out = np.zeros((3, 3), np.float32)
+    out[0, 0], out[0, 1], out[0, 2] = f(c0 * invdet), f(c1 * invdet), f(c2 * invdet)
+    out[1, 0], out[1, 1], out[1, 2] = f(cof(0, 1) * invdet), f(cof(1, 1) * invdet), f(cof(2, 1) * invdet)
+    out[2, 0], out[2, 1], out[2, 2] = f(cof(0, 2) * invdet), f(cof(1, 2) * invdet), f(cof(2, 2) * invdet)
+    return out
+
+
+def mm3_f32(A, B):
+    """3x3 float32 product with the sequential inner-product order of the reference's fixed-size Eigen product, ((a0*b0 + a1*b1) + a2*b2),
+    every step rounded to float32 (numpy's matmul may reorder / fuse)."""
+    A = np.asarray(A, np.float32); B = np.asarray(B, np.float32)
+    return ((A[:, 0:1] * B[0:1, :] + A[:, 1:2] * B[1:2, :]) + A[:, 2:3] * B[2:3, :]).astype(np.float32)
+
+
 def precalc_table(W, state=None, K_scaled=None):
     """nf*nf*32 float32, index h*nf+t: KRKi[9] Kt[3] R0[9] t0[3] aff[2] b0 pad[5]."""
     nf = W["nf"]
@@ -40,8 +67,7 @@ def precalc_table(W, state=None, K_scaled=None):
     k8 = calib8(K_scaled)
     K = np.zeros((3, 3), np.float32)
     K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[2, 2] = k8[0], k8[1], k8[2], k8[3], 1
-    Ki = np.zeros((3, 3), np.float32)
-    Ki[0, 0], Ki[1, 1], Ki[0, 2], Ki[1, 2], Ki[2, 2] = k8[4], k8[5], k8[6], k8[7], 1
+    Ki = inv3_cofactor_f32(K)
     cur = frame_poses(W, state)
     out = np.zeros((nf * nf, 32), np.float32)
     for h in range(nf):
@@ -52,8 +78,8 @@ def precalc_table(W, state=None, K_scaled=None):
             R, tt = se3_mul(cur[t][0], cur[t][1], Rhi, thi)
             Rf = R.astype(np.float32)
             q = out[h * nf + t]
-            q[0:9] = (K @ Rf @ Ki).reshape(-1)
-            q[9:12] = K @ tt.astype(np.float32)
+            q[0:9] = mm3_f32(mm3_f32(K, Rf), Ki).reshape(-1)
+            q[9:12] = mm3_f32(K, tt.astype(np.float32).reshape(3, 1)).reshape(-1)
             q[12:21] = R0.astype(np.float32).reshape(-1)
             q[21:24] = t0.astype(np.float32)
             a, b = aff_from_to(W["exposure"][h], W["exposure"][t], state[h, 6] * SCALE_A, state[h, 7] * SCALE_B, state[t, 6] * SCALE_A,

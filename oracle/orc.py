@@ -107,8 +107,8 @@ def _ptr(a):
 class Window:
     """A sliding window loaded into the oracle from a dmvio_b200.synth.make_window() dict."""
 
-    def __init__(self, W, nthreads=1, native=False, settings=None):
-        self.L = lib(native)
+    def __init__(self, W, nthreads=1, native=False, settings=None, _lib=None):
+        self.L = _lib if _lib is not None else lib(native)
         self.W = W
         self.nf, self.npts, self.nres = W["nf"], len(W["host"]), len(W["res_point"])
         self.N = 8 * self.nf + 4
@@ -131,7 +131,8 @@ class Window:
         self.L.orc_win_set_residuals(self.h, self.nres, c(W["res_point"], np.int32), c(W["res_target"], np.int32),
                                      _ptr(None if ss is None else c(ss, np.int32)), _ptr(None if se is None else c(se, np.float32)), None)
         HM, bM = W.get("HM"), W.get("bM")
-        self.L.orc_win_set_marg_prior(self.h, _ptr(None if HM is None else c(HM, np.float64)), _ptr(None if bM is None else c(bM, np.float64)))
+        if HM is not None or bM is not None or _lib is None:
+            self.L.orc_win_set_marg_prior(self.h, _ptr(None if HM is None else c(HM, np.float64)), _ptr(None if bM is None else c(bM, np.float64)))
         self.L.orc_win_prepare(self.h)
 
     def __del__(self):

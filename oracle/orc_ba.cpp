@@ -86,10 +86,10 @@ void Window::setPrecalcValues() {
       p.distanceLL = (float)std::sqrt(tt[0] * tt[0] + tt[1] * tt[1] + tt[2] * tt[2]);
       Mat33f K;
       K(0, 0) = calib.fxl(); K(1, 1) = calib.fyl(); K(0, 2) = calib.cxl(); K(1, 2) = calib.cyl(); K(2, 2) = 1;
-      // K.inverse() of an upper-triangular pinhole matrix (Eigen computes the general 3x3 inverse in float)
-      Mat33f Ki;
-      Ki(0, 0) = 1.0f / K(0, 0); Ki(1, 1) = 1.0f / K(1, 1); Ki(2, 2) = 1;
-      Ki(0, 2) = -K(0, 2) / K(0, 0); Ki(1, 2) = -K(1, 2) / K(1, 1);
+      // K.inverse(): Eigen evaluates a fixed-size 3x3 inverse in float by cofactors (det from the first column, ONE reciprocal,
+      // every cofactor times that reciprocal), so e.g. Ki(0,2) = -(cx*fy) * (1/(fy*fx)), not -cx/fx; the rounding is visible
+      // in PRE_KRKiTll (pinned against the compiled reference, tests/test_ref_pin.py)
+      const Mat33f Ki = inverse3_cofactor(K);
       p.PRE_KRKiTll = K * p.PRE_RTll * Ki;
       p.PRE_RKiTll = p.PRE_RTll * Ki;
       p.PRE_KtTll = K * p.PRE_tTll;

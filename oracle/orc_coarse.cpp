@@ -78,9 +78,7 @@ void CoarseTracker::makeK(const GlobalCalib& g) {  // CoarseTracker.cpp:L105-134
     w[l] = g.wG[l]; h[l] = g.hG[l]; fx[l] = g.fxG[l]; fy[l] = g.fyG[l]; cx[l] = g.cxG[l]; cy[l] = g.cyG[l];
     Mat33f K;
     K(0, 0) = fx[l]; K(0, 2) = cx[l]; K(1, 1) = fy[l]; K(1, 2) = cy[l]; K(2, 2) = 1;
-    Mat33f I;
-    I(0, 0) = 1.0f / fx[l]; I(1, 1) = 1.0f / fy[l]; I(2, 2) = 1; I(0, 2) = -cx[l] / fx[l]; I(1, 2) = -cy[l] / fy[l];
-    Ki[l] = I;
+    Ki[l] = inverse3_cofactor(K);  // K[level].inverse() in float, as Eigen evaluates it (CoarseTracker.cpp:L128)
   }
 }
 

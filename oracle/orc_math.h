@@ -252,4 +252,24 @@ inline bool ldlt_solve(const MatX& A, const VecX& b, VecX& x) {
   return true;
 }
 
+
+// Fixed-size 3x3 inverse the way Eigen evaluates it (cofactors, determinant from the first column, ONE reciprocal): the reference
+// calls K.inverse() on float 3x3 pinhole matrices (HessianBlocks.cpp:L217, CoarseTracker.cpp:L128, globalCalib.cpp:L82) and the
+// rounding of that inverse is visible downstream; pinned against the compiled reference by tests/test_ref_pin.py.
+template <class T>
+inline Mat<T, 3, 3> inverse3_cofactor(const Mat<T, 3, 3>& K) {
+  auto cof = [&](int i, int j) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return K(i1, j1) * K(i2, j2) - K(i1, j2) * K(i2, j1);
+  };
+  const T c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+  const T det = (c0 * K(0, 0) + c1 * K(1, 0)) + c2 * K(2, 0);
+  const T invdet = T(1) / det;
+  Mat<T, 3, 3> R;
+  R(0, 0) = c0 * invdet; R(0, 1) = c1 * invdet; R(0, 2) = c2 * invdet;
+  R(1, 0) = cof(0, 1) * invdet; R(1, 1) = cof(1, 1) * invdet; R(1, 2) = cof(2, 1) * invdet;
+  R(2, 0) = cof(0, 2) * invdet; R(2, 1) = cof(1, 2) * invdet; R(2, 2) = cof(2, 2) * invdet;
+  return R;
+}
+
 }  // namespace orc

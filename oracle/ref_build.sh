@@ -1,0 +1,30 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE ONLY — builds oracle/_ref/libdso_ref.so from the REFERENCE's own sources where they lie under
+# /root/reference (read-only; nothing is copied into the repo) plus oracle/ref_harness.cpp.  The reference's build system is
+# not run: a plain g++ loop over the hot-path translation units, with the flags of its CMakeLists.txt:L44-57 (-O3, no
+# -march).  Eigen / Sophus-on-Eigen / Boost.Thread are absent from this image: oracle/shim/ provides stand-ins (first on the
+# include path), and shadows the two reference headers that pull in GTSAM / yaml-cpp (FullSystem/FullSystem.h,
+# IMU/IMUIntegration.hpp).  Output goes to oracle/_ref/ only (git-ignored, travels to the GPU box with gpurun).
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF=${REF_ROOT:-/root/reference}
+if [ ! -d "$REF/src/dso" ]; then echo "ref_build: $REF/src/dso not present (GPU box): keeping the prebuilt oracle/_ref"; exit 0; fi
+OUT="$HERE/_ref"
+mkdir -p "$OUT/obj"
+CXX=${CXX:-g++}
+FLAGS="-std=c++17 -O3 -fPIC -w -I$HERE/shim -I$REF/src/dso -I$REF/src"
+SRCS="dso/OptimizationBackend/AccumulatedTopHessian.cpp dso/OptimizationBackend/AccumulatedSCHessian.cpp dso/OptimizationBackend/EnergyFunctional.cpp
+dso/OptimizationBackend/EnergyFunctionalStructs.cpp dso/FullSystem/HessianBlocks.cpp dso/FullSystem/Residuals.cpp dso/FullSystem/ImmaturePoint.cpp
+dso/FullSystem/CoarseTracker.cpp dso/util/settings.cpp dso/util/globalCalib.cpp util/TimeMeasurement.cpp"
+OBJS=""
+for s in $SRCS; do
+  o="$OUT/obj/$(basename "$s" .cpp).o"
+  if [ ! -f "$o" ] || [ "$REF/src/$s" -nt "$o" ] || [ "$HERE/shim/Eigen/Core" -nt "$o" ] || [ "$HERE/shim/sophus/se3.hpp" -nt "$o" ]; then
+    $CXX $FLAGS -c "$REF/src/$s" -o "$o" &
+  fi
+  OBJS="$OBJS $o"
+done
+wait
+$CXX $FLAGS -c "$HERE/ref_harness.cpp" -o "$OUT/obj/ref_harness.o"
+$CXX -shared -pthread -o "$OUT/libdso_ref.so" $OBJS "$OUT/obj/ref_harness.o"
+echo "ref_build: $OUT/libdso_ref.so"

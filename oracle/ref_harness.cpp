@@ -1,0 +1,552 @@
+// TEST INFRASTRUCTURE ONLY — C harness around the REFERENCE's own hot-path code, compiled from where it lies under
+// /root/reference into oracle/_ref/libdso_ref.so by oracle/ref_build.sh (nothing of the reference is copied into this repo).
+//
+// Compiled reference translation units (unmodified): OptimizationBackend/{AccumulatedTopHessian,AccumulatedSCHessian,
+// EnergyFunctional,EnergyFunctionalStructs}.cpp, FullSystem/{Residuals,HessianBlocks,ImmaturePoint,CoarseTracker}.cpp,
+// util/{settings,globalCalib}.cpp, src/util/TimeMeasurement.cpp.  Third-party headers the image lacks are replaced by the
+// stand-ins in oracle/shim/ (Eigen, Sophus, Boost.Thread); the reference headers FullSystem/FullSystem.h and
+// IMU/IMUIntegration.hpp are shadowed there because they drag in GTSAM / yaml-cpp (DESIGN.md §2 lists exactly what is
+// shadowed).  This file only builds the object graph the reference's functions expect (FrameHessian / PointHessian /
+// PointFrameResidual / EnergyFunctional / CoarseTracker) from flat arrays and calls them; it exports the same C entry points as
+// oracle/orc_capi.h with the prefix ref_ so that tests/test_ref_pin.py can run the oracle and the reference side by side.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <deque>
+#include <fstream>
+#include <iostream>
+#include <functional>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+
+#define private public
+#define protected public
+#include "FullSystem/FullSystem.h"
+#include "FullSystem/CoarseTracker.h"
+#include "FullSystem/ImmaturePoint.h"
+#include "OptimizationBackend/EnergyFunctional.h"
+#include "OptimizationBackend/EnergyFunctionalStructs.h"
+#include "OptimizationBackend/AccumulatedTopHessian.h"
+#include "OptimizationBackend/AccumulatedSCHessian.h"
+#include "util/globalCalib.h"
+#include "util/settings.h"
+#undef private
+#undef protected
+
+using namespace dso;
+
+// ---- link-time leftovers of translation units that are NOT compiled (FullSystem.cpp, IOWrapper): never executed
+namespace dso {
+int PointHessian::instanceCounter = 0;  // FullSystem.cpp:L66-68
+int FrameHessian::instanceCounter = 0;
+int CalibHessian::instanceCounter = 0;
+namespace IOWrap {
+void displayImage(const char*, const MinimalImageB3*, bool) {}
+int waitKey(int) { return 0; }
+void writeImage(std::string, MinimalImageB3*) {}
+}  // namespace IOWrap
+}  // namespace dso
+
+namespace {
+
+struct RefWin {
+  int w, h, nf;
+  CalibHessian* Hcalib = nullptr;
+  dmvio::BAGTSAMIntegration gtsam;
+  EnergyFunctional* ef = nullptr;
+  std::vector<FrameHessian*> frames;
+  std::vector<PointHessian*> points;
+  std::vector<PointFrameResidual*> residuals;
+  bool prepared = false;
+  // staged inputs
+  struct Pt { int host; float u, v, idepth, idepth_zero; float color[8], weights[8]; unsigned char prior; };
+  struct Rs { int point, target, state; float energy; };
+  std::vector<Pt> pts;
+  std::vector<Rs> res;
+};
+
+void set_calib_globals(int w, int h, const double K[4]) {
+  Eigen::Matrix3f Km;
+  Km.setZero();
+  Km(0, 0) = (float)K[0]; Km(1, 1) = (float)K[1]; Km(0, 2) = (float)K[2]; Km(1, 2) = (float)K[3]; Km(2, 2) = 1.f;
+  setGlobalCalib(w, h, Km);
+  setting_useIMU = false;               // visual-only branches of the reference (no GTSAM in this image)
+  setting_useGTSAMIntegration = false;
+  multiThreading = false;
+  setting_debugout_runquiet = true;
+}
+
+template <class M> void copy_rowmajor(const M& m, int r, int c, float* out) { for (int i = 0; i < r; i++) for (int j = 0; j < c; j++) out[i * c + j] = (float)m(i, j); }
+
+}  // namespace
+
+extern "C" {
+
+RefWin* ref_win_create(int w, int h, int nf, const double calib_value_scaled[4], int nthreads) {
+  set_calib_globals(w, h, calib_value_scaled);
+  RefWin* W = new RefWin();
+  W->w = w; W->h = h; W->nf = nf;
+  W->Hcalib = new CalibHessian();
+  W->ef = new EnergyFunctional(W->gtsam);
+  W->frames.assign(nf, nullptr);
+  // the reference's own worker pool (NUM_THREADS = 6 workers, util/IndexThreadReduce.h); FullSystem always attaches it
+  // (FullSystem.cpp:L170) and calcLEnergyF_MT uses it unconditionally; `multiThreading` selects the MT accumulation paths
+  W->ef->red = new IndexThreadReduce<Vec10>();
+  multiThreading = nthreads > 1;
+  return W;
+}
+
+void ref_win_destroy(RefWin* W) {
+  if (!W) return;
+  // tear down in the reference's ownership order (residuals -> EF mirrors -> points -> frames)
+  for (PointFrameResidual* r : W->residuals) { if (r->efResidual) { delete r->efResidual; r->efResidual = 0; } }
+  for (PointHessian* p : W->points) { if (p->efPoint) { delete p->efPoint; p->efPoint = 0; } }
+  for (FrameHessian* f : W->frames) if (f) { if (f->efFrame) { delete f->efFrame; f->efFrame = 0; } }
+  W->ef->frames.clear();
+  W->ef->allPoints.clear();
+  if (W->ef->red) { delete W->ef->red; W->ef->red = 0; }
+  for (FrameHessian* f : W->frames) delete f;  // deletes its pointHessians, which delete their residuals
+  delete W->ef;
+  delete W->Hcalib;
+  delete W;
+}
+
+void ref_win_set_setting(RefWin*, const char* name, double v) {
+  std::string n(name);
+  if (n == "huberTH") setting_huberTH = (float)v;
+  else if (n == "outlierTHSumComponent") setting_outlierTHSumComponent = (float)v;
+  else if (n == "affineOptModeA") setting_affineOptModeA = (float)v;
+  else if (n == "affineOptModeB") setting_affineOptModeB = (float)v;
+  else if (n == "solverMode") setting_solverMode = (int)v;
+  else fprintf(stderr, "ref_win_set_setting: unknown setting %s\n", name);
+}
+
+void ref_win_set_frame(RefWin* W, int idx, const double R[9], const double t[3], const double state[10], const double state_zero[10], float ab_exposure,
+                       float frameEnergyTH, int frameID, const float* dI) {
+  FrameHessian* fh = new FrameHessian();
+  fh->shell = 0;
+  fh->idx = idx;
+  fh->frameID = frameID;
+  fh->ab_exposure = ab_exposure;
+  fh->frameEnergyTH = frameEnergyTH;
+  Mat33 Rm; Vec3 tv;
+  for (int i = 0; i < 3; i++) { tv[i] = t[i]; for (int j = 0; j < 3; j++) Rm(i, j) = R[3 * i + j]; }
+  fh->worldToCam_evalPT = SE3(Rm, tv);
+  Vec10 s, s0;
+  for (int i = 0; i < 10; i++) { s[i] = state[i]; s0[i] = state_zero[i]; }
+  fh->setStateZero(s0);
+  fh->setState(s);
+  fh->step.setZero(); fh->step_backup.setZero(); fh->state_backup = s;
+  for (int l = 0; l < PYR_LEVELS; l++) { fh->dIp[l] = 0; fh->absSquaredGrad[l] = 0; }
+  for (int l = 0; l < pyrLevelsUsed; l++) {
+    fh->dIp[l] = new Eigen::Vector3f[wG[l] * hG[l]];
+    fh->absSquaredGrad[l] = new float[wG[l] * hG[l]];
+  }
+  for (int i = 0; i < W->w * W->h; i++) fh->dIp[0][i] = Eigen::Vector3f(dI[3 * i], dI[3 * i + 1], dI[3 * i + 2]);
+  fh->dI = fh->dIp[0];
+  W->frames[idx] = fh;
+}
+
+void ref_win_set_points(RefWin* W, int npts, const int32_t* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
+                        const float* color8, const float* weights8, const uint8_t* hasDepthPrior) {
+  W->pts.resize(npts);
+  for (int i = 0; i < npts; i++) {
+    RefWin::Pt& p = W->pts[i];
+    p.host = host[i]; p.u = u[i]; p.v = v[i]; p.idepth = idepth[i]; p.idepth_zero = idepth_zero[i];
+    std::memcpy(p.color, color8 + 8 * i, 32); std::memcpy(p.weights, weights8 + 8 * i, 32);
+    p.prior = hasDepthPrior ? hasDepthPrior[i] : 0;
+  }
+}
+
+void ref_win_set_residuals(RefWin* W, int nres, const int32_t* point, const int32_t* target, const int32_t* state_state, const float* state_energy,
+                           const uint8_t*) {
+  W->res.resize(nres);
+  for (int i = 0; i < nres; i++) {
+    W->res[i].point = point[i]; W->res[i].target = target[i];
+    W->res[i].state = state_state ? state_state[i] : 0;
+    W->res[i].energy = state_energy ? state_energy[i] : 0.f;
+  }
+}
+
+void ref_win_prepare(RefWin* W) {
+  // FullSystem::makeKeyFrame order: frames into the energy functional, then points, then residuals
+  for (FrameHessian* fh : W->frames) W->ef->insertFrame(fh, W->Hcalib);
+  for (const RefWin::Pt& p : W->pts) {
+    FrameHessian* host = W->frames[p.host];
+    ImmaturePoint ipt((int)p.u, (int)p.v, host, 1.f, W->Hcalib);  // samples colour / weights from the host image (ImmaturePoint.cpp:L34-63)
+    ipt.idepth_min = ipt.idepth_max = p.idepth;
+    PointHessian* ph = new PointHessian(&ipt, W->Hcalib);
+    ph->u = p.u; ph->v = p.v;
+    std::memcpy(ph->color, p.color, 32);      // identical inputs on both sides of the comparison
+    std::memcpy(ph->weights, p.weights, 32);
+    ph->setIdepthScaled(p.idepth);
+    ph->setIdepthZero(p.idepth_zero);
+    ph->hasDepthPrior = p.prior != 0;
+    ph->setPointStatus(PointHessian::ACTIVE);
+    ph->step = ph->step_backup = 0; ph->idepth_backup = p.idepth;
+    ph->idx = (int)host->pointHessians.size();
+    host->pointHessians.push_back(ph);
+    W->ef->insertPoint(ph);
+    W->points.push_back(ph);
+  }
+  for (const RefWin::Rs& r : W->res) {
+    PointHessian* ph = W->points[r.point];
+    PointFrameResidual* pr = new PointFrameResidual(ph, ph->host, W->frames[r.target]);
+    pr->setState((ResState)r.state);
+    pr->state_energy = r.energy;
+    ph->residuals.push_back(pr);
+    W->ef->insertResidual(pr);
+    W->residuals.push_back(pr);
+  }
+  W->ef->setAdjointsF(W->Hcalib);
+  W->ef->makeIDX();
+  // FullSystem::setPrecalcValues (FullSystem.cpp:L1670-1680)
+  for (FrameHessian* fh : W->frames) {
+    fh->targetPrecalc.resize(W->frames.size());
+    for (unsigned int i = 0; i < W->frames.size(); i++) fh->targetPrecalc[i].set(fh, W->frames[i], W->Hcalib);
+  }
+  W->ef->setDeltaF(W->Hcalib);
+  W->prepared = true;
+}
+
+int ref_win_nres(RefWin* W) { return (int)W->residuals.size(); }
+int ref_win_npts(RefWin* W) { return (int)W->points.size(); }
+int ref_win_nf(RefWin* W) { return W->nf; }
+
+void ref_win_get_precalc(RefWin* W, float* out) {
+  const int nf = W->nf;
+  for (int h = 0; h < nf; h++)
+    for (int t = 0; t < nf; t++) {
+      float* o = out + (size_t)(h * nf + t) * 32;
+      std::memset(o, 0, 32 * sizeof(float));
+      const FrameFramePrecalc& p = W->frames[h]->targetPrecalc[t];
+      copy_rowmajor(p.PRE_KRKiTll, 3, 3, o);
+      for (int k = 0; k < 3; k++) o[9 + k] = p.PRE_KtTll[k];
+      copy_rowmajor(p.PRE_RTll_0, 3, 3, o + 12);
+      for (int k = 0; k < 3; k++) o[21 + k] = p.PRE_tTll_0[k];
+      o[24] = p.PRE_aff_mode[0]; o[25] = p.PRE_aff_mode[1]; o[26] = p.PRE_b0_mode;
+    }
+}
+
+void ref_win_get_adjoints(RefWin* W, double* adHost, double* adTarget) {
+  const int nf = W->nf;
+  for (int k = 0; k < nf * nf; k++)
+    for (int i = 0; i < 8; i++)
+      for (int j = 0; j < 8; j++) { adHost[(size_t)k * 64 + i * 8 + j] = W->ef->adHost[k](i, j); adTarget[(size_t)k * 64 + i * 8 + j] = W->ef->adTarget[k](i, j); }
+}
+
+void ref_win_get_adHTdeltaF(RefWin* W, float* out) {
+  for (int k = 0; k < W->nf * W->nf; k++) for (int i = 0; i < 8; i++) out[k * 8 + i] = W->ef->adHTdeltaF[k][i];
+}
+
+void ref_win_get_frame_tables(RefWin* W, double* prior8, double* delta_prior8, double* delta8, float* TH) {
+  for (int f = 0; f < W->nf; f++) {
+    EFFrame* e = W->frames[f]->efFrame;
+    for (int i = 0; i < 8; i++) { prior8[f * 8 + i] = e->prior[i]; delta_prior8[f * 8 + i] = e->delta_prior[i]; delta8[f * 8 + i] = e->delta[i]; }
+    TH[f] = W->frames[f]->frameEnergyTH;
+  }
+}
+
+void ref_win_get_calib(RefWin* W, float* k8, float* cDeltaF4, double* cPrior4) {
+  for (int i = 0; i < 4; i++) { k8[i] = W->Hcalib->value_scaledf[i]; k8[4 + i] = W->Hcalib->value_scaledi[i]; cDeltaF4[i] = W->ef->cDeltaF[i]; cPrior4[i] = W->ef->cPrior[i]; }
+}
+
+// FullSystem::linearizeAll(false) without setNewFrameEnergyTH (FullSystemOptimize.cpp:L55-88, L150-172): map linearize, sum the energies
+double ref_win_linearize_all(RefWin* W, int fixLinearization, int updateEnergyTH) {
+  if (fixLinearization || updateEnergyTH) { fprintf(stderr, "ref harness: fixLinearization / setNewFrameEnergyTH live in FullSystem (not compiled)\n"); abort(); }
+  double E = 0;
+  for (PointFrameResidual* r : W->residuals) E += r->linearize(W->Hcalib);
+  return E;
+}
+
+void ref_win_apply_res(RefWin* W) { for (PointFrameResidual* r : W->residuals) r->applyRes(true); }
+
+void ref_win_get_res_outputs(RefWin* W, int32_t* newState, float* newEnergy, float* newEnergyWithOutlier, float* cpt3, float* J74, int32_t* state_state,
+                             uint8_t* isActive, float* JpJdF8) {
+  for (size_t i = 0; i < W->residuals.size(); i++) {
+    PointFrameResidual* r = W->residuals[i];
+    if (newState) newState[i] = (int)r->state_NewState;
+    if (newEnergy) newEnergy[i] = (float)r->state_NewEnergy;
+    if (newEnergyWithOutlier) newEnergyWithOutlier[i] = (float)r->state_NewEnergyWithOutlier;
+    if (cpt3) for (int k = 0; k < 3; k++) cpt3[3 * i + k] = r->centerProjectedTo[k];
+    if (J74) {
+      float* o = J74 + 74 * i;
+      const RawResidualJacobian* J = r->J;
+      for (int k = 0; k < 8; k++) o[k] = J->resF[k];
+      for (int a = 0; a < 2; a++) for (int k = 0; k < 6; k++) o[8 + a * 6 + k] = J->Jpdxi[a][k];
+      for (int a = 0; a < 2; a++) for (int k = 0; k < 4; k++) o[20 + a * 4 + k] = J->Jpdc[a][k];
+      o[28] = J->Jpdd[0]; o[29] = J->Jpdd[1];
+      for (int a = 0; a < 2; a++) for (int k = 0; k < 8; k++) { o[30 + a * 8 + k] = J->JIdx[a][k]; o[46 + a * 8 + k] = J->JabF[a][k]; }
+      for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) { o[62 + a * 2 + b] = J->JIdx2(a, b); o[66 + a * 2 + b] = J->JabJIdx(a, b); o[70 + a * 2 + b] = J->Jab2(a, b); }
+    }
+    if (state_state) state_state[i] = (int)r->state_state;
+    if (isActive) isActive[i] = r->efResidual->isActiveAndIsGoodNEW ? 1 : 0;
+    if (JpJdF8) for (int k = 0; k < 8; k++) JpJdF8[8 * i + k] = r->efResidual->JpJdF[k];
+  }
+}
+
+static void out_mat(const MatXX& M, double* out) { if (out) for (int i = 0; i < M.rows(); i++) for (int j = 0; j < M.cols(); j++) out[(size_t)i * M.cols() + j] = M(i, j); }
+static void out_vec(const VecX& v, double* out) { if (out) for (int i = 0; i < v.size(); i++) out[i] = v[i]; }
+
+// the accumulate half of EnergyFunctional::solveSystemF (EnergyFunctional.cpp:L853-860)
+void ref_win_accumulate(RefWin* W, int, double* HA, double* bA, double* HL, double* bL, double* Hsc, double* bsc, int* resInA) {
+  MatXX HA_top, HL_top, H_sc;
+  VecX bA_top, bL_top, b_sc;
+  W->ef->accumulateAF_MT(HA_top, bA_top, multiThreading);
+  W->ef->accumulateLF_MT(HL_top, bL_top, multiThreading);
+  W->ef->accumulateSCF_MT(H_sc, b_sc, multiThreading);
+  out_mat(HA_top, HA); out_vec(bA_top, bA); out_mat(HL_top, HL); out_vec(bL_top, bL); out_mat(H_sc, Hsc); out_vec(b_sc, bsc);
+  if (resInA) *resInA = W->ef->resInA;
+}
+
+void ref_win_get_point_outputs(RefWin* W, float* Hdd, float* bd, float* Hcd4, float* HdiF, float* bdSumF, float* step, float* idepth, float* maxRelBaseline) {
+  for (size_t i = 0; i < W->points.size(); i++) {
+    PointHessian* p = W->points[i];
+    EFPoint* e = p->efPoint;
+    if (Hdd) Hdd[i] = e->Hdd_accAF;
+    if (bd) bd[i] = e->bd_accAF;
+    if (Hcd4) for (int k = 0; k < 4; k++) Hcd4[4 * i + k] = e->Hcd_accAF[k];
+    if (HdiF) HdiF[i] = e->HdiF;
+    if (bdSumF) bdSumF[i] = e->bdSumF;
+    if (step) step[i] = p->step;
+    if (idepth) idepth[i] = p->idepth;
+    if (maxRelBaseline) maxRelBaseline[i] = p->maxRelBaseline;
+  }
+}
+
+// EnergyFunctional::solveSystemF (EnergyFunctional.cpp:L841-996), no-GTSAM branch, including resubstituteF_MT
+void ref_win_solve(RefWin* W, int iteration, double lambda, int, double* x_out, double* HFinal, double* bFinal) {
+  W->ef->solveSystemF(iteration, lambda, W->Hcalib);
+  out_vec(W->ef->lastX, x_out);
+  out_mat(W->ef->lastHS, HFinal);
+  out_vec(W->ef->lastbS, bFinal);
+}
+
+double ref_win_calc_LEnergy(RefWin* W) { return W->ef->calcLEnergyF_MT(); }
+double ref_win_calc_MEnergy(RefWin* W) { return W->ef->calcMEnergyF(false); }
+
+// ---- images
+int ref_pyr_levels(int w, int h, const double K[4]) { set_calib_globals(w, h, K); return pyrLevelsUsed; }
+
+// FrameHessian::makeImages (HessianBlocks.cpp:L128-191): out = concatenated levels of [I,dx,dy]; returns floats written
+int64_t ref_make_images(int w, int h, const double K[4], const float* color, float* dIp_out, float* absSqGrad_out) {
+  set_calib_globals(w, h, K);
+  CalibHessian Hc;
+  FrameHessian* fh = new FrameHessian();
+  for (int l = 0; l < PYR_LEVELS; l++) { fh->dIp[l] = 0; fh->absSquaredGrad[l] = 0; }
+  std::vector<float> img(color, color + (size_t)w * h);
+  fh->makeImages(img.data(), &Hc);
+  int64_t n = 0, m = 0;
+  for (int l = 0; l < pyrLevelsUsed; l++)
+    for (int i = 0; i < wG[l] * hG[l]; i++) {
+      for (int k = 0; k < 3; k++) dIp_out[n++] = fh->dIp[l][i][k];
+      if (absSqGrad_out) absSqGrad_out[m++] = fh->absSquaredGrad[l][i];
+    }
+  delete fh;
+  return n;
+}
+
+// ImmaturePoint constructor (ImmaturePoint.cpp:L34-63): colour and gradient weights of the 8-pattern in the host image
+int ref_init_point(const float* dI, int w, int h, const double K[4], float u, float v, float* color8, float* weights8) {
+  set_calib_globals(w, h, K);
+  CalibHessian Hc;
+  FrameHessian* fh = new FrameHessian();
+  for (int l = 0; l < PYR_LEVELS; l++) { fh->dIp[l] = 0; fh->absSquaredGrad[l] = 0; }
+  for (int l = 0; l < pyrLevelsUsed; l++) { fh->dIp[l] = new Eigen::Vector3f[wG[l] * hG[l]]; fh->absSquaredGrad[l] = new float[wG[l] * hG[l]]; }
+  for (int i = 0; i < w * h; i++) fh->dIp[0][i] = Eigen::Vector3f(dI[3 * i], dI[3 * i + 1], dI[3 * i + 2]);
+  fh->dI = fh->dIp[0];
+  ImmaturePoint ipt((int)u, (int)v, fh, 1.f, &Hc);
+  std::memcpy(color8, ipt.color, 32); std::memcpy(weights8, ipt.weights, 32);
+  const int ok = std::isfinite(ipt.energyTH) ? 1 : 0;
+  delete fh;
+  return ok;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// Coarse tracker: the reference's CoarseTracker driven through its own setCoarseTrackingRef / calcRes / calcGSSSE /
+// trackNewestCoarse (FullSystem/CoarseTracker.cpp), visual-only branch.
+// =====================================================================================================================
+namespace {
+struct RefCT {
+  int w, h;
+  CalibHessian* Hcalib = nullptr;
+  dmvio::IMUIntegration imu;
+  CoarseTracker* ct = nullptr;
+  FrameHessian* host = nullptr;     // hosts the points whose residuals target lastRef
+  FrameHessian* lastRef = nullptr;
+  FrameHessian* newFrame = nullptr;
+  std::vector<PointHessian*> points;
+  std::vector<PointFrameResidual*> residuals;
+  SE3 lastPose;                     // pose of the last calcRes (calcGSSSE takes it as an argument but only uses the warped buffers)
+};
+
+FrameHessian* blank_frame(int id) {
+  FrameHessian* fh = new FrameHessian();
+  fh->shell = new FrameShell();
+  fh->shell->id = id;
+  fh->frameID = id; fh->idx = id;
+  fh->ab_exposure = 1.f;
+  fh->worldToCam_evalPT = SE3();
+  Vec10 z = Vec10::Zero();
+  fh->setStateZero(z);
+  fh->setState(z);
+  for (int l = 0; l < PYR_LEVELS; l++) { fh->dIp[l] = 0; fh->absSquaredGrad[l] = 0; }
+  for (int l = 0; l < pyrLevelsUsed; l++) {
+    fh->dIp[l] = new Eigen::Vector3f[wG[l] * hG[l]];
+    fh->absSquaredGrad[l] = new float[wG[l] * hG[l]];
+    for (int i = 0; i < wG[l] * hG[l]; i++) { fh->dIp[l][i] = Eigen::Vector3f(0, 0, 0); fh->absSquaredGrad[l][i] = 0; }
+  }
+  fh->dI = fh->dIp[0];
+  return fh;
+}
+void load_pyramid(FrameHessian* fh, const float* concat) {
+  size_t off = 0;
+  for (int l = 0; l < pyrLevelsUsed; l++)
+    for (int i = 0; i < wG[l] * hG[l]; i++, off += 3) fh->dIp[l][i] = Eigen::Vector3f(concat[off], concat[off + 1], concat[off + 2]);
+}
+void free_frame(FrameHessian* fh) {
+  if (!fh) return;
+  if (fh->efFrame) { delete fh->efFrame; fh->efFrame = 0; }
+  FrameShell* s = fh->shell;
+  delete fh;
+  delete s;
+}
+}  // namespace
+
+extern "C" {
+
+RefCT* ref_ct_create(int w, int h, const double K[4]) {
+  set_calib_globals(w, h, K);
+  RefCT* C = new RefCT();
+  C->w = w; C->h = h;
+  C->Hcalib = new CalibHessian();
+  C->ct = new CoarseTracker(w, h, C->imu);
+  C->ct->makeK(C->Hcalib);
+  C->host = blank_frame(0);
+  C->lastRef = blank_frame(1);
+  C->newFrame = blank_frame(2);
+  C->host->efFrame = new EFFrame(C->host);
+  C->lastRef->efFrame = new EFFrame(C->lastRef);
+  return C;
+}
+
+void ref_ct_destroy(RefCT* C) {
+  if (!C) return;
+  for (PointFrameResidual* r : C->residuals) { delete r->efResidual; r->efResidual = 0; }
+  for (PointHessian* p : C->points) { delete p->efPoint; p->efPoint = 0; }
+  free_frame(C->host);  // deletes its pointHessians and their residuals
+  free_frame(C->lastRef);
+  free_frame(C->newFrame);
+  delete C->ct;
+  delete C->Hcalib;
+  delete C;
+}
+
+int ref_ct_levels(RefCT*) { return pyrLevelsUsed; }
+
+// setCoarseTrackingRef (CoarseTracker.cpp:L524-538) -> makeCoarseDepthL0 (L138-295) from per-residual (Ku, Kv, new_idepth) and per-point HdiF
+int ref_ct_make_coarse_depth(RefCT* C, int n, const float* Ku, const float* Kv, const float* new_idepth, const float* HdiF, const float* ref_dIp_concat) {
+  load_pyramid(C->lastRef, ref_dIp_concat);
+  for (int i = 0; i < n; i++) {
+    ImmaturePoint ipt(8, 8, C->host, 1.f, C->Hcalib);
+    ipt.idepth_min = ipt.idepth_max = 1.f;
+    PointHessian* ph = new PointHessian(&ipt, C->Hcalib);
+    ph->setPointStatus(PointHessian::ACTIVE);
+    C->host->pointHessians.push_back(ph);
+    ph->efPoint = new EFPoint(ph, C->host->efFrame);
+    ph->efPoint->HdiF = HdiF[i];
+    PointFrameResidual* r = new PointFrameResidual(ph, C->host, C->lastRef);
+    r->efResidual = new EFResidual(r, ph->efPoint, C->host->efFrame, C->lastRef->efFrame);
+    r->efResidual->isActiveAndIsGoodNEW = true;
+    r->centerProjectedTo = Vec3f(Ku[i], Kv[i], new_idepth[i]);
+    r->setState(ResState::IN);
+    ph->residuals.push_back(r);
+    ph->lastResiduals[0] = std::pair<PointFrameResidual*, ResState>(r, ResState::IN);
+    ph->lastResiduals[1] = std::pair<PointFrameResidual*, ResState>(0, ResState::OOB);
+    C->points.push_back(ph);
+    C->residuals.push_back(r);
+  }
+  std::vector<FrameHessian*> fhs;
+  fhs.push_back(C->host);
+  fhs.push_back(C->lastRef);
+  C->ct->setCoarseTrackingRef(fhs);
+  return C->ct->pc_n[0];
+}
+
+int ref_ct_get_ref_points(RefCT* C, int lvl, float* u, float* v, float* idepth, float* color) {
+  const int n = C->ct->pc_n[lvl];
+  for (int i = 0; i < n; i++) {
+    if (u) u[i] = C->ct->pc_u[lvl][i];
+    if (v) v[i] = C->ct->pc_v[lvl][i];
+    if (idepth) idepth[i] = C->ct->pc_idepth[lvl][i];
+    if (color) color[i] = C->ct->pc_color[lvl][i];
+  }
+  return n;
+}
+
+void ref_ct_set_new_frame(RefCT* C, const float* dIp_concat, float ref_exposure, float new_exposure, double ref_a, double ref_b) {
+  load_pyramid(C->newFrame, dIp_concat);
+  C->newFrame->ab_exposure = new_exposure;
+  C->lastRef->ab_exposure = ref_exposure;
+  C->ct->lastRef_aff_g2l = AffLight(ref_a, ref_b);
+  C->ct->newFrame = C->newFrame;
+}
+
+void ref_ct_get_K(RefCT* C, int lvl, float* k4, int* wh) {
+  k4[0] = C->ct->fx[lvl]; k4[1] = C->ct->fy[lvl]; k4[2] = C->ct->cx[lvl]; k4[3] = C->ct->cy[lvl];
+  wh[0] = C->ct->w[lvl]; wh[1] = C->ct->h[lvl];
+}
+
+static SE3 pose_from(const double R[9], const double t[3]) {
+  Mat33 Rm; Vec3 tv;
+  for (int i = 0; i < 3; i++) { tv[i] = t[i]; for (int j = 0; j < 3; j++) Rm(i, j) = R[3 * i + j]; }
+  return SE3(Rm, tv);
+}
+
+void ref_ct_calc_res(RefCT* C, int lvl, const double R[9], const double t[3], double a, double b, float cutoffTH, double out6[6]) {
+  C->lastPose = pose_from(R, t);
+  Vec6 r = C->ct->calcRes(lvl, C->lastPose, AffLight(a, b), cutoffTH);
+  for (int i = 0; i < 6; i++) out6[i] = r[i];
+}
+
+int ref_ct_get_warped(RefCT* C, float* buf8xn) {
+  const int n = C->ct->buf_warped_n;
+  if (buf8xn) {
+    const float* src[8] = {C->ct->buf_warped_idepth, C->ct->buf_warped_u, C->ct->buf_warped_v, C->ct->buf_warped_dx, C->ct->buf_warped_dy,
+                           C->ct->buf_warped_residual, C->ct->buf_warped_weight, C->ct->buf_warped_refColor};
+    for (int k = 0; k < 8; k++) std::memcpy(buf8xn + (size_t)k * n, src[k], sizeof(float) * n);
+  }
+  return n;
+}
+
+void ref_ct_calc_gs(RefCT* C, int lvl, double a, double b, int, double H64[64], double b8[8]) {
+  Mat88 H; Vec8 bb;
+  C->ct->calcGSSSE(lvl, H, bb, C->lastPose, AffLight(a, b));
+  for (int i = 0; i < 8; i++) { b8[i] = bb[i]; for (int j = 0; j < 8; j++) H64[i * 8 + j] = H(i, j); }
+}
+
+int ref_ct_track(RefCT* C, double R[9], double t[3], double* a, double* b, int coarsestLvl, const double minRes[5], int, double lastRes[5],
+                 double flow3[3], int* iterations) {
+  SE3 T = pose_from(R, t);
+  AffLight aff(*a, *b);
+  Vec5 mr;
+  for (int i = 0; i < 5; i++) mr[i] = minRes[i];
+  const bool good = C->ct->trackNewestCoarse(C->newFrame, T, aff, coarsestLvl, mr, 0);
+  for (int i = 0; i < 3; i++) { t[i] = T.translation()[i]; for (int j = 0; j < 3; j++) R[3 * i + j] = T.rotationMatrix()(i, j); }
+  *a = aff.a; *b = aff.b;
+  for (int i = 0; i < 5; i++) lastRes[i] = C->ct->lastResiduals[i];
+  for (int i = 0; i < 3; i++) flow3[i] = C->ct->lastFlowIndicators[i];
+  if (iterations) *iterations = -1;  // not exposed by the reference
+  return good ? 1 : 0;
+}
+
+}  // extern "C"
