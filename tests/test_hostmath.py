@@ -7,7 +7,7 @@ def test_precalc_adjoints_match_oracle(orc, synth):
     W = synth.make_window(nf=5, npts=50, seed=3)
     ow = orc.Window(W)
     pc_o, pc_p = ow.precalc(), hm.precalc_table(W)
-    np.testing.assert_allclose(pc_p, pc_o, rtol=2e-6, atol=1e-4)  # fp32 K*R*K^-1 cancels values ~fx
+    np.testing.assert_allclose(pc_p, pc_o, rtol=0, atol=1e-12)  # same float32 operation order as the reference (sequential products, cofactor inverse)
     adH_o, adT_o = ow.adjoints()
     adH_p, adT_p = hm.adjoints(W)
     np.testing.assert_allclose(adH_p, adH_o, rtol=1e-12, atol=1e-12)
@@ -22,4 +22,5 @@ def test_precalc_adjoints_match_oracle(orc, synth):
     # same dense solve
     x_o, _, _ = ow.solve(0, 1e-5, 1)
     x_p = hm.solve_reduced(a["HA"], a["bA"], a["Hsc"], a["bsc"], HL, bL, lam=1e-5)
-    assert np.linalg.norm(x_p - x_o) <= 1e-5 * np.linalg.norm(x_o)  # LU vs LDLT on a system with condition ~1e12
+    # LU vs LDLT on a 44x44 system with condition ~1e12 (50 points only): cond * eps(fp64) ~ 1e-4 is the attainable agreement
+    assert np.linalg.norm(x_p - x_o) <= 1e-3 * np.linalg.norm(x_o)
