@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY — see orc_ba.h.  CPU restatement of the BA hot path (parity unpinned).
+// TEST INFRASTRUCTURE ONLY — see orc_ba.h.  CPU restatement of the BA hot path; pinned bit-exact against the compiled reference (oracle/_ref, tests/test_ref_pin.py).
 #include "orc_ba.h"
 #include "orc_threads.h"
 #include <algorithm>

@@ -1,9 +1,11 @@
 // TEST INFRASTRUCTURE ONLY — CPU oracle (restatement) of DM-VIO's sliding-window photometric
-// bundle-adjustment hot path.  PARITY UNPINNED: the reference has no tests/golden vectors on this
-// path and cannot be compiled in this image (Eigen3/Boost/GTSAM absent), so this restatement is
-// validated by finite differences, closed-form cases and invariants (tests/test_oracle_*.py) only.
+// bundle-adjustment hot path.  The reference has no tests/golden vectors on this path and its build
+// (Eigen3/Boost/GTSAM) cannot run in this image; this restatement is validated by finite differences, closed-form cases
+// and invariants (tests/test_oracle_*.py).
 //
 // Every function cites the reference file:line (relative to /root/reference/src/dso) it follows.
+// PINNED: bit-exact against the reference's own translation units compiled into oracle/_ref (oracle/ref_build.sh,
+// oracle/ref_harness.cpp, tests/test_ref_pin.py; DESIGN.md §2 lists the substituted third-party headers).
 #pragma once
 #include "orc_math.h"
 #include <cstdint>

@@ -66,6 +66,8 @@ def lib():
         L.ref_win_accumulate.argtypes = [vp, C.c_int, f64p, f64p, f64p, f64p, f64p, f64p, C.POINTER(C.c_int)]
         L.ref_win_get_point_outputs.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p]
         L.ref_win_solve.argtypes = [vp, C.c_int, C.c_double, C.c_int, f64p, f64p, f64p]
+        L.ref_win_hot_iteration.restype = C.c_double
+        L.ref_win_hot_iteration.argtypes = [vp, f64p, C.c_int]
         L.ref_win_calc_LEnergy.restype = C.c_double
         L.ref_win_calc_LEnergy.argtypes = [vp]
         L.ref_win_calc_MEnergy.restype = C.c_double

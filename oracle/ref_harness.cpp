@@ -329,6 +329,59 @@ void ref_win_solve(RefWin* W, int iteration, double lambda, int, double* x_out, 
   out_vec(W->ef->lastbS, bFinal);
 }
 
+// One GN iteration of the hot path WITHOUT the dense solve, as timed by bench.py (same sequence as orc_win_hot_iteration):
+// backup, accumulateAF/LF/SCF (+stitch), resubstituteF_MT(x), doStepFromBackup (frames, points, setPrecalcValues), linearizeAll, applyRes,
+// restore.  The pieces that live in FullSystem (not compiled) are restated with the reference's own setters; linearize / applyRes run on
+// the reference's IndexThreadReduce pool with its split rules (static n/NUM_THREADS for linearize, chunks of 50 for applyRes).
+double ref_win_hot_iteration(RefWin* W, const double* x, int) {
+  EnergyFunctional* ef = W->ef;
+  const int N = W->nf * 8 + CPARS;
+  // FullSystem::backupState (FullSystemOptimize.cpp:L322-370)
+  W->Hcalib->value_backup = W->Hcalib->value;
+  for (FrameHessian* fh : W->frames) fh->state_backup = fh->get_state();
+  for (PointHessian* ph : W->points) ph->idepth_backup = ph->idepth;
+  MatXX HA, HL, Hsc;
+  VecX bA, bL, bsc;
+  ef->accumulateAF_MT(HA, bA, multiThreading);
+  ef->accumulateLF_MT(HL, bL, multiThreading);
+  ef->accumulateSCF_MT(Hsc, bsc, multiThreading);
+  VecX xv(N);
+  for (int i = 0; i < N; i++) xv[i] = x[i];
+  ef->resubstituteF_MT(xv, W->Hcalib, multiThreading);
+  // FullSystem::doStepFromBackup (L224-317), stepfac = 1
+  W->Hcalib->setValue(W->Hcalib->value_backup + W->Hcalib->step);
+  for (FrameHessian* fh : W->frames) {
+    fh->setState(fh->state_backup + fh->step);
+    for (PointHessian* ph : fh->pointHessians) { ph->setIdepth(ph->idepth_backup + ph->step); ph->setIdepthZero(ph->idepth_backup + ph->step); }
+  }
+  EFDeltaValid = false;
+  for (FrameHessian* fh : W->frames)
+    for (unsigned int i = 0; i < W->frames.size(); i++) fh->targetPrecalc[i].set(fh, W->frames[i], W->Hcalib);
+  ef->setDeltaF(W->Hcalib);
+  // FullSystem::linearizeAll(false) (L150-172) + applyRes_Reductor (L90-94)
+  double E = 0;
+  const int n = (int)W->residuals.size();
+  if (multiThreading) {
+    ef->red->reduce([W](int a, int b, Vec10* stats, int) { for (int k = a; k < b; k++) (*stats)[0] += W->residuals[k]->linearize(W->Hcalib); }, 0, n, 0);
+    E = ef->red->stats[0];
+    ef->red->reduce([W](int a, int b, Vec10*, int) { for (int k = a; k < b; k++) W->residuals[k]->applyRes(true); }, 0, n, 50);
+  } else {
+    for (PointFrameResidual* r : W->residuals) E += r->linearize(W->Hcalib);
+    for (PointFrameResidual* r : W->residuals) r->applyRes(true);
+  }
+  // FullSystem::loadSateBackup (L371-388)
+  W->Hcalib->setValue(W->Hcalib->value_backup);
+  for (FrameHessian* fh : W->frames) {
+    fh->setState(fh->state_backup);
+    for (PointHessian* ph : fh->pointHessians) { ph->setIdepth(ph->idepth_backup); ph->setIdepthZero(ph->idepth_backup); }
+  }
+  EFDeltaValid = false;
+  for (FrameHessian* fh : W->frames)
+    for (unsigned int i = 0; i < W->frames.size(); i++) fh->targetPrecalc[i].set(fh, W->frames[i], W->Hcalib);
+  ef->setDeltaF(W->Hcalib);
+  return E;
+}
+
 double ref_win_calc_LEnergy(RefWin* W) { return W->ef->calcLEnergyF_MT(); }
 double ref_win_calc_MEnergy(RefWin* W) { return W->ef->calcMEnergyF(false); }
 
