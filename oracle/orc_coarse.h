@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY — CPU oracle (restatement) of DM-VIO's coarse direct image alignment
 // (FullSystem/CoarseTracker.cpp) and of the image pyramid construction (FullSystem/HessianBlocks.cpp
-// makeImages).  PARITY UNPINNED (see orc_ba.h).
+// makeImages).  Pinned bit-exact against the compiled reference (see orc_ba.h, tests/test_ref_pin.py).
 #pragma once
 #include "orc_ba.h"
 
