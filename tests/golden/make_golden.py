@@ -106,13 +106,17 @@ def main():
     ct.set_new_frame(T["pyr_new"])
     d = dict(in_wh=np.array([T["w"], T["h"]], np.int32), in_K=T["K"], in_Ku=T["Ku"], in_Kv=T["Kv"], in_new_idepth=T["new_idepth"], in_HdiF=T["HdiF"],
              in_img_ref=T["img_ref"], in_img_new=T["img_new"], levels=np.int32(ct.levels))
+    # a generic pose near the truth (not the identity: integer reference pixels would sit exactly on the bounds tests)
+    R, t = synth.se3_mul(*synth.se3_exp(np.array([0.003, -0.002, 0.001, 0.001, -0.001, 0.001])), T["R_true"], T["t_true"])
+    a, b = T["a_new"] + 0.01, T["b_new"] - 0.3
+    d.update(pose_R=R, pose_t=t, pose_ab=np.array([a, b]))
     for l in range(ct.levels):
         rp = ct.ref_points(l)
         for k in ("u", "v", "idepth", "color"):
             d[f"ref{l}_{k}"] = rp[k]
-        d[f"res6_{l}"] = ct.calc_res(l, np.eye(3), np.zeros(3), 0.0, 0.0, 20.0)
-        H, b = ct.calc_gs(l, 0.0, 0.0, 1)
-        d[f"H_{l}"], d[f"b_{l}"] = H, b
+        d[f"res6_{l}"] = ct.calc_res(l, R, t, a, b, 20.0)
+        H, bb = ct.calc_gs(l, a, b, 1)
+        d[f"H_{l}"], d[f"b_{l}"] = H, bb
     r = ct.track(np.eye(3), np.zeros(3), 0.0, 0.0)
     d.update(track_R=r["R"], track_t=r["t"], track_ab=np.array([r["a"], r["b"]]), track_lastRes=r["lastResiduals"], track_good=np.int32(r["good"]),
              track_iterations=np.int32(r["iterations"]))

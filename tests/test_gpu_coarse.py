@@ -36,9 +36,10 @@ def _setup(capi, orc, synth, levels, seed=4321):
 
 
 def _pose_args(synth, oct_, lvl, R, t, a, b):
+    import dmvio_b200.hostmath as hm
     k, _ = oct_.K(lvl)
-    Ki = np.array([[1 / k[0], 0, -k[2] / k[0]], [0, 1 / k[1], -k[3] / k[1]], [0, 0, 1]], np.float32)
-    RKi = R.astype(np.float32) @ Ki
+    Ki = hm.inv3_cofactor_f32(np.array([[k[0], 0, k[2]], [0, k[1], k[3]], [0, 0, 1]], np.float32))  # K[lvl].inverse() as the reference rounds it
+    RKi = hm.mm3_f32(R.astype(np.float32), Ki)
     affLL = np.array([np.exp(a), b], np.float32)  # ref aff_g2l = (0,0), exposures 1
     return RKi, t.astype(np.float32), affLL
 
