@@ -15,7 +15,6 @@ void launch_resub_kernel(const BAWinDev& W, const BAIter& it, int apply, double*
 void launch_repack(const float* src, float4* dst, int n, cudaStream_t s);
 void launch_make_dI(const float* img, float4* dst, int w, int h, cudaStream_t s);
 void launch_l2_flush(float4* buf, size_t n, cudaStream_t s);
-void launch_xchg_kernel(const XchgDev& X, cudaStream_t s);
 }  // namespace dmv
 
 using namespace dmv;
@@ -84,33 +83,18 @@ struct dmv_ba {
   // NCCL
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
-  // peer-memory exchange (ba_xchg.cu)
+  // peer-memory exchange (fused into ba_stitch_kernel)
   void* xchg_own = nullptr;                 // this rank's inbox (cudaMalloc, exported through CUDA IPC)
   void* xchg_map[XCHG_MAXR] = {nullptr};    // every rank's inbox as mapped here ([rank] == xchg_own)
   int xchg_pitch = 0;
   bool xchg_on = false;
-  unsigned long long xchg_seq = 0;
+  unsigned int xchg_seq = 0;
 };
 
-// all-reduce of the stitched result blob across ranks, on the handle's stream, behind the stitch kernel
+// all-reduce of the stitched result blob across ranks: fused into the stitch kernel when the peer-memory exchange is on
+// (fill_descriptor/next_exchange hand it the inbox table), otherwise one ncclAllReduce behind it
 static int enqueue_exchange(dmv_ba* b) {
-  if (b->xchg_on) {
-    XchgDev X;
-    std::memset(&X, 0, sizeof(X));
-    X.nranks = b->nranks; X.rank = b->rank;
-    X.nvec = result_doubles(b->N, b->ntiles) / 2;
-    X.pitch = b->xchg_pitch;
-    X.seq = ++b->xchg_seq;
-    for (int r = 0; r < b->nranks; r++) {
-      X.flags[r] = reinterpret_cast<unsigned long long*>(b->xchg_map[r]);
-      X.inbox[r] = reinterpret_cast<double2*>(reinterpret_cast<char*>(b->xchg_map[r]) + XCHG_FLAG_BYTES);
-    }
-    X.buf = reinterpret_cast<double2*>(b->d_result[b->tent]);
-    launch_xchg_kernel(X, b->stream);
-    b->launches += 1;
-    if (cudaGetLastError() != cudaSuccess) return dmv::set_error(DMV_ERR_CUDA, "ba_xchg_kernel launch failed");
-    return DMV_OK;
-  }
+  if (b->xchg_on) return DMV_OK;
   if (b->nccl_comm) return dmv::nccl_allreduce_double(b->nccl_comm, b->d_result[b->tent], result_doubles(b->N, b->ntiles), b->stream);
   return DMV_OK;
 }
@@ -153,7 +137,20 @@ static int fill_descriptor(dmv_ba* b) {
   W.ticket = b->d_ticket;
   W.stage = b->d_stage;
   W.result = b->d_result[t];
+  W.xc.nranks = b->xchg_on ? b->nranks : 1;
+  W.xc.rank = b->rank;
+  W.xc.pitch = b->xchg_pitch;
+  W.xc.seq = 0;
+  for (int r = 0; r < XCHG_MAXR; r++) W.xc.inbox[r] = reinterpret_cast<uint4*>(b->xchg_map[r]);
   return DMV_OK;
+}
+
+// every stitch launch of a sharded handle is one exchange: number it (all ranks launch the same sequence of stitches)
+static void next_exchange(dmv_ba* b) {
+  if (!b->xchg_on) return;
+  b->xchg_seq++;
+  if (b->xchg_seq == 0) b->xchg_seq = 2;  // 0 is the "empty" flag; keep the parity sequence alternating after a wrap
+  b->h_up->win.xc.seq = b->xchg_seq;
 }
 
 extern "C" {
@@ -442,6 +439,7 @@ int dmv_ba_set_state(dmv_ba* b, const dmv_ba_state* st) {
 static int enqueue_linearize(dmv_ba* b, bool with_resub) {
   (void)with_resub;  // the resubstitute + step prologue is fused into the point kernel (it.have_x)
   fill_descriptor(b);
+  next_exchange(b);
   const HostUpload& U = *b->h_up;
   if (b->timing) CK(cudaEventRecord(b->ev[0], b->stream));
   launch_point_kernel(U.win, U.it, b->stream);   // residuals + Hessian blocks + Schur Gram -> fp64 accumulators
@@ -708,6 +706,7 @@ int dmv_ba_bench_device(dmv_ba* b, const double* x, int iters, int flush_l2, flo
   for (int i = 0; i < iters; i++) {
     if (flush_l2) launch_l2_flush(b->d_flush, b->flush_n, b->stream);
     fill_descriptor(b);
+    next_exchange(b);
     const HostUpload& U = *b->h_up;
     CK(cudaEventRecord(e[3 * i], b->stream));
     launch_point_kernel(U.win, U.it, b->stream);
@@ -757,9 +756,8 @@ extern "C" int dmv_ba_p2p_export(dmv_ba* b, void* ipc_handle64) {
   CK(cudaSetDevice(b->device));
   if (!b->xchg_own) {
     const int maxT = (8 * MAXF + 4 + 1 + 3) / 4, maxTiles = maxT * (maxT + 1) / 2;
-    b->xchg_pitch = (result_doubles(8 * MAXF + 4, maxTiles) / 2 + 7) & ~7;
-    if ((b->xchg_pitch + XCHG_CTAS - 1) / XCHG_CTAS > XCHG_THREADS) return set_error(DMV_ERR_INVALID, "result blob too large for the exchange kernel");
-    const size_t bytes = XCHG_FLAG_BYTES + (size_t)2 * XCHG_MAXR * b->xchg_pitch * sizeof(double2);
+    b->xchg_pitch = (result_doubles(8 * MAXF + 4, maxTiles) + 7) & ~7;
+    const size_t bytes = (size_t)2 * XCHG_MAXR * b->xchg_pitch * sizeof(uint4);
     CK(cudaMalloc(&b->xchg_own, bytes));
     CK(cudaMemset(b->xchg_own, 0, bytes));
     CK(cudaDeviceSynchronize());

@@ -34,6 +34,15 @@ struct BAAdj {
   double adTdiag[MAXF * MAXF][8];
 };
 
+// peer-memory exchange fused into ba_stitch_kernel.  Inbox of one rank (cudaMalloc + CUDA IPC):
+// [2 parities][XCHG_MAXR source ranks][pitch] 16-byte packets {value.lo, seq, value.hi, seq}  ("LL" packets: flag travels with the data)
+constexpr int XCHG_MAXR = 8;
+struct BAXchg {
+  int nranks, rank, pitch;            // pitch = packets per (parity, source) slot >= result_doubles
+  unsigned int seq;                   // exchange number 1, 2, ... (identical on every rank); 0 never appears as a flag of a live packet
+  uint4* inbox[XCHG_MAXR];            // rank r's inbox as mapped in THIS process ([rank] = own)
+};
+
 struct BAWinDev {
   int nf, npts, nchunks, w, h, N, NW, T, ntiles, mp, P;  // mp = capacity (row pitch of the [target][point] slot arrays)
   float huberTH, outlierTHSum;
@@ -74,17 +83,7 @@ struct BAWinDev {
   unsigned int* ticket;      // [0] CTA completion counter, [1+h] per-host counters (last CTA of a host / overall stitches); self-resetting
   double* stage;             // scratch of the stitch: per pair B|G|GA (272 doubles) + per host 20 calibration sums
   double* result;            // H_top N*N | b_top N | Schur tiles ntiles*16 | ACC_MISC tail
-};
-
-// peer-memory exchange (ba_xchg.cu): inbox of one rank = flags [2][XCHG_MAXR][XCHG_CTAS] u64, then data [2][XCHG_MAXR][pitch] double2
-constexpr int XCHG_MAXR = 8, XCHG_CTAS = 8, XCHG_THREADS = 512;
-constexpr size_t XCHG_FLAG_BYTES = 2 * XCHG_MAXR * XCHG_CTAS * sizeof(unsigned long long);
-struct XchgDev {
-  int nranks, rank, nvec, pitch;      // nvec = 16-byte vectors in the result blob, pitch = slot stride in vectors
-  unsigned long long seq;             // exchange number, 1, 2, ... (identical on every rank)
-  double2* inbox[XCHG_MAXR];          // data area of rank r's inbox as mapped in THIS process
-  unsigned long long* flags[XCHG_MAXR];
-  double2* buf;                       // local stitched result, all-reduced in place
+  BAXchg xc;                 // nranks <= 1: no exchange
 };
 
 // result blob: H_top N*N | b_top N | raw Schur Gram tiles ntiles*16 | ACC_MISC counters

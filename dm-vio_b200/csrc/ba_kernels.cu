@@ -46,6 +46,53 @@ struct alignas(16) StitchSmem {
   double GA[MAXF][64];            // (adHost P) adHost^T for the pairs hosted by a
 };
 
+// ---- exchange of the stitched system between ranks (sharded BA): "LL" packets over NVLink peer memory.
+// Every entry of the result blob has exactly one producing CTA (the same CTA index on every rank).  After a CTA has written
+// its entries it (1) pushes each of them as a 16-byte packet {lo, seq, hi, seq} into slot [parity][my rank][entry] of every
+// peer's inbox (st.volatile.v4: each 8-byte half carries its own flag, so no fence and no separate flag round trip), then
+// (2) spins on its OWN inbox until the nranks-1 packets of an entry carry this exchange's sequence number, adds the values
+// in RANK ORDER (bit-identical sums on every rank) and overwrites the local entry.  Double-buffered by parity: a peer can be
+// at most one exchange ahead (it needs my packets of exchange k+1, which my stream issues only after this kernel retired).
+__device__ __forceinline__ void xchg_push(const BAXchg& X, int idx, double v) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  const uint4 pk = make_uint4((unsigned)(u & 0xffffffffull), X.seq, (unsigned)(u >> 32), X.seq);
+  const size_t off = (size_t)(((X.seq & 1u) * XCHG_MAXR + X.rank)) * X.pitch + idx;
+#pragma unroll 1
+  for (int k = 1; k < X.nranks; k++) {
+    const int r = (X.rank + k) % X.nranks;  // start with the neighbour: spreads the NVSwitch ports
+    uint4* dst = X.inbox[r] + off;
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+  }
+}
+__device__ __forceinline__ double xchg_pull_sum(const BAXchg& X, int idx, double mine) {
+  double s = 0.0;
+  for (int r = 0; r < X.nranks; r++) {
+    if (r == X.rank) { s += mine; continue; }
+    const uint4* src = X.inbox[X.rank] + (size_t)(((X.seq & 1u) * XCHG_MAXR + r)) * X.pitch + idx;
+    uint4 pk;
+    do {
+      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "l"(src) : "memory");
+    } while (pk.y != X.seq || pk.w != X.seq);
+    s += __longlong_as_double((long long)(((unsigned long long)pk.z << 32) | pk.x));
+  }
+  return s;
+}
+// entry e (0 <= e < count) of the list of result-blob indices produced by stitch CTA a
+__device__ __forceinline__ int xchg_owned_count(const BAWinDev& W, int a) {
+  return (a < W.nf) ? 8 * (W.N + 1) + 32 : 20 + W.ntiles * 16 + ACC_MISC;
+}
+__device__ __forceinline__ int xchg_owned_index(const BAWinDev& W, int a, int e) {
+  const int N = W.N;
+  if (a < W.nf) {
+    const int r0 = 4 + 8 * a;
+    if (e < 8 * (N + 1)) { const int ia = e / (N + 1), J = e - ia * (N + 1); return (J == N) ? N * N + r0 + ia : (r0 + ia) * N + J; }
+    const int m = e - 8 * (N + 1);  // mirrored calibration columns H[J][r0+ia], J < 4
+    return (m >> 3) * N + r0 + (m & 7);
+  }
+  if (e < 20) { const int i = e / 5, j = e - i * 5; return (j < 4) ? i * N + j : N * N + i; }
+  return N * N + N + (e - 20);
+}
+
 __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_constant__ BAWinDev W) {
   extern __shared__ __align__(16) unsigned char st_smem[];
   StitchSmem& Q = *reinterpret_cast<StitchSmem*>(st_smem);
@@ -89,8 +136,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
       for (int pr = 0; pr < nf * nf; pr++) v += __ldcg(TS + (size_t)pr * TOP_PART + rr * TOP_COLS + cc);
       if (j < 4) R[(size_t)i * N + j] = v; else R[(size_t)N * N + i] = v;
     }
-    return;
-  }
+  } else {
   for (int e = tid; e < nf * (TOP_PART / 2); e += ST_THREADS) {
     const int t = e / (TOP_PART / 2), k = (e - t * (TOP_PART / 2)) * 2;
     cp_async16(&Q.raw[0][t][k], TS + (size_t)(a * nf + t) * TOP_PART + k);
@@ -142,7 +188,21 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
     }
     R[(size_t)(r0 + ia) * N + J] = v;
   }
+  }  // a < nf
   STAMP_ST(4);
+  if (W.xc.nranks > 1) {
+    __syncthreads();  // every entry of this CTA is in R (same-CTA global writes are visible after the barrier)
+    const int cnt = xchg_owned_count(W, a);
+    for (int e = tid; e < cnt; e += ST_THREADS) {
+      const int idx = xchg_owned_index(W, a, e);
+      xchg_push(W.xc, idx, __ldcg(R + idx));
+    }
+    for (int e = tid; e < cnt; e += ST_THREADS) {
+      const int idx = xchg_owned_index(W, a, e);
+      R[idx] = xchg_pull_sum(W.xc, idx, __ldcg(R + idx));
+    }
+    STAMP_ST(5);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -158,9 +158,11 @@ int dmv_ba_comm_init(dmv_ba* ba, int nranks, int rank, const void* nccl_unique_i
 
 /* The same exchange without NCCL, over NVLink/NVSwitch peer memory (CUDA IPC, one process per GPU of one node, <= 8 ranks):
  * every rank exports its inbox (64-byte cudaIpcMemHandle_t), the caller all-gathers the handles (any transport: MPI,
- * torch.distributed, a file) and every rank imports all of them.  From then on the all-reduce is one kernel chained behind the
- * stitch (push to all peers, flag, wait, sum in rank order => bit-identical H,b on all ranks).  Takes precedence over a NCCL
- * communicator if both are set.  No reference counterpart (the reference is single-node CPU). */
+ * torch.distributed, a file) and every rank imports all of them.  From then on the all-reduce is FUSED INTO THE STITCH KERNEL:
+ * each stitch CTA pushes the entries it produced to every peer as 16-byte flag-carrying packets, waits for the peers' packets of
+ * the same entries and adds them in rank order (bit-identical H,b on all ranks; no extra launch, no fence round trip).
+ * Takes precedence over a NCCL communicator if both are set; nranks = 1 in dmv_ba_p2p_import switches it off again.
+ * No reference counterpart (the reference is single-node CPU). */
 int dmv_ba_p2p_export(dmv_ba* ba, void* ipc_handle64);
 int dmv_ba_p2p_import(dmv_ba* ba, int nranks, int rank, const void* ipc_handles /* nranks*64 bytes, rank order */);
 
