@@ -348,7 +348,7 @@ def main():
             "ms_per_step": ms_iter, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"sliding window {NF} KF / {NPTS * world} pts / {W_}x{H_}, pattern 8, {nres_total} point-residuals "
                                    f"({nres_local}/GPU), one GN iteration of the hot path per step (host solve excluded)",
-                       "parallelism": f"points sharded over {world} GPU(s), images replicated" + ({"p2p": ", all-reduce of H,b per step by ba_xchg_kernel over NVLink peer memory", "nccl": ", NCCL all-reduce of H,b per step", "none": ""}[exchange]),
+                       "parallelism": f"points sharded over {world} GPU(s), images replicated" + ({"p2p": ", all-reduce of H,b per step fused into ba_stitch_kernel (LL packets over NVLink peer memory, CUDA IPC)", "nccl": ", NCCL all-reduce of H,b per step", "none": ""}[exchange]),
                        "l2": "L2 scrubbed (256 MiB write) between timed steps of `value`", "chunk_points": args.chunk or 16,
                        "n_in": r0["n_in"], "n_oob": r0["n_oob"], "n_outlier": r0["n_outlier"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -73,6 +73,7 @@ struct dmv_ba {
   std::vector<int> res_slot;   // residual index -> slot (t*mp+p)
   std::vector<uint8_t> h_st_in;
   std::vector<float> h_en_in;
+  bool no_zero_copy = false;   // DMV_NO_ZERO_COPY=1: D2H copy node instead of in-kernel writes to the pinned result (A/B experiment)
   bool timing = false;         // record CUDA events around the kernels of every call (dmv_ba_set_timing)
   int iter2 = 0;
   int dbg = 0;                 // DMV_DBG experiment mask (see ba_device.cuh); never set in production
@@ -137,6 +138,7 @@ static int fill_descriptor(dmv_ba* b) {
   W.ticket = b->d_ticket;
   W.stage = b->d_stage;
   W.result = b->d_result[t];
+  W.result_host = nullptr;
   W.xc.nranks = b->xchg_on ? b->nranks : 1;
   W.xc.rank = b->rank;
   W.xc.pitch = b->xchg_pitch;
@@ -179,6 +181,7 @@ int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
   dmv_ba_default_params(&b->prm);
   if (const char* e = getenv("DMV_DBG")) b->dbg = atoi(e);
   if (const char* e = getenv("DMV_ITER2")) b->iter2 = atoi(e);
+  if (const char* e = getenv("DMV_NO_ZERO_COPY")) b->no_zero_copy = atoi(e) != 0;
   b->P = (cfg->chunk_points == 8 || cfg->chunk_points == 16 || cfg->chunk_points == 32) ? cfg->chunk_points : 16;
   b->mp = (cfg->max_points + 31) & ~31;
   const int MF = MAXF, mp = b->mp;
@@ -440,6 +443,9 @@ static int enqueue_linearize(dmv_ba* b, bool with_resub) {
   (void)with_resub;  // the resubstitute + step prologue is fused into the point kernel (it.have_x)
   fill_descriptor(b);
   next_exchange(b);
+  // the stitch kernel writes the final blob into the pinned host mirror itself, unless a NCCL all-reduce still follows it
+  const bool zero_copy = !(b->nccl_comm && !b->xchg_on) && !b->no_zero_copy;
+  if (zero_copy) b->h_up->win.result_host = b->h_result[b->tent];
   const HostUpload& U = *b->h_up;
   if (b->timing) CK(cudaEventRecord(b->ev[0], b->stream));
   launch_point_kernel(U.win, U.it, b->stream);   // residuals + Hessian blocks + Schur Gram -> fp64 accumulators
@@ -453,7 +459,8 @@ static int enqueue_linearize(dmv_ba* b, bool with_resub) {
     int rc = enqueue_exchange(b);
     if (rc != DMV_OK) return rc;
   }
-  CK(cudaMemcpyAsync(b->h_result[b->tent], b->d_result[b->tent], sizeof(double) * result_doubles(b->N, b->ntiles), cudaMemcpyDeviceToHost, b->stream));
+  if (!zero_copy)
+    CK(cudaMemcpyAsync(b->h_result[b->tent], b->d_result[b->tent], sizeof(double) * result_doubles(b->N, b->ntiles), cudaMemcpyDeviceToHost, b->stream));
   if (b->timing) CK(cudaEventRecord(b->ev[3], b->stream));
   return DMV_OK;
 }

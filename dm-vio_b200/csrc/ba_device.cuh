@@ -83,6 +83,7 @@ struct BAWinDev {
   unsigned int* ticket;      // [0] CTA completion counter, [1+h] per-host counters (last CTA of a host / overall stitches); self-resetting
   double* stage;             // scratch of the stitch: per pair B|G|GA (272 doubles) + per host 20 calibration sums
   double* result;            // H_top N*N | b_top N | Schur tiles ntiles*16 | ACC_MISC tail
+  double* result_host;       // pinned host mirror of the result blob written by the stitch kernel itself (zero-copy), or nullptr
   BAXchg xc;                 // nranks <= 1: no exchange
 };
 

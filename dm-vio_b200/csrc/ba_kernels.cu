@@ -41,9 +41,7 @@ struct alignas(16) StitchSmem {
   double raw[2][MAXF][TOP_PART];  // [0][t] pair (a,t) (a hosts), [1][t] pair (t,a) (a is target)
   double Ah[2][MAXF][64];
   double d[2][MAXF][8];
-  double B[2][MAXF][8][13];       // [P | Q | p] rows 4..11 of the pair block
-  double G[2][MAXF][8][13];       // adHost * B   ([1]: only the P part is used)
-  double GA[MAXF][64];            // (adHost P) adHost^T for the pairs hosted by a
+  double G[2][MAXF][8][13];       // adHost * [P | Q | p]   ([1]: only the P part is used)
 };
 
 // ---- exchange of the stitched system between ranks (sharded BA): "LL" packets over NVLink peer memory.
@@ -145,27 +143,18 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
   cp_async_wait_all();
   __syncthreads();
   STAMP_ST(2);
-  for (int e = tid; e < 2 * nf * 104; e += ST_THREADS) {  // B[s][t][k][c] = H13[4+k][col(c)], col = 4..11, 0..3, 12
-    const int s2 = e / (nf * 104), e1 = e - s2 * nf * 104, t = e1 / 104, r = e1 - t * 104, k = r / 13, c = r - k * 13;
-    const int col = (c < 8) ? 4 + c : (c < 12 ? c - 8 : 12);
-    (&Q.B[s2][t][0][0])[r] = (t == a) ? 0.0 : h13(Q.raw[s2][t], 4 + k, col);
-  }
-  __syncthreads();
-  for (int e = tid; e < 2 * nf * 104; e += ST_THREADS) {  // G = Ah (8x8) * B (8x13)
+  // G[s][t] = adHost(s,t) * [P | Q | p](s,t)  with [P|Q|p][k][c] = H13[4+k][col(c)], col = 4..11, 0..3, 12, read straight from the
+  // symmetric 136-entry storage ([1]: only the P part is used)
+  for (int e = tid; e < 2 * nf * 104; e += ST_THREADS) {
     const int s2 = e / (nf * 104), e1 = e - s2 * nf * 104, t = e1 / 104, r = e1 - t * 104, i = r / 13, c = r - i * 13;
     if (s2 == 1 && c >= 8) continue;
+    const int col = (c < 8) ? 4 + c : (c < 12 ? c - 8 : 12);
     double m = 0.0;
+    if (t != a) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) m += Q.Ah[s2][t][i * 8 + k] * Q.B[s2][t][k][c];
+      for (int k = 0; k < 8; k++) m += Q.Ah[s2][t][i * 8 + k] * h13(Q.raw[s2][t], 4 + k, col);
+    }
     (&Q.G[s2][t][0][0])[r] = m;
-  }
-  __syncthreads();
-  for (int e = tid; e < nf * 64; e += ST_THREADS) {  // GA = G[0][:, 0:8] * Ah[0]^T
-    const int t = e >> 6, i = (e >> 3) & 7, j = e & 7;
-    double m = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) m += Q.G[0][t][i][k] * Q.Ah[0][t][j * 8 + k];
-    Q.GA[t][e & 63] = m;
   }
   __syncthreads();
   STAMP_ST(3);
@@ -175,14 +164,22 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
     double v = 0.0;
     if (J == N || J < 4) {  // b[a] / H[a,C] = sum_t Ah(a,t) (p|Q)(a,t) + At(t,a) (p|Q)(t,a)
       const int c = (J == N) ? 12 : 8 + J;
-      for (int t = 0; t < nf; t++) v += Q.G[0][t][ia][c] + Q.d[1][t][ia] * Q.B[1][t][ia][c];
+      const int col = (J == N) ? 12 : J;
+      for (int t = 0; t < nf; t++)
+        if (t != a) v += Q.G[0][t][ia][c] + Q.d[1][t][ia] * h13(Q.raw[1][t], 4 + ia, col);
       if (J == N) R[(size_t)N * N + r0 + ia] = v;
       else { R[(size_t)(r0 + ia) * N + J] = v; R[(size_t)J * N + r0 + ia] = v; }
       continue;
     }
     const int fb = (J - 4) >> 3, jb = (J - 4) & 7;
     if (fb == a) {  // diagonal block: sum_t (Ah P Ah^T)(a,t) + At(t,a) P(t,a) At(t,a)
-      for (int t = 0; t < nf; t++) v += Q.GA[t][ia * 8 + jb] + Q.d[1][t][ia] * Q.B[1][t][ia][jb] * Q.d[1][t][jb];
+      for (int t = 0; t < nf; t++) {
+        if (t == a) continue;
+        double ga = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) ga += Q.G[0][t][ia][k] * Q.Ah[0][t][jb * 8 + k];
+        v += ga + Q.d[1][t][ia] * h13(Q.raw[1][t], 4 + ia, 4 + jb) * Q.d[1][t][jb];
+      }
     } else {  // raw[a,b](ia,jb) + raw[b,a](jb,ia), raw[h,t] = (Ah P) At^T
       v = Q.G[0][fb][ia][jb] * Q.d[0][fb][jb] + Q.G[1][fb][jb][ia] * Q.d[1][fb][ia];
     }
@@ -190,16 +187,28 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
   }
   }  // a < nf
   STAMP_ST(4);
-  if (W.xc.nranks > 1) {
+  double* __restrict__ RH = W.result_host;
+  if (W.xc.nranks > 1 || RH != nullptr) {
     __syncthreads();  // every entry of this CTA is in R (same-CTA global writes are visible after the barrier)
     const int cnt = xchg_owned_count(W, a);
-    for (int e = tid; e < cnt; e += ST_THREADS) {
-      const int idx = xchg_owned_index(W, a, e);
-      xchg_push(W.xc, idx, __ldcg(R + idx));
-    }
-    for (int e = tid; e < cnt; e += ST_THREADS) {
-      const int idx = xchg_owned_index(W, a, e);
-      R[idx] = xchg_pull_sum(W.xc, idx, __ldcg(R + idx));
+    if (W.xc.nranks > 1) {
+      for (int e = tid; e < cnt; e += ST_THREADS) {
+        const int idx = xchg_owned_index(W, a, e);
+        xchg_push(W.xc, idx, __ldcg(R + idx));
+      }
+      for (int e = tid; e < cnt; e += ST_THREADS) {
+        const int idx = xchg_owned_index(W, a, e);
+        const double v = xchg_pull_sum(W.xc, idx, __ldcg(R + idx));
+        R[idx] = v;
+        if (RH) RH[idx] = v;
+      }
+    } else {
+      // single GPU: the CTA streams its part of the blob straight into the caller's pinned buffer (posted PCIe writes):
+      // no D2H copy node behind the kernel
+      for (int e = tid; e < cnt; e += ST_THREADS) {
+        const int idx = xchg_owned_index(W, a, e);
+        RH[idx] = __ldcg(R + idx);
+      }
     }
     STAMP_ST(5);
   }
