@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Secondary benchmark (BASELINE config 2): CoarseTracker::trackNewestCoarse on a 640x480 synthetic pair,
+GPU (C++ host adapter over the C ABI: H2D of the new image, pyramid on the device, one fused calcRes+calcGSSSE launch per LM
+evaluation, 8x8 solve on the host) vs the CPU oracle (single thread, like the reference).  Prints one JSON line.
+  python tools/bench_coarse.py [--levels 0|5] [--frames 200]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--levels", type=int, default=0, help="0 = what setGlobalCalib yields (4 at 640x480); 5 = forced, as BASELINE config 2 words it")
+    ap.add_argument("--frames", type=int, default=200)
+    ap.add_argument("--cpu-frames", type=int, default=20)
+    args = ap.parse_args()
+    import dmvio_b200.hostapi as hostapi
+    import dmvio_b200.synth as synth
+    from oracle import orc
+    T = synth.make_tracking_pair(seed=4321, levels=args.levels)
+    L = T["levels"]
+    g = hostapi.CoarseTracker(T["w"], T["h"], T["K"], L)
+    counts = g.set_ref(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
+    R0, t0 = np.eye(3), np.zeros(3)
+    for _ in range(5):
+        g.set_new_image(T["img_new"]); r = g.track(R0, t0, 0.0, 0.0)
+    t_start = time.perf_counter()
+    ev = 0
+    for _ in range(args.frames):   # per frame: upload + device pyramid + the whole LM loop, like FullSystem::trackNewCoarse does per camera frame
+        g.set_new_image(T["img_new"])
+        r = g.track(R0, t0, 0.0, 0.0)
+        ev += r["evaluations"]
+    gpu_ms = (time.perf_counter() - t_start) / args.frames * 1e3
+    oc = orc.CoarseTracker(T["w"], T["h"], T["K"], args.levels)
+    oc.make_coarse_depth(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
+    oc.set_new_frame(T["pyr_new"])
+    ro = oc.track(R0, t0, 0.0, 0.0, precision=0)
+    t_start = time.perf_counter()
+    for _ in range(args.cpu_frames):
+        ro = oc.track(R0, t0, 0.0, 0.0, precision=0)
+    cpu_ms = (time.perf_counter() - t_start) / args.cpu_frames * 1e3
+    pts_per_eval = float(np.mean(counts))
+    out = {"metric": "coarse tracking ms/frame (trackNewestCoarse, 640x480)", "levels": L, "ref_points_per_level": counts,
+           "gpu_ms_per_frame": gpu_ms, "gpu_evaluations_per_frame": ev / args.frames, "gpu_us_per_evaluation": gpu_ms * 1e3 / (ev / args.frames),
+           "gpu_points_per_s": sum(counts) / L * (ev / args.frames) / (gpu_ms * 1e-3),
+           "cpu_oracle_ms_per_frame": cpu_ms, "cpu_threads": 1, "speedup": cpu_ms / gpu_ms,
+           "pose_error_vs_truth_t": float(np.linalg.norm(r["t"] - T["t_true"])), "gpu_vs_cpu_dt": float(np.abs(r["t"] - ro["t"]).max()),
+           "iterations_gpu": r["iterations"], "iterations_cpu": ro["iterations"],
+           "timed": "per frame: H2D of the raw image, device pyramid, LM loop (1 fused launch + 0.6 KB D2H per evaluation), host 8x8 LDLT"}
+    print(json.dumps(out))
+    g.close()
+
+
+if __name__ == "__main__":
+    main()
