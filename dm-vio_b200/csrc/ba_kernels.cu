@@ -63,32 +63,49 @@ __device__ __forceinline__ void xchg_push(const BAXchg& X, int idx, double v) {
   }
 }
 __device__ __forceinline__ double xchg_pull_sum(const BAXchg& X, int idx, double mine) {
-  double s = 0.0;
-  for (int r = 0; r < X.nranks; r++) {
-    if (r == X.rank) { s += mine; continue; }
-    const uint4* src = X.inbox[X.rank] + (size_t)(((X.seq & 1u) * XCHG_MAXR + r)) * X.pitch + idx;
-    uint4 pk;
-    do {
-      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "l"(src) : "memory");
-    } while (pk.y != X.seq || pk.w != X.seq);
-    s += __longlong_as_double((long long)(((unsigned long long)pk.z << 32) | pk.x));
+  // poll all peers' packets of this entry at once (independent loads: one memory round trip when they have all arrived)
+  const uint4* base = X.inbox[X.rank] + (size_t)((X.seq & 1u) * XCHG_MAXR) * X.pitch + idx;
+  uint4 pk[XCHG_MAXR];
+  unsigned pending = ((1u << X.nranks) - 1u) & ~(1u << X.rank);
+  while (pending) {
+#pragma unroll
+    for (int r = 0; r < XCHG_MAXR; r++)
+      if ((pending >> r) & 1u) {
+        const uint4* src = base + (size_t)r * X.pitch;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[r].x), "=r"(pk[r].y), "=r"(pk[r].z), "=r"(pk[r].w) : "l"(src) : "memory");
+      }
+#pragma unroll
+    for (int r = 0; r < XCHG_MAXR; r++)
+      if (((pending >> r) & 1u) && pk[r].y == X.seq && pk[r].w == X.seq) pending &= ~(1u << r);
+  }
+  double s = 0.0;  // rank order => bit-identical sums on every rank
+#pragma unroll
+  for (int r = 0; r < XCHG_MAXR; r++) {
+    if (r >= X.nranks) break;
+    s += (r == X.rank) ? mine : __longlong_as_double((long long)(((unsigned long long)pk[r].z << 32) | pk[r].x));
   }
   return s;
 }
-// entry e (0 <= e < count) of the list of result-blob indices produced by stitch CTA a
-__device__ __forceinline__ int xchg_owned_count(const BAWinDev& W, int a) {
-  return (a < W.nf) ? 8 * (W.N + 1) + 32 : 20 + W.ntiles * 16 + ACC_MISC;
+// The raw Schur tiles + counters (ntiles*16 + ACC_MISC doubles, copied unchanged) are split evenly over the nf+1 CTAs.
+__device__ __forceinline__ int tiles_share(const BAWinDev& W) { return (W.ntiles * 16 + ACC_MISC + W.nf) / (W.nf + 1); }
+__device__ __forceinline__ int tiles_count(const BAWinDev& W, int a) {
+  const int per = tiles_share(W), nsc = W.ntiles * 16 + ACC_MISC;
+  return max(0, min(per, nsc - a * per));
 }
+// entry e (0 <= e < count) of the list of result-blob indices produced by stitch CTA a
+__device__ __forceinline__ int xchg_owned_count(const BAWinDev& W, int a) { return ((a < W.nf) ? 8 * (W.N + 1) + 32 : 20) + tiles_count(W, a); }
 __device__ __forceinline__ int xchg_owned_index(const BAWinDev& W, int a, int e) {
   const int N = W.N;
+  const int own = (a < W.nf) ? 8 * (N + 1) + 32 : 20;
+  if (e >= own) return N * N + N + a * tiles_share(W) + (e - own);
   if (a < W.nf) {
     const int r0 = 4 + 8 * a;
     if (e < 8 * (N + 1)) { const int ia = e / (N + 1), J = e - ia * (N + 1); return (J == N) ? N * N + r0 + ia : (r0 + ia) * N + J; }
     const int m = e - 8 * (N + 1);  // mirrored calibration columns H[J][r0+ia], J < 4
     return (m >> 3) * N + r0 + (m & 7);
   }
-  if (e < 20) { const int i = e / 5, j = e - i * 5; return (j < 4) ? i * N + j : N * N + i; }
-  return N * N + N + (e - 20);
+  const int i = e / 5, j = e - i * 5;
+  return (j < 4) ? i * N + j : N * N + i;
 }
 
 __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_constant__ BAWinDev W) {
@@ -120,10 +137,12 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
   double* __restrict__ R = W.result;
   const int nH = N * N + N;
 
+  {  // this CTA's share of the raw Schur tiles + counters
+    const int o = a * tiles_share(W), c = tiles_count(W, a);
+    for (int e = tid; e < c; e += ST_THREADS) R[nH + o + e] = __ldcg(SC + o + e);
+  }
   if (a == nf) {
-    // calibration rows, raw Schur tiles + counters, and the next iteration's accumulators
-    const int nsc = W.ntiles * 16 + ACC_MISC;
-    for (int e = tid; e < nsc; e += ST_THREADS) R[nH + e] = __ldcg(SC + e);
+    // calibration rows and the next iteration's accumulators
     const int nacc = acc_doubles(nf, W.ntiles);
     for (int i = tid; i < nacc; i += ST_THREADS) W.acc_next[i] = 0.0;
     if (tid < 20) {

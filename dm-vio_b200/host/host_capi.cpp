@@ -34,6 +34,7 @@ int dmvh_window_add_frame(void* p, const float* data, int is_image, const double
   const SE3 T = mkSE3(R, t);
   return is_image ? W->insertFrame(data, T, state, state_zero, ab_exposure, frameID) : W->insertFrameDI(data, T, state, state_zero, ab_exposure, frameID);
 }
+void dmvh_window_drop_frame(void* p, int idx) { static_cast<WindowBA*>(p)->dropFrame(idx); }
 int dmvh_window_set_points(void* p, int n, const int32_t* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
                            const float* color8, const float* weights8, const uint8_t* hdp) {
   static_cast<WindowBA*>(p)->insertPoints(n, host, u, v, idepth, idepth_zero, color8, weights8, hdp);

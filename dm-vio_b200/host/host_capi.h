@@ -11,6 +11,7 @@ const char* dmvh_window_error(void* win);
 /* is_image: 1 = raw w*h float image (level-0 [I,dx,dy] built on the device), 0 = w*h*3 dI AoS */
 int dmvh_window_add_frame(void* win, const float* data, int is_image, const double R[9], const double t[3], const double state[10],
                           const double state_zero[10], float ab_exposure, int frameID);
+void dmvh_window_drop_frame(void* win, int idx); /* the frame leaves the window; its image slot is reused by the next add_frame */
 int dmvh_window_set_points(void* win, int n, const int32_t* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
                            const float* color8, const float* weights8, const uint8_t* hasDepthPrior);
 int dmvh_window_set_residuals(void* win, int n, const int32_t* point, const int32_t* target);

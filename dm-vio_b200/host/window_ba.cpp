@@ -64,7 +64,11 @@ int WindowBA::insertFrame(const float* image, const SE3& evalPT, const double st
   for (int i = 0; i < 10; i++) { f.state_zero[i] = state_zero[i]; f.step[i] = 0; f.state_backup[i] = state[i]; }
   f.ab_exposure = ab_exposure;
   f.frameID = frameID;
-  f.slot = nf();
+  f.slot = 0;  // first image slot not used by a frame of the window: frames stay resident on the device while window indices shift
+  for (bool used = true; used; f.slot += used ? 1 : 0) {
+    used = false;
+    for (const FrameHessian& g : frameHessians) used = used || g.slot == f.slot;
+  }
   f.setState(state);
   if (image && dmv_ba_upload_image(ba_, f.slot, image) != DMV_OK) { fail("dmv_ba_upload_image"); return -1; }
   frameHessians.push_back(f);
@@ -75,6 +79,14 @@ int WindowBA::insertFrameDI(const float* dI, const SE3& evalPT, const double sta
   if (idx < 0) return idx;
   if (dmv_ba_upload_frame(ba_, frameHessians[idx].slot, dI) != DMV_OK) { fail("dmv_ba_upload_frame"); return -1; }
   return idx;
+}
+
+// EnergyFunctional::marginalizeFrame as far as the GPU side is concerned (EnergyFunctional.cpp:L511-676): the frame leaves the window,
+// its image slot becomes free, later frames shift down by one index.  (The marginalisation prior HM/bM is host data owned by the caller.)
+void WindowBA::dropFrame(int idx) {
+  if (idx < 0 || idx >= nf()) return;
+  frameHessians.erase(frameHessians.begin() + idx);
+  HM.clear(); bM.clear();
 }
 
 void WindowBA::insertPoints(int n, const int* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,

@@ -92,6 +92,7 @@ class WindowBA {
                   int frameID);
   int insertFrameDI(const float* dI_aos3, const SE3& worldToCam_evalPT, const double state[10], const double state_zero[10], float ab_exposure,
                     int frameID);
+  void dropFrame(int idx);
   void insertPoints(int n, const int* host, const float* u, const float* v, const float* idepth, const float* idepth_zero, const float* color8,
                     const float* weights8, const unsigned char* hasDepthPrior);
   void insertResiduals(int n, const int* point, const int* target);

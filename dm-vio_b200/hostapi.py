@@ -23,6 +23,7 @@ def lib():
         L.dmvh_window_error.restype = C.c_char_p
         L.dmvh_window_error.argtypes = [vp]
         L.dmvh_window_add_frame.argtypes = [vp, f32p, C.c_int, f64p, f64p, f64p, f64p, C.c_float, C.c_int]
+        L.dmvh_window_drop_frame.argtypes = [vp, C.c_int]
         L.dmvh_window_set_points.argtypes = [vp, C.c_int, i32p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
         L.dmvh_window_set_residuals.argtypes = [vp, C.c_int, i32p, i32p]
         L.dmvh_window_prepare.argtypes = [vp]
