@@ -54,7 +54,7 @@ SYMBOLS = [
     "dmv_ba_resubstitute", "dmv_ba_backup_points", "dmv_ba_restore_points", "dmv_ba_get_idepth", "dmv_ba_gn_step", "dmv_nccl_unique_id",
     "dmv_ba_comm_init", "dmv_ba_p2p_export", "dmv_ba_p2p_import", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e", "dmv_ba_debug_clocks",
     "dmv_ct_create", "dmv_ct_destroy", "dmv_ct_set_K", "dmv_ct_set_ref", "dmv_ct_upload_new", "dmv_ct_upload_new_image", "dmv_ct_set_huber",
-    "dmv_ct_calc_res_gs", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count",
+    "dmv_ct_calc_res_gs", "dmv_ct_set_timing", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count",
 ]
 
 
@@ -107,6 +107,7 @@ def lib():
         L.dmv_ct_upload_new_image.argtypes = [vp, f32p]
         L.dmv_ct_set_huber.argtypes = [vp, C.c_float]
         L.dmv_ct_calc_res_gs.argtypes = [vp, C.c_int, f32p, f32p, f32p, C.c_float, C.c_float, C.c_int, f64p, f64p, f64p, C.POINTER(C.c_int)]
+        L.dmv_ct_set_timing.argtypes = [vp, C.c_int]
         L.dmv_ct_last_timing.argtypes = [vp, f32p]
         L.dmv_ct_kernel_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
         _LIB = L
@@ -349,6 +350,9 @@ class CT:
         check(self.L.dmv_ct_calc_res_gs(self.h, lvl, _c(RKi, np.float32).reshape(-1), _c(t, np.float32), _c(affLL, np.float32), b0, cutoff,
                                         int(want_gs), res6, H, b, C.byref(n)))
         return res6, H.reshape(8, 8), b, n.value
+
+    def set_timing(self, enable=True):
+        check(self.L.dmv_ct_set_timing(self.h, int(enable)))
 
     def last_timing(self):
         ms = np.zeros(4, np.float32)

@@ -172,6 +172,7 @@ struct dmv_ct {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool timing = false;  // CUDA-event timing of every evaluation (dmv_ct_set_timing); off by default: two event records per launch
   int w[DMV_MAX_PYR_LEVELS], h[DMV_MAX_PYR_LEVELS];
   float fx[DMV_MAX_PYR_LEVELS], fy[DMV_MAX_PYR_LEVELS], cx[DMV_MAX_PYR_LEVELS], cy[DMV_MAX_PYR_LEVELS];
   bool haveK[DMV_MAX_PYR_LEVELS];
@@ -337,15 +338,15 @@ int dmv_ct_calc_res_gs(dmv_ct* c, int l, const float RKi[9], const float t[3], c
   P.maxEnergy = 2 * c->huber * cutoffTH - c->huber * c->huber;
   P.w = c->w[l]; P.h = c->h[l]; P.n = c->n[l]; P.lvl = l; P.want_gs = want_gs;
   const int nb = std::max(1, (c->n[l] + CT_THREADS - 1) / CT_THREADS);
-  CK(cudaEventRecord(c->ev[0], c->stream));
+  if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+  // the last block writes the 53 reduced doubles straight into the pinned host buffer (zero-copy): no D2H copy node per evaluation
   ct_res_gs_kernel<<<nb, CT_THREADS, 0, c->stream>>>(P, c->d_u[l], c->d_v[l], c->d_id[l], c->d_col[l], c->d_img[l], c->d_partial, c->d_ticket,
-                                                      c->d_out);
+                                                      c->h_out);
   c->launches++;
-  CK(cudaEventRecord(c->ev[1], c->stream));
+  if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(c->h_out, c->d_out, sizeof(double) * CT_NRED, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
+  if (c->timing) cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
   const double* o = c->h_out;
   const double E = o[45], nE = o[46], nSat = o[47], nW = o[48];
   res6[0] = E;
@@ -372,6 +373,11 @@ int dmv_ct_calc_res_gs(dmv_ct* c, int l, const float RKi[9], const float t[3], c
   return DMV_OK;
 }
 
+int dmv_ct_set_timing(dmv_ct* c, int enable) {
+  if (!c) return set_error(DMV_ERR_INVALID, "null handle");
+  c->timing = enable != 0;
+  return DMV_OK;
+}
 int dmv_ct_last_timing(dmv_ct* c, float ms[4]) {
   if (!c || !ms) return set_error(DMV_ERR_INVALID, "null argument");
   for (int i = 0; i < 4; i++) ms[i] = c->last_ms[i];

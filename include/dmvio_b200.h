@@ -215,6 +215,8 @@ int dmv_ct_set_huber(dmv_ct* ct, float huberTH);
  * (divided by the 4-padded warped count, SCALE_* applied); n_warped = buf_warped_n (padded). */
 int dmv_ct_calc_res_gs(dmv_ct* ct, int level, const float RKi[9], const float t[3], const float affLL[2], float b0, float cutoffTH,
                        int want_gs, double res6[6], double H[64], double b[8], int* n_warped);
+/* enable/disable the CUDA-event timing of dmv_ct_calc_res_gs (off by default); dmv_ct_last_timing()[0] = kernel milliseconds */
+int dmv_ct_set_timing(dmv_ct* ct, int enable);
 int dmv_ct_last_timing(dmv_ct* ct, float ms[4]);
 int dmv_ct_kernel_launch_count(dmv_ct* ct, long long* n);
 
