@@ -108,6 +108,29 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of ba_point_kernel from the newest committed `ncu --set full` capture
+    (profiles/*_ba_point_summary.md, written by tools/summarize_profiles.py); None if there is none."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ba_point_summary.md")))
+    if not files:
+        return None, None
+    rd = wr = None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in open(files[-1]):
+        m = re.match(r"\| dram__bytes_(read|write)\.sum \| ([0-9.]+) \| (\w+) \|", line)
+        if m:
+            v = float(m.group(2)) * unit.get(m.group(3), 1.0)
+            if m.group(1) == "read" and rd is None:
+                rd = v
+            if m.group(1) == "write" and wr is None:
+                wr = v
+    if rd is None:
+        return None, None
+    return rd + (wr or 0.0), os.path.relpath(files[-1], ROOT)
+
+
 def algorithmic_bytes(nres, npts, nf):
     """B_alg = 436*nres + 112*npts + 8*(8nf+4)(8nf+5)."""
     N = 8 * nf + 4
@@ -331,6 +354,7 @@ def main():
     e2e_value = nres_total / (e2e_ms * 1e-3)
     peak, peak_src = measured_peak()
     balg = algorithmic_bytes(nres_local, len(Wr["host"]), NF)
+    traffic, traffic_src = ncu_traffic()
     ach = balg / (ms_point * 1e-3) / 1e9
 
     cpu = None
@@ -355,9 +379,11 @@ def main():
                     "device_ms_last_step": float(tm[0]), "ms_per_step_via_python_ctypes": e2e_ms_py,
                     "timed": "steps x {dmv_ba_gn_step(host x, host tables) ; dmv_ba_apply_res()} issued from C, wall clock, incl. H2D/D2H + sync"},
             "gpu_launches": int(ba.launch_count() - launches0),
-            "roofline": {"bound": "hbm", "kernel": "ba_point_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": balg, "kernel_ms": ms_point,
-                         "note": "working set (7 level-0 planes = 34 MB as float4) is L2-sized; the step is latency-bound, see DESIGN.md"},
+            "roofline": {"bound": "hbm", "kernel": "ba_point_kernel (+ ba_stitch_kernel chained by PDL)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": balg, "kernel_ms": ms_point,
+                         "note": "working set (7 level-0 planes = 34 MB as float4) is L2-sized and one window is a single wave of 129 CTAs: the step is "
+                                 "bound by instruction issue + the dependent launch/load/reduce chain, not by HBM (DESIGN.md section 6)"},
             "clocks": clocks,
         }
         if cpu:

@@ -10,7 +10,12 @@ namespace dmv {
 constexpr int MAXF = 8;             // DMV_MAX_FRAMES
 constexpr int TOP_ROWS = 10;        // geometric rows [C4 | xi6] of the 13x13 pair block
 constexpr int TOP_COLS = 13;
-constexpr int TOP_PART = TOP_ROWS * TOP_COLS + 6;  // 136: 10 full rows + 6 bottom-right (a,b,r) entries
+// One (host,target) pair block = the 91 distinct entries of the symmetric 13x13 AccumulatorApprox (MatrixAccumulators.h:L595-972):
+// rows 0..9 packed upper-triangular (row r holds columns r..12), then the 6 bottom-right (a,b,r) entries, padded to 92 (16-byte rows).
+constexpr int TOP_TRI = 85;                        // sum_{r=0}^{9} (13 - r)
+constexpr int TOP_USED = TOP_TRI + 6;              // 91
+constexpr int TOP_PART = 92;
+__host__ __device__ constexpr int top_off(int r) { return r * TOP_COLS - (r * (r - 1)) / 2; }  // offset of entry (r, r); entry (r, c>=r) = top_off(r) + c - r
 constexpr int REC = 16;             // per (point,target) record kept in shared memory
 constexpr int RES_NONE = 255, RES_IN = 0, RES_OOB = 1, RES_OUTLIER = 2;
 constexpr int ACC_MISC = 8;         // energy, n_in, n_oob, n_outlier, sum step^2, sum |idepth_backup|, npts, pad

@@ -19,12 +19,12 @@
 
 namespace dmv {
 
-// 13x13 pair block from the 136-double layout (rows 0..9 full, then the 6 bottom-right entries)
+// 13x13 pair block from the packed 92-double layout (rows 0..9 upper-triangular, then the 6 bottom-right entries)
 __device__ __forceinline__ double h13(const double* S, int r, int c) {
   if (r > c) { int tmp = r; r = c; c = tmp; }
-  if (r < TOP_ROWS) return S[r * TOP_COLS + c];
+  if (r < TOP_ROWS) return S[top_off(r) + c - r];
   const int rr = r - 10, cc = c - 10;  // (0,0)->0 (0,1)->1 (0,2)->2 (1,1)->3 (1,2)->4 (2,2)->5
-  return S[TOP_ROWS * TOP_COLS + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5))];
+  return S[TOP_TRI + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5))];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
       double v = 0.0;
       const int c = (j < 4) ? j : 12;
       const int rr = i < c ? i : c, cc = i < c ? c : i;  // rows 0..3 are stored in full: entry (rr, cc) with rr <= cc
-      for (int pr = 0; pr < nf * nf; pr++) v += __ldcg(TS + (size_t)pr * TOP_PART + rr * TOP_COLS + cc);
+      for (int pr = 0; pr < nf * nf; pr++) v += __ldcg(TS + (size_t)pr * TOP_PART + top_off(rr) + cc - rr);
       if (j < 4) R[(size_t)i * N + j] = v; else R[(size_t)N * N + i] = v;
     }
   } else {

@@ -20,7 +20,7 @@ namespace dmv {
 
 template <int P>
 struct PointSmem {
-  float part[MAXF][P / 4][4][TOP_PART];  // [target][quad][8-lane group][rows 0..9 x 13 | 6]
+  float part[MAXF][P / 4][4][TOP_PART];  // [target][quad][8-lane group][rows 0..9 upper-triangular (85) | 6 | pad]
   float rec[P][MAXF][REC];               // per (point,target): JpJdF[8] Hdd bd Hcd[4] active pad
   float Wv[P][8 * MAXF + 8];             // Schur vectors
   float hdi[P];
@@ -274,12 +274,15 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
         const float xr2 = (j & 1) ? x[9] : x[8], yr2 = (j & 1) ? y[9] : y[8];
         const float al1 = JI00 * xr1 + JI10 * yr1, be1 = JI10 * xr1 + JI11 * yr1;
         const float al2 = JI00 * xr2 + JI10 * yr2, be2 = JI10 * xr2 + JI11 * yr2;
-        float* row1 = part + j * TOP_COLS;
-        float* row2 = part + (8 + (j & 1)) * TOP_COLS;
+        // packed upper-triangular storage: row r keeps columns r..12 only (the lower triangle is the mirror image)
+        float* row1 = part + top_off(j) - j;
+        const int r2 = 8 + (j & 1);
+        float* row2 = part + top_off(r2) - r2;
 #pragma unroll
         for (int c = 0; c < 10; c++) {
-          row1[c] = al1 * x[c] + be1 * y[c];
-          if (j < 2) row2[c] = al2 * x[c] + be2 * y[c];
+          const float v1 = al1 * x[c] + be1 * y[c];
+          if (c >= j) row1[c] = v1;
+          if (c >= 8 && j < 2 && c >= r2) row2[c] = al2 * x[c] + be2 * y[c];
         }
         row1[10] = xr1 * JabJI00 + yr1 * JabJI01;
         row1[11] = xr1 * JabJI10 + yr1 * JabJI11;
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
           row2[11] = xr2 * JabJI10 + yr2 * JabJI11;
           row2[12] = xr2 * JIr0 + yr2 * JIr1;
         }
-        if (j < 6) part[TOP_ROWS * TOP_COLS + j] = (j == 0) ? Jab00 : (j == 1) ? Jab01 : (j == 2) ? Jabr0 : (j == 3) ? Jab11 : (j == 4) ? Jabr1 : rr;
+        if (j < 6) part[TOP_TRI + j] = (j == 0) ? Jab00 : (j == 1) ? Jab01 : (j == 2) ? Jabr0 : (j == 3) ? Jab11 : (j == 4) ? Jabr1 : rr;
       } else {
         for (int c = j; c < TOP_PART; c += 8) part[c] = 0.f;
         if (j == 0 && valid) S.rec[pl][t][14] = 0.f;  // "no active residual" flag (shared memory is not pre-zeroed)
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
   for (int e0 = tid; e0 < nf * TOP_PART; e0 += nthreads) {
     const int e = (e0 + (int)blockIdx.x * 53) % (nf * TOP_PART);  // staggered start per CTA (RED address spreading)
     const int tt = e / TOP_PART, k = e - tt * TOP_PART;
-    if (tt == h) continue;
+    if (tt == h || k >= TOP_USED) continue;
     float s = 0.f;
 #pragma unroll
     for (int q = 0; q < P / 4; q++)
