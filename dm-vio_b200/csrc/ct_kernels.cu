@@ -27,12 +27,10 @@ struct CTParams {
   int w, h, n, lvl, want_gs;
 };
 
-__global__ void __launch_bounds__(CT_THREADS) ct_res_gs_kernel(CTParams P, const float* __restrict__ pc_u, const float* __restrict__ pc_v,
-                                                               const float* __restrict__ pc_id, const float* __restrict__ pc_col,
-                                                               const float4* __restrict__ img, double* __restrict__ partial,
-                                                               unsigned int* __restrict__ ticket, double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float v[CT_NRED];
+// one reference point: CoarseTracker::calcRes (L399-483) + its row of calcGSSSE (L316-336); v[] = this point's contribution
+__device__ __forceinline__ void ct_eval_point(const CTParams& P, int i, const float* __restrict__ pc_u, const float* __restrict__ pc_v,
+                                              const float* __restrict__ pc_id, const float* __restrict__ pc_col, const float4* __restrict__ img,
+                                              float v[CT_NRED]) {
 #pragma unroll
   for (int k = 0; k < CT_NRED; k++) v[k] = 0.f;
   if (i < P.n) {
@@ -99,8 +97,10 @@ __global__ void __launch_bounds__(CT_THREADS) ct_res_gs_kernel(CTParams P, const
       }
     }
   }
-  // ---- block reduction: warp shuffles, then 8 warp partials through shared memory
-  __shared__ float s_red[CT_THREADS / 32][CT_NRED];
+}
+
+// block reduction: warp shuffles, then the 8 warp partials through shared memory; thread k < CT_NRED returns the block's sum of v[k] in fp64
+__device__ __forceinline__ double ct_block_reduce(const float v[CT_NRED], float (*s_red)[CT_NRED]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < CT_NRED; k++) {
@@ -113,12 +113,24 @@ __global__ void __launch_bounds__(CT_THREADS) ct_res_gs_kernel(CTParams P, const
     if (lane == 0) s_red[warp][k] = a;
   }
   __syncthreads();
+  double s = 0.0;
   if (threadIdx.x < CT_NRED) {
-    double s = 0.0;
 #pragma unroll
     for (int wv = 0; wv < CT_THREADS / 32; wv++) s += (double)s_red[wv][threadIdx.x];
-    partial[(size_t)blockIdx.x * CT_NRED + threadIdx.x] = s;
   }
+  return s;
+}
+
+__global__ void __launch_bounds__(CT_THREADS) ct_res_gs_kernel(CTParams P, const float* __restrict__ pc_u, const float* __restrict__ pc_v,
+                                                               const float* __restrict__ pc_id, const float* __restrict__ pc_col,
+                                                               const float4* __restrict__ img, double* __restrict__ partial,
+                                                               unsigned int* __restrict__ ticket, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float v[CT_NRED];
+  ct_eval_point(P, i, pc_u, pc_v, pc_id, pc_col, img, v);
+  __shared__ float s_red[CT_THREADS / 32][CT_NRED];
+  const double bs = ct_block_reduce(v, s_red);
+  if (threadIdx.x < CT_NRED) partial[(size_t)blockIdx.x * CT_NRED + threadIdx.x] = bs;
   // ---- last block folds the per-block partials in block order
   __shared__ bool s_last;
   __threadfence();
@@ -136,6 +148,298 @@ __global__ void __launch_bounds__(CT_THREADS) ct_res_gs_kernel(CTParams P, const
       out[threadIdx.x] = s;
     }
     if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ct_track_kernel — CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:L539-770, visual-only branch L639-683) as ONE persistent
+// launch: the Levenberg-Marquardt loop over all pyramid levels runs on the device.  G = ceil(max_l n_l / 256) co-resident CTAs
+// (cooperative launch); one evaluation = every CTA evaluates its points (calcRes + calcGSSSE row, as ct_res_gs_kernel), per-CTA
+// fp64 partials, a grid barrier, then EVERY CTA folds the partials in CTA order and its thread 0 advances the same scalar state
+// machine in double (8x8 LDLT, SE3 exp, accept/reject, level schedule) - identical inputs, identical decisions, so no second
+// barrier and no broadcast.  Replaces ~21 launch + sync round trips per frame by one launch.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int CT_L = DMV_MAX_PYR_LEVELS;
+struct CTTrack {
+  int levels, coarsest, G;
+  int n[CT_L], w[CT_L], h[CT_L];
+  float fx[CT_L], fy[CT_L], cx[CT_L], cy[CT_L];
+  float Ki[CT_L][9];
+  const float *u[CT_L], *v[CT_L], *id[CT_L], *col[CT_L];
+  const float4* img[CT_L];
+  double R0[9], t0[3], a0, b0;   // lastToNew_out / aff_g2l_out on entry
+  double ref_a, ref_b;           // lastRef_aff_g2l
+  float ref_exposure, new_exposure;
+  float huber, cutoffTH, affModeA, affModeB;
+  double minRes[5];
+  double* partial;               // [2][G][CT_NRED]
+  unsigned int* bar;             // monotonic arrival counter, zero at launch
+  double* out;                   // pinned host: R[9] t[3] a b lastResiduals[5] flow[3] good iterations evaluations status
+};
+
+struct CTLM {  // the scalar state of trackNewestCoarse, one copy per CTA (shared memory), advanced by thread 0
+  double R[9], t[3], a, b;          // refToNew_current, aff_g2l_current
+  double Rn[9], tn[3], an, bn;      // candidate
+  double H[64], bb[8], resOld[6];
+  double inc[8];
+  double lastResiduals[5], flow[3];
+  float RKi[9], tf[3], affLL[2], cutoff;  // operands of the pending evaluation
+  float lambda, rep;
+  int lvl, iteration, phase, haveRepeated, iterations, evaluations, done, good, status;
+};
+enum { CT_PH_INIT = 0, CT_PH_LM = 1 };
+
+__device__ __forceinline__ void ct_se3_exp_mul(const double xi[6], const double R[9], const double t[3], double Ro[9], double to[3]) {
+  // SE3::exp(xi) * (R,t)   (Sophus: tangent = (translation, rotation), left increment)
+  const double wx = xi[3], wy = xi[4], wz = xi[5];
+  const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
+  const double W[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+  double W2[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) W2[i * 3 + j] = W[i * 3] * W[j] + W[i * 3 + 1] * W[3 + j] + W[i * 3 + 2] * W[6 + j];
+  double ca, cb, cc;
+  if (th < 1e-8) { ca = 1.0 - th2 / 6.0; cb = 0.5 - th2 / 24.0; cc = 1.0 / 6.0 - th2 / 120.0; }
+  else { ca = sin(th) / th; cb = (1.0 - cos(th)) / th2; cc = (th - sin(th)) / (th2 * th); }
+  double E[9], V[9], et[3];
+  for (int i = 0; i < 9; i++) {
+    const double I = (i % 4 == 0) ? 1.0 : 0.0;
+    E[i] = I + ca * W[i] + cb * W2[i];
+    V[i] = I + cb * W[i] + cc * W2[i];
+  }
+  for (int i = 0; i < 3; i++) et[i] = V[i * 3] * xi[0] + V[i * 3 + 1] * xi[1] + V[i * 3 + 2] * xi[2];
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) Ro[i * 3 + j] = E[i * 3] * R[j] + E[i * 3 + 1] * R[3 + j] + E[i * 3 + 2] * R[6 + j];
+    to[i] = E[i * 3] * t[0] + E[i * 3 + 1] * t[1] + E[i * 3 + 2] * t[2] + et[i];
+  }
+}
+__device__ __forceinline__ void ct_ldlt_solve(int n, const double* A, const double* b, double* x) {  // plain LDL^T, n <= 8, row-major
+  double L[64], D[8], y[8];
+  for (int i = 0; i < n * n; i++) L[i] = 0.0;
+  for (int j = 0; j < n; j++) {
+    double dj = A[j * n + j];
+    for (int k = 0; k < j; k++) dj -= L[j * n + k] * L[j * n + k] * D[k];
+    D[j] = dj;
+    L[j * n + j] = 1.0;
+    for (int i = j + 1; i < n; i++) {
+      double sm = A[i * n + j];
+      for (int k = 0; k < j; k++) sm -= L[i * n + k] * L[j * n + k] * D[k];
+      L[i * n + j] = dj != 0.0 ? sm / dj : 0.0;
+    }
+  }
+  for (int i = 0; i < n; i++) { double sm = b[i]; for (int k = 0; k < i; k++) sm -= L[i * n + k] * y[k]; y[i] = sm; }
+  for (int i = 0; i < n; i++) y[i] = D[i] != 0.0 ? y[i] / D[i] : 0.0;
+  for (int i = n - 1; i >= 0; i--) { double sm = y[i]; for (int k = i + 1; k < n; k++) sm -= L[k * n + i] * x[k]; x[i] = sm; }
+}
+// operands of calcRes for a pose (CoarseTracker.cpp:L377-379): RKi = R.cast<float>() * Ki[lvl], t.cast<float>(), affLL.cast<float>()
+__device__ __forceinline__ void ct_request(const CTTrack& T, CTLM& S, const double R[9], const double t[3], double a, double b) {
+  float Rf[9];
+  for (int i = 0; i < 9; i++) Rf[i] = (float)R[i];
+  const float* Ki = T.Ki[S.lvl];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) S.RKi[i * 3 + j] = Rf[i * 3] * Ki[j] + Rf[i * 3 + 1] * Ki[3 + j] + Rf[i * 3 + 2] * Ki[6 + j];
+  for (int i = 0; i < 3; i++) S.tf[i] = (float)t[i];
+  float eF = T.ref_exposure, eT = T.new_exposure;  // AffLight::fromToVecExposure (util/NumType.h:L174-186)
+  if (eF == 0 || eT == 0) eT = eF = 1;
+  const double aa = exp(a - T.ref_a) * eT / eF;
+  S.affLL[0] = (float)aa;
+  S.affLL[1] = (float)(b - aa * T.ref_b);
+  S.cutoff = T.cutoffTH * S.rep;
+  S.evaluations++;
+}
+// Vec6 of calcRes (L508-516) and H, b of calcGSSSE (L341-355) from the 53 folded sums
+__device__ __forceinline__ void ct_finish(const double* o, double res6[6], double H[64], double b[8]) {
+  const double E = o[45], nE = o[46], nSat = o[47], nW = o[48];
+  res6[0] = E; res6[1] = nE;
+  res6[2] = (double)((float)o[49] / ((float)o[51] + 0.1f));
+  res6[3] = 0;
+  res6[4] = (double)((float)o[50] / ((float)o[51] + 0.1f));
+  res6[5] = (double)((float)nSat / (float)nE);
+  const int npad = ((int)nW + 3) & ~3;
+  double M[9][9];
+  int e = 0;
+  for (int r = 0; r < 9; r++)
+    for (int c = r; c < 9; c++) { M[r][c] = M[c][r] = o[e]; e++; }
+  const double inv = (double)(1.0f / (float)npad);
+  const double sc[8] = {1, 1, 1, 1, 1, 1, 10.0, 1000.0};
+  for (int r = 0; r < 8; r++) {
+    for (int c = 0; c < 8; c++) H[r * 8 + c] = M[r][c] * inv * sc[r] * sc[c];
+    b[r] = M[r][8] * inv * sc[r];
+  }
+}
+__device__ void ct_begin_level(const CTTrack& T, CTLM& S) {
+  S.rep = 1.f;
+  S.phase = CT_PH_INIT;
+  ct_request(T, S, S.R, S.t, S.a, S.b);
+}
+// one LM trial step from the current linearisation (L605-683)
+__device__ void ct_propose(const CTTrack& T, CTLM& S) {
+  S.iterations++;
+  double Hl[64];
+  for (int i = 0; i < 64; i++) Hl[i] = S.H[i];
+  for (int i = 0; i < 8; i++) Hl[i * 8 + i] *= (1 + S.lambda);
+  float extrapFac = 1;
+  const float lambdaExtrapolationLimit = 0.001f;
+  if (S.lambda < lambdaExtrapolationLimit) extrapFac = sqrtf(sqrtf(lambdaExtrapolationLimit / S.lambda));
+  double inc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  {
+    int map[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    int n = 8;
+    const bool fixA = T.affModeA < 0, fixB = T.affModeB < 0;
+    if (fixA && fixB) n = 6;
+    else if (!fixA && fixB) n = 7;
+    else if (fixA && !fixB) { n = 7; map[6] = 7; }
+    double A[64], rhs[8], x[8];
+    for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) A[i * n + j] = Hl[map[i] * 8 + map[j]]; rhs[i] = -S.bb[map[i]]; }
+    ct_ldlt_solve(n, A, rhs, x);
+    for (int i = 0; i < n; i++) inc[map[i]] = x[i];
+  }
+  for (int i = 0; i < 8; i++) inc[i] *= extrapFac;
+  double incScaled[8];
+  for (int i = 0; i < 8; i++) incScaled[i] = inc[i];
+  incScaled[6] *= 10.0;    // SCALE_A
+  incScaled[7] *= 1000.0;  // SCALE_B
+  double ssum = 0;
+  for (int i = 0; i < 8; i++) ssum += incScaled[i];
+  if (!isfinite(ssum)) for (int i = 0; i < 8; i++) incScaled[i] = 0;
+  ct_se3_exp_mul(incScaled, S.R, S.t, S.Rn, S.tn);
+  S.an = S.a + incScaled[6];
+  S.bn = S.b + incScaled[7];
+  for (int i = 0; i < 8; i++) S.inc[i] = inc[i];
+  S.phase = CT_PH_LM;
+  ct_request(T, S, S.Rn, S.tn, S.an, S.bn);
+}
+__device__ void ct_end_level(const CTTrack& T, CTLM& S) {  // L722-745
+  const int lvl = S.lvl;
+  S.lastResiduals[lvl] = sqrtf((float)(S.resOld[0] / S.resOld[1]));
+  S.flow[0] = S.resOld[2]; S.flow[1] = S.resOld[3]; S.flow[2] = S.resOld[4];
+  if (isnan(S.lastResiduals[lvl]) || S.lastResiduals[lvl] > 1.5 * T.minRes[lvl]) { S.done = 1; S.good = 0; S.status = 2; return; }
+  if (S.rep > 1 && !S.haveRepeated) { S.haveRepeated = 1; ct_begin_level(T, S); return; }  // lvl++ ; continue  => the same level again
+  S.lvl = lvl - 1;
+  if (S.lvl < 0) {  // L747-769
+    S.done = 1;
+    bool good = true;
+    if ((T.affModeA != 0 && (fabsf((float)S.a) > 1.2f)) || (T.affModeB != 0 && (fabsf((float)S.b) > 200.f))) good = false;
+    float eF = T.ref_exposure, eT = T.new_exposure;
+    if (eF == 0 || eT == 0) eT = eF = 1;
+    const double ra = exp(S.a - T.ref_a) * eT / eF, rb = S.b - ra * T.ref_b;
+    if ((T.affModeA == 0 && (fabsf(logf((float)ra)) > 1.5f)) || (T.affModeB == 0 && (fabsf((float)rb) > 200.f))) good = false;
+    if (T.affModeA < 0) S.a = 0;
+    if (T.affModeB < 0) S.b = 0;
+    S.good = good ? 1 : 0;
+    return;
+  }
+  ct_begin_level(T, S);
+}
+// thread 0: consume the folded sums of the evaluation that just finished and decide what to evaluate next
+__device__ void ct_advance(const CTTrack& T, CTLM& S, const double* red) {
+  const int maxIterations[5] = {10, 20, 50, 50, 50};
+  double res[6], Hn[64], bn[8];
+  ct_finish(red, res, Hn, bn);
+  if (S.phase == CT_PH_INIT) {  // L566-578: first evaluation of a level, cutoff doubling while too many residuals saturate
+    for (int i = 0; i < 6; i++) S.resOld[i] = res[i];
+    for (int i = 0; i < 64; i++) S.H[i] = Hn[i];
+    for (int i = 0; i < 8; i++) S.bb[i] = bn[i];
+    if (S.resOld[5] > 0.6 && (S.rep < 50 || S.resOld[5] > 0.99)) { S.rep *= 2; ct_request(T, S, S.R, S.t, S.a, S.b); return; }
+    S.lambda = 0.01f;
+    S.iteration = 0;
+    if (S.iteration >= maxIterations[S.lvl]) { ct_end_level(T, S); return; }
+    ct_propose(T, S);
+    return;
+  }
+  // CT_PH_LM: accept / reject (L686-716)
+  const bool accept = (res[0] / res[1]) < (S.resOld[0] / S.resOld[1]);
+  if (accept) {
+    for (int i = 0; i < 64; i++) S.H[i] = Hn[i];
+    for (int i = 0; i < 8; i++) S.bb[i] = bn[i];
+    for (int i = 0; i < 6; i++) S.resOld[i] = res[i];
+    S.a = S.an; S.b = S.bn;
+    for (int i = 0; i < 9; i++) S.R[i] = S.Rn[i];
+    for (int i = 0; i < 3; i++) S.t[i] = S.tn[i];
+    S.lambda *= 0.5f;
+  } else {
+    S.lambda *= 4;
+    if (S.lambda < 0.001f) S.lambda = 0.001f;
+  }
+  double incNorm = 0;
+  for (int i = 0; i < 8; i++) incNorm += S.inc[i] * S.inc[i];
+  incNorm = sqrt(incNorm);
+  S.iteration++;
+  if (!(incNorm > 1e-3) || S.iteration >= maxIterations[S.lvl]) { ct_end_level(T, S); return; }
+  ct_propose(T, S);
+}
+
+__global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_constant__ CTTrack T) {
+  __shared__ float s_red[CT_THREADS / 32][CT_NRED];
+  __shared__ double s_sum[CT_NRED];
+  __shared__ CTLM S;
+  const int tid = threadIdx.x;
+  const int G = T.G;
+  unsigned int epoch = 0;
+  int par = 0;
+  if (tid == 0) {
+    for (int i = 0; i < 9; i++) S.R[i] = T.R0[i];
+    for (int i = 0; i < 3; i++) S.t[i] = T.t0[i];
+    S.a = T.a0; S.b = T.b0;
+    for (int i = 0; i < 5; i++) S.lastResiduals[i] = __longlong_as_double(0x7ff8000000000000ll);  // NAN
+    for (int i = 0; i < 3; i++) S.flow[i] = 1000;
+    S.haveRepeated = 0; S.iterations = 0; S.evaluations = 0; S.done = 0; S.good = 0; S.status = 0;
+    S.lvl = T.coarsest;
+    ct_begin_level(T, S);
+  }
+  __syncthreads();
+  while (!S.done) {
+    // ---- one evaluation: calcRes + calcGSSSE at the requested pose
+    CTParams P;
+    const int l = S.lvl;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { P.RKi[i] = S.RKi[i]; P.Ki[i] = T.Ki[l][i]; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) P.t[i] = S.tf[i];
+    P.fx = T.fx[l]; P.fy = T.fy[l]; P.cx = T.cx[l]; P.cy = T.cy[l];
+    P.affa = S.affLL[0]; P.affb = S.affLL[1]; P.a_gs = S.affLL[0]; P.b0 = (float)T.ref_b;
+    P.cutoff = S.cutoff; P.huber = T.huber; P.maxEnergy = 2 * T.huber * S.cutoff - T.huber * T.huber;
+    P.w = T.w[l]; P.h = T.h[l]; P.n = T.n[l]; P.lvl = l; P.want_gs = 1;
+    float v[CT_NRED];
+    ct_eval_point(P, blockIdx.x * CT_THREADS + tid, T.u[l], T.v[l], T.id[l], T.col[l], T.img[l], v);
+    const double bs = ct_block_reduce(v, s_red);
+    if (tid < CT_NRED) T.partial[((size_t)par * G + blockIdx.x) * CT_NRED + tid] = bs;
+    // ---- grid barrier (all G CTAs are co-resident: cooperative launch)
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      epoch += (unsigned)G;
+      atomicAdd(T.bar, 1u);
+      unsigned long long t_start;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+      while (*((volatile unsigned int*)T.bar) < epoch) {
+        unsigned long long t_now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_now));
+        if (t_now - t_start > 200000000ull) { S.done = 1; S.good = 0; S.status = 1; break; }  // 0.2 s: never hang the GPU on a lost CTA
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    if (S.status == 1) break;
+    // ---- every CTA folds the partials in CTA order (bit-identical sums everywhere) and advances the same state machine
+    if (tid < CT_NRED) {
+      double sm = 0.0;
+      for (int bk = 0; bk < G; bk++) sm += __ldcg(&T.partial[((size_t)par * G + bk) * CT_NRED + tid]);
+      s_sum[tid] = sm;
+    }
+    par ^= 1;
+    __syncthreads();
+    if (tid == 0) ct_advance(T, S, s_sum);
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    double* o = T.out;
+    const bool ok = (S.status == 0);
+    for (int i = 0; i < 9; i++) o[i] = ok ? S.R[i] : T.R0[i];
+    for (int i = 0; i < 3; i++) o[9 + i] = ok ? S.t[i] : T.t0[i];
+    o[12] = ok ? S.a : T.a0; o[13] = ok ? S.b : T.b0;
+    for (int i = 0; i < 5; i++) o[14 + i] = S.lastResiduals[i];
+    for (int i = 0; i < 3; i++) o[19 + i] = S.flow[i];
+    o[22] = S.good; o[23] = S.iterations; o[24] = S.evaluations; o[25] = S.status;
   }
 }
 
@@ -172,6 +476,7 @@ struct dmv_ct {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool staging_busy = false;  // an asynchronous upload from h_scratch may be in flight
   bool timing = false;  // CUDA-event timing of every evaluation (dmv_ct_set_timing); off by default: two event records per launch
   int w[DMV_MAX_PYR_LEVELS], h[DMV_MAX_PYR_LEVELS];
   float fx[DMV_MAX_PYR_LEVELS], fy[DMV_MAX_PYR_LEVELS], cx[DMV_MAX_PYR_LEVELS], cy[DMV_MAX_PYR_LEVELS];
@@ -184,6 +489,7 @@ struct dmv_ct {
   int n[DMV_MAX_PYR_LEVELS];
   double* d_partial = nullptr;
   unsigned int* d_ticket = nullptr;
+  unsigned int* d_bar = nullptr;   // grid-barrier counter of ct_track_kernel
   double* d_out = nullptr;
   double* h_out = nullptr;
   float* h_scratch = nullptr;
@@ -230,7 +536,8 @@ int dmv_ct_create(const dmv_ct_config* cfg, dmv_ct** out) {
   const size_t npx0 = (size_t)cfg->w * cfg->h;
   CK(cudaMalloc(&c->d_stage, npx0 * 3 * sizeof(float)));
   const int maxBlocks = (cfg->max_points + CT_THREADS - 1) / CT_THREADS;
-  CK(cudaMalloc(&c->d_partial, sizeof(double) * CT_NRED * maxBlocks));
+  CK(cudaMalloc(&c->d_partial, sizeof(double) * CT_NRED * maxBlocks * 2));  // x2: ct_track_kernel double-buffers the per-CTA partials
+  CK(cudaMalloc(&c->d_bar, sizeof(unsigned int)));
   CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
   CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
   CK(cudaMalloc(&c->d_out, sizeof(double) * 64));
@@ -247,7 +554,7 @@ int dmv_ct_destroy(dmv_ct* c) {
   for (int l = 0; l < DMV_MAX_PYR_LEVELS; l++) {
     cudaFree(c->d_img[l]); cudaFree(c->d_gray[l]); cudaFree(c->d_u[l]); cudaFree(c->d_v[l]); cudaFree(c->d_id[l]); cudaFree(c->d_col[l]);
   }
-  cudaFree(c->d_stage); cudaFree(c->d_partial); cudaFree(c->d_ticket); cudaFree(c->d_out);
+  cudaFree(c->d_stage); cudaFree(c->d_partial); cudaFree(c->d_ticket); cudaFree(c->d_bar); cudaFree(c->d_out);
   cudaFreeHost(c->h_out); cudaFreeHost(c->h_scratch);
   cudaEventDestroy(c->ev[0]); cudaEventDestroy(c->ev[1]);
   cudaStreamDestroy(c->stream);
@@ -272,6 +579,7 @@ int dmv_ct_set_ref(dmv_ct* c, int l, int n, const float* u, const float* v, cons
   CK(cudaSetDevice(c->device));
   c->n[l] = n;
   if (n > 0) {
+    if (c->staging_busy) { CK(cudaStreamSynchronize(c->stream)); c->staging_busy = false; }
     float* s = c->h_scratch;
     std::memcpy(s, u, 4 * (size_t)n); std::memcpy(s + n, v, 4 * (size_t)n); std::memcpy(s + 2 * (size_t)n, id, 4 * (size_t)n);
     std::memcpy(s + 3 * (size_t)n, col, 4 * (size_t)n);
@@ -288,6 +596,7 @@ int dmv_ct_upload_new(dmv_ct* c, int l, const float* dIp) {
   if (!c || !dIp || l < 0 || l >= c->cfg.levels) return set_error(DMV_ERR_INVALID, "bad level / pointer");
   CK(cudaSetDevice(c->device));
   const size_t npx = (size_t)c->w[l] * c->h[l];
+  if (c->staging_busy) { CK(cudaStreamSynchronize(c->stream)); c->staging_busy = false; }
   std::memcpy(c->h_scratch, dIp, npx * 3 * sizeof(float));
   CK(cudaMemcpyAsync(c->d_stage, c->h_scratch, npx * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   ct_repack_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, c->stream>>>(c->d_stage, c->d_img[l], (int)npx);
@@ -301,6 +610,7 @@ int dmv_ct_upload_new_image(dmv_ct* c, const float* image) {
   if (!c || !image) return set_error(DMV_ERR_INVALID, "null argument");
   CK(cudaSetDevice(c->device));
   const size_t npx = (size_t)c->w[0] * c->h[0];
+  if (c->staging_busy) { CK(cudaStreamSynchronize(c->stream)); c->staging_busy = false; }  // a previous upload may still read the staging buffer
   std::memcpy(c->h_scratch, image, npx * sizeof(float));
   CK(cudaMemcpyAsync(c->d_gray[0], c->h_scratch, npx * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   for (int l = 0; l < c->cfg.levels; l++) {
@@ -314,7 +624,9 @@ int dmv_ct_upload_new_image(dmv_ct* c, const float* image) {
     c->launches++;
   }
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(c->stream));
+  // no synchronisation: every consumer (dmv_ct_calc_res_gs / dmv_ct_track) runs on the same stream and synchronises itself; the image
+  // was copied into the handle's pinned staging buffer above, so the caller's buffer is already free
+  c->staging_busy = true;
   return DMV_OK;
 }
 
@@ -346,6 +658,7 @@ int dmv_ct_calc_res_gs(dmv_ct* c, int l, const float RKi[9], const float t[3], c
   if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
+  c->staging_busy = false;
   if (c->timing) cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
   const double* o = c->h_out;
   const double E = o[45], nE = o[46], nSat = o[47], nW = o[48];
@@ -370,6 +683,52 @@ int dmv_ct_calc_res_gs(dmv_ct* c, int l, const float RKi[9], const float t[3], c
       b[r] = M[r][8] * inv * sc[r];
     }
   }
+  return DMV_OK;
+}
+
+// CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:L539-770, visual-only branch) in one persistent launch
+int dmv_ct_track(dmv_ct* c, const dmv_ct_track_args* in, dmv_ct_track_result* out) {
+  if (!c || !in || !out) return set_error(DMV_ERR_INVALID, "null argument");
+  if (in->coarsestLvl < 0 || in->coarsestLvl >= c->cfg.levels || in->coarsestLvl >= 5) return set_error(DMV_ERR_INVALID, "coarsestLvl out of range");
+  CK(cudaSetDevice(c->device));
+  CTTrack T;
+  std::memset(&T, 0, sizeof(T));
+  T.levels = c->cfg.levels; T.coarsest = in->coarsestLvl;
+  int maxn = 1;
+  for (int l = 0; l < c->cfg.levels; l++) {
+    if (!c->haveK[l]) return set_error(DMV_ERR_STATE, "dmv_ct_set_K(level) first");
+    T.n[l] = c->n[l]; T.w[l] = c->w[l]; T.h[l] = c->h[l];
+    T.fx[l] = c->fx[l]; T.fy[l] = c->fy[l]; T.cx[l] = c->cx[l]; T.cy[l] = c->cy[l];
+    const float Kl[9] = {c->fx[l], 0.f, c->cx[l], 0.f, c->fy[l], c->cy[l], 0.f, 0.f, 1.f};
+    inv3_cofactor(Kl, T.Ki[l]);
+    T.u[l] = c->d_u[l]; T.v[l] = c->d_v[l]; T.id[l] = c->d_id[l]; T.col[l] = c->d_col[l]; T.img[l] = c->d_img[l];
+    if (l <= in->coarsestLvl) maxn = std::max(maxn, c->n[l]);
+  }
+  T.G = (maxn + CT_THREADS - 1) / CT_THREADS;
+  int dev_sms = 0;
+  CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device));
+  if (T.G > dev_sms) return set_error(DMV_ERR_INVALID, "%d reference points need %d co-resident CTAs, the device has %d SMs: use dmv_ct_calc_res_gs", maxn, T.G, dev_sms);
+  for (int i = 0; i < 9; i++) T.R0[i] = in->R[i];
+  for (int i = 0; i < 3; i++) T.t0[i] = in->t[i];
+  T.a0 = in->a; T.b0 = in->b; T.ref_a = in->ref_a; T.ref_b = in->ref_b;
+  T.ref_exposure = in->ref_exposure; T.new_exposure = in->new_exposure;
+  T.huber = c->huber; T.cutoffTH = in->coarseCutoffTH; T.affModeA = in->affineOptModeA; T.affModeB = in->affineOptModeB;
+  for (int i = 0; i < 5; i++) T.minRes[i] = in->minResForAbort[i];
+  T.partial = c->d_partial; T.bar = c->d_bar; T.out = c->h_out;
+  CK(cudaMemsetAsync(c->d_bar, 0, sizeof(unsigned int), c->stream));
+  void* args[] = {&T};
+  CK(cudaLaunchCooperativeKernel((void*)ct_track_kernel, dim3(T.G), dim3(CT_THREADS), args, 0, c->stream));  // co-residency of all CTAs guaranteed
+  c->launches++;
+  CK(cudaStreamSynchronize(c->stream));
+  c->staging_busy = false;
+  const double* o = c->h_out;
+  for (int i = 0; i < 9; i++) out->R[i] = o[i];
+  for (int i = 0; i < 3; i++) out->t[i] = o[9 + i];
+  out->a = o[12]; out->b = o[13];
+  for (int i = 0; i < 5; i++) out->lastResiduals[i] = o[14 + i];
+  for (int i = 0; i < 3; i++) out->flowIndicators[i] = o[19 + i];
+  out->trackingGood = (int)o[22]; out->iterations = (int)o[23]; out->evaluations = (int)o[24]; out->status = (int)o[25];
+  if (out->status == 1) return set_error(DMV_ERR_CUDA, "ct_track_kernel: grid barrier timed out");
   return DMV_OK;
 }
 

@@ -122,6 +122,28 @@ bool CoarseTracker::eval(int lvl, const SE3& refToNew, AffLight aff_g2l, float c
 bool CoarseTracker::trackNewestCoarse(SE3& lastToNew_out, AffLight& aff_g2l_out, int coarsestLvl, const double minResForAbort[5]) {
   // CoarseTracker.cpp:L539-770, visual-only branch.  calcRes and calcGSSSE are one launch: every evaluation returns the
   // residual statistics AND the Gauss-Newton system at that pose; H,b are adopted only when the step is accepted.
+  if (useDeviceLM) {
+    dmv_ct_track_args in;
+    for (int i = 0; i < 9; i++) in.R[i] = lastToNew_out.R[i];
+    for (int i = 0; i < 3; i++) in.t[i] = lastToNew_out.t[i];
+    in.a = aff_g2l_out.a; in.b = aff_g2l_out.b;
+    in.ref_a = lastRef_aff_g2l_.a; in.ref_b = lastRef_aff_g2l_.b;
+    in.ref_exposure = lastRef_ab_exposure_; in.new_exposure = newFrame_ab_exposure_;
+    in.coarseCutoffTH = s.setting_coarseCutoffTH; in.affineOptModeA = s.setting_affineOptModeA; in.affineOptModeB = s.setting_affineOptModeB;
+    in.coarsestLvl = coarsestLvl;
+    for (int i = 0; i < 5; i++) in.minResForAbort[i] = minResForAbort[i];
+    dmv_ct_track_result r;
+    if (dmv_ct_track(ct_, &in, &r) != DMV_OK) { err_ = dmv_last_error(); return false; }
+    for (int i = 0; i < 5; i++) lastResiduals[i] = r.lastResiduals[i];
+    for (int i = 0; i < 3; i++) lastFlowIndicators[i] = r.flowIndicators[i];
+    iterations = r.iterations;
+    evaluations = r.evaluations;
+    if (r.status != 0) return false;  // aborted inside the level loop: outputs untouched, like the reference's early return
+    for (int i = 0; i < 9; i++) lastToNew_out.R[i] = r.R[i];
+    for (int i = 0; i < 3; i++) lastToNew_out.t[i] = r.t[i];
+    aff_g2l_out.a = r.a; aff_g2l_out.b = r.b;
+    return r.trackingGood != 0;
+  }
   for (int i = 0; i < 5; i++) lastResiduals[i] = NAN;
   for (int i = 0; i < 3; i++) lastFlowIndicators[i] = 1000;
   const int maxIterations[] = {10, 20, 50, 50, 50};

@@ -32,6 +32,9 @@ class CoarseTracker {
   // CoarseTracker.cpp:L539-770 (visual-only branch L639-683)
   bool trackNewestCoarse(SE3& lastToNew_out, AffLight& aff_g2l_out, int coarsestLvl, const double minResForAbort[5]);
 
+  // true (default): the whole LM loop runs on the device in one persistent launch (dmv_ct_track); false: the loop below on the host,
+  // one fused calcRes+calcGSSSE launch per evaluation (dmv_ct_calc_res_gs)
+  bool useDeviceLM = true;
   double lastResiduals[5];
   double lastFlowIndicators[3];
   int pc_n[DMV_MAX_PYR_LEVELS];

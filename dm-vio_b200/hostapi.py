@@ -43,6 +43,7 @@ def lib():
         L.dmvh_ct_set_ref.argtypes = [vp, C.c_int, f32p, f32p, f32p, f32p, f32p, C.c_double, C.c_double, C.c_float]
         L.dmvh_ct_pc_n.argtypes = [vp, C.c_int]
         L.dmvh_ct_set_new_image.argtypes = [vp, f32p, C.c_float]
+        L.dmvh_ct_set_device_lm.argtypes = [vp, C.c_int]
         L.dmvh_ct_track.argtypes = [vp, f64p, f64p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, f64p, f64p, f64p, C.POINTER(C.c_int),
                                     C.POINTER(C.c_longlong)]
         _L = L
@@ -145,7 +146,8 @@ class CoarseTracker:
         if self.L.dmvh_ct_set_new_image(self.h, _c(img, np.float32).reshape(-1), exposure) != 0:
             raise capi.DmvError("dmvh_ct_set_new_image failed")
 
-    def track(self, R, t, a, b, coarsest=None, minRes=None):
+    def track(self, R, t, a, b, coarsest=None, minRes=None, device_lm=True):
+        self.L.dmvh_ct_set_device_lm(self.h, int(device_lm))
         R = _c(R, np.float64).reshape(-1).copy(); t = _c(t, np.float64).copy()
         ca, cb = C.c_double(a), C.c_double(b)
         its, ev = C.c_int(0), C.c_longlong(0)

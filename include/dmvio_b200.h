@@ -215,6 +215,30 @@ int dmv_ct_set_huber(dmv_ct* ct, float huberTH);
  * (divided by the 4-padded warped count, SCALE_* applied); n_warped = buf_warped_n (padded). */
 int dmv_ct_calc_res_gs(dmv_ct* ct, int level, const float RKi[9], const float t[3], const float affLL[2], float b0, float cutoffTH,
                        int want_gs, double res6[6], double H[64], double b[8], int* n_warped);
+/* CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:L539-770, visual-only branch L639-683) as ONE persistent launch: the whole
+ * Levenberg-Marquardt loop over the pyramid levels (calcRes + calcGSSSE per evaluation, 8x8 LDLT, SE3 update, accept/reject, cutoff
+ * doubling, level repeat) runs on the device; the host gets the tracked pose back.  Same semantics as driving dmv_ct_calc_res_gs from the
+ * host loop: R,t = lastToNew_out (refToNew, row-major), a,b = aff_g2l_out; on an aborted track (NaN residual or > 1.5*minResForAbort)
+ * trackingGood = 0, status = 2 and R,t,a,b are returned unchanged, like the reference's early `return false`.
+ * Needs all ceil(n/256) CTAs co-resident (n <= 148*256 reference points per level); otherwise DMV_ERR_INVALID. */
+typedef struct dmv_ct_track_args {
+  double R[9], t[3];          /* in: initial refToNew */
+  double a, b;                /* in: initial aff_g2l of the new frame */
+  double ref_a, ref_b;        /* lastRef_aff_g2l */
+  float ref_exposure, new_exposure; /* lastRef->ab_exposure, newFrame->ab_exposure */
+  float coarseCutoffTH;       /* setting_coarseCutoffTH = 20 */
+  float affineOptModeA, affineOptModeB;
+  int coarsestLvl;
+  double minResForAbort[5];   /* NaN = never abort */
+} dmv_ct_track_args;
+typedef struct dmv_ct_track_result {
+  double R[9], t[3], a, b;
+  double lastResiduals[5];    /* CoarseTracker::lastResiduals */
+  double flowIndicators[3];   /* CoarseTracker::lastFlowIndicators */
+  int trackingGood, iterations, evaluations, status;
+} dmv_ct_track_result;
+int dmv_ct_track(dmv_ct* ct, const dmv_ct_track_args* in, dmv_ct_track_result* out);
+
 /* enable/disable the CUDA-event timing of dmv_ct_calc_res_gs (off by default); dmv_ct_last_timing()[0] = kernel milliseconds */
 int dmv_ct_set_timing(dmv_ct* ct, int enable);
 int dmv_ct_last_timing(dmv_ct* ct, float ms[4]);

@@ -61,8 +61,9 @@ def test_device_pyramid_frames(hostapi, orc, synth):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("device_lm", [False, True], ids=["host_lm", "device_lm"])
 @pytest.mark.parametrize("levels", [4, 5])
-def test_track_newest_coarse(hostapi, orc, synth, levels):
+def test_track_newest_coarse(hostapi, orc, synth, levels, device_lm):
     T = synth.make_tracking_pair(seed=4321, levels=levels if levels == 5 else 0)
     oct_ = orc.CoarseTracker(T["w"], T["h"], T["K"], levels if levels == 5 else 0)
     oct_.make_coarse_depth(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
@@ -72,7 +73,8 @@ def test_track_newest_coarse(hostapi, orc, synth, levels):
     counts = g.set_ref(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
     assert counts == [len(oct_.ref_points(l)["u"]) for l in range(levels)]
     g.set_new_image(T["img_new"])
-    r_g = g.track(np.eye(3), np.zeros(3), 0.0, 0.0)
+    r_g = g.track(np.eye(3), np.zeros(3), 0.0, 0.0, device_lm=device_lm)
+    assert r_g["evaluations"] >= r_g["iterations"] >= levels
     assert r_g["good"] == r_o["good"]
     assert np.abs(r_g["R"] - r_o["R"]).max() < 2e-5
     assert np.abs(r_g["t"] - r_o["t"]).max() < 2e-5
