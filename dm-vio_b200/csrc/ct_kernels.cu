@@ -121,6 +121,28 @@ __device__ __forceinline__ double ct_block_reduce(const float v[CT_NRED], float 
   return s;
 }
 
+// fold of the per-CTA fp64 partials in a FIXED order with the loads in flight together: thread (q, k) adds quarter q of the CTAs for
+// entry k (independent loads, batches of 8), then thread k adds the four quarter sums.  A plain `for (bk) s += partial[bk]` loop issues
+// one L2 round trip per CTA (~0.35 us each, 13 us for 39 CTAs) because every add waits for its own load.
+__device__ __forceinline__ void ct_fold(const double* __restrict__ partial, int G, double (*s_q)[CT_NRED], double* s_sum) {
+  const int tid = threadIdx.x;
+  if (tid < 4 * CT_NRED) {
+    const int q = tid / CT_NRED, k = tid - q * CT_NRED;
+    const int per = (G + 3) >> 2, b0 = q * per, b1 = min(G, b0 + per);
+    double sm = 0.0;
+    for (int bk = b0; bk < b1; bk += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = (bk + u < b1) ? __ldcg(&partial[(size_t)(bk + u) * CT_NRED + k]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) sm += v[u];
+    }
+    s_q[q][k] = sm;
+  }
+  __syncthreads();
+  if (tid < CT_NRED) s_sum[tid] = ((s_q[0][tid] + s_q[1][tid]) + s_q[2][tid]) + s_q[3][tid];
+}
+
 __global__ void __launch_bounds__(CT_THREADS) ct_res_gs_kernel(CTParams P, const float* __restrict__ pc_u, const float* __restrict__ pc_v,
                                                                const float* __restrict__ pc_id, const float* __restrict__ pc_col,
                                                                const float4* __restrict__ img, double* __restrict__ partial,
@@ -140,13 +162,13 @@ __global__ void __launch_bounds__(CT_THREADS) ct_res_gs_kernel(CTParams P, const
     s_last = (tk == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last) {
+  if (s_last) {  // block-uniform
     __threadfence();
-    if (threadIdx.x < CT_NRED) {
-      double s = 0.0;
-      for (unsigned int bk = 0; bk < gridDim.x; bk++) s += __ldcg(&partial[(size_t)bk * CT_NRED + threadIdx.x]);
-      out[threadIdx.x] = s;
-    }
+    __shared__ double s_q[4][CT_NRED];
+    __shared__ double s_sum[CT_NRED];
+    ct_fold(partial, (int)gridDim.x, s_q, s_sum);
+    __syncthreads();
+    if (threadIdx.x < CT_NRED) out[threadIdx.x] = s_sum[threadIdx.x];
     if (threadIdx.x == 0) *ticket = 0u;
   }
 }
@@ -180,7 +202,8 @@ struct CTTrack {
 struct CTLM {  // the scalar state of trackNewestCoarse, one copy per CTA (shared memory), advanced by thread 0
   double R[9], t[3], a, b;          // refToNew_current, aff_g2l_current
   double Rn[9], tn[3], an, bn;      // candidate
-  double H[64], bb[8], resOld[6];
+  double H[2][64], bb[2][8], res[2][6];   // [cur]: linearisation at the current pose (resOld); [cur^1]: the evaluation that just finished
+  int cur;
   double inc[8];
   double lastResiduals[5], flow[3];
   float RKi[9], tf[3], affLL[2], cutoff;  // operands of the pending evaluation
@@ -212,23 +235,43 @@ __device__ __forceinline__ void ct_se3_exp_mul(const double xi[6], const double 
     to[i] = E[i * 3] * t[0] + E[i * 3 + 1] * t[1] + E[i * 3 + 2] * t[2] + et[i];
   }
 }
-__device__ __forceinline__ void ct_ldlt_solve(int n, const double* A, const double* b, double* x) {  // plain LDL^T, n <= 8, row-major
-  double L[64], D[8], y[8];
-  for (int i = 0; i < n * n; i++) L[i] = 0.0;
-  for (int j = 0; j < n; j++) {
-    double dj = A[j * n + j];
-    for (int k = 0; k < j; k++) dj -= L[j * n + k] * L[j * n + k] * D[k];
+// Hl.ldlt().solve(-b) for the 8x8 system (L639-665), plain LDL^T fully unrolled so that everything stays in registers.  A parameter
+// that is not optimised (setting_affineOptModeA/B < 0: the reference solves the 6x6 / 7x7 sub-system) is padded with an identity
+// row/column and a zero right-hand side: the extra terms are exact zeros, the other components come out bit-identical.
+__device__ __forceinline__ void ct_ldlt_solve8(const double* A, const double* b, double* x) {
+  double L[8][8], D[8], y[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    double dj = A[j * 8 + j];
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < j) dj -= L[j][k] * L[j][k] * D[k];
     D[j] = dj;
-    L[j * n + j] = 1.0;
-    for (int i = j + 1; i < n; i++) {
-      double sm = A[i * n + j];
-      for (int k = 0; k < j; k++) sm -= L[i * n + k] * L[j * n + k] * D[k];
-      L[i * n + j] = dj != 0.0 ? sm / dj : 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (i > j) {
+        double sm = A[i * 8 + j];
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (k < j) sm -= L[i][k] * L[j][k] * D[k];
+        L[i][j] = dj != 0.0 ? sm / dj : 0.0;
+      }
     }
   }
-  for (int i = 0; i < n; i++) { double sm = b[i]; for (int k = 0; k < i; k++) sm -= L[i * n + k] * y[k]; y[i] = sm; }
-  for (int i = 0; i < n; i++) y[i] = D[i] != 0.0 ? y[i] / D[i] : 0.0;
-  for (int i = n - 1; i >= 0; i--) { double sm = y[i]; for (int k = i + 1; k < n; k++) sm -= L[k * n + i] * x[k]; x[i] = sm; }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    double sm = b[i];
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < i) sm -= L[i][k] * y[k];
+    y[i] = sm;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) y[i] = D[i] != 0.0 ? y[i] / D[i] : 0.0;
+#pragma unroll
+  for (int i = 7; i >= 0; i--) {
+    double sm = y[i];
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k > i) sm -= L[k][i] * x[k];
+    x[i] = sm;
+  }
 }
 // operands of calcRes for a pose (CoarseTracker.cpp:L377-379): RKi = R.cast<float>() * Ki[lvl], t.cast<float>(), affLL.cast<float>()
 __device__ __forceinline__ void ct_request(const CTTrack& T, CTLM& S, const double R[9], const double t[3], double a, double b) {
@@ -246,24 +289,28 @@ __device__ __forceinline__ void ct_request(const CTTrack& T, CTLM& S, const doub
   S.cutoff = T.cutoffTH * S.rep;
   S.evaluations++;
 }
-// Vec6 of calcRes (L508-516) and H, b of calcGSSSE (L341-355) from the 53 folded sums
-__device__ __forceinline__ void ct_finish(const double* o, double res6[6], double H[64], double b[8]) {
-  const double E = o[45], nE = o[46], nSat = o[47], nW = o[48];
-  res6[0] = E; res6[1] = nE;
-  res6[2] = (double)((float)o[49] / ((float)o[51] + 0.1f));
-  res6[3] = 0;
-  res6[4] = (double)((float)o[50] / ((float)o[51] + 0.1f));
-  res6[5] = (double)((float)nSat / (float)nE);
-  const int npad = ((int)nW + 3) & ~3;
-  double M[9][9];
-  int e = 0;
-  for (int r = 0; r < 9; r++)
-    for (int c = r; c < 9; c++) { M[r][c] = M[c][r] = o[e]; e++; }
+// Vec6 of calcRes (L508-516) and H, b of calcGSSSE (L341-355) from the 53 folded sums, one output per thread (tid < 78)
+__device__ __forceinline__ void ct_finish_parallel(const double* o, double* res6, double* H, double* b, int tid) {
+  const int npad = ((int)o[48] + 3) & ~3;
   const double inv = (double)(1.0f / (float)npad);
-  const double sc[8] = {1, 1, 1, 1, 1, 1, 10.0, 1000.0};
-  for (int r = 0; r < 8; r++) {
-    for (int c = 0; c < 8; c++) H[r * 8 + c] = M[r][c] * inv * sc[r] * sc[c];
-    b[r] = M[r][8] * inv * sc[r];
+  if (tid < 72) {
+    const int r = tid >> 3, c = (tid < 64) ? (tid & 7) : 8;   // tid 64..71: r = 8 -> handled below as the b column
+    const int rr = (tid < 64) ? r : (tid - 64);
+    const int lo = rr < c ? rr : c, hi = rr < c ? c : rr;
+    const int e = lo * 9 - (lo * (lo - 1)) / 2 + (hi - lo);     // upper-triangular index of the 9x9 accumulator
+    const double scr = (rr == 6) ? 10.0 : (rr == 7 ? 1000.0 : 1.0);
+    if (tid < 64) {
+      const double scc = (c == 6) ? 10.0 : (c == 7 ? 1000.0 : 1.0);
+      H[rr * 8 + c] = o[e] * inv * scr * scc;
+    } else {
+      b[rr] = o[e] * inv * scr;
+    }
+  } else if (tid == 72) {
+    res6[0] = o[45]; res6[1] = o[46];
+    res6[2] = (double)((float)o[49] / ((float)o[51] + 0.1f));
+    res6[3] = 0;
+    res6[4] = (double)((float)o[50] / ((float)o[51] + 0.1f));
+    res6[5] = (double)((float)o[47] / (float)o[46]);
   }
 }
 __device__ void ct_begin_level(const CTTrack& T, CTLM& S) {
@@ -274,44 +321,53 @@ __device__ void ct_begin_level(const CTTrack& T, CTLM& S) {
 // one LM trial step from the current linearisation (L605-683)
 __device__ void ct_propose(const CTTrack& T, CTLM& S) {
   S.iterations++;
-  double Hl[64];
-  for (int i = 0; i < 64; i++) Hl[i] = S.H[i];
-  for (int i = 0; i < 8; i++) Hl[i * 8 + i] *= (1 + S.lambda);
+  const double* Hc = S.H[S.cur];
+  const double* bc = S.bb[S.cur];
+  const bool fixA = T.affModeA < 0, fixB = T.affModeB < 0;
+  double A[64], rhs[8], inc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const bool fi = (i == 6 && fixA) || (i == 7 && fixB);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const bool fj = (j == 6 && fixA) || (j == 7 && fixB);
+      double vv = Hc[i * 8 + j];
+      if (i == j) vv *= (1 + S.lambda);
+      A[i * 8 + j] = (fi || fj) ? ((i == j) ? 1.0 : 0.0) : vv;
+    }
+    rhs[i] = fi ? 0.0 : -bc[i];
+  }
+  ct_ldlt_solve8(A, rhs, inc);
   float extrapFac = 1;
   const float lambdaExtrapolationLimit = 0.001f;
   if (S.lambda < lambdaExtrapolationLimit) extrapFac = sqrtf(sqrtf(lambdaExtrapolationLimit / S.lambda));
-  double inc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  {
-    int map[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-    int n = 8;
-    const bool fixA = T.affModeA < 0, fixB = T.affModeB < 0;
-    if (fixA && fixB) n = 6;
-    else if (!fixA && fixB) n = 7;
-    else if (fixA && !fixB) { n = 7; map[6] = 7; }
-    double A[64], rhs[8], x[8];
-    for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) A[i * n + j] = Hl[map[i] * 8 + map[j]]; rhs[i] = -S.bb[map[i]]; }
-    ct_ldlt_solve(n, A, rhs, x);
-    for (int i = 0; i < n; i++) inc[map[i]] = x[i];
-  }
+#pragma unroll
   for (int i = 0; i < 8; i++) inc[i] *= extrapFac;
   double incScaled[8];
+#pragma unroll
   for (int i = 0; i < 8; i++) incScaled[i] = inc[i];
   incScaled[6] *= 10.0;    // SCALE_A
   incScaled[7] *= 1000.0;  // SCALE_B
   double ssum = 0;
+#pragma unroll
   for (int i = 0; i < 8; i++) ssum += incScaled[i];
-  if (!isfinite(ssum)) for (int i = 0; i < 8; i++) incScaled[i] = 0;
+  if (!isfinite(ssum)) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) incScaled[i] = 0;
+  }
   ct_se3_exp_mul(incScaled, S.R, S.t, S.Rn, S.tn);
   S.an = S.a + incScaled[6];
   S.bn = S.b + incScaled[7];
+#pragma unroll
   for (int i = 0; i < 8; i++) S.inc[i] = inc[i];
   S.phase = CT_PH_LM;
   ct_request(T, S, S.Rn, S.tn, S.an, S.bn);
 }
 __device__ void ct_end_level(const CTTrack& T, CTLM& S) {  // L722-745
   const int lvl = S.lvl;
-  S.lastResiduals[lvl] = sqrtf((float)(S.resOld[0] / S.resOld[1]));
-  S.flow[0] = S.resOld[2]; S.flow[1] = S.resOld[3]; S.flow[2] = S.resOld[4];
+  const double* resOld = S.res[S.cur];
+  S.lastResiduals[lvl] = sqrtf((float)(resOld[0] / resOld[1]));
+  S.flow[0] = resOld[2]; S.flow[1] = resOld[3]; S.flow[2] = resOld[4];
   if (isnan(S.lastResiduals[lvl]) || S.lastResiduals[lvl] > 1.5 * T.minRes[lvl]) { S.done = 1; S.good = 0; S.status = 2; return; }
   if (S.rep > 1 && !S.haveRepeated) { S.haveRepeated = 1; ct_begin_level(T, S); return; }  // lvl++ ; continue  => the same level again
   S.lvl = lvl - 1;
@@ -330,16 +386,14 @@ __device__ void ct_end_level(const CTTrack& T, CTLM& S) {  // L722-745
   }
   ct_begin_level(T, S);
 }
-// thread 0: consume the folded sums of the evaluation that just finished and decide what to evaluate next
-__device__ void ct_advance(const CTTrack& T, CTLM& S, const double* red) {
+// thread 0: the evaluation that just finished sits in S.res/H/bb[cur^1] (ct_finish_parallel); decide what to evaluate next
+__device__ void ct_advance(const CTTrack& T, CTLM& S) {
   const int maxIterations[5] = {10, 20, 50, 50, 50};
-  double res[6], Hn[64], bn[8];
-  ct_finish(red, res, Hn, bn);
+  const int nw = S.cur ^ 1;
+  const double* res = S.res[nw];
   if (S.phase == CT_PH_INIT) {  // L566-578: first evaluation of a level, cutoff doubling while too many residuals saturate
-    for (int i = 0; i < 6; i++) S.resOld[i] = res[i];
-    for (int i = 0; i < 64; i++) S.H[i] = Hn[i];
-    for (int i = 0; i < 8; i++) S.bb[i] = bn[i];
-    if (S.resOld[5] > 0.6 && (S.rep < 50 || S.resOld[5] > 0.99)) { S.rep *= 2; ct_request(T, S, S.R, S.t, S.a, S.b); return; }
+    S.cur = nw;                 // this evaluation becomes the current linearisation (resOld, H, b)
+    if (res[5] > 0.6 && (S.rep < 50 || res[5] > 0.99)) { S.rep *= 2; ct_request(T, S, S.R, S.t, S.a, S.b); return; }
     S.lambda = 0.01f;
     S.iteration = 0;
     if (S.iteration >= maxIterations[S.lvl]) { ct_end_level(T, S); return; }
@@ -347,11 +401,10 @@ __device__ void ct_advance(const CTTrack& T, CTLM& S, const double* red) {
     return;
   }
   // CT_PH_LM: accept / reject (L686-716)
-  const bool accept = (res[0] / res[1]) < (S.resOld[0] / S.resOld[1]);
+  const double* resOld = S.res[S.cur];
+  const bool accept = (res[0] / res[1]) < (resOld[0] / resOld[1]);
   if (accept) {
-    for (int i = 0; i < 64; i++) S.H[i] = Hn[i];
-    for (int i = 0; i < 8; i++) S.bb[i] = bn[i];
-    for (int i = 0; i < 6; i++) S.resOld[i] = res[i];
+    S.cur = nw;  // calcGSSSE at the accepted pose == the H,b of the evaluation that just finished
     S.a = S.an; S.b = S.bn;
     for (int i = 0; i < 9; i++) S.R[i] = S.Rn[i];
     for (int i = 0; i < 3; i++) S.t[i] = S.tn[i];
@@ -371,6 +424,7 @@ __device__ void ct_advance(const CTTrack& T, CTLM& S, const double* red) {
 __global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_constant__ CTTrack T) {
   __shared__ float s_red[CT_THREADS / 32][CT_NRED];
   __shared__ double s_sum[CT_NRED];
+  __shared__ double s_q[4][CT_NRED];
   __shared__ CTLM S;
   const int tid = threadIdx.x;
   const int G = T.G;
@@ -382,7 +436,7 @@ __global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_const
     S.a = T.a0; S.b = T.b0;
     for (int i = 0; i < 5; i++) S.lastResiduals[i] = __longlong_as_double(0x7ff8000000000000ll);  // NAN
     for (int i = 0; i < 3; i++) S.flow[i] = 1000;
-    S.haveRepeated = 0; S.iterations = 0; S.evaluations = 0; S.done = 0; S.good = 0; S.status = 0;
+    S.haveRepeated = 0; S.iterations = 0; S.evaluations = 0; S.done = 0; S.good = 0; S.status = 0; S.cur = 0;
     S.lvl = T.coarsest;
     ct_begin_level(T, S);
   }
@@ -421,14 +475,12 @@ __global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_const
     __syncthreads();
     if (S.status == 1) break;
     // ---- every CTA folds the partials in CTA order (bit-identical sums everywhere) and advances the same state machine
-    if (tid < CT_NRED) {
-      double sm = 0.0;
-      for (int bk = 0; bk < G; bk++) sm += __ldcg(&T.partial[((size_t)par * G + bk) * CT_NRED + tid]);
-      s_sum[tid] = sm;
-    }
+    ct_fold(T.partial + (size_t)par * G * CT_NRED, G, s_q, s_sum);
     par ^= 1;
     __syncthreads();
-    if (tid == 0) ct_advance(T, S, s_sum);
+    ct_finish_parallel(s_sum, S.res[S.cur ^ 1], S.H[S.cur ^ 1], S.bb[S.cur ^ 1], tid);
+    __syncthreads();
+    if (tid == 0) ct_advance(T, S);
     __syncthreads();
   }
   if (blockIdx.x == 0 && tid == 0) {
