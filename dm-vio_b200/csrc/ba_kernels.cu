@@ -145,13 +145,22 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_cons
     // calibration rows and the next iteration's accumulators
     const int nacc = acc_doubles(nf, W.ntiles);
     for (int i = tid; i < nacc; i += ST_THREADS) W.acc_next[i] = 0.0;
-    if (tid < 20) {
-      const int i = tid / 5, j = tid - i * 5;
-      double v = 0.0;
+    if (tid < 20 * 8) {  // 20 outputs x 8 lanes: a plain `v += TS[pr]` loop issues one dependent L2 round trip per pair (49 x ~0.3 us)
+      const int o = tid >> 3, part = tid & 7;
+      const int i = o / 5, j = o - i * 5;
       const int c = (j < 4) ? j : 12;
-      const int rr = i < c ? i : c, cc = i < c ? c : i;  // rows 0..3 are stored in full: entry (rr, cc) with rr <= cc
-      for (int pr = 0; pr < nf * nf; pr++) v += __ldcg(TS + (size_t)pr * TOP_PART + top_off(rr) + cc - rr);
-      if (j < 4) R[(size_t)i * N + j] = v; else R[(size_t)N * N + i] = v;
+      const int rr = i < c ? i : c, cc = i < c ? c : i;  // packed upper-triangular storage: entry (rr, cc) with rr <= cc
+      const double* src = TS + top_off(rr) + cc - rr;
+      double x[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const int pr = part + 8 * u; x[u] = (pr < nf * nf) ? __ldcg(src + (size_t)pr * TOP_PART) : 0.0; }
+      double v = 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) v += x[u];   // MAXF*MAXF = 64 pairs = 8 lanes x 8
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (part == 0) { if (j < 4) R[(size_t)i * N + j] = v; else R[(size_t)N * N + i] = v; }
     }
   } else {
   for (int e = tid; e < nf * (TOP_PART / 2); e += ST_THREADS) {

@@ -35,3 +35,4 @@ for flush in (True, False):
         prev = k
     print(f"  stitch (ns rel. to first point-CTA start, mean/max over {len(ts)} CTAs): resident {np.mean(ts[:,0]-t0):.0f}/{np.max(ts[:,0]-t0)}, dependency released {np.mean(ts[:,1]-t0):.0f}/{np.max(ts[:,1]-t0)}, "
           f"staged {np.mean(ts[:-1,2]-t0):.0f}/{np.max(ts[:-1,2]-t0)}, products done {np.mean(ts[:-1,3]-t0):.0f}/{np.max(ts[:-1,3]-t0)}, written {np.mean(ts[:-1,4]-t0):.0f}/{np.max(ts[:-1,4]-t0)}")
+    print(f"  stitch CTA nf (calibration rows + tiles share): released {ts[-1,1]-t0}, done {ts[-1,4]-t0}")
