@@ -10,6 +10,7 @@
 #include "../../include/dmvio_b200.h"
 #include "common_host.h"
 #include "inv3.h"
+#include "ip_trace.h"
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -545,6 +546,9 @@ struct dmv_ct {
   double* d_out = nullptr;
   double* h_out = nullptr;
   float* h_scratch = nullptr;
+  float* d_ip = nullptr;   // immature-point arrays (dmv_ct_trace_points)
+  float* h_ip = nullptr;
+  int ip_cap = 0;
   float huber = 9.f;
   long long launches = 0;
   float last_ms[4] = {0, 0, 0, 0};
@@ -607,7 +611,7 @@ int dmv_ct_destroy(dmv_ct* c) {
     cudaFree(c->d_img[l]); cudaFree(c->d_gray[l]); cudaFree(c->d_u[l]); cudaFree(c->d_v[l]); cudaFree(c->d_id[l]); cudaFree(c->d_col[l]);
   }
   cudaFree(c->d_stage); cudaFree(c->d_partial); cudaFree(c->d_ticket); cudaFree(c->d_bar); cudaFree(c->d_out);
-  cudaFreeHost(c->h_out); cudaFreeHost(c->h_scratch);
+  cudaFreeHost(c->h_out); cudaFreeHost(c->h_scratch); cudaFree(c->d_ip); cudaFreeHost(c->h_ip);
   cudaEventDestroy(c->ev[0]); cudaEventDestroy(c->ev[1]);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -781,6 +785,57 @@ int dmv_ct_track(dmv_ct* c, const dmv_ct_track_args* in, dmv_ct_track_result* ou
   for (int i = 0; i < 3; i++) out->flowIndicators[i] = o[19 + i];
   out->trackingGood = (int)o[22]; out->iterations = (int)o[23]; out->evaluations = (int)o[24]; out->status = (int)o[25];
   if (out->status == 1) return set_error(DMV_ERR_CUDA, "ct_track_kernel: grid barrier timed out");
+  return DMV_OK;
+}
+
+void dmv_ip_default_settings(dmv_ip_settings* s) {
+  s->maxPixSearch = 0.027f; s->trace_stepsize = 1.0f; s->trace_GNThreshold = 0.1f; s->trace_extraSlackOnTH = 1.2f; s->trace_slackInterval = 1.5f;
+  s->trace_minImprovementFactor = 2.f; s->huberTH = 9.f; s->trace_GNIterations = 3; s->minTraceTestRadius = 2;
+}
+
+// one host frame's immature points traced against the resident newest frame (ip_trace.cu)
+int dmv_ct_trace_points(dmv_ct* c, const dmv_ip_points* p, const float KRKi[9], const float Kt[3], const float aff[2], const dmv_ip_settings* settings) {
+  if (!c || !p || !KRKi || !Kt || !aff) return set_error(DMV_ERR_INVALID, "null argument");
+  if (p->n < 0 || (p->n > 0 && (!p->u || !p->v || !p->color8 || !p->weights8 || !p->gradH4 || !p->energyTH || !p->idepth_min || !p->idepth_max || !p->quality ||
+                                !p->lastTraceStatus || !p->lastTraceUV2 || !p->lastTracePixelInterval)))
+    return set_error(DMV_ERR_INVALID, "incomplete dmv_ip_points");
+  if (p->n == 0) return DMV_OK;
+  CK(cudaSetDevice(c->device));
+  const int n = p->n;
+  if (n > c->ip_cap) {  // device + pinned staging: 23 read-only floats and 7 in/out words per point
+    if (c->d_ip) cudaFree(c->d_ip);
+    if (c->h_ip) cudaFreeHost(c->h_ip);
+    c->ip_cap = std::max(n, 2048);
+    CK(cudaMalloc(&c->d_ip, sizeof(float) * 30 * c->ip_cap));
+    CK(cudaMallocHost(&c->h_ip, sizeof(float) * 30 * c->ip_cap));
+  }
+  if (c->staging_busy) { CK(cudaStreamSynchronize(c->stream)); c->staging_busy = false; }
+  const size_t cap = c->ip_cap;
+  float* hb = c->h_ip;
+  // layout (floats): u | v | color*8 | weights*8 | gradH*4 | energyTH | idmin | idmax | quality | status(int) | uv*2 | interval
+  const size_t o_u = 0, o_v = cap, o_col = 2 * cap, o_wgt = 10 * cap, o_g = 18 * cap, o_eth = 22 * cap, o_min = 23 * cap, o_max = 24 * cap, o_q = 25 * cap,
+               o_st = 26 * cap, o_uv = 27 * cap, o_iv = 29 * cap;
+  std::memcpy(hb + o_u, p->u, 4 * n); std::memcpy(hb + o_v, p->v, 4 * n);
+  std::memcpy(hb + o_col, p->color8, 32 * (size_t)n); std::memcpy(hb + o_wgt, p->weights8, 32 * (size_t)n);
+  std::memcpy(hb + o_g, p->gradH4, 16 * (size_t)n); std::memcpy(hb + o_eth, p->energyTH, 4 * n);
+  std::memcpy(hb + o_min, p->idepth_min, 4 * n); std::memcpy(hb + o_max, p->idepth_max, 4 * n); std::memcpy(hb + o_q, p->quality, 4 * n);
+  std::memcpy(hb + o_st, p->lastTraceStatus, 4 * n); std::memcpy(hb + o_uv, p->lastTraceUV2, 8 * (size_t)n); std::memcpy(hb + o_iv, p->lastTracePixelInterval, 4 * n);
+  CK(cudaMemcpyAsync(c->d_ip, hb, sizeof(float) * 30 * cap, cudaMemcpyHostToDevice, c->stream));
+  IPTraceArgs A;
+  A.n = n; A.w = c->w[0]; A.h = c->h[0];
+  std::memcpy(A.KRKi, KRKi, sizeof(A.KRKi)); std::memcpy(A.Kt, Kt, sizeof(A.Kt)); std::memcpy(A.aff, aff, sizeof(A.aff));
+  if (settings) A.s = *settings; else dmv_ip_default_settings(&A.s);
+  float* d = c->d_ip;
+  A.u = d + o_u; A.v = d + o_v; A.color = d + o_col; A.weights = d + o_wgt; A.gradH = d + o_g; A.energyTH = d + o_eth;
+  A.idepth_min = d + o_min; A.idepth_max = d + o_max; A.quality = d + o_q; A.status = reinterpret_cast<int*>(d + o_st); A.uv = d + o_uv; A.interval = d + o_iv;
+  A.img = c->d_img[0];
+  launch_ip_trace(A, c->stream);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(hb + o_min, d + o_min, sizeof(float) * 7 * cap, cudaMemcpyDeviceToHost, c->stream));  // the 7 in/out words per point
+  CK(cudaStreamSynchronize(c->stream));
+  std::memcpy(p->idepth_min, hb + o_min, 4 * n); std::memcpy(p->idepth_max, hb + o_max, 4 * n); std::memcpy(p->quality, hb + o_q, 4 * n);
+  std::memcpy(p->lastTraceStatus, hb + o_st, 4 * n); std::memcpy(p->lastTraceUV2, hb + o_uv, 8 * (size_t)n); std::memcpy(p->lastTracePixelInterval, hb + o_iv, 4 * n);
   return DMV_OK;
 }
 

@@ -150,3 +150,21 @@ def prior_system(W, state=None, cPrior=5e9, initialTransPrior=1e10, initialRotPr
         HL[idx, idx] += p
         bL[idx] += p * state[f, :8]
     return HL, bL
+
+
+def trace_tables(W, host, new, state=None):
+    """Operands of ImmaturePoint::traceOn as FullSystem::traceNewCoarse builds them (FullSystem.cpp:L548-561), in the reference's
+    float operation order: KRKi = K * R.cast<float>() * K.inverse(), Kt = K * t.cast<float>(), aff = fromToVecExposure(...).cast<float>()."""
+    state = W["state"] if state is None else state
+    k8 = calib8(W["K"])
+    K = np.zeros((3, 3), np.float32)
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[2, 2] = k8[0], k8[1], k8[2], k8[3], 1
+    Ki = inv3_cofactor_f32(K)
+    cur = frame_poses(W, state)
+    Rhi, thi = se3_inv(*cur[host])
+    R, t = se3_mul(cur[new][0], cur[new][1], Rhi, thi)
+    KRKi = mm3_f32(mm3_f32(K, R.astype(np.float32)), Ki)
+    Kt = mm3_f32(K, t.astype(np.float32).reshape(3, 1)).reshape(-1)
+    a, b = aff_from_to(W["exposure"][host], W["exposure"][new], state[host, 6] * SCALE_A, state[host, 7] * SCALE_B, state[new, 6] * SCALE_A,
+                       state[new, 7] * SCALE_B)
+    return KRKi, Kt, np.array([a, b], np.float32)

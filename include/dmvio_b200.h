@@ -239,6 +239,39 @@ typedef struct dmv_ct_track_result {
 } dmv_ct_track_result;
 int dmv_ct_track(dmv_ct* ct, const dmv_ct_track_args* in, dmv_ct_track_result* out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Immature-point tracing  ==  ImmaturePoint::traceOn (FullSystem/ImmaturePoint.cpp:L77-437) for all immature points of ONE host
+ * frame against the newest frame, i.e. one iteration of the host loop of FullSystem::traceNewCoarse (FullSystem.cpp:L554-575).
+ * Runs on the coarse-tracker handle: the frame traced against is the one last given to dmv_ct_upload_new_image / dmv_ct_upload_new
+ * (level 0), which is resident there anyway.  Results are BIT-IDENTICAL to the reference's CPU code (the kernel is compiled without
+ * FMA contraction and keeps the reference's operation order).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dmv_ip_settings {   /* util/settings.cpp:L79, L178-187 */
+  float maxPixSearch;              /* setting_maxPixSearch = 0.027 */
+  float trace_stepsize;            /* 1.0 */
+  float trace_GNThreshold;         /* 0.1 */
+  float trace_extraSlackOnTH;      /* 1.2 */
+  float trace_slackInterval;       /* 1.5 */
+  float trace_minImprovementFactor;/* 2 */
+  float huberTH;                   /* setting_huberTH = 9 */
+  int trace_GNIterations;          /* 3 */
+  int minTraceTestRadius;          /* 2 */
+} dmv_ip_settings;
+void dmv_ip_default_settings(dmv_ip_settings* s);
+/* ImmaturePoint fields (ImmaturePoint.h:L56-90), structure of arrays over the n points of one host frame.
+ * in: u, v, color[8], weights[8], gradH (Mat22f row-major), energyTH.   in/out: idepth_min, idepth_max, quality,
+ * lastTraceStatus (ImmaturePointStatus: 0 GOOD, 1 OOB, 2 OUTLIER, 3 SKIPPED, 4 BADCONDITION, 5 UNINITIALIZED), lastTraceUV, lastTracePixelInterval. */
+typedef struct dmv_ip_points {
+  int n;
+  const float *u, *v, *color8, *weights8, *gradH4, *energyTH;
+  float *idepth_min, *idepth_max, *quality;
+  int32_t* lastTraceStatus;
+  float *lastTraceUV2, *lastTracePixelInterval;
+} dmv_ip_points;
+/* hostToFrame_KRKi (row-major 3x3), hostToFrame_Kt, hostToFrame_affine exactly as traceNewCoarse computes them (FullSystem.cpp:L557-561).
+ * settings may be NULL (defaults). */
+int dmv_ct_trace_points(dmv_ct* ct, const dmv_ip_points* pts, const float KRKi[9], const float Kt[3], const float aff[2], const dmv_ip_settings* settings);
+
 /* enable/disable the CUDA-event timing of dmv_ct_calc_res_gs (off by default); dmv_ct_last_timing()[0] = kernel milliseconds */
 int dmv_ct_set_timing(dmv_ct* ct, int enable);
 int dmv_ct_last_timing(dmv_ct* ct, float ms[4]);

@@ -90,6 +90,8 @@ def _declare(L):
     L.orc_ct_get_warped.argtypes = [vp, vp]
     L.orc_ct_calc_gs.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_int, f64p, f64p]
     L.orc_ct_track.argtypes = [vp, f64p, f64p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, f64p, C.c_int, f64p, f64p, C.POINTER(C.c_int)]
+    L.orc_ip_init.argtypes = [C.c_int, f32p, C.c_int, C.c_int, i32p, i32p, f32p, f32p, f32p, f32p, u8p]
+    L.orc_ip_trace.argtypes = [C.c_int, f32p, C.c_int, C.c_int, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, i32p, f32p, f32p]
     L.orc_se3_exp.argtypes = [f64p, f64p, f64p]
     L.orc_se3_log.argtypes = [f64p, f64p, f64p]
     return L
@@ -318,3 +320,33 @@ class CoarseTracker:
         good = self.L.orc_ct_track(self.hd, R, t, C.byref(ca), C.byref(cb), self.levels - 1 if coarsest is None else coarsest, mr, precision,
                                    lastRes, flow, C.byref(its))
         return dict(good=bool(good), R=R.reshape(3, 3), t=t, a=ca.value, b=cb.value, lastResiduals=lastRes, flow=flow, iterations=its.value)
+
+
+# ---- immature points: ImmaturePoint constructor + traceOn
+IP_STATE_KEYS = ("idepth_min", "idepth_max", "quality", "status", "lastTraceUV", "lastTracePixelInterval")
+
+
+def ip_init(dI_host, w, h, u, v, _fn=None):
+    """ImmaturePoint constructor for integer pixels (u, v) of the host frame -> dict of per-point arrays (fresh trace state included)."""
+    n = len(u)
+    c = lambda a, t: np.ascontiguousarray(a, t)
+    P = dict(u=c(u, np.float32), v=c(v, np.float32), color=np.zeros((n, 8), np.float32), weights=np.zeros((n, 8), np.float32),
+             gradH=np.zeros((n, 4), np.float32), energyTH=np.zeros(n, np.float32), ok=np.zeros(n, np.uint8))
+    fn = _fn or (lambda *a: lib().orc_ip_init(*a))
+    fn(n, c(dI_host, np.float32).reshape(-1), w, h, c(u, np.int32), c(v, np.int32), P["color"], P["weights"], P["gradH"], P["energyTH"], P["ok"])
+    P.update(idepth_min=np.zeros(n, np.float32), idepth_max=np.full(n, np.nan, np.float32), quality=np.full(n, 10000, np.float32),
+             status=np.full(n, 5, np.int32), lastTraceUV=np.zeros((n, 2), np.float32), lastTracePixelInterval=np.zeros(n, np.float32))
+    return P
+
+
+def ip_trace(P, dI, w, h, KRKi, Kt, aff, _fn=None):
+    """ImmaturePoint::traceOn for every point of P against the frame dI; returns the updated state (P is not modified)."""
+    c = lambda a, t: np.ascontiguousarray(a, t)
+    out = {k: np.array(P[k], copy=True) for k in IP_STATE_KEYS}
+    fn = _fn or (lambda *a: lib().orc_ip_trace(*a))
+    fn(len(P["u"]), c(dI, np.float32).reshape(-1), w, h, c(KRKi, np.float32).reshape(-1), c(Kt, np.float32), c(aff, np.float32), P["u"], P["v"],
+       P["color"], P["weights"], P["gradH"], P["energyTH"], out["idepth_min"], out["idepth_max"], out["quality"], out["status"], out["lastTraceUV"],
+       out["lastTracePixelInterval"])
+    Q = dict(P)
+    Q.update(out)
+    return Q

@@ -76,6 +76,9 @@ def lib():
         L.ref_make_images.restype = C.c_int64
         L.ref_make_images.argtypes = [C.c_int, C.c_int, f64p, f32p, f32p, vp]
         L.ref_init_point.argtypes = [f32p, C.c_int, C.c_int, f64p, C.c_float, C.c_float, f32p, f32p]
+        L.ref_ip_init.argtypes = [C.c_int, f32p, C.c_int, C.c_int, f64p, i32p, i32p, f32p, f32p, f32p, f32p, u8p]
+        L.ref_ip_trace.argtypes = [C.c_int, f32p, C.c_int, C.c_int, f64p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, i32p, f32p,
+                                   f32p]
         L.ref_ct_create.restype = vp
         L.ref_ct_create.argtypes = [C.c_int, C.c_int, f64p]
         L.ref_ct_destroy.argtypes = [vp]
@@ -148,3 +151,13 @@ class CoarseTracker(orc.CoarseTracker):
             self._ref.ref_ct_destroy(self.hd)
         except Exception:
             pass
+
+
+def ip_init(dI_host, w, h, K, u, v):
+    K = np.ascontiguousarray(K, np.float64)
+    return orc.ip_init(dI_host, w, h, u, v, _fn=lambda n, dI, w_, h_, *rest: lib().ref_ip_init(n, dI, w_, h_, K, *rest))
+
+
+def ip_trace(P, dI, w, h, K, KRKi, Kt, aff):
+    K = np.ascontiguousarray(K, np.float64)
+    return orc.ip_trace(P, dI, w, h, KRKi, Kt, aff, _fn=lambda n, dI_, w_, h_, *rest: lib().ref_ip_trace(n, dI_, w_, h_, K, *rest))

@@ -603,3 +603,62 @@ int ref_ct_track(RefCT* C, double R[9], double t[3], double* a, double* b, int c
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Immature points: the reference's ImmaturePoint constructor and ImmaturePoint::traceOn (FullSystem/ImmaturePoint.cpp)
+// =====================================================================================================================
+namespace {
+FrameHessian* frame_with_dI(const float* dI, int w, int h) {
+  FrameHessian* fh = blank_frame(0);
+  for (int i = 0; i < w * h; i++) fh->dIp[0][i] = Eigen::Vector3f(dI[3 * i], dI[3 * i + 1], dI[3 * i + 2]);
+  return fh;
+}
+}  // namespace
+
+extern "C" {
+
+int ref_ip_init(int n, const float* dI_host, int w, int h, const double K[4], const int32_t* u, const int32_t* v, float* color8, float* weights8,
+                float* gradH4, float* energyTH, uint8_t* ok) {
+  set_calib_globals(w, h, K);
+  CalibHessian Hc;
+  FrameHessian* host = frame_with_dI(dI_host, w, h);
+  int good = 0;
+  for (int i = 0; i < n; i++) {
+    ImmaturePoint ipt(u[i], v[i], host, 1.f, &Hc);
+    std::memcpy(color8 + 8 * i, ipt.color, 32); std::memcpy(weights8 + 8 * i, ipt.weights, 32);
+    gradH4[4 * i] = ipt.gradH(0, 0); gradH4[4 * i + 1] = ipt.gradH(0, 1); gradH4[4 * i + 2] = ipt.gradH(1, 0); gradH4[4 * i + 3] = ipt.gradH(1, 1);
+    energyTH[i] = ipt.energyTH;
+    ok[i] = std::isfinite(ipt.energyTH) ? 1 : 0;
+    good += ok[i];
+  }
+  free_frame(host);
+  return good;
+}
+
+void ref_ip_trace(int n, const float* dI, int w, int h, const double K[4], const float* KRKi9, const float* Kt3, const float* aff2, const float* u,
+                  const float* v, const float* color8, const float* weights8, const float* gradH4, const float* energyTH, float* idepth_min,
+                  float* idepth_max, float* quality, int32_t* status, float* uv2, float* interval) {
+  set_calib_globals(w, h, K);
+  CalibHessian Hc;
+  FrameHessian* frame = frame_with_dI(dI, w, h);
+  FrameHessian* host = blank_frame(1);   // the constructor samples it; every sampled field is overwritten below
+  Mat33f KRKi; Vec3f Kt; Vec2f aff;
+  for (int i = 0; i < 3; i++) { Kt[i] = Kt3[i]; for (int j = 0; j < 3; j++) KRKi(i, j) = KRKi9[3 * i + j]; }
+  aff[0] = aff2[0]; aff[1] = aff2[1];
+  for (int i = 0; i < n; i++) {
+    ImmaturePoint ipt(8, 8, host, 1.f, &Hc);
+    ipt.u = u[i]; ipt.v = v[i];
+    std::memcpy(ipt.color, color8 + 8 * i, 32); std::memcpy(ipt.weights, weights8 + 8 * i, 32);
+    ipt.gradH(0, 0) = gradH4[4 * i]; ipt.gradH(0, 1) = gradH4[4 * i + 1]; ipt.gradH(1, 0) = gradH4[4 * i + 2]; ipt.gradH(1, 1) = gradH4[4 * i + 3];
+    ipt.energyTH = energyTH[i]; ipt.idepth_min = idepth_min[i]; ipt.idepth_max = idepth_max[i]; ipt.quality = quality[i];
+    ipt.lastTraceStatus = (ImmaturePointStatus)status[i];
+    ipt.lastTraceUV = Vec2f(uv2[2 * i], uv2[2 * i + 1]); ipt.lastTracePixelInterval = interval[i];
+    ipt.traceOn(frame, KRKi, Kt, aff, &Hc, false);
+    idepth_min[i] = ipt.idepth_min; idepth_max[i] = ipt.idepth_max; quality[i] = ipt.quality; status[i] = (int)ipt.lastTraceStatus;
+    uv2[2 * i] = ipt.lastTraceUV[0]; uv2[2 * i + 1] = ipt.lastTraceUV[1]; interval[i] = ipt.lastTracePixelInterval;
+  }
+  free_frame(host);
+  free_frame(frame);
+}
+
+}  // extern "C"

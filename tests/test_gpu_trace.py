@@ -1,0 +1,63 @@
+"""GPU parity of immature-point tracing (dmv_ct_trace_points == ImmaturePoint::traceOn): BIT-EXACT against the CPU oracle, which is
+itself pinned bit-exact against the reference's compiled ImmaturePoint.cpp (tests/test_ref_pin.py).  No tolerance: the kernel is built
+with -fmad=false and keeps the reference's operation order."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import dmvio_b200.capi as c
+    if c.lib().dmv_device_count() < 1:
+        pytest.fail("no CUDA device visible: GPU tests must run on the B200 box")
+    return c
+
+
+@pytest.mark.parametrize("cfg", [dict(seed=5, trans=0.05, rot=0.01, n=3000), dict(seed=12, trans=0.12, rot=0.03, n=1500, w=512, h=512)], ids=["640x480", "512x512_fast"])
+def test_trace_bit_exact(capi, orc, synth, cfg):
+    import dmvio_b200.hostmath as hm
+    kw = {k: cfg[k] for k in ("w", "h") if k in cfg}
+    W = synth.make_window(nf=3, npts=10, seed=cfg["seed"], trans=cfg["trans"], rot=cfg["rot"], **kw)
+    w, h = W["w"], W["h"]
+    rng = np.random.default_rng(cfg["seed"])
+    n = cfg["n"]
+    u, v = rng.integers(10, w - 10, n), rng.integers(10, h - 10, n)
+    P = orc.ip_init(W["dI"][0], w, h, u, v)
+    g = capi.CT(w, h, synth.pyr_levels(w, h), max_points=1024)
+    st = P
+    seen = np.zeros(6, int)
+    for new in (1, 2, 1):
+        KRKi, Kt, aff = hm.trace_tables(W, 0, new)
+        g.upload_new(0, W["dI"][new])
+        Qg = g.trace_points(st, KRKi, Kt, aff)
+        Qo = orc.ip_trace(st, W["dI"][new], w, h, KRKi, Kt, aff)
+        for k in orc.IP_STATE_KEYS:
+            np.testing.assert_array_equal(Qg[k], Qo[k], err_msg=f"frame {new}: {k}")
+        seen += np.bincount(Qo["status"], minlength=6)
+        st = Qo
+    assert seen[0] > 0 and seen[1] > 0
+    g.close()
+
+
+def test_trace_device_pyramid_and_edge_cases(capi, orc, synth):
+    import dmvio_b200.hostmath as hm
+    W = synth.make_window(nf=2, npts=10, seed=3, trans=0.05, rot=0.01)
+    w, h = W["w"], W["h"]
+    g = capi.CT(w, h, 4, max_points=1024)
+    g.upload_new_image(W["images"][1])      # level-0 [I,dx,dy] built on the device from the raw image
+    KRKi, Kt, aff = hm.trace_tables(W, 0, 1)
+    # empty set
+    P0 = orc.ip_init(W["dI"][0], w, h, np.zeros(0, int), np.zeros(0, int))
+    assert len(g.trace_points(P0, KRKi, Kt, aff)["status"]) == 0
+    # border points go OOB, OOB is sticky
+    u = np.array([10, 11, 320, 629]); v = np.array([10, 470, 240, 10])
+    P = orc.ip_init(W["dI"][0], w, h, u, v)
+    dI1 = W["dI"][1].reshape(h, w, 3).copy()
+    Qg, Qo = g.trace_points(P, KRKi, Kt, aff), orc.ip_trace(P, dI1, w, h, KRKi, Kt, aff)
+    for k in orc.IP_STATE_KEYS:
+        np.testing.assert_array_equal(Qg[k], Qo[k], err_msg=k)
+    Q2 = g.trace_points(Qg, KRKi, Kt, aff)
+    np.testing.assert_array_equal(Q2["status"][Qg["status"] == 1], 1)
+    g.close()
