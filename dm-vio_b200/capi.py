@@ -41,6 +41,11 @@ class BALinResult(C.Structure):
     _fields_ = [("energy", C.c_double), ("n_in", C.c_int), ("n_oob", C.c_int), ("n_outlier", C.c_int)]
 
 
+class BAActivateArgs(C.Structure):
+    _fields_ = [("n", C.c_int)] + [(k, C.c_void_p) for k in ("host", "u", "v", "color8", "weights8", "energyTH", "idepth_min", "idepth_max", "RT")] + \
+               [("minObs", C.c_int)] + [(k, C.c_void_p) for k in ("status", "idepth", "res_state")]
+
+
 class IPPoints(C.Structure):
     _fields_ = [("n", C.c_int)] + [(k, C.c_void_p) for k in ("u", "v", "color8", "weights8", "gradH4", "energyTH", "idepth_min", "idepth_max", "quality",
                                                               "lastTraceStatus", "lastTraceUV2", "lastTracePixelInterval")]
@@ -57,9 +62,9 @@ SYMBOLS = [
     "dmv_ba_set_window", "dmv_ba_set_points", "dmv_ba_set_residuals", "dmv_ba_set_adjoints", "dmv_ba_set_state", "dmv_ba_linearize",
     "dmv_ba_get_residual_outputs", "dmv_ba_get_target_energies", "dmv_ba_apply_res", "dmv_ba_accumulate", "dmv_ba_get_point_outputs",
     "dmv_ba_resubstitute", "dmv_ba_backup_points", "dmv_ba_restore_points", "dmv_ba_get_idepth", "dmv_ba_gn_step", "dmv_nccl_unique_id",
-    "dmv_ba_comm_init", "dmv_ba_p2p_export", "dmv_ba_p2p_import", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e", "dmv_ba_debug_clocks",
+    "dmv_ba_comm_init", "dmv_ba_activate_points", "dmv_ba_p2p_export", "dmv_ba_p2p_import", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e", "dmv_ba_debug_clocks",
     "dmv_ct_create", "dmv_ct_destroy", "dmv_ct_set_K", "dmv_ct_set_ref", "dmv_ct_upload_new", "dmv_ct_upload_new_image", "dmv_ct_set_huber",
-    "dmv_ct_calc_res_gs", "dmv_ct_track", "dmv_ip_default_settings", "dmv_ct_trace_points", "dmv_ct_set_timing", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count",
+    "dmv_ct_calc_res_gs", "dmv_ct_track", "dmv_ip_default_settings", "dmv_ct_init_points", "dmv_ct_trace_points", "dmv_ct_set_timing", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count",
 ]
 
 
@@ -95,6 +100,7 @@ def lib():
         L.dmv_ba_gn_step.argtypes = [vp, vp, C.POINTER(BAState), C.POINTER(BALinResult), f64p]
         L.dmv_nccl_unique_id.argtypes = [vp]
         L.dmv_ba_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.dmv_ba_activate_points.argtypes = [vp, C.POINTER(BAActivateArgs)]
         L.dmv_ba_p2p_export.argtypes = [vp, vp]
         L.dmv_ba_p2p_import.argtypes = [vp, C.c_int, C.c_int, vp]
         L.dmv_ba_last_timing.argtypes = [vp, f32p]
@@ -112,6 +118,7 @@ def lib():
         L.dmv_ct_upload_new_image.argtypes = [vp, f32p]
         L.dmv_ct_set_huber.argtypes = [vp, C.c_float]
         L.dmv_ct_calc_res_gs.argtypes = [vp, C.c_int, f32p, f32p, f32p, C.c_float, C.c_float, C.c_int, f64p, f64p, f64p, C.POINTER(C.c_int)]
+        L.dmv_ct_init_points.argtypes = [vp, C.c_int, i32p, i32p, f32p, f32p, f32p, f32p, i32p]
         L.dmv_ct_trace_points.argtypes = [vp, C.POINTER(IPPoints), f32p, f32p, f32p, vp]
         L.dmv_ct_set_timing.argtypes = [vp, C.c_int]
         L.dmv_ct_last_timing.argtypes = [vp, f32p]
@@ -298,6 +305,16 @@ class BA:
         check(self.L.dmv_ba_comm_init(self.h, nranks, rank, C.cast(buf, vp)))
 
 
+    def activate_points(self, host, P, RT, minObs=1):
+        """FullSystem::optimizeImmaturePoint for the immature points P (dict as oracle.orc.ip_init) hosted in window frames `host`;
+        returns status (1 activate / 0 keep / -1 delete), idepth, res_state (n, nf)."""
+        n = len(P["u"])
+        keep = [_c(host, np.int32)] + [_c(P[k], np.float32) for k in ("u", "v", "color", "weights", "energyTH", "idepth_min", "idepth_max")] + [_c(RT, np.float32)]
+        status = np.zeros(n, np.int32); idepth = np.zeros(n, np.float32); rs = np.zeros((n, self.nf), np.int32)
+        args = BAActivateArgs(n, *[a.ctypes.data for a in keep], int(minObs), status.ctypes.data, idepth.ctypes.data, rs.ctypes.data)
+        check(self.L.dmv_ba_activate_points(self.h, C.byref(args)))
+        return status, idepth, rs
+
     def p2p_export(self):
         """64-byte CUDA IPC handle of this rank's exchange inbox (all-gather it, then p2p_import)."""
         buf = C.create_string_buffer(64)
@@ -356,6 +373,19 @@ class CT:
         check(self.L.dmv_ct_calc_res_gs(self.h, lvl, _c(RKi, np.float32).reshape(-1), _c(t, np.float32), _c(affLL, np.float32), b0, cutoff,
                                         int(want_gs), res6, H, b, C.byref(n)))
         return res6, H.reshape(8, 8), b, n.value
+
+    def init_points(self, u, v):
+        """ImmaturePoint constructor on the resident frame; same dict layout as oracle.orc.ip_init."""
+        n = len(u)
+        P = dict(u=_c(u, np.float32), v=_c(v, np.float32), color=np.zeros((n, 8), np.float32), weights=np.zeros((n, 8), np.float32),
+                 gradH=np.zeros((n, 4), np.float32), energyTH=np.zeros(n, np.float32))
+        ok = np.zeros(n, np.int32)
+        check(self.L.dmv_ct_init_points(self.h, n, _c(u, np.int32), _c(v, np.int32), P["color"].reshape(-1), P["weights"].reshape(-1), P["gradH"].reshape(-1),
+                                        P["energyTH"], ok))
+        P["ok"] = ok.astype(np.uint8)
+        P.update(idepth_min=np.zeros(n, np.float32), idepth_max=np.full(n, np.nan, np.float32), quality=np.full(n, 10000, np.float32),
+                 status=np.full(n, 5, np.int32), lastTraceUV=np.zeros((n, 2), np.float32), lastTracePixelInterval=np.zeros(n, np.float32))
+        return P
 
     def trace_points(self, P, KRKi, Kt, aff):
         """ImmaturePoint::traceOn for the points of one host frame (dict of arrays as oracle.orc.ip_init returns) against the resident newest

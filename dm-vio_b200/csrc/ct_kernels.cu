@@ -793,6 +793,43 @@ void dmv_ip_default_settings(dmv_ip_settings* s) {
   s->trace_minImprovementFactor = 2.f; s->huberTH = 9.f; s->trace_GNIterations = 3; s->minTraceTestRadius = 2;
 }
 
+// ImmaturePoint constructor on the resident frame (ip_trace.cu)
+int dmv_ct_init_points(dmv_ct* c, int n, const int32_t* u, const int32_t* v, float* color8, float* weights8, float* gradH4, float* energyTH, int32_t* ok) {
+  if (!c || n < 0 || (n > 0 && (!u || !v || !color8 || !weights8 || !gradH4 || !energyTH || !ok))) return set_error(DMV_ERR_INVALID, "null argument");
+  if (n == 0) return DMV_OK;
+  for (int i = 0; i < n; i++)
+    if (u[i] < 2 || v[i] < 2 || u[i] >= c->w[0] - 3 || v[i] >= c->h[0] - 3) return set_error(DMV_ERR_INVALID, "point %d (%d,%d): the pattern leaves the image", i, u[i], v[i]);
+  CK(cudaSetDevice(c->device));
+  if (n > c->ip_cap) {
+    if (c->d_ip) cudaFree(c->d_ip);
+    if (c->h_ip) cudaFreeHost(c->h_ip);
+    c->ip_cap = std::max(n, 2048);
+    CK(cudaMalloc(&c->d_ip, sizeof(float) * 30 * c->ip_cap));
+    CK(cudaMallocHost(&c->h_ip, sizeof(float) * 30 * c->ip_cap));
+  }
+  if (c->staging_busy) { CK(cudaStreamSynchronize(c->stream)); c->staging_busy = false; }
+  const size_t cap = c->ip_cap;
+  float* hb = c->h_ip;
+  float* d = c->d_ip;
+  // layout (words): u | v | color*8 | weights*8 | gradH*4 | energyTH | ok
+  std::memcpy(hb, u, 4 * (size_t)n); std::memcpy(hb + cap, v, 4 * (size_t)n);
+  CK(cudaMemcpyAsync(d, hb, sizeof(float) * 2 * cap, cudaMemcpyHostToDevice, c->stream));
+  IPInitArgs A;
+  A.n = n; A.w = c->w[0];
+  A.outlierTHSumComponent = 50.f * 50.f; A.outlierTH = 12.f * 12.f; A.overallEnergyTHWeight = 1.f;  // util/settings.cpp:L111-114, L159
+  A.u = reinterpret_cast<const int*>(d); A.v = reinterpret_cast<const int*>(d + cap);
+  A.color = d + 2 * cap; A.weights = d + 10 * cap; A.gradH = d + 18 * cap; A.energyTH = d + 22 * cap; A.ok = reinterpret_cast<int*>(d + 23 * cap);
+  A.img = c->d_img[0];
+  launch_ip_init(A, c->stream);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(hb + 2 * cap, d + 2 * cap, sizeof(float) * 22 * cap, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  std::memcpy(color8, hb + 2 * cap, 32 * (size_t)n); std::memcpy(weights8, hb + 10 * cap, 32 * (size_t)n); std::memcpy(gradH4, hb + 18 * cap, 16 * (size_t)n);
+  std::memcpy(energyTH, hb + 22 * cap, 4 * (size_t)n); std::memcpy(ok, hb + 23 * cap, 4 * (size_t)n);
+  return DMV_OK;
+}
+
 // one host frame's immature points traced against the resident newest frame (ip_trace.cu)
 int dmv_ct_trace_points(dmv_ct* c, const dmv_ip_points* p, const float KRKi[9], const float Kt[3], const float aff[2], const dmv_ip_settings* settings) {
   if (!c || !p || !KRKi || !Kt || !aff) return set_error(DMV_ERR_INVALID, "null argument");

@@ -201,6 +201,154 @@ __global__ void __launch_bounds__(128) ip_trace_kernel(const __grid_constant__ I
 #undef IP_RETURN
 }
 
+// ImmaturePoint::ImmaturePoint (ImmaturePoint.cpp:L34-63): pattern colours, gradient weights, gradH and energyTH from the HOST frame's level-0
+// plane (getInterpolatedElement33BiLin, util/globalFuncs.h:L203-226) for integer pixels (u, v); ok = 0 where a colour is not finite
+// (the reference then leaves energyTH = NaN and the caller drops the point)
+__global__ void __launch_bounds__(128) ip_init_kernel(const __grid_constant__ IPInitArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int u = A.u[i], v = A.v[i];
+  float g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+  bool ok = true;
+  float col[8], wgt[8];
+#pragma unroll
+  for (int idx = 0; idx < 8; idx++) {
+    col[idx] = 0.f; wgt[idx] = 0.f;
+    if (!ok) continue;
+    const float x = (float)(u + c_ip_pattern[idx][0]), y = (float)(v + c_ip_pattern[idx][1]);
+    const int ix = (int)x, iy = (int)y;
+    const float4* bp = A.img + ix + iy * A.w;
+    const float tl = __ldg(bp).x, tr = __ldg(bp + 1).x, bl = __ldg(bp + A.w).x, br = __ldg(bp + A.w + 1).x;
+    const float dx = x - ix, dy = y - iy;
+    const float topInt = dx * tr + (1 - dx) * tl;
+    const float botInt = dx * br + (1 - dx) * bl;
+    const float leftInt = dy * bl + (1 - dy) * tl;
+    const float rightInt = dy * br + (1 - dy) * tr;
+    const float c0 = dx * rightInt + (1 - dx) * leftInt, c1 = rightInt - leftInt, c2 = botInt - topInt;
+    col[idx] = c0;
+    if (!isfinite(c0)) { ok = false; continue; }
+    g0 += c1 * c1; g1 += c1 * c2; g2 += c2 * c1; g3 += c2 * c2;
+    wgt[idx] = sqrtf(A.outlierTHSumComponent / (A.outlierTHSumComponent + (c1 * c1 + c2 * c2)));
+  }
+#pragma unroll
+  for (int idx = 0; idx < 8; idx++) { A.color[8 * i + idx] = col[idx]; A.weights[8 * i + idx] = wgt[idx]; }
+  A.gradH[4 * i] = g0; A.gradH[4 * i + 1] = g1; A.gradH[4 * i + 2] = g2; A.gradH[4 * i + 3] = g3;
+  float eth = 8 * A.outlierTH;
+  eth *= A.overallEnergyTHWeight * A.overallEnergyTHWeight;
+  A.energyTH[i] = ok ? eth : __int_as_float(0x7fc00000);
+  A.ok[i] = ok ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ip_activate_kernel — FullSystem::optimizeImmaturePoint (FullSystem/FullSystemOptPoint.cpp:L51-205) with ImmaturePoint::linearizeResidual
+// (FullSystem/ImmaturePoint.cpp:L498-565), projectPoint / derive_idepth (FullSystem/ResidualProjections.h:L36-87): one thread per immature
+// point, residuals against every other keyframe of the window, <= 3 damped Gauss-Newton steps on the inverse depth.  Same -fmad=false
+// rule as the tracing kernel: bit-identical to the CPU code (float/double promotions of the reference kept explicitly).
+// ---------------------------------------------------------------------------------------------------------------------
+struct IPTmpRes { int state_state, state_NewState, target; double state_energy, state_NewEnergy; };
+
+__device__ double ip_linearize_residual(const IPActArgs& A, int host, float pu, float pv, const float* color, const float* weights, float energyTH,
+                                        float outlierTHSlack, IPTmpRes* tmp, float& Hdd, float& bd, float idepth) {
+  if (tmp->state_state == 1) { tmp->state_NewState = 1; return tmp->state_energy; }
+  const float* R = A.RT + (size_t)(host * A.nf + tmp->target) * 12;
+  const float* t = R + 9;
+  const float* affLL = A.aff + (size_t)(host * A.nf + tmp->target) * 2;
+  const float4* __restrict__ dIl = A.img[tmp->target];
+  const float wM3G = (float)(A.w - 3), hM3G = (float)(A.h - 3);
+  float energyLeft = 0;
+  for (int idx = 0; idx < 8; idx++) {
+    const int dx = c_ip_pattern[idx][0], dy = c_ip_pattern[idx][1];
+    const float K0 = (pu + dx - A.cxl) * A.fxli, K1 = (pv + dy - A.cyl) * A.fyli, K2 = 1;
+    float ptp[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) ptp[i] = ((R[3 * i] * K0 + R[3 * i + 1] * K1) + R[3 * i + 2] * K2) + t[i] * idepth;
+    const float drescale = 1.0f / ptp[2];
+    if (!(drescale > 0)) { tmp->state_NewState = 1; return tmp->state_energy; }
+    const float u = ptp[0] * drescale, v = ptp[1] * drescale;
+    const float Ku = u * A.fxl + A.cxl, Kv = v * A.fyl + A.cyl;
+    if (!(Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G)) { tmp->state_NewState = 1; return tmp->state_energy; }
+    float hit[3];
+    ip_interp33(dIl, Ku, Kv, A.w, hit);
+    if (!isfinite(hit[0])) { tmp->state_NewState = 1; return tmp->state_energy; }
+    const float residual = hit[0] - (affLL[0] * color[idx] + affLL[1]);
+    float hw = fabsf(residual) < A.huberTH ? 1 : A.huberTH / fabsf(residual);
+    energyLeft += weights[idx] * weights[idx] * hw * residual * residual * (2 - hw);
+    const float dxInterp = hit[1] * A.fxl, dyInterp = hit[2] * A.fyl;
+    const float d_idepth = (dxInterp * drescale * (t[0] - t[2] * u) + dyInterp * drescale * (t[1] - t[2] * v)) * 1.0f;
+    hw *= weights[idx] * weights[idx];
+    Hdd += (hw * d_idepth) * d_idepth;
+    bd += (hw * residual) * d_idepth;
+  }
+  if (energyLeft > energyTH * outlierTHSlack) { energyLeft = energyTH * outlierTHSlack; tmp->state_NewState = 2; }
+  else tmp->state_NewState = 0;
+  tmp->state_NewEnergy = energyLeft;
+  return energyLeft;
+}
+
+__global__ void __launch_bounds__(128) ip_activate_kernel(const __grid_constant__ IPActArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int nf = A.nf, host = A.host[i];
+  const float pu = A.u[i], pv = A.v[i], energyTH = A.energyTH[i];
+  float color[8], weights[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { color[k] = A.color[8 * i + k]; weights[k] = A.weights[8 * i + k]; }
+  int* rs = A.res_state + (size_t)i * nf;
+  IPTmpRes res[DMV_MAX_FRAMES];
+  int nres = 0;
+  for (int f = 0; f < nf; f++) {
+    rs[f] = 255;
+    if (f == host) continue;
+    res[nres].state_NewEnergy = res[nres].state_energy = 0;
+    res[nres].state_NewState = 2;
+    res[nres].state_state = 0;
+    res[nres].target = f;
+    nres++;
+  }
+  float lastEnergy = 0, lastHdd = 0, lastbd = 0;
+  float currentIdepth = (A.idepth_max[i] + A.idepth_min[i]) * 0.5f;
+  for (int k = 0; k < nres; k++) {
+    lastEnergy = (float)((double)lastEnergy + ip_linearize_residual(A, host, pu, pv, color, weights, energyTH, 1000.f, res + k, lastHdd, lastbd, currentIdepth));
+    res[k].state_state = res[k].state_NewState;
+    res[k].state_energy = res[k].state_NewEnergy;
+  }
+  A.idepth[i] = currentIdepth;
+  if (!isfinite(lastEnergy) || lastHdd < A.minIdepthH_act) { A.status[i] = 0; return; }
+  float lambda = 0.1f;
+  for (int iteration = 0; iteration < A.GNIts; iteration++) {
+    float H = lastHdd;
+    H *= 1 + lambda;
+    const float step = (float)((1.0 / (double)H) * (double)lastbd);
+    const float newIdepth = currentIdepth - step;
+    float newHdd = 0, newbd = 0, newEnergy = 0;
+    for (int k = 0; k < nres; k++)
+      newEnergy = (float)((double)newEnergy + ip_linearize_residual(A, host, pu, pv, color, weights, energyTH, 1.f, res + k, newHdd, newbd, newIdepth));
+    if (!isfinite(lastEnergy) || newHdd < A.minIdepthH_act) { A.idepth[i] = currentIdepth; A.status[i] = 0; return; }
+    if (newEnergy < lastEnergy) {
+      currentIdepth = newIdepth;
+      lastHdd = newHdd; lastbd = newbd; lastEnergy = newEnergy;
+      for (int k = 0; k < nres; k++) { res[k].state_state = res[k].state_NewState; res[k].state_energy = res[k].state_NewEnergy; }
+      lambda = (float)((double)lambda * 0.5);
+    } else {
+      lambda *= 5;
+    }
+    if ((double)fabsf(step) < 0.0001 * (double)currentIdepth) break;
+  }
+  A.idepth[i] = currentIdepth;
+  if (!isfinite(currentIdepth)) { A.status[i] = -1; return; }
+  int numGoodRes = 0;
+  for (int k = 0; k < nres; k++) {
+    rs[res[k].target] = res[k].state_state;
+    if (res[k].state_state == 0) numGoodRes++;
+  }
+  if (numGoodRes < A.minObs || !isfinite(energyTH)) { A.status[i] = -1; return; }
+  A.status[i] = 1;
+}
+
+void launch_ip_activate(const IPActArgs& A, cudaStream_t s) { ip_activate_kernel<<<(A.n + 127) / 128, 128, 0, s>>>(A); }
+
+void launch_ip_init(const IPInitArgs& A, cudaStream_t s) { ip_init_kernel<<<(A.n + 127) / 128, 128, 0, s>>>(A); }
+
 void launch_ip_trace(const IPTraceArgs& A, cudaStream_t s) { ip_trace_kernel<<<(A.n + 127) / 128, 128, 0, s>>>(A); }
 
 }  // namespace dmv

@@ -150,6 +150,25 @@ int dmv_ba_get_idepth(dmv_ba* ba, float* idepth, float* idepth_zero);
  * x may be NULL (first linearisation).  Equivalent to dmv_ba_resubstitute(x, apply=1) ; dmv_ba_set_state(st) ; dmv_ba_linearize(). */
 int dmv_ba_gn_step(dmv_ba* ba, const double* x, const dmv_ba_state* st, dmv_ba_lin_result* out, double sums[3]);
 
+/* Point activation: FullSystem::optimizeImmaturePoint (FullSystem/FullSystemOptPoint.cpp:L51-205) with ImmaturePoint::linearizeResidual
+ * (FullSystem/ImmaturePoint.cpp:L498-565) for n immature points against every other keyframe of the window, as
+ * FullSystem::activatePointsMT_Reductor does (FullSystem.cpp:L586-602).  Uses the frames, calibration and PRE_aff_mode of the last
+ * dmv_ba_set_state / dmv_ba_gn_step.  RT: nf*nf*12 floats, index h*nf+t: PRE_RTll (row-major) | PRE_tTll of FrameFramePrecalc (current state).
+ * out: status 1 = activate (the caller creates the PointHessian with idepth and one residual per res_state == 0), 0 = not well
+ * constrained (keep as immature point), -1 = outlier (delete); idepth = optimised inverse depth; res_state[i*nf+f]: 0 IN, 1 OOB, 2 OUTLIER,
+ * 255 = no residual.  Bit-identical to the CPU code (see dmv_ct_trace_points). */
+typedef struct dmv_ba_activate_args {
+  int n;
+  const int32_t* host;
+  const float *u, *v, *color8, *weights8, *energyTH, *idepth_min, *idepth_max;
+  const float* RT;
+  int minObs;               /* 1 in activatePointsMT_Reductor */
+  int32_t* status;
+  float* idepth;
+  int32_t* res_state;
+} dmv_ba_activate_args;
+int dmv_ba_activate_points(dmv_ba* ba, const dmv_ba_activate_args* a);
+
 /* Multi-GPU: points are sharded over ranks, images/tables replicated.  After dmv_ba_comm_init every
  * dmv_ba_linearize all-reduces the stitched system (and energy/counters) over NCCL so all ranks hold identical H,b.
  * nccl_unique_id: 128 bytes from ncclGetUniqueId() on rank 0, distributed by the caller. */
@@ -268,6 +287,11 @@ typedef struct dmv_ip_points {
   int32_t* lastTraceStatus;
   float *lastTraceUV2, *lastTracePixelInterval;
 } dmv_ip_points;
+/* ImmaturePoint::ImmaturePoint (ImmaturePoint.cpp:L34-63) for n integer pixels (u, v) of the frame resident in the handle (the frame that
+ * just became a keyframe, FullSystem::makeNewTraces, FullSystem.cpp:L1284-1330): pattern colours, weights (setting_outlierTHSumComponent = 50*50),
+ * gradH (row-major 2x2), energyTH (= 8 * setting_outlierTH * setting_overallEnergyTHWeight^2 = 1152); ok[i] = 0 where a colour is not finite
+ * (energyTH = NaN, the caller drops the point like the reference).  Bit-identical to the CPU code. */
+int dmv_ct_init_points(dmv_ct* ct, int n, const int32_t* u, const int32_t* v, float* color8, float* weights8, float* gradH4, float* energyTH, int32_t* ok);
 /* hostToFrame_KRKi (row-major 3x3), hostToFrame_Kt, hostToFrame_affine exactly as traceNewCoarse computes them (FullSystem.cpp:L557-561).
  * settings may be NULL (defaults). */
 int dmv_ct_trace_points(dmv_ct* ct, const dmv_ip_points* pts, const float KRKi[9], const float Kt[3], const float aff[2], const dmv_ip_settings* settings);

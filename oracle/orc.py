@@ -50,6 +50,7 @@ def _declare(L):
     for n in ("orc_win_nres", "orc_win_npts", "orc_win_nf"):
         getattr(L, n).argtypes = [vp]
     L.orc_win_get_precalc.argtypes = [vp, f32p]
+    L.orc_win_get_RT.argtypes = [vp, f32p]
     L.orc_win_get_adjoints.argtypes = [vp, f64p, f64p]
     L.orc_win_get_adHTdeltaF.argtypes = [vp, f32p]
     L.orc_win_get_frame_tables.argtypes = [vp, f64p, f64p, f64p, f32p]
@@ -90,6 +91,8 @@ def _declare(L):
     L.orc_ct_get_warped.argtypes = [vp, vp]
     L.orc_ct_calc_gs.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_int, f64p, f64p]
     L.orc_ct_track.argtypes = [vp, f64p, f64p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, f64p, C.c_int, f64p, f64p, C.POINTER(C.c_int)]
+    L.orc_ip_activate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, f32p, i32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_int,
+                                  i32p, f32p, i32p]
     L.orc_ip_init.argtypes = [C.c_int, f32p, C.c_int, C.c_int, i32p, i32p, f32p, f32p, f32p, f32p, u8p]
     L.orc_ip_trace.argtypes = [C.c_int, f32p, C.c_int, C.c_int, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, i32p, f32p, f32p]
     L.orc_se3_exp.argtypes = [f64p, f64p, f64p]
@@ -147,6 +150,12 @@ class Window:
     def precalc(self):
         out = np.zeros((self.nf * self.nf, 32), np.float32)
         self.L.orc_win_get_precalc(self.h, out)
+        return out
+
+    def RT(self):
+        """PRE_RTll | PRE_tTll per pair [h*nf+t] (current relative poses), nf*nf x 12 float32"""
+        out = np.zeros((self.nf * self.nf, 12), np.float32)
+        self.L.orc_win_get_RT(self.h, out)
         return out
 
     def adjoints(self):
@@ -350,3 +359,17 @@ def ip_trace(P, dI, w, h, KRKi, Kt, aff, _fn=None):
     Q = dict(P)
     Q.update(out)
     return Q
+
+
+def ip_activate(W, RT, aff, calib6, host, P, minObs=1):
+    """FullSystem::optimizeImmaturePoint for the immature points P (dict as ip_init / ip_trace) hosted in frames `host` of the window W.
+    RT: (nf*nf, 12), aff: (nf*nf, 2), calib6 = fxl fyl cxl cyl fxli fyli.  Returns status (1/0/-1), idepth, res_state (n, nf)."""
+    nf, w, h = W["nf"], W["w"], W["h"]
+    n = len(P["u"])
+    c = lambda a, t: np.ascontiguousarray(a, t)
+    dI_all = c(np.stack([np.asarray(d, np.float32).reshape(-1) for d in W["dI"]]), np.float32)
+    status = np.zeros(n, np.int32); idepth = np.zeros(n, np.float32); rs = np.zeros((n, nf), np.int32)
+    lib().orc_ip_activate(n, nf, w, h, c(calib6, np.float32), dI_all.reshape(-1), c(RT, np.float32).reshape(-1), c(aff, np.float32).reshape(-1),
+                          c(host, np.int32), P["u"], P["v"], P["color"], P["weights"], P["energyTH"], c(P["idepth_min"], np.float32),
+                          c(P["idepth_max"], np.float32), int(minObs), status, idepth, rs.reshape(-1))
+    return status, idepth, rs

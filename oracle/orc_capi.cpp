@@ -130,6 +130,17 @@ void orc_win_get_precalc(OrcWin* o, float* out) {
     for (int k = 27; k < 32; k++) q[k] = 0;
   }
 }
+// PRE_RTll (row-major) | PRE_tTll per pair [h*nf+t]: the CURRENT relative pose (FrameFramePrecalc::set, HessianBlocks.cpp:L204-206), read by
+// ImmaturePoint::linearizeResidual
+void orc_win_get_RT(OrcWin* o, float* out) {
+  Window& W = o->W;
+  const int n = W.nf();
+  for (int i = 0; i < n * n; i++) {
+    const FramePrecalc& p = W.precalc[i];
+    for (int k = 0; k < 9; k++) out[12 * i + k] = p.PRE_RTll.d[k];
+    for (int k = 0; k < 3; k++) out[12 * i + 9 + k] = p.PRE_tTll[k];
+  }
+}
 void orc_win_get_adjoints(OrcWin* o, double* adHost, double* adTarget) {
   Window& W = o->W;
   const int n = W.nf();

@@ -30,6 +30,7 @@ int orc_win_npts(OrcWin*);
 int orc_win_nf(OrcWin*);
 /* 32 floats per pair [h*nf+t]: KRKi[9] Kt[3] R0[9] t0[3] aff[2] b0 pad[5] */
 void orc_win_get_precalc(OrcWin*, float* out);
+void orc_win_get_RT(OrcWin*, float* out);                               /* nf*nf*12: PRE_RTll row-major | PRE_tTll, [h*nf+t] */
 void orc_win_get_adjoints(OrcWin*, double* adHost, double* adTarget); /* nf*nf*64 each, [h+t*nf], row-major 8x8 */
 void orc_win_get_adHTdeltaF(OrcWin*, float* out);                     /* nf*nf*8 */
 void orc_win_get_frame_tables(OrcWin*, double* prior8, double* delta_prior8, double* delta8, float* frameEnergyTH); /* nf*8 ... */

@@ -250,3 +250,131 @@ void orc_ip_trace(int n, const float* dI, int w, int h, const float* KRKi, const
   }
 }
 }
+
+// =====================================================================================================================
+// Point activation (second half): FullSystem::optimizeImmaturePoint (FullSystem/FullSystemOptPoint.cpp:L51-205) driving
+// ImmaturePoint::linearizeResidual (FullSystem/ImmaturePoint.cpp:L498-565) with projectPoint / derive_idepth
+// (FullSystem/ResidualProjections.h:L36-87).  Pinned: linearizeResidual is the reference's compiled code in oracle/_ref; the 60-line
+// driver lives in FullSystem (not compiled there) and is mirrored by the harness.
+// =====================================================================================================================
+namespace orc {
+
+struct ActFrameTables {
+  int nf, w, h;
+  float fxl, fyl, cxl, cyl, fxli, fyli;
+  const float* const* dI;  // nf level-0 planes [I,dx,dy]
+  const float* RT;         // [h*nf+t][12]: PRE_RTll row-major, PRE_tTll
+  const float* aff;        // [h*nf+t][2]:  PRE_aff_mode
+};
+struct TmpRes { int state_state, state_NewState; double state_energy, state_NewEnergy; int target; };
+enum { RS_IN = 0, RS_OOB = 1, RS_OUTLIER = 2 };
+
+// ImmaturePoint::linearizeResidual
+static double linearizeResidual(const ActFrameTables& F, int host, float pu, float pv, const float* color, const float* weights, float energyTH,
+                                const float huberTH, const float outlierTHSlack, TmpRes* tmp, float& Hdd, float& bd, float idepth) {
+  if (tmp->state_state == RS_OOB) { tmp->state_NewState = RS_OOB; return tmp->state_energy; }
+  const float* R = F.RT + (size_t)(host * F.nf + tmp->target) * 12;
+  const float* t = R + 9;
+  const float* affLL = F.aff + (size_t)(host * F.nf + tmp->target) * 2;
+  const float* dIl = F.dI[tmp->target];
+  const float wM3G = (float)(F.w - 3), hM3G = (float)(F.h - 3);
+  float energyLeft = 0;
+  for (int idx = 0; idx < 8; idx++) {
+    const int dx = patternP[idx][0], dy = patternP[idx][1];
+    // projectPoint (ResidualProjections.h:L62-87)
+    const float K0 = (pu + dx - F.cxl) * F.fxli, K1 = (pv + dy - F.cyl) * F.fyli, K2 = 1;
+    float ptp[3];
+    for (int i = 0; i < 3; i++) ptp[i] = ((R[3 * i] * K0 + R[3 * i + 1] * K1) + R[3 * i + 2] * K2) + t[i] * idepth;
+    const float drescale = 1.0f / ptp[2];
+    if (!(drescale > 0)) { tmp->state_NewState = RS_OOB; return tmp->state_energy; }
+    const float u = ptp[0] * drescale, v = ptp[1] * drescale;
+    const float Ku = u * F.fxl + F.cxl, Kv = v * F.fyl + F.cyl;
+    if (!(Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G)) { tmp->state_NewState = RS_OOB; return tmp->state_energy; }
+    float hit[3];
+    interp33(dIl, Ku, Kv, F.w, hit);
+    if (!std::isfinite((float)hit[0])) { tmp->state_NewState = RS_OOB; return tmp->state_energy; }
+    const float residual = hit[0] - (affLL[0] * color[idx] + affLL[1]);
+    float hw = fabsf(residual) < huberTH ? 1 : huberTH / fabsf(residual);
+    energyLeft += weights[idx] * weights[idx] * hw * residual * residual * (2 - hw);
+    const float dxInterp = hit[1] * F.fxl, dyInterp = hit[2] * F.fyl;
+    const float d_idepth = (dxInterp * drescale * (t[0] - t[2] * u) + dyInterp * drescale * (t[1] - t[2] * v)) * 1.0f;  // derive_idepth, SCALE_IDEPTH = 1
+    hw *= weights[idx] * weights[idx];
+    Hdd += (hw * d_idepth) * d_idepth;
+    bd += (hw * residual) * d_idepth;
+  }
+  if (energyLeft > energyTH * outlierTHSlack) { energyLeft = energyTH * outlierTHSlack; tmp->state_NewState = RS_OUTLIER; }
+  else tmp->state_NewState = RS_IN;
+  tmp->state_NewEnergy = energyLeft;
+  return energyLeft;
+}
+
+// FullSystem::optimizeImmaturePoint: returns 1 (activated), 0 (not well constrained: skipped), -1 (outlier / NaN depth)
+static int optimizeImmaturePoint(const ActFrameTables& F, int host, float pu, float pv, const float* color, const float* weights, float energyTH,
+                                 float idepth_min, float idepth_max, int minObs, float huberTH, float minIdepthH_act, int GNIts, float* idepth_out,
+                                 int32_t* res_state /* nf */) {
+  TmpRes res[16];
+  int nres = 0;
+  for (int f = 0; f < F.nf; f++) {
+    res_state[f] = 255;
+    if (f == host) continue;
+    res[nres].state_NewEnergy = res[nres].state_energy = 0;
+    res[nres].state_NewState = RS_OUTLIER;
+    res[nres].state_state = RS_IN;
+    res[nres].target = f;
+    nres++;
+  }
+  float lastEnergy = 0, lastHdd = 0, lastbd = 0;
+  float currentIdepth = (idepth_max + idepth_min) * 0.5f;
+  for (int i = 0; i < nres; i++) {
+    lastEnergy += linearizeResidual(F, host, pu, pv, color, weights, energyTH, huberTH, 1000, res + i, lastHdd, lastbd, currentIdepth);
+    res[i].state_state = res[i].state_NewState;
+    res[i].state_energy = res[i].state_NewEnergy;
+  }
+  *idepth_out = currentIdepth;
+  if (!std::isfinite(lastEnergy) || lastHdd < minIdepthH_act) return 0;
+  float lambda = 0.1;
+  for (int iteration = 0; iteration < GNIts; iteration++) {
+    float H = lastHdd;
+    H *= 1 + lambda;
+    const float step = (1.0 / H) * lastbd;
+    const float newIdepth = currentIdepth - step;
+    float newHdd = 0, newbd = 0, newEnergy = 0;
+    for (int i = 0; i < nres; i++) newEnergy += linearizeResidual(F, host, pu, pv, color, weights, energyTH, huberTH, 1, res + i, newHdd, newbd, newIdepth);
+    if (!std::isfinite(lastEnergy) || newHdd < minIdepthH_act) { *idepth_out = currentIdepth; return 0; }
+    if (newEnergy < lastEnergy) {
+      currentIdepth = newIdepth;
+      lastHdd = newHdd; lastbd = newbd; lastEnergy = newEnergy;
+      for (int i = 0; i < nres; i++) { res[i].state_state = res[i].state_NewState; res[i].state_energy = res[i].state_NewEnergy; }
+      lambda *= 0.5;
+    } else {
+      lambda *= 5;
+    }
+    if (fabsf(step) < 0.0001 * currentIdepth) break;
+  }
+  *idepth_out = currentIdepth;
+  if (!std::isfinite(currentIdepth)) return -1;
+  int numGoodRes = 0;
+  for (int i = 0; i < nres; i++) {
+    res_state[res[i].target] = res[i].state_state;
+    if (res[i].state_state == RS_IN) numGoodRes++;
+  }
+  if (numGoodRes < minObs) return -1;
+  if (!std::isfinite(energyTH)) return -1;
+  return 1;
+}
+
+}  // namespace orc
+
+extern "C" void orc_ip_activate(int n, int nf, int w, int h, const float calib6[6], const float* dI_all, const float* RT, const float* aff,
+                                const int32_t* host, const float* u, const float* v, const float* color8, const float* weights8, const float* energyTH,
+                                const float* idepth_min, const float* idepth_max, int minObs, int32_t* status, float* idepth, int32_t* res_state) {
+  orc::ActFrameTables F;
+  F.nf = nf; F.w = w; F.h = h;
+  F.fxl = calib6[0]; F.fyl = calib6[1]; F.cxl = calib6[2]; F.cyl = calib6[3]; F.fxli = calib6[4]; F.fyli = calib6[5];
+  const float* planes[16];
+  for (int f = 0; f < nf; f++) planes[f] = dI_all + (size_t)f * w * h * 3;
+  F.dI = planes; F.RT = RT; F.aff = aff;
+  for (int i = 0; i < n; i++)
+    status[i] = orc::optimizeImmaturePoint(F, host[i], u[i], v[i], color8 + 8 * i, weights8 + 8 * i, energyTH[i], idepth_min[i], idepth_max[i], minObs, 9.f,
+                                           100.f, 3, idepth + i, res_state + (size_t)i * nf);
+}

@@ -55,6 +55,8 @@ def lib():
         for n in ("ref_win_nres", "ref_win_npts", "ref_win_nf"):
             getattr(L, n).argtypes = [vp]
         L.ref_win_get_precalc.argtypes = [vp, f32p]
+        L.ref_win_get_RT.argtypes = [vp, f32p]
+        L.ref_win_activate.argtypes = [vp, C.c_int, i32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, i32p, f32p, i32p]
         L.ref_win_get_adjoints.argtypes = [vp, f64p, f64p]
         L.ref_win_get_adHTdeltaF.argtypes = [vp, f32p]
         L.ref_win_get_frame_tables.argtypes = [vp, f64p, f64p, f64p, f32p]
@@ -104,6 +106,15 @@ class Window(orc.Window):
         W.pop("HM", None); W.pop("bM", None)
         self._ref = lib()
         super().__init__(W, nthreads=nthreads, settings=settings, _lib=_Adapter(self._ref))
+
+    def activate(self, host, P, minObs=1):
+        """the reference's ImmaturePoint::linearizeResidual under the optimizeImmaturePoint driver, on this window's frames"""
+        n = len(P["u"])
+        c = lambda a, t: np.ascontiguousarray(a, t)
+        status = np.zeros(n, np.int32); idepth = np.zeros(n, np.float32); rs = np.zeros((n, self.nf), np.int32)
+        self._ref.ref_win_activate(self.h, n, c(host, np.int32), P["u"], P["v"], P["color"], P["weights"], P["energyTH"], c(P["idepth_min"], np.float32),
+                                   c(P["idepth_max"], np.float32), int(minObs), status, idepth, rs.reshape(-1))
+        return status, idepth, rs
 
     def __del__(self):
         try:

@@ -216,6 +216,86 @@ void ref_win_prepare(RefWin* W) {
   W->prepared = true;
 }
 
+void ref_win_get_RT(RefWin* W, float* out) {
+  const int nf = W->nf;
+  for (int h = 0; h < nf; h++)
+    for (int t = 0; t < nf; t++) {
+      const FrameFramePrecalc& p = W->frames[h]->targetPrecalc[t];
+      float* o = out + (size_t)(h * nf + t) * 12;
+      copy_rowmajor(p.PRE_RTll, 3, 3, o);
+      for (int k = 0; k < 3; k++) o[9 + k] = p.PRE_tTll[k];
+    }
+}
+
+// FullSystem::optimizeImmaturePoint (FullSystemOptPoint.cpp:L51-205; a FullSystem member, so its driver loop is mirrored here) around the
+// reference's own ImmaturePoint::linearizeResidual (ImmaturePoint.cpp:L498-565).  status: 1 activated, 0 skipped, -1 outlier.
+void ref_win_activate(RefWin* W, int n, const int32_t* host, const float* u, const float* v, const float* color8, const float* weights8,
+                      const float* energyTH, const float* idepth_min, const float* idepth_max, int minObs, int32_t* status, float* idepth,
+                      int32_t* res_state) {
+  const int nf = W->nf;
+  for (int i = 0; i < n; i++) {
+    FrameHessian* hostF = W->frames[host[i]];
+    ImmaturePoint ipt(8, 8, hostF, 1.f, W->Hcalib);
+    ipt.u = u[i]; ipt.v = v[i];
+    std::memcpy(ipt.color, color8 + 8 * i, 32); std::memcpy(ipt.weights, weights8 + 8 * i, 32);
+    ipt.energyTH = energyTH[i]; ipt.idepth_min = idepth_min[i]; ipt.idepth_max = idepth_max[i];
+    ImmaturePoint* point = &ipt;
+    ImmaturePointTemporaryResidual residuals[16];
+    int32_t* rs = res_state + (size_t)i * nf;
+    for (int f = 0; f < nf; f++) rs[f] = 255;
+    int nres = 0;
+    for (FrameHessian* fh : W->frames) {
+      if (fh != point->host) {
+        residuals[nres].state_NewEnergy = residuals[nres].state_energy = 0;
+        residuals[nres].state_NewState = ResState::OUTLIER;
+        residuals[nres].state_state = ResState::IN;
+        residuals[nres].target = fh;
+        nres++;
+      }
+    }
+    float lastEnergy = 0, lastHdd = 0, lastbd = 0;
+    float currentIdepth = (point->idepth_max + point->idepth_min) * 0.5f;
+    for (int k = 0; k < nres; k++) {
+      lastEnergy += point->linearizeResidual(W->Hcalib, 1000, residuals + k, lastHdd, lastbd, currentIdepth);
+      residuals[k].state_state = residuals[k].state_NewState;
+      residuals[k].state_energy = residuals[k].state_NewEnergy;
+    }
+    idepth[i] = currentIdepth;
+    if (!std::isfinite(lastEnergy) || lastHdd < setting_minIdepthH_act) { status[i] = 0; continue; }
+    float lambda = 0.1;
+    bool skipped = false;
+    for (int iteration = 0; iteration < setting_GNItsOnPointActivation; iteration++) {
+      float H = lastHdd;
+      H *= 1 + lambda;
+      float step = (1.0 / H) * lastbd;
+      float newIdepth = currentIdepth - step;
+      float newHdd = 0; float newbd = 0; float newEnergy = 0;
+      for (int k = 0; k < nres; k++) newEnergy += point->linearizeResidual(W->Hcalib, 1, residuals + k, newHdd, newbd, newIdepth);
+      if (!std::isfinite(lastEnergy) || newHdd < setting_minIdepthH_act) { skipped = true; break; }
+      if (newEnergy < lastEnergy) {
+        currentIdepth = newIdepth;
+        lastHdd = newHdd; lastbd = newbd; lastEnergy = newEnergy;
+        for (int k = 0; k < nres; k++) { residuals[k].state_state = residuals[k].state_NewState; residuals[k].state_energy = residuals[k].state_NewEnergy; }
+        lambda *= 0.5;
+      } else {
+        lambda *= 5;
+      }
+      if (fabsf(step) < 0.0001 * currentIdepth) break;
+    }
+    idepth[i] = currentIdepth;
+    if (skipped) { status[i] = 0; continue; }
+    if (!std::isfinite(currentIdepth)) { status[i] = -1; continue; }
+    int numGoodRes = 0;
+    for (int k = 0; k < nres; k++) {
+      rs[residuals[k].target->idx] = (int)residuals[k].state_state;
+      if (residuals[k].state_state == ResState::IN) numGoodRes++;
+    }
+    if (numGoodRes < minObs) { status[i] = -1; continue; }
+    if (!std::isfinite(point->energyTH)) { status[i] = -1; continue; }
+    status[i] = 1;
+  }
+}
+
 int ref_win_nres(RefWin* W) { return (int)W->residuals.size(); }
 int ref_win_npts(RefWin* W) { return (int)W->points.size(); }
 int ref_win_nf(RefWin* W) { return W->nf; }

@@ -23,3 +23,21 @@ def product_ba_from_oracle(capi, W, ow, chunk_points=0, device=0, max_points=Non
 def rel(a, b):
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def activation_case(synth, orc, seed=9, nf=5, n=2000, **kw):
+    """A window plus immature points with depth intervals (half of them wide, half narrow) for the point-activation tests."""
+    W = synth.make_window(nf=nf, npts=50, seed=seed, trans=0.06, rot=0.01, **kw)
+    w, h = W["w"], W["h"]
+    rng = np.random.default_rng(seed)
+    host = np.sort(rng.integers(0, nf, n)).astype(np.int32)
+    u, v = rng.integers(10, w - 10, n), rng.integers(10, h - 10, n)
+    parts = [orc.ip_init(W["dI"][hh], w, h, u[host == hh], v[host == hh]) for hh in range(nf)]
+    P = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    idt = (0.5 * (1 + 0.02 * rng.standard_normal(n))).astype(np.float32)
+    wide = rng.random(n) < 0.5
+    P["idepth_min"] = (idt * np.where(wide, 0.7, 0.97)).astype(np.float32)
+    P["idepth_max"] = (idt * np.where(wide, 1.4, 1.03)).astype(np.float32)
+    bad = rng.random(n) < 0.03            # a few hopeless intervals: far from the truth
+    P["idepth_min"][bad] *= 3; P["idepth_max"][bad] *= 3
+    return W, host, P

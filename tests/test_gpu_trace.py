@@ -61,3 +61,38 @@ def test_trace_device_pyramid_and_edge_cases(capi, orc, synth):
     Q2 = g.trace_points(Qg, KRKi, Kt, aff)
     np.testing.assert_array_equal(Q2["status"][Qg["status"] == 1], 1)
     g.close()
+
+
+def test_init_points_bit_exact(capi, orc, synth):
+    """dmv_ct_init_points == ImmaturePoint constructor: colours, weights, gradH, energyTH equal to the oracle bit for bit."""
+    W = synth.make_window(nf=2, npts=10, seed=4)
+    w, h = W["w"], W["h"]
+    rng = np.random.default_rng(2)
+    n = 2500
+    u, v = rng.integers(3, w - 4, n), rng.integers(3, h - 4, n)
+    g = capi.CT(w, h, 4, max_points=1024)
+    g.upload_new(0, W["dI"][0])
+    Pg, Po = g.init_points(u, v), orc.ip_init(W["dI"][0], w, h, u, v)
+    for k in ("color", "weights", "gradH", "energyTH", "ok"):
+        np.testing.assert_array_equal(Pg[k], Po[k], err_msg=k)
+    with pytest.raises(capi.DmvError):
+        g.init_points(np.array([0]), np.array([5]))   # pattern would leave the image
+    g.close()
+
+
+def test_point_activation_bit_exact(capi, orc, synth):
+    """dmv_ba_activate_points == FullSystem::optimizeImmaturePoint: status, inverse depth and residual states equal to the oracle bit for bit."""
+    from helpers import activation_case, product_ba_from_oracle
+    W, host, P = activation_case(synth, orc)
+    ow = orc.Window(W)
+    ba = product_ba_from_oracle(capi, W, ow)
+    aff = ow.precalc()[:, 24:26].copy()
+    calib6 = ow.calib()["k8"][:6]
+    for minObs in (1, 3):
+        s_g, i_g, r_g = ba.activate_points(host, P, ow.RT(), minObs=minObs)
+        s_o, i_o, r_o = orc.ip_activate(W, ow.RT(), aff, calib6, host, P, minObs=minObs)
+        np.testing.assert_array_equal(s_g, s_o)
+        np.testing.assert_array_equal(i_g, i_o)
+        np.testing.assert_array_equal(r_g, r_o)
+    assert (s_o == 1).sum() > 0.8 * len(s_o)
+    ba.close()
