@@ -63,7 +63,7 @@ SYMBOLS = [
     "dmv_ba_get_residual_outputs", "dmv_ba_get_target_energies", "dmv_ba_apply_res", "dmv_ba_accumulate", "dmv_ba_get_point_outputs",
     "dmv_ba_resubstitute", "dmv_ba_backup_points", "dmv_ba_restore_points", "dmv_ba_get_idepth", "dmv_ba_gn_step", "dmv_nccl_unique_id",
     "dmv_ba_comm_init", "dmv_ba_activate_points", "dmv_ba_p2p_export", "dmv_ba_p2p_import", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e", "dmv_ba_debug_clocks",
-    "dmv_ct_create", "dmv_ct_destroy", "dmv_ct_set_K", "dmv_ct_set_ref", "dmv_ct_upload_new", "dmv_ct_upload_new_image", "dmv_ct_set_huber",
+    "dmv_ct_create", "dmv_ct_destroy", "dmv_ct_set_K", "dmv_ct_set_ref", "dmv_ct_make_coarse_depth", "dmv_ct_get_ref", "dmv_ct_upload_new", "dmv_ct_upload_new_image", "dmv_ct_set_huber",
     "dmv_ct_calc_res_gs", "dmv_ct_track", "dmv_ip_default_settings", "dmv_ct_init_points", "dmv_ct_trace_points", "dmv_ct_set_timing", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count",
 ]
 
@@ -114,6 +114,8 @@ def lib():
         L.dmv_ct_destroy.argtypes = [vp]
         L.dmv_ct_set_K.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
         L.dmv_ct_set_ref.argtypes = [vp, C.c_int, C.c_int, f32p, f32p, f32p, f32p]
+        L.dmv_ct_make_coarse_depth.argtypes = [vp, C.c_int, f32p, f32p, f32p, f32p, i32p]
+        L.dmv_ct_get_ref.argtypes = [vp, C.c_int, C.POINTER(C.c_int), vp, vp, vp, vp]
         L.dmv_ct_upload_new.argtypes = [vp, C.c_int, f32p]
         L.dmv_ct_upload_new_image.argtypes = [vp, f32p]
         L.dmv_ct_set_huber.argtypes = [vp, C.c_float]
@@ -373,6 +375,19 @@ class CT:
         check(self.L.dmv_ct_calc_res_gs(self.h, lvl, _c(RKi, np.float32).reshape(-1), _c(t, np.float32), _c(affLL, np.float32), b0, cutoff,
                                         int(want_gs), res6, H, b, C.byref(n)))
         return res6, H.reshape(8, 8), b, n.value
+
+    def make_coarse_depth(self, Ku, Kv, new_idepth, HdiF):
+        """makeCoarseDepthL0 on the device with the resident frame as the reference; returns pc_n per level"""
+        pc_n = np.zeros(8, np.int32)
+        check(self.L.dmv_ct_make_coarse_depth(self.h, len(Ku), _c(Ku, np.float32), _c(Kv, np.float32), _c(new_idepth, np.float32), _c(HdiF, np.float32), pc_n))
+        return pc_n
+
+    def get_ref(self, lvl):
+        n = C.c_int(0)
+        check(self.L.dmv_ct_get_ref(self.h, lvl, C.byref(n), None, None, None, None))
+        a = [np.zeros(n.value, np.float32) for _ in range(4)]
+        check(self.L.dmv_ct_get_ref(self.h, lvl, C.byref(n), *[x.ctypes.data for x in a]))
+        return dict(u=a[0], v=a[1], idepth=a[2], color=a[3])
 
     def init_points(self, u, v):
         """ImmaturePoint constructor on the resident frame; same dict layout as oracle.orc.ip_init."""

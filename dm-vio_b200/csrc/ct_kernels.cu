@@ -11,6 +11,8 @@
 #include "common_host.h"
 #include "inv3.h"
 #include "ip_trace.h"
+#include "ct_depth.h"
+#include <unordered_map>
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -546,6 +548,9 @@ struct dmv_ct {
   double* d_out = nullptr;
   double* h_out = nullptr;
   float* h_scratch = nullptr;
+  // device-side makeCoarseDepthL0 (ct_depth.cu)
+  float *cd_idepth[DMV_MAX_PYR_LEVELS] = {nullptr}, *cd_ws[DMV_MAX_PYR_LEVELS] = {nullptr}, *cd_ws2[DMV_MAX_PYR_LEVELS] = {nullptr};
+  int *cd_rowcnt = nullptr, *cd_rowoff = nullptr, *cd_totals = nullptr;  // cd_totals: pinned host, device-visible
   float* d_ip = nullptr;   // immature-point arrays (dmv_ct_trace_points)
   float* h_ip = nullptr;
   int ip_cap = 0;
@@ -612,6 +617,8 @@ int dmv_ct_destroy(dmv_ct* c) {
   }
   cudaFree(c->d_stage); cudaFree(c->d_partial); cudaFree(c->d_ticket); cudaFree(c->d_bar); cudaFree(c->d_out);
   cudaFreeHost(c->h_out); cudaFreeHost(c->h_scratch); cudaFree(c->d_ip); cudaFreeHost(c->h_ip);
+  for (int l = 0; l < DMV_MAX_PYR_LEVELS; l++) { cudaFree(c->cd_idepth[l]); cudaFree(c->cd_ws[l]); cudaFree(c->cd_ws2[l]); }
+  cudaFree(c->cd_rowcnt); cudaFree(c->cd_rowoff); cudaFreeHost(c->cd_totals);
   cudaEventDestroy(c->ev[0]); cudaEventDestroy(c->ev[1]);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -791,6 +798,85 @@ int dmv_ct_track(dmv_ct* c, const dmv_ct_track_args* in, dmv_ct_track_result* ou
 void dmv_ip_default_settings(dmv_ip_settings* s) {
   s->maxPixSearch = 0.027f; s->trace_stepsize = 1.0f; s->trace_GNThreshold = 0.1f; s->trace_extraSlackOnTH = 1.2f; s->trace_slackInterval = 1.5f;
   s->trace_minImprovementFactor = 2.f; s->huberTH = 9.f; s->trace_GNIterations = 3; s->minTraceTestRadius = 2;
+}
+
+// CoarseTracker::setCoarseTrackingRef -> makeCoarseDepthL0 (CoarseTracker.cpp:L138-295) on the device (ct_depth.cu); the reference frame is
+// the one resident in the handle (last dmv_ct_upload_new_image / dmv_ct_upload_new of every level)
+int dmv_ct_make_coarse_depth(dmv_ct* c, int n, const float* Ku, const float* Kv, const float* new_idepth, const float* HdiF, int32_t* pc_n_out) {
+  if (!c || n < 0 || (n > 0 && (!Ku || !Kv || !new_idepth || !HdiF))) return set_error(DMV_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int L = c->cfg.levels, w0 = c->w[0], h0 = c->h[0];
+  if (!c->cd_totals) {
+    for (int l = 0; l < L; l++) {
+      const size_t npx = (size_t)c->w[l] * c->h[l];
+      CK(cudaMalloc(&c->cd_idepth[l], npx * sizeof(float)));
+      CK(cudaMalloc(&c->cd_ws[l], npx * sizeof(float)));
+      CK(cudaMalloc(&c->cd_ws2[l], npx * sizeof(float)));
+    }
+    CK(cudaMalloc(&c->cd_rowcnt, sizeof(int) * h0));
+    CK(cudaMalloc(&c->cd_rowoff, sizeof(int) * h0));
+    CK(cudaMallocHost(&c->cd_totals, sizeof(int) * DMV_MAX_PYR_LEVELS));
+  }
+  // ---- the splat's only order-dependent part on the host: points hitting the same pixel are folded in input order (L144-160)
+  if (n > c->ip_cap) {
+    if (c->d_ip) cudaFree(c->d_ip);
+    if (c->h_ip) cudaFreeHost(c->h_ip);
+    c->ip_cap = std::max(n, 2048);
+    CK(cudaMalloc(&c->d_ip, sizeof(float) * 30 * c->ip_cap));
+    CK(cudaMallocHost(&c->h_ip, sizeof(float) * 30 * c->ip_cap));
+  }
+  if (c->staging_busy) { CK(cudaStreamSynchronize(c->stream)); c->staging_busy = false; }
+  const size_t cap = c->ip_cap;
+  int* h_pix = reinterpret_cast<int*>(c->h_ip);
+  float* h_idw = c->h_ip + cap;
+  float* h_ws = c->h_ip + 2 * cap;
+  int nu = 0;
+  {
+    std::unordered_map<int, int> slot;
+    slot.reserve((size_t)n * 2);
+    for (int i = 0; i < n; i++) {
+      const int u = Ku[i] + 0.5f, v = Kv[i] + 0.5f;
+      if (u < 0 || v < 0 || u >= w0 || v >= h0) return set_error(DMV_ERR_INVALID, "residual %d projects to (%d,%d) outside the image", i, u, v);
+      const float weight = sqrtf(1e-3 / (HdiF[i] + 1e-12));
+      const int pix = u + w0 * v;
+      auto it = slot.find(pix);
+      if (it == slot.end()) { slot.emplace(pix, nu); h_pix[nu] = pix; h_idw[nu] = 0.f + new_idepth[i] * weight; h_ws[nu] = 0.f + weight; nu++; }
+      else { h_idw[it->second] += new_idepth[i] * weight; h_ws[it->second] += weight; }
+    }
+  }
+  CK(cudaMemcpyAsync(c->d_ip, c->h_ip, sizeof(float) * 3 * cap, cudaMemcpyHostToDevice, c->stream));
+  CDLevels Lv;
+  Lv.levels = L; Lv.cap = c->cfg.max_points;
+  for (int l = 0; l < L; l++) {
+    Lv.w[l] = c->w[l]; Lv.h[l] = c->h[l];
+    Lv.idepth[l] = c->cd_idepth[l]; Lv.ws[l] = c->cd_ws[l]; Lv.ws2[l] = c->cd_ws2[l]; Lv.img[l] = c->d_img[l];
+    Lv.pc_u[l] = c->d_u[l]; Lv.pc_v[l] = c->d_v[l]; Lv.pc_id[l] = c->d_id[l]; Lv.pc_col[l] = c->d_col[l];
+  }
+  Lv.rowcnt = c->cd_rowcnt; Lv.rowoff = c->cd_rowoff; Lv.totals = c->cd_totals;
+  cd_launch(Lv, nu, reinterpret_cast<const int*>(c->d_ip), c->d_ip + cap, c->d_ip + 2 * cap, c->stream);
+  c->launches += 2 + 4 * L;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  for (int l = 0; l < L; l++) {
+    if (c->cd_totals[l] > c->cfg.max_points) return set_error(DMV_ERR_INVALID, "level %d: %d reference points exceed max_points %d", l, c->cd_totals[l], c->cfg.max_points);
+    c->n[l] = c->cd_totals[l];
+    if (pc_n_out) pc_n_out[l] = c->n[l];
+  }
+  return DMV_OK;
+}
+
+// pc_u / pc_v / pc_idepth / pc_color of a level as they sit on the device (tests; any pointer may be NULL); returns pc_n[level] in *n
+int dmv_ct_get_ref(dmv_ct* c, int l, int* n, float* pc_u, float* pc_v, float* pc_idepth, float* pc_color) {
+  if (!c || !n || l < 0 || l >= c->cfg.levels) return set_error(DMV_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  *n = c->n[l];
+  const size_t bytes = sizeof(float) * c->n[l];
+  if (pc_u) CK(cudaMemcpy(pc_u, c->d_u[l], bytes, cudaMemcpyDeviceToHost));
+  if (pc_v) CK(cudaMemcpy(pc_v, c->d_v[l], bytes, cudaMemcpyDeviceToHost));
+  if (pc_idepth) CK(cudaMemcpy(pc_idepth, c->d_id[l], bytes, cudaMemcpyDeviceToHost));
+  if (pc_color) CK(cudaMemcpy(pc_color, c->d_col[l], bytes, cudaMemcpyDeviceToHost));
+  return DMV_OK;
 }
 
 // ImmaturePoint constructor on the resident frame (ip_trace.cu)

@@ -97,6 +97,17 @@ bool CoarseTracker::setNewFramePyramid(const float* const* dIp, float ab_exposur
   return true;
 }
 
+bool CoarseTracker::setCoarseTrackingRefOnDevice(int n, const float* Ku, const float* Kv, const float* new_idepth, const float* HdiF,
+                                                 const float* ref_image_wh, AffLight ref_aff, float ref_exposure) {
+  lastRef_aff_g2l_ = ref_aff;
+  lastRef_ab_exposure_ = ref_exposure;
+  if (!ct_ || dmv_ct_upload_new_image(ct_, ref_image_wh) != DMV_OK) { err_ = dmv_last_error(); return false; }
+  int32_t cnt[DMV_MAX_PYR_LEVELS] = {0};
+  if (dmv_ct_make_coarse_depth(ct_, n, Ku, Kv, new_idepth, HdiF, cnt) != DMV_OK) { err_ = dmv_last_error(); return false; }
+  for (int l = 0; l < levels_; l++) { pc_n[l] = cnt[l]; pc_u[l].clear(); pc_v[l].clear(); pc_idepth[l].clear(); pc_color[l].clear(); }
+  return true;
+}
+
 bool CoarseTracker::eval(int lvl, const SE3& refToNew, AffLight aff_g2l, float cutoffTH, bool wantGS, double res6[6], double H[64], double b[8]) {
   // operands of calcRes (CoarseTracker.cpp:L377-379): RKi = R * Ki[lvl] in float, t in float, affLL in float
   float R[9], t[3], RKi[9];

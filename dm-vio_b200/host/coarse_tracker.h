@@ -26,6 +26,10 @@ class CoarseTracker {
   // refdIp[l] = lastRef->dIp[l] (w_l*h_l*3 floats).
   void setCoarseTrackingRef(int n, const float* Ku, const float* Kv, const float* new_idepth, const float* HdiF, const float* const* refdIp,
                             AffLight lastRef_aff_g2l, float lastRef_ab_exposure);
+  // Same, entirely on the device (dmv_ct_make_coarse_depth): the reference keyframe's raw image is uploaded (pyramid built on the device),
+  // splat / pooling / dilation / compaction run there and the pc_* lists never leave the GPU.  Bit-identical lists.
+  bool setCoarseTrackingRefOnDevice(int n, const float* Ku, const float* Kv, const float* new_idepth, const float* HdiF, const float* ref_image_wh,
+                                    AffLight lastRef_aff_g2l, float lastRef_ab_exposure);
   // newFrame: raw image (pyramid built on the device) and its exposure
   bool setNewFrame(const float* image_wh, float ab_exposure);
   bool setNewFramePyramid(const float* const* dIp, float ab_exposure);

@@ -105,6 +105,11 @@ int dmvh_ct_set_ref(void* p, int n, const float* Ku, const float* Kv, const floa
 }
 int dmvh_ct_pc_n(void* p, int lvl) { return static_cast<CoarseTracker*>(p)->pc_n[lvl]; }
 int dmvh_ct_set_new_image(void* p, const float* image, float exposure) { return static_cast<CoarseTracker*>(p)->setNewFrame(image, exposure) ? 0 : -1; }
+int dmvh_ct_set_ref_device(void* p, int n, const float* Ku, const float* Kv, const float* nid, const float* HdiF, const float* ref_image, double ref_a,
+                           double ref_b, float ref_exposure) {
+  AffLight a; a.a = ref_a; a.b = ref_b;
+  return static_cast<CoarseTracker*>(p)->setCoarseTrackingRefOnDevice(n, Ku, Kv, nid, HdiF, ref_image, a, ref_exposure) ? 0 : -1;
+}
 void dmvh_ct_set_device_lm(void* p, int on) { static_cast<CoarseTracker*>(p)->useDeviceLM = on != 0; }
 int dmvh_ct_track(void* p, double R[9], double t[3], double* a, double* b, int coarsestLvl, const double minRes[5], double lastRes[5], double flow[3],
                   int* iterations, long long* evaluations) {

@@ -31,6 +31,8 @@ int dmvh_ct_set_ref(void* ct, int n, const float* Ku, const float* Kv, const flo
                     double ref_a, double ref_b, float ref_exposure);
 int dmvh_ct_pc_n(void* ct, int lvl);
 int dmvh_ct_set_new_image(void* ct, const float* image, float exposure);
+int dmvh_ct_set_ref_device(void* ct, int n, const float* Ku, const float* Kv, const float* new_idepth, const float* HdiF, const float* ref_image_wh,
+                           double ref_a, double ref_b, float ref_exposure); /* makeCoarseDepthL0 on the device */
 void dmvh_ct_set_device_lm(void* ct, int on); /* 1 (default): LM loop on the device (dmv_ct_track); 0: host loop */
 int dmvh_ct_track(void* ct, double R[9], double t[3], double* a, double* b, int coarsestLvl, const double minResForAbort[5],
                   double lastResiduals[5], double flow[3], int* iterations, long long* evaluations);

@@ -43,6 +43,7 @@ def lib():
         L.dmvh_ct_set_ref.argtypes = [vp, C.c_int, f32p, f32p, f32p, f32p, f32p, C.c_double, C.c_double, C.c_float]
         L.dmvh_ct_pc_n.argtypes = [vp, C.c_int]
         L.dmvh_ct_set_new_image.argtypes = [vp, f32p, C.c_float]
+        L.dmvh_ct_set_ref_device.argtypes = [vp, C.c_int, f32p, f32p, f32p, f32p, f32p, C.c_double, C.c_double, C.c_float]
         L.dmvh_ct_set_device_lm.argtypes = [vp, C.c_int]
         L.dmvh_ct_track.argtypes = [vp, f64p, f64p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, f64p, f64p, f64p, C.POINTER(C.c_int),
                                     C.POINTER(C.c_longlong)]
@@ -140,6 +141,14 @@ class CoarseTracker:
         rc = self.L.dmvh_ct_set_ref(self.h, len(Ku), _c(Ku, np.float32), _c(Kv, np.float32), _c(nid, np.float32), _c(HdiF, np.float32), ref, ref_a, ref_b, ref_exposure)
         if rc != 0:
             raise capi.DmvError("dmvh_ct_set_ref failed")
+        return [self.L.dmvh_ct_pc_n(self.h, l) for l in range(self.levels)]
+
+    def set_ref_device(self, Ku, Kv, nid, HdiF, img_ref, ref_a=0.0, ref_b=0.0, ref_exposure=1.0):
+        """setCoarseTrackingRef with makeCoarseDepthL0 on the device (the reference keyframe arrives as a raw image)"""
+        rc = self.L.dmvh_ct_set_ref_device(self.h, len(Ku), _c(Ku, np.float32), _c(Kv, np.float32), _c(nid, np.float32), _c(HdiF, np.float32),
+                                           _c(img_ref, np.float32).reshape(-1), ref_a, ref_b, ref_exposure)
+        if rc != 0:
+            raise capi.DmvError("dmvh_ct_set_ref_device failed")
         return [self.L.dmvh_ct_pc_n(self.h, l) for l in range(self.levels)]
 
     def set_new_image(self, img, exposure=1.0):

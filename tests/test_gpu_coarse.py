@@ -93,3 +93,33 @@ def test_edge_cases(capi, orc, synth):
     r, H, b, n = g.calc_res_gs(1, RKi, tf, affLL, 0.0, 20.0, True)
     assert r[1] == 0 and n == 0
     g.close()
+
+
+@pytest.mark.parametrize("cfg", [dict(seed=4321), dict(seed=77, w=160, h=120, npts=400), dict(seed=5, npts=6000)], ids=["640x480", "160x120", "dense"])
+def test_make_coarse_depth_on_device_bit_exact(capi, orc, synth, cfg):
+    """dmv_ct_make_coarse_depth == makeCoarseDepthL0: the pc_u / pc_v / pc_idepth / pc_color lists of every level equal the oracle's
+    (itself equal to the reference's compiled code) in values AND order."""
+    T = synth.make_tracking_pair(**cfg)
+    oct_ = orc.CoarseTracker(T["w"], T["h"], T["K"], 0)
+    oct_.make_coarse_depth(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
+    L = oct_.levels
+    g = capi.CT(T["w"], T["h"], L, max_points=65536)
+    for l in range(L):
+        g.upload_new(l, T["pyr_ref"][l])                  # the reference frame is the resident frame
+    pc_n = g.make_coarse_depth(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"])
+    for l in range(L):
+        po, pg = oct_.ref_points(l), g.get_ref(l)
+        assert pc_n[l] == len(po["u"])
+        for k in po:
+            np.testing.assert_array_equal(pg[k], po[k], err_msg=f"lvl{l} pc_{k}")
+    # colliding splats (several residuals in one pixel) are folded in input order
+    Ku = np.concatenate([T["Ku"], T["Ku"][:50], T["Ku"][:50], T["Ku"][:20]]); Kv = np.concatenate([T["Kv"], T["Kv"][:50], T["Kv"][:50], T["Kv"][:20]])
+    nid = np.concatenate([T["new_idepth"], T["new_idepth"][:50] * 1.1, T["new_idepth"][:50] * 0.9, T["new_idepth"][:20] * 1.3]).astype(np.float32)
+    Hd = np.concatenate([T["HdiF"], T["HdiF"][:50] * 2, T["HdiF"][:50] * 0.5, T["HdiF"][:20] * 3]).astype(np.float32)
+    oct_.make_coarse_depth(Ku, Kv, nid, Hd, T["pyr_ref"])
+    g.make_coarse_depth(Ku, Kv, nid, Hd)
+    for l in range(L):
+        po, pg = oct_.ref_points(l), g.get_ref(l)
+        for k in po:
+            np.testing.assert_array_equal(pg[k], po[k], err_msg=f"collisions lvl{l} pc_{k}")
+    g.close()

@@ -83,3 +83,19 @@ def test_track_newest_coarse(hostapi, orc, synth, levels, device_lm):
     assert abs(r_g["iterations"] - r_o["iterations"]) <= 2
     assert np.linalg.norm(r_g["t"] - T["t_true"]) < 5e-4
     g.close()
+
+
+def test_track_with_device_built_reference(hostapi, orc, synth):
+    """setCoarseTrackingRef entirely on the device (raw keyframe image in, pc_* lists never leave the GPU) gives the same track as the host-built reference."""
+    T = synth.make_tracking_pair(seed=4321)
+    L = T["levels"]
+    a = hostapi.CoarseTracker(T["w"], T["h"], T["K"], L)
+    b = hostapi.CoarseTracker(T["w"], T["h"], T["K"], L)
+    ca = a.set_ref(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
+    cb = b.set_ref_device(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["img_ref"])
+    assert ca == cb
+    a.set_new_image(T["img_new"]); b.set_new_image(T["img_new"])
+    ra, rb = a.track(np.eye(3), np.zeros(3), 0.0, 0.0), b.track(np.eye(3), np.zeros(3), 0.0, 0.0)
+    np.testing.assert_array_equal(ra["R"], rb["R"]); np.testing.assert_array_equal(ra["t"], rb["t"])
+    assert ra["iterations"] == rb["iterations"]
+    a.close(); b.close()

@@ -26,6 +26,18 @@ def main():
     L = T["levels"]
     g = hostapi.CoarseTracker(T["w"], T["h"], T["K"], L)
     counts = g.set_ref(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
+    # setCoarseTrackingRef (makeCoarseDepthL0, once per keyframe): host build + upload of the lists vs everything on the device
+    t_start = time.perf_counter()
+    for _ in range(20):
+        g.set_ref(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
+    set_ref_host_ms = (time.perf_counter() - t_start) / 20 * 1e3
+    for _ in range(3):
+        g.set_ref_device(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["img_ref"])
+    t_start = time.perf_counter()
+    for _ in range(50):
+        counts_dev = g.set_ref_device(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["img_ref"])
+    set_ref_dev_ms = (time.perf_counter() - t_start) / 50 * 1e3
+    assert counts_dev == counts
     R0, t0 = np.eye(3), np.zeros(3)
     # the two halves of a frame separately: upload + device pyramid, then tracking only (the CPU side is timed the same way)
     for _ in range(3):
@@ -73,6 +85,7 @@ def main():
     out = {"metric": "coarse tracking ms/frame (trackNewestCoarse, 640x480)", "levels": L, "ref_points_per_level": counts,
            "gpu_ms_per_frame": gpu_ms, "gpu_ms_per_frame_host_lm_loop": host_lm_ms, "gpu_evaluations_per_frame": ev / args.frames, "gpu_us_per_evaluation": gpu_ms * 1e3 / (ev / args.frames),
            "gpu_points_per_s": sum(counts) / L * (ev / args.frames) / (gpu_ms * 1e-3),
+           "set_ref_ms_device": set_ref_dev_ms, "set_ref_ms_host_build_plus_upload": set_ref_host_ms,
            "gpu_track_only_ms": track_only[True], "gpu_track_only_ms_host_lm_loop": track_only[False], "gpu_upload_pyramid_plus_one_eval_ms": upload_ms,
            "cpu_oracle_ms_per_frame": cpu_ms, "cpu_oracle_make_images_ms": cpu_pyr_ms, "cpu_threads": 1,
            "speedup_track_only": cpu_ms / track_only[True], "speedup_frame_incl_pyramid": (cpu_ms + cpu_pyr_ms) / gpu_ms, "speedup": cpu_ms / gpu_ms,
