@@ -12,7 +12,7 @@ import numpy as np
 from . import orc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libdso_ref.so")
+LIB_PATH = os.environ.get("DMV_REF_LIB", os.path.join(_HERE, "_ref", "libdso_ref.so"))  # DMV_REF_LIB: tools/eigen_order_sensitivity.py
 _LIB = None
 
 

@@ -10,21 +10,26 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 REF=${REF_ROOT:-/root/reference}
 if [ ! -d "$REF/src/dso" ]; then echo "ref_build: $REF/src/dso not present (GPU box): keeping the prebuilt oracle/_ref"; exit 0; fi
 OUT="$HERE/_ref"
-mkdir -p "$OUT/obj"
 CXX=${CXX:-g++}
 FLAGS="-std=c++17 -O3 -fPIC -w -I$HERE/shim -I$REF/src/dso -I$REF/src"
+LIBNAME=libdso_ref.so
+OBJDIR=obj
+if [ "$1" = "tree" ]; then  # sensitivity build: halves-splitting inner products in the stand-in Eigen (see oracle/shim/Eigen/Core)
+  FLAGS="$FLAGS -DEIGSHIM_TREE_REDUX"; LIBNAME=libdso_ref_tree.so; OBJDIR=obj_tree
+fi
+mkdir -p "$OUT/$OBJDIR"
 SRCS="dso/OptimizationBackend/AccumulatedTopHessian.cpp dso/OptimizationBackend/AccumulatedSCHessian.cpp dso/OptimizationBackend/EnergyFunctional.cpp
 dso/OptimizationBackend/EnergyFunctionalStructs.cpp dso/FullSystem/HessianBlocks.cpp dso/FullSystem/Residuals.cpp dso/FullSystem/ImmaturePoint.cpp
 dso/FullSystem/CoarseTracker.cpp dso/util/settings.cpp dso/util/globalCalib.cpp util/TimeMeasurement.cpp"
 OBJS=""
 for s in $SRCS; do
-  o="$OUT/obj/$(basename "$s" .cpp).o"
+  o="$OUT/$OBJDIR/$(basename "$s" .cpp).o"
   if [ ! -f "$o" ] || [ "$REF/src/$s" -nt "$o" ] || [ "$HERE/shim/Eigen/Core" -nt "$o" ] || [ "$HERE/shim/sophus/se3.hpp" -nt "$o" ]; then
     $CXX $FLAGS -c "$REF/src/$s" -o "$o" &
   fi
   OBJS="$OBJS $o"
 done
 wait
-$CXX $FLAGS -c "$HERE/ref_harness.cpp" -o "$OUT/obj/ref_harness.o"
-$CXX -shared -pthread -o "$OUT/libdso_ref.so" $OBJS "$OUT/obj/ref_harness.o"
-echo "ref_build: $OUT/libdso_ref.so"
+$CXX $FLAGS -c "$HERE/ref_harness.cpp" -o "$OUT/$OBJDIR/ref_harness.o"
+$CXX -shared -pthread -o "$OUT/$LIBNAME" $OBJS "$OUT/$OBJDIR/ref_harness.o"
+echo "ref_build: $OUT/$LIBNAME"
