@@ -60,6 +60,7 @@ def _declare(L):
     L.orc_win_apply_res.argtypes = [vp]
     L.orc_win_get_res_outputs.argtypes = [vp, i32p, f32p, f32p, f32p, vp, i32p, u8p, f32p]
     L.orc_win_accumulate.argtypes = [vp, C.c_int, f64p, f64p, f64p, f64p, f64p, f64p, C.POINTER(C.c_int)]
+    L.orc_win_marginalize.argtypes = [vp, C.c_int, i32p, C.c_int, f64p, f64p, f64p, f64p, f64p, f64p, C.POINTER(C.c_int), i32p, f32p, u8p]
     L.orc_win_get_point_outputs.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p]
     L.orc_win_solve.argtypes = [vp, C.c_int, C.c_double, C.c_int, f64p, f64p, f64p]
     L.orc_win_resubstitute.argtypes = [vp, f64p]
@@ -200,6 +201,20 @@ class Window:
         n = C.c_int(0)
         self.L.orc_win_accumulate(self.h, precision, o["HA"], o["bA"], o["HL"], o["bL"], o["Hsc"], o["bsc"], C.byref(n))
         o["resInA"] = n.value
+        return o
+
+    def marginalize(self, pts, precision=1):
+        """flagPointsForRemoval's linearize/applyRes/fixLinearizationF loop + marginalizePointsF on the listed points
+        (FullSystem.cpp:L826-838, EnergyFunctional.cpp:L678-742).  H = M - Msc, b = Mb - Mbsc (before margWeightFac); HM, bM after the update."""
+        N, nres = self.N, self.L.orc_win_nres(self.h)
+        pts = np.ascontiguousarray(pts, np.int32)
+        o = dict(M=np.zeros((N, N)), Mb=np.zeros(N), Msc=np.zeros((N, N)), Mbsc=np.zeros(N), HM=np.zeros((N, N)), bM=np.zeros(N),
+                 ngood=np.zeros(len(pts), np.int32), rtz=np.zeros((nres, 8), np.float32), isLinearized=np.zeros(nres, np.uint8))
+        n = C.c_int(0)
+        self.L.orc_win_marginalize(self.h, len(pts), pts, precision, o["M"], o["Mb"], o["Msc"], o["Mbsc"], o["HM"], o["bM"], C.byref(n),
+                                   o["ngood"], o["rtz"], o["isLinearized"])
+        o["resInM"] = n.value
+        o["H"], o["b"] = o["M"] - o["Msc"], o["Mb"] - o["Mbsc"]
         return o
 
     def point_outputs(self):

@@ -888,6 +888,73 @@ static void accumulateT(Window& W, ReducedSystem& sys) {
   }
 }
 
+// EFResidual::fixLinearizationF (EnergyFunctionalStructs.cpp:L88-114): res_toZeroF = resF - [JIdx*Jp | JabF] * delta
+static void fixLinearizationF(const Window& W, Residual& r, const Point& p) {
+  const RawJ& J = r.Jef;
+  const Mat<float, 1, 8>& dp = W.adHTdeltaF[r.host + W.nf() * r.target];
+  float d6x = 0, d6y = 0, d4x = 0, d4y = 0;
+  for (int i = 0; i < 6; i++) { d6x += J.Jpdxi[0][i] * dp[i]; d6y += J.Jpdxi[1][i] * dp[i]; }
+  for (int i = 0; i < 4; i++) { d4x += J.Jpdc[0][i] * W.cDeltaF[i]; d4y += J.Jpdc[1][i] * W.cDeltaF[i]; }
+  const float Jp_delta_x = d6x + d4x + J.Jpdd[0] * p.deltaF;
+  const float Jp_delta_y = d6y + d4y + J.Jpdd[1] * p.deltaF;
+  const float delta_a = dp[6], delta_b = dp[7];
+  for (int i = 0; i < PATTERN_NUM; i++) {
+    float rtz = J.resF[i];
+    rtz = rtz - J.JIdx[0][i] * Jp_delta_x;
+    rtz = rtz - J.JIdx[1][i] * Jp_delta_y;
+    rtz = rtz - J.JabF[0][i] * delta_a;
+    rtz = rtz - J.JabF[1][i] * delta_b;
+    r.res_toZeroF[i] = rtz;
+  }
+  r.isLinearized = true;
+}
+
+std::vector<int> Window::fixLinearization(const std::vector<int>& pts) {  // FullSystem.cpp:L826-838
+  std::vector<int> ngood(pts.size(), 0);
+  for (size_t k = 0; k < pts.size(); k++) {
+    Point& p = points[pts[k]];
+    for (int ri : p.residuals) {
+      Residual& r = residuals[ri];
+      r.state_NewEnergy = r.state_energy = 0;  // resetOOB (Residuals.h:L91-98)
+      r.state_NewState = RS_OUTLIER;
+      r.state_state = RS_IN;
+      linearizeOne<float>(*this, r, &r.Jnew);
+      r.isLinearized = false;
+      applyRes(r);
+      if (r.isActive()) { fixLinearizationF(*this, r, p); ngood[k]++; }
+    }
+  }
+  return ngood;
+}
+
+template <class T>
+static void marginalizeT(Window& W, const std::vector<int>& pts, ReducedSystem& sys) {
+  const int nf = W.nf();
+  sys.N = nf * 8 + CPARS;
+  std::vector<AccSet<T>> top(1), bot(1);
+  top[0].setZero(nf);
+  bot[0].setZero(nf);
+  for (int i : pts) {
+    Point& p = W.points[i];
+    p.priorF *= W.s.idepthFixPriorMargFac;
+    topAddPoint<T>(W, top[0], p, 2);
+    scAddPoint<T>(W, bot[0], p, false);
+  }
+  stitchTop<T>(W, top, sys.HA, sys.bA, false, &sys.resInA);
+  stitchSC<T>(W, bot, sys.Hsc, sys.bsc);
+}
+
+void Window::marginalizePoints(const std::vector<int>& pts, int precision, ReducedSystem& sys) {  // EnergyFunctional.cpp:L678-742
+  if (precision == 0) marginalizeT<float>(*this, pts, sys);
+  else marginalizeT<double>(*this, pts, sys);
+  const int N = sys.N;
+  if ((int)HM.rows != N) { HM = MatX(N, N); bM.assign(N, 0.0); }
+  for (int i = 0; i < N; i++) {
+    for (int j = 0; j < N; j++) HM(i, j) += (double)s.margWeightFac * (sys.HA(i, j) - sys.Hsc(i, j));
+    bM[i] += (double)s.margWeightFac * (sys.bA[i] - sys.bsc[i]);
+  }
+}
+
 void Window::accumulate(ReducedSystem& sys, int precision) {
   if (precision == 0) accumulateT<float>(*this, sys);
   else accumulateT<double>(*this, sys);

@@ -39,6 +39,7 @@ struct Settings {
   float initialCalibHessian = 5e9f;
   float frameEnergyTHConstWeight = 0.5f, frameEnergyTHN = 0.7f, frameEnergyTHFacMedian = 1.5f;
   float margWeightFac = 0.25f;
+  float minIdepthH_marg = 50;               // util/settings.cpp:L89
   float thOptIterations = 1.2f;
   int minOptIterations = 1;
   double solverModeDelta = 0.00001;
@@ -190,6 +191,16 @@ struct Window {
   void resubstitute(const VecX& x);  // EnergyFunctional.cpp:L267-321
   double calcLEnergy();              // EnergyFunctional.cpp:L349-431
   double calcMEnergy();              // EnergyFunctional.cpp:L324-346 (no GTSAM)
+
+  // Marginalisation of a point subset (makeKeyFrame's flagPointsForRemoval + marginalizePointsF):
+  //   fixLinearization(): the compute part of FullSystem::flagPointsForRemoval (FullSystem.cpp:L826-838) for every listed point:
+  //     resetOOB, linearize, applyRes(true) and EFResidual::fixLinearizationF (EnergyFunctionalStructs.cpp:L88-114) per residual;
+  //     returns ngoodRes per point.
+  //   marginalizePoints(): EnergyFunctional::marginalizePointsF (EnergyFunctional.cpp:L678-742) restricted to the listed points
+  //     (the caller's PS_MARGINALIZE set): priorF *= idepthFixPriorMargFac, addPoint<2> + SC addPoint(shiftPriorToZero = false),
+  //     stitch without priors; sys gets M/Mb (HA/bA) and Msc/Mbsc; HM += margWeightFac (M - Msc), bM likewise. Points are not erased.
+  std::vector<int> fixLinearization(const std::vector<int>& pts);
+  void marginalizePoints(const std::vector<int>& pts, int precision, ReducedSystem& sys);
 
   // FullSystemOptimize.cpp:L224-388
   void backupState();

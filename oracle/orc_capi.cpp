@@ -202,6 +202,28 @@ void orc_win_accumulate(OrcWin* o, int precision, double* HA, double* bA, double
   if (resInA) *resInA = sys.resInA;
 }
 
+// fixLinearization + marginalizePoints on the listed points (FullSystem.cpp:L826-838, EnergyFunctional.cpp:L678-742); rtz8 / isLin are
+// indexed like the residual list
+void orc_win_marginalize(OrcWin* o, int n, const int32_t* pts, int precision, double* M, double* Mb, double* Msc, double* Mbsc, double* HM,
+                         double* bM, int* resInM, int32_t* ngood, float* rtz8, uint8_t* isLin) {
+  Window& W = o->W;
+  std::vector<int> list(pts, pts + n);
+  std::vector<int> ng = W.fixLinearization(list);
+  if (ngood) for (int k = 0; k < n; k++) ngood[k] = ng[k];
+  for (size_t i = 0; i < W.residuals.size(); i++) {
+    const Residual& r = W.residuals[i];
+    if (isLin) isLin[i] = r.isLinearized ? 1 : 0;
+    if (rtz8) for (int c = 0; c < 8; c++) rtz8[8 * i + c] = r.isLinearized ? r.res_toZeroF[c] : 0.f;
+  }
+  ReducedSystem sys;
+  W.marginalizePoints(list, precision, sys);
+  const int N = sys.N;
+  auto cp = [&](const MatX& A, double* out) { if (out) std::memcpy(out, A.d.data(), sizeof(double) * N * N); };
+  auto cv = [&](const VecX& v, double* out) { if (out) std::memcpy(out, v.data(), sizeof(double) * N); };
+  cp(sys.HA, M); cv(sys.bA, Mb); cp(sys.Hsc, Msc); cv(sys.bsc, Mbsc); cp(W.HM, HM); cv(W.bM, bM);
+  if (resInM) *resInM = sys.resInA;
+}
+
 void orc_win_get_point_outputs(OrcWin* o, float* Hdd, float* bd, float* Hcd4, float* HdiF, float* bdSumF, float* step, float* idepth,
                                float* maxRelBaseline) {
   Window& W = o->W;

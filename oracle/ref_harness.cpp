@@ -17,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include <deque>
 #include <fstream>
@@ -112,7 +113,7 @@ void ref_win_destroy(RefWin* W) {
   W->ef->frames.clear();
   W->ef->allPoints.clear();
   if (W->ef->red) { delete W->ef->red; W->ef->red = 0; }
-  for (FrameHessian* f : W->frames) delete f;  // deletes its pointHessians, which delete their residuals
+  for (FrameHessian* f : W->frames) { FrameShell* sh = f ? f->shell : 0; delete f; delete sh; }  // a frame deletes its pointHessians, which delete their residuals
   delete W->ef;
   delete W->Hcalib;
   delete W;
@@ -131,7 +132,8 @@ void ref_win_set_setting(RefWin*, const char* name, double v) {
 void ref_win_set_frame(RefWin* W, int idx, const double R[9], const double t[3], const double state[10], const double state_zero[10], float ab_exposure,
                        float frameEnergyTH, int frameID, const float* dI) {
   FrameHessian* fh = new FrameHessian();
-  fh->shell = 0;
+  fh->shell = new FrameShell();  // EnergyFunctional::dropResidual counts into host->data->shell (EnergyFunctional.cpp:L510-513)
+  fh->shell->id = frameID;
   fh->idx = idx;
   fh->frameID = frameID;
   fh->ab_exposure = ab_exposure;
@@ -460,6 +462,49 @@ double ref_win_hot_iteration(RefWin* W, const double* x, int) {
     for (unsigned int i = 0; i < W->frames.size(); i++) fh->targetPrecalc[i].set(fh, W->frames[i], W->Hcalib);
   ef->setDeltaF(W->Hcalib);
   return E;
+}
+
+// Marginalisation of the listed points.  The per-point loop is the body of FullSystem::flagPointsForRemoval (FullSystem.cpp:L826-838; a
+// FullSystem member, so the loop is mirrored here around the reference's own resetOOB / linearize / applyRes / fixLinearizationF), then the
+// reference's EnergyFunctional::marginalizePointsF (EnergyFunctional.cpp:L678-742) runs unchanged on the flagged points.  It ERASES the
+// points from the energy functional: call this last on a window.  rtz8 / isLin are indexed like the residual list of ref_win_set_residuals.
+void ref_win_marginalize(RefWin* W, int n, const int32_t* pts, int, double* M, double* Mb, double* Msc, double* Mbsc, double* HM, double* bM,
+                         int* resInM, int32_t* ngood, float* rtz8, uint8_t* isLin) {
+  std::unordered_map<PointFrameResidual*, size_t> index;
+  for (size_t i = 0; i < W->residuals.size(); i++) index[W->residuals[i]] = i;
+  if (isLin) std::memset(isLin, 0, W->residuals.size());
+  if (rtz8) std::memset(rtz8, 0, sizeof(float) * 8 * W->residuals.size());
+  for (int k = 0; k < n; k++) {
+    PointHessian* ph = W->points[pts[k]];
+    int ngoodRes = 0;
+    for (PointFrameResidual* r : ph->residuals) {
+      r->resetOOB();
+      r->linearize(W->Hcalib);
+      r->efResidual->isLinearized = false;
+      r->applyRes(true);
+      if (r->efResidual->isActive()) {
+        r->efResidual->fixLinearizationF(W->ef);
+        ngoodRes++;
+      }
+      const size_t i = index[r];
+      if (isLin) isLin[i] = r->efResidual->isLinearized ? 1 : 0;
+      if (rtz8 && r->efResidual->isLinearized) for (int c = 0; c < 8; c++) rtz8[8 * i + c] = r->efResidual->res_toZeroF[c];
+    }
+    if (ngood) ngood[k] = ngoodRes;
+    ph->efPoint->stateFlag = EFPointStatus::PS_MARGINALIZE;
+  }
+  const int resBefore = W->ef->resInM;
+  // the two stitched halves are locals of marginalizePointsF: recover M - Msc from the change of HM (margWeightFac is a global setting)
+  MatXX HM0 = W->ef->HM; VecX bM0 = W->ef->bM;
+  W->ef->marginalizePointsF();
+  if (resInM) *resInM = W->ef->resInM - resBefore;
+  MatXX dH = (W->ef->HM - HM0) * (1.0 / setting_margWeightFac);
+  VecX db = (W->ef->bM - bM0) * (1.0 / setting_margWeightFac);
+  out_mat(dH, M); out_vec(db, Mb);  // M := M - Msc, Mb := Mb - Mbsc (Msc / Mbsc are reported as zero)
+  if (Msc) std::memset(Msc, 0, sizeof(double) * dH.rows() * dH.cols());
+  if (Mbsc) std::memset(Mbsc, 0, sizeof(double) * db.size());
+  out_mat(W->ef->HM, HM); out_vec(W->ef->bM, bM);
+  // the flagged points are gone from the energy functional (efPoint / efResidual are null now; ref_win_destroy copes)
 }
 
 double ref_win_calc_LEnergy(RefWin* W) { return W->ef->calcLEnergyF_MT(); }
