@@ -46,6 +46,11 @@ class BAActivateArgs(C.Structure):
                [("minObs", C.c_int)] + [(k, C.c_void_p) for k in ("status", "idepth", "res_state")]
 
 
+class BAMargArgs(C.Structure):
+    _fields_ = [("n", C.c_int32), ("point", C.c_void_p), ("adHTdeltaF", C.c_void_p), ("cDeltaF", C.c_float * 4), ("idepthFixPriorMargFac", C.c_float)] + \
+               [(k, C.c_void_p) for k in ("M", "Mb", "Msc", "Mbsc", "resInM", "ngoodRes", "res_toZeroF", "isLinearized")]
+
+
 class IPPoints(C.Structure):
     _fields_ = [("n", C.c_int)] + [(k, C.c_void_p) for k in ("u", "v", "color8", "weights8", "gradH4", "energyTH", "idepth_min", "idepth_max", "quality",
                                                               "lastTraceStatus", "lastTraceUV2", "lastTracePixelInterval")]
@@ -62,7 +67,7 @@ SYMBOLS = [
     "dmv_ba_set_window", "dmv_ba_set_points", "dmv_ba_set_residuals", "dmv_ba_set_adjoints", "dmv_ba_set_state", "dmv_ba_linearize",
     "dmv_ba_get_residual_outputs", "dmv_ba_get_target_energies", "dmv_ba_apply_res", "dmv_ba_accumulate", "dmv_ba_get_point_outputs",
     "dmv_ba_resubstitute", "dmv_ba_backup_points", "dmv_ba_restore_points", "dmv_ba_get_idepth", "dmv_ba_gn_step", "dmv_nccl_unique_id",
-    "dmv_ba_comm_init", "dmv_ba_activate_points", "dmv_ba_p2p_export", "dmv_ba_p2p_import", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e", "dmv_ba_debug_clocks",
+    "dmv_ba_comm_init", "dmv_ba_activate_points", "dmv_ba_marginalize_points", "dmv_ba_p2p_export", "dmv_ba_p2p_import", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e", "dmv_ba_debug_clocks",
     "dmv_ct_create", "dmv_ct_destroy", "dmv_ct_set_K", "dmv_ct_set_ref", "dmv_ct_make_coarse_depth", "dmv_ct_get_ref", "dmv_ct_upload_new", "dmv_ct_upload_new_image", "dmv_ct_set_huber",
     "dmv_ct_calc_res_gs", "dmv_ct_track", "dmv_ip_default_settings", "dmv_ct_init_points", "dmv_ct_trace_points", "dmv_ct_set_timing", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count",
 ]
@@ -101,6 +106,7 @@ def lib():
         L.dmv_nccl_unique_id.argtypes = [vp]
         L.dmv_ba_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
         L.dmv_ba_activate_points.argtypes = [vp, C.POINTER(BAActivateArgs)]
+        L.dmv_ba_marginalize_points.argtypes = [vp, C.POINTER(BAMargArgs)]
         L.dmv_ba_p2p_export.argtypes = [vp, vp]
         L.dmv_ba_p2p_import.argtypes = [vp, C.c_int, C.c_int, vp]
         L.dmv_ba_last_timing.argtypes = [vp, f32p]
@@ -316,6 +322,24 @@ class BA:
         args = BAActivateArgs(n, *[a.ctypes.data for a in keep], int(minObs), status.ctypes.data, idepth.ctypes.data, rs.ctypes.data)
         check(self.L.dmv_ba_activate_points(self.h, C.byref(args)))
         return status, idepth, rs
+
+    def marginalize_points(self, pts, adHTdeltaF, cDeltaF, prior_fac=600.0 * 600.0):
+        """flagPointsForRemoval's linearize / fixLinearizationF loop + marginalizePointsF for the listed points (dmv_ba_marginalize_points).
+        Returns dict: M, Mb, Msc, Mbsc, H = M - Msc, b = Mb - Mbsc, resInM, ngood [n], rtz [nres, 8], isLinearized [nres]."""
+        N = 8 * self.nf + 4
+        pts = _c(pts, np.int32)
+        ad = _c(adHTdeltaF, np.float32)
+        assert ad.size == self.nf * self.nf * 8
+        o = dict(M=np.zeros((N, N)), Mb=np.zeros(N), Msc=np.zeros((N, N)), Mbsc=np.zeros(N), ngood=np.zeros(len(pts), np.int32),
+                 rtz=np.zeros((self.nres, 8), np.float32), isLinearized=np.zeros(self.nres, np.uint8))
+        n = C.c_int32(0)
+        args = BAMargArgs(len(pts), pts.ctypes.data, ad.ctypes.data, (C.c_float * 4)(*[float(x) for x in cDeltaF]), float(prior_fac),
+                          o["M"].ctypes.data, o["Mb"].ctypes.data, o["Msc"].ctypes.data, o["Mbsc"].ctypes.data, C.addressof(n),
+                          o["ngood"].ctypes.data, o["rtz"].ctypes.data, o["isLinearized"].ctypes.data)
+        check(self.L.dmv_ba_marginalize_points(self.h, C.byref(args)))
+        o["resInM"] = n.value
+        o["H"], o["b"] = o["M"] - o["Msc"], o["Mb"] - o["Mbsc"]
+        return o
 
     def p2p_export(self):
         """64-byte CUDA IPC handle of this rank's exchange inbox (all-gather it, then p2p_import)."""

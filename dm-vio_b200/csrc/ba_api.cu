@@ -11,6 +11,7 @@
 
 namespace dmv {
 void launch_point_kernel(const BAWinDev& W, const BAIter& it, cudaStream_t s);
+void launch_point_kernel_marg(const BAWinDev& W, const BAIter& it, cudaStream_t s);
 void launch_stitch_kernel(const BAWinDev& W, cudaStream_t s);
 void launch_resub_kernel(const BAWinDev& W, const BAIter& it, int apply, double* sums, cudaStream_t s);
 void launch_repack(const float* src, float4* dst, int n, cudaStream_t s);
@@ -85,6 +86,13 @@ struct dmv_ba {
   // NCCL
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  // marginalisation launch (dmv_ba_marginalize_points): allocated on first use
+  BAMarg* d_marg = nullptr;
+  uint8_t* d_marg_mask = nullptr;
+  float* d_marg_rtz = nullptr;
+  double* d_marg_acc = nullptr;      // [acc | scratch the stitch zeroes]
+  double* d_marg_result = nullptr;
+  double* h_marg_result = nullptr;
   float* d_act = nullptr;      // point-activation staging (dmv_ba_activate_points)
   float* h_act = nullptr;
   int act_cap = 0;
@@ -260,6 +268,8 @@ int dmv_ba_destroy(dmv_ba* b) {
   for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   if (b->nccl_comm) dmv::nccl_destroy(b->nccl_comm);
   cudaFree(b->d_act); cudaFreeHost(b->h_act);
+  cudaFree(b->d_marg); cudaFree(b->d_marg_mask); cudaFree(b->d_marg_rtz); cudaFree(b->d_marg_acc); cudaFree(b->d_marg_result);
+  cudaFreeHost(b->h_marg_result);
   for (int r = 0; r < XCHG_MAXR; r++)
     if (b->xchg_map[r] && b->xchg_map[r] != b->xchg_own) cudaIpcCloseMemHandle(b->xchg_map[r]);
   cudaFree(b->xchg_own);
@@ -590,11 +600,18 @@ int dmv_ba_apply_res(dmv_ba* b) {
   return DMV_OK;
 }
 
+static void unpack_system(const dmv_ba* b, const double* r, double* H_A, double* b_A, double* H_sc, double* b_sc, int* resInA);
+
 int dmv_ba_accumulate(dmv_ba* b, double* H_A, double* b_A, double* H_sc, double* b_sc, int* resInA) {
   if (!b) return set_error(DMV_ERR_INVALID, "null handle");
   if (!b->have_committed) return set_error(DMV_ERR_STATE, "no committed linearisation (linearize + apply_res first)");
+  unpack_system(b, b->h_result[1 - b->tent], H_A, b_A, H_sc, b_sc, resInA);
+  return DMV_OK;
+}
+
+// result blob -> dense top system + Schur complement (shared by dmv_ba_accumulate and dmv_ba_marginalize_points)
+static void unpack_system(const dmv_ba* b, const double* r, double* H_A, double* b_A, double* H_sc, double* b_sc, int* resInA) {
   const int N = b->N, T = b->T;
-  const double* r = b->h_result[1 - b->tent];
   if (H_A) {
     std::memcpy(H_A, r, sizeof(double) * N * N);
     for (int i = 4; i < N; i++)  // the device fills H[frame,C]; mirror into H[C,frame] (AccumulatedTopHessian.h:L127-130)
@@ -614,6 +631,78 @@ int dmv_ba_accumulate(dmv_ba* b, double* H_A, double* b_A, double* H_sc, double*
   if (b_sc)
     for (int i = 0; i < N; i++) b_sc[i] = gram(i, N);
   if (resInA) *resInA = (int)sc[(size_t)b->ntiles * 16 + 1];
+}
+
+int dmv_ba_marginalize_points(dmv_ba* b, const dmv_ba_marg_args* a) {
+  int rc = check_ready(b);
+  if (rc != DMV_OK) return rc;
+  if (!a || a->n < 0 || (a->n > 0 && !a->point) || !a->adHTdeltaF) return set_error(DMV_ERR_INVALID, "null argument");
+  if (b->nranks > 1) return set_error(DMV_ERR_STATE, "sharded handle: marginalise per rank and sum (M - Msc) on the host");
+  CK(cudaSetDevice(b->device));
+  const int nf = b->nf, N = b->N;
+  const size_t nacc = acc_doubles(nf, b->ntiles), nres_d = result_doubles(N, b->ntiles), nslots = (size_t)MAXF * b->mp;
+  if (!b->d_marg) {
+    CK(cudaMalloc(&b->d_marg, sizeof(BAMarg)));
+    CK(cudaMalloc(&b->d_marg_mask, b->mp));
+    CK(cudaMalloc(&b->d_marg_rtz, sizeof(float) * 8 * nslots));
+    CK(cudaMalloc(&b->d_marg_acc, sizeof(double) * 2 * b->acc_cap));
+    const size_t maxres = result_doubles(8 * MAXF + 4, ((2 * MAXF + 2) * (2 * MAXF + 3)) / 2);
+    CK(cudaMalloc(&b->d_marg_result, sizeof(double) * maxres));
+    CK(cudaHostAlloc(&b->h_marg_result, sizeof(double) * maxres, cudaHostAllocDefault));
+  }
+  // tables
+  BAMarg M;
+  std::memset(&M, 0, sizeof(M));
+  for (int h = 0; h < nf; h++)
+    for (int t = 0; t < nf; t++) std::memcpy(M.adHTdelta[h * nf + t], a->adHTdeltaF + (size_t)(h + t * nf) * 8, sizeof(float) * 8);
+  std::memcpy(M.cDelta, a->cDeltaF, sizeof(M.cDelta));
+  M.priorFac = a->idepthFixPriorMargFac;
+  std::vector<uint8_t> mask(b->mp, 0);
+  for (int i = 0; i < a->n; i++) {
+    if (a->point[i] < 0 || a->point[i] >= b->npts) return set_error(DMV_ERR_INVALID, "point[%d] = %d out of range", i, a->point[i]);
+    mask[a->point[i]] = 1;
+  }
+  CK(cudaMemcpyAsync(b->d_marg, &M, sizeof(M), cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemcpyAsync(b->d_marg_mask, mask.data(), b->mp, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemsetAsync(b->d_marg_rtz, 0, sizeof(float) * 8 * nslots, b->stream));
+  CK(cudaMemsetAsync(b->d_marg_acc, 0, sizeof(double) * nacc, b->stream));
+  // descriptor: the production one with private accumulators / result blob, no fused step, no exchange
+  b->h_up->it.have_x = 0;
+  fill_descriptor(b);
+  BAWinDev& W = b->h_up->win;
+  W.acc = b->d_marg_acc;
+  W.acc_next = b->d_marg_acc + b->acc_cap;
+  W.result = b->d_marg_result;
+  W.result_host = nullptr;
+  W.xc.nranks = 1;
+  W.marg = b->d_marg; W.marg_mask = b->d_marg_mask; W.marg_rtz = b->d_marg_rtz;
+  launch_point_kernel_marg(W, b->h_up->it, b->stream);
+  launch_stitch_kernel(W, b->stream);
+  b->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(b->h_marg_result, b->d_marg_result, sizeof(double) * nres_d, cudaMemcpyDeviceToHost, b->stream));
+  std::vector<uint8_t> st(nslots);
+  std::vector<float> rtz;
+  CK(cudaMemcpyAsync(st.data(), b->d_st_new[b->tent], nslots, cudaMemcpyDeviceToHost, b->stream));
+  if (a->res_toZeroF) {
+    rtz.resize(8 * nslots);
+    CK(cudaMemcpyAsync(rtz.data(), b->d_marg_rtz, sizeof(float) * 8 * nslots, cudaMemcpyDeviceToHost, b->stream));
+  }
+  CK(cudaStreamSynchronize(b->stream));
+  b->have_tentative = false;  // the tentative buffers now hold the flagged points' re-linearisation only
+  unpack_system(b, b->h_marg_result, a->M, a->Mb, a->Msc, a->Mbsc, nullptr);
+  if (a->resInM) *a->resInM = (int)b->h_marg_result[(size_t)N * N + N + (size_t)b->ntiles * 16 + 1];
+  std::vector<int> good(b->mp, 0);
+  for (int i = 0; i < b->nres; i++) {
+    const int slot = b->res_slot[i], p = slot % b->mp;
+    const bool lin = mask[p] && st[slot] == RES_IN;
+    if (lin) good[p]++;
+    if (a->isLinearized) a->isLinearized[i] = lin ? 1 : 0;
+    if (a->res_toZeroF)
+      for (int c = 0; c < 8; c++) a->res_toZeroF[(size_t)i * 8 + c] = lin ? rtz[(size_t)slot * 8 + c] : 0.f;
+  }
+  if (a->ngoodRes)
+    for (int i = 0; i < a->n; i++) a->ngoodRes[i] = good[a->point[i]];
   return DMV_OK;
 }
 

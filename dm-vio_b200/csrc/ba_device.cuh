@@ -48,6 +48,14 @@ struct BAXchg {
   uint4* inbox[XCHG_MAXR];            // rank r's inbox as mapped in THIS process ([rank] = own)
 };
 
+// tables of a marginalisation launch (dmv_ba_marginalize_points -> ba_point_kernel<.., MARG = true>); device memory, never read in production
+struct BAMarg {
+  float adHTdelta[MAXF * MAXF][8];  // [h*nf + t]: (state - state_zero)_h^T adHostF + (..)_t^T adTargetF  (EnergyFunctional.cpp:L175-198)
+  float cDelta[4];                  // calibration value - value_zero (scaled), as float
+  float priorFac;                   // setting_idepthFixPriorMargFac (EnergyFunctional.cpp:L693)
+  int pad[3];
+};
+
 struct BAWinDev {
   int nf, npts, nchunks, w, h, N, NW, T, ntiles, mp, P;  // mp = capacity (row pitch of the [target][point] slot arrays)
   float huberTH, outlierTHSum;
@@ -90,6 +98,10 @@ struct BAWinDev {
   double* result;            // H_top N*N | b_top N | Schur tiles ntiles*16 | ACC_MISC tail
   double* result_host;       // pinned host mirror of the result blob written by the stitch kernel itself (zero-copy), or nullptr
   BAXchg xc;                 // nranks <= 1: no exchange
+  // marginalisation launch only (nullptr otherwise)
+  const BAMarg* marg;
+  const uint8_t* marg_mask;  // [p] 1 = point is being marginalised
+  float* marg_rtz;           // [slot][8] EFResidual::res_toZeroF of the residuals linearised by the launch
 };
 
 // result blob: H_top N*N | b_top N | raw Schur Gram tiles ntiles*16 | ACC_MISC counters

@@ -30,7 +30,26 @@ struct PointSmem {
   float misc[MAXF * (P / 4)][4];
 };
 
-template <int P, int ITER>
+// geometric Jacobians of the centre pixel (Residuals.cpp:L113-156): x = d(Ku)/d[C4|xi6], y = d(Kv)/d[C4|xi6], dd = d(Ku,Kv)/d(idepth)
+__device__ __forceinline__ void geo_jac(const float* pc, float Kl0, float Kl1, float cu, float cv, float drescale, float new_idepth, float fx,
+                                        float fy, float fxi, float fyi, float x[10], float y[10], float& ddx, float& ddy) {
+  const float dCx2 = drescale * (pc[18] * cu - pc[12]);
+  const float dCx3 = fx * drescale * (pc[19] * cu - pc[13]) * fyi;
+  const float dCy2 = fy * drescale * (pc[18] * cv - pc[15]) * fxi;
+  const float dCy3 = drescale * (pc[19] * cv - pc[16]);
+  x[0] = (Kl0 * dCx2 + cu) * 50.0f; x[1] = (Kl1 * dCx3) * 50.0f; x[2] = (dCx2 + 1.f) * 50.0f; x[3] = dCx3 * 50.0f;
+  y[0] = (Kl0 * dCy2) * 50.0f; y[1] = (Kl1 * dCy3 + cv) * 50.0f; y[2] = dCy2 * 50.0f; y[3] = (dCy3 + 1.f) * 50.0f;
+  x[4] = new_idepth * fx; x[5] = 0.f; x[6] = -new_idepth * cu * fx; x[7] = -cu * cv * fx; x[8] = (1.f + cu * cu) * fx; x[9] = -cv * fx;
+  y[4] = 0.f; y[5] = new_idepth * fy; y[6] = -new_idepth * cv * fy; y[7] = -(1.f + cv * cv) * fy; y[8] = cu * cv * fy; y[9] = cu * fy;
+  ddx = drescale * (pc[21] - pc[23] * cu) * fx;  // Jpdd (SCALE_IDEPTH = 1)
+  ddy = drescale * (pc[22] - pc[23] * cv) * fy;
+}
+
+// MARG = true is the marginalisation launch (dmv_ba_marginalize_points): only the points flagged in W.marg_mask take part, their
+// residuals are re-linearised from scratch (PointFrameResidual::resetOOB; FullSystem.cpp:L826-838), EFResidual::fixLinearizationF
+// (EnergyFunctionalStructs.cpp:L88-114) turns resF into res_toZeroF, and the accumulation is AccumulatedTopHessian::addPoint<2> +
+// AccumulatedSCHessian::addPoint(p, shiftPriorToZero = false) with priorF * idepthFixPriorMargFac (EnergyFunctional.cpp:L678-742).
+template <int P, int ITER, bool MARG>
 __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
     ba_point_kernel(const __grid_constant__ BAWinDev W, const __grid_constant__ BAIter it) {
   constexpr int WQ = P / (4 * ITER);  // warps per target
@@ -69,7 +88,12 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
   }
   // the thread that finalises point pl_b in phase B fetches its prior now
   const int pl_b = nthreads - 1 - tid;
-  const float prior_b = (pl_b < ch_count) ? __ldg(W.priorF + ch_start + pl_b) : 0.f;
+  float prior_b = (pl_b < ch_count) ? __ldg(W.priorF + ch_start + pl_b) : 0.f;
+  bool masked_b = true;
+  if constexpr (MARG) {
+    masked_b = (pl_b < ch_count) && __ldg(W.marg_mask + ch_start + pl_b) != 0;
+    prior_b *= __ldg(&W.marg->priorFac);
+  }
   STAMP(6);
 
   // ---------------------------------------------------------------- phase A
@@ -104,8 +128,14 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
       const int p = ch_start + pl;
       const int slot = t * mp + p;
       // ---- direct loads (all independent: one memory round trip)
-      const int st = valid ? (int)__ldg(W.st_in + slot) : RES_NONE;
-      const float en_old = __ldg(W.en_in + slot);
+      int st = valid ? (int)__ldg(W.st_in + slot) : RES_NONE;
+      float en_old = __ldg(W.en_in + slot);
+      bool masked = true;
+      if constexpr (MARG) {  // resetOOB: every existing residual of a flagged point starts as IN with zero energy; other points sit out
+        masked = valid && __ldg(W.marg_mask + p) != 0;
+        st = (masked && st != RES_NONE) ? RES_IN : RES_NONE;
+        en_old = 0.f;
+      }
       const float2 uv = __ldg(W.uv + p);
       const float col = __ldg(W.color + (size_t)p * 8 + j);
       const float wgt = __ldg(W.weights + (size_t)p * 8 + j);
@@ -202,9 +232,22 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
       const float JI00 = group_sum8(gx * gx), JI11 = group_sum8(gy * gy), JI10 = group_sum8(gx * gy);
       const float JabJI00 = group_sum8(ja * gx), JabJI01 = group_sum8(ja * gy), JabJI10 = group_sum8(jb * gx), JabJI11 = group_sum8(jb * gy);
       const float Jab00 = group_sum8(ja * ja), Jab01 = group_sum8(ja * jb), Jab11 = group_sum8(jb * jb);
-      const float JIr0 = group_sum8(resF * gx), JIr1 = group_sum8(resF * gy);
-      const float Jabr0 = group_sum8(resF * jaF), Jabr1 = group_sum8(resF * jbF);
-      const float rr = group_sum8(resF * resF);
+      float resAcc = resF;  // what the right-hand sides are built from: resF, or res_toZeroF when marginalising
+      float x[10], y[10], ddx, ddy;
+      if constexpr (MARG) {
+        geo_jac(pc, Kl0, Kl1, cu, cv, drescale, new_idepth, fx, fy, fxi, fyi, x, y, ddx, ddy);
+        const float* dp = W.marg->adHTdelta[h * nf + t];
+        const float* cD = W.marg->cDelta;
+        const float dlt = idepth - idz;  // EFPoint::deltaF
+        const float jpx = (x[4] * dp[0] + x[5] * dp[1] + x[6] * dp[2] + x[7] * dp[3] + x[8] * dp[4] + x[9] * dp[5]) +
+                          (x[0] * cD[0] + x[1] * cD[1] + x[2] * cD[2] + x[3] * cD[3]) + ddx * dlt;
+        const float jpy = (y[4] * dp[0] + y[5] * dp[1] + y[6] * dp[2] + y[7] * dp[3] + y[8] * dp[4] + y[9] * dp[5]) +
+                          (y[0] * cD[0] + y[1] * cD[1] + y[2] * cD[2] + y[3] * cD[3]) + ddy * dlt;
+        resAcc = live ? (((resF - gx * jpx) - gy * jpy) - jaF * dp[6]) - jbF * dp[7] : 0.f;
+      }
+      const float JIr0 = group_sum8(resAcc * gx), JIr1 = group_sum8(resAcc * gy);
+      const float Jabr0 = group_sum8(resAcc * jaF), Jabr1 = group_sum8(resAcc * jbF);
+      const float rr = group_sum8(resAcc * resAcc);
       const float energy = group_sum8(e_px);
       // the reference sums hw*hw*(hitColor[1]^2+hitColor[2]^2) with hitColor already multiplied by hw (Residuals.cpp:L217-244)
       const float wJI2 = group_sum8(hw * hw * (gx * gx + gy * gy));
@@ -226,7 +269,10 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
         e_sum += newEnergy;
         n_in += in; n_oob += (newState == RES_OOB); n_outl += (newState == RES_OUTLIER);
       }
-      if (valid && j == 0) {
+      if constexpr (MARG) {
+        if (masked) W.marg_rtz[(size_t)slot * 8 + j] = in ? resAcc : 0.f;
+      }
+      if (valid && j == 0 && masked) {
         W.st_new[slot] = (uint8_t)newState;
         W.en_new[slot] = newEnergy;
         W.en_wo[slot] = (st == RES_NONE || !live) ? -1.f : energy;
@@ -235,20 +281,7 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
       }
 
       if (in) {
-        // geometric Jacobians of the centre pixel (Residuals.cpp:L113-156): x = d(Ku)/d[C4|xi6], y = d(Kv)/d[C4|xi6]
-        float x[10], y[10];
-        {
-          const float dCx2 = drescale * (pc[18] * cu - pc[12]);
-          const float dCx3 = fx * drescale * (pc[19] * cu - pc[13]) * fyi;
-          const float dCy2 = fy * drescale * (pc[18] * cv - pc[15]) * fxi;
-          const float dCy3 = drescale * (pc[19] * cv - pc[16]);
-          x[0] = (Kl0 * dCx2 + cu) * 50.0f; x[1] = (Kl1 * dCx3) * 50.0f; x[2] = (dCx2 + 1.f) * 50.0f; x[3] = dCx3 * 50.0f;
-          y[0] = (Kl0 * dCy2) * 50.0f; y[1] = (Kl1 * dCy3 + cv) * 50.0f; y[2] = dCy2 * 50.0f; y[3] = (dCy3 + 1.f) * 50.0f;
-          x[4] = new_idepth * fx; x[5] = 0.f; x[6] = -new_idepth * cu * fx; x[7] = -cu * cv * fx; x[8] = (1.f + cu * cu) * fx; x[9] = -cv * fx;
-          y[4] = 0.f; y[5] = new_idepth * fy; y[6] = -new_idepth * cv * fy; y[7] = -(1.f + cv * cv) * fy; y[8] = cu * cv * fy; y[9] = cu * fy;
-        }
-        const float ddx = drescale * (pc[21] - pc[23] * cu) * fx;  // Jpdd (SCALE_IDEPTH = 1)
-        const float ddy = drescale * (pc[22] - pc[23] * cv) * fy;
+        if constexpr (!MARG) geo_jac(pc, Kl0, Kl1, cu, cv, drescale, new_idepth, fx, fy, fxi, fyi, x, y, ddx, ddy);
         // EFResidual::takeDataF (EnergyFunctionalStructs.cpp:L39-49) and the per-point terms of addPoint (AccumulatedTopHessian.cpp:L131-135)
         const float J0 = JI00 * ddx + JI10 * ddy, J1 = JI10 * ddx + JI11 * ddy;  // JIdx2 * Jpdd
         if (j == 0) {
@@ -366,16 +399,18 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
         float H = Hdd + prior;
         if (H < 1e-10f) H = 1e-10f;
         HdiF = 1.0f / H;
-        bdSum = bd + prior * (S.id[pl] - S.idz[pl]);
+        bdSum = MARG ? bd : bd + prior * (S.id[pl] - S.idz[pl]);  // shiftPriorToZero (AccumulatedSCHessian.cpp:L47-50)
         w0 = Hcd0; w1 = Hcd1; w2 = Hcd2; w3 = Hcd3;
       }
       S.Wv[pl][0] = w0; S.Wv[pl][1] = w1; S.Wv[pl][2] = w2; S.Wv[pl][3] = w3;
       S.Wv[pl][N] = bdSum;
       for (int c = N + 1; c < W.NW; c++) S.Wv[pl][c] = 0.f;  // padding columns of the last 4x4 tiles
       S.hdi[pl] = HdiF;
-      float4* po = reinterpret_cast<float4*>(W.pout + (size_t)p * 8);
-      po[0] = make_float4(Hdd, bd, Hcd0, Hcd1);
-      po[1] = make_float4(Hcd2, Hcd3, HdiF, bdSum);
+      if (masked_b) {
+        float4* po = reinterpret_cast<float4*>(W.pout + (size_t)p * 8);
+        po[0] = make_float4(Hdd, bd, Hcd0, Hcd1);
+        po[1] = make_float4(Hcd2, Hcd3, HdiF, bdSum);
+      }
     }
   }
   // (b) Schur vector entries: (point, frame, k)
@@ -453,24 +488,31 @@ __global__ void __launch_bounds__(32 * MAXF * (P / (4 * ITER)), 1)
 
 }
 
-template <int P, int ITER>
+template <int P, int ITER, bool MARG>
 static void launch_cfg(const BAWinDev& W, const BAIter& it, cudaStream_t s) {
   static bool configured = false;
   const int smem = (int)sizeof(PointSmem<P>);
   if (!configured) {
-    cudaFuncSetAttribute(ba_point_kernel<P, ITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(ba_point_kernel<P, ITER, MARG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     configured = true;
   }
   const int WQ = P / (4 * ITER);
   dim3 grid(W.nchunks), block(32 * WQ * (W.nf < 2 ? 2 : W.nf));
-  ba_point_kernel<P, ITER><<<grid, block, smem, s>>>(W, it);
+  ba_point_kernel<P, ITER, MARG><<<grid, block, smem, s>>>(W, it);
 }
 
 void launch_point_kernel(const BAWinDev& W, const BAIter& it, cudaStream_t s) {
-  if (W.P == 8) launch_cfg<8, 1>(W, it, s);
-  else if (W.P == 32) launch_cfg<32, 2>(W, it, s);
-  else if (W.iter2) launch_cfg<16, 2>(W, it, s);
-  else launch_cfg<16, 1>(W, it, s);
+  if (W.P == 8) launch_cfg<8, 1, false>(W, it, s);
+  else if (W.P == 32) launch_cfg<32, 2, false>(W, it, s);
+  else if (W.iter2) launch_cfg<16, 2, false>(W, it, s);
+  else launch_cfg<16, 1, false>(W, it, s);
+}
+
+// marginalisation launch: same chunking as the production kernel, W.marg / W.marg_mask / W.marg_rtz set, it.have_x = 0
+void launch_point_kernel_marg(const BAWinDev& W, const BAIter& it, cudaStream_t s) {
+  if (W.P == 8) launch_cfg<8, 1, true>(W, it, s);
+  else if (W.P == 32) launch_cfg<32, 2, true>(W, it, s);
+  else launch_cfg<16, 1, true>(W, it, s);
 }
 
 }  // namespace dmv

@@ -35,6 +35,16 @@ int dmvh_window_add_frame(void* p, const float* data, int is_image, const double
   return is_image ? W->insertFrame(data, T, state, state_zero, ab_exposure, frameID) : W->insertFrameDI(data, T, state, state_zero, ab_exposure, frameID);
 }
 void dmvh_window_drop_frame(void* p, int idx) { static_cast<WindowBA*>(p)->dropFrame(idx); }
+int dmvh_window_marginalize_points(void* p, int nmarg, const int32_t* marg, int ndrop, const int32_t* drop, double* HM, double* bM, int* npts_left,
+                                   int* nres_left) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  const int rc = W->marginalizePointsF(std::vector<int>(marg, marg + nmarg), std::vector<int>(drop, drop + ndrop));
+  if (HM) std::memcpy(HM, W->HM.data(), sizeof(double) * W->HM.size());
+  if (bM) std::memcpy(bM, W->bM.data(), sizeof(double) * W->bM.size());
+  if (npts_left) *npts_left = (int)W->points.size();
+  if (nres_left) *nres_left = (int)W->activeResiduals.size();
+  return rc;
+}
 int dmvh_window_set_points(void* p, int n, const int32_t* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
                            const float* color8, const float* weights8, const uint8_t* hdp) {
   static_cast<WindowBA*>(p)->insertPoints(n, host, u, v, idepth, idepth_zero, color8, weights8, hdp);

@@ -24,6 +24,10 @@ void dmvh_window_get_tables(void* win, float* precalc, double* adHost, double* a
 void dmvh_window_get_system(void* win, double* HA, double* bA, double* Hsc, double* bsc, double* lastHS, double* lastbS);
 void dmvh_window_get_states(void* win, double* states10, float* idepth, float* frameEnergyTH);
 double dmvh_window_energy_L(void* win);
+/* WindowBA::marginalizePointsF: marginalises `marg` (dropping the badly constrained ones) and drops `drop`; erases them, re-uploads the window.
+ * Returns the resInM increment (-1 on error); HM/bM (N*N, N) and the surviving point count are written if non-NULL. */
+int dmvh_window_marginalize_points(void* win, int nmarg, const int32_t* marg, int ndrop, const int32_t* drop, double* HM, double* bM, int* npts_left,
+                                   int* nres_left);
 
 void* dmvh_ct_create(int w, int h, int levels, int max_points, int device, const double calib_value_scaled[4]);
 void dmvh_ct_destroy(void* ct);

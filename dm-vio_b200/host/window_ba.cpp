@@ -216,6 +216,87 @@ void WindowBA::setPrecalcValues() {  // FullSystem.cpp:L1670-1680 -> FrameFrameP
     for (int i = 0; i < 8; i++) { f.delta[i] = f.state[i] - f.state_zero[i]; f.delta_prior[i] = f.state[i]; }
 }
 
+std::vector<float> WindowBA::adHTdeltaF() const {  // EnergyFunctional.cpp:L175-187
+  const int n = nf();
+  std::vector<float> out((size_t)n * n * 8, 0.f);
+  for (int h = 0; h < n; h++)
+    for (int t = 0; t < n; t++) {
+      const int idx = h + t * n;
+      const FrameHessian &fh = frameHessians[h], &ft = frameHessians[t];
+      for (int c = 0; c < 8; c++) {
+        float sacc = 0, tacc = 0;
+        for (int k = 0; k < 8; k++) sacc += (float)(fh.state[k] - fh.state_zero[k]) * (float)adHost[(size_t)idx * 64 + k * 8 + c];
+        for (int k = 0; k < 8; k++) tacc += (float)(ft.state[k] - ft.state_zero[k]) * (float)adTarget[(size_t)idx * 64 + k * 8 + c];
+        out[(size_t)idx * 8 + c] = sacc + tacc;
+      }
+    }
+  return out;
+}
+
+int WindowBA::marginalizePointsF(const std::vector<int>& toMargIn, const std::vector<int>& toDrop) {
+  if (!ba_) return -1;
+  const int n = nf(), N = 8 * n + CPARS, np = (int)points.size();
+  // FullSystem.cpp:L840-850: a candidate is marginalised only if its inverse depth is well constrained, otherwise dropped
+  std::vector<float> HdiF(np, 0.f);
+  if (np > 0) dmv_ba_get_point_outputs(ba_, nullptr, nullptr, nullptr, HdiF.data(), nullptr);  // no linearisation yet: idepth_hessian = 0, candidates are dropped
+  {  // the residual states live on the device (applyRes_Reductor commits there): pull them for the re-upload below
+    const int nr = (int)activeResiduals.size();
+    std::vector<int32_t> ns(nr);
+    std::vector<float> ne(nr);
+    if (nr > 0 && dmv_ba_get_residual_outputs(ba_, ns.data(), ne.data(), nullptr, nullptr, nullptr) == DMV_OK)
+      for (int i = 0; i < nr; i++) { activeResiduals[i].state_state = ns[i]; activeResiduals[i].state_energy = ne[i]; }
+  }
+  std::vector<int32_t> toMarg;
+  std::vector<char> erase(np, 0);
+  for (int i : toDrop) if (i >= 0 && i < np) erase[i] = 1;
+  for (int i : toMargIn) {
+    if (i < 0 || i >= np) continue;
+    erase[i] = 1;
+    const float idepth_hessian = HdiF[i] > 0 ? 1.0f / HdiF[i] : 0.f;  // AccumulatedSCHessian.cpp:L42-50
+    if (idepth_hessian > s.setting_minIdepthH_marg) toMarg.push_back(i);
+  }
+  int added = 0;
+  if (!toMarg.empty()) {
+    const std::vector<float> ad = adHTdeltaF();
+    std::vector<double> M((size_t)N * N), Mb(N), Msc((size_t)N * N), Mbsc(N);
+    dmv_ba_marg_args a;
+    a.n = (int32_t)toMarg.size(); a.point = toMarg.data(); a.adHTdeltaF = ad.data();
+    for (int i = 0; i < 4; i++) a.cDeltaF[i] = (float)Hcalib.value_minus_value_zero[i];
+    a.idepthFixPriorMargFac = s.setting_idepthFixPriorMargFac;
+    a.M = M.data(); a.Mb = Mb.data(); a.Msc = Msc.data(); a.Mbsc = Mbsc.data();
+    int32_t nres = 0;
+    a.resInM = &nres; a.ngoodRes = nullptr; a.res_toZeroF = nullptr; a.isLinearized = nullptr;
+    if (dmv_ba_marginalize_points(ba_, &a) != DMV_OK) { fail("dmv_ba_marginalize_points"); return -1; }
+    if ((int)HM.size() != N * N) { HM.assign((size_t)N * N, 0.0); bM.assign(N, 0.0); }
+    for (size_t i = 0; i < (size_t)N * N; i++) HM[i] += (double)s.setting_margWeightFac * (M[i] - Msc[i]);   // EnergyFunctional.cpp:L729-730
+    for (int i = 0; i < N; i++) bM[i] += (double)s.setting_margWeightFac * (Mb[i] - Mbsc[i]);
+    added = nres;
+    resInM += nres;
+  }
+  // EnergyFunctional::removePoint for every listed point: erase it and its residuals, renumber, upload the smaller window
+  std::vector<int> newIndex(np, -1);
+  std::vector<PointHessian> keep;
+  keep.reserve(np);
+  for (int i = 0; i < np; i++)
+    if (!erase[i]) { newIndex[i] = (int)keep.size(); keep.push_back(points[i]); }
+  // the device keeps the optimised depths: pull them before the re-upload
+  if (np > 0) {
+    std::vector<float> id(np);
+    getIdepths(id.data());
+    for (int i = 0; i < np; i++)
+      if (newIndex[i] >= 0) { keep[newIndex[i]].idepth = id[i]; keep[newIndex[i]].idepth_zero = id[i]; keep[newIndex[i]].idepth_backup = id[i]; }
+  }
+  std::vector<PointFrameResidual> rkeep;
+  rkeep.reserve(activeResiduals.size());
+  for (const PointFrameResidual& r : activeResiduals)
+    if (newIndex[r.point] >= 0) { rkeep.push_back(r); rkeep.back().point = newIndex[r.point]; }
+  points.swap(keep);
+  activeResiduals.swap(rkeep);
+  if (!makeIDX()) return -1;
+  setAdjointsF();  // makeIDX re-binds the window on the device: the adjoints go with it (FullSystem::makeKeyFrame calls ef->setAdjointsF next)
+  return err_.empty() ? added : -1;
+}
+
 void WindowBA::fillState(dmv_ba_state* st, float* th) const {
   for (int i = 0; i < 4; i++) { st->calib[i] = Hcalib.value_scaledf[i]; st->calib[4 + i] = Hcalib.value_scaledi[i]; }
   for (int f = 0; f < nf(); f++) th[f] = frameHessians[f].frameEnergyTH;

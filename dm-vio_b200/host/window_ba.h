@@ -27,6 +27,7 @@ struct Settings {  // util/settings.cpp:L60-160
   float setting_frameEnergyTHConstWeight = 0.5f, setting_frameEnergyTHN = 0.7f, setting_frameEnergyTHFacMedian = 1.5f;
   float setting_thOptIterations = 1.2f;
   int setting_minOptIterations = 1;
+  float setting_idepthFixPriorMargFac = 600 * 600, setting_margWeightFac = 0.5f * 0.5f, setting_minIdepthH_marg = 50;  // settings.cpp:L68, L118, L89
 };
 
 struct AffLight {  // util/NumType.h:L166-192
@@ -111,6 +112,17 @@ class WindowBA {
   bool doStepFromBackup();             // FullSystemOptimize.cpp:L224-317 (point part deferred to the next linearizeAll: fused on the GPU)
   void loadSateBackup();               // FullSystemOptimize.cpp:L371-388
   int optimize(int mnumOptIts, std::vector<double>* energyLog = nullptr);  // FullSystemOptimize.cpp:L417-647 (no IMU); returns #iterations
+
+  // ---- keyframe marginalisation of points (FullSystem::makeKeyFrame: flagPointsForRemoval -> marginalizePointsF / dropPointsF)
+  // toMarg: the caller's PS_MARGINALIZE candidates (PointHessian::isOOB && isInlierNew, or host frame flagged); for each the device runs
+  // resetOOB / linearize / applyRes / fixLinearizationF (FullSystem.cpp:L826-838) and EnergyFunctional::marginalizePointsF
+  // (EnergyFunctional.cpp:L678-742); candidates whose idepth_hessian (1 / HdiF of the last accumulation) is <= setting_minIdepthH_marg
+  // are dropped instead (FullSystem.cpp:L840-850).  toDrop: PS_DROP points (EnergyFunctional::dropPointsF).  HM / bM are updated with
+  // setting_margWeightFac, all listed points and their residuals are erased and the window is re-uploaded (makeIDX).  Returns the number
+  // of residuals that entered the prior (resInM increment), -1 on error.
+  int marginalizePointsF(const std::vector<int>& toMarg, const std::vector<int>& toDrop = std::vector<int>());
+  std::vector<float> adHTdeltaF() const;   // EnergyFunctional::setDeltaF (EnergyFunctional.cpp:L175-187), [h + t*nf][8]
+  int resInM = 0;
 
   // ---- results
   void syncResidualStates();           // pulls state_NewState / energies / centerProjectedTo of the last linearisation from the device

@@ -24,6 +24,7 @@ def lib():
         L.dmvh_window_error.argtypes = [vp]
         L.dmvh_window_add_frame.argtypes = [vp, f32p, C.c_int, f64p, f64p, f64p, f64p, C.c_float, C.c_int]
         L.dmvh_window_drop_frame.argtypes = [vp, C.c_int]
+        L.dmvh_window_marginalize_points.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.dmvh_window_set_points.argtypes = [vp, C.c_int, i32p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
         L.dmvh_window_set_residuals.argtypes = [vp, C.c_int, i32p, i32p]
         L.dmvh_window_prepare.argtypes = [vp]
@@ -112,6 +113,19 @@ class WindowBA:
         log = np.zeros(64)
         n = self.L.dmvh_window_optimize(self.h, its, log, 64)
         return n, log[log >= 0]
+
+    def marginalize_points(self, marg, drop=()):
+        """WindowBA::marginalizePointsF: marginalises `marg` into HM/bM (badly constrained ones are dropped), drops `drop`, erases all of them
+        and re-uploads the window.  Returns dict(resInM, HM, bM, npts, nres)."""
+        N = self.N
+        m, d = _c(np.asarray(marg, np.int32), np.int32), _c(np.asarray(drop, np.int32), np.int32)
+        HM, bM = np.zeros((N, N)), np.zeros(N)
+        npl, nrl = C.c_int(0), C.c_int(0)
+        rc = self.L.dmvh_window_marginalize_points(self.h, len(m), m.ctypes.data, len(d), d.ctypes.data, HM.ctypes.data, bM.ctypes.data, C.byref(npl), C.byref(nrl))
+        if rc < 0:
+            raise capi.DmvError(self.L.dmvh_window_error(self.h).decode())
+        self.npts = npl.value
+        return dict(resInM=rc, HM=HM, bM=bM, npts=npl.value, nres=nrl.value)
 
     def states(self):
         st = np.zeros((self.nf, 10)); idd = np.zeros(self.npts, np.float32); th = np.zeros(self.nf, np.float32)

@@ -169,6 +169,32 @@ typedef struct dmv_ba_activate_args {
 } dmv_ba_activate_args;
 int dmv_ba_activate_points(dmv_ba* ba, const dmv_ba_activate_args* a);
 
+/* Point marginalisation at keyframe creation, one launch pair for the whole flagged set:
+ *   - the compute of FullSystem::flagPointsForRemoval for each flagged point (FullSystem/FullSystem.cpp:L826-838): PointFrameResidual::resetOOB,
+ *     linearize, applyRes(true), EFResidual::fixLinearizationF (OptimizationBackend/EnergyFunctionalStructs.cpp:L88-114) -> res_toZeroF;
+ *   - EnergyFunctional::marginalizePointsF (OptimizationBackend/EnergyFunctional.cpp:L678-742): priorF *= idepthFixPriorMargFac,
+ *     AccumulatedTopHessian::addPoint<2>, AccumulatedSCHessian::addPoint(p, shiftPriorToZero = false), stitch without priors.
+ * The caller decides WHICH points (PointHessian::isOOB / isInlierNew / idepth_hessian > setting_minIdepthH_marg are host bookkeeping) and finishes
+ * with HM += setting_margWeightFac * (M - Msc), bM += setting_margWeightFac * (Mb - Mbsc), then re-uploads the window without the points.
+ * Uses the frames / calibration / depths of the last dmv_ba_set_state or dmv_ba_gn_step.  adHTdeltaF: nf*nf*8 floats, entry [h + t*nf]
+ * (EnergyFunctional::setDeltaF, EnergyFunctional.cpp:L175-198); cDeltaF: calibration value - value_zero.  Any output may be NULL.
+ * M/Msc: N*N row-major, N = 8 nf + 4.  res_toZeroF [nres*8] / isLinearized [nres] follow the dmv_ba_set_residuals order (zero for residuals
+ * that were not linearised); ngoodRes [n] follows `point`.  Invalidates the tentative linearisation; the committed one is untouched.
+ * Sharded handles (dmv_ba_comm_init / dmv_ba_p2p_import): not supported, returns DMV_ERR_STATE (marginalise per rank and sum on the host). */
+typedef struct dmv_ba_marg_args {
+  int32_t n;
+  const int32_t* point;          /* [n] indices in dmv_ba_set_points order */
+  const float* adHTdeltaF;
+  float cDeltaF[4];
+  float idepthFixPriorMargFac;   /* 600*600 (util/settings.cpp:L68) */
+  double *M, *Mb, *Msc, *Mbsc;
+  int32_t* resInM;
+  int32_t* ngoodRes;
+  float* res_toZeroF;
+  uint8_t* isLinearized;
+} dmv_ba_marg_args;
+int dmv_ba_marginalize_points(dmv_ba* ba, const dmv_ba_marg_args* a);
+
 /* Multi-GPU: points are sharded over ranks, images/tables replicated.  After dmv_ba_comm_init every
  * dmv_ba_linearize all-reduces the stitched system (and energy/counters) over NCCL so all ranks hold identical H,b.
  * nccl_unique_id: 128 bytes from ncclGetUniqueId() on rank 0, distributed by the caller. */

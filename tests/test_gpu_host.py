@@ -99,3 +99,34 @@ def test_track_with_device_built_reference(hostapi, orc, synth):
     np.testing.assert_array_equal(ra["R"], rb["R"]); np.testing.assert_array_equal(ra["t"], rb["t"])
     assert ra["iterations"] == rb["iterations"]
     a.close(); b.close()
+
+
+def test_marginalize_points_after_optimize(hostapi, orc, synth):
+    """makeKeyFrame's point marginalisation through the C++ adapter (WindowBA::marginalizePointsF): after the same optimize() on both
+    sides the marginalisation prior HM/bM matches the oracle's marginalizePointsF (tolerances: those of the optimised states it is
+    linearised at), the listed points and their residuals are gone, and the smaller window keeps optimising."""
+    W = synth.make_window(nf=5, npts=800, seed=17, state_noise=2e-3)
+    ow = orc.Window(W)
+    ow.optimize(4, precision=1)
+    hw = hostapi.WindowBA(W)
+    hw.optimize(4)
+    po = ow.point_outputs()
+    idepth_hessian = np.where(po["HdiF"] > 0, 1.0 / np.maximum(po["HdiF"], 1e-30), 0.0)
+    rng = np.random.default_rng(0)
+    well = np.nonzero(idepth_hessian > 200)[0]                      # far from setting_minIdepthH_marg = 50: both sides marginalise all of them
+    marg = np.sort(rng.choice(well, len(well) // 3, replace=False)).astype(np.int32)
+    rest = np.setdiff1d(np.arange(len(W["host"])), marg)
+    drop = np.sort(rng.choice(rest, 20, replace=False)).astype(np.int32)
+    o = ow.marginalize(marg, precision=1)
+    g = hw.marginalize_points(marg, drop)
+    assert g["npts"] == len(W["host"]) - len(marg) - len(drop)
+    assert g["nres"] == int((~np.isin(W["res_point"], np.concatenate([marg, drop]))).sum())
+    assert abs(g["resInM"] - o["resInM"]) <= max(2, o["resInM"] // 500)
+    assert rel(g["HM"], o["HM"]) < 2e-3
+    assert rel(g["bM"], o["bM"]) < 2e-2     # signed sums of res_toZeroF at slightly different optima
+    assert np.allclose(g["HM"], g["HM"].T, rtol=1e-9, atol=1e-9 * np.abs(g["HM"]).max())
+    e0 = hw.linearize()
+    assert np.isfinite(e0) and e0 > 0
+    n, log = hw.optimize(3)
+    assert n >= 1 and np.all(np.isfinite(log))
+    hw.close()
