@@ -67,7 +67,7 @@ SYMBOLS = [
     "dmv_ba_set_window", "dmv_ba_set_points", "dmv_ba_set_residuals", "dmv_ba_set_adjoints", "dmv_ba_set_state", "dmv_ba_linearize",
     "dmv_ba_get_residual_outputs", "dmv_ba_get_target_energies", "dmv_ba_apply_res", "dmv_ba_accumulate", "dmv_ba_get_point_outputs",
     "dmv_ba_resubstitute", "dmv_ba_backup_points", "dmv_ba_restore_points", "dmv_ba_get_idepth", "dmv_ba_gn_step", "dmv_nccl_unique_id",
-    "dmv_ba_comm_init", "dmv_ba_activate_points", "dmv_ba_marginalize_points", "dmv_ba_p2p_export", "dmv_ba_p2p_import", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e", "dmv_ba_debug_clocks",
+    "dmv_ba_comm_init", "dmv_ba_activate_points", "dmv_ba_marginalize_points", "dmv_ba_drop_residuals", "dmv_ba_reset_oob", "dmv_ba_p2p_export", "dmv_ba_p2p_import", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e", "dmv_ba_debug_clocks",
     "dmv_ct_create", "dmv_ct_destroy", "dmv_ct_set_K", "dmv_ct_set_ref", "dmv_ct_make_coarse_depth", "dmv_ct_get_ref", "dmv_ct_upload_new", "dmv_ct_upload_new_image", "dmv_ct_set_huber",
     "dmv_ct_calc_res_gs", "dmv_ct_track", "dmv_ip_default_settings", "dmv_ct_init_points", "dmv_ct_trace_points", "dmv_ct_set_timing", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count",
 ]
@@ -107,6 +107,8 @@ def lib():
         L.dmv_ba_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
         L.dmv_ba_activate_points.argtypes = [vp, C.POINTER(BAActivateArgs)]
         L.dmv_ba_marginalize_points.argtypes = [vp, C.POINTER(BAMargArgs)]
+        L.dmv_ba_drop_residuals.argtypes = [vp, C.c_int, i32p]
+        L.dmv_ba_reset_oob.argtypes = [vp]
         L.dmv_ba_p2p_export.argtypes = [vp, vp]
         L.dmv_ba_p2p_import.argtypes = [vp, C.c_int, C.c_int, vp]
         L.dmv_ba_last_timing.argtypes = [vp, f32p]
@@ -322,6 +324,15 @@ class BA:
         args = BAActivateArgs(n, *[a.ctypes.data for a in keep], int(minObs), status.ctypes.data, idepth.ctypes.data, rs.ctypes.data)
         check(self.L.dmv_ba_activate_points(self.h, C.byref(args)))
         return status, idepth, rs
+
+    def reset_oob(self):
+        check(self.L.dmv_ba_reset_oob(self.h))
+
+    def drop_residuals(self, idx):
+        """residuals leave the window (FullSystemOptimize.cpp:L196-214); the remaining ones keep their order"""
+        idx = _c(idx, np.int32)
+        check(self.L.dmv_ba_drop_residuals(self.h, len(idx), idx))
+        self.nres -= len(np.unique(idx))
 
     def marginalize_points(self, pts, adHTdeltaF, cDeltaF, prior_fac=600.0 * 600.0):
         """flagPointsForRemoval's linearize / fixLinearizationF loop + marginalizePointsF for the listed points (dmv_ba_marginalize_points).

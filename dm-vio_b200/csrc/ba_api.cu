@@ -633,6 +633,48 @@ static void unpack_system(const dmv_ba* b, const double* r, double* H_A, double*
   if (resInA) *resInA = (int)sc[(size_t)b->ntiles * 16 + 1];
 }
 
+int dmv_ba_reset_oob(dmv_ba* b) {
+  if (!b) return set_error(DMV_ERR_INVALID, "null handle");
+  if (b->npts < 1) return set_error(DMV_ERR_STATE, "points/residuals not set");
+  CK(cudaSetDevice(b->device));
+  const size_t ns = (size_t)MAXF * b->mp;
+  for (int i = 0; i < b->nres; i++) { b->h_st_in[b->res_slot[i]] = (uint8_t)RES_IN; b->h_en_in[b->res_slot[i]] = 0.f; }
+  CK(cudaStreamSynchronize(b->stream));
+  CK(cudaMemcpy(b->d_st_in, b->h_st_in.data(), ns, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b->d_en_in, b->h_en_in.data(), ns * sizeof(float), cudaMemcpyHostToDevice));
+  b->have_tentative = b->have_committed = false;
+  return DMV_OK;
+}
+
+int dmv_ba_drop_residuals(dmv_ba* b, int n, const int32_t* res_idx) {
+  if (!b || n < 0 || (n > 0 && !res_idx)) return set_error(DMV_ERR_INVALID, "null argument");
+  if (n == 0) return DMV_OK;
+  CK(cudaSetDevice(b->device));
+  std::vector<char> gone(b->nres, 0);
+  for (int i = 0; i < n; i++) {
+    if (res_idx[i] < 0 || res_idx[i] >= b->nres) return set_error(DMV_ERR_INVALID, "res_idx[%d] = %d out of range", i, res_idx[i]);
+    gone[res_idx[i]] = 1;
+  }
+  // once per keyframe, <= 64 KB per array: round-trip the state arrays instead of a scatter kernel
+  const size_t ns = (size_t)MAXF * b->mp;
+  CK(cudaStreamSynchronize(b->stream));
+  std::vector<uint8_t> st(ns);
+  for (int k = 0; k < 2; k++) {
+    CK(cudaMemcpy(st.data(), b->d_st_new[k], ns, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < b->nres; i++) if (gone[i]) st[b->res_slot[i]] = (uint8_t)RES_NONE;
+    CK(cudaMemcpy(b->d_st_new[k], st.data(), ns, cudaMemcpyHostToDevice));
+  }
+  int w = 0;
+  for (int i = 0; i < b->nres; i++) {
+    if (gone[i]) { b->h_st_in[b->res_slot[i]] = (uint8_t)RES_NONE; b->h_en_in[b->res_slot[i]] = 0.f; }
+    else b->res_slot[w++] = b->res_slot[i];
+  }
+  b->nres = w;
+  b->res_slot.resize(w);
+  CK(cudaMemcpy(b->d_st_in, b->h_st_in.data(), ns, cudaMemcpyHostToDevice));
+  return DMV_OK;
+}
+
 int dmv_ba_marginalize_points(dmv_ba* b, const dmv_ba_marg_args* a) {
   int rc = check_ready(b);
   if (rc != DMV_OK) return rc;

@@ -69,9 +69,38 @@ int dmvh_window_solve(void* p, int iteration, double lambda, double* x) {
   if (x) std::memcpy(x, W->lastX.data(), sizeof(double) * W->lastX.size());
   return (int)W->lastX.size();
 }
+double dmvh_window_finish_optimize(void* p, int32_t* removed, int cap, int* nremoved, int* nres_left) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  const double E = W->finishOptimize();
+  const std::vector<int>& r = W->lastRemovedResiduals;
+  for (int i = 0; i < cap && i < (int)r.size(); i++) removed[i] = r[i];
+  if (nremoved) *nremoved = (int)r.size();
+  if (nres_left) *nres_left = (int)W->activeResiduals.size();
+  return E;
+}
+void dmvh_window_get_point_stats(void* p, float* maxRelBaseline, int32_t* numGoodResiduals) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  for (size_t i = 0; i < W->points.size(); i++) {
+    if (maxRelBaseline) maxRelBaseline[i] = W->points[i].maxRelBaseline;
+    if (numGoodResiduals) numGoodResiduals[i] = W->points[i].numGoodResiduals;
+  }
+}
+void dmvh_window_set_last_residuals(void* p, const int32_t* target2, const int32_t* state2) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  for (size_t i = 0; i < W->points.size(); i++)
+    for (int k = 0; k < 2; k++) { W->points[i].lastResiduals_target[k] = target2[2 * i + k]; W->points[i].lastResiduals_state[k] = state2[2 * i + k]; }
+}
+void dmvh_window_flag_points(void* p, int nflagged, const int32_t* flagged, int32_t* marg, int* nmarg, int32_t* drop, int* ndrop) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  std::vector<int> m, d;
+  W->flagPointsForRemoval(std::vector<int>(flagged, flagged + nflagged), &m, &d);
+  for (size_t i = 0; i < m.size(); i++) marg[i] = m[i];
+  for (size_t i = 0; i < d.size(); i++) drop[i] = d[i];
+  *nmarg = (int)m.size(); *ndrop = (int)d.size();
+}
 int dmvh_window_optimize(void* p, int its, double* log, int cap) {
   std::vector<double> e;
-  const int n = static_cast<WindowBA*>(p)->optimize(its, &e);
+  const int n = static_cast<WindowBA*>(p)->optimize(its, &e, false);
   for (int i = 0; i < cap; i++) log[i] = i < (int)e.size() ? e[i] : -1.0;
   return n;
 }

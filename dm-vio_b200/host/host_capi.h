@@ -19,7 +19,13 @@ int dmvh_window_prepare(void* win); /* makeIDX + setAdjointsF + setPrecalcValues
 double dmvh_window_linearize(void* win, int fix);
 void dmvh_window_apply(void* win);
 int dmvh_window_solve(void* win, int iteration, double lambda, double* x_out);
-int dmvh_window_optimize(void* win, int its, double* energyLog, int cap);
+int dmvh_window_optimize(void* win, int its, double* energyLog, int cap); /* the LM loop only (WindowBA::optimize(its, log, finish = false)) */
+/* tail of FullSystem::optimize (WindowBA::finishOptimize): returns the energy; removed (cap entries) gets the indices of the deleted residuals */
+double dmvh_window_finish_optimize(void* win, int32_t* removed, int cap, int* nremoved, int* nres_left);
+void dmvh_window_get_point_stats(void* win, float* maxRelBaseline, int32_t* numGoodResiduals);
+void dmvh_window_set_last_residuals(void* win, const int32_t* target_frameID2, const int32_t* state2); /* per point: lastResiduals[0..1] */
+/* WindowBA::flagPointsForRemoval; returns counts through nmarg / ndrop (arrays sized npts) */
+void dmvh_window_flag_points(void* win, int nflagged, const int32_t* flagged_frames, int32_t* marg, int* nmarg, int32_t* drop, int* ndrop);
 void dmvh_window_get_tables(void* win, float* precalc, double* adHost, double* adTarget);
 void dmvh_window_get_system(void* win, double* HA, double* bA, double* Hsc, double* bsc, double* lastHS, double* lastbS);
 void dmvh_window_get_states(void* win, double* states10, float* idepth, float* frameEnergyTH);

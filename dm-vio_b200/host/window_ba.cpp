@@ -317,8 +317,94 @@ double WindowBA::linearizeAll(bool fixLinearization) {
   const double* x = have_pending_x_ ? pending_x_.data() : nullptr;
   if (dmv_ba_gn_step(ba_, x, &st, &r, step_sums_) != DMV_OK) { fail("dmv_ba_gn_step"); return NAN; }
   have_pending_x_ = false;
+  if (fixLinearization) applyRes_Reductor();  // linearizeAll_Reductor applies inside the map (L64); the energies read below are the same
   setNewFrameEnergyTH();
+  if (!fixLinearization) return r.energy;
+  // ---- FullSystemOptimize.cpp:L66-84 (per active residual: maxRelBaseline, numGoodResiduals; the others are collected) and L186-215
+  syncResidualStates();
+  const int n = nf(), np = (int)points.size(), nr = (int)activeResiduals.size();
+  std::vector<float> id(np);
+  if (np > 0) getIdepths(id.data());
+  std::vector<int32_t> toRemove;
+  for (int i = 0; i < nr; i++) {
+    PointFrameResidual& res = activeResiduals[i];
+    PointHessian& p = points[res.point];
+    if (res.state_state != 1) { res.state_state = res.state_NewState; res.state_energy = res.state_NewEnergy; }  // applyRes; OOB is final (Residuals.cpp:L306-328)
+    if (res.state_state == 0) {  // isActive(): state_NewState == IN
+      // every residual is "new" in the reference (PointFrameResidual::isNew is never cleared)
+      const float* q = &precalc[(size_t)(p.host * n + res.target) * 32];
+      float inf3[3], ptp[3];
+      for (int k = 0; k < 3; k++) inf3[k] = q[3 * k] * p.u + q[3 * k + 1] * p.v + q[3 * k + 2];
+      for (int k = 0; k < 3; k++) ptp[k] = inf3[k] + q[9 + k] * id[res.point];
+      const float dx = inf3[0] / inf3[2] - ptp[0] / ptp[2], dy = inf3[1] / inf3[2] - ptp[1] / ptp[2];
+      const float relBS = 0.01 * std::sqrt(dx * dx + dy * dy);  // 0.01 = one pixel
+      if (relBS > p.maxRelBaseline) p.maxRelBaseline = relBS;
+      p.numGoodResiduals++;
+    } else {
+      toRemove.push_back(i);
+    }
+    const int tid = frameHessians[res.target].frameID;
+    for (int k = 0; k < 2; k++)
+      if (p.lastResiduals_target[k] == tid) { p.lastResiduals_state[k] = res.state_state; break; }
+  }
+  lastRemovedResiduals.assign(toRemove.begin(), toRemove.end());
+  if (!toRemove.empty()) {
+    if (dmv_ba_drop_residuals(ba_, (int)toRemove.size(), toRemove.data()) != DMV_OK) { fail("dmv_ba_drop_residuals"); return NAN; }
+    std::vector<char> gone(nr, 0);
+    for (int i : toRemove) {
+      gone[i] = 1;
+      PointHessian& p = points[activeResiduals[i].point];
+      const int tid = frameHessians[activeResiduals[i].target].frameID;
+      for (int k = 0; k < 2; k++)
+        if (p.lastResiduals_target[k] == tid) { p.lastResiduals_target[k] = -1; break; }
+    }
+    int w = 0;
+    for (int i = 0; i < nr; i++)
+      if (!gone[i]) activeResiduals[w++] = activeResiduals[i];
+    activeResiduals.resize(w);
+  }
   return r.energy;
+}
+
+double WindowBA::finishOptimize() {  // FullSystemOptimize.cpp:L591-609
+  FrameHessian& newest = frameHessians.back();
+  double newStateZero[10] = {0, 0, 0, 0, 0, 0, newest.state[6], newest.state[7], 0, 0};
+  newest.worldToCam_evalPT = newest.PRE_worldToCam;  // FrameHessian::setEvalPT (HessianBlocks.h:L209-215)
+  newest.setState(newStateZero);
+  for (int i = 0; i < 10; i++) newest.state_zero[i] = newStateZero[i];
+  setAdjointsF();
+  setPrecalcValues();
+  return linearizeAll(true);
+}
+
+void WindowBA::flagPointsForRemoval(const std::vector<int>& flaggedFrames, std::vector<int>* toMarg, std::vector<int>* toDrop) {
+  // FullSystem.cpp:L785-879 (fhsToKeepPoints is always empty there: the loop at L795 never runs)
+  const int n = nf(), np = (int)points.size();
+  std::vector<char> flagged(n, 0);
+  for (int f : flaggedFrames) if (f >= 0 && f < n) flagged[f] = 1;
+  std::vector<float> id(np);
+  if (np > 0) getIdepths(id.data());  // the optimised depths live on the device
+  std::vector<int> nres(np, 0), visInToMarg(np, 0);
+  for (const PointFrameResidual& r : activeResiduals) {
+    nres[r.point]++;
+    if (r.state_state == 0 && flagged[r.target]) visInToMarg[r.point]++;
+  }
+  for (int i = 0; i < np; i++) {
+    const PointHessian& p = points[i];
+    if (id[i] * SCALE_IDEPTH < s.setting_minIdepth || nres[i] == 0) { toDrop->push_back(i); continue; }
+    // PointHessian::isOOB (HessianBlocks.h:L476-499)
+    bool oob = false;
+    if (nres[i] >= s.setting_minGoodActiveResForMarg && p.numGoodResiduals > s.setting_minGoodResForMarg + 10 &&
+        nres[i] - visInToMarg[i] < s.setting_minGoodActiveResForMarg)
+      oob = true;
+    else if (p.lastResiduals_state[0] == 1) oob = true;
+    else if (nres[i] < 2) oob = false;
+    else if (p.lastResiduals_state[0] == 2 && p.lastResiduals_state[1] == 2) oob = true;
+    if (!oob && !flagged[p.host]) continue;
+    // PointHessian::isInlierNew (HessianBlocks.h:L502-506)
+    const bool inlier = nres[i] >= s.setting_minGoodActiveResForMarg && p.numGoodResiduals >= s.setting_minGoodResForMarg;
+    (inlier ? toMarg : toDrop)->push_back(i);
+  }
 }
 
 void WindowBA::setNewFrameEnergyTH() {  // FullSystemOptimize.cpp:L96-149 (no IMU cap)
@@ -448,11 +534,13 @@ void WindowBA::loadSateBackup() {  // FullSystemOptimize.cpp:L371-388
   setPrecalcValues();
 }
 
-int WindowBA::optimize(int mnumOptIts, std::vector<double>* energyLog) {
+int WindowBA::optimize(int mnumOptIts, std::vector<double>* energyLog, bool finish) {
   // FullSystemOptimize.cpp:L417-647 without IMU / GTSAM / logging
   if (nf() < 2) return 0;
   if (nf() < 3) mnumOptIts = 20;
   if (nf() < 4) mnumOptIts = 15;
+  // activeResiduals = every residual that is not linearised, each reset with resetOOB (L431-448)
+  if (dmv_ba_reset_oob(ba_) != DMV_OK) { fail("dmv_ba_reset_oob"); return 0; }
   double lastEnergy = linearizeAll(false);
   double lastEnergyL = calcLEnergyF_MT();
   double lastEnergyM = calcMEnergyF();
@@ -493,6 +581,7 @@ int WindowBA::optimize(int mnumOptIts, std::vector<double>* energyLog) {
     if (canbreak && iteration >= s.setting_minOptIterations) break;
   }
   lastEnergyTotal = lastEnergy;
+  if (finish) lastEnergyTotal = finishOptimize();
   return numIterations;
 }
 

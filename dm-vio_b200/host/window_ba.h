@@ -27,6 +27,8 @@ struct Settings {  // util/settings.cpp:L60-160
   float setting_frameEnergyTHConstWeight = 0.5f, setting_frameEnergyTHN = 0.7f, setting_frameEnergyTHFacMedian = 1.5f;
   float setting_thOptIterations = 1.2f;
   int setting_minOptIterations = 1;
+  float setting_minIdepth = 0.02f;                                       // settings.cpp:L53
+  int setting_minGoodActiveResForMarg = 3, setting_minGoodResForMarg = 4;  // settings.cpp:L127-128
   float setting_idepthFixPriorMargFac = 600 * 600, setting_margWeightFac = 0.5f * 0.5f, setting_minIdepthH_marg = 50;  // settings.cpp:L68, L118, L89
 };
 
@@ -60,6 +62,12 @@ struct PointHessian {  // FullSystem/HessianBlocks.h:L413-508 (+ EFPoint)
   float color[8], weights[8];
   bool hasDepthPrior = false;
   float priorF = 0;
+  float maxRelBaseline = 0;          // updated by linearizeAll(true) (FullSystemOptimize.cpp:L66-79)
+  int numGoodResiduals = 0;
+  // PointHessian::lastResiduals (HessianBlocks.h:L447): the residuals to the two newest keyframes, identified by the target's frameID
+  // (-1 = none) instead of a pointer, with their last committed state (0 IN, 1 OOB, 2 OUTLIER)
+  int lastResiduals_target[2] = {-1, -1};
+  int lastResiduals_state[2] = {0, 0};
 };
 
 struct PointFrameResidual {  // FullSystem/Residuals.h:L53-110
@@ -111,7 +119,15 @@ class WindowBA {
   void backupState();                  // FullSystemOptimize.cpp:L322-370
   bool doStepFromBackup();             // FullSystemOptimize.cpp:L224-317 (point part deferred to the next linearizeAll: fused on the GPU)
   void loadSateBackup();               // FullSystemOptimize.cpp:L371-388
-  int optimize(int mnumOptIts, std::vector<double>* energyLog = nullptr);  // FullSystemOptimize.cpp:L417-647 (no IMU); returns #iterations
+  // FullSystemOptimize.cpp:L417-647 (no IMU); returns #iterations.  finish = true runs the reference's tail (L591-609): setEvalPT of the newest
+  // frame, setAdjointsF, setPrecalcValues and linearizeAll(true); finish = false stops after the LM loop (tests / benches of the loop alone).
+  int optimize(int mnumOptIts, std::vector<double>* energyLog = nullptr, bool finish = true);
+  double finishOptimize();             // the tail alone; returns the energy of linearizeAll(true)
+  std::vector<int> lastRemovedResiduals;   // indices (before the erase) of the residuals linearizeAll(true) deleted (L196-214)
+  // FullSystem::flagPointsForRemoval (FullSystem.cpp:L785-879), decision part: which points leave the window when the frames in
+  // `flaggedFrames` (window indices, FrameHessian::flaggedForMarginalization) are about to be marginalised.  toMarg: candidates for
+  // marginalizePointsF (isOOB || host flagged, and isInlierNew); toDrop: PS_DROP.
+  void flagPointsForRemoval(const std::vector<int>& flaggedFrames, std::vector<int>* toMarg, std::vector<int>* toDrop);
 
   // ---- keyframe marginalisation of points (FullSystem::makeKeyFrame: flagPointsForRemoval -> marginalizePointsF / dropPointsF)
   // toMarg: the caller's PS_MARGINALIZE candidates (PointHessian::isOOB && isInlierNew, or host frame flagged); for each the device runs

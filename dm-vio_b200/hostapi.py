@@ -24,6 +24,11 @@ def lib():
         L.dmvh_window_error.argtypes = [vp]
         L.dmvh_window_add_frame.argtypes = [vp, f32p, C.c_int, f64p, f64p, f64p, f64p, C.c_float, C.c_int]
         L.dmvh_window_drop_frame.argtypes = [vp, C.c_int]
+        L.dmvh_window_finish_optimize.restype = C.c_double
+        L.dmvh_window_finish_optimize.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.dmvh_window_get_point_stats.argtypes = [vp, vp, vp]
+        L.dmvh_window_set_last_residuals.argtypes = [vp, vp, vp]
+        L.dmvh_window_flag_points.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int), vp, C.POINTER(C.c_int)]
         L.dmvh_window_marginalize_points.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.dmvh_window_set_points.argtypes = [vp, C.c_int, i32p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
         L.dmvh_window_set_residuals.argtypes = [vp, C.c_int, i32p, i32p]
@@ -61,7 +66,7 @@ class WindowBA:
 
     def __init__(self, W, device=0, use_device_pyramid=False):
         self.L = lib()
-        self.nf, self.npts = W["nf"], len(W["host"])
+        self.nf, self.npts, self.nres = W["nf"], len(W["host"]), len(W["res_point"])
         self.N = 8 * self.nf + 4
         self.h = self.L.dmvh_window_create(W["w"], W["h"], max(2, self.nf), self.npts, device, _c(W["K"], np.float64))
         for k in range(self.nf):
@@ -114,6 +119,35 @@ class WindowBA:
         n = self.L.dmvh_window_optimize(self.h, its, log, 64)
         return n, log[log >= 0]
 
+    def finish_optimize(self):
+        """WindowBA::finishOptimize — tail of FullSystem::optimize (setEvalPT of the newest frame, adjoints, precalc, linearizeAll(true)).
+        Returns (energy, indices of the residuals that were deleted, residuals left)."""
+        rem = np.zeros(max(1, self.nres), np.int32)
+        n, left = C.c_int(0), C.c_int(0)
+        E = self.L.dmvh_window_finish_optimize(self.h, rem.ctypes.data, len(rem), C.byref(n), C.byref(left))
+        if not np.isfinite(E):
+            raise capi.DmvError(self.L.dmvh_window_error(self.h).decode())
+        self.nres = left.value
+        return E, rem[:n.value].copy()
+
+    def point_stats(self):
+        mrb = np.zeros(self.npts, np.float32); ng = np.zeros(self.npts, np.int32)
+        self.L.dmvh_window_get_point_stats(self.h, mrb.ctypes.data, ng.ctypes.data)
+        return dict(maxRelBaseline=mrb, numGoodResiduals=ng)
+
+    def set_last_residuals(self, target_frameID, state):
+        t, s = _c(target_frameID, np.int32), _c(state, np.int32)
+        assert t.shape == (self.npts, 2) and s.shape == (self.npts, 2)
+        self.L.dmvh_window_set_last_residuals(self.h, t.ctypes.data, s.ctypes.data)
+
+    def flag_points(self, flagged_frames):
+        """WindowBA::flagPointsForRemoval: (toMarg, toDrop) point indices"""
+        f = _c(np.asarray(flagged_frames, np.int32), np.int32)
+        m = np.zeros(max(1, self.npts), np.int32); d = np.zeros(max(1, self.npts), np.int32)
+        nm, nd = C.c_int(0), C.c_int(0)
+        self.L.dmvh_window_flag_points(self.h, len(f), f.ctypes.data, m.ctypes.data, C.byref(nm), d.ctypes.data, C.byref(nd))
+        return m[:nm.value].copy(), d[:nd.value].copy()
+
     def marginalize_points(self, marg, drop=()):
         """WindowBA::marginalizePointsF: marginalises `marg` into HM/bM (badly constrained ones are dropped), drops `drop`, erases all of them
         and re-uploads the window.  Returns dict(resInM, HM, bM, npts, nres)."""
@@ -124,7 +158,7 @@ class WindowBA:
         rc = self.L.dmvh_window_marginalize_points(self.h, len(m), m.ctypes.data, len(d), d.ctypes.data, HM.ctypes.data, bM.ctypes.data, C.byref(npl), C.byref(nrl))
         if rc < 0:
             raise capi.DmvError(self.L.dmvh_window_error(self.h).decode())
-        self.npts = npl.value
+        self.npts, self.nres = npl.value, nrl.value
         return dict(resInM=rc, HM=HM, bM=bM, npts=npl.value, nres=nrl.value)
 
     def states(self):

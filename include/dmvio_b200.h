@@ -169,6 +169,17 @@ typedef struct dmv_ba_activate_args {
 } dmv_ba_activate_args;
 int dmv_ba_activate_points(dmv_ba* ba, const dmv_ba_activate_args* a);
 
+/* PointFrameResidual::resetOOB for every residual of the window, as FullSystem::optimize does when it collects activeResiduals
+ * (FullSystem/FullSystemOptimize.cpp:L431-448; FullSystem/Residuals.h:L91-98): state IN, energy 0.  Discards the tentative and the committed
+ * linearisation (the next dmv_ba_linearize / dmv_ba_gn_step starts from these states). */
+int dmv_ba_reset_oob(dmv_ba* ba);
+
+/* Residuals leave the window: the deletion loop of FullSystem::linearizeAll(fixLinearization = true) (FullSystem/FullSystemOptimize.cpp:L196-214 ->
+ * EnergyFunctional::dropResidual, OptimizationBackend/EnergyFunctional.cpp:L500-520) for residuals that did not end up IN.  res_idx: indices in
+ * the current dmv_ba_set_residuals order; the remaining residuals keep their relative order (per-residual outputs shrink accordingly).  The
+ * committed linearisation stays valid (a non-active residual contributes nothing to it). */
+int dmv_ba_drop_residuals(dmv_ba* ba, int n, const int32_t* res_idx);
+
 /* Point marginalisation at keyframe creation, one launch pair for the whole flagged set:
  *   - the compute of FullSystem::flagPointsForRemoval for each flagged point (FullSystem/FullSystem.cpp:L826-838): PointFrameResidual::resetOOB,
  *     linearize, applyRes(true), EFResidual::fixLinearizationF (OptimizationBackend/EnergyFunctionalStructs.cpp:L88-114) -> res_toZeroF;

@@ -60,6 +60,9 @@ def _declare(L):
     L.orc_win_apply_res.argtypes = [vp]
     L.orc_win_get_res_outputs.argtypes = [vp, i32p, f32p, f32p, f32p, vp, i32p, u8p, f32p]
     L.orc_win_accumulate.argtypes = [vp, C.c_int, f64p, f64p, f64p, f64p, f64p, f64p, C.POINTER(C.c_int)]
+    L.orc_win_finish_optimize.restype = C.c_double
+    L.orc_win_finish_optimize.argtypes = [vp, i32p, C.c_int, C.POINTER(C.c_int)]
+    L.orc_win_get_point_stats.argtypes = [vp, f32p, i32p]
     L.orc_win_marginalize.argtypes = [vp, C.c_int, i32p, C.c_int, f64p, f64p, f64p, f64p, f64p, f64p, C.POINTER(C.c_int), i32p, f32p, u8p]
     L.orc_win_get_point_outputs.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p]
     L.orc_win_solve.argtypes = [vp, C.c_int, C.c_double, C.c_int, f64p, f64p, f64p]
@@ -237,6 +240,19 @@ class Window:
         log = np.zeros(64)
         n = self.L.orc_win_optimize(self.h, its, precision, log, 64)
         return n, log[log >= 0]
+
+    def finish_optimize(self):
+        """tail of FullSystem::optimize (FullSystemOptimize.cpp:L591-609): setEvalPT of the newest frame, adjoints, precalc, linearizeAll(true).
+        Returns (energy, removed residual indices)."""
+        rem = np.zeros(self.L.orc_win_nres(self.h), np.int32)
+        n = C.c_int(0)
+        E = self.L.orc_win_finish_optimize(self.h, rem, len(rem), C.byref(n))
+        return E, rem[:n.value].copy()
+
+    def point_stats(self):
+        mrb = np.zeros(self.npts, np.float32); ng = np.zeros(self.npts, np.int32)
+        self.L.orc_win_get_point_stats(self.h, mrb, ng)
+        return dict(maxRelBaseline=mrb, numGoodResiduals=ng)
 
     def frame_states(self):
         s = np.zeros((self.nf, 10))

@@ -417,7 +417,7 @@ void Window::setNewFrameEnergyTH() {  // FullSystemOptimize.cpp:L96-149 (no IMU 
   allResVec.reserve(residuals.size());
   const int newest = nf() - 1;
   for (const Residual& r : residuals)
-    if (!r.isLinearized && r.state_NewEnergyWithOutlier >= 0 && r.target == newest) allResVec.push_back((float)r.state_NewEnergyWithOutlier);
+    if (!r.isLinearized && !r.dropped && r.state_NewEnergyWithOutlier >= 0 && r.target == newest) allResVec.push_back((float)r.state_NewEnergyWithOutlier);
   Frame& newFrame = frames.back();
   if (allResVec.empty()) { newFrame.frameEnergyTH = 12 * 12 * PATTERN_NUM; return; }
   int nthIdx = (int)(s.frameEnergyTHN * allResVec.size());
@@ -435,7 +435,7 @@ double Window::linearizeAll(bool fixLinearization, std::vector<int>* toRemove, b
   auto body = [&](int lo, int hi, double* stats, int /*tid*/, std::vector<int>* rem) {
     for (int k = lo; k < hi; k++) {
       Residual& r = residuals[k];
-      if (r.isLinearized) continue;  // activeResiduals = all !isLinearized (L431-448)
+      if (r.isLinearized || r.dropped) continue;  // activeResiduals = all !isLinearized (L431-448)
       stats[0] += linearizeOne<float>(*this, r, &r.Jnew);
       if (fixLinearization) {
         applyRes(r);
@@ -473,7 +473,7 @@ double Window::linearizeAll(bool fixLinearization, std::vector<int>* toRemove, b
 
 void Window::applyResAll() {
   for (Residual& r : residuals)
-    if (!r.isLinearized) applyRes(r);
+    if (!r.isLinearized && !r.dropped) applyRes(r);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1126,13 +1126,37 @@ void Window::loadStateBackup() {  // FullSystemOptimize.cpp:L371-388
   setPrecalcValues();
 }
 
+double Window::finishOptimize(std::vector<int>* toRemove) {  // FullSystemOptimize.cpp:L591-609
+  Frame& newest = frames.back();
+  Vec10 newStateZero;
+  for (int i = 0; i < 10; i++) newStateZero[i] = 0;
+  newStateZero[6] = newest.state[6];
+  newStateZero[7] = newest.state[7];
+  newest.worldToCam_evalPT = newest.PRE_worldToCam;  // FrameHessian::setEvalPT (HessianBlocks.h:L237-245)
+  newest.setState(newStateZero);
+  newest.state_zero = newStateZero;
+  setAdjointsF();
+  setPrecalcValues();
+  std::vector<int> rem;
+  const double E = linearizeAll(true, &rem, true);
+  for (int k : rem) {  // FullSystemOptimize.cpp:L196-214: the residual leaves its point and the energy functional
+    Residual& r = residuals[k];
+    r.dropped = true;
+    r.isActiveAndIsGoodNEW = false;
+    std::vector<int>& list = points[r.point].residuals;
+    list.erase(std::remove(list.begin(), list.end(), k), list.end());
+  }
+  if (toRemove) *toRemove = rem;
+  return E;
+}
+
 int Window::optimize(int mnumOptIts, int precision, std::vector<double>* energyLog) {
   // FullSystemOptimize.cpp:L417-647 without IMU/GTSAM, logging and the final linearizeAll(true) bookkeeping
   if (nf() < 2) return 0;
   if (nf() < 3) mnumOptIts = 20;
   if (nf() < 4) mnumOptIts = 15;
-  for (Residual& r : residuals) if (!r.isLinearized) { r.state_state = RS_IN; r.state_NewState = RS_OUTLIER; }  // resetOOB (Residuals.h:L91-98)
-  for (Residual& r : residuals) if (!r.isLinearized) { r.state_energy = 0; r.state_NewEnergy = 0; }
+  for (Residual& r : residuals) if (!r.isLinearized && !r.dropped) { r.state_state = RS_IN; r.state_NewState = RS_OUTLIER; }  // resetOOB (Residuals.h:L91-98)
+  for (Residual& r : residuals) if (!r.isLinearized && !r.dropped) { r.state_energy = 0; r.state_NewEnergy = 0; }
   double lastEnergy = linearizeAll(false, nullptr);
   double lastEnergyL = calcLEnergy();
   double lastEnergyM = calcMEnergy();

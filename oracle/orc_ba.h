@@ -117,6 +117,7 @@ struct Residual {  // FullSystem/Residuals.h:L53-110 (PointFrameResidual) + Ener
   float res_toZeroF[8] = {0};
   float JpJdF[8] = {0};
   bool isLinearized = false;
+  bool dropped = false;  // deleted by linearizeAll(true) (FullSystemOptimize.cpp:L196-214); kept in the vector so that indices stay stable
   bool isActiveAndIsGoodNEW = false;
   bool isActive() const { return isActiveAndIsGoodNEW; }
 };
@@ -208,6 +209,11 @@ struct Window {
   void loadStateBackup();
   // FullSystemOptimize.cpp:L417-647 (without IMU / GTSAM / logging); returns number of iterations run
   int optimize(int mnumOptIts, int precision, std::vector<double>* energyLog = nullptr);
+  // the tail of FullSystem::optimize (FullSystemOptimize.cpp:L591-609): the newest frame's evaluation point moves to its estimate
+  // (FrameHessian::setEvalPT, HessianBlocks.h:L237-245), setAdjointsF, setPrecalcValues, then linearizeAll(true): applyRes, maxRelBaseline /
+  // numGoodResiduals of the active residuals (L55-88), setNewFrameEnergyTH, and the list of residuals the reference now deletes (L186-215).
+  // Returns the energy; `toRemove` gets the residual indices (they are marked `dropped` and skipped from then on).
+  double finishOptimize(std::vector<int>* toRemove);
 };
 
 // Residuals.cpp:L78-274. T = float follows the reference's arithmetic; T = double is used for finite-difference tests.

@@ -262,6 +262,20 @@ int orc_win_optimize(OrcWin* o, int mnumOptIts, int precision, double* energyLog
   for (int i = (int)log.size(); i < cap; i++) energyLog[i] = -1;
   return n;
 }
+// tail of FullSystem::optimize (FullSystemOptimize.cpp:L591-609); returns the energy, writes up to cap removed residual indices
+double orc_win_finish_optimize(OrcWin* o, int32_t* removed, int cap, int* nremoved) {
+  std::vector<int> rem;
+  const double E = o->W.finishOptimize(&rem);
+  for (int i = 0; i < cap && i < (int)rem.size(); i++) removed[i] = rem[i];
+  if (nremoved) *nremoved = (int)rem.size();
+  return E;
+}
+void orc_win_get_point_stats(OrcWin* o, float* maxRelBaseline, int32_t* numGoodResiduals) {
+  for (size_t i = 0; i < o->W.points.size(); i++) {
+    if (maxRelBaseline) maxRelBaseline[i] = o->W.points[i].maxRelBaseline;
+    if (numGoodResiduals) numGoodResiduals[i] = o->W.points[i].numGoodResiduals;
+  }
+}
 void orc_win_get_frame_states(OrcWin* o, double* state10) {
   for (int f = 0; f < o->W.nf(); f++) for (int k = 0; k < 10; k++) state10[10 * f + k] = o->W.frames[f].state[k];
 }

@@ -130,3 +130,78 @@ def test_marginalize_points_after_optimize(hostapi, orc, synth):
     n, log = hw.optimize(3)
     assert n >= 1 and np.all(np.isfinite(log))
     hw.close()
+
+
+def test_finish_optimize_matches_oracle(hostapi, orc, synth):
+    """The tail of FullSystem::optimize (FullSystemOptimize.cpp:L591-609) through WindowBA::finishOptimize: setEvalPT of the newest frame,
+    linearizeAll(true) with its bookkeeping (maxRelBaseline, numGoodResiduals, deletion of the residuals that are not IN), and a second
+    optimize() on the thinned window (resetOOB on the device, deleted residuals stay out) against the oracle."""
+    W = synth.make_window(nf=5, npts=600, seed=21, state_noise=2e-3)
+    nres = len(W["res_point"])
+    ow = orc.Window(W)
+    ow.optimize(4, precision=1)
+    E_o, rem_o = ow.finish_optimize()
+    hw = hostapi.WindowBA(W)
+    hw.optimize(4)
+    E_g, rem_g = hw.finish_optimize()
+    assert abs(E_g - E_o) <= 2e-4 * abs(E_o)
+    ties = np.setxor1d(rem_o, rem_g)
+    assert len(ties) <= max(2, nres // 500), ties                     # identical up to energy-threshold ties
+    assert hw.nres == nres - len(rem_g)
+    touched = np.unique(np.asarray(W["res_point"])[ties]) if len(ties) else np.zeros(0, int)
+    ok = np.ones(len(W["host"]), bool); ok[touched] = False
+    ps_o, ps_g = ow.point_stats(), hw.point_stats()
+    np.testing.assert_array_equal(ps_g["numGoodResiduals"][ok], ps_o["numGoodResiduals"][ok])
+    np.testing.assert_allclose(ps_g["maxRelBaseline"][ok], ps_o["maxRelBaseline"][ok], rtol=2e-3, atol=1e-6)
+    st_g, _, th_g = hw.states()
+    st_o = ow.frame_states()
+    assert np.all(st_g[-1, :6] == 0)                                  # the newest frame's pose now lives in its evaluation point
+    assert np.abs(st_g - st_o).max() < 2e-5
+    np.testing.assert_allclose(th_g, ow.frame_tables()["frameEnergyTH"], rtol=2e-3)
+    if len(ties) == 0:
+        n_o, log_o = ow.optimize(3, precision=1)
+        n_g, log_g = hw.optimize(3)
+        assert n_g == n_o
+        np.testing.assert_allclose(log_g, log_o, rtol=5e-4)
+    hw.close()
+
+
+def test_flag_points_for_removal_rules(hostapi, orc, synth):
+    """WindowBA::flagPointsForRemoval (FullSystem.cpp:L785-879 with PointHessian::isOOB / isInlierNew) against a numpy restatement of the
+    rules on the adapter's own bookkeeping, then the flagged points go through marginalizePointsF."""
+    W = synth.make_window(nf=6, npts=500, seed=29, state_noise=1e-3, hosts="all")
+    hw = hostapi.WindowBA(W)
+    hw.optimize(3)
+    for _ in range(4):                                                # numGoodResiduals grows by the active residuals at every keyframe optimisation
+        E, rem = hw.finish_optimize()
+        # the adapter compacts its residual list: track it the same way
+        W["res_point"] = np.asarray(W["res_point"])[np.setdiff1d(np.arange(len(W["res_point"])), rem)]
+        W["res_target"] = np.asarray(W["res_target"])[np.setdiff1d(np.arange(len(W["res_target"])), rem)]
+    npts = len(W["host"])
+    rng = np.random.default_rng(4)
+    last_t = np.tile(np.asarray(W["frameID"])[[-1, -2]], (npts, 1)).astype(np.int32)
+    last_s = rng.choice([0, 1, 2], (npts, 2), p=[0.8, 0.1, 0.1]).astype(np.int32)
+    hw.set_last_residuals(last_t, last_s)
+    flagged = [0]
+    marg, drop = hw.flag_points(flagged)
+    _, idepth, _ = hw.states()
+    ps = hw.point_stats()
+    nres_p = np.bincount(W["res_point"], minlength=npts)
+    vis = np.bincount(W["res_point"][np.isin(W["res_target"], flagged)], minlength=npts)     # every remaining residual is IN after linearizeAll(true)
+    exp_m, exp_d = [], []
+    for i in range(npts):
+        if idepth[i] < 0.02 or nres_p[i] == 0:
+            exp_d.append(i); continue
+        oob = (nres_p[i] >= 3 and ps["numGoodResiduals"][i] > 14 and nres_p[i] - vis[i] < 3)
+        if not oob:
+            oob = last_s[i, 0] == 1 or (nres_p[i] >= 2 and last_s[i, 0] == 2 and last_s[i, 1] == 2)
+        if not oob and W["host"][i] != 0:
+            continue
+        (exp_m if (nres_p[i] >= 3 and ps["numGoodResiduals"][i] >= 4) else exp_d).append(i)
+    np.testing.assert_array_equal(marg, np.asarray(exp_m, np.int32))
+    np.testing.assert_array_equal(drop, np.asarray(exp_d, np.int32))
+    assert len(marg) > 20 and len(drop) > 0
+    g = hw.marginalize_points(marg, drop)
+    assert g["npts"] == npts - len(drop) - len(marg) and g["resInM"] > 0
+    assert np.isfinite(hw.linearize())
+    hw.close()

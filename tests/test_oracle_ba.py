@@ -160,6 +160,38 @@ def test_gn_converges(orc, synth):
     assert np.all(np.diff(log) <= 1e-9 * log[0])
 
 
+def test_finish_optimize_tail(orc, synth):
+    """tail of FullSystem::optimize (FullSystemOptimize.cpp:L591-609): the newest frame is re-based on its estimate without moving
+    (precalc tables unchanged up to rounding), linearizeAll(true) counts the active residuals and lists the others for deletion."""
+    W = synth.make_window(nf=5, npts=600, seed=21, state_noise=2e-3)
+    ow = orc.Window(W)
+    ow.optimize(4)
+    pc0 = ow.precalc()
+    st0 = ow.frame_states()
+    E, removed = ow.finish_optimize()
+    st1 = ow.frame_states()
+    assert np.all(st1[-1, :6] == 0) and np.all(st1[-1, 6:8] == st0[-1, 6:8])      # setEvalPT: pose part of the state folded into the evaluation point
+    np.testing.assert_array_equal(st1[:-1], st0[:-1])
+    pc1 = ow.precalc().reshape(-1, 32); pc0 = pc0.reshape(-1, 32)
+    cur = np.r_[0:12, 24:26]                                                       # current-state tables: KRKi, Kt, aff (the *_0 / b0 entries follow the new FEJ point)
+    np.testing.assert_allclose(pc1[:, cur], pc0[:, cur], rtol=1e-5, atol=1e-4)     # nothing moved: exp(0) * (exp(xi) * T) == exp(xi) * T
+    assert np.isfinite(E) and E > 0
+    r = ow.res_outputs(False)
+    keep = np.ones(ow.nres, bool); keep[removed] = False
+    assert np.all(r["state"][removed] != 0) and np.all(r["state"][keep] == 0)     # exactly the non-IN residuals leave
+    assert np.all(r["isActive"][keep] == 1)
+    ps = ow.point_stats()
+    good = np.bincount(np.asarray(W["res_point"])[keep], minlength=ow.npts)
+    np.testing.assert_array_equal(ps["numGoodResiduals"], good)
+    assert np.all(ps["maxRelBaseline"][good > 0] > 0) and np.all(ps["maxRelBaseline"][good == 0] == 0)
+    # the removed residuals never come back: another optimisation leaves them out of the sums
+    n_active_before = int(keep.sum())
+    ow.linearize_all(update_th=False); ow.apply_res()
+    assert ow.accumulate(0)["resInA"] <= n_active_before
+    E2, removed2 = ow.finish_optimize()
+    assert not np.intersect1d(removed, removed2).size
+
+
 def test_oob_keeps_old_energy(orc, synth):
     W = synth.make_window(nf=2, npts=40, seed=17)
     W["res_state"] = np.ones(len(W["res_point"]), np.int32)  # all OOB
