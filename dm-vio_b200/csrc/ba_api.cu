@@ -75,6 +75,7 @@ struct dmv_ba {
   std::vector<int> res_slot;   // residual index -> slot (t*mp+p)
   std::vector<uint8_t> h_st_in;
   std::vector<float> h_en_in;
+  bool st_in_clean = false;    // every existing residual's INPUT state on the device is IN with zero energy (dmv_ba_reset_oob becomes a flag flip)
   bool no_zero_copy = false;   // DMV_NO_ZERO_COPY=1: D2H copy node instead of in-kernel writes to the pinned result (A/B experiment)
   bool timing = false;         // record CUDA events around the kernels of every call (dmv_ba_set_timing)
   int iter2 = 0;
@@ -394,6 +395,9 @@ int dmv_ba_set_residuals(dmv_ba* b, int nres, const int32_t* point, const int32_
     b->res_slot[i] = (int)slot;
   }
   b->nres = nres;
+  b->st_in_clean = true;
+  for (int i = 0; i < nres; i++)
+    if (b->h_st_in[b->res_slot[i]] != RES_IN || b->h_en_in[b->res_slot[i]] != 0.f) { b->st_in_clean = false; break; }
   CK(cudaMemcpy(b->d_st_in, b->h_st_in.data(), ns, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(b->d_en_in, b->h_en_in.data(), ns * sizeof(float), cudaMemcpyHostToDevice));
   for (int k = 0; k < 2; k++) CK(cudaMemset(b->d_st_new[k], 0xff, ns));
@@ -638,10 +642,13 @@ int dmv_ba_reset_oob(dmv_ba* b) {
   if (b->npts < 1) return set_error(DMV_ERR_STATE, "points/residuals not set");
   CK(cudaSetDevice(b->device));
   const size_t ns = (size_t)MAXF * b->mp;
-  for (int i = 0; i < b->nres; i++) { b->h_st_in[b->res_slot[i]] = (uint8_t)RES_IN; b->h_en_in[b->res_slot[i]] = 0.f; }
-  CK(cudaStreamSynchronize(b->stream));
-  CK(cudaMemcpy(b->d_st_in, b->h_st_in.data(), ns, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(b->d_en_in, b->h_en_in.data(), ns * sizeof(float), cudaMemcpyHostToDevice));
+  if (!b->st_in_clean) {  // otherwise the input arrays already say "IN, energy 0" for every residual: switching back to them is the reset
+    for (int i = 0; i < b->nres; i++) { b->h_st_in[b->res_slot[i]] = (uint8_t)RES_IN; b->h_en_in[b->res_slot[i]] = 0.f; }
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaMemcpy(b->d_st_in, b->h_st_in.data(), ns, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->d_en_in, b->h_en_in.data(), ns * sizeof(float), cudaMemcpyHostToDevice));
+    b->st_in_clean = true;
+  }
   b->have_tentative = b->have_committed = false;
   return DMV_OK;
 }
