@@ -1,6 +1,7 @@
 #include "host_capi.h"
 #include "coarse_tracker.h"
 #include "window_ba.h"
+#include "marg_frame.h"
 #include <cstring>
 
 using namespace dmvio_b200;
@@ -68,6 +69,22 @@ int dmvh_window_solve(void* p, int iteration, double lambda, double* x) {
   W->solveSystemF(iteration, lambda);
   if (x) std::memcpy(x, W->lastX.data(), sizeof(double) * W->lastX.size());
   return (int)W->lastX.size();
+}
+int dmvh_window_marginalize_frame(void* p, int idx, double* HM, double* bM, int* nf_left, int* nres_left) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  const bool ok = W->marginalizeFrame(idx);
+  if (HM) std::memcpy(HM, W->HM.data(), sizeof(double) * W->HM.size());
+  if (bM) std::memcpy(bM, W->bM.data(), sizeof(double) * W->bM.size());
+  if (nf_left) *nf_left = (int)W->frameHessians.size();
+  if (nres_left) *nres_left = (int)W->activeResiduals.size();
+  return ok ? 0 : -1;
+}
+void dmvh_marginalize_frame_hm(double* HM, double* bM, int nFrames, int idx, const double prior8[8], const double delta_prior8[8]) {
+  const int odim = 8 * nFrames + 4;
+  std::vector<double> H(HM, HM + (size_t)odim * odim), b(bM, bM + odim);
+  marginalizeFrameHM(H, b, nFrames, idx, prior8, delta_prior8);
+  std::memcpy(HM, H.data(), sizeof(double) * H.size());
+  std::memcpy(bM, b.data(), sizeof(double) * b.size());
 }
 double dmvh_window_finish_optimize(void* p, int32_t* removed, int cap, int* nremoved, int* nres_left) {
   WindowBA* W = static_cast<WindowBA*>(p);

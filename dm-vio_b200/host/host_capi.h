@@ -30,6 +30,10 @@ void dmvh_window_get_tables(void* win, float* precalc, double* adHost, double* a
 void dmvh_window_get_system(void* win, double* HA, double* bA, double* Hsc, double* bsc, double* lastHS, double* lastbS);
 void dmvh_window_get_states(void* win, double* states10, float* idepth, float* frameEnergyTH);
 double dmvh_window_energy_L(void* win);
+/* WindowBA::marginalizeFrame: 0 ok, -1 error (dmvh_window_error) */
+int dmvh_window_marginalize_frame(void* win, int idx, double* HM, double* bM, int* nf_left, int* nres_left);
+/* host/marg_frame.h on plain arrays (no handle, no GPU): HM (odim*odim) / bM (odim) are overwritten with the ndim = odim - 8 system */
+void dmvh_marginalize_frame_hm(double* HM, double* bM, int nFrames, int idx, const double prior8[8], const double delta_prior8[8]);
 /* WindowBA::marginalizePointsF: marginalises `marg` (dropping the badly constrained ones) and drops `drop`; erases them, re-uploads the window.
  * Returns the resInM increment (-1 on error); HM/bM (N*N, N) and the surviving point count are written if non-NULL. */
 int dmvh_window_marginalize_points(void* win, int nmarg, const int32_t* marg, int ndrop, const int32_t* drop, double* HM, double* bM, int* npts_left,

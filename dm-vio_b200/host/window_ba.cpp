@@ -1,5 +1,6 @@
 // Host-side C++ mirror of FullSystem::optimize / EnergyFunctional on top of the C ABI — see window_ba.h.
 #include "window_ba.h"
+#include "marg_frame.h"
 #include "../csrc/inv3.h"
 #include <algorithm>
 #include <cmath>
@@ -71,6 +72,7 @@ int WindowBA::insertFrame(const float* image, const SE3& evalPT, const double st
   }
   f.setState(state);
   if (image && dmv_ba_upload_image(ba_, f.slot, image) != DMV_OK) { fail("dmv_ba_upload_image"); return -1; }
+  growHM(HM, bM, nf());  // EnergyFunctional::insertFrame (EnergyFunctional.cpp:L453-496): 8 zero rows / columns for the new keyframe
   frameHessians.push_back(f);
   return nf() - 1;
 }
@@ -87,6 +89,53 @@ void WindowBA::dropFrame(int idx) {
   if (idx < 0 || idx >= nf()) return;
   frameHessians.erase(frameHessians.begin() + idx);
   HM.clear(); bM.clear();
+}
+
+bool WindowBA::marginalizeFrame(int idx) {
+  const int n = nf();
+  if (idx < 0 || idx >= n) return false;
+  for (const PointHessian& p : points)
+    if (p.host == idx) { err_ = "marginalizeFrame: the frame still hosts points (flagPointsForRemoval + marginalizePointsF first)"; return false; }
+  // EnergyFunctional.cpp:L569-631 on the host prior; EFFrame::prior / delta_prior as takeData left them (EnergyFunctionalStructs.cpp:L52-64)
+  if ((int)HM.size() != (8 * n + CPARS) * (8 * n + CPARS)) { HM.assign((size_t)(8 * n + CPARS) * (8 * n + CPARS), 0.0); bM.assign(8 * n + CPARS, 0.0); }
+  {
+    const FrameHessian& f = frameHessians[idx];
+    double pr[10], prior8[8], dprior8[8];
+    framePrior(f, pr);
+    for (int i = 0; i < 8; i++) { prior8[i] = pr[i]; dprior8[i] = f.state[i]; }  // getPriorZero() == 0
+    marginalizeFrameHM(HM, bM, n, idx, prior8, dprior8);
+  }
+  // FullSystemMarginalize.cpp:L168-198: drop all observations of existing points in that frame (lastResiduals entries cleared); the frame
+  // leaves, later frames shift down by one index (EnergyFunctional.cpp:L642-649)
+  const int goneID = frameHessians[idx].frameID;
+  for (PointHessian& p : points)
+    for (int k = 0; k < 2; k++) if (p.lastResiduals_target[k] == goneID) p.lastResiduals_target[k] = -1;
+  std::vector<PointFrameResidual> rkeep;
+  rkeep.reserve(activeResiduals.size());
+  for (const PointFrameResidual& r : activeResiduals)
+    if (r.target != idx) { rkeep.push_back(r); if (rkeep.back().target > idx) rkeep.back().target--; }
+  {  // the residual states and the optimised depths live on the device: pull them before the re-upload
+    const int nr = (int)activeResiduals.size(), np = (int)points.size();
+    std::vector<int32_t> ns(nr);
+    std::vector<float> ne(nr);
+    if (nr > 0 && dmv_ba_get_residual_outputs(ba_, ns.data(), ne.data(), nullptr, nullptr, nullptr) == DMV_OK) {
+      int w = 0;
+      for (int i = 0; i < nr; i++)
+        if (activeResiduals[i].target != idx) { rkeep[w].state_state = ns[i]; rkeep[w].state_energy = ne[i]; w++; }
+    }
+    if (np > 0) {
+      std::vector<float> id(np);
+      getIdepths(id.data());
+      for (int i = 0; i < np; i++) { points[i].idepth = id[i]; points[i].idepth_zero = id[i]; points[i].idepth_backup = id[i]; }
+    }
+  }
+  activeResiduals.swap(rkeep);
+  for (PointHessian& p : points) if (p.host > idx) p.host--;
+  frameHessians.erase(frameHessians.begin() + idx);
+  if (!makeIDX()) return false;
+  setAdjointsF();
+  setPrecalcValues();
+  return err_.empty();
 }
 
 void WindowBA::insertPoints(int n, const int* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,

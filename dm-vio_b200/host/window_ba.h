@@ -101,7 +101,12 @@ class WindowBA {
                   int frameID);
   int insertFrameDI(const float* dI_aos3, const SE3& worldToCam_evalPT, const double state[10], const double state_zero[10], float ab_exposure,
                     int frameID);
-  void dropFrame(int idx);
+  void dropFrame(int idx);             // the frame leaves the window and the marginalisation prior is RESET (tests / streaming bench)
+  // FullSystem::marginalizeFrame (FullSystem/FullSystemMarginalize.cpp:L156-219) + EnergyFunctional::marginalizeFrame (EnergyFunctional.cpp:L522-675):
+  // the residuals that still target the frame are dropped, HM/bM are Schur-complemented with respect to the frame's 8 variables (host fp64,
+  // host/marg_frame.h), the frame leaves the window (its image slot becomes free) and the smaller window is re-uploaded.  The frame must not
+  // host points any more (flagPointsForRemoval + marginalizePointsF first).  Returns false on error.
+  bool marginalizeFrame(int idx);
   void insertPoints(int n, const int* host, const float* u, const float* v, const float* idepth, const float* idepth_zero, const float* color8,
                     const float* weights8, const unsigned char* hasDepthPrior);
   void insertResiduals(int n, const int* point, const int* target);

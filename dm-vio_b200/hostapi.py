@@ -24,6 +24,9 @@ def lib():
         L.dmvh_window_error.argtypes = [vp]
         L.dmvh_window_add_frame.argtypes = [vp, f32p, C.c_int, f64p, f64p, f64p, f64p, C.c_float, C.c_int]
         L.dmvh_window_drop_frame.argtypes = [vp, C.c_int]
+        L.dmvh_window_marginalize_frame.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.dmvh_marginalize_frame_hm.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+        L.dmvh_marginalize_frame_hm.restype = None
         L.dmvh_window_finish_optimize.restype = C.c_double
         L.dmvh_window_finish_optimize.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.dmvh_window_get_point_stats.argtypes = [vp, vp, vp]
@@ -59,6 +62,16 @@ def lib():
 
 def _c(a, t):
     return np.ascontiguousarray(a, t)
+
+
+def marginalize_frame_hm(HM, bM, nframes, idx, prior8, delta_prior8):
+    """host/marg_frame.h (EnergyFunctional::marginalizeFrame, visual branch) on plain arrays — host-only, usable without a GPU"""
+    odim = 8 * nframes + 4
+    H = np.array(HM, np.float64).reshape(odim * odim).copy(); b = np.array(bM, np.float64).copy()
+    p, d = _c(prior8, np.float64), _c(delta_prior8, np.float64)
+    lib().dmvh_marginalize_frame_hm(H.ctypes.data, b.ctypes.data, int(nframes), int(idx), p.ctypes.data, d.ctypes.data)
+    n = odim - 8
+    return H[:n * n].reshape(n, n).copy(), b[:n].copy()
 
 
 class WindowBA:
@@ -147,6 +160,17 @@ class WindowBA:
         nm, nd = C.c_int(0), C.c_int(0)
         self.L.dmvh_window_flag_points(self.h, len(f), f.ctypes.data, m.ctypes.data, C.byref(nm), d.ctypes.data, C.byref(nd))
         return m[:nm.value].copy(), d[:nd.value].copy()
+
+    def marginalize_frame(self, idx):
+        """WindowBA::marginalizeFrame: returns dict(HM, bM, nf, nres) of the smaller window"""
+        nfl, nrl = C.c_int(0), C.c_int(0)
+        N = self.N - 8
+        HM, bM = np.zeros(self.N * self.N), np.zeros(self.N)
+        rc = self.L.dmvh_window_marginalize_frame(self.h, int(idx), HM.ctypes.data, bM.ctypes.data, C.byref(nfl), C.byref(nrl))
+        if rc != 0:
+            raise capi.DmvError(self.L.dmvh_window_error(self.h).decode())
+        self.nf, self.nres, self.N = nfl.value, nrl.value, N
+        return dict(HM=HM[:N * N].reshape(N, N).copy(), bM=bM[:N].copy(), nf=self.nf, nres=self.nres)
 
     def marginalize_points(self, marg, drop=()):
         """WindowBA::marginalizePointsF: marginalises `marg` into HM/bM (badly constrained ones are dropped), drops `drop`, erases all of them

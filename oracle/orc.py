@@ -60,6 +60,7 @@ def _declare(L):
     L.orc_win_apply_res.argtypes = [vp]
     L.orc_win_get_res_outputs.argtypes = [vp, i32p, f32p, f32p, f32p, vp, i32p, u8p, f32p]
     L.orc_win_accumulate.argtypes = [vp, C.c_int, f64p, f64p, f64p, f64p, f64p, f64p, C.POINTER(C.c_int)]
+    L.orc_win_marginalize_frame.argtypes = [vp, C.c_int, f64p, f64p, f64p, f64p]
     L.orc_win_finish_optimize.restype = C.c_double
     L.orc_win_finish_optimize.argtypes = [vp, i32p, C.c_int, C.POINTER(C.c_int)]
     L.orc_win_get_point_stats.argtypes = [vp, f32p, i32p]
@@ -240,6 +241,15 @@ class Window:
         log = np.zeros(64)
         n = self.L.orc_win_optimize(self.h, its, precision, log, 64)
         return n, log[log >= 0]
+
+    def marginalize_frame(self, idx, HM, bM):
+        """EnergyFunctional::marginalizeFrame (EnergyFunctional.cpp:L522-675) of frame idx on the prior (HM, bM); the frame leaves the window"""
+        odim = 8 * self.nf + 4
+        HM = np.ascontiguousarray(HM, np.float64).reshape(odim * odim); bM = np.ascontiguousarray(bM, np.float64)
+        Ho = np.zeros((odim - 8) * (odim - 8)); bo = np.zeros(odim - 8)
+        self.L.orc_win_marginalize_frame(self.h, int(idx), HM, bM, Ho, bo)
+        self.nf -= 1; self.N -= 8
+        return Ho.reshape(odim - 8, odim - 8), bo
 
     def finish_optimize(self):
         """tail of FullSystem::optimize (FullSystemOptimize.cpp:L591-609): setEvalPT of the newest frame, adjoints, precalc, linearizeAll(true).

@@ -1126,6 +1126,103 @@ void Window::loadStateBackup() {  // FullSystemOptimize.cpp:L371-388
   setPrecalcValues();
 }
 
+// 8x8 inverse by LU with partial pivoting (what Eigen's inverse() does for fixed sizes above 4x4)
+static void inverse8(const double A[8][8], double Ainv[8][8]) {
+  double M[8][16];
+  for (int i = 0; i < 8; i++)
+    for (int j = 0; j < 8; j++) { M[i][j] = A[i][j]; M[i][8 + j] = (i == j) ? 1.0 : 0.0; }
+  for (int c = 0; c < 8; c++) {
+    int piv = c;
+    for (int r = c + 1; r < 8; r++) if (std::fabs(M[r][c]) > std::fabs(M[piv][c])) piv = r;
+    if (piv != c) for (int j = 0; j < 16; j++) std::swap(M[c][j], M[piv][j]);
+    const double d = M[c][c];
+    for (int r = c + 1; r < 8; r++) {
+      const double f = M[r][c] / d;
+      if (f == 0.0) continue;
+      for (int j = c; j < 16; j++) M[r][j] -= f * M[c][j];
+    }
+  }
+  for (int c = 7; c >= 0; c--) {  // back substitution on the 8 right-hand sides
+    for (int j = 8; j < 16; j++) {
+      double v = M[c][j];
+      for (int k = c + 1; k < 8; k++) v -= M[c][k] * M[k][j];
+      M[c][j] = v / M[c][c];
+    }
+  }
+  for (int i = 0; i < 8; i++)
+    for (int j = 0; j < 8; j++) Ainv[i][j] = M[i][8 + j];
+}
+
+void Window::marginalizeFrame(int idx) {  // EnergyFunctional.cpp:L522-675
+  const int n = nf(), odim = n * 8 + CPARS, ndim = odim - 8;
+  for (const Point& p : points) if (p.host == idx && !p.residuals.empty()) { fprintf(stderr, "orc: marginalizeFrame: frame still hosts points\n"); abort(); }
+  if ((int)HM.rows != odim) { HM = MatX(odim, odim); bM.assign(odim, 0.0); }
+  // L572-592: move the frame's block to the end
+  std::vector<int> perm;
+  const int io = idx * 8 + CPARS;
+  for (int i = 0; i < odim; i++) if (i < io || i >= io + 8) perm.push_back(i);
+  for (int k = 0; k < 8; k++) perm.push_back(io + k);
+  MatX H(odim, odim);
+  VecX b(odim);
+  for (int i = 0; i < odim; i++) {
+    b[i] = bM[perm[i]];
+    for (int j = 0; j < odim; j++) H(i, j) = HM(perm[i], perm[j]);
+  }
+  // L595-596: the frame's own prior
+  const Frame& f = frames[idx];
+  for (int k = 0; k < 8; k++) { H(ndim + k, ndim + k) += f.prior[k]; b[ndim + k] += f.prior[k] * f.delta_prior[k]; }
+  // L603-612: diagonal scaling
+  VecX SVec(odim), SVecI(odim);
+  for (int i = 0; i < odim; i++) { SVec[i] = std::sqrt(std::fabs(H(i, i)) + 10.0); SVecI[i] = 1.0 / SVec[i]; }
+  for (int i = 0; i < odim; i++) {
+    for (int j = 0; j < odim; j++) H(i, j) = (SVecI[i] * H(i, j)) * SVecI[j];
+    b[i] = SVecI[i] * b[i];
+  }
+  // L615-618: hpi = inverse of the bottom-right block (the 0.5f*(hpi+hpi) lines of the reference are the identity)
+  double blk[8][8], hpi[8][8];
+  for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) blk[i][j] = H(ndim + i, ndim + j);
+  inverse8(blk, hpi);
+  // L621-623: Schur complement
+  MatX bli(ndim, 8);
+  for (int i = 0; i < ndim; i++)
+    for (int k = 0; k < 8; k++) {
+      double v = 0;
+      for (int m = 0; m < 8; m++) v += H(ndim + m, i) * hpi[m][k];
+      bli(i, k) = v;
+    }
+  MatX Hn(ndim, ndim);
+  VecX bn(ndim);
+  for (int i = 0; i < ndim; i++) {
+    for (int j = 0; j < ndim; j++) {
+      double v = 0;
+      for (int k = 0; k < 8; k++) v += bli(i, k) * H(ndim + k, j);
+      Hn(i, j) = H(i, j) - v;
+    }
+    double v = 0;
+    for (int k = 0; k < 8; k++) v += bli(i, k) * b[ndim + k];
+    bn[i] = b[i] - v;
+  }
+  // L626-631: unscale, symmetrise
+  for (int i = 0; i < ndim; i++) {
+    for (int j = 0; j < ndim; j++) Hn(i, j) = (SVec[i] * Hn(i, j)) * SVec[j];
+    bn[i] = SVec[i] * bn[i];
+  }
+  HM = MatX(ndim, ndim);
+  bM.assign(ndim, 0.0);
+  for (int i = 0; i < ndim; i++) {
+    for (int j = 0; j < ndim; j++) HM(i, j) = 0.5 * (Hn(i, j) + Hn(j, i));
+    bM[i] = bn[i];
+  }
+  // L642-649: the frame leaves the window; later frames shift down
+  for (Residual& r : residuals) {
+    if ((r.target == idx || r.host == idx) && !r.dropped) { fprintf(stderr, "orc: marginalizeFrame: live residual still references the frame\n"); abort(); }
+    if (r.target > idx) r.target--;
+    if (r.host > idx) r.host--;
+  }
+  for (Point& p : points) if (p.host > idx) p.host--;
+  frames.erase(frames.begin() + idx);
+}
+
 double Window::finishOptimize(std::vector<int>* toRemove) {  // FullSystemOptimize.cpp:L591-609
   Frame& newest = frames.back();
   Vec10 newStateZero;

@@ -203,6 +203,12 @@ struct Window {
   std::vector<int> fixLinearization(const std::vector<int>& pts);
   void marginalizePoints(const std::vector<int>& pts, int precision, ReducedSystem& sys);
 
+  // EnergyFunctional::marginalizeFrame (EnergyFunctional.cpp:L522-675, visual branch L569-631): the frame's 8 rows/columns of HM, bM are
+  // moved to the end, its prior is added, the system is diagonally scaled, the 8x8 block is inverted and Schur-complemented away, the
+  // result is unscaled and symmetrised.  The frame must not host points or be targeted by residuals any more; it is erased from `frames`
+  // (adjoints / precalc / deltas must be rebuilt by the caller, as the reference invalidates them).
+  void marginalizeFrame(int idx);
+
   // FullSystemOptimize.cpp:L224-388
   void backupState();
   bool doStepFromBackup();

@@ -276,6 +276,19 @@ void orc_win_get_point_stats(OrcWin* o, float* maxRelBaseline, int32_t* numGoodR
     if (numGoodResiduals) numGoodResiduals[i] = o->W.points[i].numGoodResiduals;
   }
 }
+// EnergyFunctional::marginalizeFrame on the given prior (HM_in: odim*odim, bM_in: odim); outputs ndim = odim - 8.  The window must hold no
+// points hosted in / residuals targeting the frame (use a frames-only window).
+void orc_win_marginalize_frame(OrcWin* o, int idx, const double* HM_in, const double* bM_in, double* HM_out, double* bM_out) {
+  Window& W = o->W;
+  const int odim = W.nf() * 8 + CPARS, ndim = odim - 8;
+  W.HM = MatX(odim, odim);
+  W.bM.assign(odim, 0.0);
+  std::memcpy(W.HM.d.data(), HM_in, sizeof(double) * odim * odim);
+  std::memcpy(W.bM.data(), bM_in, sizeof(double) * odim);
+  W.marginalizeFrame(idx);
+  std::memcpy(HM_out, W.HM.d.data(), sizeof(double) * ndim * ndim);
+  std::memcpy(bM_out, W.bM.data(), sizeof(double) * ndim);
+}
 void orc_win_get_frame_states(OrcWin* o, double* state10) {
   for (int f = 0; f < o->W.nf(); f++) for (int k = 0; k < 10; k++) state10[10 * f + k] = o->W.frames[f].state[k];
 }

@@ -507,6 +507,23 @@ void ref_win_marginalize(RefWin* W, int n, const int32_t* pts, int, double* M, d
   // the flagged points are gone from the energy functional (efPoint / efResidual are null now; ref_win_destroy copes)
 }
 
+// The reference's EnergyFunctional::marginalizeFrame (EnergyFunctional.cpp:L522-675) on a given prior.  The frame must host no points and
+// be the target of no residuals (frames-only window).  The frame object stays in the harness list for ref_win_destroy (efFrame is null).
+void ref_win_marginalize_frame(RefWin* W, int idx, const double* HM_in, const double* bM_in, double* HM_out, double* bM_out) {
+  const int odim = W->nf * 8 + CPARS;
+  W->ef->HM = MatXX::Zero(odim, odim);
+  W->ef->bM = VecX::Zero(odim);
+  for (int i = 0; i < odim; i++) {
+    W->ef->bM[i] = bM_in[i];
+    for (int j = 0; j < odim; j++) W->ef->HM(i, j) = HM_in[(size_t)i * odim + j];
+  }
+  W->ef->HMForGTSAM = MatXX::Zero(odim, odim);
+  W->ef->bMForGTSAM = VecX::Zero(odim);
+  W->ef->marginalizeFrame(W->frames[idx]->efFrame);
+  out_mat(W->ef->HM, HM_out); out_vec(W->ef->bM, bM_out);
+  W->nf--;
+}
+
 double ref_win_calc_LEnergy(RefWin* W) { return W->ef->calcLEnergyF_MT(); }
 double ref_win_calc_MEnergy(RefWin* W) { return W->ef->calcMEnergyF(false); }
 

@@ -52,3 +52,14 @@ def test_no_device_means_error_not_cpu_fallback(capi):
 
 def test_version_string(capi):
     assert b"sm_100a" in capi.lib().dmv_version()
+
+
+def test_keyframe_entry_points_validate_arguments(capi):
+    """null handles / null argument blocks are rejected before anything touches CUDA"""
+    L = capi.lib()
+    assert L.dmv_ba_reset_oob(None) == DMV_ERR_INVALID
+    import numpy as np
+    assert L.dmv_ba_drop_residuals(None, 0, np.zeros(1, np.int32)) == DMV_ERR_INVALID
+    assert L.dmv_ba_marginalize_points(None, None) != DMV_OK
+    assert L.dmv_ba_activate_points(None, None) != DMV_OK
+    assert L.dmv_last_error() != b""

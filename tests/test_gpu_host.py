@@ -206,3 +206,34 @@ def test_flag_points_for_removal_rules(hostapi, orc, synth):
     assert g["npts"] == npts - len(drop) - len(marg) and g["resInM"] > 0
     assert np.isfinite(hw.linearize())
     hw.close()
+
+
+def test_keyframe_turnover_flow(hostapi, orc, synth):
+    """The makeKeyFrame sequence on the adapter: optimize -> tail -> flagPointsForRemoval(frame 0) -> marginalizePointsF -> marginalizeFrame(0)
+    (FullSystemMarginalize.cpp:L156-219 + EnergyFunctional.cpp:L522-675).  The prior that comes out is exactly host/marg_frame.h applied to
+    the prior after the point marginalisation (that function is pinned to the reference through the oracle on the CPU); the window of
+    nf - 1 frames keeps optimising with the prior in place."""
+    nf = 6
+    W = synth.make_window(nf=nf, npts=500, seed=31, state_noise=1e-3, hosts="all")
+    prior0 = orc.Window(W).frame_tables()["prior"][0]
+    hw = hostapi.WindowBA(W)
+    hw.optimize(3)
+    hw.finish_optimize()
+    marg, drop = hw.flag_points([0])
+    assert len(marg) > 10
+    g = hw.marginalize_points(marg, drop)
+    assert g["resInM"] > 0 and np.abs(g["HM"]).max() > 0
+    st, _, _ = hw.states()
+    exp_H, exp_b = hostapi.marginalize_frame_hm(g["HM"], g["bM"], nf, 0, prior0, st[0][:8])
+    nres_before = hw.nres
+    m = hw.marginalize_frame(0)
+    assert m["nf"] == nf - 1 and m["HM"].shape == (8 * (nf - 1) + 4,) * 2
+    assert rel(m["HM"], exp_H) < 1e-12 and rel(m["bM"], exp_b) < 1e-12
+    assert m["nres"] < nres_before                                   # the observations in the marginalised frame are gone
+    e = hw.linearize()
+    assert np.isfinite(e) and e > 0
+    n, log = hw.optimize(3)
+    assert n >= 1 and np.all(np.isfinite(log)) and log[-1] <= log[0] * (1 + 1e-9)
+    st2, _, _ = hw.states()
+    assert st2.shape[0] == nf - 1
+    hw.close()
