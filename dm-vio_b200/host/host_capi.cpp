@@ -139,6 +139,7 @@ void dmvh_window_get_states(void* p, double* st, float* idepth, float* th) {
   if (th) for (size_t f = 0; f < W->frameHessians.size(); f++) th[f] = W->frameHessians[f].frameEnergyTH;
 }
 double dmvh_window_energy_L(void* p) { return static_cast<WindowBA*>(p)->calcLEnergyF_MT(); }
+double dmvh_window_energy_M(void* p) { return static_cast<WindowBA*>(p)->calcMEnergyF(); }
 
 void* dmvh_ct_create(int w, int h, int levels, int max_points, int device, const double cvs[4]) {
   CoarseTracker* C = new CoarseTracker(w, h, levels, max_points, device);

@@ -30,6 +30,7 @@ void dmvh_window_get_tables(void* win, float* precalc, double* adHost, double* a
 void dmvh_window_get_system(void* win, double* HA, double* bA, double* Hsc, double* bsc, double* lastHS, double* lastbS);
 void dmvh_window_get_states(void* win, double* states10, float* idepth, float* frameEnergyTH);
 double dmvh_window_energy_L(void* win);
+double dmvh_window_energy_M(void* win); /* EnergyFunctional::calcMEnergyF: the marginalisation prior's energy at the current state */
 /* WindowBA::marginalizeFrame: 0 ok, -1 error (dmvh_window_error) */
 int dmvh_window_marginalize_frame(void* win, int idx, double* HM, double* bM, int* nf_left, int* nres_left);
 /* host/marg_frame.h on plain arrays (no handle, no GPU): HM (odim*odim) / bM (odim) are overwritten with the ndim = odim - 8 system */

@@ -46,6 +46,8 @@ def lib():
         L.dmvh_window_get_states.argtypes = [vp, f64p, f32p, f32p]
         L.dmvh_window_energy_L.restype = C.c_double
         L.dmvh_window_energy_L.argtypes = [vp]
+        L.dmvh_window_energy_M.restype = C.c_double
+        L.dmvh_window_energy_M.argtypes = [vp]
         L.dmvh_ct_create.restype = vp
         L.dmvh_ct_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64p]
         L.dmvh_ct_destroy.argtypes = [vp]
@@ -160,6 +162,10 @@ class WindowBA:
         nm, nd = C.c_int(0), C.c_int(0)
         self.L.dmvh_window_flag_points(self.h, len(f), f.ctypes.data, m.ctypes.data, C.byref(nm), d.ctypes.data, C.byref(nd))
         return m[:nm.value].copy(), d[:nd.value].copy()
+
+    def energies_LM(self):
+        """(calcLEnergyF_MT, calcMEnergyF) at the current state"""
+        return self.L.dmvh_window_energy_L(self.h), self.L.dmvh_window_energy_M(self.h)
 
     def marginalize_frame(self, idx):
         """WindowBA::marginalizeFrame: returns dict(HM, bM, nf, nres) of the smaller window"""

@@ -232,7 +232,12 @@ def test_keyframe_turnover_flow(hostapi, orc, synth):
     assert m["nres"] < nres_before                                   # the observations in the marginalised frame are gone
     e = hw.linearize()
     assert np.isfinite(e) and e > 0
+    eL, eM = hw.energies_LM()
+    assert eM != 0                                                    # the prior is active: the window sits off the marginalisation point
     n, log = hw.optimize(3)
+    eL1, eM1 = hw.energies_LM()
+    # what the LM loop minimises (FullSystemOptimize.cpp:L548-551); log[0] / log[-1] are the photometric energies at the same two states
+    assert log[-1] + eL1 + eM1 <= (log[0] + eL + eM) * (1 + 1e-9)
     # the log holds the photometric energy only; steps are accepted on photometric + prior energies (L + M), so with the marginalisation
     # prior in place the photometric part may give a little while the total goes down
     assert n >= 1 and np.all(np.isfinite(log)) and log[-1] <= log[0] * 1.01
