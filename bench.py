@@ -216,6 +216,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="points per thread block (8/16/32, 0 = library default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--points", type=int, default=0,
+                    help="points per GPU; default 2000 = BASELINE.json configs[1] (the headline).  8000 = SURVEY config 4, an extra data point only")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: all-reduce of the stitched system by the peer-memory kernel (NVLink, CUDA IPC) or by NCCL")
     args = ap.parse_args()
@@ -224,6 +226,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.steps < 1:
         args.steps = 1
+    if args.points > 0:
+        global NPTS, METRIC
+        NPTS = args.points
+        METRIC = METRIC.replace("2000 pts", f"{NPTS} pts")
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
