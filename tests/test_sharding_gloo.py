@@ -86,6 +86,55 @@ def test_shard_allreduce_matches_unsharded(orc, synth, cfg):
     np.testing.assert_array_equal(tot["counts"], [(st == 0).sum(), (st == 1).sum(), (st == 2).sum()])
 
 
+def _marg_worker(rank, world, port, cfg, flagged, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import dmvio_b200.synth as synth
+    from dmvio_b200.sharding import shard_window, shard_points
+    from oracle import orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    W = synth.make_window(**cfg)
+    mine = np.nonzero(shard_points(W["host"], rank, world))[0]          # global indices of this rank's points, in shard order
+    local = np.nonzero(np.isin(mine, flagged))[0].astype(np.int32)       # the flagged ones, as shard-local indices
+    S = shard_window(W, rank, world)
+    o = orc.Window(S).marginalize(local, precision=1)
+    N = 8 * W["nf"] + 4
+    buf = torch.from_numpy(np.concatenate([o["H"].reshape(-1), o["b"], [float(o["resInM"])]]))
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)                           # the exchange a sharded marginalisation needs: one sum of M - Msc | Mb - Mbsc
+    q.put((rank, len(local), buf.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_marginalisation_sums_to_unsharded(orc, synth):
+    """point marginalisation shards like the rest of the path: every rank marginalises the flagged points it owns, the sum of the per-rank
+    M - Msc, Mb - Mbsc, resInM equals the unsharded EnergyFunctional::marginalizePointsF (per-point terms only: SURVEY.md section 8e)"""
+    cfg = dict(nf=4, npts=301, seed=5, w=160, h=120)
+    W = synth.make_window(**cfg)
+    flagged = np.sort(np.random.default_rng(3).choice(len(W["host"]), 120, replace=False))
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_marg_worker, args=(r, world, port, cfg, flagged, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sum(r[1] for r in res) == len(flagged)
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    N = 8 * W["nf"] + 4
+    full = orc.Window(W).marginalize(flagged.astype(np.int32), precision=1)
+    tot = res[0][2]
+    assert rel(tot[:N * N].reshape(N, N), full["H"]) < 1e-12
+    assert rel(tot[N * N:N * N + N], full["b"]) < 1e-11
+    assert int(tot[-1]) == full["resInM"]
+
+
 def test_shard_edge_cases(synth):
     from dmvio_b200.sharding import shard_window, shard_points
     W = synth.make_window(nf=3, npts=5, seed=2, w=96, h=64, hosts="all")
