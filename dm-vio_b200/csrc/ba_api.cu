@@ -170,6 +170,8 @@ static void next_exchange(dmv_ba* b) {
 
 extern "C" {
 
+static int ba_allocate(dmv_ba* b, const dmv_ba_config* cfg);
+
 void dmv_ba_default_params(dmv_ba_params* p) {
   p->huberTH = 9.f;
   p->outlierTHSumComponent = 50.f * 50.f;
@@ -189,6 +191,16 @@ int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
   if (cfg->device < 0 || cfg->device >= ndev) return set_error(DMV_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
   CK(cudaSetDevice(cfg->device));
   dmv_ba* b = new dmv_ba();
+  const int rc = ba_allocate(b, cfg);
+  if (rc != DMV_OK) {  // e.g. out of device memory half-way: release what was allocated (the error message of the failing call is kept)
+    dmv_ba_destroy(b);
+    return rc;
+  }
+  *out = b;
+  return DMV_OK;
+}
+
+static int ba_allocate(dmv_ba* b, const dmv_ba_config* cfg) {
   b->cfg = *cfg;
   b->device = cfg->device;
   dmv_ba_default_params(&b->prm);
@@ -248,7 +260,6 @@ int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
   b->scratch_floats = std::max((size_t)mp * 8 * MF, npx * 3);
   CK(cudaMallocHost(&b->h_scratch, sizeof(float) * b->scratch_floats));
   for (int f = 0; f < MF; f++) b->slots[f] = f;
-  *out = b;
   return DMV_OK;
 }
 

@@ -567,6 +567,8 @@ struct dmv_ct {
 
 extern "C" {
 
+static int ct_allocate(dmv_ct* c, const dmv_ct_config* cfg);
+
 int dmv_ct_create(const dmv_ct_config* cfg, dmv_ct** out) {
   if (!cfg || !out) return set_error(DMV_ERR_INVALID, "null argument");
   if (cfg->levels < 1 || cfg->levels > DMV_MAX_PYR_LEVELS || cfg->w < 16 || cfg->h < 16 || cfg->max_points < 1)
@@ -579,6 +581,16 @@ int dmv_ct_create(const dmv_ct_config* cfg, dmv_ct** out) {
   if (cfg->device < 0 || cfg->device >= ndev) return set_error(DMV_ERR_INVALID, "device out of range");
   CK(cudaSetDevice(cfg->device));
   dmv_ct* c = new dmv_ct();
+  const int rc = ct_allocate(c, cfg);
+  if (rc != DMV_OK) {  // allocation failed half-way: release what exists, keep the failing call's error message
+    dmv_ct_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return DMV_OK;
+}
+
+static int ct_allocate(dmv_ct* c, const dmv_ct_config* cfg) {
   c->cfg = *cfg;
   c->device = cfg->device;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -604,7 +616,6 @@ int dmv_ct_create(const dmv_ct_config* cfg, dmv_ct** out) {
   CK(cudaMalloc(&c->d_out, sizeof(double) * 64));
   CK(cudaMallocHost(&c->h_out, sizeof(double) * 64));
   CK(cudaMallocHost(&c->h_scratch, sizeof(float) * std::max(npx0 * 3, (size_t)cfg->max_points * 4)));
-  *out = c;
   return DMV_OK;
 }
 
@@ -619,8 +630,9 @@ int dmv_ct_destroy(dmv_ct* c) {
   cudaFreeHost(c->h_out); cudaFreeHost(c->h_scratch); cudaFree(c->d_ip); cudaFreeHost(c->h_ip);
   for (int l = 0; l < DMV_MAX_PYR_LEVELS; l++) { cudaFree(c->cd_idepth[l]); cudaFree(c->cd_ws[l]); cudaFree(c->cd_ws2[l]); }
   cudaFree(c->cd_rowcnt); cudaFree(c->cd_rowoff); cudaFreeHost(c->cd_totals);
-  cudaEventDestroy(c->ev[0]); cudaEventDestroy(c->ev[1]);
-  cudaStreamDestroy(c->stream);
+  if (c->ev[0]) cudaEventDestroy(c->ev[0]);
+  if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return DMV_OK;
 }
