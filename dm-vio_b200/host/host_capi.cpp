@@ -2,6 +2,7 @@
 #include "coarse_tracker.h"
 #include "window_ba.h"
 #include "marg_frame.h"
+#include "nullspace.h"
 #include <cstring>
 
 using namespace dmvio_b200;
@@ -78,6 +79,18 @@ int dmvh_window_marginalize_frame(void* p, int idx, double* HM, double* bM, int*
   if (nf_left) *nf_left = (int)W->frameHessians.size();
   if (nres_left) *nres_left = (int)W->activeResiduals.size();
   return ok ? 0 : -1;
+}
+void dmvh_nullspaces_orthogonalize(int nf, const double* evalPT12, double* ns_out, double* x, double solverModeDelta) {
+  std::vector<SE3> T(nf);
+  for (int f = 0; f < nf; f++) T[f] = mkSE3(evalPT12 + 12 * f, evalPT12 + 12 * f + 9);
+  const std::vector<std::vector<double>> ns = windowNullspaces(T, SCALE_XI_TRANS, SCALE_XI_ROT);
+  const int N = 8 * nf + 4;
+  if (ns_out) for (int a = 0; a < 7; a++) std::memcpy(ns_out + (size_t)a * N, ns[a].data(), sizeof(double) * N);
+  if (x) {
+    std::vector<double> v(x, x + N);
+    orthogonalizeX(v, ns, solverModeDelta);
+    std::memcpy(x, v.data(), sizeof(double) * N);
+  }
 }
 void dmvh_marginalize_frame_hm(double* HM, double* bM, int nFrames, int idx, const double prior8[8], const double delta_prior8[8]) {
   const int odim = 8 * nFrames + 4;

@@ -33,6 +33,9 @@ double dmvh_window_energy_L(void* win);
 double dmvh_window_energy_M(void* win); /* EnergyFunctional::calcMEnergyF: the marginalisation prior's energy at the current state */
 /* WindowBA::marginalizeFrame: 0 ok, -1 error (dmvh_window_error) */
 int dmvh_window_marginalize_frame(void* win, int idx, double* HM, double* bM, int* nf_left, int* nres_left);
+/* host/nullspace.h on plain arrays (no handle, no GPU): evalPT = nf x (R row-major 9 | t 3); ns_out 7 x (8 nf + 4), may be NULL;
+ * x (8 nf + 4, may be NULL) is orthogonalised in place (EnergyFunctional::orthogonalize) */
+void dmvh_nullspaces_orthogonalize(int nf, const double* evalPT12, double* ns_out, double* x, double solverModeDelta);
 /* host/marg_frame.h on plain arrays (no handle, no GPU): HM (odim*odim) / bM (odim) are overwritten with the ndim = odim - 8 system */
 void dmvh_marginalize_frame_hm(double* HM, double* bM, int nFrames, int idx, const double prior8[8], const double delta_prior8[8]);
 /* WindowBA::marginalizePointsF: marginalises `marg` (dropping the badly constrained ones) and drops `drop`; erases them, re-uploads the window.

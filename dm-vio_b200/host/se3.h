@@ -2,6 +2,7 @@
 // Conventions follow Sophus: tangent = (translation, rotation), exp(xi) * T is a LEFT increment
 // (reference thirdparty/Sophus/sophus/se3.hpp:L131-139 Adj, L407-428 exp).  Rotation matrices, row-major, double.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -41,6 +42,27 @@ struct SE3 {
         A[(i + 3) * 6 + j + 3] = R[i * 3 + j];
         A[i * 6 + j + 3] = h[i * 3] * R[j] + h[i * 3 + 1] * R[3 + j] + h[i * 3 + 2] * R[6 + j];
       }
+  }
+  // Sophus SE3::log (se3.hpp): xi = (V^-1 t, omega), omega from the rotation matrix
+  void log(double xi[6]) const {
+    const double tr = R[0] + R[4] + R[8];
+    const double c = std::min(1.0, std::max(-1.0, 0.5 * (tr - 1.0)));
+    const double th = std::acos(c);
+    const double v[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+    const double f = (th < 1e-10) ? (0.5 + th * th / 12.0) : th / (2.0 * std::sin(th));
+    const double om[3] = {v[0] * f, v[1] * f, v[2] * f};
+    const double th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2], tho = std::sqrt(th2);
+    const double W[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0};
+    double W2[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) W2[i * 3 + j] = W[i * 3] * W[j] + W[i * 3 + 1] * W[3 + j] + W[i * 3 + 2] * W[6 + j];
+    const double k = (tho < 1e-10) ? (1.0 / 12.0 + th2 / 720.0) : (1.0 - tho * std::cos(0.5 * tho) / (2.0 * std::sin(0.5 * tho))) / th2;
+    for (int i = 0; i < 3; i++) {
+      double s = 0;
+      for (int j = 0; j < 3; j++) s += (((i == j) ? 1.0 : 0.0) - 0.5 * W[i * 3 + j] + k * W2[i * 3 + j]) * t[j];
+      xi[i] = s;
+      xi[3 + i] = om[i];
+    }
   }
   static SE3 exp(const double xi[6]) {
     const double wx = xi[3], wy = xi[4], wz = xi[5];

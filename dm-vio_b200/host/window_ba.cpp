@@ -1,6 +1,7 @@
 // Host-side C++ mirror of FullSystem::optimize / EnergyFunctional on top of the C ABI — see window_ba.h.
 #include "window_ba.h"
 #include "marg_frame.h"
+#include "nullspace.h"
 #include "../csrc/inv3.h"
 #include <algorithm>
 #include <cmath>
@@ -502,8 +503,7 @@ double WindowBA::calcMEnergyF() {  // EnergyFunctional.cpp:L324-346
 }
 
 void WindowBA::solveSystemF(int iteration, double lambda) {
-  // EnergyFunctional.cpp:L841-996, default solver mode, no-GTSAM branch (L971-973)
-  (void)iteration;
+  // EnergyFunctional.cpp:L841-996, default solver mode (SOLVER_ORTHOGONALIZE_X_LATER), no-GTSAM branch (L971-973)
   const int n = nf(), N = 8 * n + CPARS;
   last_HA.assign((size_t)N * N, 0.0); last_bA.assign(N, 0.0); last_Hsc.assign((size_t)N * N, 0.0); last_bsc.assign(N, 0.0);
   if (dmv_ba_accumulate(ba_, last_HA.data(), last_bA.data(), last_Hsc.data(), last_bsc.data(), &resInA) != DMV_OK) { fail("dmv_ba_accumulate"); return; }
@@ -539,6 +539,11 @@ void WindowBA::solveSystemF(int iteration, double lambda) {
   ldlt_solve(N, Hs.data(), bs.data(), xs.data());
   lastX.resize(N);
   for (int i = 0; i < N; i++) lastX[i] = SVecI[i] * xs[i];
+  if (iteration >= 2 && s.setting_orthogonalizeXLater) {  // L980-984: project x off the 7 gauge directions (6 pose + 1 scale)
+    std::vector<SE3> evalPT(n);
+    for (int h = 0; h < n; h++) evalPT[h] = frameHessians[h].worldToCam_evalPT;
+    orthogonalizeX(lastX, windowNullspaces(evalPT, SCALE_XI_TRANS, SCALE_XI_ROT), s.setting_solverModeDelta);
+  }
   // resubstituteF_MT (EnergyFunctional.cpp:L267-289): frame / calib steps here, the per-point half is fused into the next linearizeAll
   for (int i = 0; i < 4; i++) Hcalib.step[i] = -lastX[i];
   for (int h = 0; h < n; h++) {

@@ -27,6 +27,8 @@ struct Settings {  // util/settings.cpp:L60-160
   float setting_frameEnergyTHConstWeight = 0.5f, setting_frameEnergyTHN = 0.7f, setting_frameEnergyTHFacMedian = 1.5f;
   float setting_thOptIterations = 1.2f;
   int setting_minOptIterations = 1;
+  bool setting_orthogonalizeXLater = true;   // setting_solverMode & SOLVER_ORTHOGONALIZE_X_LATER (settings.cpp:L81)
+  double setting_solverModeDelta = 0.00001;  // settings.cpp:L82
   float setting_minIdepth = 0.02f;                                       // settings.cpp:L53
   int setting_minGoodActiveResForMarg = 3, setting_minGoodResForMarg = 4;  // settings.cpp:L127-128
   float setting_idepthFixPriorMargFac = 600 * 600, setting_margWeightFac = 0.5f * 0.5f, setting_minIdepthH_marg = 50;  // settings.cpp:L68, L118, L89

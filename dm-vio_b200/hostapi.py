@@ -27,6 +27,8 @@ def lib():
         L.dmvh_window_marginalize_frame.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.dmvh_marginalize_frame_hm.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
         L.dmvh_marginalize_frame_hm.restype = None
+        L.dmvh_nullspaces_orthogonalize.argtypes = [C.c_int, vp, vp, vp, C.c_double]
+        L.dmvh_nullspaces_orthogonalize.restype = None
         L.dmvh_window_finish_optimize.restype = C.c_double
         L.dmvh_window_finish_optimize.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.dmvh_window_get_point_stats.argtypes = [vp, vp, vp]
@@ -64,6 +66,17 @@ def lib():
 
 def _c(a, t):
     return np.ascontiguousarray(a, t)
+
+
+def nullspaces_orthogonalize(R_eval, t_eval, x=None, delta=1e-5):
+    """host/nullspace.h on plain arrays: returns (nullspaces (7, N), x projected off them or None) — host-only, usable without a GPU"""
+    nf = len(R_eval)
+    N = 8 * nf + 4
+    T = np.concatenate([np.asarray(R_eval, np.float64).reshape(nf, 9), np.asarray(t_eval, np.float64).reshape(nf, 3)], axis=1).copy()
+    ns = np.zeros((7, N))
+    xv = None if x is None else np.array(x, np.float64).copy()
+    lib().dmvh_nullspaces_orthogonalize(nf, T.ctypes.data, ns.ctypes.data, None if xv is None else xv.ctypes.data, float(delta))
+    return ns, xv
 
 
 def marginalize_frame_hm(HM, bM, nframes, idx, prior8, delta_prior8):

@@ -60,6 +60,8 @@ def _declare(L):
     L.orc_win_apply_res.argtypes = [vp]
     L.orc_win_get_res_outputs.argtypes = [vp, i32p, f32p, f32p, f32p, vp, i32p, u8p, f32p]
     L.orc_win_accumulate.argtypes = [vp, C.c_int, f64p, f64p, f64p, f64p, f64p, f64p, C.POINTER(C.c_int)]
+    L.orc_win_get_nullspaces.argtypes = [vp, f64p]
+    L.orc_win_orthogonalize.argtypes = [vp, f64p]
     L.orc_win_marginalize_frame.argtypes = [vp, C.c_int, f64p, f64p, f64p, f64p]
     L.orc_win_finish_optimize.restype = C.c_double
     L.orc_win_finish_optimize.argtypes = [vp, i32p, C.c_int, C.POINTER(C.c_int)]
@@ -241,6 +243,18 @@ class Window:
         log = np.zeros(64)
         n = self.L.orc_win_optimize(self.h, its, precision, log, 64)
         return n, log[log >= 0]
+
+    def nullspaces(self):
+        """FullSystem::getNullspaces: (7, N) = 6 pose + 1 scale gauge directions at the frames' evaluation points"""
+        out = np.zeros((7, self.N))
+        self.L.orc_win_get_nullspaces(self.h, out.reshape(-1))
+        return out
+
+    def orthogonalize(self, x):
+        """EnergyFunctional::orthogonalize(&x, 0)"""
+        v = np.ascontiguousarray(x, np.float64).copy()
+        self.L.orc_win_orthogonalize(self.h, v)
+        return v
 
     def marginalize_frame(self, idx, HM, bM):
         """EnergyFunctional::marginalizeFrame (EnergyFunctional.cpp:L522-675) of frame idx on the prior (HM, bM); the frame leaves the window"""

@@ -1006,6 +1006,102 @@ void Window::resubstitute(const VecX& x) {
   else body(0, (int)points.size(), nullptr, 0);
 }
 
+std::vector<VecX> Window::getNullspaces() const {
+  const int n = nf(), N = 8 * n + CPARS;
+  std::vector<VecX> ns(7, VecX(N));
+  for (VecX& v : ns) std::fill(v.begin(), v.end(), 0.0);
+  for (int f = 0; f < n; f++) {
+    const SE3& T = frames[f].worldToCam_evalPT;
+    const SE3 Ti = T.inverse();
+    for (int i = 0; i < 6; i++) {  // HessianBlocks.cpp:L81-89
+      Vec6 eps; for (int k = 0; k < 6; k++) eps[k] = 0; eps[i] = 1e-3;
+      Vec6 epsm; for (int k = 0; k < 6; k++) epsm[k] = -eps[k];
+      const Vec6 lp = ((T * SE3::exp(eps)) * Ti).log(), lm = ((T * SE3::exp(epsm)) * Ti).log();
+      for (int k = 0; k < 6; k++) {
+        double v = (lp[k] - lm[k]) / (2e-3);
+        v *= (k < 3) ? (1.0 / SCALE_XI_TRANS) : (1.0 / SCALE_XI_ROT);  // FullSystemOptimize.cpp:L725-726
+        ns[i][CPARS + 8 * f + k] = v;
+      }
+    }
+    // HessianBlocks.cpp:L94-100: global scale change
+    SE3 P = T, M = T;
+    for (int k = 0; k < 3; k++) { P.t[k] *= 1.00001; M.t[k] /= 1.00001; }
+    const Vec6 lp = (P * Ti).log(), lm = (M * Ti).log();
+    for (int k = 0; k < 6; k++) {
+      double v = (lp[k] - lm[k]) / (2e-3);
+      v *= (k < 3) ? (1.0 / SCALE_XI_TRANS) : (1.0 / SCALE_XI_ROT);
+      ns[6][CPARS + 8 * f + k] = v;
+    }
+  }
+  return ns;
+}
+
+// symmetric eigen-decomposition by cyclic Jacobi rotations (k x k, k <= 9): A = V diag(w) V^T
+static void jacobiEigen(std::vector<double>& A, int k, std::vector<double>& w, std::vector<double>& V) {
+  V.assign((size_t)k * k, 0.0);
+  for (int i = 0; i < k; i++) V[(size_t)i * k + i] = 1.0;
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0;
+    for (int p = 0; p < k; p++) for (int q = p + 1; q < k; q++) off += A[(size_t)p * k + q] * A[(size_t)p * k + q];
+    if (off < 1e-300) break;
+    for (int p = 0; p < k; p++)
+      for (int q = p + 1; q < k; q++) {
+        const double apq = A[(size_t)p * k + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[(size_t)q * k + q] - A[(size_t)p * k + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int r = 0; r < k; r++) {
+          const double arp = A[(size_t)r * k + p], arq = A[(size_t)r * k + q];
+          A[(size_t)r * k + p] = c * arp - sn * arq;
+          A[(size_t)r * k + q] = sn * arp + c * arq;
+        }
+        for (int r = 0; r < k; r++) {
+          const double apr = A[(size_t)p * k + r], aqr = A[(size_t)q * k + r];
+          A[(size_t)p * k + r] = c * apr - sn * aqr;
+          A[(size_t)q * k + r] = sn * apr + c * aqr;
+        }
+        for (int r = 0; r < k; r++) {
+          const double vrp = V[(size_t)r * k + p], vrq = V[(size_t)r * k + q];
+          V[(size_t)r * k + p] = c * vrp - sn * vrq;
+          V[(size_t)r * k + q] = sn * vrp + c * vrq;
+        }
+      }
+  }
+  w.resize(k);
+  for (int i = 0; i < k; i++) w[i] = A[(size_t)i * k + i];
+}
+
+void Window::orthogonalize(VecX& x) const {  // EnergyFunctional.cpp:L784-838 (b only)
+  std::vector<VecX> ns = getNullspaces();
+  const int k = (int)ns.size(), N = (int)x.size();
+  for (VecX& v : ns) {  // L806-807: normalised columns
+    double nrm = 0;
+    for (double e : v) nrm += e * e;
+    nrm = std::sqrt(nrm);
+    for (double& e : v) e /= nrm;
+  }
+  // the singular values of N are the square roots of the eigenvalues of N^T N; U = N V / sigma
+  std::vector<double> G((size_t)k * k), w, V;
+  for (int a = 0; a < k; a++)
+    for (int b = 0; b < k; b++) { double d = 0; for (int i = 0; i < N; i++) d += ns[a][i] * ns[b][i]; G[(size_t)a * k + b] = d; }
+  jacobiEigen(G, k, w, V);
+  double maxSv = 0;
+  for (int a = 0; a < k; a++) maxSv = std::max(maxSv, std::sqrt(std::max(0.0, w[a])));
+  VecX proj(N);
+  std::fill(proj.begin(), proj.end(), 0.0);
+  for (int a = 0; a < k; a++) {
+    const double sv = std::sqrt(std::max(0.0, w[a]));
+    if (!(sv > s.solverModeDelta * maxSv)) continue;  // L821-822
+    VecX u(N);
+    for (int i = 0; i < N; i++) { double d = 0; for (int b = 0; b < k; b++) d += ns[b][i] * V[(size_t)b * k + a]; u[i] = d / sv; }
+    double ux = 0;
+    for (int i = 0; i < N; i++) ux += u[i] * x[i];
+    for (int i = 0; i < N; i++) proj[i] += u[i] * ux;
+  }
+  for (int i = 0; i < N; i++) x[i] -= proj[i];  // L828: b -= N N^+ b
+}
+
 // EnergyFunctional.cpp:L841-996 — default solver mode (SOLVER_ORTHOGONALIZE_X_LATER only), no GTSAM (L971-973)
 void Window::solveSystem(int iteration, double lambda, int precision, ReducedSystem* sysOut, MatX* HFinalOut, VecX* bFinalOut) {
   ReducedSystem sys;
@@ -1039,7 +1135,7 @@ void Window::solveSystem(int iteration, double lambda, int precision, ReducedSys
   ldlt_solve(Hs, bs, xs);
   VecX x(N);
   for (int i = 0; i < N; i++) x[i] = SVecI[i] * xs[i];
-  (void)iteration;  // nullspace orthogonalisation (L980-984) is part of the host solve, outside the measured path
+  if (iteration >= 2 && s.orthogonalizeXLater) orthogonalize(x);  // L980-984 (SOLVER_ORTHOGONALIZE_X_LATER)
   lastX = x;
   resubstitute(x);
 }

@@ -187,6 +187,13 @@ struct Window {
 
   // EnergyFunctional.cpp:L201-265
   void accumulate(ReducedSystem& sys, int precision);
+  // Gauge nullspaces of the window at the frames' evaluation points: FrameHessian::setStateZero (HessianBlocks.cpp:L74-126: numeric
+  // derivatives of a global left perturbation / a global scale change, seen as left increments of each frame) assembled by
+  // FullSystem::getNullspaces (FullSystemOptimize.cpp:L704-760).  Returns 7 vectors of size 8 nf + 4: 6 pose + 1 scale.
+  std::vector<VecX> getNullspaces() const;
+  // EnergyFunctional::orthogonalize (EnergyFunctional.cpp:L784-838) for a vector: x -= N N^+ x with N = normalised [pose | scale]
+  // nullspaces and singular values below solverModeDelta * max dropped.
+  void orthogonalize(VecX& x) const;
   // EnergyFunctional.cpp:L841-996 (default solver mode, no GTSAM branch L971-973) — fills lastX, steps
   void solveSystem(int iteration, double lambda, int precision, ReducedSystem* sysOut = nullptr, MatX* HFinal = nullptr, VecX* bFinal = nullptr);
   void resubstitute(const VecX& x);  // EnergyFunctional.cpp:L267-321

@@ -31,6 +31,7 @@ static void setSetting(Settings& s, const char* name, double v) {
   else if (n == "thOptIterations") s.thOptIterations = (float)v;
   else if (n == "minOptIterations") s.minOptIterations = (int)v;
   else if (n == "initialCalibHessian") s.initialCalibHessian = (float)v;
+  else if (n == "orthogonalizeXLater") s.orthogonalizeXLater = v != 0;
 }
 
 extern "C" {
@@ -288,6 +289,18 @@ void orc_win_marginalize_frame(OrcWin* o, int idx, const double* HM_in, const do
   W.marginalizeFrame(idx);
   std::memcpy(HM_out, W.HM.d.data(), sizeof(double) * ndim * ndim);
   std::memcpy(bM_out, W.bM.data(), sizeof(double) * ndim);
+}
+// getNullspaces: out[7][N]; orthogonalize: x (N) in place
+void orc_win_get_nullspaces(OrcWin* o, double* out) {
+  std::vector<VecX> ns = o->W.getNullspaces();
+  const int N = 8 * o->W.nf() + CPARS;
+  for (int a = 0; a < 7; a++) std::memcpy(out + (size_t)a * N, ns[a].data(), sizeof(double) * N);
+}
+void orc_win_orthogonalize(OrcWin* o, double* x) {
+  const int N = 8 * o->W.nf() + CPARS;
+  VecX v(x, x + N);
+  o->W.orthogonalize(v);
+  std::memcpy(x, v.data(), sizeof(double) * N);
 }
 void orc_win_get_frame_states(OrcWin* o, double* state10) {
   for (int f = 0; f < o->W.nf(); f++) for (int k = 0; k < 10; k++) state10[10 * f + k] = o->W.frames[f].state[k];

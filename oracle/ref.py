@@ -59,6 +59,8 @@ def lib():
         L.ref_win_activate.argtypes = [vp, C.c_int, i32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, i32p, f32p, i32p]
         L.ref_win_marginalize.argtypes = [vp, C.c_int, i32p, C.c_int, f64p, f64p, f64p, f64p, f64p, f64p, C.POINTER(C.c_int), i32p, f32p, u8p]
         L.ref_win_marginalize_frame.argtypes = [vp, C.c_int, f64p, f64p, f64p, f64p]
+        L.ref_win_get_nullspaces.argtypes = [vp, f64p]
+        L.ref_win_orthogonalize.argtypes = [vp, f64p]
         L.ref_win_get_adjoints.argtypes = [vp, f64p, f64p]
         L.ref_win_get_adHTdeltaF.argtypes = [vp, f32p]
         L.ref_win_get_frame_tables.argtypes = [vp, f64p, f64p, f64p, f32p]

@@ -403,8 +403,50 @@ void ref_win_get_point_outputs(RefWin* W, float* Hdd, float* bd, float* Hcd4, fl
   }
 }
 
+// FullSystem::getNullspaces (FullSystemOptimize.cpp:L704-760; a FullSystem member, mirrored) from the reference's own
+// FrameHessian::nullspaces_pose / nullspaces_scale (computed by its setStateZero, HessianBlocks.cpp:L74-126)
+static void fill_nullspaces(RefWin* W) {
+  EnergyFunctional* ef = W->ef;
+  ef->lastNullspaces_pose.clear(); ef->lastNullspaces_scale.clear(); ef->lastNullspaces_affA.clear(); ef->lastNullspaces_affB.clear();
+  const int n = CPARS + (int)W->frames.size() * 8;
+  for (int i = 0; i < 6; i++) {
+    VecX nullspace_x0(n);
+    nullspace_x0.setZero();
+    for (FrameHessian* fh : W->frames) {
+      nullspace_x0.segment<6>(CPARS + fh->idx * 8) = fh->nullspaces_pose.col(i);
+      nullspace_x0.segment<3>(CPARS + fh->idx * 8) *= SCALE_XI_TRANS_INVERSE;
+      nullspace_x0.segment<3>(CPARS + fh->idx * 8 + 3) *= SCALE_XI_ROT_INVERSE;
+    }
+    ef->lastNullspaces_pose.push_back(nullspace_x0);
+  }
+  VecX nullspace_x0(n);
+  nullspace_x0.setZero();
+  for (FrameHessian* fh : W->frames) {
+    nullspace_x0.segment<6>(CPARS + fh->idx * 8) = fh->nullspaces_scale;
+    nullspace_x0.segment<3>(CPARS + fh->idx * 8) *= SCALE_XI_TRANS_INVERSE;
+    nullspace_x0.segment<3>(CPARS + fh->idx * 8 + 3) *= SCALE_XI_ROT_INVERSE;
+  }
+  ef->lastNullspaces_scale.push_back(nullspace_x0);
+}
+void ref_win_get_nullspaces(RefWin* W, double* out) {
+  fill_nullspaces(W);
+  const int N = CPARS + (int)W->frames.size() * 8;
+  for (int a = 0; a < 6; a++) for (int i = 0; i < N; i++) out[(size_t)a * N + i] = W->ef->lastNullspaces_pose[a][i];
+  for (int i = 0; i < N; i++) out[(size_t)6 * N + i] = W->ef->lastNullspaces_scale[0][i];
+}
+// the reference's EnergyFunctional::orthogonalize (EnergyFunctional.cpp:L784-838) on a vector
+void ref_win_orthogonalize(RefWin* W, double* x) {
+  fill_nullspaces(W);
+  const int N = CPARS + (int)W->frames.size() * 8;
+  VecX v(N);
+  for (int i = 0; i < N; i++) v[i] = x[i];
+  W->ef->orthogonalize(&v, 0);
+  for (int i = 0; i < N; i++) x[i] = v[i];
+}
+
 // EnergyFunctional::solveSystemF (EnergyFunctional.cpp:L841-996), no-GTSAM branch, including resubstituteF_MT
 void ref_win_solve(RefWin* W, int iteration, double lambda, int, double* x_out, double* HFinal, double* bFinal) {
+  fill_nullspaces(W);  // FullSystem::solveSystem (FullSystemOptimize.cpp:L655-661) refreshes them before every solve
   W->ef->solveSystemF(iteration, lambda, W->Hcalib);
   out_vec(W->ef->lastX, x_out);
   out_mat(W->ef->lastHS, HFinal);

@@ -48,3 +48,27 @@ def test_grow_then_marginalize_roundtrip(orc, synth):
     bbig = np.r_[bM, np.zeros(8)]
     H2, b2 = hostapi.marginalize_frame_hm(big, bbig, nf + 1, nf, np.full(8, 3.0), np.full(8, 0.5))
     assert rel(H2, HM) < 1e-12 and rel(b2, bM) < 1e-12
+
+
+@pytest.mark.parametrize("cfg", [dict(nf=7, npts=50, seed=1234), dict(nf=2, npts=20, seed=3), dict(nf=8, npts=30, seed=99, rot=0.2, trans=0.5)],
+                         ids=["nf7", "nf2", "nf8_big_motion"])
+def test_host_nullspaces_and_orthogonalize_match_oracle(orc, synth, cfg):
+    """host/nullspace.h (used by WindowBA::solveSystemF from iteration 2 on) vs the oracle, which tests/test_ref_pin.py pins to the reference's
+    setStateZero / orthogonalize: nullspace vectors, projection of a random x, and its defining properties."""
+    import dmvio_b200.hostapi as hostapi
+    W = synth.make_window(**cfg)
+    ow = orc.Window(W)
+    rng = np.random.default_rng(cfg["seed"])
+    x = rng.standard_normal(8 * W["nf"] + 4)
+    ns_g, x_g = hostapi.nullspaces_orthogonalize(W["R_eval"], W["t_eval"], x)
+    ns_o, x_o = ow.nullspaces(), ow.orthogonalize(x)
+    np.testing.assert_allclose(ns_g, ns_o, rtol=0, atol=1e-9 * np.abs(ns_o).max())
+    assert rel(x_g, x_o) < 1e-10
+    Nn = ns_g / np.linalg.norm(ns_g, axis=1, keepdims=True)
+    assert np.abs(Nn @ x_g).max() < 1e-9 * np.linalg.norm(x)
+    # first principles: the projector onto the complement of span(N), from numpy's pseudo-inverse
+    P = np.eye(len(x)) - Nn.T @ np.linalg.pinv(Nn.T)
+    assert rel(x_g, P @ x) < 1e-9
+    # the calibration and affine entries are untouched by pose / scale gauge directions
+    idx = np.r_[0:4, [4 + 8 * f + k for f in range(W["nf"]) for k in (6, 7)]]
+    np.testing.assert_allclose(x_g[idx], x[idx], rtol=0, atol=1e-12)
