@@ -16,7 +16,14 @@ _L = None
 def lib():
     global _L
     if _L is None:
-        L = capi.lib()
+        _L = _bind(capi.lib())
+    return _L
+
+
+def _bind(L):
+    """declares the signatures of the C glue on a loaded library (the product's libdmvio_b200.so; tests/test_host_on_oracle.py binds the
+    host-logic test build the same way)"""
+    if True:
         L.dmvh_window_create.restype = vp
         L.dmvh_window_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64p]
         L.dmvh_window_destroy.argtypes = [vp]
@@ -60,8 +67,7 @@ def lib():
         L.dmvh_ct_set_device_lm.argtypes = [vp, C.c_int]
         L.dmvh_ct_track.argtypes = [vp, f64p, f64p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, f64p, f64p, f64p, C.POINTER(C.c_int),
                                     C.POINTER(C.c_longlong)]
-        _L = L
-    return _L
+    return L
 
 
 def _c(a, t):

@@ -1,0 +1,322 @@
+// TEST INFRASTRUCTURE ONLY — never shipped, never linked into libdmvio_b200.so.
+//
+// A CPU stand-in for the part of the C ABI (include/dmvio_b200.h) that the C++ host adapter dm-vio_b200/host/window_ba.cpp calls,
+// implemented on top of the oracle (orc_ba).  oracle/Makefile links it with the UNMODIFIED host adapter sources into
+// oracle/libhost_on_oracle.so so that tests/test_host_on_oracle.py can run the adapter's own control flow — FullSystem::optimize's LM
+// loop, its tail (linearizeAll(true)), flagPointsForRemoval, marginalizePointsF, marginalizeFrame, solveSystemF with the gauge
+// projection — in the CPU test tier, where no GPU exists.  What it checks is the HOST LOGIC (call order, index bookkeeping, table
+// plumbing, priors, step handling); the device arithmetic is covered by the `-m gpu` parity tests.  The semantics mirrored here are the
+// documented ones of the header: tentative vs committed linearisation, fused resubstitute + point step in dmv_ba_gn_step, ping-pong
+// depth backup, residual slots that can be dropped, a marginalisation launch that leaves the committed linearisation alone.
+#include "../include/dmvio_b200.h"
+#include "orc_ba.h"
+#include "orc_coarse.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace orc;
+
+struct dmv_ba {
+  Window W;
+  dmv_ba_config cfg;
+  std::vector<std::vector<float>> slot_dI;  // per image slot: level-0 [I, dx, dy] AoS
+  std::vector<int> slots;                   // window frame -> slot
+  bool have_tentative = false, have_committed = false, have_adj = false;
+  ReducedSystem sys;                        // system of the committed linearisation
+};
+struct dmv_ct { int unused; };
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+extern "C" {
+
+const char* dmv_last_error(void) { return g_err.c_str(); }
+const char* dmv_version(void) { return "dmvio_b200 host-logic mock over the CPU oracle (test infrastructure)"; }
+int dmv_device_count(void) { return 0; }
+
+void dmv_ba_default_params(dmv_ba_params* p) { p->huberTH = 9.f; p->outlierTHSumComponent = 2500.f; p->affineOptModeA = 1e12f; p->affineOptModeB = 1e8f; }
+
+int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
+  if (!cfg || !out) return fail(DMV_ERR_INVALID, "null argument");
+  dmv_ba* b = new dmv_ba();
+  b->cfg = *cfg;
+  b->W.w = cfg->w; b->W.h = cfg->h;
+  b->slot_dI.resize(cfg->max_frames);
+  *out = b;
+  return DMV_OK;
+}
+int dmv_ba_destroy(dmv_ba* b) { delete b; return DMV_OK; }
+int dmv_ba_set_params(dmv_ba* b, const dmv_ba_params* p) {
+  b->W.s.huberTH = p->huberTH; b->W.s.outlierTHSumComponent = p->outlierTHSumComponent;
+  b->W.s.affineOptModeA = p->affineOptModeA; b->W.s.affineOptModeB = p->affineOptModeB;
+  return DMV_OK;
+}
+int dmv_ba_upload_frame(dmv_ba* b, int slot, const float* dI) {
+  if (slot < 0 || slot >= b->cfg.max_frames) return fail(DMV_ERR_INVALID, "slot out of range");
+  b->slot_dI[slot].assign(dI, dI + (size_t)b->cfg.w * b->cfg.h * 3);
+  return DMV_OK;
+}
+int dmv_ba_upload_image(dmv_ba* b, int slot, const float* image) {
+  if (slot < 0 || slot >= b->cfg.max_frames) return fail(DMV_ERR_INVALID, "slot out of range");
+  GlobalCalib g;
+  g.set(b->cfg.w, b->cfg.h, 1.f, 1.f, 0.f, 0.f, 1);
+  std::vector<float> lvl0((size_t)b->cfg.w * b->cfg.h * 3);
+  float* lv[1] = {lvl0.data()};
+  makeImages(g, image, lv, nullptr);
+  b->slot_dI[slot] = lvl0;
+  return DMV_OK;
+}
+int dmv_ba_set_window(dmv_ba* b, int nf, const int* slots) {
+  if (nf < 2 || nf > b->cfg.max_frames) return fail(DMV_ERR_INVALID, "bad window size");
+  b->W.frames.assign(nf, Frame());
+  b->slots.assign(slots, slots + nf);
+  for (int f = 0; f < nf; f++) b->W.frames[f].dI = b->slot_dI[slots[f]].data();
+  b->W.points.clear(); b->W.residuals.clear();
+  b->have_tentative = b->have_committed = b->have_adj = false;
+  return DMV_OK;
+}
+int dmv_ba_set_points(dmv_ba* b, int npts, const int32_t* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
+                      const float* color8, const float* weights8, const float* priorF) {
+  Window& W = b->W;
+  W.points.assign(npts, Point());
+  for (int i = 0; i < npts; i++) {
+    Point& p = W.points[i];
+    if (i > 0 && host[i] < host[i - 1]) return fail(DMV_ERR_INVALID, "points must be ordered by host frame");
+    p.host = host[i]; p.u = u[i]; p.v = v[i]; p.idepth = idepth[i]; p.idepth_zero = idepth_zero ? idepth_zero[i] : idepth[i];
+    p.idepth_backup = p.idepth;
+    std::memcpy(p.color, color8 + 8 * i, 32); std::memcpy(p.weights, weights8 + 8 * i, 32);
+    p.priorF = priorF ? priorF[i] : 0.f;
+    p.deltaF = p.idepth - p.idepth_zero;
+  }
+  W.residuals.clear();
+  b->have_tentative = b->have_committed = false;
+  return DMV_OK;
+}
+int dmv_ba_set_residuals(dmv_ba* b, int nres, const int32_t* point, const int32_t* target, const int32_t* st, const float* en) {
+  Window& W = b->W;
+  W.residuals.assign(nres, Residual());
+  for (Point& p : W.points) p.residuals.clear();
+  for (int i = 0; i < nres; i++) {
+    if (point[i] < 0 || point[i] >= (int)W.points.size() || target[i] < 0 || target[i] >= W.nf()) return fail(DMV_ERR_INVALID, "residual %d out of range", i);
+    Residual& r = W.residuals[i];
+    r.point = point[i]; r.host = W.points[point[i]].host; r.target = target[i];
+    if (r.target == r.host) return fail(DMV_ERR_INVALID, "residual %d targets its own host frame", i);
+    r.state_state = st ? st[i] : RS_IN;
+    r.state_energy = en ? en[i] : 0;
+    W.points[point[i]].residuals.push_back(i);
+  }
+  b->have_tentative = b->have_committed = false;
+  return DMV_OK;
+}
+int dmv_ba_set_adjoints(dmv_ba* b, const double* adHost, const double* adTarget) {
+  Window& W = b->W;
+  const int n = W.nf();
+  W.adHost.assign((size_t)n * n, Mat88()); W.adTarget.assign((size_t)n * n, Mat88());
+  W.adHostF.assign((size_t)n * n, Mat88f()); W.adTargetF.assign((size_t)n * n, Mat88f());
+  for (int i = 0; i < n * n; i++)
+    for (int r = 0; r < 8; r++)
+      for (int c = 0; c < 8; c++) {
+        W.adHost[i](r, c) = adHost[(size_t)i * 64 + r * 8 + c]; W.adTarget[i](r, c) = adTarget[(size_t)i * 64 + r * 8 + c];
+        W.adHostF[i](r, c) = (float)adHost[(size_t)i * 64 + r * 8 + c]; W.adTargetF[i](r, c) = (float)adTarget[(size_t)i * 64 + r * 8 + c];
+      }
+  W.adHTdeltaF.assign((size_t)n * n, Mat<float, 1, 8>());
+  b->have_adj = true;
+  return DMV_OK;
+}
+
+static void take_state(dmv_ba* b, const dmv_ba_state* st) {
+  Window& W = b->W;
+  const int n = W.nf();
+  for (int i = 0; i < 4; i++) { W.calib.value_scaledf[i] = st->calib[i]; W.calib.value_scaledi[i] = st->calib[4 + i]; }
+  W.precalc.assign((size_t)n * n, FramePrecalc());
+  for (int i = 0; i < n * n; i++) {
+    const float* q = st->precalc + (size_t)32 * i;
+    FramePrecalc& p = W.precalc[i];
+    for (int k = 0; k < 9; k++) p.PRE_KRKiTll.d[k] = q[k];
+    for (int k = 0; k < 3; k++) p.PRE_KtTll[k] = q[9 + k];
+    for (int k = 0; k < 9; k++) p.PRE_RTll_0.d[k] = q[12 + k];
+    for (int k = 0; k < 3; k++) p.PRE_tTll_0[k] = q[21 + k];
+    p.PRE_aff_mode[0] = q[24]; p.PRE_aff_mode[1] = q[25]; p.PRE_b0_mode = q[26];
+  }
+  for (int f = 0; f < n; f++) W.frames[f].frameEnergyTH = st->frameEnergyTH[f];
+  if (st->idepth) for (size_t i = 0; i < W.points.size(); i++) W.points[i].idepth = st->idepth[i];
+  if (st->idepth_zero) for (size_t i = 0; i < W.points.size(); i++) W.points[i].idepth_zero = st->idepth_zero[i];
+  for (Point& p : W.points) p.deltaF = p.idepth - p.idepth_zero;
+}
+
+int dmv_ba_gn_step(dmv_ba* b, const double* x, const dmv_ba_state* st, dmv_ba_lin_result* out, double sums[3]) {
+  if (!b || !st) return fail(DMV_ERR_INVALID, "null argument");
+  if (!b->have_adj) return fail(DMV_ERR_STATE, "dmv_ba_set_adjoints first");
+  if (x && !b->have_committed) return fail(DMV_ERR_STATE, "no committed linearisation to resubstitute");
+  Window& W = b->W;
+  double s3[3] = {0, 0, 0};
+  if (x) {  // EnergyFunctional::resubstituteF_MT + the point part of doStepFromBackup, on the committed linearisation
+    VecX xv(x, x + 8 * W.nf() + CPARS);
+    W.resubstitute(xv);
+    for (Point& p : W.points) {
+      s3[0] += (double)p.step * p.step; s3[1] += std::fabs(p.idepth_backup); s3[2] += 1;
+      p.idepth = p.idepth_backup + p.step;
+      p.idepth_zero = p.idepth;
+    }
+  }
+  take_state(b, st);
+  const double E = W.linearizeAll(false, nullptr, false);
+  if (out) {
+    out->energy = E; out->n_in = out->n_oob = out->n_outlier = 0;
+    for (const Residual& r : W.residuals) {
+      if (r.dropped) continue;
+      out->n_in += r.state_NewState == RS_IN; out->n_oob += r.state_NewState == RS_OOB; out->n_outlier += r.state_NewState == RS_OUTLIER;
+    }
+  }
+  if (sums) { sums[0] = s3[0]; sums[1] = s3[1]; sums[2] = s3[2]; }
+  b->have_tentative = true;
+  return DMV_OK;
+}
+int dmv_ba_apply_res(dmv_ba* b) {
+  if (!b->have_tentative) return fail(DMV_ERR_STATE, "no tentative linearisation to commit");
+  b->W.applyResAll();
+  b->W.accumulate(b->sys, 1);  // the device accumulates while it linearises: the committed system belongs to the committed state
+  b->have_committed = true; b->have_tentative = false;
+  return DMV_OK;
+}
+int dmv_ba_accumulate(dmv_ba* b, double* HA, double* bA, double* Hsc, double* bsc, int* resInA) {
+  if (!b->have_committed) return fail(DMV_ERR_STATE, "no committed linearisation (linearize + apply_res first)");
+  const int N = b->sys.N;
+  if (HA) std::memcpy(HA, b->sys.HA.d.data(), sizeof(double) * N * N);
+  if (bA) std::memcpy(bA, b->sys.bA.data(), sizeof(double) * N);
+  if (Hsc) std::memcpy(Hsc, b->sys.Hsc.d.data(), sizeof(double) * N * N);
+  if (bsc) std::memcpy(bsc, b->sys.bsc.data(), sizeof(double) * N);
+  if (resInA) *resInA = b->sys.resInA;
+  return DMV_OK;
+}
+int dmv_ba_get_residual_outputs(dmv_ba* b, int32_t* ns, float* ne, float* nw, float* cpt3, float* jp8) {
+  if (!b->have_tentative && !b->have_committed) return fail(DMV_ERR_STATE, "linearize first");
+  int i = 0;
+  for (const Residual& r : b->W.residuals) {
+    if (r.dropped) continue;
+    // after the commit the residual's state IS the committed new state (applyRes); an OOB residual reports OOB / its old energy
+    const bool tent = b->have_tentative;
+    if (ns) ns[i] = tent ? r.state_NewState : r.state_state;
+    if (ne) ne[i] = (float)(tent ? r.state_NewEnergy : r.state_energy);
+    if (nw) nw[i] = (float)r.state_NewEnergyWithOutlier;
+    if (cpt3) for (int k = 0; k < 3; k++) cpt3[3 * i + k] = r.centerProjectedTo[k];
+    if (jp8) for (int k = 0; k < 8; k++) jp8[8 * i + k] = r.JpJdF[k];
+    i++;
+  }
+  return DMV_OK;
+}
+int dmv_ba_get_target_energies(dmv_ba* b, int target, float* out, int cap, int* n) {
+  if (!b->have_tentative && !b->have_committed) return fail(DMV_ERR_STATE, "linearize first");
+  int c = 0;
+  // point order, like the device (slot arrays [target][point])
+  for (const Point& p : b->W.points)
+    for (int ri : p.residuals) {
+      const Residual& r = b->W.residuals[ri];
+      if (r.target == target && !r.dropped && r.state_NewEnergyWithOutlier >= 0 && c < cap) out[c++] = (float)r.state_NewEnergyWithOutlier;
+    }
+  *n = c;
+  return DMV_OK;
+}
+int dmv_ba_get_point_outputs(dmv_ba* b, float* Hdd, float* bd, float* Hcd4, float* HdiF, float* bdSum) {
+  if (!b->have_tentative && !b->have_committed) return fail(DMV_ERR_STATE, "linearize first");
+  for (size_t i = 0; i < b->W.points.size(); i++) {
+    const Point& p = b->W.points[i];
+    if (Hdd) Hdd[i] = p.Hdd_accAF;
+    if (bd) bd[i] = p.bd_accAF;
+    if (Hcd4) for (int k = 0; k < 4; k++) Hcd4[4 * i + k] = p.Hcd_accAF[k];
+    if (HdiF) HdiF[i] = p.HdiF;
+    if (bdSum) bdSum[i] = p.bdSumF;
+  }
+  return DMV_OK;
+}
+int dmv_ba_backup_points(dmv_ba* b) { for (Point& p : b->W.points) p.idepth_backup = p.idepth; return DMV_OK; }
+int dmv_ba_restore_points(dmv_ba* b) {
+  for (Point& p : b->W.points) { p.idepth = p.idepth_backup; p.idepth_zero = p.idepth_backup; p.deltaF = 0; }
+  return DMV_OK;
+}
+int dmv_ba_get_idepth(dmv_ba* b, float* idepth, float* idepth_zero) {
+  for (size_t i = 0; i < b->W.points.size(); i++) {
+    if (idepth) idepth[i] = b->W.points[i].idepth;
+    if (idepth_zero) idepth_zero[i] = b->W.points[i].idepth_zero;
+  }
+  return DMV_OK;
+}
+int dmv_ba_last_timing(dmv_ba*, float ms[4]) { ms[0] = ms[1] = ms[2] = ms[3] = 0; return DMV_OK; }
+
+int dmv_ba_reset_oob(dmv_ba* b) {
+  for (Residual& r : b->W.residuals)
+    if (!r.dropped) { r.state_state = RS_IN; r.state_NewState = RS_OUTLIER; r.state_energy = r.state_NewEnergy = 0; }
+  b->have_tentative = b->have_committed = false;
+  return DMV_OK;
+}
+int dmv_ba_drop_residuals(dmv_ba* b, int n, const int32_t* idx) {
+  // indices refer to the CURRENT (compacted) residual order: map them onto the oracle's stable storage
+  std::vector<int> live;
+  for (int i = 0; i < (int)b->W.residuals.size(); i++) if (!b->W.residuals[i].dropped) live.push_back(i);
+  for (int k = 0; k < n; k++) {
+    if (idx[k] < 0 || idx[k] >= (int)live.size()) return fail(DMV_ERR_INVALID, "res_idx[%d] out of range", k);
+    Residual& r = b->W.residuals[live[idx[k]]];
+    r.dropped = true; r.isActiveAndIsGoodNEW = false;
+    std::vector<int>& list = b->W.points[r.point].residuals;
+    for (size_t j = 0; j < list.size(); j++) if (list[j] == live[idx[k]]) { list.erase(list.begin() + j); break; }
+  }
+  return DMV_OK;
+}
+int dmv_ba_marginalize_points(dmv_ba* b, const dmv_ba_marg_args* a) {
+  if (!b || !a || (a->n > 0 && !a->point) || !a->adHTdeltaF) return fail(DMV_ERR_INVALID, "null argument");
+  // works on a COPY of the window: the launch must leave the committed linearisation alone
+  Window W = b->W;
+  const int n = W.nf(), N = 8 * n + CPARS;
+  for (int i = 0; i < n * n; i++) for (int c = 0; c < 8; c++) W.adHTdeltaF[i](0, c) = a->adHTdeltaF[(size_t)i * 8 + c];
+  for (int i = 0; i < 4; i++) W.cDeltaF[i] = a->cDeltaF[i];
+  W.s.idepthFixPriorMargFac = a->idepthFixPriorMargFac;
+  W.HM = MatX(N, N); W.bM.assign(N, 0.0);
+  std::vector<int> pts(a->point, a->point + a->n);
+  for (int p : pts) if (p < 0 || p >= (int)W.points.size()) return fail(DMV_ERR_INVALID, "point out of range");
+  std::vector<int> good = W.fixLinearization(pts);
+  ReducedSystem sys;
+  W.marginalizePoints(pts, 1, sys);
+  if (a->M) std::memcpy(a->M, sys.HA.d.data(), sizeof(double) * N * N);
+  if (a->Mb) std::memcpy(a->Mb, sys.bA.data(), sizeof(double) * N);
+  if (a->Msc) std::memcpy(a->Msc, sys.Hsc.d.data(), sizeof(double) * N * N);
+  if (a->Mbsc) std::memcpy(a->Mbsc, sys.bsc.data(), sizeof(double) * N);
+  if (a->resInM) *a->resInM = sys.resInA;
+  if (a->ngoodRes) for (int i = 0; i < a->n; i++) a->ngoodRes[i] = good[i];
+  int k = 0;
+  for (const Residual& r : W.residuals) {
+    if (r.dropped) continue;
+    if (a->isLinearized) a->isLinearized[k] = r.isLinearized ? 1 : 0;
+    if (a->res_toZeroF) for (int c = 0; c < 8; c++) a->res_toZeroF[(size_t)8 * k + c] = r.isLinearized ? r.res_toZeroF[c] : 0.f;
+    k++;
+  }
+  b->have_tentative = false;
+  return DMV_OK;
+}
+
+// ---- the coarse tracker adapter is linked into the same library but not exercised by the host-logic tests
+int dmv_ct_create(const dmv_ct_config*, dmv_ct**) { return fail(DMV_ERR_NO_DEVICE, "mock: no coarse tracker"); }
+int dmv_ct_destroy(dmv_ct*) { return DMV_OK; }
+int dmv_ct_set_K(dmv_ct*, int, float, float, float, float) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
+int dmv_ct_set_ref(dmv_ct*, int, int, const float*, const float*, const float*, const float*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
+int dmv_ct_make_coarse_depth(dmv_ct*, int, const float*, const float*, const float*, const float*, int32_t*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
+int dmv_ct_get_ref(dmv_ct*, int, int*, float*, float*, float*, float*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
+int dmv_ct_upload_new(dmv_ct*, int, const float*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
+int dmv_ct_upload_new_image(dmv_ct*, const float*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
+int dmv_ct_set_huber(dmv_ct*, float) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
+int dmv_ct_calc_res_gs(dmv_ct*, int, const float*, const float*, const float*, float, float, int, double*, double*, double*, int*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
+int dmv_ct_track(dmv_ct*, const dmv_ct_track_args*, dmv_ct_track_result*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
+
+}  // extern "C"

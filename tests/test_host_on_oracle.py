@@ -1,0 +1,170 @@
+"""Host logic of the C++ adapter (dm-vio_b200/host/window_ba.cpp) in the CPU test tier.
+
+oracle/libhost_on_oracle.so = the adapter's UNMODIFIED sources linked against oracle/mock_capi.cpp, a CPU stand-in of the C ABI built on the
+oracle (test infrastructure, never shipped).  The adapter therefore runs its own control flow here — FullSystem::optimize's LM loop with
+solveSystemF (priors, marginalisation prior, Jacobi-preconditioned LDLT, gauge projection from iteration 2 on), backup / step / restore,
+the tail (setEvalPT, linearizeAll(true) bookkeeping, residual deletion), flagPointsForRemoval, marginalizePointsF, marginalizeFrame — and is
+compared with the oracle's own optimize / finishOptimize / marginalize, which tests/test_ref_pin.py pins to the reference.  Both sides use the
+same residual arithmetic (the oracle's), so the tolerances are tight: what differs is only the adapter's host-side fp64 code and its float
+tables.  The same scenarios run against the CUDA kernels in tests/test_gpu_host.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import rel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "oracle", "libhost_on_oracle.so")
+
+
+@pytest.fixture(scope="module")
+def hostapi(orc):
+    import dmvio_b200.hostapi as h
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "libhost_on_oracle.so"])
+    mock = h._bind(C.CDLL(LIB))
+    saved = h._L
+    h._L = mock            # WindowBA() picks the library up through hostapi.lib()
+    yield h
+    h._L = saved
+
+
+def test_tables_and_first_linearisation(hostapi, orc, synth):
+    W = synth.make_window(nf=5, npts=300, seed=3)
+    ow = orc.Window(W)
+    hw = hostapi.WindowBA(W)
+    pc, adH, adT = hw.tables()
+    np.testing.assert_allclose(pc, ow.precalc(), rtol=2e-6, atol=1e-4)
+    a_o, t_o = ow.adjoints()
+    np.testing.assert_allclose(adH, a_o, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(adT, t_o, rtol=1e-12, atol=1e-12)
+    e_g, e_o = hw.linearize(), ow.linearize_all(update_th=False)
+    assert abs(e_g - e_o) <= 1e-5 * abs(e_o)
+    hw.close()
+
+
+@pytest.mark.parametrize("cfg", [dict(nf=4, npts=600, seed=13), dict(nf=7, npts=800, seed=1234)], ids=["nf4", "nf7"])
+def test_optimize_loop_matches_oracle(hostapi, orc, synth, cfg):
+    """the LM loop incl. the gauge projection of x from iteration 2 on: same accept / reject sequence, energies and final states"""
+    W = synth.make_window(state_noise=2e-3, **cfg)
+    ow = orc.Window(W)
+    n_o, log_o = ow.optimize(6, precision=1)
+    hw = hostapi.WindowBA(W)
+    n_g, log_g = hw.optimize(6)
+    assert n_g == n_o and n_o >= 3                                   # at least one iteration with the projection active
+    np.testing.assert_allclose(log_g, log_o, rtol=1e-5)
+    st_g, id_g, th_g = hw.states()
+    assert np.abs(st_g - ow.frame_states()).max() < 2e-6
+    np.testing.assert_allclose(id_g, ow.point_outputs()["idepth"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(th_g, ow.frame_tables()["frameEnergyTH"], rtol=1e-4)
+    # without the projection the oracle ends somewhere measurably different: the call site in WindowBA::solveSystemF matters
+    ob = orc.Window(W, settings=dict(orthogonalizeXLater=0))
+    ob.optimize(6, precision=1)
+    assert np.abs(ob.frame_states() - ow.frame_states()).max() > 10 * np.abs(st_g - ow.frame_states()).max()
+    hw.close()
+
+
+def test_finish_optimize_and_second_optimize(hostapi, orc, synth):
+    W = synth.make_window(nf=5, npts=600, seed=21, state_noise=2e-3)
+    nres = len(W["res_point"])
+    ow = orc.Window(W)
+    ow.optimize(4, precision=1)
+    E_o, rem_o = ow.finish_optimize()
+    hw = hostapi.WindowBA(W)
+    hw.optimize(4)
+    E_g, rem_g = hw.finish_optimize()
+    assert abs(E_g - E_o) <= 1e-5 * abs(E_o)
+    np.testing.assert_array_equal(rem_g, rem_o)
+    assert hw.nres == nres - len(rem_g)
+    ps_o, ps_g = ow.point_stats(), hw.point_stats()
+    np.testing.assert_array_equal(ps_g["numGoodResiduals"], ps_o["numGoodResiduals"])
+    np.testing.assert_allclose(ps_g["maxRelBaseline"], ps_o["maxRelBaseline"], rtol=1e-4, atol=1e-7)
+    st_g, _, th_g = hw.states()
+    assert np.all(st_g[-1, :6] == 0)
+    assert np.abs(st_g - ow.frame_states()).max() < 2e-6
+    n_o, log_o = ow.optimize(3, precision=1)
+    n_g, log_g = hw.optimize(3)                                       # resetOOB on the thinned window; deleted residuals stay out
+    assert n_g == n_o
+    np.testing.assert_allclose(log_g, log_o, rtol=1e-5)
+    hw.close()
+
+
+def test_point_marginalisation_matches_oracle(hostapi, orc, synth):
+    W = synth.make_window(nf=5, npts=800, seed=17, state_noise=2e-3)
+    ow = orc.Window(W)
+    ow.optimize(4, precision=1)
+    hw = hostapi.WindowBA(W)
+    hw.optimize(4)
+    po = ow.point_outputs()
+    idepth_hessian = np.where(po["HdiF"] > 0, 1.0 / np.maximum(po["HdiF"], 1e-30), 0.0)
+    rng = np.random.default_rng(0)
+    well = np.nonzero(idepth_hessian > 200)[0]
+    marg = np.sort(rng.choice(well, len(well) // 3, replace=False)).astype(np.int32)
+    weak = np.nonzero((idepth_hessian > 0) & (idepth_hessian < 40))[0][:5].astype(np.int32)     # below setting_minIdepthH_marg: dropped, not marginalised
+    rest = np.setdiff1d(np.arange(len(W["host"])), np.concatenate([marg, weak]))
+    drop = np.sort(rng.choice(rest, 20, replace=False)).astype(np.int32)
+    o = ow.marginalize(marg, precision=1)
+    g = hw.marginalize_points(np.concatenate([marg, weak]), drop)
+    assert g["npts"] == len(W["host"]) - len(marg) - len(weak) - len(drop)
+    assert g["nres"] == int((~np.isin(W["res_point"], np.concatenate([marg, weak, drop]))).sum())
+    assert g["resInM"] == o["resInM"]
+    assert rel(g["HM"], o["HM"]) < 1e-5 and rel(g["bM"], o["bM"]) < 1e-4
+    e = hw.linearize()
+    assert np.isfinite(e) and e > 0
+    hw.close()
+
+
+def test_keyframe_turnover_flow(hostapi, orc, synth):
+    nf = 6
+    W = synth.make_window(nf=nf, npts=500, seed=31, state_noise=1e-3, hosts="all")
+    prior0 = orc.Window(W).frame_tables()["prior"][0]
+    hw = hostapi.WindowBA(W)
+    hw.optimize(3)
+    E, rem = hw.finish_optimize()
+    res_point = np.asarray(W["res_point"])[np.setdiff1d(np.arange(len(W["res_point"])), rem)]
+    res_target = np.asarray(W["res_target"])[np.setdiff1d(np.arange(len(W["res_target"])), rem)]
+    for _ in range(3):
+        assert len(hw.finish_optimize()[1]) == 0                       # nothing left to delete; numGoodResiduals keeps counting
+    npts = len(W["host"])
+    rng = np.random.default_rng(4)
+    last_t = np.tile(np.asarray(W["frameID"])[[-1, -2]], (npts, 1)).astype(np.int32)
+    last_s = rng.choice([0, 1, 2], (npts, 2), p=[0.8, 0.1, 0.1]).astype(np.int32)
+    hw.set_last_residuals(last_t, last_s)
+    marg, drop = hw.flag_points([0])
+    # ---- flagPointsForRemoval against a numpy restatement of PointHessian::isOOB / isInlierNew (HessianBlocks.h:L476-506)
+    _, idepth, _ = hw.states()
+    ps = hw.point_stats()
+    nres_p = np.bincount(res_point, minlength=npts)
+    vis = np.bincount(res_point[res_target == 0], minlength=npts)
+    exp_m, exp_d = [], []
+    for i in range(npts):
+        if idepth[i] < 0.02 or nres_p[i] == 0:
+            exp_d.append(i); continue
+        oob = (nres_p[i] >= 3 and ps["numGoodResiduals"][i] > 14 and nres_p[i] - vis[i] < 3)
+        if not oob:
+            oob = last_s[i, 0] == 1 or (nres_p[i] >= 2 and last_s[i, 0] == 2 and last_s[i, 1] == 2)
+        if not oob and W["host"][i] != 0:
+            continue
+        (exp_m if (nres_p[i] >= 3 and ps["numGoodResiduals"][i] >= 4) else exp_d).append(i)
+    np.testing.assert_array_equal(marg, np.asarray(exp_m, np.int32))
+    np.testing.assert_array_equal(drop, np.asarray(exp_d, np.int32))
+    assert len(marg) > 20 and len(drop) > 0
+    # ---- marginalise the points, then the frame
+    g = hw.marginalize_points(marg, drop)
+    assert g["resInM"] > 0
+    st, _, _ = hw.states()
+    exp_H, exp_b = hostapi.marginalize_frame_hm(g["HM"], g["bM"], nf, 0, prior0, st[0][:8])
+    nres_before = hw.nres
+    m = hw.marginalize_frame(0)
+    assert m["nf"] == nf - 1 and rel(m["HM"], exp_H) < 1e-12 and rel(m["bM"], exp_b) < 1e-12
+    assert m["nres"] == nres_before - int(np.isin(res_point, np.setdiff1d(np.arange(npts), np.concatenate([marg, drop])))[res_target == 0].sum())
+    e = hw.linearize()
+    eL, eM = hw.energies_LM()
+    assert np.isfinite(e) and e > 0 and eM != 0
+    n, log = hw.optimize(3)
+    eL1, eM1 = hw.energies_LM()
+    assert n >= 1 and np.all(np.isfinite(log))
+    assert log[-1] + eL1 + eM1 <= (log[0] + eL + eM) * (1 + 1e-9)
+    hw.close()
