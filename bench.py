@@ -200,7 +200,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{steps} full GN iterations of the window; oracle = CPU restatement of the reference's SSE path, g++ -O3 (no -march, as the "
                                    f"reference's CMakeLists), {threads} worker threads = best of {{{', '.join(f'{t}: {r / 1e6:.2f} M/s' for t, r in rates.items())}}} "
-                                   f"on this {os.cpu_count()}-thread host (the reference itself hard-codes NUM_THREADS=6 and cannot be compiled here: Eigen/Boost/GTSAM absent)"},
+                                   f"on this {os.cpu_count()}-thread host (the reference hard-codes NUM_THREADS=6; its own sources do compile here against stand-in headers, oracle/_ref, but run 2-5x slower than this port because of the stand-in matrix class, so timing them would flatter the GPU: DESIGN.md section 2)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
