@@ -428,3 +428,97 @@ def ip_activate(W, RT, aff, calib6, host, P, minObs=1):
                           c(host, np.int32), P["u"], P["v"], P["color"], P["weights"], P["energyTH"], c(P["idepth_min"], np.float32),
                           c(P["idepth_max"], np.float32), int(minObs), status, idepth, rs.reshape(-1))
     return status, idepth, rs
+
+
+class CoarseInit:
+    """CoarseInitializer (FullSystem/CoarseInitializer.cpp) restated (orc_init.h), or — through oracle/ref.py — the reference's compiled one.
+    Points (all levels), parents and neighbour lists are inputs: the pixel selector and the kd-tree are not part of the restated path."""
+
+    _PREFIX = "orc_ci_"
+
+    def __init__(self, w, h, K, _lib=None):
+        self.L = _lib if _lib is not None else lib()
+        self._bind(self.L)
+        self.w, self.h = w, h
+        self.hd = self._f("create")(w, h, np.ascontiguousarray(K, np.float64))
+        self.levels = self._f("levels")(self.hd)
+        self.n = None
+
+    def _f(self, name):
+        return getattr(self.L, self._PREFIX + name)
+
+    @classmethod
+    def _bind(cls, L):
+        vp = C.c_void_p
+        f = lambda n: getattr(L, cls._PREFIX + n)
+        f("create").restype = vp
+        f("create").argtypes = [C.c_int, C.c_int, f64p]
+        f("destroy").argtypes = [vp]
+        f("levels").argtypes = [vp]
+        f("set_first").argtypes = [vp, f32p, C.c_float, i32p, f32p, f32p, f32p, i32p, i32p]
+        f("set_new").argtypes = [vp, f32p, C.c_float]
+        f("calc").argtypes = [vp, C.c_int, f64p, f64p, C.c_double, C.c_double, f32p, f32p, f32p, f32p, f32p]
+        for n in ("apply_step", "opt_reg", "propagate_up", "propagate_down", "reset_points", "set_snapped", "npts"):
+            f(n).argtypes = [vp, C.c_int]
+        f("do_step").argtypes = [vp, C.c_int, C.c_float, f32p]
+        f("calc_ec").argtypes = [vp, C.c_int, f32p]
+        f("get_points").argtypes = [vp, C.c_int, f32p]
+        f("set_points").argtypes = [vp, C.c_int, f32p]
+        f("track").argtypes = [vp, f32p, C.c_float, f64p, f64p, f64p, i32p]
+
+    def __del__(self):
+        try:
+            self._f("destroy")(self.hd)
+        except Exception:
+            pass
+
+    @staticmethod
+    def _concat(pyr):
+        return np.ascontiguousarray(np.concatenate([np.asarray(p, np.float32).reshape(-1) for p in pyr]))
+
+    def set_first(self, pyr, exposure, pts):
+        """pts: list per level of dict(u, v, type, parent, neighbours (n, 10))"""
+        self.n = np.array([len(p["u"]) for p in pts], np.int32)
+        cat = lambda k, t: np.ascontiguousarray(np.concatenate([np.asarray(p[k], t).reshape(-1) for p in pts]))
+        self._keep = (self._concat(pyr[:self.levels]),)
+        self._f("set_first")(self.hd, self._keep[0], float(exposure), self.n, cat("u", np.float32), cat("v", np.float32), cat("type", np.float32),
+                             cat("parent", np.int32), cat("neighbours", np.int32))
+
+    def set_new(self, pyr, exposure):
+        self._f("set_new")(self.hd, self._concat(pyr[:self.levels]), float(exposure))
+
+    def calc(self, lvl, R, t, a, b):
+        H, bb, Hsc, bsc, res = np.zeros(64, np.float32), np.zeros(8, np.float32), np.zeros(64, np.float32), np.zeros(8, np.float32), np.zeros(3, np.float32)
+        self._f("calc")(self.hd, lvl, np.ascontiguousarray(R, np.float64).reshape(-1), np.ascontiguousarray(t, np.float64), float(a), float(b), H, bb, Hsc, bsc, res)
+        return dict(H=H.reshape(8, 8), b=bb, Hsc=Hsc.reshape(8, 8), bsc=bsc, res=res)
+
+    def points(self, lvl):
+        n = self._f("npts")(self.hd, lvl)
+        o = np.zeros((n, 12), np.float32)
+        self._f("get_points")(self.hd, lvl, o.reshape(-1))
+        keys = ("idepth", "idepth_new", "iR", "energy0", "energy1", "energy_new0", "energy_new1", "lastHessian", "lastHessian_new", "maxstep", "isGood", "isGood_new")
+        return {k: o[:, i].copy() for i, k in enumerate(keys)}
+
+    def set_points(self, lvl, idepth, idepth_new, iR, lastHessian, isGood):
+        a = np.ascontiguousarray(np.stack([idepth, idepth_new, iR, lastHessian, np.asarray(isGood, np.float32)], axis=1), np.float32)
+        self._f("set_points")(self.hd, lvl, a.reshape(-1))
+
+    def apply_step(self, lvl): self._f("apply_step")(self.hd, lvl)
+    def opt_reg(self, lvl): self._f("opt_reg")(self.hd, lvl)
+    def propagate_up(self, lvl): self._f("propagate_up")(self.hd, lvl)
+    def propagate_down(self, lvl): self._f("propagate_down")(self.hd, lvl)
+    def reset_points(self, lvl): self._f("reset_points")(self.hd, lvl)
+    def set_snapped(self, s): self._f("set_snapped")(self.hd, int(s))
+
+    def do_step(self, lvl, lam, inc):
+        self._f("do_step")(self.hd, lvl, float(lam), np.ascontiguousarray(inc, np.float32))
+
+    def calc_ec(self, lvl):
+        o = np.zeros(3, np.float32)
+        self._f("calc_ec")(self.hd, lvl, o)
+        return o
+
+    def track(self, pyr, exposure):
+        R, t, ab, st = np.zeros(9), np.zeros(3), np.zeros(2), np.zeros(3, np.int32)
+        ok = self._f("track")(self.hd, self._concat(pyr[:self.levels]), float(exposure), R, t, ab, st)
+        return dict(ok=bool(ok), R=R.reshape(3, 3), t=t, a=ab[0], b=ab[1], snapped=bool(st[0]), snappedAt=int(st[1]), frameID=int(st[2]))

@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY — C API glue of the CPU oracle.
 #include "orc_capi.h"
+#include "orc_init.h"
 #include "orc_ba.h"
 #include "orc_coarse.h"
 #include "orc_threads.h"
@@ -493,3 +494,95 @@ void orc_se3_inv(const double Ra[9], const double ta[3], double R[9], double t[3
 }
 
 }  // extern "C"
+
+/* ---- coarse initialiser (orc_init.h) ---- */
+extern "C" {
+struct OrcCI {
+  orc::CoarseInit ci;
+  std::vector<std::vector<float>> first, cur;  // pyramids [lvl][w*h*3]
+};
+static void ci_load(OrcCI* o, std::vector<std::vector<float>>& dst, const float* concat) {
+  dst.resize(o->ci.levels);
+  size_t off = 0;
+  for (int l = 0; l < o->ci.levels; l++) {
+    const size_t n = (size_t)o->ci.w[l] * o->ci.h[l] * 3;
+    dst[l].assign(concat + off, concat + off + n);
+    off += n;
+  }
+}
+OrcCI* orc_ci_create(int w, int h, const double K[4]) {
+  OrcCI* o = new OrcCI();
+  o->ci.makeK(w, h, K[0], K[1], K[2], K[3]);
+  return o;
+}
+void orc_ci_destroy(OrcCI* o) { delete o; }
+int orc_ci_levels(OrcCI* o) { return o->ci.levels; }
+// points of all levels concatenated: n[lvl]; u, v, type (floats); parent (index in lvl+1 or -1); neighbours 10 per point
+void orc_ci_set_first(OrcCI* o, const float* dIp_concat, float exposure, const int32_t* n, const float* u, const float* v, const float* type,
+                      const int32_t* parent, const int32_t* neighbours10) {
+  ci_load(o, o->first, dIp_concat);
+  size_t off = 0;
+  for (int l = 0; l < o->ci.levels; l++) {
+    o->ci.points[l].assign(n[l], orc::InitPnt());
+    for (int i = 0; i < n[l]; i++, off++) {
+      orc::InitPnt& p = o->ci.points[l][i];
+      p.u = u[off]; p.v = v[off]; p.my_type = type[off]; p.parent = parent[off];
+      for (int k = 0; k < 10; k++) p.neighbours[k] = neighbours10[10 * off + k];
+    }
+  }
+  const float* lv[orc::PYR_LEVELS];
+  for (int l = 0; l < o->ci.levels; l++) lv[l] = o->first[l].data();
+  o->ci.setFirst(lv, exposure);
+}
+void orc_ci_set_new(OrcCI* o, const float* dIp_concat, float exposure) {
+  ci_load(o, o->cur, dIp_concat);
+  for (int l = 0; l < o->ci.levels; l++) o->ci.dINew[l] = o->cur[l].data();
+  o->ci.new_exposure = exposure;
+}
+void orc_ci_calc(OrcCI* o, int lvl, const double R[9], const double t[3], double a, double b, float* H64, float* b8, float* Hsc64, float* bsc8, float* res3) {
+  orc::InitSystem S;
+  orc::AffLight aff; aff.a = a; aff.b = b;
+  o->ci.calcResAndGS(lvl, S, orc::SE3::fromRt(R, t), aff, res3);
+  std::memcpy(H64, S.H, sizeof(S.H)); std::memcpy(b8, S.b, sizeof(S.b)); std::memcpy(Hsc64, S.Hsc, sizeof(S.Hsc)); std::memcpy(bsc8, S.bsc, sizeof(S.bsc));
+}
+void orc_ci_apply_step(OrcCI* o, int lvl) { o->ci.applyStep(lvl); }
+void orc_ci_do_step(OrcCI* o, int lvl, float lambda, const float* inc8) { o->ci.doStep(lvl, lambda, inc8); }
+void orc_ci_calc_ec(OrcCI* o, int lvl, float* out3) { o->ci.calcEC(lvl, out3); }
+void orc_ci_opt_reg(OrcCI* o, int lvl) { o->ci.optReg(lvl); }
+void orc_ci_propagate_up(OrcCI* o, int lvl) { o->ci.propagateUp(lvl); }
+void orc_ci_propagate_down(OrcCI* o, int lvl) { o->ci.propagateDown(lvl); }
+void orc_ci_reset_points(OrcCI* o, int lvl) { o->ci.resetPoints(lvl); }
+void orc_ci_set_snapped(OrcCI* o, int snapped) { o->ci.snapped = snapped != 0; }
+int orc_ci_npts(OrcCI* o, int lvl) { return (int)o->ci.points[lvl].size(); }
+// per-point state, 12 floats: idepth idepth_new iR energy0 energy1 energy_new0 energy_new1 lastHessian lastHessian_new maxstep isGood isGood_new
+void orc_ci_get_points(OrcCI* o, int lvl, float* out12) {
+  for (size_t i = 0; i < o->ci.points[lvl].size(); i++) {
+    const orc::InitPnt& p = o->ci.points[lvl][i];
+    float* q = out12 + 12 * i;
+    q[0] = p.idepth; q[1] = p.idepth_new; q[2] = p.iR; q[3] = p.energy[0]; q[4] = p.energy[1]; q[5] = p.energy_new[0]; q[6] = p.energy_new[1];
+    q[7] = p.lastHessian; q[8] = p.lastHessian_new; q[9] = p.maxstep; q[10] = p.isGood ? 1.f : 0.f; q[11] = p.isGood_new ? 1.f : 0.f;
+  }
+}
+// sets idepth, idepth_new, iR, lastHessian, isGood (5 floats per point) — lets the tests start from arbitrary states
+void orc_ci_set_points(OrcCI* o, int lvl, const float* in5) {
+  for (size_t i = 0; i < o->ci.points[lvl].size(); i++) {
+    orc::InitPnt& p = o->ci.points[lvl][i];
+    const float* q = in5 + 5 * i;
+    p.idepth = q[0]; p.idepth_new = q[1]; p.iR = q[2]; p.lastHessian = q[3]; p.isGood = q[4] != 0.f;
+  }
+}
+// CoarseInitializer::trackFrame; out: R[9] t[3] a b, state[3] = snapped, snappedAt, frameID; returns its bool
+int orc_ci_track(OrcCI* o, const float* dIp_concat, float exposure, double* R9, double* t3, double* ab2, int32_t* state3) {
+  ci_load(o, o->cur, dIp_concat);
+  const float* lv[orc::PYR_LEVELS];
+  for (int l = 0; l < o->ci.levels; l++) lv[l] = o->cur[l].data();
+  const bool ok = o->ci.trackFrame(lv, exposure);
+  const orc::Mat33 Rm = o->ci.thisToNext.rotationMatrix();
+  for (int i = 0; i < 9; i++) R9[i] = Rm.d[i];
+  for (int i = 0; i < 3; i++) t3[i] = o->ci.thisToNext.t[i];
+  ab2[0] = o->ci.thisToNext_aff.a; ab2[1] = o->ci.thisToNext_aff.b;
+  state3[0] = o->ci.snapped ? 1 : 0; state3[1] = o->ci.snappedAt; state3[2] = o->ci.frameID;
+  return ok ? 1 : 0;
+}
+}  // extern "C"
+

@@ -176,3 +176,13 @@ def ip_init(dI_host, w, h, K, u, v):
 def ip_trace(P, dI, w, h, K, KRKi, Kt, aff):
     K = np.ascontiguousarray(K, np.float64)
     return orc.ip_trace(P, dI, w, h, KRKi, Kt, aff, _fn=lambda n, dI_, w_, h_, *rest: lib().ref_ip_trace(n, dI_, w_, h_, K, *rest))
+
+
+class CoarseInit(orc.CoarseInit):
+    """the reference's compiled CoarseInitializer behind the same interface (oracle/ref_harness.cpp ref_ci_*).  Process-global calibration
+    state belongs to the reference: keep one alive at a time."""
+
+    _PREFIX = "ref_ci_"
+
+    def __init__(self, w, h, K):
+        super().__init__(w, h, K, _lib=lib())

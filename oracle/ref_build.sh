@@ -20,7 +20,7 @@ fi
 mkdir -p "$OUT/$OBJDIR"
 SRCS="dso/OptimizationBackend/AccumulatedTopHessian.cpp dso/OptimizationBackend/AccumulatedSCHessian.cpp dso/OptimizationBackend/EnergyFunctional.cpp
 dso/OptimizationBackend/EnergyFunctionalStructs.cpp dso/FullSystem/HessianBlocks.cpp dso/FullSystem/Residuals.cpp dso/FullSystem/ImmaturePoint.cpp
-dso/FullSystem/CoarseTracker.cpp dso/util/settings.cpp dso/util/globalCalib.cpp util/TimeMeasurement.cpp"
+dso/FullSystem/CoarseTracker.cpp dso/FullSystem/CoarseInitializer.cpp dso/FullSystem/PixelSelector2.cpp dso/util/settings.cpp dso/util/globalCalib.cpp util/TimeMeasurement.cpp"
 OBJS=""
 for s in $SRCS; do
   o="$OUT/$OBJDIR/$(basename "$s" .cpp).o"

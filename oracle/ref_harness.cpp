@@ -32,6 +32,9 @@
 #include "FullSystem/FullSystem.h"
 #include "FullSystem/CoarseTracker.h"
 #include "FullSystem/ImmaturePoint.h"
+#define private public  /* the harness drives CoarseInitializer::calcResAndGS & co. directly (test infrastructure) */
+#include "FullSystem/CoarseInitializer.h"
+#undef private
 #include "OptimizationBackend/EnergyFunctional.h"
 #include "OptimizationBackend/EnergyFunctionalStructs.h"
 #include "OptimizationBackend/AccumulatedTopHessian.h"
@@ -846,3 +849,141 @@ void ref_ip_trace(int n, const float* dI, int w, int h, const double K[4], const
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Coarse initialiser: the reference's CoarseInitializer (FullSystem/CoarseInitializer.cpp) driven function by function.
+// The pixel selection of setFirst and the kd-tree of makeNN are replaced by caller-provided points / parents / neighbours
+// (everything else of setFirst, L804-889, is mirrored); trackFrame & co. are the reference's compiled code.
+// Note: IndexThreadReduce::reduce always fans out to its worker threads with dynamic chunks of 50 points
+// (util/IndexThreadReduce.h:L77-135), so the summed H / b of calcResAndGS are reproducible only up to float summation order
+// once a level has more than 50 points; the per-point results are deterministic.
+// =====================================================================================================================
+namespace {
+struct RefCI {
+  CalibHessian* Hcalib = nullptr;
+  CoarseInitializer* ci = nullptr;
+  FrameHessian* first = nullptr;
+  FrameHessian* cur = nullptr;
+  std::vector<IOWrap::Output3DWrapper*> wraps;
+};
+}  // namespace
+
+extern "C" {
+
+RefCI* ref_ci_create(int w, int h, const double K[4]) {
+  set_calib_globals(w, h, K);
+  RefCI* C = new RefCI();
+  C->Hcalib = new CalibHessian();
+  C->ci = new CoarseInitializer(w, h);
+  C->ci->printDebug = false;
+  return C;
+}
+void ref_ci_destroy(RefCI* C) {
+  if (!C) return;
+  delete C->ci;
+  free_frame(C->first);
+  free_frame(C->cur);
+  delete C->Hcalib;
+  delete C;
+}
+int ref_ci_levels(RefCI*) { return pyrLevelsUsed; }
+
+void ref_ci_set_first(RefCI* C, const float* dIp_concat, float exposure, const int32_t* n, const float* u, const float* v, const float* type,
+                      const int32_t* parent, const int32_t* neighbours10) {
+  CoarseInitializer* ci = C->ci;
+  free_frame(C->first);
+  C->first = blank_frame(0);
+  load_pyramid(C->first, dIp_concat);
+  C->first->ab_exposure = exposure;
+  ci->makeK(C->Hcalib);
+  ci->firstFrame = C->first;
+  size_t off = 0;
+  for (int lvl = 0; lvl < pyrLevelsUsed; lvl++) {
+    if (ci->points[lvl] != 0) delete[] ci->points[lvl];
+    ci->points[lvl] = new Pnt[n[lvl] > 0 ? n[lvl] : 1];
+    Pnt* pl = ci->points[lvl];
+    for (int i = 0; i < n[lvl]; i++, off++) {  // CoarseInitializer.cpp:L843-872
+      pl[i].u = u[off];
+      pl[i].v = v[off];
+      pl[i].idepth = 1;
+      pl[i].iR = 1;
+      pl[i].isGood = true;
+      pl[i].energy.setZero();
+      pl[i].lastHessian = 0;
+      pl[i].lastHessian_new = 0;
+      pl[i].my_type = type[off];
+      pl[i].outlierTH = patternNum * setting_outlierTH;
+      pl[i].parent = parent[off];
+      pl[i].parentDist = 0;
+      pl[i].isGood_new = false; pl[i].idepth_new = 1; pl[i].energy_new.setZero(); pl[i].iRSumNum = 0; pl[i].maxstep = 0;
+      for (int k = 0; k < 10; k++) { pl[i].neighbours[k] = neighbours10[10 * off + k]; pl[i].neighboursDist[k] = 0; }
+    }
+    ci->numPoints[lvl] = n[lvl];
+  }
+  ci->thisToNext = SE3();
+  ci->thisToNext_aff = AffLight(0, 0);
+  ci->snapped = false;
+  ci->frameID = ci->snappedAt = 0;
+  for (int i = 0; i < pyrLevelsUsed; i++) ci->dGrads[i].setZero();
+  // trackFrame sets these at its start (CoarseInitializer.cpp:L94-97); the function-by-function tests call calcResAndGS before any trackFrame
+  ci->alphaK = 2.5 * 2.5;
+  ci->alphaW = 150 * 150;
+  ci->regWeight = 0.8;
+  ci->couplingWeight = 1;
+}
+void ref_ci_set_new(RefCI* C, const float* dIp_concat, float exposure) {
+  free_frame(C->cur);
+  C->cur = blank_frame(1);
+  load_pyramid(C->cur, dIp_concat);
+  C->cur->ab_exposure = exposure;
+  C->ci->newFrame = C->cur;
+}
+void ref_ci_calc(RefCI* C, int lvl, const double R[9], const double t[3], double a, double b, float* H64, float* b8, float* Hsc64, float* bsc8, float* res3) {
+  Mat88f H, Hsc; Vec8f bb, bsc;
+  Vec3f r = C->ci->calcResAndGS(lvl, H, bb, Hsc, bsc, pose_from(R, t), AffLight(a, b), false);
+  for (int i = 0; i < 8; i++) {
+    for (int j = 0; j < 8; j++) { H64[i * 8 + j] = H(i, j); Hsc64[i * 8 + j] = Hsc(i, j); }
+    b8[i] = bb[i]; bsc8[i] = bsc[i];
+  }
+  for (int i = 0; i < 3; i++) res3[i] = r[i];
+}
+void ref_ci_apply_step(RefCI* C, int lvl) { C->ci->applyStep(lvl); }
+void ref_ci_do_step(RefCI* C, int lvl, float lambda, const float* inc8) {
+  Vec8f inc;
+  for (int i = 0; i < 8; i++) inc[i] = inc8[i];
+  C->ci->doStep(lvl, lambda, inc);
+}
+void ref_ci_calc_ec(RefCI* C, int lvl, float* out3) { Vec3f r = C->ci->calcEC(lvl); for (int i = 0; i < 3; i++) out3[i] = r[i]; }
+void ref_ci_opt_reg(RefCI* C, int lvl) { C->ci->optReg(lvl); }
+void ref_ci_propagate_up(RefCI* C, int lvl) { C->ci->propagateUp(lvl); }
+void ref_ci_propagate_down(RefCI* C, int lvl) { C->ci->propagateDown(lvl); }
+void ref_ci_reset_points(RefCI* C, int lvl) { C->ci->resetPoints(lvl); }
+void ref_ci_set_snapped(RefCI* C, int snapped) { C->ci->snapped = snapped != 0; }
+int ref_ci_npts(RefCI* C, int lvl) { return C->ci->numPoints[lvl]; }
+void ref_ci_get_points(RefCI* C, int lvl, float* out12) {
+  for (int i = 0; i < C->ci->numPoints[lvl]; i++) {
+    const Pnt& p = C->ci->points[lvl][i];
+    float* q = out12 + 12 * i;
+    q[0] = p.idepth; q[1] = p.idepth_new; q[2] = p.iR; q[3] = p.energy[0]; q[4] = p.energy[1]; q[5] = p.energy_new[0]; q[6] = p.energy_new[1];
+    q[7] = p.lastHessian; q[8] = p.lastHessian_new; q[9] = p.maxstep; q[10] = p.isGood ? 1.f : 0.f; q[11] = p.isGood_new ? 1.f : 0.f;
+  }
+}
+void ref_ci_set_points(RefCI* C, int lvl, const float* in5) {
+  for (int i = 0; i < C->ci->numPoints[lvl]; i++) {
+    Pnt& p = C->ci->points[lvl][i];
+    const float* q = in5 + 5 * i;
+    p.idepth = q[0]; p.idepth_new = q[1]; p.iR = q[2]; p.lastHessian = q[3]; p.isGood = q[4] != 0.f;
+  }
+}
+int ref_ci_track(RefCI* C, const float* dIp_concat, float exposure, double* R9, double* t3, double* ab2, int32_t* state3) {
+  ref_ci_set_new(C, dIp_concat, exposure);
+  const bool ok = C->ci->trackFrame(C->cur, C->wraps);
+  const Mat33 Rm = C->ci->thisToNext.rotationMatrix();
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) R9[i * 3 + j] = Rm(i, j); t3[i] = C->ci->thisToNext.translation()[i]; }
+  ab2[0] = C->ci->thisToNext_aff.a; ab2[1] = C->ci->thisToNext_aff.b;
+  state3[0] = C->ci->snapped ? 1 : 0; state3[1] = C->ci->snappedAt; state3[2] = C->ci->frameID;
+  return ok ? 1 : 0;
+}
+
+}  // extern "C"
+

@@ -4,7 +4,9 @@
 #pragma once
 #include <cstdio>
 #include <cstdlib>
+#include <array>
 #include "util/NumType.h"
+#include "util/IndexThreadReduce.h"  // FullSystem/CoarseInitializer.h names IndexThreadReduce / std::array after including this header
 namespace dmvio {
 class IMUIntegration {
  public:
