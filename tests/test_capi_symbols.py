@@ -41,3 +41,13 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, fn), errors="ignore").read()
                 assert "liborc" not in txt and "from oracle" not in txt and "import oracle" not in txt and "orc_" not in txt, fn
+
+
+def test_integration_doc_maps_every_symbol():
+    """INTEGRATION.md's symbol map names every entry point of the header (full name, or the `_suffix` shorthand used for families like
+    `dmv_ba_create / _destroy`)"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    for s in _header_symbols():
+        suffix = "_" + s.split("_", 2)[2]
+        assert s in doc or suffix in doc, f"{s} is not mapped in INTEGRATION.md"
