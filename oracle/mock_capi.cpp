@@ -28,7 +28,10 @@ struct dmv_ba {
   bool have_tentative = false, have_committed = false, have_adj = false;
   ReducedSystem sys;                        // system of the committed linearisation
 };
-struct dmv_ct { int unused; };
+struct dmv_ct {
+  CoarseTracker ct;
+  std::vector<std::vector<float>> pyr;  // pyramid of the frame uploaded last
+};
 
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...) {
@@ -306,17 +309,99 @@ int dmv_ba_marginalize_points(dmv_ba* b, const dmv_ba_marg_args* a) {
   return DMV_OK;
 }
 
-// ---- the coarse tracker adapter is linked into the same library but not exercised by the host-logic tests
-int dmv_ct_create(const dmv_ct_config*, dmv_ct**) { return fail(DMV_ERR_NO_DEVICE, "mock: no coarse tracker"); }
-int dmv_ct_destroy(dmv_ct*) { return DMV_OK; }
-int dmv_ct_set_K(dmv_ct*, int, float, float, float, float) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
-int dmv_ct_set_ref(dmv_ct*, int, int, const float*, const float*, const float*, const float*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
-int dmv_ct_make_coarse_depth(dmv_ct*, int, const float*, const float*, const float*, const float*, int32_t*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
-int dmv_ct_get_ref(dmv_ct*, int, int*, float*, float*, float*, float*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
-int dmv_ct_upload_new(dmv_ct*, int, const float*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
-int dmv_ct_upload_new_image(dmv_ct*, const float*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
-int dmv_ct_set_huber(dmv_ct*, float) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
-int dmv_ct_calc_res_gs(dmv_ct*, int, const float*, const float*, const float*, float, float, int, double*, double*, double*, int*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
-int dmv_ct_track(dmv_ct*, const dmv_ct_track_args*, dmv_ct_track_result*) { return fail(DMV_ERR_NO_DEVICE, "mock"); }
+// ---- coarse tracker handle on the oracle's CoarseTracker: the frame uploaded last is "the new frame"; dmv_ct_make_coarse_depth treats it as
+// the reference keyframe (the reference builds the point lists when a keyframe becomes the tracking reference)
+int dmv_ct_create(const dmv_ct_config* cfg, dmv_ct** out) {
+  if (!cfg || !out) return fail(DMV_ERR_INVALID, "null argument");
+  dmv_ct* c = new dmv_ct();
+  c->ct.levels = cfg->levels;
+  for (int l = 0; l < cfg->levels; l++) { c->ct.w[l] = cfg->w >> l; c->ct.h[l] = cfg->h >> l; c->ct.pc_n[l] = 0; }
+  c->pyr.resize(cfg->levels);
+  *out = c;
+  return DMV_OK;
+}
+int dmv_ct_destroy(dmv_ct* c) { delete c; return DMV_OK; }
+int dmv_ct_set_K(dmv_ct* c, int l, float fx, float fy, float cx, float cy) {
+  c->ct.fx[l] = fx; c->ct.fy[l] = fy; c->ct.cx[l] = cx; c->ct.cy[l] = cy;
+  Mat33f K;
+  K(0, 0) = fx; K(0, 2) = cx; K(1, 1) = fy; K(1, 2) = cy; K(2, 2) = 1;
+  c->ct.Ki[l] = inverse3_cofactor(K);
+  return DMV_OK;
+}
+int dmv_ct_set_huber(dmv_ct* c, float huberTH) { c->ct.s.huberTH = huberTH; return DMV_OK; }
+int dmv_ct_set_ref(dmv_ct* c, int l, int n, const float* u, const float* v, const float* id, const float* col) {
+  c->ct.pc_u[l].assign(u, u + n); c->ct.pc_v[l].assign(v, v + n); c->ct.pc_idepth[l].assign(id, id + n); c->ct.pc_color[l].assign(col, col + n);
+  c->ct.pc_n[l] = n;
+  return DMV_OK;
+}
+int dmv_ct_upload_new(dmv_ct* c, int l, const float* dIp) {
+  c->pyr[l].assign(dIp, dIp + (size_t)c->ct.w[l] * c->ct.h[l] * 3);
+  c->ct.newFrame_dIp[l] = c->pyr[l].data();
+  return DMV_OK;
+}
+int dmv_ct_upload_new_image(dmv_ct* c, const float* image) {
+  GlobalCalib g;
+  g.set(c->ct.w[0], c->ct.h[0], 1.f, 1.f, 0.f, 0.f, c->ct.levels);
+  float* lv[PYR_LEVELS];
+  for (int l = 0; l < c->ct.levels; l++) { c->pyr[l].assign((size_t)c->ct.w[l] * c->ct.h[l] * 3, 0.f); lv[l] = c->pyr[l].data(); }
+  makeImages(g, image, lv, nullptr);
+  for (int l = 0; l < c->ct.levels; l++) c->ct.newFrame_dIp[l] = c->pyr[l].data();
+  return DMV_OK;
+}
+int dmv_ct_make_coarse_depth(dmv_ct* c, int n, const float* Ku, const float* Kv, const float* nid, const float* HdiF, int32_t* pc_n_out) {
+  const float* lv[PYR_LEVELS];
+  for (int l = 0; l < c->ct.levels; l++) lv[l] = c->pyr[l].data();
+  c->ct.makeCoarseDepthL0(n, Ku, Kv, nid, HdiF, lv);
+  if (pc_n_out) for (int l = 0; l < c->ct.levels; l++) pc_n_out[l] = c->ct.pc_n[l];
+  return DMV_OK;
+}
+int dmv_ct_get_ref(dmv_ct* c, int l, int* n, float* u, float* v, float* id, float* col) {
+  const int k = c->ct.pc_n[l];
+  if (n) *n = k;
+  if (u) std::memcpy(u, c->ct.pc_u[l].data(), sizeof(float) * k);
+  if (v) std::memcpy(v, c->ct.pc_v[l].data(), sizeof(float) * k);
+  if (id) std::memcpy(id, c->ct.pc_idepth[l].data(), sizeof(float) * k);
+  if (col) std::memcpy(col, c->ct.pc_color[l].data(), sizeof(float) * k);
+  return DMV_OK;
+}
+int dmv_ct_calc_res_gs(dmv_ct* c, int lvl, const float RKi[9], const float t[3], const float affLL[2], float b0, float cutoffTH, int want_gs,
+                       double res6[6], double H[64], double b[8], int* n_warped) {
+  Mat33f M;
+  for (int i = 0; i < 9; i++) M.d[i] = RKi[i];
+  Vec3f tv;
+  for (int i = 0; i < 3; i++) tv[i] = t[i];
+  c->ct.calcResRaw(lvl, M, tv, affLL, cutoffTH, res6);
+  if (n_warped) *n_warped = c->ct.buf_warped_n;
+  if (want_gs) {
+    Mat88 Hm; Vec8 bm;
+    c->ct.calcGSRaw(lvl, Hm, bm, affLL[0], b0, 1);
+    for (int i = 0; i < 8; i++) { for (int j = 0; j < 8; j++) H[i * 8 + j] = Hm(i, j); b[i] = bm[i]; }
+  }
+  return DMV_OK;
+}
+int dmv_ct_track(dmv_ct* c, const dmv_ct_track_args* in, dmv_ct_track_result* out) {
+  CoarseTracker& ct = c->ct;
+  ct.lastRef_aff_g2l.a = in->ref_a; ct.lastRef_aff_g2l.b = in->ref_b;
+  ct.lastRef_ab_exposure = in->ref_exposure; ct.newFrame_ab_exposure = in->new_exposure;
+  ct.s.coarseCutoffTH = in->coarseCutoffTH; ct.s.affineOptModeA = in->affineOptModeA; ct.s.affineOptModeB = in->affineOptModeB;
+  SE3 T = SE3::fromRt(in->R, in->t);
+  AffLight aff; aff.a = in->a; aff.b = in->b;
+  const SE3 T0 = T; const AffLight aff0 = aff;
+  int its = 0;
+  const bool good = ct.trackNewestCoarse(T, aff, in->coarsestLvl, in->minResForAbort, 1, &its);
+  // the reference returns early (outputs untouched) when a level's residual is NaN or above 1.5 x minResForAbort (CoarseTracker.cpp:L731-735)
+  bool aborted = false;
+  for (int l = 0; l <= in->coarsestLvl; l++)  // levels run from coarsestLvl down to 0: an unfinished (NaN) or over-threshold level means the early return
+    if (ct.lastResiduals[l] != ct.lastResiduals[l] || ct.lastResiduals[l] > 1.5 * in->minResForAbort[l]) aborted = true;
+  if (aborted) { T = T0; aff = aff0; }
+  const Mat33 Rm = T.rotationMatrix();
+  for (int i = 0; i < 9; i++) out->R[i] = Rm.d[i];
+  for (int i = 0; i < 3; i++) out->t[i] = T.t[i];
+  out->a = aff.a; out->b = aff.b;
+  for (int i = 0; i < 5; i++) out->lastResiduals[i] = ct.lastResiduals[i];
+  for (int i = 0; i < 3; i++) out->flowIndicators[i] = ct.lastFlowIndicators[i];
+  out->trackingGood = good ? 1 : 0; out->iterations = its; out->evaluations = 0; out->status = aborted ? 2 : 0;
+  return DMV_OK;
+}
 
 }  // extern "C"

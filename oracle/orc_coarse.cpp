@@ -167,17 +167,21 @@ void CoarseTracker::makeCoarseDepthL0(int n, const float* Ku, const float* Kv, c
 }
 
 void CoarseTracker::calcRes(int lvl, const SE3& refToNew, AffLight aff_g2l, float cutoffTH, double out[6]) {
-  // CoarseTracker.cpp:L361-517
-  float E = 0;
-  int numTermsInE = 0, numTermsInWarped = 0, numSaturated = 0;
-  int wl = w[lvl], hl = h[lvl];
-  const float* dINewl = newFrame_dIp[lvl];
-  float fxl = fx[lvl], fyl = fy[lvl], cxl = cx[lvl], cyl = cy[lvl];
+  // CoarseTracker.cpp:L361-517: the operands (L377-379), then the point loop
   Mat33f RKi = refToNew.rotationMatrix().cast<float>() * Ki[lvl];
   Vec3f t = refToNew.translation().cast<float>();
   double aff2[2];
   AffLight::fromToVecExposure(lastRef_ab_exposure, newFrame_ab_exposure, lastRef_aff_g2l, aff_g2l, aff2);
   float affLL[2] = {(float)aff2[0], (float)aff2[1]};
+  calcResRaw(lvl, RKi, t, affLL, cutoffTH, out);
+}
+
+void CoarseTracker::calcResRaw(int lvl, const Mat33f& RKi, const Vec3f& t, const float affLL[2], float cutoffTH, double out[6]) {
+  float E = 0;
+  int numTermsInE = 0, numTermsInWarped = 0, numSaturated = 0;
+  int wl = w[lvl], hl = h[lvl];
+  const float* dINewl = newFrame_dIp[lvl];
+  float fxl = fx[lvl], fyl = fy[lvl], cxl = cx[lvl], cyl = cy[lvl];
   float sumSquaredShiftT = 0, sumSquaredShiftRT = 0, sumSquaredShiftNum = 0;
   float maxEnergy = 2 * s.huberTH * cutoffTH - s.huberTH * s.huberTH;
   int nl = pc_n[lvl];
@@ -309,8 +313,10 @@ static void gsAccumulate(const CoarseTracker& ct, int lvl, float a, float b0, Ma
 void CoarseTracker::calcGSSSE(int lvl, Mat88& H_out, Vec8& b_out, const SE3& /*refToNew*/, AffLight aff_g2l, int precision) {
   double aff2[2];
   AffLight::fromToVecExposure(lastRef_ab_exposure, newFrame_ab_exposure, lastRef_aff_g2l, aff_g2l, aff2);
-  float a = (float)aff2[0];
-  float b0 = (float)lastRef_aff_g2l.b;
+  calcGSRaw(lvl, H_out, b_out, (float)aff2[0], (float)lastRef_aff_g2l.b, precision);
+}
+
+void CoarseTracker::calcGSRaw(int lvl, Mat88& H_out, Vec8& b_out, float a, float b0, int precision) {
   Mat<double, 9, 9> H;
   if (precision == 0) gsAccumulate<float>(*this, lvl, a, b0, H);
   else gsAccumulate<double>(*this, lvl, a, b0, H);

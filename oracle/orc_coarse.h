@@ -47,6 +47,9 @@ struct CoarseTracker {
   void makeCoarseDepthL0(int n, const float* Ku, const float* Kv, const float* new_idepth, const float* HdiF, const float* const* refdIp);
   void calcRes(int lvl, const SE3& refToNew, AffLight aff_g2l, float cutoffTH, double out6[6]);            // L361-517
   void calcGSSSE(int lvl, Mat88& H_out, Vec8& b_out, const SE3& refToNew, AffLight aff_g2l, int precision);  // L299-356
+  // the same two functions behind their operand set-up (RKi, t, affLL / a, b0 given): what the C ABI's dmv_ct_calc_res_gs takes
+  void calcResRaw(int lvl, const Mat33f& RKi, const Vec3f& t, const float affLL[2], float cutoffTH, double out6[6]);
+  void calcGSRaw(int lvl, Mat88& H_out, Vec8& b_out, float a, float b0, int precision);
   // L539-770 (no IMU branch).  returns trackingGood; iterations per level are logged in itsOut (optional)
   bool trackNewestCoarse(SE3& lastToNew_out, AffLight& aff_g2l_out, int coarsestLvl, const double minResForAbort[5], int precision,
                          int* totalIterations = nullptr);

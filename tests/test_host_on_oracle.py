@@ -1,4 +1,4 @@
-"""Host logic of the C++ adapter (dm-vio_b200/host/window_ba.cpp) in the CPU test tier.
+"""Host logic of the C++ adapters (dm-vio_b200/host/window_ba.cpp, coarse_tracker.cpp) in the CPU test tier.
 
 oracle/libhost_on_oracle.so = the adapter's UNMODIFIED sources linked against oracle/mock_capi.cpp, a CPU stand-in of the C ABI built on the
 oracle (test infrastructure, never shipped).  The adapter therefore runs its own control flow here — FullSystem::optimize's LM loop with
@@ -6,7 +6,8 @@ solveSystemF (priors, marginalisation prior, Jacobi-preconditioned LDLT, gauge p
 the tail (setEvalPT, linearizeAll(true) bookkeeping, residual deletion), flagPointsForRemoval, marginalizePointsF, marginalizeFrame — and is
 compared with the oracle's own optimize / finishOptimize / marginalize, which tests/test_ref_pin.py pins to the reference.  Both sides use the
 same residual arithmetic (the oracle's), so the tolerances are tight: what differs is only the adapter's host-side fp64 code and its float
-tables.  The same scenarios run against the CUDA kernels in tests/test_gpu_host.py."""
+tables.  The coarse-tracker adapter (makeK, host makeCoarseDepthL0, calcRes operand set-up, its own LM loop, the abort path) is driven the same
+way against the oracle's trackNewestCoarse.  The same scenarios run against the CUDA kernels in tests/test_gpu_host.py."""
 import ctypes as C
 import os
 import subprocess
@@ -168,3 +169,51 @@ def test_keyframe_turnover_flow(hostapi, orc, synth):
     assert n >= 1 and np.all(np.isfinite(log))
     assert log[-1] + eL1 + eM1 <= (log[0] + eL + eM) * (1 + 1e-9)
     hw.close()
+
+
+@pytest.mark.parametrize("device_lm", [False, True], ids=["host_lm_loop", "one_call_track"])
+@pytest.mark.parametrize("levels", [4, 5])
+def test_coarse_tracker_adapter(hostapi, orc, synth, levels, device_lm):
+    """host/coarse_tracker.cpp on the stand-in C ABI: makeK, the host-side makeCoarseDepthL0 + reference upload, the operand set-up of
+    calcRes (R*Ki in float with the reference's K inverse, affLL) and — with device_lm = False — the adapter's own Levenberg-Marquardt loop of
+    trackNewestCoarse (level repeats, cutoff doubling, accept / reject, 8x8 solve) against the oracle's trackNewestCoarse."""
+    T = synth.make_tracking_pair(seed=4321, levels=levels if levels == 5 else 0)
+    oct_ = orc.CoarseTracker(T["w"], T["h"], T["K"], levels if levels == 5 else 0)
+    oct_.make_coarse_depth(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
+    oct_.set_new_frame(T["pyr_new"])
+    r_o = oct_.track(np.eye(3), np.zeros(3), 0.0, 0.0)
+    g = hostapi.CoarseTracker(T["w"], T["h"], T["K"], levels)
+    counts = g.set_ref(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
+    assert counts == [len(oct_.ref_points(l)["u"]) for l in range(levels)]
+    g.set_new_image(T["img_new"])
+    r_g = g.track(np.eye(3), np.zeros(3), 0.0, 0.0, device_lm=device_lm)
+    assert r_g["good"] == r_o["good"]
+    assert np.abs(r_g["R"] - r_o["R"]).max() < 1e-7 and np.abs(r_g["t"] - r_o["t"]).max() < 1e-7
+    assert abs(r_g["a"] - r_o["a"]) < 1e-6 and abs(r_g["b"] - r_o["b"]) < 1e-4
+    np.testing.assert_allclose(r_g["lastResiduals"][:levels], r_o["lastResiduals"][:levels], rtol=1e-6)
+    assert r_g["iterations"] == r_o["iterations"]
+    assert np.linalg.norm(r_g["t"] - T["t_true"]) < 5e-4
+    # setCoarseTrackingRef with makeCoarseDepthL0 behind the C ABI (raw keyframe image in) gives the same lists and track
+    b = hostapi.CoarseTracker(T["w"], T["h"], T["K"], levels)
+    assert b.set_ref_device(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["img_ref"]) == counts
+    b.set_new_image(T["img_new"])
+    r_b = b.track(np.eye(3), np.zeros(3), 0.0, 0.0, device_lm=device_lm)
+    np.testing.assert_array_equal(r_b["R"], r_g["R"]); np.testing.assert_array_equal(r_b["t"], r_g["t"])
+    g.close(); b.close()
+
+
+def test_coarse_tracker_abort_leaves_outputs_untouched(hostapi, orc, synth):
+    """residual above 1.5 x minResForAbort: trackNewestCoarse returns false before it writes its outputs (CoarseTracker.cpp:L731-735), on both
+    paths of the adapter"""
+    T = synth.make_tracking_pair(seed=4321)
+    L = T["levels"]
+    R0, t0 = synth.se3_exp(np.array([0.01, 0.0, 0.0, 0.0, 0.002, 0.0]))
+    for device_lm in (False, True):
+        g = hostapi.CoarseTracker(T["w"], T["h"], T["K"], L)
+        g.set_ref(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
+        g.set_new_image(T["img_new"])
+        r = g.track(R0, t0, 0.1, 0.2, minRes=np.full(5, 1e-6), device_lm=device_lm)
+        assert not r["good"]
+        np.testing.assert_array_equal(r["R"], R0); np.testing.assert_array_equal(r["t"], t0)
+        assert r["a"] == 0.1 and r["b"] == 0.2
+        g.close()
