@@ -190,6 +190,10 @@ int dmv_ba_create(const dmv_ba_config* cfg, dmv_ba** out) {
   }
   if (cfg->device < 0 || cfg->device >= ndev) return set_error(DMV_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
   CK(cudaSetDevice(cfg->device));
+  if (const char* e = getenv("DMV_L2_FETCH")) {  // experiment: L2 -> DRAM fetch granularity in bytes (32 / 64 / 128; the driver default is 64)
+    const int g = atoi(e);
+    if (g == 32 || g == 64 || g == 128) CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g));
+  }
   dmv_ba* b = new dmv_ba();
   const int rc = ba_allocate(b, cfg);
   if (rc != DMV_OK) {  // e.g. out of device memory half-way: release what was allocated (the error message of the failing call is kept)
@@ -276,6 +280,7 @@ int dmv_ba_destroy(dmv_ba* b) {
     cudaFree(b->d_pout[k]); cudaFree(b->d_result[k]); cudaFreeHost(b->h_result[k]);
   }
   cudaFree(b->d_step); cudaFree(b->d_acc[0]); cudaFree(b->d_acc[1]); cudaFree(b->d_resub_sums); cudaFree(b->d_flush);
+  cudaFree(b->d_ticket); cudaFree(b->d_stage); cudaFree(b->d_dbg_clk);
   cudaFreeHost(b->h_up); cudaFreeHost(b->h_adj); cudaFreeHost(b->h_scratch);
   for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   if (b->nccl_comm) dmv::nccl_destroy(b->nccl_comm);

@@ -58,6 +58,8 @@ def _declare(L):
     L.orc_win_linearize_all.restype = C.c_double
     L.orc_win_linearize_all.argtypes = [vp, C.c_int, C.c_int]
     L.orc_win_apply_res.argtypes = [vp]
+    L.orc_win_override_new_states.restype = C.c_double
+    L.orc_win_override_new_states.argtypes = [vp, i32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.orc_win_get_res_outputs.argtypes = [vp, i32p, f32p, f32p, f32p, vp, i32p, u8p, f32p]
     L.orc_win_accumulate.argtypes = [vp, C.c_int, f64p, f64p, f64p, f64p, f64p, f64p, C.POINTER(C.c_int)]
     L.orc_win_get_nullspaces.argtypes = [vp, f64p]
@@ -191,6 +193,13 @@ class Window:
 
     def apply_res(self):
         self.L.orc_win_apply_res(self.h)
+
+    def override_new_states(self, newState):
+        """impose another implementation's classification on the tentative linearisation (threshold ties); returns
+        (energy sum under that classification, #changed, #unfixable)"""
+        ch, bad = C.c_int(0), C.c_int(0)
+        E = self.L.orc_win_override_new_states(self.h, np.ascontiguousarray(newState, np.int32), C.byref(ch), C.byref(bad))
+        return E, ch.value, bad.value
 
     def res_outputs(self, want_J=True):
         n = self.nres

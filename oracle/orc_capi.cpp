@@ -178,6 +178,35 @@ double orc_win_linearize_all(OrcWin* o, int fix, int updateEnergyTH) {
 }
 void orc_win_apply_res(OrcWin* o) { o->W.applyResAll(); }
 
+double orc_win_override_new_states(OrcWin* o, const int32_t* newState, int* changed, int* unfixable) {
+  Window& W = o->W;
+  int nch = 0, nbad = 0;
+  double E = 0;
+  for (size_t i = 0; i < W.residuals.size(); i++) {
+    Residual& r = W.residuals[i];
+    if (r.isLinearized || r.dropped) continue;
+    const int want = newState[i];
+    if (want != r.state_NewState) {
+      if (r.state_NewState == RS_OOB) {
+        nbad++;  // left through an OOB exit: no Jacobian / energy to reuse
+      } else if (want == RS_OOB) {
+        r.state_NewState = RS_OOB;
+        r.state_NewEnergy = r.state_energy;  // OOB exits return the old energy (Residuals.cpp:L82-83)
+        nch++;
+      } else {
+        const float TH = std::max(W.frames[r.host].frameEnergyTH, W.frames[r.target].frameEnergyTH);
+        r.state_NewState = want;
+        r.state_NewEnergy = (want == RS_IN) ? r.state_NewEnergyWithOutlier : (double)TH;  // Residuals.cpp:L262-271
+        nch++;
+      }
+    }
+    E += r.state_NewEnergy;
+  }
+  if (changed) *changed = nch;
+  if (unfixable) *unfixable = nbad;
+  return E;
+}
+
 void orc_win_get_res_outputs(OrcWin* o, int32_t* newState, float* newEnergy, float* newEnergyWithOutlier, float* cpt3, float* Jnew74,
                              int32_t* state_state, uint8_t* isActive, float* JpJdF8) {
   Window& W = o->W;

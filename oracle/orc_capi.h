@@ -39,6 +39,12 @@ void orc_win_get_calib(OrcWin*, float* fxfycxcy_and_inv8, float* cDeltaF4, doubl
 /* ---- hot path ---- */
 double orc_win_linearize_all(OrcWin*, int fixLinearization, int updateEnergyTH);
 void orc_win_apply_res(OrcWin*);
+/* Test helper for threshold ties: impose the classification another implementation reached (IN / OOB / OUTLIER per residual) on the
+ * tentative linearisation, so that the committed systems of both sides cover the same residual set.  IN <-> OUTLIER flips reuse the
+ * Jacobian linearize() already produced (it is computed before the classification, Residuals.cpp:L260-273); -> OOB drops the residual.
+ * A residual that left through an OOB exit here but not there cannot be fixed (no Jacobian): counted in *unfixable.
+ * Returns the energy sum of the imposed classification (what linearizeAll would have returned). */
+double orc_win_override_new_states(OrcWin*, const int32_t* newState, int* changed, int* unfixable);
 /* per-residual outputs of the last linearize */
 void orc_win_get_res_outputs(OrcWin*, int32_t* newState, float* newEnergy, float* newEnergyWithOutlier, float* centerProjectedTo3,
                              float* Jnew74 /* may be NULL */, int32_t* state_state, uint8_t* isActive, float* JpJdF8);

@@ -30,6 +30,8 @@ CONFIGS = [
     dict(nf=3, npts=333, seed=7),                      # ragged chunk sizes
     dict(nf=7, npts=2000, seed=1234),                  # BASELINE config 3
     dict(nf=8, npts=777, seed=99, hosts="all"),        # max window size, newest frame hosts points too
+    dict(nf=7, npts=8000, seed=1234),                  # BASELINE config 4 (all 8000 points on one GPU)
+    dict(nf=7, npts=2000, seed=1234, w=512, h=512),    # BASELINE config 5's image shape (TUM-VI 512x512)
 ]
 
 
@@ -54,37 +56,41 @@ def test_linearize_accumulate_parity(capi, orc, synth, cfg, P):
         eo, TH = o["newEnergyWithOutlier"][i], 512.0
         assert abs(eo - TH) < 2e-3 * TH or o["newState"][i] == 1 or g["newState"][i] == 1, (i, o["newState"][i], g["newState"][i], eo)
     assert len(mism) <= max(2, ow.nres // 500)
-    same = o["newState"] == g["newState"]
     assert r["n_in"] == int((g["newState"] == 0).sum())
     assert r["n_oob"] == int((g["newState"] == 1).sum())
+    # ---- threshold ties: impose the GPU's classification on the oracle (its Jacobians exist on both sides of the threshold), so that every
+    # comparison below runs UNCONDITIONALLY on the same residual set
+    E_o, nchanged, unfixable = ow.override_new_states(g["newState"])
+    assert unfixable == 0, "an OOB-boundary tie cannot be imposed on the oracle: pick another seed for this config"
+    assert nchanged == len(mism)
+    o = ow.res_outputs(False)
+    assert np.array_equal(o["newState"], g["newState"])
     # ---- energies
-    ev = same & (o["newState"] != 1)
+    ev = o["newState"] != 1
     np.testing.assert_allclose(g["newEnergy"][ev], o["newEnergy"][ev], rtol=2e-3, atol=0.05)
     np.testing.assert_allclose(g["newEnergyWithOutlier"][ev], o["newEnergyWithOutlier"][ev], rtol=2e-3, atol=0.05)
     relerr = np.abs(g["newEnergyWithOutlier"][ev] - o["newEnergyWithOutlier"][ev]) / (np.abs(o["newEnergyWithOutlier"][ev]) + 1.0)
     assert np.median(relerr) < 2e-4
-    if len(mism) == 0:
-        assert abs(r["energy"] - E_o) <= 2e-5 * abs(E_o)
+    assert abs(r["energy"] - E_o) <= 2e-5 * abs(E_o)
     np.testing.assert_allclose(g["centerProjectedTo"][ev], o["centerProjectedTo"][ev], rtol=1e-5, atol=2e-4)
     # ---- commit, then per-residual JpJdF and per-point accumulations
     ow.apply_res()
     ba.apply_res()
     o2 = ow.res_outputs(False)
-    act = (o2["isActive"] == 1) & same
+    act = o2["isActive"] == 1
     scale = np.abs(o2["JpJdF"][act]).max()
     assert np.abs(g["JpJdF"][act] - o2["JpJdF"][act]).max() <= 2e-3 * scale
     assert np.median(np.abs(g["JpJdF"][act] - o2["JpJdF"][act])) <= 2e-5 * scale
     a_o = ow.accumulate(1)
     a_g = ba.accumulate()
     po, pg = ow.point_outputs(), ba.point_outputs()
-    if len(mism) == 0:
-        assert a_g["resInA"] == a_o["resInA"]
-        for k in ("Hdd", "bd", "HdiF", "bdSumF"):
-            np.testing.assert_allclose(pg[k], po[k], rtol=2e-3, atol=2e-4 * np.abs(po[k]).max())
-        assert rel(a_g["HA"], a_o["HA"]) < 1e-5
-        assert rel(a_g["bA"], a_o["bA"]) < 1e-4
-        assert rel(a_g["Hsc"], a_o["Hsc"]) < 1e-5
-        assert rel(a_g["bsc"], a_o["bsc"]) < 1e-4
+    assert a_g["resInA"] == a_o["resInA"]
+    for k in ("Hdd", "bd", "HdiF", "bdSumF"):
+        np.testing.assert_allclose(pg[k], po[k], rtol=2e-3, atol=2e-4 * np.abs(po[k]).max())
+    assert rel(a_g["HA"], a_o["HA"]) < 1e-5
+    assert rel(a_g["bA"], a_o["bA"]) < 1e-4
+    assert rel(a_g["Hsc"], a_o["Hsc"]) < 1e-5
+    assert rel(a_g["bsc"], a_o["bsc"]) < 1e-4
     # invariants that hold regardless of ties
     assert np.abs(a_g["HA"] - a_g["HA"].T).max() <= 1e-9 * np.abs(a_g["HA"]).max()
     assert np.abs(a_g["Hsc"] - a_g["Hsc"].T).max() <= 1e-9 * np.abs(a_g["Hsc"]).max()
@@ -129,8 +135,9 @@ def test_oob_and_prior_states(capi, orc, synth):
     assert np.all(g["newState"][W["res_state"] == 1] == 1)     # can never go back from OOB
     same = o["newState"] == g["newState"]
     assert same.mean() > 0.99
-    if same.all():
-        assert abs(r["energy"] - E_o) <= 2e-5 * abs(E_o)
+    E_o, _, unfixable = ow.override_new_states(g["newState"])
+    assert unfixable == 0
+    assert abs(r["energy"] - E_o) <= 2e-5 * abs(E_o)
     ba.close()
 
 
