@@ -1,133 +1,28 @@
 // C-ABI of the bundle-adjustment handle (include/dmvio_b200.h).  Host-side plumbing only: buffer ownership, the
 // [target][point] residual-slot layout, tentative/committed double buffering, one stream + pinned staging per handle.
-#include "../../include/dmvio_b200.h"
-#include "ba_device.cuh"
-#include "common_host.h"
+#include "ba_handle.h"
 #include "ip_trace.h"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
-#include <vector>
-
-namespace dmv {
-void launch_point_kernel(const BAWinDev& W, const BAIter& it, cudaStream_t s);
-void launch_point_kernel_marg(const BAWinDev& W, const BAIter& it, cudaStream_t s);
-void launch_stitch_kernel(const BAWinDev& W, cudaStream_t s);
-void launch_resub_kernel(const BAWinDev& W, const BAIter& it, int apply, double* sums, cudaStream_t s);
-void launch_repack(const float* src, float4* dst, int n, cudaStream_t s);
-void launch_make_dI(const float* img, float4* dst, int w, int h, cudaStream_t s);
-void launch_l2_flush(float4* buf, size_t n, cudaStream_t s);
-}  // namespace dmv
 
 using namespace dmv;
 
-struct HostUpload {  // descriptor + per-iteration tables: passed BY VALUE as __grid_constant__ kernel parameters (no H2D copy)
-  BAWinDev win;
-  BAIter it;
-};
-
-struct dmv_ba {
-  dmv_ba_config cfg;
-  dmv_ba_params prm;
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  int P = 16;
-  int mp = 0;  // point capacity (slot pitch)
-  int nf = 0, npts = 0, nres = 0, nchunks = 0, max_chunks = 0;
-  int N = 0, NW = 0, T = 0, ntiles = 0;
-  int slots[MAXF];
-  // device buffers
-  float4* d_img[MAXF] = {nullptr};
-  float* d_stage_img = nullptr;
-  BAAdj* d_adj = nullptr;
-  float2* d_uv = nullptr;
-  float* d_idepth[2] = {nullptr, nullptr};  // ping-pong: [cur] current depths, [bak] FullSystem::backupState copy
-  int id_cur = 0, id_bak = 0;
-  bool zero_alias = false;                  // idepth_zero == idepth (true after any step / restore)
-  float *d_idepth_zero = nullptr, *d_color = nullptr, *d_weights = nullptr, *d_priorF = nullptr;
-  uint8_t* d_st_in = nullptr;
-  float* d_en_in = nullptr;
-  uint8_t* d_st_new[2] = {nullptr, nullptr};
-  float *d_en_new[2] = {nullptr, nullptr}, *d_en_wo[2] = {nullptr, nullptr}, *d_cpt[2] = {nullptr, nullptr}, *d_jpjd[2] = {nullptr, nullptr},
-        *d_pout[2] = {nullptr, nullptr};
-  double* d_result[2] = {nullptr, nullptr};
-  float* d_step = nullptr;
-  double* d_acc[2] = {nullptr, nullptr};  // fp64 accumulator sets (current / being zeroed for the next iteration)
-  int acc_cur = 0;
-  size_t acc_cap = 0;
-  double* d_resub_sums = nullptr;
-  unsigned long long* d_dbg_clk = nullptr;
-  unsigned int* d_ticket = nullptr;
-  double* d_stage = nullptr;
-  float4* d_flush = nullptr;
-  size_t flush_n = 0;
-  // pinned host
-  HostUpload* h_up = nullptr;
-  BAAdj* h_adj = nullptr;
-  double* h_result[2] = {nullptr, nullptr};
-  float* h_scratch = nullptr;  // max(mp*8, w*h*3) floats
-  size_t scratch_floats = 0;
-  // host bookkeeping
-  int host_start[MAXF + 1];
-  int chunk_beg[MAXF + 1];
-  std::vector<int> host_of_point;
-  std::vector<int> res_slot;   // residual index -> slot (t*mp+p)
-  std::vector<uint8_t> h_st_in;
-  std::vector<float> h_en_in;
-  bool st_in_clean = false;    // every existing residual's INPUT state on the device is IN with zero energy (dmv_ba_reset_oob becomes a flag flip)
-  bool no_zero_copy = false;   // DMV_NO_ZERO_COPY=1: D2H copy node instead of in-kernel writes to the pinned result (A/B experiment)
-  bool timing = false;         // record CUDA events around the kernels of every call (dmv_ba_set_timing)
-  int iter2 = 0;
-  int dbg = 0;                 // DMV_DBG experiment mask (see ba_device.cuh); never set in production
-  int tent = 0;                // index of the tentative buffer set; committed = 1 - tent
-  bool have_tentative = false, have_committed = false, have_adj = false, have_state = false;
-  long long launches = 0;
-  float last_ms[4] = {0, 0, 0, 0};
-  // NCCL
-  void* nccl_comm = nullptr;
-  int nranks = 1, rank = 0;
-  // marginalisation launch (dmv_ba_marginalize_points): allocated on first use
-  BAMarg* d_marg = nullptr;
-  uint8_t* d_marg_mask = nullptr;
-  float* d_marg_rtz = nullptr;
-  double* d_marg_acc = nullptr;      // [acc | scratch the stitch zeroes]
-  double* d_marg_result = nullptr;
-  double* h_marg_result = nullptr;
-  float* d_act = nullptr;      // point-activation staging (dmv_ba_activate_points)
-  float* h_act = nullptr;
-  int act_cap = 0;
-  // peer-memory exchange (fused into ba_stitch_kernel)
-  void* xchg_own = nullptr;                 // this rank's inbox (cudaMalloc, exported through CUDA IPC)
-  void* xchg_map[XCHG_MAXR] = {nullptr};    // every rank's inbox as mapped here ([rank] == xchg_own)
-  int xchg_pitch = 0;
-  bool xchg_on = false;
-  unsigned int xchg_seq = 0;
-};
-
 // all-reduce of the stitched result blob across ranks: fused into the stitch kernel when the peer-memory exchange is on
 // (fill_descriptor/next_exchange hand it the inbox table), otherwise one ncclAllReduce behind it
-static int enqueue_exchange(dmv_ba* b) {
+int dmv_ba_enqueue_exchange(dmv_ba* b) {
   if (b->xchg_on) return DMV_OK;
   if (b->nccl_comm) return dmv::nccl_allreduce_double(b->nccl_comm, b->d_result[b->tent], result_doubles(b->N, b->ntiles), b->stream);
   return DMV_OK;
 }
 
-#define CK(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t _e = (call);                                                                       \
-    if (_e != cudaSuccess) return dmv::set_error(DMV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); \
-  } while (0)
-
-static int fill_descriptor(dmv_ba* b) {
+int dmv_ba_fill_descriptor(dmv_ba* b) {
   BAWinDev& W = b->h_up->win;
   std::memset(&W, 0, sizeof(W));
   W.nf = b->nf; W.npts = b->npts; W.nchunks = b->nchunks; W.w = b->cfg.w; W.h = b->cfg.h;
   W.N = b->N; W.NW = b->NW; W.T = b->T; W.ntiles = b->ntiles; W.mp = b->mp; W.P = b->P;
   W.huberTH = b->prm.huberTH; W.outlierTHSum = b->prm.outlierTHSumComponent;
   W.zeroA = b->prm.affineOptModeA < 0; W.zeroB = b->prm.affineOptModeB < 0;
-  W.dbg = b->dbg;
-  W.iter2 = b->iter2;
   for (int h = 0; h <= MAXF; h++) { W.host_start[h] = b->host_start[h]; W.chunk_beg[h] = b->chunk_beg[h]; }
   for (int f = 0; f < b->nf; f++) W.img[f] = b->d_img[b->slots[f]];
   W.adj = b->d_adj;
@@ -145,11 +40,8 @@ static int fill_descriptor(dmv_ba* b) {
   W.st_new = b->d_st_new[t]; W.en_new = b->d_en_new[t]; W.en_wo = b->d_en_wo[t]; W.cpt = b->d_cpt[t]; W.jpjd = b->d_jpjd[t]; W.pout = b->d_pout[t];
   W.c_st = b->d_st_new[c2]; W.c_jpjd = b->d_jpjd[c2]; W.c_pout = b->d_pout[c2];
   W.step = b->d_step;
-  W.acc = b->d_acc[b->acc_cur];
-  W.acc_next = b->d_acc[1 - b->acc_cur];
-  W.dbg_clk = b->d_dbg_clk;
-  W.ticket = b->d_ticket;
-  W.stage = b->d_stage;
+  W.part = b->d_part; W.wg = b->d_wg; W.hdig = b->d_hdig;
+  W.bar = b->d_bar;
   W.result = b->d_result[t];
   W.result_host = nullptr;
   W.xc.nranks = b->xchg_on ? b->nranks : 1;
@@ -161,7 +53,7 @@ static int fill_descriptor(dmv_ba* b) {
 }
 
 // every stitch launch of a sharded handle is one exchange: number it (all ranks launch the same sequence of stitches)
-static void next_exchange(dmv_ba* b) {
+void dmv_ba_next_exchange(dmv_ba* b) {
   if (!b->xchg_on) return;
   b->xchg_seq++;
   if (b->xchg_seq == 0) b->xchg_seq = 2;  // 0 is the "empty" flag; keep the parity sequence alternating after a wrap
@@ -208,10 +100,8 @@ static int ba_allocate(dmv_ba* b, const dmv_ba_config* cfg) {
   b->cfg = *cfg;
   b->device = cfg->device;
   dmv_ba_default_params(&b->prm);
-  if (const char* e = getenv("DMV_DBG")) b->dbg = atoi(e);
-  if (const char* e = getenv("DMV_ITER2")) b->iter2 = atoi(e);
   if (const char* e = getenv("DMV_NO_ZERO_COPY")) b->no_zero_copy = atoi(e) != 0;
-  b->P = (cfg->chunk_points == 8 || cfg->chunk_points == 16 || cfg->chunk_points == 32) ? cfg->chunk_points : 16;
+  b->P = (cfg->chunk_points == 16 || cfg->chunk_points == 32) ? cfg->chunk_points : 16;
   b->mp = (cfg->max_points + 31) & ~31;
   const int MF = MAXF, mp = b->mp;
   b->max_chunks = (mp + b->P - 1) / b->P + MF;
@@ -245,19 +135,12 @@ static int ba_allocate(dmv_ba* b, const dmv_ba_config* cfg) {
   }
   CK(cudaMalloc(&b->d_step, sizeof(float) * mp));
   CK(cudaMemset(b->d_step, 0, sizeof(float) * mp));
-  const int maxT = (8 * MF + 4 + 1 + 3) / 4, maxTiles = maxT * (maxT + 1) / 2;
-  b->acc_cap = (size_t)acc_doubles(MF, maxTiles);
-  for (int k = 0; k < 2; k++) {
-    CK(cudaMalloc(&b->d_acc[k], sizeof(double) * b->acc_cap));
-    CK(cudaMemset(b->d_acc[k], 0, sizeof(double) * b->acc_cap));
-  }
+  CK(cudaMalloc(&b->d_part, sizeof(double) * PART_STRIDE * (size_t)b->max_chunks));
+  CK(cudaMalloc(&b->d_wg, sizeof(float4) * (size_t)maxT0 * mp));
+  CK(cudaMalloc(&b->d_hdig, sizeof(float) * mp));
+  CK(cudaMalloc(&b->d_bar, sizeof(unsigned int)));
+  CK(cudaMemset(b->d_bar, 0, sizeof(unsigned int)));
   CK(cudaMalloc(&b->d_resub_sums, sizeof(double) * 4));
-  CK(cudaMalloc(&b->d_ticket, sizeof(unsigned int) * 16));
-  CK(cudaMemset(b->d_ticket, 0, sizeof(unsigned int) * 16));
-  CK(cudaMalloc(&b->d_stage, sizeof(double) * (MF * MF * 272 + MF * 20)));
-  CK(cudaMemset(b->d_stage, 0, sizeof(double) * (MF * MF * 272 + MF * 20)));
-  CK(cudaMalloc(&b->d_dbg_clk, sizeof(unsigned long long) * 16 * (b->max_chunks + MAXF + 1)));
-  CK(cudaMemset(b->d_dbg_clk, 0, sizeof(unsigned long long) * 16 * (b->max_chunks + MAXF + 1)));
   CK(cudaMallocHost(&b->h_up, sizeof(HostUpload)));
   CK(cudaMallocHost(&b->h_adj, sizeof(BAAdj)));
   std::memset(b->h_up, 0, sizeof(HostUpload));
@@ -279,13 +162,13 @@ int dmv_ba_destroy(dmv_ba* b) {
     cudaFree(b->d_st_new[k]); cudaFree(b->d_en_new[k]); cudaFree(b->d_en_wo[k]); cudaFree(b->d_cpt[k]); cudaFree(b->d_jpjd[k]);
     cudaFree(b->d_pout[k]); cudaFree(b->d_result[k]); cudaFreeHost(b->h_result[k]);
   }
-  cudaFree(b->d_step); cudaFree(b->d_acc[0]); cudaFree(b->d_acc[1]); cudaFree(b->d_resub_sums); cudaFree(b->d_flush);
-  cudaFree(b->d_ticket); cudaFree(b->d_stage); cudaFree(b->d_dbg_clk);
+  cudaFree(b->d_step); cudaFree(b->d_resub_sums); cudaFree(b->d_flush);
+  cudaFree(b->d_part); cudaFree(b->d_wg); cudaFree(b->d_hdig); cudaFree(b->d_bar);
   cudaFreeHost(b->h_up); cudaFreeHost(b->h_adj); cudaFreeHost(b->h_scratch);
   for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   if (b->nccl_comm) dmv::nccl_destroy(b->nccl_comm);
   cudaFree(b->d_act); cudaFreeHost(b->h_act);
-  cudaFree(b->d_marg); cudaFree(b->d_marg_mask); cudaFree(b->d_marg_rtz); cudaFree(b->d_marg_acc); cudaFree(b->d_marg_result);
+  cudaFree(b->d_marg); cudaFree(b->d_marg_mask); cudaFree(b->d_marg_rtz); cudaFree(b->d_marg_result);
   cudaFreeHost(b->h_marg_result);
   for (int r = 0; r < XCHG_MAXR; r++)
     if (b->xchg_map[r] && b->xchg_map[r] != b->xchg_own) cudaIpcCloseMemHandle(b->xchg_map[r]);
@@ -341,9 +224,6 @@ int dmv_ba_set_window(dmv_ba* b, int nf, const int* slots) {
   b->ntiles = b->T * (b->T + 1) / 2;
   b->have_adj = b->have_state = b->have_tentative = b->have_committed = false;
   b->npts = b->nres = b->nchunks = 0;
-  CK(cudaSetDevice(b->device));
-  CK(cudaStreamSynchronize(b->stream));
-  for (int k = 0; k < 2; k++) CK(cudaMemset(b->d_acc[k], 0, sizeof(double) * b->acc_cap));  // accumulator layout depends on nf
   return DMV_OK;
 }
 
@@ -474,24 +354,21 @@ int dmv_ba_set_state(dmv_ba* b, const dmv_ba_state* st) {
   return DMV_OK;
 }
 
-static int enqueue_linearize(dmv_ba* b, bool with_resub) {
-  (void)with_resub;  // the resubstitute + step prologue is fused into the point kernel (it.have_x)
-  fill_descriptor(b);
-  next_exchange(b);
-  // the stitch kernel writes the final blob into the pinned host mirror itself, unless a NCCL all-reduce still follows it
+static int enqueue_linearize(dmv_ba* b) {
+  dmv_ba_fill_descriptor(b);
+  dmv_ba_next_exchange(b);
+  // the kernel writes the final blob into the pinned host mirror itself, unless a NCCL all-reduce still follows it
   const bool zero_copy = !(b->nccl_comm && !b->xchg_on) && !b->no_zero_copy;
-  if (zero_copy) b->h_up->win.result_host = b->h_result[b->tent];
-  const HostUpload& U = *b->h_up;
+  double* hres = b->h_result[b->tent];
+  hres[(size_t)b->N * b->N + b->N + (size_t)b->ntiles * 16 + (ACC_MISC - 1)] = 0.0;  // error flag: written by the device on a timeout only
+  if (zero_copy) b->h_up->win.result_host = hres;
+  HostUpload& U = *b->h_up;
   if (b->timing) CK(cudaEventRecord(b->ev[0], b->stream));
-  launch_point_kernel(U.win, U.it, b->stream);   // residuals + Hessian blocks + Schur Gram -> fp64 accumulators
+  CK(launch_fused_kernel(U.win, U.it, false, b->stream, &b->bar_count));  // whole linearisation: residuals -> H_top, b_top, [H_sc | b_sc]
+  b->launches += 1;
   if (b->timing) CK(cudaEventRecord(b->ev[1], b->stream));
-  launch_stitch_kernel(U.win, b->stream);         // programmatic dependent launch: resident early, waits on the grid dependency
-  b->launches += 2;
-  b->acc_cur = 1 - b->acc_cur;
-  if (b->timing) CK(cudaEventRecord(b->ev[2], b->stream));
-  CK(cudaGetLastError());
   {
-    int rc = enqueue_exchange(b);
+    int rc = dmv_ba_enqueue_exchange(b);
     if (rc != DMV_OK) return rc;
   }
   if (!zero_copy)
@@ -509,14 +386,15 @@ static int finish_linearize(dmv_ba* b, dmv_ba_lin_result* out, double sums[3]) {
   if (b->timing) {
     cudaEventElapsedTime(&b->last_ms[0], b->ev[0], b->ev[3]);
     cudaEventElapsedTime(&b->last_ms[1], b->ev[0], b->ev[1]);
-    cudaEventElapsedTime(&b->last_ms[2], b->ev[1], b->ev[2]);
-    cudaEventElapsedTime(&b->last_ms[3], b->ev[2], b->ev[3]);
+    b->last_ms[2] = 0.f;
+    cudaEventElapsedTime(&b->last_ms[3], b->ev[1], b->ev[3]);
   }
+  if (tail[ACC_MISC - 1] != 0.0) return set_error(DMV_ERR_TIMEOUT, "grid barrier / peer exchange timed out inside ba_fused_kernel (a rank or CTA went missing)");
   b->have_tentative = true;
   return DMV_OK;
 }
 
-static int check_ready(dmv_ba* b) {
+int dmv_ba_check_ready(dmv_ba* b) {
   if (!b) return set_error(DMV_ERR_INVALID, "null handle");
   if (b->npts < 1 || b->nres < 0) return set_error(DMV_ERR_STATE, "points/residuals not set");
   if (!b->have_adj) return set_error(DMV_ERR_STATE, "dmv_ba_set_adjoints first");
@@ -525,16 +403,16 @@ static int check_ready(dmv_ba* b) {
 }
 
 int dmv_ba_linearize(dmv_ba* b, dmv_ba_lin_result* out) {
-  int rc = check_ready(b);
+  int rc = dmv_ba_check_ready(b);
   if (rc != DMV_OK) return rc;
   CK(cudaSetDevice(b->device));
   b->h_up->it.have_x = 0;
-  rc = enqueue_linearize(b, false);
+  rc = enqueue_linearize(b);
   if (rc != DMV_OK) return rc;
   return finish_linearize(b, out, nullptr);
 }
 
-static void stage_x(dmv_ba* b, const double* x) {
+void dmv_ba_stage_x(dmv_ba* b, const double* x) {
   // EnergyFunctional::resubstituteF_MT (EnergyFunctional.cpp:L272-283): xAd[h*nf+t] = x_h^T adHostF + x_t^T adTargetF in float
   BAIter& it = b->h_up->it;
   const int nf = b->nf;
@@ -554,13 +432,13 @@ static void stage_x(dmv_ba* b, const double* x) {
 }
 
 int dmv_ba_resubstitute(dmv_ba* b, const double* x, float* step_out, int apply, double sums[3]) {
-  int rc = check_ready(b);
+  int rc = dmv_ba_check_ready(b);
   if (rc != DMV_OK) return rc;
   if (!x) return set_error(DMV_ERR_INVALID, "x is null");
   if (!b->have_committed) return set_error(DMV_ERR_STATE, "no committed linearisation (linearize + apply_res first)");
   CK(cudaSetDevice(b->device));
-  stage_x(b, x);
-  fill_descriptor(b);
+  dmv_ba_stage_x(b, x);
+  dmv_ba_fill_descriptor(b);
   CK(cudaMemsetAsync(b->d_resub_sums, 0, sizeof(double) * 4, b->stream));
   launch_resub_kernel(b->h_up->win, b->h_up->it, apply, b->d_resub_sums, b->stream);
   b->launches += 1;
@@ -583,8 +461,8 @@ int dmv_ba_gn_step(dmv_ba* b, const double* x, const dmv_ba_state* st, dmv_ba_li
   CK(cudaSetDevice(b->device));
   int rc = stage_state(b, st);
   if (rc != DMV_OK) return rc;
-  if (x) stage_x(b, x); else b->h_up->it.have_x = 0;
-  rc = enqueue_linearize(b, x != nullptr);
+  if (x) dmv_ba_stage_x(b, x); else b->h_up->it.have_x = 0;
+  rc = enqueue_linearize(b);
   if (rc != DMV_OK) return rc;
   rc = finish_linearize(b, out, sums);
   b->h_up->it.have_x = 0;
@@ -699,18 +577,17 @@ int dmv_ba_drop_residuals(dmv_ba* b, int n, const int32_t* res_idx) {
 }
 
 int dmv_ba_marginalize_points(dmv_ba* b, const dmv_ba_marg_args* a) {
-  int rc = check_ready(b);
+  int rc = dmv_ba_check_ready(b);
   if (rc != DMV_OK) return rc;
   if (!a || a->n < 0 || (a->n > 0 && !a->point) || !a->adHTdeltaF) return set_error(DMV_ERR_INVALID, "null argument");
   if (b->nranks > 1) return set_error(DMV_ERR_STATE, "sharded handle: marginalise per rank and sum (M - Msc) on the host");
   CK(cudaSetDevice(b->device));
   const int nf = b->nf, N = b->N;
-  const size_t nacc = acc_doubles(nf, b->ntiles), nres_d = result_doubles(N, b->ntiles), nslots = (size_t)MAXF * b->mp;
+  const size_t nres_d = result_doubles(N, b->ntiles), nslots = (size_t)MAXF * b->mp;
   if (!b->d_marg) {
     CK(cudaMalloc(&b->d_marg, sizeof(BAMarg)));
     CK(cudaMalloc(&b->d_marg_mask, b->mp));
     CK(cudaMalloc(&b->d_marg_rtz, sizeof(float) * 8 * nslots));
-    CK(cudaMalloc(&b->d_marg_acc, sizeof(double) * 2 * b->acc_cap));
     const size_t maxres = result_doubles(8 * MAXF + 4, ((2 * MAXF + 2) * (2 * MAXF + 3)) / 2);
     CK(cudaMalloc(&b->d_marg_result, sizeof(double) * maxres));
     CK(cudaHostAlloc(&b->h_marg_result, sizeof(double) * maxres, cudaHostAllocDefault));
@@ -730,21 +607,16 @@ int dmv_ba_marginalize_points(dmv_ba* b, const dmv_ba_marg_args* a) {
   CK(cudaMemcpyAsync(b->d_marg, &M, sizeof(M), cudaMemcpyHostToDevice, b->stream));
   CK(cudaMemcpyAsync(b->d_marg_mask, mask.data(), b->mp, cudaMemcpyHostToDevice, b->stream));
   CK(cudaMemsetAsync(b->d_marg_rtz, 0, sizeof(float) * 8 * nslots, b->stream));
-  CK(cudaMemsetAsync(b->d_marg_acc, 0, sizeof(double) * nacc, b->stream));
-  // descriptor: the production one with private accumulators / result blob, no fused step, no exchange
+  // descriptor: the production one with a private result blob, no fused step, no exchange
   b->h_up->it.have_x = 0;
-  fill_descriptor(b);
+  dmv_ba_fill_descriptor(b);
   BAWinDev& W = b->h_up->win;
-  W.acc = b->d_marg_acc;
-  W.acc_next = b->d_marg_acc + b->acc_cap;
   W.result = b->d_marg_result;
   W.result_host = nullptr;
   W.xc.nranks = 1;
   W.marg = b->d_marg; W.marg_mask = b->d_marg_mask; W.marg_rtz = b->d_marg_rtz;
-  launch_point_kernel_marg(W, b->h_up->it, b->stream);
-  launch_stitch_kernel(W, b->stream);
-  b->launches += 2;
-  CK(cudaGetLastError());
+  CK(launch_fused_kernel(W, b->h_up->it, true, b->stream, &b->bar_count));
+  b->launches += 1;
   CK(cudaMemcpyAsync(b->h_marg_result, b->d_marg_result, sizeof(double) * nres_d, cudaMemcpyDeviceToHost, b->stream));
   std::vector<uint8_t> st(nslots);
   std::vector<float> rtz;
@@ -855,52 +727,6 @@ int dmv_ba_kernel_launch_count(dmv_ba* b, long long* n) {
   return DMV_OK;
 }
 
-int dmv_ba_bench_device(dmv_ba* b, const double* x, int iters, int flush_l2, float* ms_per_iter, float* ms_point_kernel) {
-  int rc = check_ready(b);
-  if (rc != DMV_OK) return rc;
-  if (iters < 1 || iters > 4096) return set_error(DMV_ERR_INVALID, "iters out of range");
-  if (x && !b->have_committed) return set_error(DMV_ERR_STATE, "no committed linearisation to resubstitute");
-  CK(cudaSetDevice(b->device));
-  if (flush_l2 && !b->d_flush) {
-    b->flush_n = (size_t)256 * 1024 * 1024 / sizeof(float4);  // 256 MiB > 126 MB L2
-    CK(cudaMalloc(&b->d_flush, b->flush_n * sizeof(float4)));
-    CK(cudaMemset(b->d_flush, 0, b->flush_n * sizeof(float4)));
-  }
-  if (x) stage_x(b, x); else b->h_up->it.have_x = 0;
-  std::vector<cudaEvent_t> e(3 * (size_t)iters);
-  for (auto& ev : e) CK(cudaEventCreate(&ev));
-  for (int i = 0; i < iters; i++) {
-    if (flush_l2) launch_l2_flush(b->d_flush, b->flush_n, b->stream);
-    fill_descriptor(b);
-    next_exchange(b);
-    const HostUpload& U = *b->h_up;
-    CK(cudaEventRecord(e[3 * i], b->stream));
-    launch_point_kernel(U.win, U.it, b->stream);
-    launch_stitch_kernel(U.win, b->stream);
-    CK(cudaEventRecord(e[3 * i + 1], b->stream));
-    b->acc_cur = 1 - b->acc_cur;
-    rc = enqueue_exchange(b);
-    if (rc != DMV_OK) return rc;
-    CK(cudaEventRecord(e[3 * i + 2], b->stream));
-    b->launches += 2;
-  }
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(b->stream));
-  double tot = 0, pk = 0;
-  for (int i = 0; i < iters; i++) {
-    float a = 0, c = 0;
-    cudaEventElapsedTime(&a, e[3 * i], e[3 * i + 2]);
-    cudaEventElapsedTime(&c, e[3 * i], e[3 * i + 1]);
-    tot += a; pk += c;
-  }
-  for (auto& x : e) cudaEventDestroy(x);
-  if (ms_per_iter) *ms_per_iter = (float)(tot / iters);
-  if (ms_point_kernel) *ms_point_kernel = (float)(pk / iters);
-  b->h_up->it.have_x = 0;
-  b->have_tentative = true;
-  return DMV_OK;
-}
-
 int dmv_nccl_unique_id(void* id128) { return dmv::nccl_unique_id(id128); }
 
 int dmv_ba_comm_init(dmv_ba* b, int nranks, int rank, const void* id) {
@@ -1007,37 +833,9 @@ extern "C" int dmv_ba_io_bytes(dmv_ba* b, long long* h2d, long long* d2h) {
   return DMV_OK;
 }
 
-extern "C" int dmv_ba_debug_clocks(dmv_ba* b, unsigned long long* out, int cap) {
-  if (!b || !out) return set_error(DMV_ERR_INVALID, "null argument");
-  const int n = std::min(cap, 16 * (b->nchunks + b->nf + 1));  // point-kernel CTAs, then the stitch CTAs
-  CK(cudaSetDevice(b->device));
-  CK(cudaMemcpy(out, b->d_dbg_clk, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
-  return n;
-}
-
 extern "C" int dmv_ba_set_timing(dmv_ba* b, int enable) {
   if (!b) return set_error(DMV_ERR_INVALID, "null handle");
   b->timing = enable != 0;
   return DMV_OK;
 }
 
-// End-to-end timing of the public call sequence a DM-VIO host makes per GN iteration, from C (no interpreter in the loop):
-// iters x { dmv_ba_gn_step(x, st) ; dmv_ba_apply_res() } with host buffers in and H/b out, wall clock (steady_clock).
-#include <chrono>
-extern "C" int dmv_ba_bench_e2e(dmv_ba* b, const double* x, const dmv_ba_state* st, int iters, double* ms_per_iter) {
-  if (!b || !st || !ms_per_iter || iters < 1) return set_error(DMV_ERR_INVALID, "bad argument");
-  dmv_ba_lin_result r;
-  double sums[3];
-  CK(cudaSetDevice(b->device));
-  CK(cudaStreamSynchronize(b->stream));
-  const auto t0 = std::chrono::steady_clock::now();
-  for (int i = 0; i < iters; i++) {
-    int rc = dmv_ba_gn_step(b, x, st, &r, sums);
-    if (rc != DMV_OK) return rc;
-    rc = dmv_ba_apply_res(b);
-    if (rc != DMV_OK) return rc;
-  }
-  const auto t1 = std::chrono::steady_clock::now();
-  *ms_per_iter = std::chrono::duration<double, std::milli>(t1 - t0).count() / iters;
-  return DMV_OK;
-}

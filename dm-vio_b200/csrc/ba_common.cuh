@@ -40,8 +40,8 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 __device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); }  // result unused -> RED.E.ADD.F64
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define STAMP(k) do { if ((W.dbg & 16) && threadIdx.x == 0) W.dbg_clk[(size_t)blockIdx.x * 16 + (k)] = gtime(); } while (0)
-#define RED_ADD(p, v) do { if (!(W.dbg & 1)) red_add((p), (v)); } while (0)
+
+
 
 // EnergyFunctional::resubstituteFPt for one point (EnergyFunctional.cpp:L295-321)
 __device__ __forceinline__ float resub_point(const BAWinDev& W, const BAIter& it, int p, int h) {

@@ -16,9 +16,15 @@ constexpr int TOP_TRI = 85;                        // sum_{r=0}^{9} (13 - r)
 constexpr int TOP_USED = TOP_TRI + 6;              // 91
 constexpr int TOP_PART = 92;
 __host__ __device__ constexpr int top_off(int r) { return r * TOP_COLS - (r * (r - 1)) / 2; }  // offset of entry (r, r); entry (r, c>=r) = top_off(r) + c - r
-constexpr int REC = 16;             // per (point,target) record kept in shared memory
 constexpr int RES_NONE = 255, RES_IN = 0, RES_OOB = 1, RES_OUTLIER = 2;
-constexpr int ACC_MISC = 8;         // energy, n_in, n_oob, n_outlier, sum step^2, sum |idepth_backup|, npts, pad
+constexpr int ACC_MISC = 8;         // energy, n_in, n_oob, n_outlier, sum step^2, sum |idepth_backup|, npts, error flag (barrier / peer timeout)
+// Partial blob of one chunk (P points of host frame h), fp64, written by phase C of ba_fused_kernel with plain stores and summed in a
+// fixed order by phase D.  Per frame slot t: [O 64 | D 64 | C 32 | b 8]: t != h: O = contribution to H[h,t], D to H[t,t], C to H[t,C],
+// b to b[t]; t == h: D to H[h,h], C to H[h,C], b to b[h] (O unused).  Then H[C,C] (16), b[C] (4), the ACC_MISC counters.
+constexpr int PART_SLOT = 168;
+constexpr int PART_CC = MAXF * PART_SLOT;
+constexpr int PART_MISC = PART_CC + 20;
+constexpr int PART_STRIDE = PART_MISC + ACC_MISC;
 
 // per-iteration parameter block
 struct BAIter {
@@ -60,8 +66,6 @@ struct BAWinDev {
   int nf, npts, nchunks, w, h, N, NW, T, ntiles, mp, P;  // mp = capacity (row pitch of the [target][point] slot arrays)
   float huberTH, outlierTHSum;
   int zeroA, zeroB;
-  int iter2;                 // experiment: 2 quads per warp (half the warps) for P = 16
-  int dbg;                   // DMV_DBG experiment mask (bit0: skip global REDs, bit1: skip phase C, bit2: skip image gathers); 0 in production
   int host_start[MAXF + 1];  // points of host h are [host_start[h], host_start[h+1])
   int chunk_beg[MAXF + 1];   // chunks (CTAs) of host h are [chunk_beg[h], chunk_beg[h+1]); chunk c covers P consecutive points
   const float4* img[MAXF];   // per window frame index: level-0 texels (I, dx, dy, 0)
@@ -89,14 +93,14 @@ struct BAWinDev {
   const float* c_jpjd;
   const float* c_pout;
   float* step;               // [p]
-  // fp64 accumulators: [nf*nf*TOP_PART top | ntiles*16 schur tiles | ACC_MISC | dense H N*N | b N]
-  double* acc;               // accumulated into by this iteration's point kernel, consumed by its stitch kernel
-  double* acc_next;          // zeroed by this iteration's stitch kernel for the next iteration
-  unsigned long long* dbg_clk; // [chunk][8] phase timestamps (globaltimer ns) when dbg & 16
-  unsigned int* ticket;      // [0] CTA completion counter, [1+h] per-host counters (last CTA of a host / overall stitches); self-resetting
-  double* stage;             // scratch of the stitch: per pair B|G|GA (272 doubles) + per host 20 calibration sums
+  // scratch of one launch (never read by the host)
+  double* part;              // [chunk][PART_STRIDE] partial blobs
+  float4* wg;                // [4-column group][mp] Schur vectors w_p, transposed
+  float* hdig;               // [p] HdiF
+  unsigned int* bar;         // grid-barrier arrival counter (monotonic)
+  unsigned int bar_target;   // arrivals expected once every CTA of THIS launch has arrived
   double* result;            // H_top N*N | b_top N | Schur tiles ntiles*16 | ACC_MISC tail
-  double* result_host;       // pinned host mirror of the result blob written by the stitch kernel itself (zero-copy), or nullptr
+  double* result_host;       // pinned host mirror of the result blob written by the kernel itself (zero-copy), or nullptr
   BAXchg xc;                 // nranks <= 1: no exchange
   // marginalisation launch only (nullptr otherwise)
   const BAMarg* marg;
@@ -106,7 +110,5 @@ struct BAWinDev {
 
 // result blob: H_top N*N | b_top N | raw Schur Gram tiles ntiles*16 | ACC_MISC counters
 inline __host__ __device__ int result_doubles(int N, int ntiles) { return N * N + N + ntiles * 16 + ACC_MISC; }
-// accumulators: pair blocks nf*nf*TOP_PART | Schur tiles ntiles*16 | ACC_MISC | dense H (N*N) | b (N)
-inline __host__ __device__ int acc_doubles(int nf, int ntiles) { return nf * nf * TOP_PART + ntiles * 16 + ACC_MISC; }
 
 }  // namespace dmv

@@ -1,0 +1,750 @@
+// ba_fused_kernel — one launch = one Gauss-Newton linearisation of the whole window:
+//   FullSystem::linearizeAll (FullSystemOptimize.cpp:L150-218) + EFResidual::takeDataF + AccumulatedTopHessianSSE::addPoint<0/2> +
+//   AccumulatedSCHessianSSE::addPoint + both stitchDouble passes (AccumulatedTopHessian.cpp:L241-303, AccumulatedSCHessian.cpp:L78-157)
+//   + the point half of resubstituteF_MT / doStepFromBackup of the PREVIOUS iteration (EnergyFunctional.cpp:L295-321).
+//
+// B200 design: ONE THREAD PER POINT-RESIDUAL.  A residual is a ~1000-instruction chain whose reductions over the 8 pattern pixels
+// stay in registers (no shuffles, nothing per-residual is computed twice), and the 16 / 32 residuals of one (host, target) pair sit in
+// adjacent lanes, so the pair's 13x13 block is reduced with a transposing butterfly (96 exchanges per pair instead of 96 x log2 P).
+//
+//   chunk    P consecutive points of one host frame h; CTA = P x (nf-1) threads, lane = point, (half-)warp = target frame
+//   phase A  per thread: optional fused resubstitute + step, PointFrameResidual::linearize (Residuals.cpp:L78-274): FEJ centre
+//            projection, 8 pattern pixels x 4 float4 taps, Huber, classification; per-residual outputs; JpJdF; the residual's 91
+//            AccumulatorApprox entries (MatrixAccumulators.h:L754-915) summed over the pair's lanes -> shared memory
+//   phase B  per point: Hdd / bd / Hcd, HdiF, bdSum (AccumulatedSCHessian.cpp:L36-58) and its Schur vector in ABSOLUTE frame
+//            coordinates w_p = [Hcd | sum_t adHost JpJdF_t | adTarget JpJdF_t ... | bdSum]  -> global (transposed for phase E)
+//   phase C  the chunk's pair blocks pushed through the adjoints IN THE CTA (fp64): contributions to H[h,h], H[h,t], H[t,t], H[.,C], b
+//            are written to the chunk's partial blob with plain coalesced stores — no atomics, no accumulators to zero
+//   -------- grid barrier (cooperative launch; every CTA is resident) --------
+//   phase D  every final entry of H_top / b_top = fixed-order fp64 sum of the chunk partials that touch it: a warp per entry
+//   phase E  Schur complement [H_sc | b_sc] = sum_p HdiF w_p w_p^T as 4x4 tiles, one CTA per tile over ALL points (replaces the nf^3
+//            accD blocks and their stitch)
+//   every result entry has exactly one producing warp, which also streams it into the caller's pinned host buffer and, on a sharded
+//   window, exchanges it with the peer GPUs (LL packets over NVLink peer memory, bounded spin).
+// Results are bit-reproducible run to run (no atomics anywhere on the data path).
+#include "ba_common.cuh"
+#include <mutex>
+#include <type_traits>
+
+namespace dmv {
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// compile-time helpers
+// ---------------------------------------------------------------------------------------------------------------------------
+template <int K, int END, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (K < END) {
+    f(std::integral_constant<int, K>{});
+    static_for<K + 1, END>(f);
+  }
+}
+__host__ __device__ constexpr int top_row(int k) {  // packed upper-triangular index (rows 0..9, columns r..12) -> row
+  int r = 0;
+  while (r < 9 && k >= top_off(r + 1)) r++;
+  return r;
+}
+__host__ __device__ constexpr int top_col(int k) { return top_row(k) + k - top_off(top_row(k)); }
+
+struct PixSums {  // the 2x2 / 2x1 sums of RawResidualJacobian (RawResidualJacobian.h:L49-59) + right-hand sides
+  float JI00, JI10, JI11, JabJI00, JabJI01, JabJI10, JabJI11, Jab00, Jab01, Jab11, JIr0, JIr1, Jabr0, Jabr1, rr;
+};
+
+// entry K of the residual's contribution to the pair's symmetric 13x13 block [C4 | xi6 | a b | r]
+template <int K>
+__device__ __forceinline__ float top_entry(const float (&x)[10], const float (&y)[10], const float (&al)[10], const float (&be)[10], const PixSums& s) {
+  if constexpr (K < TOP_TRI) {
+    constexpr int r = top_row(K), c = top_col(K);
+    if constexpr (c < 10) return al[r] * x[c] + be[r] * y[c];
+    else if constexpr (c == 10) return x[r] * s.JabJI00 + y[r] * s.JabJI01;
+    else if constexpr (c == 11) return x[r] * s.JabJI10 + y[r] * s.JabJI11;
+    else return x[r] * s.JIr0 + y[r] * s.JIr1;
+  } else if constexpr (K == TOP_TRI) return s.Jab00;
+  else if constexpr (K == TOP_TRI + 1) return s.Jab01;
+  else if constexpr (K == TOP_TRI + 2) return s.Jabr0;
+  else if constexpr (K == TOP_TRI + 3) return s.Jab11;
+  else if constexpr (K == TOP_TRI + 4) return s.Jabr1;
+  else if constexpr (K == TOP_TRI + 5) return s.rr;
+  else return 0.f;
+}
+
+// (r, c) of the symmetric 13x13 block from the packed float layout
+__device__ __forceinline__ float h13f(const float* S, int r, int c) {
+  if (r > c) { const int t = r; r = c; c = t; }
+  if (r < TOP_ROWS) return S[top_off(r) + c - r];
+  const int rr = r - 10, cc = c - 10;
+  return S[TOP_TRI + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5))];
+}
+
+// geometric Jacobians of the centre pixel (Residuals.cpp:L113-156): x = d(Ku)/d[C4|xi6], y = d(Kv)/d[C4|xi6], dd = d(Ku,Kv)/d(idepth)
+__device__ __forceinline__ void geo_jac(const float* pc, float Kl0, float Kl1, float cu, float cv, float drescale, float new_idepth, float fx,
+                                        float fy, float fxi, float fyi, float (&x)[10], float (&y)[10], float& ddx, float& ddy) {
+  const float dCx2 = drescale * (pc[18] * cu - pc[12]);
+  const float dCx3 = fx * drescale * (pc[19] * cu - pc[13]) * fyi;
+  const float dCy2 = fy * drescale * (pc[18] * cv - pc[15]) * fxi;
+  const float dCy3 = drescale * (pc[19] * cv - pc[16]);
+  x[0] = (Kl0 * dCx2 + cu) * 50.0f; x[1] = (Kl1 * dCx3) * 50.0f; x[2] = (dCx2 + 1.f) * 50.0f; x[3] = dCx3 * 50.0f;
+  y[0] = (Kl0 * dCy2) * 50.0f; y[1] = (Kl1 * dCy3 + cv) * 50.0f; y[2] = dCy2 * 50.0f; y[3] = (dCy3 + 1.f) * 50.0f;
+  x[4] = new_idepth * fx; x[5] = 0.f; x[6] = -new_idepth * cu * fx; x[7] = -cu * cv * fx; x[8] = (1.f + cu * cu) * fx; x[9] = -cv * fx;
+  y[4] = 0.f; y[5] = new_idepth * fy; y[6] = -new_idepth * cv * fy; y[7] = -(1.f + cv * cv) * fy; y[8] = cu * cv * fy; y[9] = cu * fy;
+  ddx = drescale * (pc[21] - pc[23] * cu) * fx;  // Jpdd (SCALE_IDEPTH = 1)
+  ddy = drescale * (pc[22] - pc[23] * cv) * fy;
+}
+
+template <int P>
+struct FusedSmem {
+  double AhD[MAXF][64];        // adHost(h, t) fp64, row-major, slot = target frame
+  double dT[MAXF][8];          // diag adTarget(h, t)
+  double G[MAXF][104];         // adHost * [P | Q | p]
+  float adH[MAXF][64];         // fp32 copies used for the Schur vector (the reference's adHostF / adTargetF)
+  float adT[MAXF][8];
+  float pair[MAXF][96];        // the chunk's pair blocks (91 used), slot = target frame
+  float rec[MAXF][16][P];      // per target: adHost*JpJdF [8], Hdd, bd, Hcd[4], active, pad   (lane = point: conflict-free)
+  float Wv[P][8 * MAXF + 8];   // Schur vectors
+  float hdi[P];
+  float id[P], idz[P];
+  float misc[8][8];            // per warp: energy, n_in, n_oob, n_outlier, step^2, |idepth_backup|, count
+  double red[8][16];           // phase E: per-warp tile partials
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// all CTAs of the (cooperative) grid; monotonic arrival counter, target = arrivals expected so far.  Bounded: a lost CTA can delay the
+// launch by ~0.1 s but never hang the GPU (the result then carries the error flag).
+__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned target) {
+  __shared__ int ok_s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    int ok = 1;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_u32(bar) - target) < 0) {
+      if (clock64() - t0 > 200000000ll) { ok = 0; break; }
+    }
+    __threadfence();
+    ok_s = ok;
+  }
+  __syncthreads();
+  return ok_s != 0;
+}
+
+// ---- exchange of result entries between ranks (sharded BA): "LL" packets over NVLink peer memory.  Every result
+// entry has one producing warp (the same on every rank): it pushes the entry as a 16-byte packet {lo, seq, hi, seq} into slot
+// [parity][my rank][entry] of every peer's inbox (st.volatile.v4: each 8-byte half carries its own flag, no fence, no separate flag
+// round trip), later polls its OWN inbox until the peers' packets of that entry carry this exchange's sequence number and adds them in
+// RANK ORDER (bit-identical sums on every rank).  Double-buffered by parity; the poll is bounded (a dead peer yields an error flag).
+__device__ __forceinline__ void xchg_push(const BAXchg& X, int idx, double v) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  const uint4 pk = make_uint4((unsigned)(u & 0xffffffffull), X.seq, (unsigned)(u >> 32), X.seq);
+  const size_t off = (size_t)(((X.seq & 1u) * XCHG_MAXR + X.rank)) * X.pitch + idx;
+#pragma unroll 1
+  for (int k = 1; k < X.nranks; k++) {
+    const int r = (X.rank + k) % X.nranks;  // start with the neighbour: spreads the NVSwitch ports
+    uint4* dst = X.inbox[r] + off;
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+  }
+}
+__device__ __forceinline__ double xchg_pull_sum(const BAXchg& X, int idx, double mine, bool& ok) {
+  const uint4* base = X.inbox[X.rank] + (size_t)((X.seq & 1u) * XCHG_MAXR) * X.pitch + idx;
+  uint4 pk[XCHG_MAXR];
+  unsigned pending = ((1u << X.nranks) - 1u) & ~(1u << X.rank);
+  const long long t0 = clock64();
+  while (pending) {
+#pragma unroll
+    for (int r = 0; r < XCHG_MAXR; r++)
+      if ((pending >> r) & 1u) {
+        const uint4* src = base + (size_t)r * X.pitch;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[r].x), "=r"(pk[r].y), "=r"(pk[r].z), "=r"(pk[r].w) : "l"(src) : "memory");
+      }
+#pragma unroll
+    for (int r = 0; r < XCHG_MAXR; r++)
+      if (((pending >> r) & 1u) && pk[r].y == X.seq && pk[r].w == X.seq) pending &= ~(1u << r);
+    if (pending && clock64() - t0 > 400000000ll) { ok = false; return mine; }  // ~0.2 s: peer lost
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int r = 0; r < XCHG_MAXR; r++) {
+    if (r >= X.nranks) break;
+    s += (r == X.rank) ? mine : __longlong_as_double((long long)(((unsigned long long)pk[r].z << 32) | pk[r].x));
+  }
+  return s;
+}
+
+// MARG = true is the marginalisation launch (dmv_ba_marginalize_points): only the points flagged in W.marg_mask take part, their
+// residuals are re-linearised from scratch (PointFrameResidual::resetOOB; FullSystem.cpp:L826-838), EFResidual::fixLinearizationF
+// (EnergyFunctionalStructs.cpp:L88-114) turns resF into res_toZeroF, and the accumulation is AccumulatedTopHessian::addPoint<2> +
+// AccumulatedSCHessian::addPoint(p, shiftPriorToZero = false) with priorF * idepthFixPriorMargFac (EnergyFunctional.cpp:L678-742).
+template <int P, bool MARG>
+__global__ void __launch_bounds__(P == 32 ? 224 : 128, P == 32 ? 2 : 4)
+    ba_fused_kernel(const __grid_constant__ BAWinDev W, const __grid_constant__ BAIter it) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FusedSmem<P>& S = *reinterpret_cast<FusedSmem<P>*>(smem_raw);
+  constexpr int LOGP = (P == 32) ? 5 : 4;
+  const int nf = W.nf, N = W.N, mp = W.mp;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  const BAAdj* __restrict__ A = W.adj;
+
+#pragma unroll 1
+  for (int chunk = blockIdx.x; chunk < W.nchunks; chunk += gridDim.x) {
+    int h = 0;  // host frame of this chunk: branch-free so that the constant-bank loads are independent
+#pragma unroll
+    for (int k = 1; k < MAXF; k++) h += (chunk >= W.chunk_beg[k]) ? 1 : 0;
+    h = min(h, nf - 1);
+    const int ch_start = W.host_start[h] + (chunk - W.chunk_beg[h]) * P;
+    const int ch_count = min(P, W.host_start[h + 1] - ch_start);
+
+    // ---- stage the host's adjoint blocks (fp64 for phase C, fp32 for the Schur vectors); waited for at the first block barrier,
+    // except the fp32 block of a warp's own pair(s), which the warp fetches itself below
+    for (int i = tid; i < nf * 32; i += nthreads) cp_async16(&S.AhD[i >> 5][(i & 31) * 2], &A->adHost[h * nf + (i >> 5)][(i & 31) * 2]);
+    for (int i = tid; i < nf * 4; i += nthreads) cp_async16(&S.dT[i >> 2][(i & 3) * 2], &A->adTdiag[h * nf + (i >> 2)][(i & 3) * 2]);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // ---------------------------------------------------------------- phase A: one thread = one point-residual
+    const int r = tid >> LOGP, pl = tid & (P - 1);  // r-th target frame other than h
+    const int t = r + (r >= h ? 1 : 0);
+    const bool slot_ok = r < nf - 1;
+    float e_sum = 0.f, rs_step2 = 0.f, rs_nid = 0.f, rs_cnt = 0.f;
+    int n_in = 0, n_oob = 0, n_outl = 0;
+    if ((warp << 5 >> LOGP) < nf - 1) {  // warp-uniform: this warp owns at least one pair
+      const int tc = slot_ok ? t : (h == 0 ? 1 : 0);  // idle half-warps shadow a valid pair (loads stay in bounds, nothing is written)
+      if (slot_ok) {  // the pair's fp32 adjoints: fetched by the lanes that use them (no block barrier before phase A's tail)
+        if (pl < 16) *reinterpret_cast<float4*>(&S.adH[t][pl * 4]) = __ldg(reinterpret_cast<const float4*>(&A->adHostF[h * nf + t][pl * 4]));
+        if (pl < 2) *reinterpret_cast<float4*>(&S.adT[t][pl * 4]) = __ldg(reinterpret_cast<const float4*>(&A->adTdiagF[h * nf + t][pl * 4]));
+      }
+      const bool valid = slot_ok && pl < ch_count;
+      const int p = ch_start + min(pl, ch_count - 1);
+      const int slot = tc * mp + p;
+      const float* pc = it.precalc[h * nf + tc];
+      const float fx = it.calib[0], fy = it.calib[1], cx = it.calib[2], cy = it.calib[3];
+      const float fxi = it.calib[4], fyi = it.calib[5];
+      const float TH = fmaxf(it.TH[h], it.TH[tc]);
+      const float wM3 = (float)(W.w - 3), hM3 = (float)(W.h - 3);
+      const float4* __restrict__ img = W.img[tc];
+      const int iw = W.w;
+      const float huber = W.huberTH, oth = W.outlierTHSum;
+
+      // ---- direct loads (all independent: one memory round trip)
+      int st = valid ? (int)__ldg(W.st_in + slot) : RES_NONE;
+      float en_old = __ldg(W.en_in + slot);
+      bool masked = true;
+      if constexpr (MARG) {  // resetOOB: every existing residual of a flagged point starts as IN with zero energy; other points sit out
+        masked = valid && __ldg(W.marg_mask + p) != 0;
+        st = (masked && st != RES_NONE) ? RES_IN : RES_NONE;
+        en_old = 0.f;
+      }
+      const float2 uv = __ldg(W.uv + p);
+      float col[8], wgt[8];
+      {
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(W.color + (size_t)p * 8)), c1 = __ldg(reinterpret_cast<const float4*>(W.color + (size_t)p * 8) + 1);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(W.weights + (size_t)p * 8)), w1 = __ldg(reinterpret_cast<const float4*>(W.weights + (size_t)p * 8) + 1);
+        col[0] = c0.x; col[1] = c0.y; col[2] = c0.z; col[3] = c0.w; col[4] = c1.x; col[5] = c1.y; col[6] = c1.z; col[7] = c1.w;
+        wgt[0] = w0.x; wgt[1] = w0.y; wgt[2] = w0.z; wgt[3] = w0.w; wgt[4] = w1.x; wgt[5] = w1.y; wgt[6] = w1.z; wgt[7] = w1.w;
+      }
+      float idepth, idz;
+      if (it.have_x) {
+        // fused EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:L295-321) + point step (FullSystemOptimize.cpp:L264-272): every
+        // thread of the point recomputes the same step from the committed linearisation (loads hit L1/L2), the first target's publishes
+        const float4 po0 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8));
+        const float4 po1 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8) + 1);
+        const float idb = __ldg(W.idepth_backup + p);
+        float b = po1.w - (it.xc[0] * po0.z + it.xc[1] * po0.w + it.xc[2] * po1.x + it.xc[3] * po1.y);
+        int ngood = 0;
+#pragma unroll
+        for (int tt = 0; tt < MAXF; tt++) {
+          if (tt >= nf || tt == h) continue;
+          const int cs = tt * mp + p;
+          if (__ldg(W.c_st + cs) != RES_IN) continue;
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8) + 1);
+          const float* xa = it.xAd[h * nf + tt];
+          b -= xa[0] * a0.x + xa[1] * a0.y + xa[2] * a0.z + xa[3] * a0.w + xa[4] * a1.x + xa[5] * a1.y + xa[6] * a1.z + xa[7] * a1.w;
+          ngood++;
+        }
+        const float step = ngood > 0 ? -b * po1.z : 0.f;
+        idepth = idb + step;
+        idz = idepth;  // DM-VIO: idepth_zero follows (setIdepthZero in doStepFromBackup); the host aliases the pointers
+        if (r == 0 && valid) {
+          W.step[p] = step;
+          W.idepth_out[p] = idepth;
+          rs_step2 = step * step; rs_nid = fabsf(idb); rs_cnt = 1.f;
+        }
+      } else {
+        idepth = __ldg(W.idepth + p);
+        idz = __ldg(W.idepth_zero + p);
+      }
+      if (r == 0 && valid) { S.id[pl] = idepth; S.idz[pl] = idz; }
+      bool live = (st != RES_NONE) && (st != RES_OOB);
+
+      // ---- centre pixel at the FEJ point (ResidualProjections.h:L62-87, Residuals.cpp:L108-157)
+      const float Kl0 = (uv.x - cx) * fxi, Kl1 = (uv.y - cy) * fyi;
+      const float q2 = pc[18] * Kl0 + pc[19] * Kl1 + pc[20] + pc[23] * idz;
+      const float drescale = 1.0f / q2;
+      const float new_idepth = idz * drescale;
+      const float cu = (pc[12] * Kl0 + pc[13] * Kl1 + pc[14] + pc[21] * idz) * drescale;
+      const float cv = (pc[15] * Kl0 + pc[16] * Kl1 + pc[17] + pc[22] * idz) * drescale;
+      const float cKu = cu * fx + cx, cKv = cv * fy + cy;
+      live = live && (drescale > 0.f) && cKu > 1.1f && cKv > 1.1f && cKu < wM3 && cKv < hM3;
+
+      // ---- the 8 pattern pixels at the current state (ResidualProjections.h:L47-57): all must project inside the image
+      float Ku[8], Kv[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float pu = uv.x + (float)c_pattern[j][0], pv = uv.y + (float)c_pattern[j][1];
+        const float r2 = pc[6] * pu + pc[7] * pv + pc[8] + pc[11] * idepth;
+        Ku[j] = (pc[0] * pu + pc[1] * pv + pc[2] + pc[9] * idepth) / r2;
+        Kv[j] = (pc[3] * pu + pc[4] * pv + pc[5] + pc[10] * idepth) / r2;
+        live = live && Ku[j] > 1.1f && Kv[j] > 1.1f && Ku[j] < wM3 && Kv[j] < hM3;
+      }
+      float x[10], y[10], ddx = 0.f, ddy = 0.f, jpx = 0.f, jpy = 0.f, dp6 = 0.f, dp7 = 0.f;
+      if constexpr (MARG) {  // fixLinearizationF needs the geometric Jacobians per pixel: res_toZeroF = resF - J * delta
+        if (live) {
+          geo_jac(pc, Kl0, Kl1, cu, cv, drescale, new_idepth, fx, fy, fxi, fyi, x, y, ddx, ddy);
+          const float* dp = W.marg->adHTdelta[h * nf + tc];
+          const float* cD = W.marg->cDelta;
+          const float dlt = idepth - idz;  // EFPoint::deltaF
+          jpx = (x[4] * dp[0] + x[5] * dp[1] + x[6] * dp[2] + x[7] * dp[3] + x[8] * dp[4] + x[9] * dp[5]) +
+                (x[0] * cD[0] + x[1] * cD[1] + x[2] * cD[2] + x[3] * cD[3]) + ddx * dlt;
+          jpy = (y[4] * dp[0] + y[5] * dp[1] + y[6] * dp[2] + y[7] * dp[3] + y[8] * dp[4] + y[9] * dp[5]) +
+                (y[0] * cD[0] + y[1] * cD[1] + y[2] * cD[2] + y[3] * cD[3]) + ddy * dlt;
+          dp6 = dp[6]; dp7 = dp[7];
+        }
+      }
+
+      // ---- getInterpolatedElement33 (util/globalFuncs.h:L103-118), photometric residual, gradient weight, Huber (Residuals.cpp:L194-258)
+      PixSums s = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float energy = 0.f, wJI2 = 0.f, rtz[8];
+      if (live) {
+        const bool zA = W.zeroA != 0, zB = W.zeroB != 0;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {  // 16 float4 taps in flight per thread, twice
+        float4 tap[4][4];
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          const int j = half * 4 + jj;
+          const int ix = (int)Ku[j], iy = (int)Kv[j];
+          const float4* bp = img + (size_t)iy * iw + ix;
+          tap[jj][0] = __ldg(bp); tap[jj][1] = __ldg(bp + 1); tap[jj][2] = __ldg(bp + iw); tap[jj][3] = __ldg(bp + iw + 1);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          const int j = half * 4 + jj;
+          const int ix = (int)Ku[j], iy = (int)Kv[j];
+          const float dx = Ku[j] - ix, dy = Kv[j] - iy, dxdy = dx * dy;
+          const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+          const float h0 = w11 * tap[jj][3].x + w10 * tap[jj][2].x + w01 * tap[jj][1].x + w00 * tap[jj][0].x;
+          const float h1 = w11 * tap[jj][3].y + w10 * tap[jj][2].y + w01 * tap[jj][1].y + w00 * tap[jj][0].y;
+          const float h2 = w11 * tap[jj][3].z + w10 * tap[jj][2].z + w01 * tap[jj][1].z + w00 * tap[jj][0].z;
+          live = live && isfinite(h0);
+          const float residual = h0 - (pc[24] * col[j] + pc[25]);
+          const float drdA = col[j] - pc[26];
+          float w = sqrtf(oth / (oth + (h1 * h1 + h2 * h2)));
+          w = 0.5f * (w + wgt[j]);
+          const float ar = fabsf(residual);
+          float hw = ar < huber ? 1.f : huber / ar;
+          energy += w * w * hw * residual * residual * (2.f - hw);
+          if (hw < 1.f) hw = sqrtf(hw);
+          hw = hw * w;
+          const float gx = h1 * hw, gy = h2 * hw;
+          const float resF = residual * hw;
+          const float ja = drdA * hw, jb = hw;
+          const float jaF = zA ? 0.f : ja, jbF = zB ? 0.f : jb;
+          float ra = resF;  // what the right-hand sides are built from: resF, or res_toZeroF when marginalising
+          if constexpr (MARG) { ra = (((resF - gx * jpx) - gy * jpy) - jaF * dp6) - jbF * dp7; rtz[j] = ra; }
+          s.JI00 += gx * gx; s.JI11 += gy * gy; s.JI10 += gx * gy;
+          s.JabJI00 += ja * gx; s.JabJI01 += ja * gy; s.JabJI10 += jb * gx; s.JabJI11 += jb * gy;
+          s.Jab00 += ja * ja; s.Jab01 += ja * jb; s.Jab11 += jb * jb;
+          s.JIr0 += ra * gx; s.JIr1 += ra * gy; s.Jabr0 += ra * jaF; s.Jabr1 += ra * jbF; s.rr += ra * ra;
+          // the reference sums hw*hw*(hitColor[1]^2+hitColor[2]^2) with hitColor already multiplied by hw (Residuals.cpp:L217-244)
+          wJI2 += hw * hw * (gx * gx + gy * gy);
+        }
+        }
+      }
+
+      // ---- classification (Residuals.cpp:L260-273) and per-residual outputs
+      int newState;
+      float newEnergy;
+      if (st == RES_NONE) { newState = RES_NONE; newEnergy = 0.f; }
+      else if (!live) { newState = RES_OOB; newEnergy = en_old; }  // OOB exits return the old state_energy
+      else if (energy > TH || wJI2 < 2.f) { newState = RES_OUTLIER; newEnergy = TH; }
+      else { newState = RES_IN; newEnergy = energy; }
+      const bool in = (newState == RES_IN);
+      if (st != RES_NONE) {
+        e_sum = newEnergy;
+        n_in = in; n_oob = (newState == RES_OOB); n_outl = (newState == RES_OUTLIER);
+      }
+      if constexpr (MARG) {
+        if (masked) {
+          float4* o = reinterpret_cast<float4*>(W.marg_rtz + (size_t)slot * 8);
+          o[0] = in ? make_float4(rtz[0], rtz[1], rtz[2], rtz[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          o[1] = in ? make_float4(rtz[4], rtz[5], rtz[6], rtz[7]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (valid && masked) {
+        W.st_new[slot] = (uint8_t)newState;
+        W.en_new[slot] = newEnergy;
+        W.en_wo[slot] = (st == RES_NONE || !live) ? -1.f : energy;
+        const size_t plane = (size_t)MAXF * mp;
+        W.cpt[slot] = cKu; W.cpt[plane + slot] = cKv; W.cpt[2 * plane + slot] = new_idepth;
+      }
+
+      // ---- EFResidual::takeDataF (EnergyFunctionalStructs.cpp:L39-49), the per-point terms of addPoint (AccumulatedTopHessian.cpp:L131-135)
+      // and the residual's part of the point's Schur vector
+      float jp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Hdd = 0.f, bd = 0.f, Hcd0 = 0.f, Hcd1 = 0.f, Hcd2 = 0.f, Hcd3 = 0.f;
+      if (in) {
+        if constexpr (!MARG) geo_jac(pc, Kl0, Kl1, cu, cv, drescale, new_idepth, fx, fy, fxi, fyi, x, y, ddx, ddy);
+        const float J0 = s.JI00 * ddx + s.JI10 * ddy, J1 = s.JI10 * ddx + s.JI11 * ddy;  // JIdx2 * Jpdd
+#pragma unroll
+        for (int k = 0; k < 6; k++) jp[k] = x[4 + k] * J0 + y[4 + k] * J1;
+        jp[6] = s.JabJI00 * ddx + s.JabJI01 * ddy; jp[7] = s.JabJI10 * ddx + s.JabJI11 * ddy;
+        Hdd = J0 * ddx + J1 * ddy;
+        bd = s.JIr0 * ddx + s.JIr1 * ddy;
+        Hcd0 = x[0] * J0 + y[0] * J1; Hcd1 = x[1] * J0 + y[1] * J1; Hcd2 = x[2] * J0 + y[2] * J1; Hcd3 = x[3] * J0 + y[3] * J1;
+        if (valid) {
+          float4* gj = reinterpret_cast<float4*>(W.jpjd + (size_t)slot * 8);
+          gj[0] = make_float4(jp[0], jp[1], jp[2], jp[3]);
+          gj[1] = make_float4(jp[4], jp[5], jp[6], jp[7]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 10; k++) { x[k] = 0.f; y[k] = 0.f; }
+        s = PixSums{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      }
+      __syncwarp();  // the pair's adjoints staged by this warp above
+      if (slot_ok) {
+        // host block: adHost(h,t) * JpJdF (summed over targets in phase B); target block: adTarget(h,t) is diagonal
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const float4 a0 = *reinterpret_cast<const float4*>(&S.adH[t][k * 8]), a1 = *reinterpret_cast<const float4*>(&S.adH[t][k * 8 + 4]);
+          S.rec[t][k][pl] = a0.x * jp[0] + a0.y * jp[1] + a0.z * jp[2] + a0.w * jp[3] + a1.x * jp[4] + a1.y * jp[5] + a1.z * jp[6] + a1.w * jp[7];
+          S.Wv[pl][4 + 8 * t + k] = S.adT[t][k] * jp[k];
+        }
+        S.rec[t][8][pl] = Hdd; S.rec[t][9][pl] = bd; S.rec[t][10][pl] = Hcd0; S.rec[t][11][pl] = Hcd1; S.rec[t][12][pl] = Hcd2; S.rec[t][13][pl] = Hcd3;
+        S.rec[t][14][pl] = in ? 1.f : 0.f;
+      }
+
+      // ---- the pair's 13x13 block: 96 (91 used) entries per residual, summed over the pair's P lanes with a transposing butterfly:
+      // every step exchanges HALF of the remaining values, so the whole reduction costs 96 shuffles instead of 96 * log2(P)
+      float al[10], be[10];
+#pragma unroll
+      for (int k = 0; k < 10; k++) { al[k] = s.JI00 * x[k] + s.JI10 * y[k]; be[k] = s.JI10 * x[k] + s.JI11 * y[k]; }
+      float v[48];
+      {
+        const bool up = (lane & (P / 2)) != 0;
+        static_for<0, 48>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          const float a = top_entry<k>(x, y, al, be, s), b = top_entry<k + 48>(x, y, al, be, s);
+          v[k] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, P / 2);
+        });
+      }
+      static_for<0, LOGP - 1>([&](auto sc) {  // steps 2..log2(P): 24, 12, 6 (, 3) exchanges
+        constexpr int st2 = decltype(sc)::value, hstep = 24 >> st2, m = (P / 4) >> st2;
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int k = 0; k < hstep; k++) v[k] = (up ? v[k + hstep] : v[k]) + __shfl_xor_sync(0xffffffffu, up ? v[k] : v[k + hstep], m);
+      });
+      if (slot_ok) {  // lane L of the pair's group now holds entries [(96/P) L, (96/P)(L+1))
+        constexpr int PER = 96 / P;
+#pragma unroll
+        for (int k = 0; k < PER; k++) S.pair[t][PER * pl + k] = v[k];
+      }
+    }
+    {  // counters: warp sums
+      float es = e_sum, fin = (float)n_in, foob = (float)n_oob, fout = (float)n_outl;
+#pragma unroll
+      for (int m = 1; m < 32; m <<= 1) {
+        es += __shfl_xor_sync(0xffffffffu, es, m);
+        fin += __shfl_xor_sync(0xffffffffu, fin, m);
+        foob += __shfl_xor_sync(0xffffffffu, foob, m);
+        fout += __shfl_xor_sync(0xffffffffu, fout, m);
+        rs_step2 += __shfl_xor_sync(0xffffffffu, rs_step2, m);
+        rs_nid += __shfl_xor_sync(0xffffffffu, rs_nid, m);
+        rs_cnt += __shfl_xor_sync(0xffffffffu, rs_cnt, m);
+      }
+      if (lane == 0) {
+        S.misc[warp][0] = es; S.misc[warp][1] = fin; S.misc[warp][2] = foob; S.misc[warp][3] = fout;
+        S.misc[warp][4] = rs_step2; S.misc[warp][5] = rs_nid; S.misc[warp][6] = rs_cnt; S.misc[warp][7] = 0.f;
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---------------------------------------------------------------- phase B: per point (AccumulatedSCHessian.cpp:L36-58)
+    for (int e = tid; e < ch_count * 9; e += nthreads) {
+      const int k = e / ch_count, pl2 = e - k * ch_count;  // lanes = points: conflict-free reads of rec[t][k][.]
+      if (k < 8) {  // host block of the Schur vector
+        float sum = 0.f;
+        for (int tt = 0; tt < nf; tt++)
+          if (tt != h) sum += S.rec[tt][k][pl2];
+        S.Wv[pl2][4 + 8 * h + k] = sum;
+      } else {
+        const int p = ch_start + pl2;
+        float Hdd = 0.f, bd = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, ngood = 0.f;
+        for (int tt = 0; tt < nf; tt++) {
+          if (tt == h) continue;
+          Hdd += S.rec[tt][8][pl2]; bd += S.rec[tt][9][pl2]; c0 += S.rec[tt][10][pl2]; c1 += S.rec[tt][11][pl2];
+          c2 += S.rec[tt][12][pl2]; c3 += S.rec[tt][13][pl2]; ngood += S.rec[tt][14][pl2];
+        }
+        float prior = __ldg(W.priorF + p);
+        bool masked = true;
+        if constexpr (MARG) { masked = __ldg(W.marg_mask + p) != 0; prior *= __ldg(&W.marg->priorFac); }
+        float HdiF = 0.f, bdSum = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+        if (ngood > 0.f) {
+          float H = Hdd + prior;
+          if (H < 1e-10f) H = 1e-10f;
+          HdiF = 1.0f / H;
+          bdSum = MARG ? bd : bd + prior * (S.id[pl2] - S.idz[pl2]);  // shiftPriorToZero (AccumulatedSCHessian.cpp:L47-50)
+          w0 = c0; w1 = c1; w2 = c2; w3 = c3;
+        }
+        S.Wv[pl2][0] = w0; S.Wv[pl2][1] = w1; S.Wv[pl2][2] = w2; S.Wv[pl2][3] = w3;
+        S.Wv[pl2][N] = bdSum;
+        for (int c = N + 1; c < W.NW; c++) S.Wv[pl2][c] = 0.f;  // padding columns of the last 4x4 tiles
+        S.hdi[pl2] = HdiF;
+        if (masked) {
+          float4* po = reinterpret_cast<float4*>(W.pout + (size_t)p * 8);
+          po[0] = make_float4(Hdd, bd, c0, c1);
+          po[1] = make_float4(c2, c3, HdiF, bdSum);
+        }
+      }
+    }
+    // ---- phase C, first half: G(t) = adHost(h,t) * [P | Q | p](h,t) in fp64, [P|Q|p][k][c] = H13[4+k][col(c)], col = 4..11, 0..3, 12
+    for (int e = tid; e < nf * 104; e += nthreads) {
+      const int tt = e / 104, rr = e - tt * 104, i = rr / 13, c = rr - i * 13;
+      if (tt == h) continue;
+      const int colc = (c < 8) ? 4 + c : (c < 12 ? c - 8 : 12);
+      double m = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) m += S.AhD[tt][i * 8 + k] * (double)h13f(S.pair[tt], 4 + k, colc);
+      S.G[tt][rr] = m;
+    }
+    __syncthreads();
+
+    // ---- Schur vectors -> global, transposed ([4-column group][point] float4) so that phase E reads them coalesced
+    {
+      const int T = W.T;
+      for (int e = tid; e < ch_count * T; e += nthreads) {
+        const int g4 = e / ch_count, pl2 = e - g4 * ch_count;
+        W.wg[(size_t)g4 * mp + ch_start + pl2] = *reinterpret_cast<const float4*>(&S.Wv[pl2][4 * g4]);
+      }
+      if (tid < ch_count) W.hdig[ch_start + tid] = S.hdi[tid];
+    }
+    // ---- phase C, second half: the chunk's contributions in absolute coordinates -> partial blob (AccumulatedTopHessian.cpp:L270-286)
+    {
+      double* __restrict__ out = W.part + (size_t)chunk * PART_STRIDE;
+      for (int e = tid; e < nf * PART_SLOT; e += nthreads) {
+        const int tt = e / PART_SLOT, q = e - tt * PART_SLOT;
+        double val;
+        if (tt != h) {
+          const float* B = S.pair[tt];
+          if (q < 64) { const int i = q >> 3, j = q & 7; val = S.G[tt][i * 13 + j] * S.dT[tt][j]; }                               // H[h,t] = (Ah P) At^T
+          else if (q < 128) { const int i = (q - 64) >> 3, j = q & 7; val = S.dT[tt][i] * (double)h13f(B, 4 + i, 4 + j) * S.dT[tt][j]; }  // H[t,t] = At P At^T
+          else if (q < 160) { const int i = (q - 128) >> 2, c = q & 3; val = S.dT[tt][i] * (double)h13f(B, 4 + i, c); }           // H[t,C] = At Q
+          else { const int i = q - 160; val = S.dT[tt][i] * (double)h13f(B, 4 + i, 12); }                                          // b[t] = At p
+        } else {
+          if (q < 64) continue;  // H[h,h] goes to the diagonal slot below
+          val = 0.0;
+          if (q < 128) {  // H[h,h] = sum_t (Ah P) Ah^T
+            const int i = (q - 64) >> 3, j = q & 7;
+            for (int t2 = 0; t2 < nf; t2++) {
+              if (t2 == h) continue;
+#pragma unroll
+              for (int k = 0; k < 8; k++) val += S.G[t2][i * 13 + k] * S.AhD[t2][j * 8 + k];
+            }
+          } else if (q < 160) {  // H[h,C] = sum_t Ah Q
+            const int i = (q - 128) >> 2, c = q & 3;
+            for (int t2 = 0; t2 < nf; t2++) if (t2 != h) val += S.G[t2][i * 13 + 8 + c];
+          } else {  // b[h] = sum_t Ah p
+            const int i = q - 160;
+            for (int t2 = 0; t2 < nf; t2++) if (t2 != h) val += S.G[t2][i * 13 + 12];
+          }
+        }
+        out[e] = val;
+      }
+      if (tid < 20) {  // H[C,C] (4x4) and b[C]
+        const int i = tid / 5, j = tid - i * 5;
+        double val = 0.0;
+        for (int t2 = 0; t2 < nf; t2++) if (t2 != h) val += (double)h13f(S.pair[t2], i, j < 4 ? j : 12);
+        out[PART_CC + (j < 4 ? i * 4 + j : 16 + i)] = val;
+      } else if (tid >= 32 && tid < 40) {
+        const int k = tid - 32;
+        double val = 0.0;
+        for (int wv = 0; wv < nwarps; wv++) val += (double)S.misc[wv][k];
+        out[PART_MISC + k] = val;
+      }
+    }
+    __syncthreads();  // shared memory is reused by the next chunk (persistent case)
+  }
+
+  // ================================================================== all chunks of the window are done
+  bool ok = grid_barrier(W.bar, W.bar_target);
+
+  const int nH = N * N + N;
+  double* __restrict__ R = W.result;
+  double* __restrict__ RH = W.result_host;
+  const bool xch = W.xc.nranks > 1;
+  const double* __restrict__ part = W.part;
+
+  // ---------------------------------------------------------------- phase D: H_top / b_top / counters, a warp per result entry
+  // item list: [unordered frame pairs a<b: 64 entries each][diagonal blocks: nf x 64][H[.,C]: nf x 32][b: nf x 8][CC 16][bC 4][misc 8]
+  const int npair = nf * (nf - 1) / 2;
+  const int n_off = npair * 64, n_diag = nf * 64, n_c = nf * 32, n_b = nf * 8;
+  const int nitems = n_off + n_diag + n_c + n_b + 16 + 4 + (ACC_MISC - 1);  // the last counter slot is the error flag: written on error only
+  const int gwarp = blockIdx.x * nwarps + warp, gstride = gridDim.x * nwarps;
+  const int nch = W.nchunks;
+  for (int pass = 0; pass < (xch ? 2 : 1); pass++) {
+    for (int item = gwarp; item < nitems; item += gstride) {
+      // decode: up to two (offset, chunk range) segments and up to two destinations
+      int off0 = 0, lo0 = 0, hi0 = nch, off1 = -1, lo1 = 0, hi1 = 0, d0, d1 = -1;
+      int e = item;
+      if (e < n_off) {
+        const int q = e >> 6, ij = e & 63, i = ij >> 3, j = ij & 7;
+        int a = 0, rem = q;
+        while (rem >= nf - 1 - a) { rem -= nf - 1 - a; a++; }
+        const int b = a + 1 + rem;
+        off0 = b * PART_SLOT + i * 8 + j; lo0 = W.chunk_beg[a]; hi0 = W.chunk_beg[a + 1];
+        off1 = a * PART_SLOT + j * 8 + i; lo1 = W.chunk_beg[b]; hi1 = W.chunk_beg[b + 1];
+        d0 = (4 + 8 * a + i) * N + 4 + 8 * b + j; d1 = (4 + 8 * b + j) * N + 4 + 8 * a + i;
+      } else if ((e -= n_off) < n_diag) {
+        const int a = e >> 6, ij = e & 63;
+        off0 = a * PART_SLOT + 64 + ij;
+        d0 = (4 + 8 * a + (ij >> 3)) * N + 4 + 8 * a + (ij & 7);
+      } else if ((e -= n_diag) < n_c) {
+        const int a = e >> 5, ic = e & 31;
+        off0 = a * PART_SLOT + 128 + ic;
+        d0 = (4 + 8 * a + (ic >> 2)) * N + (ic & 3); d1 = (ic & 3) * N + 4 + 8 * a + (ic >> 2);
+      } else if ((e -= n_c) < n_b) {
+        off0 = (e >> 3) * PART_SLOT + 160 + (e & 7);
+        d0 = N * N + 4 + e;
+      } else if ((e -= n_b) < 16) {
+        off0 = PART_CC + e; d0 = (e >> 2) * N + (e & 3);
+      } else if ((e -= 16) < 4) {
+        off0 = PART_CC + 16 + e; d0 = N * N + e;
+      } else {
+        e -= 4;
+        off0 = PART_MISC + e; d0 = nH + W.ntiles * 16 + e;
+      }
+      if (pass == 0) {
+        double sum = 0.0;
+        for (int c = lo0 + lane; c < hi0; c += 32) sum += __ldcg(part + (size_t)c * PART_STRIDE + off0);
+        if (off1 >= 0)
+          for (int c = lo1 + lane; c < hi1; c += 32) sum += __ldcg(part + (size_t)c * PART_STRIDE + off1);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+        if (lane == 0) {
+          if (xch) { R[d0] = sum; xchg_push(W.xc, d0, sum); }
+          else { R[d0] = sum; if (d1 >= 0) R[d1] = sum; if (RH) { RH[d0] = sum; if (d1 >= 0) RH[d1] = sum; } }
+        }
+      } else if (lane == 0) {
+        const double sum = xchg_pull_sum(W.xc, d0, R[d0], ok);
+        R[d0] = sum; if (d1 >= 0) R[d1] = sum;
+        if (RH) { RH[d0] = sum; if (d1 >= 0) RH[d1] = sum; }
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- phase E: [H_sc | b_sc] = sum_p HdiF w_p w_p^T, one CTA per 4x4 tile
+  {
+    const int T = W.T, npts = W.npts;
+    for (int tile = blockIdx.x; tile < W.ntiles; tile += gridDim.x) {
+      int ti = 0, rem = tile;
+      while (rem >= T - ti) { rem -= T - ti; ti++; }
+      const int tj = ti + rem;
+      float a[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[i][j] = 0.f;
+      const float4* __restrict__ wi_p = W.wg + (size_t)ti * mp;
+      const float4* __restrict__ wj_p = W.wg + (size_t)tj * mp;
+#pragma unroll 4
+      for (int p = tid; p < npts; p += nthreads) {
+        const float sc = __ldcg(W.hdig + p);
+        const float4 wi = __ldcg(wi_p + p), wj = __ldcg(wj_p + p);
+        const float si[4] = {sc * wi.x, sc * wi.y, sc * wi.z, sc * wi.w};
+        const float vj[4] = {wj.x, wj.y, wj.z, wj.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) a[i][j] += si[i] * vj[j];
+      }
+      // per-thread fp32 sums over <= npts / nthreads points, then fp64: warp butterfly, cross-warp through shared memory
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          double d = (double)a[i][j];
+#pragma unroll
+          for (int m = 16; m >= 1; m >>= 1) d += __shfl_xor_sync(0xffffffffu, d, m);
+          if (lane == 0) S.red[warp][i * 4 + j] = d;
+        }
+      __syncthreads();
+      if (tid < 16) {
+        double d = 0.0;
+        for (int wv = 0; wv < nwarps; wv++) d += S.red[wv][tid];
+        const int idx = nH + tile * 16 + tid;
+        if (xch) {
+          xchg_push(W.xc, idx, d);
+          d = xchg_pull_sum(W.xc, idx, d, ok);
+        }
+        R[idx] = d;
+        if (RH) RH[idx] = d;
+      }
+      __syncthreads();
+    }
+  }
+  if (!ok && lane == 0) {  // barrier / peer timeout: poison the error slot of the counters (checked by the host)
+    R[nH + W.ntiles * 16 + 7] = 1.0;
+    if (RH) RH[nH + W.ntiles * 16 + 7] = 1.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// launch: cooperative (all CTAs resident); shared-memory opt-in and occupancy are cached PER DEVICE (cudaFuncSetAttribute is a
+// per-device setting), under a mutex: handles on several devices / threads of one process are fine
+// ---------------------------------------------------------------------------------------------------------------------------
+struct FusedCfg { bool done = false; int max_ctas = 0; };
+static std::mutex g_cfg_mutex;
+
+template <int P, bool MARG>
+static cudaError_t launch_cfg(BAWinDev& W, const BAIter& it, cudaStream_t s, unsigned* bar_count) {
+  static FusedCfg cfg[64];
+  constexpr int TPB = (P == 32) ? 224 : 128;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const int smem = (int)sizeof(FusedSmem<P>);
+  const int threads = min(TPB, max(64, ((P * (W.nf - 1)) + 31) & ~31));
+  int max_ctas;
+  {
+    std::lock_guard<std::mutex> lk(g_cfg_mutex);
+    FusedCfg& c = cfg[dev & 63];
+    if (!c.done) {
+      e = cudaFuncSetAttribute(ba_fused_kernel<P, MARG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      int per_sm = 0, sms = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_fused_kernel<P, MARG>, TPB, smem);
+      if (e != cudaSuccess) return e;
+      e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (e != cudaSuccess) return e;
+      c.max_ctas = per_sm * sms;
+      c.done = true;
+    }
+    max_ctas = c.max_ctas;
+  }
+  const int grid = min(W.nchunks, max_ctas);
+  *bar_count += (unsigned)grid;   // monotonic arrival counter: every CTA of this launch adds one
+  W.bar_target = *bar_count;
+  void* args[2] = {(void*)&W, (void*)&it};
+  return cudaLaunchCooperativeKernel((const void*)ba_fused_kernel<P, MARG>, dim3(grid), dim3(threads), args, (size_t)smem, s);
+}
+
+// W.bar_target is filled in here; *bar_count is the handle's running arrival count
+cudaError_t launch_fused_kernel(BAWinDev& W, const BAIter& it, bool marg, cudaStream_t s, unsigned* bar_count) {
+  if (W.P == 32) return marg ? launch_cfg<32, true>(W, it, s, bar_count) : launch_cfg<32, false>(W, it, s, bar_count);
+  return marg ? launch_cfg<16, true>(W, it, s, bar_count) : launch_cfg<16, false>(W, it, s, bar_count);
+}
+
+}  // namespace dmv

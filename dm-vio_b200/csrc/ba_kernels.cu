@@ -1,246 +1,10 @@
-// sm_100a kernels of the bundle-adjustment hot path.
-//
-//   ba_point_kernel     one CTA = one chunk of P points of one host frame; warp t = target frame t.
-//                       prologue: cp.async staging of the chunk's point records, residual states and the host's adjoint
-//                                 blocks into shared memory; optional fused EnergyFunctional::resubstituteFPt + point step
-//                       phase A: 8 lanes per (point,target) residual = the 8 pattern pixels: project, 4-tap float4 gather
-//                                from the target plane, Huber-weighted residual, 8-lane butterfly reductions,
-//                                register-resident rows of the pair's 13x13 block      (Residuals.cpp:L78-274 +
-//                                AccumulatedTopHessian.cpp:L39-159 fused; the 304-byte RawResidualJacobian never exists)
-//                       phase B: per-point Hdd/bd/Hcd, HdiF, and the point's Schur vector in ABSOLUTE frame coordinates
-//                                w_p = [Hcd | sum_t adHost v_t | adTarget v_t ... | bdSum]
-//                       phase C: weighted Gram  sum_p HdiF w_p w_p^T  in 4x4 register tiles  (replaces the nf^3 accD blocks of
-//                                AccumulatedSCHessian.cpp:L34-157)
-//                       all block results go to fp64 global accumulators with red.global.add.f64 (no partial buffers)
-//   ba_stitch_kernel    adjoint products to the dense (8nf+4)^2 system in fp64 (AccumulatedTopHessian.cpp:L241-303, gather form);
-//                       also zeroes the accumulator set of the next iteration
-//   ba_resub_kernel     stand-alone EnergyFunctional::resubstituteFPt + point part of doStepFromBackup
+// Small sm_100a kernels of the bundle-adjustment path next to ba_fused_kernel (ba_fused.cu):
+//   ba_resub_kernel     stand-alone EnergyFunctional::resubstituteFPt + point part of doStepFromBackup (the hot loop uses the fused prologue)
+//   repack_aos3_kernel / make_dI_kernel   image ingestion (float4 texels)
+//   l2_flush_kernel     larger-than-L2 scrub used by the bench between timed iterations
 #include "ba_common.cuh"
 
 namespace dmv {
-
-// 13x13 pair block from the packed 92-double layout (rows 0..9 upper-triangular, then the 6 bottom-right entries)
-__device__ __forceinline__ double h13(const double* S, int r, int c) {
-  if (r > c) { int tmp = r; r = c; c = tmp; }
-  if (r < TOP_ROWS) return S[top_off(r) + c - r];
-  const int rr = r - 10, cc = c - 10;  // (0,0)->0 (0,1)->1 (0,2)->2 (1,1)->3 (1,2)->4 (2,2)->5
-  return S[TOP_TRI + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5))];
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// ba_stitch_kernel — AccumulatedTopHessian.cpp:L241-303 (stitchDoubleInternal + symmetrisation) in gather form, fp64.
-// Launched with programmatic stream serialisation right behind ba_point_kernel: its CTAs are resident early and wait in
-// griddepcontrol.wait.  CTA a < nf owns the 8 rows of frame a, CTA nf the 4 calibration rows + the Schur tiles + counters
-// + the zeroing of the next iteration's accumulators.  Per block row: one wave of 16-byte cp.async copies stages the
-// 2(nf-1) pair blocks touching frame a with their adjoints; B = [P|Q|p] is expanded from the symmetric storage,
-// G = adHost*B and GA = (adHost P) adHost^T are formed once; every output entry is then a short sum (adTarget is diagonal).
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int ST_THREADS = 512;
-#define STAMP_ST(k) do { if ((W.dbg & 16) && threadIdx.x == 0) W.dbg_clk[(size_t)(W.nchunks + blockIdx.x) * 16 + (k)] = gtime(); } while (0)
-struct alignas(16) StitchSmem {
-  double raw[2][MAXF][TOP_PART];  // [0][t] pair (a,t) (a hosts), [1][t] pair (t,a) (a is target)
-  double Ah[2][MAXF][64];
-  double d[2][MAXF][8];
-  double G[2][MAXF][8][13];       // adHost * [P | Q | p]   ([1]: only the P part is used)
-};
-
-// ---- exchange of the stitched system between ranks (sharded BA): "LL" packets over NVLink peer memory.
-// Every entry of the result blob has exactly one producing CTA (the same CTA index on every rank).  After a CTA has written
-// its entries it (1) pushes each of them as a 16-byte packet {lo, seq, hi, seq} into slot [parity][my rank][entry] of every
-// peer's inbox (st.volatile.v4: each 8-byte half carries its own flag, so no fence and no separate flag round trip), then
-// (2) spins on its OWN inbox until the nranks-1 packets of an entry carry this exchange's sequence number, adds the values
-// in RANK ORDER (bit-identical sums on every rank) and overwrites the local entry.  Double-buffered by parity: a peer can be
-// at most one exchange ahead (it needs my packets of exchange k+1, which my stream issues only after this kernel retired).
-__device__ __forceinline__ void xchg_push(const BAXchg& X, int idx, double v) {
-  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
-  const uint4 pk = make_uint4((unsigned)(u & 0xffffffffull), X.seq, (unsigned)(u >> 32), X.seq);
-  const size_t off = (size_t)(((X.seq & 1u) * XCHG_MAXR + X.rank)) * X.pitch + idx;
-#pragma unroll 1
-  for (int k = 1; k < X.nranks; k++) {
-    const int r = (X.rank + k) % X.nranks;  // start with the neighbour: spreads the NVSwitch ports
-    uint4* dst = X.inbox[r] + off;
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
-  }
-}
-__device__ __forceinline__ double xchg_pull_sum(const BAXchg& X, int idx, double mine) {
-  // poll all peers' packets of this entry at once (independent loads: one memory round trip when they have all arrived)
-  const uint4* base = X.inbox[X.rank] + (size_t)((X.seq & 1u) * XCHG_MAXR) * X.pitch + idx;
-  uint4 pk[XCHG_MAXR];
-  unsigned pending = ((1u << X.nranks) - 1u) & ~(1u << X.rank);
-  while (pending) {
-#pragma unroll
-    for (int r = 0; r < XCHG_MAXR; r++)
-      if ((pending >> r) & 1u) {
-        const uint4* src = base + (size_t)r * X.pitch;
-        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[r].x), "=r"(pk[r].y), "=r"(pk[r].z), "=r"(pk[r].w) : "l"(src) : "memory");
-      }
-#pragma unroll
-    for (int r = 0; r < XCHG_MAXR; r++)
-      if (((pending >> r) & 1u) && pk[r].y == X.seq && pk[r].w == X.seq) pending &= ~(1u << r);
-  }
-  double s = 0.0;  // rank order => bit-identical sums on every rank
-#pragma unroll
-  for (int r = 0; r < XCHG_MAXR; r++) {
-    if (r >= X.nranks) break;
-    s += (r == X.rank) ? mine : __longlong_as_double((long long)(((unsigned long long)pk[r].z << 32) | pk[r].x));
-  }
-  return s;
-}
-// The raw Schur tiles + counters (ntiles*16 + ACC_MISC doubles, copied unchanged) are split evenly over the nf+1 CTAs.
-__device__ __forceinline__ int tiles_share(const BAWinDev& W) { return (W.ntiles * 16 + ACC_MISC + W.nf) / (W.nf + 1); }
-__device__ __forceinline__ int tiles_count(const BAWinDev& W, int a) {
-  const int per = tiles_share(W), nsc = W.ntiles * 16 + ACC_MISC;
-  return max(0, min(per, nsc - a * per));
-}
-// entry e (0 <= e < count) of the list of result-blob indices produced by stitch CTA a
-__device__ __forceinline__ int xchg_owned_count(const BAWinDev& W, int a) { return ((a < W.nf) ? 8 * (W.N + 1) + 32 : 20) + tiles_count(W, a); }
-__device__ __forceinline__ int xchg_owned_index(const BAWinDev& W, int a, int e) {
-  const int N = W.N;
-  const int own = (a < W.nf) ? 8 * (N + 1) + 32 : 20;
-  if (e >= own) return N * N + N + a * tiles_share(W) + (e - own);
-  if (a < W.nf) {
-    const int r0 = 4 + 8 * a;
-    if (e < 8 * (N + 1)) { const int ia = e / (N + 1), J = e - ia * (N + 1); return (J == N) ? N * N + r0 + ia : (r0 + ia) * N + J; }
-    const int m = e - 8 * (N + 1);  // mirrored calibration columns H[J][r0+ia], J < 4
-    return (m >> 3) * N + r0 + (m & 7);
-  }
-  const int i = e / 5, j = e - i * 5;
-  return (j < 4) ? i * N + j : N * N + i;
-}
-
-__global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const __grid_constant__ BAWinDev W) {
-  extern __shared__ __align__(16) unsigned char st_smem[];
-  StitchSmem& Q = *reinterpret_cast<StitchSmem*>(st_smem);
-  const int nf = W.nf, N = W.N;
-  const int tid = threadIdx.x;
-  const int a = blockIdx.x;
-  const BAAdj* __restrict__ A = W.adj;
-  STAMP_ST(0);
-  // adjoints do not depend on the point kernel: prefetch them before waiting on the grid dependency
-  if (a < nf) {
-    for (int e = tid; e < nf * 32; e += ST_THREADS) {
-      const int t = e >> 5, k = (e & 31) * 2;
-      cp_async16(&Q.Ah[0][t][k], &A->adHost[a * nf + t][k]);
-      cp_async16(&Q.Ah[1][t][k], &A->adHost[t * nf + a][k]);
-    }
-    for (int e = tid; e < nf * 4; e += ST_THREADS) {
-      const int t = e >> 2, k = (e & 3) * 2;
-      cp_async16(&Q.d[0][t][k], &A->adTdiag[a * nf + t][k]);
-      cp_async16(&Q.d[1][t][k], &A->adTdiag[t * nf + a][k]);
-    }
-  }
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  STAMP_ST(1);
-  if (W.dbg & 8) return;
-  const double* __restrict__ TS = W.acc;
-  const double* __restrict__ SC = W.acc + (size_t)nf * nf * TOP_PART;
-  double* __restrict__ R = W.result;
-  const int nH = N * N + N;
-
-  {  // this CTA's share of the raw Schur tiles + counters
-    const int o = a * tiles_share(W), c = tiles_count(W, a);
-    for (int e = tid; e < c; e += ST_THREADS) R[nH + o + e] = __ldcg(SC + o + e);
-  }
-  if (a == nf) {
-    // calibration rows and the next iteration's accumulators
-    const int nacc = acc_doubles(nf, W.ntiles);
-    for (int i = tid; i < nacc; i += ST_THREADS) W.acc_next[i] = 0.0;
-    if (tid < 20 * 8) {  // 20 outputs x 8 lanes: a plain `v += TS[pr]` loop issues one dependent L2 round trip per pair (49 x ~0.3 us)
-      const int o = tid >> 3, part = tid & 7;
-      const int i = o / 5, j = o - i * 5;
-      const int c = (j < 4) ? j : 12;
-      const int rr = i < c ? i : c, cc = i < c ? c : i;  // packed upper-triangular storage: entry (rr, cc) with rr <= cc
-      const double* src = TS + top_off(rr) + cc - rr;
-      double x[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) { const int pr = part + 8 * u; x[u] = (pr < nf * nf) ? __ldcg(src + (size_t)pr * TOP_PART) : 0.0; }
-      double v = 0.0;
-#pragma unroll
-      for (int u = 0; u < 8; u++) v += x[u];   // MAXF*MAXF = 64 pairs = 8 lanes x 8
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      if (part == 0) { if (j < 4) R[(size_t)i * N + j] = v; else R[(size_t)N * N + i] = v; }
-    }
-  } else {
-  for (int e = tid; e < nf * (TOP_PART / 2); e += ST_THREADS) {
-    const int t = e / (TOP_PART / 2), k = (e - t * (TOP_PART / 2)) * 2;
-    cp_async16(&Q.raw[0][t][k], TS + (size_t)(a * nf + t) * TOP_PART + k);
-    cp_async16(&Q.raw[1][t][k], TS + (size_t)(t * nf + a) * TOP_PART + k);
-  }
-  cp_async_wait_all();
-  __syncthreads();
-  STAMP_ST(2);
-  // G[s][t] = adHost(s,t) * [P | Q | p](s,t)  with [P|Q|p][k][c] = H13[4+k][col(c)], col = 4..11, 0..3, 12, read straight from the
-  // symmetric 136-entry storage ([1]: only the P part is used)
-  for (int e = tid; e < 2 * nf * 104; e += ST_THREADS) {
-    const int s2 = e / (nf * 104), e1 = e - s2 * nf * 104, t = e1 / 104, r = e1 - t * 104, i = r / 13, c = r - i * 13;
-    if (s2 == 1 && c >= 8) continue;
-    const int col = (c < 8) ? 4 + c : (c < 12 ? c - 8 : 12);
-    double m = 0.0;
-    if (t != a) {
-#pragma unroll
-      for (int k = 0; k < 8; k++) m += Q.Ah[s2][t][i * 8 + k] * h13(Q.raw[s2][t], 4 + k, col);
-    }
-    (&Q.G[s2][t][0][0])[r] = m;
-  }
-  __syncthreads();
-  STAMP_ST(3);
-  const int r0 = 4 + 8 * a;
-  for (int e = tid; e < 8 * (N + 1); e += ST_THREADS) {
-    const int ia = e / (N + 1), J = e - ia * (N + 1);
-    double v = 0.0;
-    if (J == N || J < 4) {  // b[a] / H[a,C] = sum_t Ah(a,t) (p|Q)(a,t) + At(t,a) (p|Q)(t,a)
-      const int c = (J == N) ? 12 : 8 + J;
-      const int col = (J == N) ? 12 : J;
-      for (int t = 0; t < nf; t++)
-        if (t != a) v += Q.G[0][t][ia][c] + Q.d[1][t][ia] * h13(Q.raw[1][t], 4 + ia, col);
-      if (J == N) R[(size_t)N * N + r0 + ia] = v;
-      else { R[(size_t)(r0 + ia) * N + J] = v; R[(size_t)J * N + r0 + ia] = v; }
-      continue;
-    }
-    const int fb = (J - 4) >> 3, jb = (J - 4) & 7;
-    if (fb == a) {  // diagonal block: sum_t (Ah P Ah^T)(a,t) + At(t,a) P(t,a) At(t,a)
-      for (int t = 0; t < nf; t++) {
-        if (t == a) continue;
-        double ga = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) ga += Q.G[0][t][ia][k] * Q.Ah[0][t][jb * 8 + k];
-        v += ga + Q.d[1][t][ia] * h13(Q.raw[1][t], 4 + ia, 4 + jb) * Q.d[1][t][jb];
-      }
-    } else {  // raw[a,b](ia,jb) + raw[b,a](jb,ia), raw[h,t] = (Ah P) At^T
-      v = Q.G[0][fb][ia][jb] * Q.d[0][fb][jb] + Q.G[1][fb][jb][ia] * Q.d[1][fb][ia];
-    }
-    R[(size_t)(r0 + ia) * N + J] = v;
-  }
-  }  // a < nf
-  STAMP_ST(4);
-  double* __restrict__ RH = W.result_host;
-  if (W.xc.nranks > 1 || RH != nullptr) {
-    __syncthreads();  // every entry of this CTA is in R (same-CTA global writes are visible after the barrier)
-    const int cnt = xchg_owned_count(W, a);
-    if (W.xc.nranks > 1) {
-      for (int e = tid; e < cnt; e += ST_THREADS) {
-        const int idx = xchg_owned_index(W, a, e);
-        xchg_push(W.xc, idx, __ldcg(R + idx));
-      }
-      for (int e = tid; e < cnt; e += ST_THREADS) {
-        const int idx = xchg_owned_index(W, a, e);
-        const double v = xchg_pull_sum(W.xc, idx, __ldcg(R + idx));
-        R[idx] = v;
-        if (RH) RH[idx] = v;
-      }
-    } else {
-      // single GPU: the CTA streams its part of the blob straight into the caller's pinned buffer (posted PCIe writes):
-      // no D2H copy node behind the kernel
-      for (int e = tid; e < cnt; e += ST_THREADS) {
-        const int idx = xchg_owned_index(W, a, e);
-        RH[idx] = __ldcg(R + idx);
-      }
-    }
-    STAMP_ST(5);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // stand-alone EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:L295-321) + point part of doStepFromBackup
@@ -308,24 +72,6 @@ __global__ void l2_flush_kernel(float4* buf, size_t n) {
 // ---------------------------------------------------------------------------------------------------------------
 // launch helpers (called from ba_api.cu)
 // ---------------------------------------------------------------------------------------------------------------
-void launch_stitch_kernel(const BAWinDev& W, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(ba_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StitchSmem));
-    configured = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(W.nf + 1);
-  cfg.blockDim = dim3(ST_THREADS);
-  cfg.dynamicSmemBytes = sizeof(StitchSmem);
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, ba_stitch_kernel, W);
-}
 void launch_resub_kernel(const BAWinDev& W, const BAIter& it, int apply, double* sums, cudaStream_t s) {
   ba_resub_kernel<<<(W.npts + 127) / 128, 128, 0, s>>>(W, it, apply, sums);
 }

@@ -36,7 +36,8 @@ typedef enum dmv_status {
   DMV_ERR_NO_DEVICE = -2, /* no usable CUDA device: the product has no CPU path */
   DMV_ERR_CUDA = -3,      /* a CUDA runtime call failed (see dmv_last_error) */
   DMV_ERR_STATE = -4,     /* call order violated (e.g. accumulate before linearize+apply) */
-  DMV_ERR_NCCL = -5
+  DMV_ERR_NCCL = -5,
+  DMV_ERR_TIMEOUT = -6    /* a grid barrier or the peer exchange inside a kernel gave up waiting (lost rank / CTA) */
 } dmv_status;
 
 const char* dmv_last_error(void);
@@ -53,7 +54,7 @@ typedef struct dmv_ba_config {
   int max_frames;     /* <= DMV_MAX_FRAMES */
   int max_points;     /* capacity of the active point set */
   int device;         /* CUDA device ordinal */
-  int chunk_points;   /* points per thread block: 8, 16 or 32; 0 = default */
+  int chunk_points;   /* points per thread block: 16 or 32; 0 = default (16) */
 } dmv_ba_config;
 
 /* util/settings.cpp values read by the kernels (constant during a run) */
@@ -222,23 +223,16 @@ int dmv_ba_comm_init(dmv_ba* ba, int nranks, int rank, const void* nccl_unique_i
 int dmv_ba_p2p_export(dmv_ba* ba, void* ipc_handle64);
 int dmv_ba_p2p_import(dmv_ba* ba, int nranks, int rank, const void* ipc_handles /* nranks*64 bytes, rank order */);
 
-/* timing of the last linearize/gn_step on the handle's stream (CUDA events), milliseconds: [0]=total device time of the call,
- * [1]=point kernel, [2]=reduce+stitch */
+/* instrumentation (cheap, always present): CUDA-event timing of the last linearize / gn_step on the handle's stream, milliseconds:
+ * [0] = total device time of the call, [1] = ba_fused_kernel, [2] = 0, [3] = what follows the kernel (NCCL all-reduce / D2H copy) */
 int dmv_ba_last_timing(dmv_ba* ba, float ms[4]);
-/* raw device access for benchmarking: run the device part of one GN iteration (resubstitute+step if x != NULL, point kernel, reduce,
- * stitch, all-reduce if a communicator is attached) `iters` times on the handle's stream with all inputs resident, each iteration
- * bracketed by CUDA events (optionally preceded by an untimed L2 scrub); returns the average device milliseconds per iteration
- * and the time from the start of the iteration to the end of the point kernel. */
-int dmv_ba_bench_device(dmv_ba* ba, const double* x, int iters, int flush_l2, float* ms_per_iter, float* ms_point_kernel);
 int dmv_ba_kernel_launch_count(dmv_ba* ba, long long* n);
-/* enable/disable the CUDA-event timing of dmv_ba_linearize / dmv_ba_gn_step (off by default: 4 event records per call) */
+/* enable/disable the CUDA-event timing of dmv_ba_linearize / dmv_ba_gn_step (off by default) */
 int dmv_ba_set_timing(dmv_ba* ba, int enable);
-/* wall-clock time of `iters` x { dmv_ba_gn_step(x, st) ; dmv_ba_apply_res() } issued from C, milliseconds per iteration */
-int dmv_ba_bench_e2e(dmv_ba* ba, const double* x, const dmv_ba_state* st, int iters, double* ms_per_iter);
-/* phase timestamps of the point kernel (DMV_DBG=16 experiments only) */
-int dmv_ba_debug_clocks(dmv_ba* ba, unsigned long long* out, int cap);
 /* bytes copied host->device and device->host by one dmv_ba_gn_step / dmv_ba_linearize call */
 int dmv_ba_io_bytes(dmv_ba* ba, long long* h2d, long long* d2h);
+/* The measurement-only entry points (dmv_ba_bench_device, dmv_ba_bench_e2e, ...) live in dmvio_b200_bench.h / csrc/ba_bench.cu and
+ * are compiled in only with BENCH=1. */
 
 /* ------------------------------------------------------------------------------------------------
  * Coarse-tracker handle  ==  the GPU side of CoarseTracker (FullSystem/CoarseTracker.{h,cpp})

@@ -7,9 +7,13 @@ import pytest
 
 
 def _header_symbols():
+    """every entry point declared in include/*.h: the drop-in surface (dmvio_b200.h) and the measurement-only one (dmvio_b200_bench.h)"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    txt = open(os.path.join(root, "include", "dmvio_b200.h")).read()
-    return sorted(set(re.findall(r"\b(dmv_[A-Za-z0-9_]+)\s*\(", txt)))
+    syms = set()
+    for h in ("dmvio_b200.h", "dmvio_b200_bench.h"):
+        txt = open(os.path.join(root, "include", h)).read()
+        syms |= set(re.findall(r"\b(dmv_[A-Za-z0-9_]+)\s*\(", txt))
+    return sorted(syms)
 
 
 def test_library_exports_every_declared_symbol():

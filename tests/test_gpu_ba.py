@@ -41,7 +41,7 @@ def _states_equal_up_to_threshold(o_new, g_new, o_e, th_tol=1e-4):
 
 
 @pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"nf{c['nf']}_n{c['npts']}")
-@pytest.mark.parametrize("P", [8, 16, 32])
+@pytest.mark.parametrize("P", [16, 32])
 def test_linearize_accumulate_parity(capi, orc, synth, cfg, P):
     W = synth.make_window(**cfg)
     ow = orc.Window(W)

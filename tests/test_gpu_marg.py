@@ -32,7 +32,7 @@ def _case(synth, orc, cfg, frac):
     return W, pts
 
 
-@pytest.mark.parametrize("cfg,frac,P", [(dict(nf=7, npts=2000, seed=1234), 0.33, 16), (dict(nf=4, npts=400, seed=3, hosts="all"), 0.5, 8),
+@pytest.mark.parametrize("cfg,frac,P", [(dict(nf=7, npts=2000, seed=1234), 0.33, 16), (dict(nf=4, npts=400, seed=3, hosts="all"), 0.5, 32),
                                         (dict(nf=8, npts=777, seed=99, hosts="all"), 0.1, 32), (dict(nf=3, npts=333, seed=7), 1.0, 16)],
                          ids=["nf7_n2000_third", "nf4_n400_half", "nf8_n777_tenth", "nf3_n333_all"])
 def test_marginalize_points_parity(capi, orc, synth, cfg, frac, P):
