@@ -138,6 +138,7 @@ static int ba_allocate(dmv_ba* b, const dmv_ba_config* cfg) {
   CK(cudaMalloc(&b->d_part, sizeof(double) * PART_STRIDE * (size_t)b->max_chunks));
   CK(cudaMalloc(&b->d_wg, sizeof(float4) * (size_t)maxT0 * mp));
   CK(cudaMalloc(&b->d_hdig, sizeof(float) * mp));
+  CK(cudaMalloc(&b->d_hdi_solve, sizeof(float) * mp));
   CK(cudaMalloc(&b->d_bar, sizeof(unsigned int)));
   CK(cudaMemset(b->d_bar, 0, sizeof(unsigned int)));
   CK(cudaMalloc(&b->d_resub_sums, sizeof(double) * 4));
@@ -163,7 +164,7 @@ int dmv_ba_destroy(dmv_ba* b) {
     cudaFree(b->d_pout[k]); cudaFree(b->d_result[k]); cudaFreeHost(b->h_result[k]);
   }
   cudaFree(b->d_step); cudaFree(b->d_resub_sums); cudaFree(b->d_flush);
-  cudaFree(b->d_part); cudaFree(b->d_wg); cudaFree(b->d_hdig); cudaFree(b->d_bar);
+  cudaFree(b->d_part); cudaFree(b->d_wg); cudaFree(b->d_hdig); cudaFree(b->d_hdi_solve); cudaFree(b->d_bar);
   cudaFreeHost(b->h_up); cudaFreeHost(b->h_adj); cudaFreeHost(b->h_scratch);
   for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   if (b->nccl_comm) dmv::nccl_destroy(b->nccl_comm);
@@ -266,6 +267,7 @@ int dmv_ba_set_points(dmv_ba* b, int npts, const int32_t* host, const float* u, 
   if (priorF) CK(cudaMemcpy(b->d_priorF, priorF, sizeof(float) * npts, cudaMemcpyHostToDevice));
   else CK(cudaMemset(b->d_priorF, 0, sizeof(float) * npts));
   b->nres = 0;
+  b->hdi_solve_n = 0;
   b->have_tentative = b->have_committed = false;
   return DMV_OK;
 }
@@ -504,6 +506,21 @@ int dmv_ba_accumulate(dmv_ba* b, double* H_A, double* b_A, double* H_sc, double*
   if (!b) return set_error(DMV_ERR_INVALID, "null handle");
   if (!b->have_committed) return set_error(DMV_ERR_STATE, "no committed linearisation (linearize + apply_res first)");
   unpack_system(b, b->h_result[1 - b->tent], H_A, b_A, H_sc, b_sc, resInA);
+  // AccumulatedSCHessian::addPoint is also what writes EFPoint::HdiF / PointHessian::idepth_hessian (AccumulatedSCHessian.cpp:L42-50): keep
+  // the HdiF of THIS linearisation on the device (strided device-to-device copy on the handle's stream, no synchronisation) — later
+  // linearisations overwrite the per-point output buffers, dmv_ba_get_solve_HdiF() still returns these
+  CK(cudaSetDevice(b->device));
+  CK(cudaMemcpy2DAsync(b->d_hdi_solve, sizeof(float), b->d_pout[1 - b->tent] + 6, 8 * sizeof(float), sizeof(float), b->npts, cudaMemcpyDeviceToDevice, b->stream));
+  b->hdi_solve_n = b->npts;
+  return DMV_OK;
+}
+
+int dmv_ba_get_solve_HdiF(dmv_ba* b, float* HdiF) {
+  if (!b || !HdiF) return set_error(DMV_ERR_INVALID, "null argument");
+  if (b->hdi_solve_n != b->npts || b->npts < 1) return set_error(DMV_ERR_STATE, "no dmv_ba_accumulate since the points were set");
+  CK(cudaSetDevice(b->device));
+  CK(cudaMemcpyAsync(HdiF, b->d_hdi_solve, sizeof(float) * b->npts, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
   return DMV_OK;
 }
 

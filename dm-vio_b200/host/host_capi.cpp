@@ -52,6 +52,11 @@ int dmvh_window_set_points(void* p, int n, const int32_t* host, const float* u, 
   static_cast<WindowBA*>(p)->insertPoints(n, host, u, v, idepth, idepth_zero, color8, weights8, hdp);
   return 0;
 }
+int dmvh_window_set_points_carry(void* p, int n, const int32_t* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
+                                 const float* color8, const float* weights8, const uint8_t* hdp, const int32_t* carry_from) {
+  static_cast<WindowBA*>(p)->insertPoints(n, host, u, v, idepth, idepth_zero, color8, weights8, hdp, carry_from);
+  return 0;
+}
 int dmvh_window_set_residuals(void* p, int n, const int32_t* point, const int32_t* target) {
   static_cast<WindowBA*>(p)->insertResiduals(n, point, target);
   return 0;

@@ -14,6 +14,9 @@ int dmvh_window_add_frame(void* win, const float* data, int is_image, const doub
 void dmvh_window_drop_frame(void* win, int idx); /* the frame leaves the window; its image slot is reused by the next add_frame */
 int dmvh_window_set_points(void* win, int n, const int32_t* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
                            const float* color8, const float* weights8, const uint8_t* hasDepthPrior);
+/* same, with WindowBA::insertPoints' carry_from (index of each point in the previous list, -1 = newly activated) */
+int dmvh_window_set_points_carry(void* win, int n, const int32_t* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
+                                 const float* color8, const float* weights8, const uint8_t* hasDepthPrior, const int32_t* carry_from);
 int dmvh_window_set_residuals(void* win, int n, const int32_t* point, const int32_t* target);
 int dmvh_window_prepare(void* win); /* makeIDX + setAdjointsF + setPrecalcValues */
 double dmvh_window_linearize(void* win, int fix);

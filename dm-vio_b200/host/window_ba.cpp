@@ -93,6 +93,7 @@ void WindowBA::dropFrame(int idx) {
 }
 
 bool WindowBA::marginalizeFrame(int idx) {
+  err_.clear();  // per-call status: an earlier, already reported failure must not fail this call
   const int n = nf();
   if (idx < 0 || idx >= n) return false;
   for (const PointHessian& p : points)
@@ -140,10 +141,20 @@ bool WindowBA::marginalizeFrame(int idx) {
 }
 
 void WindowBA::insertPoints(int n, const int* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
-                            const float* color8, const float* weights8, const unsigned char* hasDepthPrior) {
-  points.resize(n);
+                            const float* color8, const float* weights8, const unsigned char* hasDepthPrior, const int* carry_from) {
+  // The list replaces the window's point set (ordered by host frame, EnergyFunctional::allPoints).  Per-point statistics the reference keeps
+  // on the PointHessian object (numGoodResiduals, maxRelBaseline, lastResiduals: HessianBlocks.h:L440-447) are RESET for every entry unless
+  // carry_from[i] >= 0 names the point's index in the PREVIOUS list: newly activated points are hosted by older keyframes, so they land in
+  // the middle of the list and every later point changes index.
+  const std::vector<PointHessian> old(points);
+  points.assign(n, PointHessian());
   for (int i = 0; i < n; i++) {
     PointHessian& p = points[i];
+    if (carry_from && carry_from[i] >= 0 && carry_from[i] < (int)old.size()) {
+      const PointHessian& q = old[carry_from[i]];
+      p.numGoodResiduals = q.numGoodResiduals; p.maxRelBaseline = q.maxRelBaseline;
+      for (int k = 0; k < 2; k++) { p.lastResiduals_target[k] = q.lastResiduals_target[k]; p.lastResiduals_state[k] = q.lastResiduals_state[k]; }
+    }
     p.host = host[i]; p.u = u[i]; p.v = v[i]; p.idepth = idepth[i]; p.idepth_zero = idepth_zero ? idepth_zero[i] : idepth[i];
     p.idepth_backup = p.idepth; p.step = 0;
     for (int k = 0; k < 8; k++) { p.color[k] = color8[8 * i + k]; p.weights[k] = weights8[8 * i + k]; }
@@ -157,6 +168,7 @@ void WindowBA::insertResiduals(int n, const int* point, const int* target) {
 }
 
 bool WindowBA::makeIDX() {
+  err_.clear();  // per-call status: an earlier, already reported failure must not fail this call
   if (!ba_) return false;
   const int n = nf(), np = (int)points.size(), nr = (int)activeResiduals.size();
   std::vector<int> slots(n);
@@ -182,6 +194,7 @@ bool WindowBA::makeIDX() {
   const int N = 8 * n + CPARS;
   if ((int)HM.size() != N * N) { HM.assign((size_t)N * N, 0.0); bM.assign(N, 0.0); }
   have_pending_x_ = false;
+  solved_since_makeIDX_ = false;
   return true;
 }
 
@@ -284,11 +297,14 @@ std::vector<float> WindowBA::adHTdeltaF() const {  // EnergyFunctional.cpp:L175-
 }
 
 int WindowBA::marginalizePointsF(const std::vector<int>& toMargIn, const std::vector<int>& toDrop) {
+  err_.clear();  // per-call status: an earlier, already reported failure must not fail this call
   if (!ba_) return -1;
   const int n = nf(), N = 8 * n + CPARS, np = (int)points.size();
   // FullSystem.cpp:L840-850: a candidate is marginalised only if its inverse depth is well constrained, otherwise dropped
+  // PointHessian::idepth_hessian is written by AccumulatedSCHessian::addPoint only (AccumulatedSCHessian.cpp:L42-50), i.e. during the LAST
+  // solveSystemF — not by the tail's linearizeAll(true): use the HdiF cached there (no solve yet: idepth_hessian = 0, candidates are dropped)
   std::vector<float> HdiF(np, 0.f);
-  if (np > 0) dmv_ba_get_point_outputs(ba_, nullptr, nullptr, nullptr, HdiF.data(), nullptr);  // no linearisation yet: idepth_hessian = 0, candidates are dropped
+  if (np > 0 && solved_since_makeIDX_ && dmv_ba_get_solve_HdiF(ba_, HdiF.data()) != DMV_OK) { fail("dmv_ba_get_solve_HdiF"); return -1; }
   {  // the residual states live on the device (applyRes_Reductor commits there): pull them for the re-upload below
     const int nr = (int)activeResiduals.size();
     std::vector<int32_t> ns(nr);
@@ -507,6 +523,7 @@ void WindowBA::solveSystemF(int iteration, double lambda) {
   const int n = nf(), N = 8 * n + CPARS;
   last_HA.assign((size_t)N * N, 0.0); last_bA.assign(N, 0.0); last_Hsc.assign((size_t)N * N, 0.0); last_bsc.assign(N, 0.0);
   if (dmv_ba_accumulate(ba_, last_HA.data(), last_bA.data(), last_Hsc.data(), last_bsc.data(), &resInA) != DMV_OK) { fail("dmv_ba_accumulate"); return; }
+  solved_since_makeIDX_ = true;  // the device keeps EFPoint::HdiF of this accumulation (dmv_ba_get_solve_HdiF) for marginalizePointsF
   std::vector<double> delta(N);
   for (int i = 0; i < 4; i++) delta[i] = (double)(float)Hcalib.value_minus_value_zero[i];
   for (int h = 0; h < n; h++) for (int i = 0; i < 8; i++) delta[CPARS + 8 * h + i] = frameHessians[h].delta[i];
@@ -589,6 +606,7 @@ void WindowBA::loadSateBackup() {  // FullSystemOptimize.cpp:L371-388
 }
 
 int WindowBA::optimize(int mnumOptIts, std::vector<double>* energyLog, bool finish) {
+  err_.clear();  // per-call status: an earlier, already reported failure must not fail this call
   // FullSystemOptimize.cpp:L417-647 without IMU / GTSAM / logging
   if (nf() < 2) return 0;
   if (nf() < 3) mnumOptIts = 20;
@@ -603,14 +621,12 @@ int WindowBA::optimize(int mnumOptIts, std::vector<double>* energyLog, bool fini
   double lambda = 1e-5;
   const double minLambda = 1e-5;
   int numIterations = 0;
-  const float savedTH = frameHessians.back().frameEnergyTH;
-  (void)savedTH;
   for (int iteration = 0; iteration < mnumOptIts; iteration++) {
     backupState();
-    const float th_before = frameHessians.back().frameEnergyTH;
     solveSystemF(iteration, lambda);
     doStepFromBackup();
     const double newEnergy = linearizeAll(false);
+    if (!std::isfinite(newEnergy) && !err_.empty()) return numIterations;
     const double newEnergyL = calcLEnergyF_MT();
     const double newEnergyM = calcMEnergyF();
     // doStepFromBackup's return value (L311-314), now that the device reported sum |idepth_backup|
@@ -624,12 +640,16 @@ int WindowBA::optimize(int mnumOptIts, std::vector<double>* energyLog, bool fini
       lambda *= 0.25;
       lambda = std::max(lambda, minLambda);
     } else {
-      // the reference restores the state and re-linearises; the committed linearisation is still on the device, so only the
-      // state (and the energy threshold that re-linearising would have recomputed) is restored
+      // FullSystemOptimize.cpp:L574-580: restore, then RE-LINEARISE at the restored state: the new baseline energy (and frameEnergyTH) come from
+      // that evaluation, which runs with the threshold the rejected linearisation produced.  One more fused launch; nothing is committed, the
+      // committed linearisation of the accepted state stays what solveSystemF reads.
       loadSateBackup();
-      frameHessians.back().frameEnergyTH = th_before;
+      lastEnergy = linearizeAll(false);
+      lastEnergyL = calcLEnergyF_MT();
+      lastEnergyM = calcMEnergyF();
       lambda *= 1e2;
     }
+    if (!std::isfinite(lastEnergy) && !err_.empty()) return numIterations;  // a failed device call (err_ says which), not a diverged energy
     if (energyLog) energyLog->push_back(lastEnergy);
     numIterations++;
     if (canbreak && iteration >= s.setting_minOptIterations) break;

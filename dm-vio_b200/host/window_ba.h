@@ -109,8 +109,10 @@ class WindowBA {
   // host/marg_frame.h), the frame leaves the window (its image slot becomes free) and the smaller window is re-uploaded.  The frame must not
   // host points any more (flagPointsForRemoval + marginalizePointsF first).  Returns false on error.
   bool marginalizeFrame(int idx);
+  // Replaces the point set (must be ordered by host frame).  carry_from (optional, n entries): index of the same point in the previous list, or
+  // -1 for a newly activated point; carries numGoodResiduals / maxRelBaseline / lastResiduals over, everything else is reset.
   void insertPoints(int n, const int* host, const float* u, const float* v, const float* idepth, const float* idepth_zero, const float* color8,
-                    const float* weights8, const unsigned char* hasDepthPrior);
+                    const float* weights8, const unsigned char* hasDepthPrior, const int* carry_from = nullptr);
   void insertResiduals(int n, const int* point, const int* target);
   bool makeIDX();  // uploads points/residuals (EnergyFunctional::makeIDX, EnergyFunctional.cpp:L998-1016)
 
@@ -169,6 +171,7 @@ class WindowBA {
   bool have_pending_x_ = false;      // resubstitute + point step are fused into the next linearizeAll
   std::vector<double> pending_x_;
   double step_sums_[3] = {0, 0, 0};
+  bool solved_since_makeIDX_ = false;  // dmv_ba_get_solve_HdiF is valid
   float canbreak_frames_[4] = {0, 0, 0, 0};
 };
 

@@ -43,6 +43,7 @@ def _bind(L):
         L.dmvh_window_flag_points.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int), vp, C.POINTER(C.c_int)]
         L.dmvh_window_marginalize_points.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.dmvh_window_set_points.argtypes = [vp, C.c_int, i32p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
+        L.dmvh_window_set_points_carry.argtypes = [vp, C.c_int, i32p, f32p, f32p, f32p, f32p, f32p, f32p, vp, i32p]
         L.dmvh_window_set_residuals.argtypes = [vp, C.c_int, i32p, i32p]
         L.dmvh_window_prepare.argtypes = [vp]
         L.dmvh_window_linearize.restype = C.c_double

@@ -27,6 +27,7 @@ struct dmv_ba {
   std::vector<int> slots;                   // window frame -> slot
   bool have_tentative = false, have_committed = false, have_adj = false;
   ReducedSystem sys;                        // system of the committed linearisation
+  std::vector<float> hdi_solve;             // EFPoint::HdiF at the last dmv_ba_accumulate
 };
 struct dmv_ct {
   CoarseTracker ct;
@@ -95,6 +96,7 @@ int dmv_ba_set_points(dmv_ba* b, int npts, const int32_t* host, const float* u, 
                       const float* color8, const float* weights8, const float* priorF) {
   Window& W = b->W;
   W.points.assign(npts, Point());
+  b->hdi_solve.clear();
   for (int i = 0; i < npts; i++) {
     Point& p = W.points[i];
     if (i > 0 && host[i] < host[i - 1]) return fail(DMV_ERR_INVALID, "points must be ordered by host frame");
@@ -203,6 +205,13 @@ int dmv_ba_accumulate(dmv_ba* b, double* HA, double* bA, double* Hsc, double* bs
   if (Hsc) std::memcpy(Hsc, b->sys.Hsc.d.data(), sizeof(double) * N * N);
   if (bsc) std::memcpy(bsc, b->sys.bsc.data(), sizeof(double) * N);
   if (resInA) *resInA = b->sys.resInA;
+  b->hdi_solve.resize(b->W.points.size());  // what AccumulatedSCHessian::addPoint left in EFPoint::HdiF for THIS accumulation
+  for (size_t i = 0; i < b->W.points.size(); i++) b->hdi_solve[i] = b->W.points[i].HdiF;
+  return DMV_OK;
+}
+int dmv_ba_get_solve_HdiF(dmv_ba* b, float* HdiF) {
+  if (b->hdi_solve.size() != b->W.points.size()) return fail(DMV_ERR_STATE, "no dmv_ba_accumulate since the points were set");
+  for (size_t i = 0; i < b->hdi_solve.size(); i++) HdiF[i] = b->hdi_solve[i];
   return DMV_OK;
 }
 int dmv_ba_get_residual_outputs(dmv_ba* b, int32_t* ns, float* ne, float* nw, float* cpt3, float* jp8) {

@@ -306,3 +306,43 @@ def test_keyframe_stream_with_prior_matches_oracle(hostapi, orc, synth):
     o3 = orc.Window(W3); o3.optimize(4, precision=1)
     assert np.abs(o3.frame_states() - ow.frame_states()).max() > 10 * np.abs(st_g - ow.frame_states()).max()
     hw.close()
+
+
+def test_insert_points_on_older_host_keeps_the_other_points_statistics(hostapi, synth):
+    """newly activated points are hosted by OLDER keyframes, so they land in the middle of the host-ordered list and every later
+    point changes index.  insertPoints resets the per-point statistics (numGoodResiduals, maxRelBaseline, lastResiduals) unless carry_from maps
+    an entry to its previous index; flagPointsForRemoval (isOOB / isInlierNew) must then see each point's OWN history."""
+    W = synth.make_window(nf=4, npts=300, seed=11)
+    hw = hostapi.WindowBA(W)
+    hw.optimize(3)
+    hw.finish_optimize()                       # linearizeAll(true): numGoodResiduals / maxRelBaseline are now non-trivial
+    s0 = hw.point_stats()
+    assert s0["numGoodResiduals"].max() > 0 and len(set(np.round(s0["maxRelBaseline"], 6))) > 10
+    _, idepth, _ = hw.states()
+    n = hw.npts
+    host = np.asarray(W["host"])
+    # 20 new points hosted by frame 0 (the oldest): inserted after frame 0's existing points, i.e. in the middle of the list
+    n0 = int((host == 0).sum())
+    new = np.arange(20)
+    order_old = np.concatenate([np.arange(n0), -np.ones(20, np.int64), np.arange(n0, n)])   # previous index of every entry, -1 = new
+    pick = lambda a, fill: np.concatenate([np.asarray(a)[:n0], fill, np.asarray(a)[n0:]])
+    host2 = pick(host, np.zeros(20, np.int32)).astype(np.int32)
+    u2, v2 = pick(W["u"], W["u"][new] + 3).astype(np.float32), pick(W["v"], W["v"][new] + 3).astype(np.float32)
+    id2 = pick(idepth, idepth[new]).astype(np.float32)
+    col2 = np.concatenate([W["color"][:n0], W["color"][new], W["color"][n0:]]).astype(np.float32)
+    wgt2 = np.concatenate([W["weights"][:n0], W["weights"][new], W["weights"][n0:]]).astype(np.float32)
+    c = lambda a, t: np.ascontiguousarray(a, t)
+    L = hw.L
+    L.dmvh_window_set_points_carry(hw.h, len(host2), host2, u2, v2, id2, id2, c(col2, np.float32).reshape(-1), c(wgt2, np.float32).reshape(-1), None,
+                                   c(order_old, np.int32))
+    hw.npts = len(host2)
+    s1 = hw.point_stats()
+    old = order_old >= 0
+    np.testing.assert_array_equal(s1["numGoodResiduals"][old], s0["numGoodResiduals"])      # every surviving point kept ITS OWN history
+    np.testing.assert_array_equal(s1["maxRelBaseline"][old], s0["maxRelBaseline"])
+    assert np.all(s1["numGoodResiduals"][~old] == 0) and np.all(s1["maxRelBaseline"][~old] == 0)
+    # without the map everything is reset (never another point's values)
+    L.dmvh_window_set_points(hw.h, len(host2), host2, u2, v2, id2, id2, c(col2, np.float32).reshape(-1), c(wgt2, np.float32).reshape(-1), None)
+    s2 = hw.point_stats()
+    assert np.all(s2["numGoodResiduals"] == 0) and np.all(s2["maxRelBaseline"] == 0)
+    hw.close()
