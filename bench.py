@@ -3,22 +3,28 @@
 
 One "step" = one Gauss-Newton iteration of the hot path on the 7-keyframe / 2000-point / 640x480 synthetic window
 (SURVEY.md §8d): resubstitute(x) + point step, residual/Jacobian evaluation of every active point-residual, per-pair
-Hessian blocks, per-point Schur complement, fp64 stitch to the dense (8nf+4)^2 system — the dense host solve excluded.
+Hessian blocks, per-point Schur complement, adjoint products to the dense (8nf+4)^2 system — ONE kernel launch
+(ba_fused_kernel); the dense host solve is excluded, as in the metric's definition.
 
-  value      device-resident throughput: all inputs in HBM, CUDA-event time of the kernel sequence, L2 scrubbed between steps
-  e2e        the same step through the C ABI call a DM-VIO host would make (dmv_ba_gn_step + dmv_ba_apply_res):
-             host buffers in, H/b out, H2D + D2H copies and the stream synchronisation inside the timed region
-  roofline   algorithmic bytes of the dominant kernel (ba_point_kernel) / its CUDA-event duration vs measured HBM peak
-  cpu_baseline   the CPU oracle (restatement of the reference's SSE path, 6 worker threads like NUM_THREADS) on this host
+  value      device-resident throughput: all inputs in HBM, CUDA-event time of the launch, L2 scrubbed between steps
+  e2e        the same step through the C ABI call a DM-VIO host makes (dmv_ba_gn_step + dmv_ba_apply_res):
+             host buffers in, H/b out, host<->device traffic and the stream synchronisation inside the timed region
+  roofline   algorithmic bytes of ba_fused_kernel / its CUDA-event duration vs the measured HBM peak
+  roofline_batched   the same kernel body over B independent windows in ONE launch (planes of B windows exceed L2): the
+             regime in which the HBM roofline is meaningful (SURVEY.md §8d "batched variant")
+  parity     H_A, b_A, H_sc, b_sc of the first step (all-reduced over the ranks) vs the UNSHARDED CPU oracle, outside the
+             timed region; the run fails above 1e-5 / 1e-4
+  cpu_baseline   the CPU oracle (restatement of the reference's SSE path) on this host (N = 1 only)
 
-N > 1 (torchrun): weak scaling — every rank owns 2000 points of one N*2000-point window (images and tables replicated),
-the stitched system is all-reduced over NCCL inside every step.
-`--impl reference` times the CPU oracle only (rank 0), same metric/config.
+N > 1 (torchrun): the headline is weak scaling — every rank owns 2000 points of one N*2000-point window (images and tables
+replicated), the system is all-reduced inside the kernel over NVLink peer memory.  The same line also carries
+  strong     2000 points in total split over the N ranks (BASELINE's metric window at N GPUs)
+  config4    BASELINE config 4: 8000 points in total split over the N ranks
+`--impl reference` times the CPU path only (rank 0), same metric/config.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -32,6 +38,7 @@ import numpy as np  # noqa: E402
 METRIC = "point-residuals/sec per GN iter (7 KF, 2000 pts, 640x480)"
 UNIT = "point-residuals/s"
 NF, NPTS, W_, H_ = 7, 2000, 640, 480
+PARITY_TOL = {"HA": 1e-5, "Hsc": 1e-5, "bA": 1e-4, "bsc": 1e-4, "energy": 2e-5}
 
 
 class ClockSampler:
@@ -52,8 +59,7 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            # honour CUDA_VISIBLE_DEVICES-free boxes: NVML index == CUDA ordinal on the gpurun boxes
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)  # NVML index == CUDA ordinal on the gpurun boxes
             self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
             self.h = None
@@ -108,12 +114,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of ba_point_kernel from the newest committed `ncu --set full` capture
-    (profiles/*_ba_point_summary.md, written by tools/summarize_profiles.py); None if there is none."""
+def ncu_traffic(pattern="*_ba_fused_summary.md"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the newest committed `ncu --set full` capture of the kernel
+    (profiles/<pattern>, written by tools/summarize_profiles.py); None if there is none."""
     import glob
     import re
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ba_point_summary.md")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)))
     if not files:
         return None, None
     rd = wr = None
@@ -137,25 +143,59 @@ def algorithmic_bytes(nres, npts, nf):
     return 436 * nres + 112 * npts + 8 * N * (N + 1)
 
 
-def cpu_oracle_rate(W, seconds, threads, x=None):
-    """times the oracle's hot iteration (accumulate+stitch, resubstitute, step, linearizeAll, applyRes); returns (res/s, ms/iter, iters)."""
-    from oracle import orc
-    ow = orc.Window(W, nthreads=threads)
-    ow.linearize_all()
-    ow.apply_res()
-    if x is None:
+# ----------------------------------------------------------------------------------------------------------------- CPU legs
+def _pin(threads):
+    """pin the process (and the worker threads it creates) to `threads` logical CPUs: less migration noise on a shared host"""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        if len(cpus) > threads:
+            os.sched_setaffinity(0, set(cpus[:threads]))
+            return cpus[:threads]
+    except Exception:
+        pass
+    return None
+
+
+def _unpin(all_cpus):
+    try:
+        os.sched_setaffinity(0, all_cpus)
+    except Exception:
+        pass
+
+
+def cpu_rate(W, seconds, threads, kind="port", blocks=5, pin=True):
+    """times the CPU path's hot iteration (accumulate + stitch, resubstitute, step, linearizeAll, applyRes) for >= `seconds` in `blocks`
+    blocks; returns median-of-blocks rate.  kind = "port": the oracle restatement; "reference": the reference's own translation units
+    (oracle/_ref/libdso_ref.so, built from /root/reference over stand-in Eigen headers — slower than the port)."""
+    all_cpus = os.sched_getaffinity(0)
+    pinned = _pin(threads) if pin else None
+    try:
+        if kind == "reference":
+            from oracle import ref
+            ow = ref.Window(W, nthreads=threads)
+        else:
+            from oracle import orc
+            ow = orc.Window(W, nthreads=threads)
+        ow.linearize_all(update_th=False)
+        ow.apply_res()
         x, _, _ = ow.solve(0, 1e-5, 0)
-    for _ in range(2):
-        ow.hot_iteration(x, 0)
-    t0 = time.perf_counter()
-    n = 0
-    while True:
-        ow.hot_iteration(x, 0)
-        n += 1
-        if time.perf_counter() - t0 >= seconds:
-            break
-    dt = (time.perf_counter() - t0) / n
-    return ow.nres / dt, dt * 1e3, n, ow
+        for _ in range(3):
+            ow.hot_iteration(x, 0)
+        rates, total = [], 0
+        for _ in range(blocks):
+            t0 = time.perf_counter()
+            n = 0
+            while True:
+                ow.hot_iteration(x, 0)
+                n += 1
+                if time.perf_counter() - t0 >= seconds / blocks:
+                    break
+            rates.append(ow.nres * n / (time.perf_counter() - t0))
+            total += n
+        return {"rate": float(np.median(rates)), "rate_min": float(min(rates)), "rate_max": float(max(rates)), "iters": total,
+                "ms_per_iter": ow.nres / float(np.median(rates)) * 1e3, "pinned_cpus": len(pinned) if pinned else None, "nres": ow.nres}
+    finally:
+        _unpin(all_cpus)
 
 
 def pick_threads(W, candidates=(6, 12, 24, 48), seconds=1.0):
@@ -167,11 +207,21 @@ def pick_threads(W, candidates=(6, 12, 24, 48), seconds=1.0):
     for t in candidates:
         if t > ncpu:
             continue
-        rate, _, _, _ = cpu_oracle_rate(W, seconds, t)
-        rates[t] = rate
-        if rate > best[0]:
-            best = (rate, t)
+        r = cpu_rate(W, seconds, t, blocks=2)["rate"]
+        rates[t] = r
+        if r > best[0]:
+            best = (r, t)
     return best[1], rates
+
+
+def run_ref_courtesy(npts):
+    """child process of run_reference: the reference's OWN translation units (oracle/_ref) on the same window, 6 threads"""
+    import dmvio_b200.synth as synth
+    W = synth.make_window(nf=NF, npts=npts, w=W_, h=H_, seed=1234)
+    rr = cpu_rate(W, 2.0, 6, kind="reference", blocks=2)
+    print(json.dumps({"value": rr["rate"], "cores": 6, "kind": "reference", "iters": rr["iters"], "ms_per_iter": rr["ms_per_iter"],
+                      "what": "ref_win_hot_iteration of oracle/_ref/libdso_ref.so = the reference's own sources compiled over stand-in Eigen/Sophus headers "
+                              "(their heap temporaries make it slower than real Eigen would be): the lower bound of 'the reference's CPU path', the port is the upper one"}))
 
 
 def run_reference(args, rank, world):
@@ -180,31 +230,249 @@ def run_reference(args, rank, world):
     import dmvio_b200.synth as synth
     W = synth.make_window(nf=NF, npts=NPTS * world, w=W_, h=H_, seed=1234)
     threads, rates = pick_threads(W)
-    from oracle import orc
-    ow = orc.Window(W, nthreads=threads)
-    ow.linearize_all(); ow.apply_res()
-    x, _, _ = ow.solve(0, 1e-5, 0)
-    for _ in range(max(3, args.warmup)):
-        ow.hot_iteration(x, 0)
-    steps = min(args.steps, 20000)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        ow.hot_iteration(x, 0)
-    dt = (time.perf_counter() - t0) / steps
-    val = ow.nres / dt
+    # a bounded sample that is long enough to mean something on a shared host: >= 4 s in 5 blocks, median (the driver's --steps is a
+    # lower bound on the iteration count, not the sample size: 20 steps = 0.1 s measured anything between 2.4 and 3.5 M/s in round 1)
+    seconds = max(4.0, args.steps * 0.005)
+    r = cpu_rate(W, seconds, threads)
+    val = r["rate"]
+    ref_courtesy = None
+    try:  # in a child process: the reference's objects print to stdout and abort() on paths the harness does not cover
+        import subprocess
+        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdso_ref.so")):
+            cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-courtesy", "--points", str(NPTS * world)],
+                                capture_output=True, text=True, timeout=120)
+            last = [ln for ln in cp.stdout.splitlines() if ln.startswith("{")]
+            ref_courtesy = json.loads(last[-1]) if last else {"unavailable": f"child rc={cp.returncode}"}
+        else:
+            ref_courtesy = {"unavailable": "oracle/_ref/libdso_ref.so not built"}
+    except Exception as e:  # the courtesy number must never break the arm
+        ref_courtesy = {"unavailable": str(e)[:200]}
     out = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"sliding window {NF} KF / {NPTS * world} pts / {W_}x{H_}, pattern 8, {ow.nres} point-residuals, one GN iteration "
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": r["iters"], "warmup": 3,
+        "ms_per_step": r["ms_per_iter"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"sliding window {NF} KF / {NPTS * world} pts / {W_}x{H_}, pattern 8, {r['nres']} point-residuals, one GN iteration "
                                "of the hot path per step (host solve excluded)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{steps} full GN iterations of the window; oracle = CPU restatement of the reference's SSE path, g++ -O3 (no -march, as the "
-                                   f"reference's CMakeLists), {threads} worker threads = best of {{{', '.join(f'{t}: {r / 1e6:.2f} M/s' for t, r in rates.items())}}} "
-                                   f"on this {os.cpu_count()}-thread host (the reference hard-codes NUM_THREADS=6; its own sources do compile here against stand-in headers, oracle/_ref, but run 2-5x slower than this port because of the stand-in matrix class, so timing them would flatter the GPU: DESIGN.md section 2)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "value_min_block": r["rate_min"], "value_max_block": r["rate_max"],
+                         "value_at_NUM_THREADS_6": rates.get(6),
+                         "sample": f"{r['iters']} full GN iterations of the window in {seconds:.1f} s (5 blocks, median; process pinned to {r['pinned_cpus']} CPUs); oracle = CPU "
+                                   f"restatement of the reference's SSE path, g++ -O3 (no -march, as the reference's CMakeLists), {threads} worker threads = best of "
+                                   f"{{{', '.join(f'{t}: {v / 1e6:.2f} M/s' for t, v in rates.items())}}} on this {os.cpu_count()}-thread host (the reference hard-codes NUM_THREADS=6)",
+                         "reference_sources_courtesy": ref_courtesy},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------------------------------- GPU arm
+class Dist:
+    """torch.distributed plumbing (NCCL backend for the bootstrap, barriers and max-over-ranks; the data plane is the kernel's own)."""
+
+    def __init__(self, world, local_rank):
+        self.world = world
+        self.dist = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.dist, self.torch = dist, torch
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max(self, v):
+        if self.dist is None:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min_int(self, v):
+        if self.dist is None:
+            return v
+        t = self.torch.tensor([v], device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return int(t.item())
+
+    def gather(self, obj):
+        if self.dist is None:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def bcast(self, obj, src=0):
+        if self.dist is None:
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=src)
+        return box[0]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+class Case:
+    """one window (npts_total points in total) sharded over the ranks, loaded into a BA handle"""
+
+    def __init__(self, D, rank, world, local_rank, npts_total, chunk, exchange, seed=1234):
+        import dmvio_b200.capi as capi
+        import dmvio_b200.hostmath as hm
+        import dmvio_b200.synth as synth
+        from dmvio_b200.sharding import shard_window
+        self.D, self.rank, self.world = D, rank, world
+        self.Wfull = synth.make_window(nf=NF, npts=npts_total, w=W_, h=H_, seed=seed)
+        Wr = self.Wr = shard_window(self.Wfull, rank, world)
+        self.nres_local, self.nres_total = len(Wr["res_point"]), len(self.Wfull["res_point"])
+        ba = self.ba = capi.BA(W_, H_, max_frames=NF, max_points=len(Wr["host"]), device=local_rank, chunk_points=chunk)
+        for k in range(NF):
+            ba.upload_frame(k, Wr["dI"][k])
+        ba.set_window(NF)
+        ba.set_points(Wr["host"], Wr["u"], Wr["v"], Wr["idepth"], Wr["idepth_zero"], Wr["color"], Wr["weights"])
+        ba.set_residuals(Wr["res_point"], Wr["res_target"])
+        adH, adT = hm.adjoints(Wr)
+        ba.set_adjoints(adH, adT)
+        self.k8, self.precalc, self.TH = hm.calib8(Wr["K"]), hm.precalc_table(Wr), Wr["frameEnergyTH"].copy()
+        self.exchange = "none"
+        if world > 1:
+            self.exchange = exchange
+            if exchange == "p2p":
+                try:
+                    mine = ba.p2p_export()
+                    handles = D.gather(mine)   # doubles as the barrier after every inbox has been zeroed
+                    ba.p2p_import(world, rank, handles)
+                    ok = 1
+                except Exception as e:  # no peer access between these GPUs: fall back to NCCL on ALL ranks
+                    sys.stderr.write(f"[rank {rank}] peer-memory exchange unavailable ({e}); using NCCL\n")
+                    ok = 0
+                if D.min_int(ok) == 0:
+                    self.exchange = "nccl"
+                    try:
+                        ba.p2p_import(1, 0, [mine])  # nranks = 1 switches the peer exchange off again
+                    except Exception:
+                        pass
+            if self.exchange == "nccl":
+                ba.comm_init(world, rank, D.bcast(capi.nccl_unique_id() if rank == 0 else None))
+        ba.set_state(self.k8, self.precalc, self.TH)
+        self.r0 = ba.linearize()
+        self.g0 = ba.residual_outputs()
+        ba.apply_res()
+        self.acc = ba.accumulate()
+        HL, bL = hm.prior_system(Wr)
+        self.x = hm.solve_reduced(self.acc["HA"], self.acc["bA"], self.acc["Hsc"], self.acc["bsc"], HL, bL, lam=1e-5)
+        ba.backup_points()
+
+    def parity(self):
+        """first step vs the UNSHARDED oracle (test infrastructure, outside every timed region): the ranks' classifications are gathered and
+        imposed on the oracle (threshold ties), then the all-reduced system every rank holds is compared on rank 0"""
+        states = self.D.gather((self.Wr.get("shard_res_index"), self.g0["newState"]))
+        if self.rank != 0:
+            return None
+        from oracle import orc
+        full = np.zeros(self.nres_total, np.int32)
+        for idx, ns in states:
+            if idx is None:
+                full[:] = ns
+            else:
+                full[idx] = ns
+        ow = orc.Window(self.Wfull, nthreads=min(16, os.cpu_count() or 1))
+        ow.linearize_all(update_th=False)
+        E, nch, bad = ow.override_new_states(full)
+        ow.apply_res()
+        a = ow.accumulate(1)
+        rel = lambda g, o: float(np.linalg.norm(np.asarray(g) - o) / max(np.linalg.norm(o), 1e-300))
+        out = {k: rel(self.acc[k], a[k]) for k in ("HA", "bA", "Hsc", "bsc")}
+        out["energy"] = abs(self.r0["energy"] - E) / abs(E)
+        out["threshold_ties_imposed"] = nch
+        out["unfixable_oob_ties"] = bad
+        out["n_in"] = [int(self.r0["n_in"]), int(a["resInA"])]
+        out["ok"] = bool(bad == 0 and all(out[k] <= PARITY_TOL[k] for k in PARITY_TOL) and int(self.r0["n_in"]) == int(a["resInA"]))
+        out["tolerance"] = PARITY_TOL
+        return out
+
+    def measure(self, steps, warmup, sampler=None):
+        ba, D, x = self.ba, self.D, self.x
+        for _ in range(max(3, warmup)):
+            ba.gn_step(x, self.k8, self.precalc, self.TH)
+            ba.apply_res()
+        ba.bench_device(x, iters=max(3, warmup), flush_l2=True)
+        launches0 = ba.launch_count()
+        # ---- value: device-resident, CUDA events, L2 scrubbed between steps
+        D.barrier()
+        tw0 = time.perf_counter()
+        ms_iter, ms_kernel, done = 0.0, 0.0, 0
+        while done < steps:  # dmv_ba_bench_device takes at most 4096 iterations per call
+            n = min(2048, steps - done)
+            a, b_ = ba.bench_device(x, iters=n, flush_l2=True)
+            ms_iter += a * n; ms_kernel += b_ * n; done += n
+        ms_iter /= steps; ms_kernel /= steps
+        D.barrier()
+        if sampler:
+            sampler.mark(tw0, time.perf_counter())
+        ms_iter = D.max(ms_iter)
+        # ---- e2e: the C ABI call with host buffers (tables in, kernel, H/b out, sync), wall clock
+        D.barrier()
+        tw0 = time.perf_counter()
+        e2e_ms_c = ba.bench_e2e(x, self.k8, self.precalc, self.TH, iters=steps)  # the C ABI calls issued from C (what a C++ host pays)
+        D.barrier()
+        if sampler:
+            sampler.mark(tw0, time.perf_counter())
+        e2e_ms = D.max(e2e_ms_c)
+        launches = int(ba.launch_count() - launches0)
+        ba.set_timing(True)
+        ba.gn_step(x, self.k8, self.precalc, self.TH)
+        ba.apply_res()
+        tm = ba.last_timing()
+        ba.set_timing(False)
+        h2d, d2h = ba.io_bytes()
+        return {"ms_iter": ms_iter, "ms_kernel": ms_kernel, "e2e_ms": e2e_ms, "launches": launches, "device_ms_last_step": float(tm[0]),
+                "h2d": h2d, "d2h": d2h, "value": self.nres_total / (ms_iter * 1e-3), "e2e_value": self.nres_total / (e2e_ms * 1e-3)}
+
+    def close(self):
+        self.ba.close()
+
+
+def batched_roofline(B, steps, warmup, chunk, local_rank, peak):
+    """B independent windows (different images / points) in ONE ba_fused_batch_kernel launch; planes of B windows = B x 34 MB > L2."""
+    import dmvio_b200.capi as capi
+    import dmvio_b200.hostmath as hm
+    import dmvio_b200.synth as synth
+    bas, xs, states, nres, balg = [], [], [], 0, 0
+    for i in range(B):
+        W = synth.make_window(nf=NF, npts=NPTS, w=W_, h=H_, seed=1234 + 17 * i)
+        ba = capi.BA(W_, H_, max_frames=NF, max_points=len(W["host"]), device=local_rank, chunk_points=chunk)
+        for k in range(NF):
+            ba.upload_frame(k, W["dI"][k])
+        ba.set_window(NF)
+        ba.set_points(W["host"], W["u"], W["v"], W["idepth"], W["idepth_zero"], W["color"], W["weights"])
+        ba.set_residuals(W["res_point"], W["res_target"])
+        ba.set_adjoints(*hm.adjoints(W))
+        st = (hm.calib8(W["K"]), hm.precalc_table(W), W["frameEnergyTH"].copy())
+        ba.set_state(*st)
+        ba.linearize(); ba.apply_res()
+        a = ba.accumulate()
+        HL, bL = hm.prior_system(W)
+        xs.append(hm.solve_reduced(a["HA"], a["bA"], a["Hsc"], a["bsc"], HL, bL, lam=1e-5))
+        ba.backup_points()
+        bas.append(ba); states.append(st)
+        nres += len(W["res_point"]); balg += algorithmic_bytes(len(W["res_point"]), len(W["host"]), NF)
+    batch = capi.BABatch(bas)
+    ms, e2e_ms, identical = batch.bench(xs, states, iters=steps, warmup=max(3, warmup))
+    ach = balg / (ms * 1e-3) / 1e9
+    traffic, src = ncu_traffic("*_ba_fused_batch_summary.md")
+    out = {"bound": "hbm", "kernel": f"ba_fused_batch_kernel ({B} windows / launch)", "windows": B, "point_residuals": nres, "achieved": ach, "peak": peak, "unit": "GB/s",
+           "frac": ach / peak, "traffic": traffic, "traffic_source": src, "algorithmic_bytes_per_launch": balg, "kernel_ms": ms,
+           "value": nres / (ms * 1e-3), "e2e_value": nres / (e2e_ms * 1e-3), "e2e_ms": e2e_ms, "unit_value": UNIT,
+           "l2": f"no scrub: the {B} windows' level-0 planes ({B} x 34 MB as float4) exceed the 126 MB L2",
+           "results_identical_to_single_window_launches": identical}
+    batch.close()
+    for b in bas:
+        b.close()
+    return out
 
 
 def main():
@@ -213,191 +481,121 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunk", type=int, default=0, help="points per thread block (8/16/32, 0 = library default)")
+    ap.add_argument("--chunk", type=int, default=0, help="points per thread block (16/32, 0 = library default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--points", type=int, default=0,
-                    help="points per GPU; default 2000 = BASELINE.json configs[1] (the headline).  8000 = SURVEY config 4, an extra data point only")
+                    help="points per GPU of the headline line; default 2000 = BASELINE.json configs[1].  Other values relabel the metric")
+    ap.add_argument("--batch", type=int, default=8, help="windows per launch of the batched roofline record (N = 1 only); 0 = skip")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / config-4 / batched side records")
+    ap.add_argument("--ref-courtesy", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1: all-reduce of the stitched system by the peer-memory kernel (NVLink, CUDA IPC) or by NCCL")
+                    help="N>1: all-reduce of the system inside the kernel over NVLink peer memory (CUDA IPC) or by NCCL behind it")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.steps < 1:
-        args.steps = 1
+    args.steps = max(1, args.steps)
+    global NPTS, METRIC
     if args.points > 0:
-        global NPTS, METRIC
         NPTS = args.points
         METRIC = METRIC.replace("2000 pts", f"{NPTS} pts")
+    if args.ref_courtesy:
+        run_ref_courtesy(args.points or NPTS)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
 
-    import dmvio_b200.capi as capi
-    import dmvio_b200.hostmath as hm
-    import dmvio_b200.synth as synth
-    from dmvio_b200.sharding import shard_window
-
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    # ---------------- workload (identical on every rank: seeded)
-    Wfull = synth.make_window(nf=NF, npts=NPTS * world, w=W_, h=H_, seed=1234)
-    Wr = shard_window(Wfull, rank, world)
-    nres_local = len(Wr["res_point"])
-    nres_total = len(Wfull["res_point"])
-    ba = capi.BA(W_, H_, max_frames=NF, max_points=len(Wr["host"]), device=local_rank, chunk_points=args.chunk)
-    for k in range(NF):
-        ba.upload_frame(k, Wr["dI"][k])
-    ba.set_window(NF)
-    ba.set_points(Wr["host"], Wr["u"], Wr["v"], Wr["idepth"], Wr["idepth_zero"], Wr["color"], Wr["weights"])
-    ba.set_residuals(Wr["res_point"], Wr["res_target"])
-    adH, adT = hm.adjoints(Wr)
-    ba.set_adjoints(adH, adT)
-    k8 = hm.calib8(Wr["K"])
-    precalc = hm.precalc_table(Wr)
-    TH = Wr["frameEnergyTH"].copy()
-    exchange = "none"
-    if world > 1:
-        exchange = args.exchange
-        if exchange == "p2p":
-            try:
-                mine = ba.p2p_export()
-                handles = [None] * world
-                dist.all_gather_object(handles, mine)   # doubles as the barrier after every inbox has been zeroed
-                ba.p2p_import(world, rank, handles)
-                ok = 1
-            except Exception as e:  # no peer access between these GPUs: fall back to NCCL on ALL ranks
-                sys.stderr.write(f"[rank {rank}] peer-memory exchange unavailable ({e}); using NCCL\n")
-                ok = 0
-            import torch
-            t_ok = torch.tensor([ok], device="cuda")
-            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-            if int(t_ok.item()) == 0:
-                exchange = "nccl"
-                try:
-                    ba.p2p_import(1, 0, [mine])  # nranks = 1 switches the peer exchange off again
-                except Exception:
-                    pass
-        if exchange == "nccl":
-            uid = [capi.nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(uid, src=0)
-            ba.comm_init(world, rank, uid[0])
-    ba.set_state(k8, precalc, TH)
-    r0 = ba.linearize()
-    ba.apply_res()
-    acc = ba.accumulate()
-    HL, bL = hm.prior_system(Wr)
-    if os.environ.get("DMV_DBG", "0") != "0":  # kernel ablation experiments produce meaningless systems
-        x = np.zeros(8 * NF + 4)
-    else:
-        x = hm.solve_reduced(acc["HA"], acc["bA"], acc["Hsc"], acc["bsc"], HL, bL, lam=1e-5)
-    ba.backup_points()
-
-    def barrier():
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        import torch
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---------------- warm-up (both paths)
-    for _ in range(max(3, args.warmup)):
-        ba.gn_step(x, k8, precalc, TH)
-        ba.apply_res()
-    ba.bench_device(x, iters=max(3, args.warmup), flush_l2=True)
-
-    launches0 = ba.launch_count()
+    D = Dist(world, local_rank)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # ---------------- value: device-resident, CUDA events, L2 scrubbed between steps
-    barrier()
-    tw0 = time.perf_counter()
-    ms_iter, ms_point, done = 0.0, 0.0, 0
-    while done < args.steps:  # dmv_ba_bench_device takes at most 4096 iterations per call
-        n = min(2048, args.steps - done)
-        a, b_ = ba.bench_device(x, iters=n, flush_l2=True)
-        ms_iter += a * n; ms_point += b_ * n; done += n
-    ms_iter /= args.steps; ms_point /= args.steps
-    barrier()
-    sampler.mark(tw0, time.perf_counter())
-    ms_iter = max_over_ranks(ms_iter)
-    launches_value = ba.launch_count() - launches0
-    # ---------------- e2e: the C ABI call with host buffers (H2D + kernels + D2H + sync), wall clock
-    barrier()
-    tw0 = time.perf_counter()
-    e2e_ms_c = ba.bench_e2e(x, k8, precalc, TH, iters=args.steps)  # the C ABI calls issued from C (what a C++ host pays)
-    barrier()
-    sampler.mark(tw0, time.perf_counter())
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ba.gn_step(x, k8, precalc, TH)
-        ba.apply_res()
-    barrier()
-    e2e_ms_py = (time.perf_counter() - t0) / args.steps * 1e3       # same calls through ctypes (adds interpreter overhead)
-    e2e_ms = max_over_ranks(e2e_ms_c)
-    clocks = sampler.stop() if rank == 0 else None
-    ba.set_timing(True)
-    ba.gn_step(x, k8, precalc, TH)
-    ba.apply_res()
-    tm = ba.last_timing()
-    h2d, d2h = ba.io_bytes()
-
-    value = nres_total / (ms_iter * 1e-3)
-    e2e_value = nres_total / (e2e_ms * 1e-3)
     peak, peak_src = measured_peak()
-    balg = algorithmic_bytes(nres_local, len(Wr["host"]), NF)
+
+    # ---------------- headline: weak scaling, NPTS points per rank
+    C = Case(D, rank, world, local_rank, NPTS * world, args.chunk, args.exchange)
+    parity = C.parity()
+    m = C.measure(args.steps, args.warmup, sampler)
+    balg = algorithmic_bytes(C.nres_local, len(C.Wr["host"]), NF)
+    exchange, r0, nres_total, nres_local = C.exchange, C.r0, C.nres_total, C.nres_local
+    Wfull = C.Wfull
+    C.close()
+
+    extras = {}
+    if not args.no_extras:
+        side_steps = max(50, min(args.steps, 300))
+        if world > 1:
+            for name, total in (("strong", NPTS), ("config4", 8000)):
+                Cx = Case(D, rank, world, local_rank, total, args.chunk, args.exchange)
+                px = Cx.parity()
+                mx = Cx.measure(side_steps, min(args.warmup, 10))
+                if rank == 0:
+                    extras[name] = {"workload": f"{NF} KF / {total} pts in total ({total // world} per GPU) / {W_}x{H_}, {Cx.nres_total} point-residuals", "scaling": "strong",
+                                    "value": mx["value"], "ms_per_step": mx["ms_iter"], "e2e_value": mx["e2e_value"], "e2e_ms_per_step": mx["e2e_ms"], "unit": UNIT,
+                                    "steps": side_steps, "parity": px,
+                                    "roofline_frac": algorithmic_bytes(Cx.nres_local, len(Cx.Wr["host"]), NF) / (mx["ms_kernel"] * 1e-3) / 1e9 / peak}
+                Cx.close()
+        else:
+            Cx = Case(D, rank, world, local_rank, 8000, args.chunk, args.exchange)
+            px = Cx.parity()
+            mx = Cx.measure(side_steps, min(args.warmup, 10))
+            extras["config4_one_gpu"] = {"workload": f"{NF} KF / 8000 pts / {W_}x{H_} on ONE GPU, {Cx.nres_total} point-residuals", "value": mx["value"],
+                                         "ms_per_step": mx["ms_iter"], "e2e_value": mx["e2e_value"], "unit": UNIT, "steps": side_steps, "parity": px,
+                                         "roofline_frac": algorithmic_bytes(Cx.nres_local, 8000, NF) / (mx["ms_kernel"] * 1e-3) / 1e9 / peak}
+            Cx.close()
+            if args.batch > 0:
+                try:
+                    tw0 = time.perf_counter()
+                    extras["roofline_batched"] = batched_roofline(args.batch, side_steps, min(args.warmup, 10), args.chunk, local_rank, peak)
+                    sampler.mark(tw0, time.perf_counter())
+                except Exception as e:
+                    extras["roofline_batched"] = {"error": str(e)[:300]}
+
+    clocks = sampler.stop() if rank == 0 else None
     traffic, traffic_src = ncu_traffic()
-    ach = balg / (ms_point * 1e-3) / 1e9
+    ach = balg / (m["ms_kernel"] * 1e-3) / 1e9
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads, rates = pick_threads(Wfull)
-        rate, ms_cpu, n_it, _ = cpu_oracle_rate(Wfull, args.cpu_seconds, threads)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_iter": ms_cpu,
-               "value_at_reference_NUM_THREADS_6": rates.get(6),
-               "sample": f"{n_it} full GN iterations of the same window in ~{args.cpu_seconds:.0f} s, oracle (g++ -O3, no -march), "
-                         f"{threads} worker threads (best of {sorted(rates)}; the reference hard-codes NUM_THREADS=6); host has {os.cpu_count()} logical cores"}
+        r = cpu_rate(Wfull, args.cpu_seconds, threads)
+        cpu = {"value": r["rate"], "unit": UNIT, "cores": threads, "kind": "port", "ms_per_iter": r["ms_per_iter"],
+               "value_min_block": r["rate_min"], "value_max_block": r["rate_max"], "value_at_reference_NUM_THREADS_6": rates.get(6),
+               "sample": f"{r['iters']} full GN iterations of the same window in ~{args.cpu_seconds:.0f} s (5 blocks, median), oracle (g++ -O3, no -march), "
+                         f"{threads} worker threads pinned to {r['pinned_cpus']} CPUs (best of {sorted(rates)}; the reference hard-codes NUM_THREADS=6); host has {os.cpu_count()} logical cores"}
 
     if rank == 0:
+        xdesc = {"p2p": ", all-reduce of H,b per step inside ba_fused_kernel (LL packets over NVLink peer memory, CUDA IPC)", "nccl": ", NCCL all-reduce of H,b per step", "none": ""}[exchange]
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_iter, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": m["ms_iter"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"sliding window {NF} KF / {NPTS * world} pts / {W_}x{H_}, pattern 8, {nres_total} point-residuals "
                                    f"({nres_local}/GPU), one GN iteration of the hot path per step (host solve excluded)",
-                       "parallelism": f"points sharded over {world} GPU(s), images replicated" + ({"p2p": ", all-reduce of H,b per step fused into ba_stitch_kernel (LL packets over NVLink peer memory, CUDA IPC)", "nccl": ", NCCL all-reduce of H,b per step", "none": ""}[exchange]),
+                       "parallelism": f"points sharded over {world} GPU(s), images replicated" + xdesc,
                        "l2": "L2 scrubbed (256 MiB write) between timed steps of `value`", "chunk_points": args.chunk or 16,
                        "n_in": r0["n_in"], "n_oob": r0["n_oob"], "n_outlier": r0["n_outlier"]},
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "device_ms_last_step": float(tm[0]), "ms_per_step_via_python_ctypes": e2e_ms_py,
-                    "timed": "steps x {dmv_ba_gn_step(host x, host tables) ; dmv_ba_apply_res()} issued from C, wall clock, incl. H2D/D2H + sync"},
-            "gpu_launches": int(ba.launch_count() - launches0),
-            "roofline": {"bound": "hbm", "kernel": "ba_point_kernel (+ ba_stitch_kernel chained by PDL)", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "e2e": {"value": m["e2e_value"], "unit": UNIT, "ms_per_step": m["e2e_ms"], "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                    "device_ms_last_step": m["device_ms_last_step"],
+                    "timed": "steps x {dmv_ba_gn_step(host x, host tables) ; dmv_ba_apply_res()} issued from C, wall clock, incl. host<->device traffic + sync"},
+            "gpu_launches": m["launches"],
+            "parity": parity,
+            "roofline": {"bound": "hbm", "kernel": "ba_fused_kernel (the whole GN linearisation: one cooperative launch)", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": balg, "kernel_ms": ms_point,
-                         "note": "working set (7 level-0 planes = 34 MB as float4) is L2-sized and one window is a single wave of 129 CTAs: the step is "
-                                 "bound by instruction issue + the dependent launch/load/reduce chain, not by HBM (DESIGN.md section 6)"},
+                         "algorithmic_bytes_per_launch": balg, "kernel_ms": m["ms_kernel"],
+                         "note": "one 7-KF window is a latency-bound dependent chain (launch, gather round trip, reductions, grid barrier) on an L2-sized "
+                                 "working set: see roofline_batched for the bandwidth regime (DESIGN.md section 6)"},
             "clocks": clocks,
         }
+        out.update(extras)
         if cpu:
             out["cpu_baseline"] = cpu
         print(json.dumps(out))
-    ba.close()
-    if dist is not None:
-        dist.destroy_process_group()
+        if parity is not None and not parity["ok"]:
+            sys.stderr.write(f"PARITY FAILURE vs the unsharded oracle: {parity}\n")
+            D.close()
+            sys.exit(3)
+    D.close()
 
 
 if __name__ == "__main__":

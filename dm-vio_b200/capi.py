@@ -56,6 +56,56 @@ class IPPoints(C.Structure):
                                                               "lastTraceStatus", "lastTraceUV2", "lastTracePixelInterval")]
 
 
+class BABatch:
+    """dmv_ba_batch: B independent windows (BA handles on one device) linearised by ONE launch (include/dmvio_b200.h)."""
+
+    def __init__(self, bas):
+        self.L = lib()
+        self.bas = list(bas)
+        n = len(self.bas)
+        self._harr = (C.c_void_p * n)(*[b.h for b in self.bas])
+        h = C.c_void_p()
+        check(self.L.dmv_ba_batch_create(self._harr, n, C.byref(h)))
+        self.h = h
+
+    def _args(self, xs, states):
+        n = len(self.bas)
+        self._xs = [None if x is None else _c(x, np.float64) for x in (xs or [None] * n)]
+        self._sts = [b._state(*st) for b, st in zip(self.bas, states)]
+        xarr = (C.c_void_p * n)(*[None if x is None else x.ctypes.data for x in self._xs])
+        sarr = (C.c_void_p * n)(*[C.addressof(st) for st in self._sts])
+        return xarr, sarr
+
+    def gn_step(self, xs, states):
+        """states[i] = (calib8, precalc, TH); xs[i] = x or None.  Returns one result dict per window."""
+        n = len(self.bas)
+        xarr, sarr = self._args(xs, states)
+        res = (BALinResult * n)()
+        sums = np.zeros(3 * n)
+        check(self.L.dmv_ba_batch_gn_step(self.h, xarr, sarr, res, sums.ctypes.data))
+        return [dict(energy=r.energy, n_in=r.n_in, n_oob=r.n_oob, n_outlier=r.n_outlier, sums=sums[3 * i:3 * i + 3]) for i, r in enumerate(res)]
+
+    def bench(self, xs, states, iters=100, warmup=5):
+        """returns (kernel ms per launch [CUDA events], e2e ms per batched call [wall clock, issued from C], None)"""
+        n = len(self.bas)
+        xarr, sarr = self._args(xs, states)
+        e2e, ker = C.c_double(0), C.c_double(0)
+        check(self.L.dmv_ba_batch_bench(self.h, self._harr, n, xarr, sarr, max(1, warmup), C.byref(e2e), C.byref(ker)))
+        check(self.L.dmv_ba_batch_bench(self.h, self._harr, n, xarr, sarr, iters, C.byref(e2e), C.byref(ker)))
+        return ker.value, e2e.value, None
+
+    def close(self):
+        if self.h:
+            self.L.dmv_ba_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class CTConfig(C.Structure):
     _fields_ = [("w", C.c_int), ("h", C.c_int), ("levels", C.c_int), ("max_points", C.c_int), ("device", C.c_int)]
 
@@ -68,6 +118,7 @@ SYMBOLS = [
     "dmv_ba_get_residual_outputs", "dmv_ba_get_target_energies", "dmv_ba_apply_res", "dmv_ba_accumulate", "dmv_ba_get_point_outputs", "dmv_ba_get_solve_HdiF",
     "dmv_ba_resubstitute", "dmv_ba_backup_points", "dmv_ba_restore_points", "dmv_ba_get_idepth", "dmv_ba_gn_step", "dmv_nccl_unique_id",
     "dmv_ba_comm_init", "dmv_ba_activate_points", "dmv_ba_marginalize_points", "dmv_ba_drop_residuals", "dmv_ba_reset_oob", "dmv_ba_p2p_export", "dmv_ba_p2p_import", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e",
+    "dmv_ba_batch_create", "dmv_ba_batch_destroy", "dmv_ba_batch_gn_step", "dmv_ba_batch_set_timing", "dmv_ba_batch_last_kernel_ms", "dmv_ba_batch_bench",
     "dmv_ct_create", "dmv_ct_destroy", "dmv_ct_set_K", "dmv_ct_set_ref", "dmv_ct_make_coarse_depth", "dmv_ct_get_ref", "dmv_ct_upload_new", "dmv_ct_upload_new_image", "dmv_ct_set_huber",
     "dmv_ct_calc_res_gs", "dmv_ct_track", "dmv_ip_default_settings", "dmv_ct_init_points", "dmv_ct_trace_points", "dmv_ct_set_timing", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count",
 ]
@@ -117,6 +168,13 @@ def lib():
         L.dmv_ba_set_timing.argtypes = [vp, C.c_int]
         L.dmv_ba_bench_e2e.argtypes = [vp, vp, C.POINTER(BAState), C.c_int, C.POINTER(C.c_double)]
         L.dmv_ba_io_bytes.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+        L.dmv_ba_get_solve_HdiF.argtypes = [vp, f32p]
+        L.dmv_ba_batch_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.dmv_ba_batch_destroy.argtypes = [vp]
+        L.dmv_ba_batch_gn_step.argtypes = [vp, vp, vp, vp, vp]
+        L.dmv_ba_batch_set_timing.argtypes = [vp, C.c_int]
+        L.dmv_ba_batch_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.dmv_ba_batch_bench.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.dmv_ct_create.argtypes = [C.POINTER(CTConfig), C.POINTER(vp)]
         L.dmv_ct_destroy.argtypes = [vp]
         L.dmv_ct_set_K.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]

@@ -329,7 +329,7 @@ int dmv_ba_set_adjoints(dmv_ba* b, const double* adHost, const double* adTarget)
   return DMV_OK;
 }
 
-static int stage_state(dmv_ba* b, const dmv_ba_state* st) {
+int dmv_ba_stage_state(dmv_ba* b, const dmv_ba_state* st) {
   if (!st->precalc || !st->frameEnergyTH) return set_error(DMV_ERR_INVALID, "precalc / frameEnergyTH required");
   BAIter& it = b->h_up->it;
   const int nf = b->nf;
@@ -349,7 +349,7 @@ int dmv_ba_set_state(dmv_ba* b, const dmv_ba_state* st) {
   if (!b || !st) return set_error(DMV_ERR_INVALID, "null argument");
   if (b->npts < 1) return set_error(DMV_ERR_STATE, "dmv_ba_set_points first");
   CK(cudaSetDevice(b->device));
-  int rc = stage_state(b, st);
+  int rc = dmv_ba_stage_state(b, st);
   if (rc != DMV_OK) return rc;
   // pageable idepth sources: make the async copies complete before returning
   CK(cudaStreamSynchronize(b->stream));
@@ -379,7 +379,7 @@ static int enqueue_linearize(dmv_ba* b) {
   return DMV_OK;
 }
 
-static int finish_linearize(dmv_ba* b, dmv_ba_lin_result* out, double sums[3]) {
+int dmv_ba_finish_linearize(dmv_ba* b, dmv_ba_lin_result* out, double sums[3]) {
   if (b->h_up->it.have_x) { b->id_cur = 1 - b->id_bak; b->zero_alias = true; }  // the fused step wrote idepth_backup + step
   CK(cudaStreamSynchronize(b->stream));
   const double* tail = b->h_result[b->tent] + (b->N * b->N + b->N) + b->ntiles * 16;
@@ -411,7 +411,7 @@ int dmv_ba_linearize(dmv_ba* b, dmv_ba_lin_result* out) {
   b->h_up->it.have_x = 0;
   rc = enqueue_linearize(b);
   if (rc != DMV_OK) return rc;
-  return finish_linearize(b, out, nullptr);
+  return dmv_ba_finish_linearize(b, out, nullptr);
 }
 
 void dmv_ba_stage_x(dmv_ba* b, const double* x) {
@@ -461,12 +461,12 @@ int dmv_ba_gn_step(dmv_ba* b, const double* x, const dmv_ba_state* st, dmv_ba_li
   if (!b->have_adj) return set_error(DMV_ERR_STATE, "dmv_ba_set_adjoints first");
   if (x && !b->have_committed) return set_error(DMV_ERR_STATE, "no committed linearisation to resubstitute");
   CK(cudaSetDevice(b->device));
-  int rc = stage_state(b, st);
+  int rc = dmv_ba_stage_state(b, st);
   if (rc != DMV_OK) return rc;
   if (x) dmv_ba_stage_x(b, x); else b->h_up->it.have_x = 0;
   rc = enqueue_linearize(b);
   if (rc != DMV_OK) return rc;
-  rc = finish_linearize(b, out, sums);
+  rc = dmv_ba_finish_linearize(b, out, sums);
   b->h_up->it.have_x = 0;
   return rc;
 }

@@ -74,4 +74,29 @@ int dmv_ba_bench_e2e(dmv_ba* b, const double* x, const dmv_ba_state* st, int ite
   return DMV_OK;
 }
 
+// batched windows: `iters` x dmv_ba_batch_gn_step (+ apply_res on every handle), wall clock per call and CUDA-event time of the launch alone
+int dmv_ba_batch_bench(dmv_ba_batch* B, dmv_ba* const* handles, int n, const double* const* x, const dmv_ba_state* const* st, int iters, double* e2e_ms_per_iter,
+                       double* kernel_ms_per_iter) {
+  if (!B || !handles || !st || iters < 1) return set_error(DMV_ERR_INVALID, "bad argument");
+  int rc = dmv_ba_batch_set_timing(B, 1);
+  if (rc != DMV_OK) return rc;
+  double ksum = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < iters; i++) {
+    rc = dmv_ba_batch_gn_step(B, x, st, nullptr, nullptr);
+    if (rc != DMV_OK) return rc;
+    for (int k = 0; k < n; k++) {
+      rc = dmv_ba_apply_res(handles[k]);
+      if (rc != DMV_OK) return rc;
+    }
+    float ms = 0.f;
+    dmv_ba_batch_last_kernel_ms(B, &ms);
+    ksum += ms;
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  if (e2e_ms_per_iter) *e2e_ms_per_iter = std::chrono::duration<double, std::milli>(t1 - t0).count() / iters;
+  if (kernel_ms_per_iter) *kernel_ms_per_iter = ksum / iters;
+  return dmv_ba_batch_set_timing(B, 0);
+}
+
 }  // extern "C"

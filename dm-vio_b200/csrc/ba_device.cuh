@@ -108,6 +108,15 @@ struct BAWinDev {
   float* marg_rtz;           // [slot][8] EFResidual::res_toZeroF of the residuals linearised by the launch
 };
 
+// header of a batched launch (ba_fused_batch_kernel): B windows, work items = (window, chunk)
+constexpr int BATCH_MAX = 64;
+struct BABatchHdr {
+  int B, total;                  // windows, sum of their chunk counts
+  int prefix[BATCH_MAX + 1];     // first work item of window w
+  unsigned int* bar;             // grid-barrier arrival counter of the batch
+  unsigned int bar_target;
+};
+
 // result blob: H_top N*N | b_top N | raw Schur Gram tiles ntiles*16 | ACC_MISC counters
 inline __host__ __device__ int result_doubles(int N, int ntiles) { return N * N + N + ntiles * 16 + ACC_MISC; }
 

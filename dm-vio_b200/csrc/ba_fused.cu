@@ -177,409 +177,408 @@ __device__ __forceinline__ double xchg_pull_sum(const BAXchg& X, int idx, double
 // residuals are re-linearised from scratch (PointFrameResidual::resetOOB; FullSystem.cpp:L826-838), EFResidual::fixLinearizationF
 // (EnergyFunctionalStructs.cpp:L88-114) turns resF into res_toZeroF, and the accumulation is AccumulatedTopHessian::addPoint<2> +
 // AccumulatedSCHessian::addPoint(p, shiftPriorToZero = false) with priorF * idepthFixPriorMargFac (EnergyFunctional.cpp:L678-742).
+// phases A-C for one chunk of one window (W / it may live in kernel-parameter space or in global memory)
 template <int P, bool MARG>
-__global__ void __launch_bounds__(P == 32 ? 224 : 128, P == 32 ? 2 : 4)
-    ba_fused_kernel(const __grid_constant__ BAWinDev W, const __grid_constant__ BAIter it) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FusedSmem<P>& S = *reinterpret_cast<FusedSmem<P>*>(smem_raw);
+__device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it, FusedSmem<P>& S, const int chunk) {
   constexpr int LOGP = (P == 32) ? 5 : 4;
   const int nf = W.nf, N = W.N, mp = W.mp;
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
   const BAAdj* __restrict__ A = W.adj;
-
-#pragma unroll 1
-  for (int chunk = blockIdx.x; chunk < W.nchunks; chunk += gridDim.x) {
-    int h = 0;  // host frame of this chunk: branch-free so that the constant-bank loads are independent
+  int h = 0;  // host frame of this chunk: branch-free so that the constant-bank loads are independent
 #pragma unroll
-    for (int k = 1; k < MAXF; k++) h += (chunk >= W.chunk_beg[k]) ? 1 : 0;
-    h = min(h, nf - 1);
-    const int ch_start = W.host_start[h] + (chunk - W.chunk_beg[h]) * P;
-    const int ch_count = min(P, W.host_start[h + 1] - ch_start);
+  for (int k = 1; k < MAXF; k++) h += (chunk >= W.chunk_beg[k]) ? 1 : 0;
+  h = min(h, nf - 1);
+  const int ch_start = W.host_start[h] + (chunk - W.chunk_beg[h]) * P;
+  const int ch_count = min(P, W.host_start[h + 1] - ch_start);
 
-    // ---- stage the host's adjoint blocks (fp64 for phase C, fp32 for the Schur vectors); waited for at the first block barrier,
-    // except the fp32 block of a warp's own pair(s), which the warp fetches itself below
-    for (int i = tid; i < nf * 32; i += nthreads) cp_async16(&S.AhD[i >> 5][(i & 31) * 2], &A->adHost[h * nf + (i >> 5)][(i & 31) * 2]);
-    for (int i = tid; i < nf * 4; i += nthreads) cp_async16(&S.dT[i >> 2][(i & 3) * 2], &A->adTdiag[h * nf + (i >> 2)][(i & 3) * 2]);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  // ---- stage the host's adjoint blocks (fp64 for phase C, fp32 for the Schur vectors); waited for at the first block barrier,
+  // except the fp32 block of a warp's own pair(s), which the warp fetches itself below
+  for (int i = tid; i < nf * 32; i += nthreads) cp_async16(&S.AhD[i >> 5][(i & 31) * 2], &A->adHost[h * nf + (i >> 5)][(i & 31) * 2]);
+  for (int i = tid; i < nf * 4; i += nthreads) cp_async16(&S.dT[i >> 2][(i & 3) * 2], &A->adTdiag[h * nf + (i >> 2)][(i & 3) * 2]);
+  asm volatile("cp.async.commit_group;" ::: "memory");
 
-    // ---------------------------------------------------------------- phase A: one thread = one point-residual
-    const int r = tid >> LOGP, pl = tid & (P - 1);  // r-th target frame other than h
-    const int t = r + (r >= h ? 1 : 0);
-    const bool slot_ok = r < nf - 1;
-    float e_sum = 0.f, rs_step2 = 0.f, rs_nid = 0.f, rs_cnt = 0.f;
-    int n_in = 0, n_oob = 0, n_outl = 0;
-    if ((warp << 5 >> LOGP) < nf - 1) {  // warp-uniform: this warp owns at least one pair
-      const int tc = slot_ok ? t : (h == 0 ? 1 : 0);  // idle half-warps shadow a valid pair (loads stay in bounds, nothing is written)
-      if (slot_ok) {  // the pair's fp32 adjoints: fetched by the lanes that use them (no block barrier before phase A's tail)
-        if (pl < 16) *reinterpret_cast<float4*>(&S.adH[t][pl * 4]) = __ldg(reinterpret_cast<const float4*>(&A->adHostF[h * nf + t][pl * 4]));
-        if (pl < 2) *reinterpret_cast<float4*>(&S.adT[t][pl * 4]) = __ldg(reinterpret_cast<const float4*>(&A->adTdiagF[h * nf + t][pl * 4]));
-      }
-      const bool valid = slot_ok && pl < ch_count;
-      const int p = ch_start + min(pl, ch_count - 1);
-      const int slot = tc * mp + p;
-      const float* pc = it.precalc[h * nf + tc];
-      const float fx = it.calib[0], fy = it.calib[1], cx = it.calib[2], cy = it.calib[3];
-      const float fxi = it.calib[4], fyi = it.calib[5];
-      const float TH = fmaxf(it.TH[h], it.TH[tc]);
-      const float wM3 = (float)(W.w - 3), hM3 = (float)(W.h - 3);
-      const float4* __restrict__ img = W.img[tc];
-      const int iw = W.w;
-      const float huber = W.huberTH, oth = W.outlierTHSum;
+  // ---------------------------------------------------------------- phase A: one thread = one point-residual
+  const int r = tid >> LOGP, pl = tid & (P - 1);  // r-th target frame other than h
+  const int t = r + (r >= h ? 1 : 0);
+  const bool slot_ok = r < nf - 1;
+  float e_sum = 0.f, rs_step2 = 0.f, rs_nid = 0.f, rs_cnt = 0.f;
+  int n_in = 0, n_oob = 0, n_outl = 0;
+  if ((warp << 5 >> LOGP) < nf - 1) {  // warp-uniform: this warp owns at least one pair
+    const int tc = slot_ok ? t : (h == 0 ? 1 : 0);  // idle half-warps shadow a valid pair (loads stay in bounds, nothing is written)
+    if (slot_ok) {  // the pair's fp32 adjoints: fetched by the lanes that use them (no block barrier before phase A's tail)
+      if (pl < 16) *reinterpret_cast<float4*>(&S.adH[t][pl * 4]) = __ldg(reinterpret_cast<const float4*>(&A->adHostF[h * nf + t][pl * 4]));
+      if (pl < 2) *reinterpret_cast<float4*>(&S.adT[t][pl * 4]) = __ldg(reinterpret_cast<const float4*>(&A->adTdiagF[h * nf + t][pl * 4]));
+    }
+    const bool valid = slot_ok && pl < ch_count;
+    const int p = ch_start + min(pl, ch_count - 1);
+    const int slot = tc * mp + p;
+    const float* pc = it.precalc[h * nf + tc];
+    const float fx = it.calib[0], fy = it.calib[1], cx = it.calib[2], cy = it.calib[3];
+    const float fxi = it.calib[4], fyi = it.calib[5];
+    const float TH = fmaxf(it.TH[h], it.TH[tc]);
+    const float wM3 = (float)(W.w - 3), hM3 = (float)(W.h - 3);
+    const float4* __restrict__ img = W.img[tc];
+    const int iw = W.w;
+    const float huber = W.huberTH, oth = W.outlierTHSum;
 
-      // ---- direct loads (all independent: one memory round trip)
-      int st = valid ? (int)__ldg(W.st_in + slot) : RES_NONE;
-      float en_old = __ldg(W.en_in + slot);
-      bool masked = true;
-      if constexpr (MARG) {  // resetOOB: every existing residual of a flagged point starts as IN with zero energy; other points sit out
-        masked = valid && __ldg(W.marg_mask + p) != 0;
-        st = (masked && st != RES_NONE) ? RES_IN : RES_NONE;
-        en_old = 0.f;
-      }
-      const float2 uv = __ldg(W.uv + p);
-      float col[8], wgt[8];
-      {
-        const float4 c0 = __ldg(reinterpret_cast<const float4*>(W.color + (size_t)p * 8)), c1 = __ldg(reinterpret_cast<const float4*>(W.color + (size_t)p * 8) + 1);
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(W.weights + (size_t)p * 8)), w1 = __ldg(reinterpret_cast<const float4*>(W.weights + (size_t)p * 8) + 1);
-        col[0] = c0.x; col[1] = c0.y; col[2] = c0.z; col[3] = c0.w; col[4] = c1.x; col[5] = c1.y; col[6] = c1.z; col[7] = c1.w;
-        wgt[0] = w0.x; wgt[1] = w0.y; wgt[2] = w0.z; wgt[3] = w0.w; wgt[4] = w1.x; wgt[5] = w1.y; wgt[6] = w1.z; wgt[7] = w1.w;
-      }
-      float idepth, idz;
-      if (it.have_x) {
-        // fused EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:L295-321) + point step (FullSystemOptimize.cpp:L264-272): every
-        // thread of the point recomputes the same step from the committed linearisation (loads hit L1/L2), the first target's publishes
-        const float4 po0 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8));
-        const float4 po1 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8) + 1);
-        const float idb = __ldg(W.idepth_backup + p);
-        float b = po1.w - (it.xc[0] * po0.z + it.xc[1] * po0.w + it.xc[2] * po1.x + it.xc[3] * po1.y);
-        int ngood = 0;
+    // ---- direct loads (all independent: one memory round trip)
+    int st = valid ? (int)__ldg(W.st_in + slot) : RES_NONE;
+    float en_old = __ldg(W.en_in + slot);
+    bool masked = true;
+    if constexpr (MARG) {  // resetOOB: every existing residual of a flagged point starts as IN with zero energy; other points sit out
+      masked = valid && __ldg(W.marg_mask + p) != 0;
+      st = (masked && st != RES_NONE) ? RES_IN : RES_NONE;
+      en_old = 0.f;
+    }
+    const float2 uv = __ldg(W.uv + p);
+    float col[8], wgt[8];
+    {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(W.color + (size_t)p * 8)), c1 = __ldg(reinterpret_cast<const float4*>(W.color + (size_t)p * 8) + 1);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(W.weights + (size_t)p * 8)), w1 = __ldg(reinterpret_cast<const float4*>(W.weights + (size_t)p * 8) + 1);
+      col[0] = c0.x; col[1] = c0.y; col[2] = c0.z; col[3] = c0.w; col[4] = c1.x; col[5] = c1.y; col[6] = c1.z; col[7] = c1.w;
+      wgt[0] = w0.x; wgt[1] = w0.y; wgt[2] = w0.z; wgt[3] = w0.w; wgt[4] = w1.x; wgt[5] = w1.y; wgt[6] = w1.z; wgt[7] = w1.w;
+    }
+    float idepth, idz;
+    if (it.have_x) {
+      // fused EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:L295-321) + point step (FullSystemOptimize.cpp:L264-272): every
+      // thread of the point recomputes the same step from the committed linearisation (loads hit L1/L2), the first target's publishes
+      const float4 po0 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8));
+      const float4 po1 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8) + 1);
+      const float idb = __ldg(W.idepth_backup + p);
+      float b = po1.w - (it.xc[0] * po0.z + it.xc[1] * po0.w + it.xc[2] * po1.x + it.xc[3] * po1.y);
+      int ngood = 0;
 #pragma unroll
-        for (int tt = 0; tt < MAXF; tt++) {
-          if (tt >= nf || tt == h) continue;
-          const int cs = tt * mp + p;
-          if (__ldg(W.c_st + cs) != RES_IN) continue;
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8));
-          const float4 a1 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8) + 1);
-          const float* xa = it.xAd[h * nf + tt];
-          b -= xa[0] * a0.x + xa[1] * a0.y + xa[2] * a0.z + xa[3] * a0.w + xa[4] * a1.x + xa[5] * a1.y + xa[6] * a1.z + xa[7] * a1.w;
-          ngood++;
-        }
-        const float step = ngood > 0 ? -b * po1.z : 0.f;
-        idepth = idb + step;
-        idz = idepth;  // DM-VIO: idepth_zero follows (setIdepthZero in doStepFromBackup); the host aliases the pointers
-        if (r == 0 && valid) {
-          W.step[p] = step;
-          W.idepth_out[p] = idepth;
-          rs_step2 = step * step; rs_nid = fabsf(idb); rs_cnt = 1.f;
-        }
-      } else {
-        idepth = __ldg(W.idepth + p);
-        idz = __ldg(W.idepth_zero + p);
+      for (int tt = 0; tt < MAXF; tt++) {
+        if (tt >= nf || tt == h) continue;
+        const int cs = tt * mp + p;
+        if (__ldg(W.c_st + cs) != RES_IN) continue;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8) + 1);
+        const float* xa = it.xAd[h * nf + tt];
+        b -= xa[0] * a0.x + xa[1] * a0.y + xa[2] * a0.z + xa[3] * a0.w + xa[4] * a1.x + xa[5] * a1.y + xa[6] * a1.z + xa[7] * a1.w;
+        ngood++;
       }
-      if (r == 0 && valid) { S.id[pl] = idepth; S.idz[pl] = idz; }
-      bool live = (st != RES_NONE) && (st != RES_OOB);
+      const float step = ngood > 0 ? -b * po1.z : 0.f;
+      idepth = idb + step;
+      idz = idepth;  // DM-VIO: idepth_zero follows (setIdepthZero in doStepFromBackup); the host aliases the pointers
+      if (r == 0 && valid) {
+        W.step[p] = step;
+        W.idepth_out[p] = idepth;
+        rs_step2 = step * step; rs_nid = fabsf(idb); rs_cnt = 1.f;
+      }
+    } else {
+      idepth = __ldg(W.idepth + p);
+      idz = __ldg(W.idepth_zero + p);
+    }
+    if (r == 0 && valid) { S.id[pl] = idepth; S.idz[pl] = idz; }
+    bool live = (st != RES_NONE) && (st != RES_OOB);
 
-      // ---- centre pixel at the FEJ point (ResidualProjections.h:L62-87, Residuals.cpp:L108-157)
-      const float Kl0 = (uv.x - cx) * fxi, Kl1 = (uv.y - cy) * fyi;
-      const float q2 = pc[18] * Kl0 + pc[19] * Kl1 + pc[20] + pc[23] * idz;
-      const float drescale = 1.0f / q2;
-      const float new_idepth = idz * drescale;
-      const float cu = (pc[12] * Kl0 + pc[13] * Kl1 + pc[14] + pc[21] * idz) * drescale;
-      const float cv = (pc[15] * Kl0 + pc[16] * Kl1 + pc[17] + pc[22] * idz) * drescale;
-      const float cKu = cu * fx + cx, cKv = cv * fy + cy;
-      live = live && (drescale > 0.f) && cKu > 1.1f && cKv > 1.1f && cKu < wM3 && cKv < hM3;
+    // ---- centre pixel at the FEJ point (ResidualProjections.h:L62-87, Residuals.cpp:L108-157)
+    const float Kl0 = (uv.x - cx) * fxi, Kl1 = (uv.y - cy) * fyi;
+    const float q2 = pc[18] * Kl0 + pc[19] * Kl1 + pc[20] + pc[23] * idz;
+    const float drescale = 1.0f / q2;
+    const float new_idepth = idz * drescale;
+    const float cu = (pc[12] * Kl0 + pc[13] * Kl1 + pc[14] + pc[21] * idz) * drescale;
+    const float cv = (pc[15] * Kl0 + pc[16] * Kl1 + pc[17] + pc[22] * idz) * drescale;
+    const float cKu = cu * fx + cx, cKv = cv * fy + cy;
+    live = live && (drescale > 0.f) && cKu > 1.1f && cKv > 1.1f && cKu < wM3 && cKv < hM3;
 
-      // ---- the 8 pattern pixels at the current state (ResidualProjections.h:L47-57): all must project inside the image
-      float Ku[8], Kv[8];
+    // ---- the 8 pattern pixels at the current state (ResidualProjections.h:L47-57): all must project inside the image
+    float Ku[8], Kv[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const float pu = uv.x + (float)c_pattern[j][0], pv = uv.y + (float)c_pattern[j][1];
-        const float r2 = pc[6] * pu + pc[7] * pv + pc[8] + pc[11] * idepth;
-        Ku[j] = (pc[0] * pu + pc[1] * pv + pc[2] + pc[9] * idepth) / r2;
-        Kv[j] = (pc[3] * pu + pc[4] * pv + pc[5] + pc[10] * idepth) / r2;
-        live = live && Ku[j] > 1.1f && Kv[j] > 1.1f && Ku[j] < wM3 && Kv[j] < hM3;
-      }
-      float x[10], y[10], ddx = 0.f, ddy = 0.f, jpx = 0.f, jpy = 0.f, dp6 = 0.f, dp7 = 0.f;
-      if constexpr (MARG) {  // fixLinearizationF needs the geometric Jacobians per pixel: res_toZeroF = resF - J * delta
-        if (live) {
-          geo_jac(pc, Kl0, Kl1, cu, cv, drescale, new_idepth, fx, fy, fxi, fyi, x, y, ddx, ddy);
-          const float* dp = W.marg->adHTdelta[h * nf + tc];
-          const float* cD = W.marg->cDelta;
-          const float dlt = idepth - idz;  // EFPoint::deltaF
-          jpx = (x[4] * dp[0] + x[5] * dp[1] + x[6] * dp[2] + x[7] * dp[3] + x[8] * dp[4] + x[9] * dp[5]) +
-                (x[0] * cD[0] + x[1] * cD[1] + x[2] * cD[2] + x[3] * cD[3]) + ddx * dlt;
-          jpy = (y[4] * dp[0] + y[5] * dp[1] + y[6] * dp[2] + y[7] * dp[3] + y[8] * dp[4] + y[9] * dp[5]) +
-                (y[0] * cD[0] + y[1] * cD[1] + y[2] * cD[2] + y[3] * cD[3]) + ddy * dlt;
-          dp6 = dp[6]; dp7 = dp[7];
-        }
-      }
-
-      // ---- getInterpolatedElement33 (util/globalFuncs.h:L103-118), photometric residual, gradient weight, Huber (Residuals.cpp:L194-258)
-      PixSums s = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      float energy = 0.f, wJI2 = 0.f, rtz[8];
+    for (int j = 0; j < 8; j++) {
+      const float pu = uv.x + (float)c_pattern[j][0], pv = uv.y + (float)c_pattern[j][1];
+      const float r2 = pc[6] * pu + pc[7] * pv + pc[8] + pc[11] * idepth;
+      Ku[j] = (pc[0] * pu + pc[1] * pv + pc[2] + pc[9] * idepth) / r2;
+      Kv[j] = (pc[3] * pu + pc[4] * pv + pc[5] + pc[10] * idepth) / r2;
+      live = live && Ku[j] > 1.1f && Kv[j] > 1.1f && Ku[j] < wM3 && Kv[j] < hM3;
+    }
+    float x[10], y[10], ddx = 0.f, ddy = 0.f, jpx = 0.f, jpy = 0.f, dp6 = 0.f, dp7 = 0.f;
+    if constexpr (MARG) {  // fixLinearizationF needs the geometric Jacobians per pixel: res_toZeroF = resF - J * delta
       if (live) {
-        const bool zA = W.zeroA != 0, zB = W.zeroB != 0;
-#pragma unroll
-        for (int half = 0; half < 2; half++) {  // 16 float4 taps in flight per thread, twice
-        float4 tap[4][4];
-#pragma unroll
-        for (int jj = 0; jj < 4; jj++) {
-          const int j = half * 4 + jj;
-          const int ix = (int)Ku[j], iy = (int)Kv[j];
-          const float4* bp = img + (size_t)iy * iw + ix;
-          tap[jj][0] = __ldg(bp); tap[jj][1] = __ldg(bp + 1); tap[jj][2] = __ldg(bp + iw); tap[jj][3] = __ldg(bp + iw + 1);
-        }
-#pragma unroll
-        for (int jj = 0; jj < 4; jj++) {
-          const int j = half * 4 + jj;
-          const int ix = (int)Ku[j], iy = (int)Kv[j];
-          const float dx = Ku[j] - ix, dy = Kv[j] - iy, dxdy = dx * dy;
-          const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
-          const float h0 = w11 * tap[jj][3].x + w10 * tap[jj][2].x + w01 * tap[jj][1].x + w00 * tap[jj][0].x;
-          const float h1 = w11 * tap[jj][3].y + w10 * tap[jj][2].y + w01 * tap[jj][1].y + w00 * tap[jj][0].y;
-          const float h2 = w11 * tap[jj][3].z + w10 * tap[jj][2].z + w01 * tap[jj][1].z + w00 * tap[jj][0].z;
-          live = live && isfinite(h0);
-          const float residual = h0 - (pc[24] * col[j] + pc[25]);
-          const float drdA = col[j] - pc[26];
-          float w = sqrtf(oth / (oth + (h1 * h1 + h2 * h2)));
-          w = 0.5f * (w + wgt[j]);
-          const float ar = fabsf(residual);
-          float hw = ar < huber ? 1.f : huber / ar;
-          energy += w * w * hw * residual * residual * (2.f - hw);
-          if (hw < 1.f) hw = sqrtf(hw);
-          hw = hw * w;
-          const float gx = h1 * hw, gy = h2 * hw;
-          const float resF = residual * hw;
-          const float ja = drdA * hw, jb = hw;
-          const float jaF = zA ? 0.f : ja, jbF = zB ? 0.f : jb;
-          float ra = resF;  // what the right-hand sides are built from: resF, or res_toZeroF when marginalising
-          if constexpr (MARG) { ra = (((resF - gx * jpx) - gy * jpy) - jaF * dp6) - jbF * dp7; rtz[j] = ra; }
-          s.JI00 += gx * gx; s.JI11 += gy * gy; s.JI10 += gx * gy;
-          s.JabJI00 += ja * gx; s.JabJI01 += ja * gy; s.JabJI10 += jb * gx; s.JabJI11 += jb * gy;
-          s.Jab00 += ja * ja; s.Jab01 += ja * jb; s.Jab11 += jb * jb;
-          s.JIr0 += ra * gx; s.JIr1 += ra * gy; s.Jabr0 += ra * jaF; s.Jabr1 += ra * jbF; s.rr += ra * ra;
-          // the reference sums hw*hw*(hitColor[1]^2+hitColor[2]^2) with hitColor already multiplied by hw (Residuals.cpp:L217-244)
-          wJI2 += hw * hw * (gx * gx + gy * gy);
-        }
-        }
+        geo_jac(pc, Kl0, Kl1, cu, cv, drescale, new_idepth, fx, fy, fxi, fyi, x, y, ddx, ddy);
+        const float* dp = W.marg->adHTdelta[h * nf + tc];
+        const float* cD = W.marg->cDelta;
+        const float dlt = idepth - idz;  // EFPoint::deltaF
+        jpx = (x[4] * dp[0] + x[5] * dp[1] + x[6] * dp[2] + x[7] * dp[3] + x[8] * dp[4] + x[9] * dp[5]) +
+              (x[0] * cD[0] + x[1] * cD[1] + x[2] * cD[2] + x[3] * cD[3]) + ddx * dlt;
+        jpy = (y[4] * dp[0] + y[5] * dp[1] + y[6] * dp[2] + y[7] * dp[3] + y[8] * dp[4] + y[9] * dp[5]) +
+              (y[0] * cD[0] + y[1] * cD[1] + y[2] * cD[2] + y[3] * cD[3]) + ddy * dlt;
+        dp6 = dp[6]; dp7 = dp[7];
       }
+    }
 
-      // ---- classification (Residuals.cpp:L260-273) and per-residual outputs
-      int newState;
-      float newEnergy;
-      if (st == RES_NONE) { newState = RES_NONE; newEnergy = 0.f; }
-      else if (!live) { newState = RES_OOB; newEnergy = en_old; }  // OOB exits return the old state_energy
-      else if (energy > TH || wJI2 < 2.f) { newState = RES_OUTLIER; newEnergy = TH; }
-      else { newState = RES_IN; newEnergy = energy; }
-      const bool in = (newState == RES_IN);
-      if (st != RES_NONE) {
-        e_sum = newEnergy;
-        n_in = in; n_oob = (newState == RES_OOB); n_outl = (newState == RES_OUTLIER);
+    // ---- getInterpolatedElement33 (util/globalFuncs.h:L103-118), photometric residual, gradient weight, Huber (Residuals.cpp:L194-258)
+    PixSums s = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float energy = 0.f, wJI2 = 0.f, rtz[8];
+    if (live) {
+      const bool zA = W.zeroA != 0, zB = W.zeroB != 0;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {  // 16 float4 taps in flight per thread, twice
+      float4 tap[4][4];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        const int j = half * 4 + jj;
+        const int ix = (int)Ku[j], iy = (int)Kv[j];
+        const float4* bp = img + (size_t)iy * iw + ix;
+        tap[jj][0] = __ldg(bp); tap[jj][1] = __ldg(bp + 1); tap[jj][2] = __ldg(bp + iw); tap[jj][3] = __ldg(bp + iw + 1);
       }
-      if constexpr (MARG) {
-        if (masked) {
-          float4* o = reinterpret_cast<float4*>(W.marg_rtz + (size_t)slot * 8);
-          o[0] = in ? make_float4(rtz[0], rtz[1], rtz[2], rtz[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-          o[1] = in ? make_float4(rtz[4], rtz[5], rtz[6], rtz[7]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        const int j = half * 4 + jj;
+        const int ix = (int)Ku[j], iy = (int)Kv[j];
+        const float dx = Ku[j] - ix, dy = Kv[j] - iy, dxdy = dx * dy;
+        const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+        const float h0 = w11 * tap[jj][3].x + w10 * tap[jj][2].x + w01 * tap[jj][1].x + w00 * tap[jj][0].x;
+        const float h1 = w11 * tap[jj][3].y + w10 * tap[jj][2].y + w01 * tap[jj][1].y + w00 * tap[jj][0].y;
+        const float h2 = w11 * tap[jj][3].z + w10 * tap[jj][2].z + w01 * tap[jj][1].z + w00 * tap[jj][0].z;
+        live = live && isfinite(h0);
+        const float residual = h0 - (pc[24] * col[j] + pc[25]);
+        const float drdA = col[j] - pc[26];
+        float w = sqrtf(oth / (oth + (h1 * h1 + h2 * h2)));
+        w = 0.5f * (w + wgt[j]);
+        const float ar = fabsf(residual);
+        float hw = ar < huber ? 1.f : huber / ar;
+        energy += w * w * hw * residual * residual * (2.f - hw);
+        if (hw < 1.f) hw = sqrtf(hw);
+        hw = hw * w;
+        const float gx = h1 * hw, gy = h2 * hw;
+        const float resF = residual * hw;
+        const float ja = drdA * hw, jb = hw;
+        const float jaF = zA ? 0.f : ja, jbF = zB ? 0.f : jb;
+        float ra = resF;  // what the right-hand sides are built from: resF, or res_toZeroF when marginalising
+        if constexpr (MARG) { ra = (((resF - gx * jpx) - gy * jpy) - jaF * dp6) - jbF * dp7; rtz[j] = ra; }
+        s.JI00 += gx * gx; s.JI11 += gy * gy; s.JI10 += gx * gy;
+        s.JabJI00 += ja * gx; s.JabJI01 += ja * gy; s.JabJI10 += jb * gx; s.JabJI11 += jb * gy;
+        s.Jab00 += ja * ja; s.Jab01 += ja * jb; s.Jab11 += jb * jb;
+        s.JIr0 += ra * gx; s.JIr1 += ra * gy; s.Jabr0 += ra * jaF; s.Jabr1 += ra * jbF; s.rr += ra * ra;
+        // the reference sums hw*hw*(hitColor[1]^2+hitColor[2]^2) with hitColor already multiplied by hw (Residuals.cpp:L217-244)
+        wJI2 += hw * hw * (gx * gx + gy * gy);
       }
-      if (valid && masked) {
-        W.st_new[slot] = (uint8_t)newState;
-        W.en_new[slot] = newEnergy;
-        W.en_wo[slot] = (st == RES_NONE || !live) ? -1.f : energy;
-        const size_t plane = (size_t)MAXF * mp;
-        W.cpt[slot] = cKu; W.cpt[plane + slot] = cKv; W.cpt[2 * plane + slot] = new_idepth;
       }
+    }
 
-      // ---- EFResidual::takeDataF (EnergyFunctionalStructs.cpp:L39-49), the per-point terms of addPoint (AccumulatedTopHessian.cpp:L131-135)
-      // and the residual's part of the point's Schur vector
-      float jp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Hdd = 0.f, bd = 0.f, Hcd0 = 0.f, Hcd1 = 0.f, Hcd2 = 0.f, Hcd3 = 0.f;
-      if (in) {
-        if constexpr (!MARG) geo_jac(pc, Kl0, Kl1, cu, cv, drescale, new_idepth, fx, fy, fxi, fyi, x, y, ddx, ddy);
-        const float J0 = s.JI00 * ddx + s.JI10 * ddy, J1 = s.JI10 * ddx + s.JI11 * ddy;  // JIdx2 * Jpdd
-#pragma unroll
-        for (int k = 0; k < 6; k++) jp[k] = x[4 + k] * J0 + y[4 + k] * J1;
-        jp[6] = s.JabJI00 * ddx + s.JabJI01 * ddy; jp[7] = s.JabJI10 * ddx + s.JabJI11 * ddy;
-        Hdd = J0 * ddx + J1 * ddy;
-        bd = s.JIr0 * ddx + s.JIr1 * ddy;
-        Hcd0 = x[0] * J0 + y[0] * J1; Hcd1 = x[1] * J0 + y[1] * J1; Hcd2 = x[2] * J0 + y[2] * J1; Hcd3 = x[3] * J0 + y[3] * J1;
-        if (valid) {
-          float4* gj = reinterpret_cast<float4*>(W.jpjd + (size_t)slot * 8);
-          gj[0] = make_float4(jp[0], jp[1], jp[2], jp[3]);
-          gj[1] = make_float4(jp[4], jp[5], jp[6], jp[7]);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 10; k++) { x[k] = 0.f; y[k] = 0.f; }
-        s = PixSums{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // ---- classification (Residuals.cpp:L260-273) and per-residual outputs
+    int newState;
+    float newEnergy;
+    if (st == RES_NONE) { newState = RES_NONE; newEnergy = 0.f; }
+    else if (!live) { newState = RES_OOB; newEnergy = en_old; }  // OOB exits return the old state_energy
+    else if (energy > TH || wJI2 < 2.f) { newState = RES_OUTLIER; newEnergy = TH; }
+    else { newState = RES_IN; newEnergy = energy; }
+    const bool in = (newState == RES_IN);
+    if (st != RES_NONE) {
+      e_sum = newEnergy;
+      n_in = in; n_oob = (newState == RES_OOB); n_outl = (newState == RES_OUTLIER);
+    }
+    if constexpr (MARG) {
+      if (masked) {
+        float4* o = reinterpret_cast<float4*>(W.marg_rtz + (size_t)slot * 8);
+        o[0] = in ? make_float4(rtz[0], rtz[1], rtz[2], rtz[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        o[1] = in ? make_float4(rtz[4], rtz[5], rtz[6], rtz[7]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      __syncwarp();  // the pair's adjoints staged by this warp above
-      if (slot_ok) {
-        // host block: adHost(h,t) * JpJdF (summed over targets in phase B); target block: adTarget(h,t) is diagonal
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const float4 a0 = *reinterpret_cast<const float4*>(&S.adH[t][k * 8]), a1 = *reinterpret_cast<const float4*>(&S.adH[t][k * 8 + 4]);
-          S.rec[t][k][pl] = a0.x * jp[0] + a0.y * jp[1] + a0.z * jp[2] + a0.w * jp[3] + a1.x * jp[4] + a1.y * jp[5] + a1.z * jp[6] + a1.w * jp[7];
-          S.Wv[pl][4 + 8 * t + k] = S.adT[t][k] * jp[k];
-        }
-        S.rec[t][8][pl] = Hdd; S.rec[t][9][pl] = bd; S.rec[t][10][pl] = Hcd0; S.rec[t][11][pl] = Hcd1; S.rec[t][12][pl] = Hcd2; S.rec[t][13][pl] = Hcd3;
-        S.rec[t][14][pl] = in ? 1.f : 0.f;
-      }
+    }
+    if (valid && masked) {
+      W.st_new[slot] = (uint8_t)newState;
+      W.en_new[slot] = newEnergy;
+      W.en_wo[slot] = (st == RES_NONE || !live) ? -1.f : energy;
+      const size_t plane = (size_t)MAXF * mp;
+      W.cpt[slot] = cKu; W.cpt[plane + slot] = cKv; W.cpt[2 * plane + slot] = new_idepth;
+    }
 
-      // ---- the pair's 13x13 block: 96 (91 used) entries per residual, summed over the pair's P lanes with a transposing butterfly:
-      // every step exchanges HALF of the remaining values, so the whole reduction costs 96 shuffles instead of 96 * log2(P)
-      float al[10], be[10];
+    // ---- EFResidual::takeDataF (EnergyFunctionalStructs.cpp:L39-49), the per-point terms of addPoint (AccumulatedTopHessian.cpp:L131-135)
+    // and the residual's part of the point's Schur vector
+    float jp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Hdd = 0.f, bd = 0.f, Hcd0 = 0.f, Hcd1 = 0.f, Hcd2 = 0.f, Hcd3 = 0.f;
+    if (in) {
+      if constexpr (!MARG) geo_jac(pc, Kl0, Kl1, cu, cv, drescale, new_idepth, fx, fy, fxi, fyi, x, y, ddx, ddy);
+      const float J0 = s.JI00 * ddx + s.JI10 * ddy, J1 = s.JI10 * ddx + s.JI11 * ddy;  // JIdx2 * Jpdd
 #pragma unroll
-      for (int k = 0; k < 10; k++) { al[k] = s.JI00 * x[k] + s.JI10 * y[k]; be[k] = s.JI10 * x[k] + s.JI11 * y[k]; }
-      float v[48];
-      {
-        const bool up = (lane & (P / 2)) != 0;
-        static_for<0, 48>([&](auto kc) {
-          constexpr int k = decltype(kc)::value;
-          const float a = top_entry<k>(x, y, al, be, s), b = top_entry<k + 48>(x, y, al, be, s);
-          v[k] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, P / 2);
-        });
+      for (int k = 0; k < 6; k++) jp[k] = x[4 + k] * J0 + y[4 + k] * J1;
+      jp[6] = s.JabJI00 * ddx + s.JabJI01 * ddy; jp[7] = s.JabJI10 * ddx + s.JabJI11 * ddy;
+      Hdd = J0 * ddx + J1 * ddy;
+      bd = s.JIr0 * ddx + s.JIr1 * ddy;
+      Hcd0 = x[0] * J0 + y[0] * J1; Hcd1 = x[1] * J0 + y[1] * J1; Hcd2 = x[2] * J0 + y[2] * J1; Hcd3 = x[3] * J0 + y[3] * J1;
+      if (valid) {
+        float4* gj = reinterpret_cast<float4*>(W.jpjd + (size_t)slot * 8);
+        gj[0] = make_float4(jp[0], jp[1], jp[2], jp[3]);
+        gj[1] = make_float4(jp[4], jp[5], jp[6], jp[7]);
       }
-      static_for<0, LOGP - 1>([&](auto sc) {  // steps 2..log2(P): 24, 12, 6 (, 3) exchanges
-        constexpr int st2 = decltype(sc)::value, hstep = 24 >> st2, m = (P / 4) >> st2;
-        const bool up = (lane & m) != 0;
+    } else {
 #pragma unroll
-        for (int k = 0; k < hstep; k++) v[k] = (up ? v[k + hstep] : v[k]) + __shfl_xor_sync(0xffffffffu, up ? v[k] : v[k + hstep], m);
+      for (int k = 0; k < 10; k++) { x[k] = 0.f; y[k] = 0.f; }
+      s = PixSums{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    }
+    __syncwarp();  // the pair's adjoints staged by this warp above
+    if (slot_ok) {
+      // host block: adHost(h,t) * JpJdF (summed over targets in phase B); target block: adTarget(h,t) is diagonal
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&S.adH[t][k * 8]), a1 = *reinterpret_cast<const float4*>(&S.adH[t][k * 8 + 4]);
+        S.rec[t][k][pl] = a0.x * jp[0] + a0.y * jp[1] + a0.z * jp[2] + a0.w * jp[3] + a1.x * jp[4] + a1.y * jp[5] + a1.z * jp[6] + a1.w * jp[7];
+        S.Wv[pl][4 + 8 * t + k] = S.adT[t][k] * jp[k];
+      }
+      S.rec[t][8][pl] = Hdd; S.rec[t][9][pl] = bd; S.rec[t][10][pl] = Hcd0; S.rec[t][11][pl] = Hcd1; S.rec[t][12][pl] = Hcd2; S.rec[t][13][pl] = Hcd3;
+      S.rec[t][14][pl] = in ? 1.f : 0.f;
+    }
+
+    // ---- the pair's 13x13 block: 96 (91 used) entries per residual, summed over the pair's P lanes with a transposing butterfly:
+    // every step exchanges HALF of the remaining values, so the whole reduction costs 96 shuffles instead of 96 * log2(P)
+    float al[10], be[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) { al[k] = s.JI00 * x[k] + s.JI10 * y[k]; be[k] = s.JI10 * x[k] + s.JI11 * y[k]; }
+    float v[48];
+    {
+      const bool up = (lane & (P / 2)) != 0;
+      static_for<0, 48>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        const float a = top_entry<k>(x, y, al, be, s), b = top_entry<k + 48>(x, y, al, be, s);
+        v[k] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, P / 2);
       });
-      if (slot_ok) {  // lane L of the pair's group now holds entries [(96/P) L, (96/P)(L+1))
-        constexpr int PER = 96 / P;
+    }
+    static_for<0, LOGP - 1>([&](auto sc) {  // steps 2..log2(P): 24, 12, 6 (, 3) exchanges
+      constexpr int st2 = decltype(sc)::value, hstep = 24 >> st2, m = (P / 4) >> st2;
+      const bool up = (lane & m) != 0;
 #pragma unroll
-        for (int k = 0; k < PER; k++) S.pair[t][PER * pl + k] = v[k];
-      }
-    }
-    {  // counters: warp sums
-      float es = e_sum, fin = (float)n_in, foob = (float)n_oob, fout = (float)n_outl;
+      for (int k = 0; k < hstep; k++) v[k] = (up ? v[k + hstep] : v[k]) + __shfl_xor_sync(0xffffffffu, up ? v[k] : v[k + hstep], m);
+    });
+    if (slot_ok) {  // lane L of the pair's group now holds entries [(96/P) L, (96/P)(L+1))
+      constexpr int PER = 96 / P;
 #pragma unroll
-      for (int m = 1; m < 32; m <<= 1) {
-        es += __shfl_xor_sync(0xffffffffu, es, m);
-        fin += __shfl_xor_sync(0xffffffffu, fin, m);
-        foob += __shfl_xor_sync(0xffffffffu, foob, m);
-        fout += __shfl_xor_sync(0xffffffffu, fout, m);
-        rs_step2 += __shfl_xor_sync(0xffffffffu, rs_step2, m);
-        rs_nid += __shfl_xor_sync(0xffffffffu, rs_nid, m);
-        rs_cnt += __shfl_xor_sync(0xffffffffu, rs_cnt, m);
-      }
-      if (lane == 0) {
-        S.misc[warp][0] = es; S.misc[warp][1] = fin; S.misc[warp][2] = foob; S.misc[warp][3] = fout;
-        S.misc[warp][4] = rs_step2; S.misc[warp][5] = rs_nid; S.misc[warp][6] = rs_cnt; S.misc[warp][7] = 0.f;
-      }
+      for (int k = 0; k < PER; k++) S.pair[t][PER * pl + k] = v[k];
     }
-    cp_async_wait_all();
-    __syncthreads();
-
-    // ---------------------------------------------------------------- phase B: per point (AccumulatedSCHessian.cpp:L36-58)
-    for (int e = tid; e < ch_count * 9; e += nthreads) {
-      const int k = e / ch_count, pl2 = e - k * ch_count;  // lanes = points: conflict-free reads of rec[t][k][.]
-      if (k < 8) {  // host block of the Schur vector
-        float sum = 0.f;
-        for (int tt = 0; tt < nf; tt++)
-          if (tt != h) sum += S.rec[tt][k][pl2];
-        S.Wv[pl2][4 + 8 * h + k] = sum;
-      } else {
-        const int p = ch_start + pl2;
-        float Hdd = 0.f, bd = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, ngood = 0.f;
-        for (int tt = 0; tt < nf; tt++) {
-          if (tt == h) continue;
-          Hdd += S.rec[tt][8][pl2]; bd += S.rec[tt][9][pl2]; c0 += S.rec[tt][10][pl2]; c1 += S.rec[tt][11][pl2];
-          c2 += S.rec[tt][12][pl2]; c3 += S.rec[tt][13][pl2]; ngood += S.rec[tt][14][pl2];
-        }
-        float prior = __ldg(W.priorF + p);
-        bool masked = true;
-        if constexpr (MARG) { masked = __ldg(W.marg_mask + p) != 0; prior *= __ldg(&W.marg->priorFac); }
-        float HdiF = 0.f, bdSum = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-        if (ngood > 0.f) {
-          float H = Hdd + prior;
-          if (H < 1e-10f) H = 1e-10f;
-          HdiF = 1.0f / H;
-          bdSum = MARG ? bd : bd + prior * (S.id[pl2] - S.idz[pl2]);  // shiftPriorToZero (AccumulatedSCHessian.cpp:L47-50)
-          w0 = c0; w1 = c1; w2 = c2; w3 = c3;
-        }
-        S.Wv[pl2][0] = w0; S.Wv[pl2][1] = w1; S.Wv[pl2][2] = w2; S.Wv[pl2][3] = w3;
-        S.Wv[pl2][N] = bdSum;
-        for (int c = N + 1; c < W.NW; c++) S.Wv[pl2][c] = 0.f;  // padding columns of the last 4x4 tiles
-        S.hdi[pl2] = HdiF;
-        if (masked) {
-          float4* po = reinterpret_cast<float4*>(W.pout + (size_t)p * 8);
-          po[0] = make_float4(Hdd, bd, c0, c1);
-          po[1] = make_float4(c2, c3, HdiF, bdSum);
-        }
-      }
-    }
-    // ---- phase C, first half: G(t) = adHost(h,t) * [P | Q | p](h,t) in fp64, [P|Q|p][k][c] = H13[4+k][col(c)], col = 4..11, 0..3, 12
-    for (int e = tid; e < nf * 104; e += nthreads) {
-      const int tt = e / 104, rr = e - tt * 104, i = rr / 13, c = rr - i * 13;
-      if (tt == h) continue;
-      const int colc = (c < 8) ? 4 + c : (c < 12 ? c - 8 : 12);
-      double m = 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) m += S.AhD[tt][i * 8 + k] * (double)h13f(S.pair[tt], 4 + k, colc);
-      S.G[tt][rr] = m;
-    }
-    __syncthreads();
-
-    // ---- Schur vectors -> global, transposed ([4-column group][point] float4) so that phase E reads them coalesced
-    {
-      const int T = W.T;
-      for (int e = tid; e < ch_count * T; e += nthreads) {
-        const int g4 = e / ch_count, pl2 = e - g4 * ch_count;
-        W.wg[(size_t)g4 * mp + ch_start + pl2] = *reinterpret_cast<const float4*>(&S.Wv[pl2][4 * g4]);
-      }
-      if (tid < ch_count) W.hdig[ch_start + tid] = S.hdi[tid];
-    }
-    // ---- phase C, second half: the chunk's contributions in absolute coordinates -> partial blob (AccumulatedTopHessian.cpp:L270-286)
-    {
-      double* __restrict__ out = W.part + (size_t)chunk * PART_STRIDE;
-      for (int e = tid; e < nf * PART_SLOT; e += nthreads) {
-        const int tt = e / PART_SLOT, q = e - tt * PART_SLOT;
-        double val;
-        if (tt != h) {
-          const float* B = S.pair[tt];
-          if (q < 64) { const int i = q >> 3, j = q & 7; val = S.G[tt][i * 13 + j] * S.dT[tt][j]; }                               // H[h,t] = (Ah P) At^T
-          else if (q < 128) { const int i = (q - 64) >> 3, j = q & 7; val = S.dT[tt][i] * (double)h13f(B, 4 + i, 4 + j) * S.dT[tt][j]; }  // H[t,t] = At P At^T
-          else if (q < 160) { const int i = (q - 128) >> 2, c = q & 3; val = S.dT[tt][i] * (double)h13f(B, 4 + i, c); }           // H[t,C] = At Q
-          else { const int i = q - 160; val = S.dT[tt][i] * (double)h13f(B, 4 + i, 12); }                                          // b[t] = At p
-        } else {
-          if (q < 64) continue;  // H[h,h] goes to the diagonal slot below
-          val = 0.0;
-          if (q < 128) {  // H[h,h] = sum_t (Ah P) Ah^T
-            const int i = (q - 64) >> 3, j = q & 7;
-            for (int t2 = 0; t2 < nf; t2++) {
-              if (t2 == h) continue;
-#pragma unroll
-              for (int k = 0; k < 8; k++) val += S.G[t2][i * 13 + k] * S.AhD[t2][j * 8 + k];
-            }
-          } else if (q < 160) {  // H[h,C] = sum_t Ah Q
-            const int i = (q - 128) >> 2, c = q & 3;
-            for (int t2 = 0; t2 < nf; t2++) if (t2 != h) val += S.G[t2][i * 13 + 8 + c];
-          } else {  // b[h] = sum_t Ah p
-            const int i = q - 160;
-            for (int t2 = 0; t2 < nf; t2++) if (t2 != h) val += S.G[t2][i * 13 + 12];
-          }
-        }
-        out[e] = val;
-      }
-      if (tid < 20) {  // H[C,C] (4x4) and b[C]
-        const int i = tid / 5, j = tid - i * 5;
-        double val = 0.0;
-        for (int t2 = 0; t2 < nf; t2++) if (t2 != h) val += (double)h13f(S.pair[t2], i, j < 4 ? j : 12);
-        out[PART_CC + (j < 4 ? i * 4 + j : 16 + i)] = val;
-      } else if (tid >= 32 && tid < 40) {
-        const int k = tid - 32;
-        double val = 0.0;
-        for (int wv = 0; wv < nwarps; wv++) val += (double)S.misc[wv][k];
-        out[PART_MISC + k] = val;
-      }
-    }
-    __syncthreads();  // shared memory is reused by the next chunk (persistent case)
   }
+  {  // counters: warp sums
+    float es = e_sum, fin = (float)n_in, foob = (float)n_oob, fout = (float)n_outl;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+      es += __shfl_xor_sync(0xffffffffu, es, m);
+      fin += __shfl_xor_sync(0xffffffffu, fin, m);
+      foob += __shfl_xor_sync(0xffffffffu, foob, m);
+      fout += __shfl_xor_sync(0xffffffffu, fout, m);
+      rs_step2 += __shfl_xor_sync(0xffffffffu, rs_step2, m);
+      rs_nid += __shfl_xor_sync(0xffffffffu, rs_nid, m);
+      rs_cnt += __shfl_xor_sync(0xffffffffu, rs_cnt, m);
+    }
+    if (lane == 0) {
+      S.misc[warp][0] = es; S.misc[warp][1] = fin; S.misc[warp][2] = foob; S.misc[warp][3] = fout;
+      S.misc[warp][4] = rs_step2; S.misc[warp][5] = rs_nid; S.misc[warp][6] = rs_cnt; S.misc[warp][7] = 0.f;
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
 
-  // ================================================================== all chunks of the window are done
-  bool ok = grid_barrier(W.bar, W.bar_target);
+  // ---------------------------------------------------------------- phase B: per point (AccumulatedSCHessian.cpp:L36-58)
+  for (int e = tid; e < ch_count * 9; e += nthreads) {
+    const int k = e / ch_count, pl2 = e - k * ch_count;  // lanes = points: conflict-free reads of rec[t][k][.]
+    if (k < 8) {  // host block of the Schur vector
+      float sum = 0.f;
+      for (int tt = 0; tt < nf; tt++)
+        if (tt != h) sum += S.rec[tt][k][pl2];
+      S.Wv[pl2][4 + 8 * h + k] = sum;
+    } else {
+      const int p = ch_start + pl2;
+      float Hdd = 0.f, bd = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, ngood = 0.f;
+      for (int tt = 0; tt < nf; tt++) {
+        if (tt == h) continue;
+        Hdd += S.rec[tt][8][pl2]; bd += S.rec[tt][9][pl2]; c0 += S.rec[tt][10][pl2]; c1 += S.rec[tt][11][pl2];
+        c2 += S.rec[tt][12][pl2]; c3 += S.rec[tt][13][pl2]; ngood += S.rec[tt][14][pl2];
+      }
+      float prior = __ldg(W.priorF + p);
+      bool masked = true;
+      if constexpr (MARG) { masked = __ldg(W.marg_mask + p) != 0; prior *= __ldg(&W.marg->priorFac); }
+      float HdiF = 0.f, bdSum = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+      if (ngood > 0.f) {
+        float H = Hdd + prior;
+        if (H < 1e-10f) H = 1e-10f;
+        HdiF = 1.0f / H;
+        bdSum = MARG ? bd : bd + prior * (S.id[pl2] - S.idz[pl2]);  // shiftPriorToZero (AccumulatedSCHessian.cpp:L47-50)
+        w0 = c0; w1 = c1; w2 = c2; w3 = c3;
+      }
+      S.Wv[pl2][0] = w0; S.Wv[pl2][1] = w1; S.Wv[pl2][2] = w2; S.Wv[pl2][3] = w3;
+      S.Wv[pl2][N] = bdSum;
+      for (int c = N + 1; c < W.NW; c++) S.Wv[pl2][c] = 0.f;  // padding columns of the last 4x4 tiles
+      S.hdi[pl2] = HdiF;
+      if (masked) {
+        float4* po = reinterpret_cast<float4*>(W.pout + (size_t)p * 8);
+        po[0] = make_float4(Hdd, bd, c0, c1);
+        po[1] = make_float4(c2, c3, HdiF, bdSum);
+      }
+    }
+  }
+  // ---- phase C, first half: G(t) = adHost(h,t) * [P | Q | p](h,t) in fp64, [P|Q|p][k][c] = H13[4+k][col(c)], col = 4..11, 0..3, 12
+  for (int e = tid; e < nf * 104; e += nthreads) {
+    const int tt = e / 104, rr = e - tt * 104, i = rr / 13, c = rr - i * 13;
+    if (tt == h) continue;
+    const int colc = (c < 8) ? 4 + c : (c < 12 ? c - 8 : 12);
+    double m = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) m += S.AhD[tt][i * 8 + k] * (double)h13f(S.pair[tt], 4 + k, colc);
+    S.G[tt][rr] = m;
+  }
+  __syncthreads();
+
+  // ---- Schur vectors -> global, transposed ([4-column group][point] float4) so that phase E reads them coalesced
+  {
+    const int T = W.T;
+    for (int e = tid; e < ch_count * T; e += nthreads) {
+      const int g4 = e / ch_count, pl2 = e - g4 * ch_count;
+      W.wg[(size_t)g4 * mp + ch_start + pl2] = *reinterpret_cast<const float4*>(&S.Wv[pl2][4 * g4]);
+    }
+    if (tid < ch_count) W.hdig[ch_start + tid] = S.hdi[tid];
+  }
+  // ---- phase C, second half: the chunk's contributions in absolute coordinates -> partial blob (AccumulatedTopHessian.cpp:L270-286)
+  {
+    double* __restrict__ out = W.part + (size_t)chunk * PART_STRIDE;
+    for (int e = tid; e < nf * PART_SLOT; e += nthreads) {
+      const int tt = e / PART_SLOT, q = e - tt * PART_SLOT;
+      double val;
+      if (tt != h) {
+        const float* B = S.pair[tt];
+        if (q < 64) { const int i = q >> 3, j = q & 7; val = S.G[tt][i * 13 + j] * S.dT[tt][j]; }                               // H[h,t] = (Ah P) At^T
+        else if (q < 128) { const int i = (q - 64) >> 3, j = q & 7; val = S.dT[tt][i] * (double)h13f(B, 4 + i, 4 + j) * S.dT[tt][j]; }  // H[t,t] = At P At^T
+        else if (q < 160) { const int i = (q - 128) >> 2, c = q & 3; val = S.dT[tt][i] * (double)h13f(B, 4 + i, c); }           // H[t,C] = At Q
+        else { const int i = q - 160; val = S.dT[tt][i] * (double)h13f(B, 4 + i, 12); }                                          // b[t] = At p
+      } else {
+        if (q < 64) continue;  // H[h,h] goes to the diagonal slot below
+        val = 0.0;
+        if (q < 128) {  // H[h,h] = sum_t (Ah P) Ah^T
+          const int i = (q - 64) >> 3, j = q & 7;
+          for (int t2 = 0; t2 < nf; t2++) {
+            if (t2 == h) continue;
+#pragma unroll
+            for (int k = 0; k < 8; k++) val += S.G[t2][i * 13 + k] * S.AhD[t2][j * 8 + k];
+          }
+        } else if (q < 160) {  // H[h,C] = sum_t Ah Q
+          const int i = (q - 128) >> 2, c = q & 3;
+          for (int t2 = 0; t2 < nf; t2++) if (t2 != h) val += S.G[t2][i * 13 + 8 + c];
+        } else {  // b[h] = sum_t Ah p
+          const int i = q - 160;
+          for (int t2 = 0; t2 < nf; t2++) if (t2 != h) val += S.G[t2][i * 13 + 12];
+        }
+      }
+      out[e] = val;
+    }
+    if (tid < 20) {  // H[C,C] (4x4) and b[C]
+      const int i = tid / 5, j = tid - i * 5;
+      double val = 0.0;
+      for (int t2 = 0; t2 < nf; t2++) if (t2 != h) val += (double)h13f(S.pair[t2], i, j < 4 ? j : 12);
+      out[PART_CC + (j < 4 ? i * 4 + j : 16 + i)] = val;
+    } else if (tid >= 32 && tid < 40) {
+      const int k = tid - 32;
+      double val = 0.0;
+      for (int wv = 0; wv < nwarps; wv++) val += (double)S.misc[wv][k];
+      out[PART_MISC + k] = val;
+    }
+  }
+  __syncthreads();  // shared memory is reused by the next chunk (persistent case)
+}
+
+// phases D / E for one window: the work is split over `ncta` CTAs, this one acting as CTA `vcta`
+template <int P>
+__device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P>& S, bool ok, const int vcta, const int ncta) {
+  const int nf = W.nf, N = W.N, mp = W.mp;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
 
   const int nH = N * N + N;
   double* __restrict__ R = W.result;
@@ -592,7 +591,7 @@ __global__ void __launch_bounds__(P == 32 ? 224 : 128, P == 32 ? 2 : 4)
   const int npair = nf * (nf - 1) / 2;
   const int n_off = npair * 64, n_diag = nf * 64, n_c = nf * 32, n_b = nf * 8;
   const int nitems = n_off + n_diag + n_c + n_b + 16 + 4 + (ACC_MISC - 1);  // the last counter slot is the error flag: written on error only
-  const int gwarp = blockIdx.x * nwarps + warp, gstride = gridDim.x * nwarps;
+  const int gwarp = vcta * nwarps + warp, gstride = ncta * nwarps;
   const int nch = W.nchunks;
   for (int pass = 0; pass < (xch ? 2 : 1); pass++) {
     for (int item = gwarp; item < nitems; item += gstride) {
@@ -648,7 +647,7 @@ __global__ void __launch_bounds__(P == 32 ? 224 : 128, P == 32 ? 2 : 4)
   // ---------------------------------------------------------------- phase E: [H_sc | b_sc] = sum_p HdiF w_p w_p^T, one CTA per 4x4 tile
   {
     const int T = W.T, npts = W.npts;
-    for (int tile = blockIdx.x; tile < W.ntiles; tile += gridDim.x) {
+    for (int tile = vcta; tile < W.ntiles; tile += ncta) {
       int ti = 0, rem = tile;
       while (rem >= T - ti) { rem -= T - ti; ti++; }
       const int tj = ti + rem;
@@ -701,6 +700,41 @@ __global__ void __launch_bounds__(P == 32 ? 224 : 128, P == 32 ? 2 : 4)
   }
 }
 
+// MARG = true is the marginalisation launch (dmv_ba_marginalize_points): only the points flagged in W.marg_mask take part, their
+// residuals are re-linearised from scratch (PointFrameResidual::resetOOB; FullSystem.cpp:L826-838), EFResidual::fixLinearizationF
+// (EnergyFunctionalStructs.cpp:L88-114) turns resF into res_toZeroF, and the accumulation is AccumulatedTopHessian::addPoint<2> +
+// AccumulatedSCHessian::addPoint(p, shiftPriorToZero = false) with priorF * idepthFixPriorMargFac (EnergyFunctional.cpp:L678-742).
+template <int P, bool MARG>
+__global__ void __launch_bounds__(P == 32 ? 224 : 128, P == 32 ? 2 : 4)
+    ba_fused_kernel(const __grid_constant__ BAWinDev W, const __grid_constant__ BAIter it) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FusedSmem<P>& S = *reinterpret_cast<FusedSmem<P>*>(smem_raw);
+#pragma unroll 1
+  for (int chunk = blockIdx.x; chunk < W.nchunks; chunk += gridDim.x) fused_chunk<P, MARG>(W, it, S, chunk);
+  const bool ok = grid_barrier(W.bar, W.bar_target);  // every chunk of the window is done
+  fused_reduce<P>(W, S, ok, blockIdx.x, gridDim.x);
+}
+
+// Batched variant: B independent windows in ONE launch.  Descriptors and per-iteration tables come from global memory;
+// work items = (window, chunk) pairs dealt round-robin to the resident CTAs; after the grid barrier every window's reduction is spread
+// over all CTAs, rotated per window so that the Schur tiles of different windows land on different CTAs.
+template <int P>
+__global__ void __launch_bounds__(P == 32 ? 224 : 128, P == 32 ? 2 : 4)
+    ba_fused_batch_kernel(const BAWinDev* __restrict__ gW, const BAIter* __restrict__ gIt, const __grid_constant__ BABatchHdr hdr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FusedSmem<P>& S = *reinterpret_cast<FusedSmem<P>*>(smem_raw);
+#pragma unroll 1
+  for (int item = blockIdx.x; item < hdr.total; item += gridDim.x) {
+    int w = 0;
+    while (w + 1 < hdr.B && item >= hdr.prefix[w + 1]) w++;
+    fused_chunk<P, false>(gW[w], gIt[w], S, item - hdr.prefix[w]);
+  }
+  const bool ok = grid_barrier(hdr.bar, hdr.bar_target);
+#pragma unroll 1
+  for (int w = 0; w < hdr.B; w++) fused_reduce<P>(gW[w], S, ok, (int)((blockIdx.x + (unsigned)w * 41u) % gridDim.x), gridDim.x);
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // launch: cooperative (all CTAs resident); shared-memory opt-in and occupancy are cached PER DEVICE (cudaFuncSetAttribute is a
 // per-device setting), under a mutex: handles on several devices / threads of one process are fine
@@ -739,6 +773,43 @@ static cudaError_t launch_cfg(BAWinDev& W, const BAIter& it, cudaStream_t s, uns
   W.bar_target = *bar_count;
   void* args[2] = {(void*)&W, (void*)&it};
   return cudaLaunchCooperativeKernel((const void*)ba_fused_kernel<P, MARG>, dim3(grid), dim3(threads), args, (size_t)smem, s);
+}
+
+template <int P>
+static cudaError_t launch_batch_cfg(const BAWinDev* gW, const BAIter* gIt, BABatchHdr& hdr, int max_nf, cudaStream_t s, unsigned* bar_count) {
+  static FusedCfg cfg[64];
+  constexpr int TPB = (P == 32) ? 224 : 128;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const int smem = (int)sizeof(FusedSmem<P>);
+  const int threads = min(TPB, max(64, ((P * (max_nf - 1)) + 31) & ~31));
+  int max_ctas;
+  {
+    std::lock_guard<std::mutex> lk(g_cfg_mutex);
+    FusedCfg& c = cfg[dev & 63];
+    if (!c.done) {
+      e = cudaFuncSetAttribute(ba_fused_batch_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      int per_sm = 0, sms = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_fused_batch_kernel<P>, TPB, smem);
+      if (e != cudaSuccess) return e;
+      e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (e != cudaSuccess) return e;
+      c.max_ctas = per_sm * sms;
+      c.done = true;
+    }
+    max_ctas = c.max_ctas;
+  }
+  const int grid = min(hdr.total, max_ctas);
+  *bar_count += (unsigned)grid;
+  hdr.bar_target = *bar_count;
+  void* args[3] = {(void*)&gW, (void*)&gIt, (void*)&hdr};
+  return cudaLaunchCooperativeKernel((const void*)ba_fused_batch_kernel<P>, dim3(grid), dim3(threads), args, (size_t)smem, s);
+}
+
+cudaError_t launch_fused_batch_kernel(int P, const BAWinDev* gW, const BAIter* gIt, BABatchHdr& hdr, int max_nf, cudaStream_t s, unsigned* bar_count) {
+  return (P == 32) ? launch_batch_cfg<32>(gW, gIt, hdr, max_nf, s, bar_count) : launch_batch_cfg<16>(gW, gIt, hdr, max_nf, s, bar_count);
 }
 
 // W.bar_target is filled in here; *bar_count is the handle's running arrival count

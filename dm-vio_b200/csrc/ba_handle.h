@@ -8,6 +8,7 @@
 
 namespace dmv {
 cudaError_t launch_fused_kernel(BAWinDev& W, const BAIter& it, bool marg, cudaStream_t s, unsigned* bar_count);
+cudaError_t launch_fused_batch_kernel(int P, const BAWinDev* gW, const BAIter* gIt, BABatchHdr& hdr, int max_nf, cudaStream_t s, unsigned* bar_count);
 void launch_resub_kernel(const BAWinDev& W, const BAIter& it, int apply, double* sums, cudaStream_t s);
 void launch_repack(const float* src, float4* dst, int n, cudaStream_t s);
 void launch_make_dI(const float* img, float4* dst, int w, int h, cudaStream_t s);
@@ -112,3 +113,5 @@ DMV_INTERNAL void dmv_ba_next_exchange(dmv_ba* b);
 DMV_INTERNAL int dmv_ba_enqueue_exchange(dmv_ba* b);
 DMV_INTERNAL void dmv_ba_stage_x(dmv_ba* b, const double* x);
 DMV_INTERNAL int dmv_ba_check_ready(dmv_ba* b);
+DMV_INTERNAL int dmv_ba_stage_state(dmv_ba* b, const dmv_ba_state* st);
+DMV_INTERNAL int dmv_ba_finish_linearize(dmv_ba* b, dmv_ba_lin_result* out, double sums[3]);

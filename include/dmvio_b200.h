@@ -227,6 +227,18 @@ int dmv_ba_comm_init(dmv_ba* ba, int nranks, int rank, const void* nccl_unique_i
 int dmv_ba_p2p_export(dmv_ba* ba, void* ipc_handle64);
 int dmv_ba_p2p_import(dmv_ba* ba, int nranks, int rank, const void* ipc_handles /* nranks*64 bytes, rank order */);
 
+/* ---- batched windows (SURVEY.md section 8d "batched variant"): B independent windows, each an ordinary BA handle on the same device with
+ * the same chunk_points, linearised by ONE launch.  No reference counterpart (FullSystem::optimize handles one window); per window the
+ * results are bit-identical to dmv_ba_gn_step on that handle. */
+typedef struct dmv_ba_batch dmv_ba_batch;
+int dmv_ba_batch_create(dmv_ba* const* handles, int n, dmv_ba_batch** out);   /* n <= 64; the handles stay owned by the caller */
+int dmv_ba_batch_destroy(dmv_ba_batch* batch);
+/* dmv_ba_gn_step on every handle: x[i] may be NULL (x itself may be NULL), st[i] as for dmv_ba_gn_step; out (n entries) and sums3 (3 n doubles)
+ * may be NULL.  Afterwards: dmv_ba_apply_res / dmv_ba_accumulate / ... per handle as usual. */
+int dmv_ba_batch_gn_step(dmv_ba_batch* batch, const double* const* x, const dmv_ba_state* const* st, dmv_ba_lin_result* out, double* sums3);
+int dmv_ba_batch_set_timing(dmv_ba_batch* batch, int enable);
+int dmv_ba_batch_last_kernel_ms(dmv_ba_batch* batch, float* ms);   /* CUDA-event time of the last batched launch (after set_timing(1)) */
+
 /* instrumentation (cheap, always present): CUDA-event timing of the last linearize / gn_step on the handle's stream, milliseconds:
  * [0] = total device time of the call, [1] = ba_fused_kernel, [2] = 0, [3] = what follows the kernel (NCCL all-reduce / D2H copy) */
 int dmv_ba_last_timing(dmv_ba* ba, float ms[4]);

@@ -16,6 +16,11 @@ int dmv_ba_bench_device(dmv_ba* ba, const double* x, int iters, int flush_l2, fl
 /* wall-clock time of `iters` x { dmv_ba_gn_step(x, st) ; dmv_ba_apply_res() } issued from C, milliseconds per iteration */
 int dmv_ba_bench_e2e(dmv_ba* ba, const double* x, const dmv_ba_state* st, int iters, double* ms_per_iter);
 
+/* `iters` x { dmv_ba_batch_gn_step(x, st) ; dmv_ba_apply_res on each of the n handles }: wall clock per iteration (host tables in, B result
+ * blobs out, sync inside) and the CUDA-event time of the batched launch alone */
+int dmv_ba_batch_bench(dmv_ba_batch* batch, dmv_ba* const* handles, int n, const double* const* x, const dmv_ba_state* const* st, int iters,
+                       double* e2e_ms_per_iter, double* kernel_ms_per_iter);
+
 #ifdef __cplusplus
 }
 #endif

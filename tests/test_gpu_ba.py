@@ -161,3 +161,96 @@ def test_full_gn_iteration_matches_oracle(capi, orc, synth):
     assert rel(x_g, x_o) < 1e-3
     ba.backup_points()
     ba.close()
+
+
+def test_batched_windows_identical_to_single_launches(capi, orc, synth):
+    """SURVEY §8d batched variant: B windows of different shapes in ONE launch (dmv_ba_batch_gn_step) give, per window, bit-identical
+    results to the window's own launch — first linearisation and a fused GN step (resubstitute + point step inside the launch)."""
+    import dmvio_b200.hostmath as hm
+    cfgs = [dict(nf=7, npts=2000, seed=1234), dict(nf=4, npts=333, seed=5), dict(nf=8, npts=777, seed=99, hosts="all"), dict(nf=2, npts=200, seed=3, hosts="first")]
+    Ws = [synth.make_window(**c) for c in cfgs]
+
+    def load(W):
+        ow = orc.Window(W)
+        ba = product_ba_from_oracle(capi, W, ow)
+        return ba, (ow.calib()["k8"], ow.precalc(), ow.frame_tables()["frameEnergyTH"])
+
+    singles, batched = [load(W) for W in Ws], [load(W) for W in Ws]
+    batch = capi.BABatch([b for b, _ in batched])
+    keys = ("HA", "bA", "Hsc", "bsc")
+    # ---- first linearisation
+    ref = []
+    for (ba, st) in singles:
+        r = ba.gn_step(None, *st); ba.apply_res()
+        ref.append((r, ba.accumulate(), ba.residual_outputs(), ba.point_outputs()))
+    rb = batch.gn_step(None, [st for _, st in batched])
+    xs = []
+    for i, (ba, st) in enumerate(batched):
+        ba.apply_res()
+        a, g, p = ba.accumulate(), ba.residual_outputs(), ba.point_outputs()
+        assert rb[i]["energy"] == ref[i][0]["energy"] and rb[i]["n_in"] == ref[i][0]["n_in"]
+        for k in keys:
+            np.testing.assert_array_equal(a[k], ref[i][1][k])
+        for k in ("newState", "newEnergy", "JpJdF"):
+            np.testing.assert_array_equal(g[k], ref[i][2][k])
+        np.testing.assert_array_equal(p["HdiF"], ref[i][3]["HdiF"])
+        HL, bL = hm.prior_system(Ws[i])
+        xs.append(hm.solve_reduced(a["HA"], a["bA"], a["Hsc"], a["bsc"], HL, bL, lam=1e-5))
+    # ---- a fused GN step
+    for (ba, st), x in zip(singles, xs):
+        ba.backup_points()
+    for (ba, st) in batched:
+        ba.backup_points()
+    ref2 = []
+    for (ba, st), x in zip(singles, xs):
+        r = ba.gn_step(x, *st); ba.apply_res()
+        ref2.append((r, ba.accumulate(), ba.get_idepth()[0]))
+    rb2 = batch.gn_step(xs, [st for _, st in batched])
+    for i, (ba, st) in enumerate(batched):
+        ba.apply_res()
+        a = ba.accumulate()
+        assert rb2[i]["energy"] == ref2[i][0]["energy"]
+        np.testing.assert_array_equal(rb2[i]["sums"], ref2[i][0]["sums"])
+        for k in keys:
+            np.testing.assert_array_equal(a[k], ref2[i][1][k])
+        np.testing.assert_array_equal(ba.get_idepth()[0], ref2[i][2])
+    batch.close()
+    for ba, _ in singles + batched:
+        ba.close()
+
+
+def test_run_to_run_bit_reproducible(capi, orc, synth):
+    """no atomics on the data path: two launches on the same inputs give the same bits"""
+    W = synth.make_window(nf=7, npts=2000, seed=1234)
+    ow = orc.Window(W)
+    ba = product_ba_from_oracle(capi, W, ow)
+    st = (ow.calib()["k8"], ow.precalc(), ow.frame_tables()["frameEnergyTH"])
+    outs = []
+    for _ in range(3):
+        r = ba.gn_step(None, *st)
+        ba.apply_res()
+        a = ba.accumulate()
+        outs.append((r["energy"], a["HA"].copy(), a["bA"].copy(), a["Hsc"].copy(), a["bsc"].copy()))
+        ba.reset_oob()
+    for o in outs[1:]:
+        assert o[0] == outs[0][0]
+        for x, y in zip(o[1:], outs[0][1:]):
+            np.testing.assert_array_equal(x, y)
+    ba.close()
+
+
+def test_handles_on_two_devices_in_one_process(capi, orc, synth):
+    """VERDICT r1 weak #9: kernel attributes are configured per DEVICE (single-process multi-device hosts, SURVEY §8b dmv_comm_init model)"""
+    if capi.lib().dmv_device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    W = synth.make_window(nf=5, npts=600, seed=8)
+    ow = orc.Window(W)
+    res = []
+    for dev in (0, 1):
+        ba = product_ba_from_oracle(capi, W, ow, device=dev)
+        r = ba.linearize(); ba.apply_res()
+        res.append((r["energy"], ba.accumulate()))
+        ba.close()
+    assert res[0][0] == res[1][0]
+    for k in ("HA", "bA", "Hsc", "bsc"):
+        np.testing.assert_array_equal(res[0][1][k], res[1][1][k])
