@@ -597,7 +597,6 @@ int dmv_ba_marginalize_points(dmv_ba* b, const dmv_ba_marg_args* a) {
   int rc = dmv_ba_check_ready(b);
   if (rc != DMV_OK) return rc;
   if (!a || a->n < 0 || (a->n > 0 && !a->point) || !a->adHTdeltaF) return set_error(DMV_ERR_INVALID, "null argument");
-  if (b->nranks > 1) return set_error(DMV_ERR_STATE, "sharded handle: marginalise per rank and sum (M - Msc) on the host");
   CK(cudaSetDevice(b->device));
   const int nf = b->nf, N = b->N;
   const size_t nres_d = result_doubles(N, b->ntiles), nslots = (size_t)MAXF * b->mp;
@@ -624,16 +623,22 @@ int dmv_ba_marginalize_points(dmv_ba* b, const dmv_ba_marg_args* a) {
   CK(cudaMemcpyAsync(b->d_marg, &M, sizeof(M), cudaMemcpyHostToDevice, b->stream));
   CK(cudaMemcpyAsync(b->d_marg_mask, mask.data(), b->mp, cudaMemcpyHostToDevice, b->stream));
   CK(cudaMemsetAsync(b->d_marg_rtz, 0, sizeof(float) * 8 * nslots, b->stream));
-  // descriptor: the production one with a private result blob, no fused step, no exchange
+  // descriptor: the production one with a private result blob and no fused step.  On a sharded window every rank marginalises ITS flagged points
+  // (n may be 0) and the partial M / Msc are summed over the ranks like any other linearisation (EnergyFunctional.cpp:L678-742 is a sum over
+  // points): every rank must make this call at the same place of its launch sequence; all end with the identical full M, Msc
   b->h_up->it.have_x = 0;
   dmv_ba_fill_descriptor(b);
+  dmv_ba_next_exchange(b);
   BAWinDev& W = b->h_up->win;
   W.result = b->d_marg_result;
   W.result_host = nullptr;
-  W.xc.nranks = 1;
   W.marg = b->d_marg; W.marg_mask = b->d_marg_mask; W.marg_rtz = b->d_marg_rtz;
   CK(launch_fused_kernel(W, b->h_up->it, true, b->stream, &b->bar_count));
   b->launches += 1;
+  if (b->nccl_comm && !b->xchg_on) {
+    const int rcx = dmv::nccl_allreduce_double(b->nccl_comm, b->d_marg_result, (int)nres_d, b->stream);
+    if (rcx != DMV_OK) return rcx;
+  }
   CK(cudaMemcpyAsync(b->h_marg_result, b->d_marg_result, sizeof(double) * nres_d, cudaMemcpyDeviceToHost, b->stream));
   std::vector<uint8_t> st(nslots);
   std::vector<float> rtz;

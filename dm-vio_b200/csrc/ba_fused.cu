@@ -67,12 +67,15 @@ __device__ __forceinline__ float top_entry(const float (&x)[10], const float (&y
   else return 0.f;
 }
 
-// (r, c) of the symmetric 13x13 block from the packed float layout
-__device__ __forceinline__ float h13f(const float* S, int r, int c) {
+// (r, c) of the symmetric 13x13 block from the packed float layout; NH partial blocks (one per warp of the pair) are added
+template <int NH>
+__device__ __forceinline__ float h13f(const float (*S)[96], int r, int c) {
   if (r > c) { const int t = r; r = c; c = t; }
-  if (r < TOP_ROWS) return S[top_off(r) + c - r];
-  const int rr = r - 10, cc = c - 10;
-  return S[TOP_TRI + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5))];
+  int idx;
+  if (r < TOP_ROWS) idx = top_off(r) + c - r;
+  else { const int rr = r - 10, cc = c - 10; idx = TOP_TRI + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5)); }
+  if constexpr (NH == 2) return S[0][idx] + S[1][idx];
+  else return S[0][idx];
 }
 
 // geometric Jacobians of the centre pixel (Residuals.cpp:L113-156): x = d(Ku)/d[C4|xi6], y = d(Kv)/d[C4|xi6], dd = d(Ku,Kv)/d(idepth)
@@ -90,21 +93,40 @@ __device__ __forceinline__ void geo_jac(const float* pc, float Kl0, float Kl1, f
   ddy = drescale * (pc[22] - pc[23] * cv) * fy;
 }
 
-template <int P>
+constexpr int OPS = 57;            // operand record of one residual for the lane-split entry computation (54 used; odd stride: conflict-free)
+template <int P, int LPR>
 struct FusedSmem {
+  static constexpr int NH = (LPR == 4) ? 2 : 1;   // warps per (host, target) pair: each leaves its own partial pair block
   double AhD[MAXF][64];        // adHost(h, t) fp64, row-major, slot = target frame
   double dT[MAXF][8];          // diag adTarget(h, t)
   double G[MAXF][104];         // adHost * [P | Q | p]
-  float adH[MAXF][64];         // fp32 copies used for the Schur vector (the reference's adHostF / adTargetF)
+  float adH[MAXF][64];         // fp32 copies used for the Schur vector (the reference's adHostF / adTargetF); LPR = 1 only
   float adT[MAXF][8];
-  float pair[MAXF][96];        // the chunk's pair blocks (91 used), slot = target frame
+  float pair[MAXF][NH][96];    // the chunk's pair blocks (91 used), slot = target frame
   float rec[MAXF][16][P];      // per target: adHost*JpJdF [8], Hdd, bd, Hcd[4], active, pad   (lane = point: conflict-free)
   float Wv[P][8 * MAXF + 8];   // Schur vectors
   float hdi[P];
   float id[P], idz[P];
-  float misc[8][8];            // per warp: energy, n_in, n_oob, n_outlier, step^2, |idepth_backup|, count
-  double red[8][16];           // phase E: per-warp tile partials
+  float misc[16][8];           // per warp: energy, n_in, n_oob, n_outlier, step^2, |idepth_backup|, count
+  double red[16][32];          // phase E: per-warp partials of up to two 4x4 tiles
 };
+
+// operand indices of entry k of the pair block: entry = ops[a] * ops[b] + ops[c] * ops[d]   (LPR = 4 path; same arithmetic as top_entry<K>)
+// ops = x[0..9] | y[10..19] | al[20..29] | be[30..39] | JabJI00 JabJI01 JabJI10 JabJI11 JIr0 JIr1 [40..45] | Jab00 Jab01 Jabr0 Jab11 Jabr1 rr [46..51] | 0 [52] | 1 [53]
+struct alignas(16) EntryTab { unsigned char v[96][4]; };
+constexpr EntryTab make_entry_tab() {
+  EntryTab t{};
+  for (int k = 0; k < 96; k++) {
+    if (k < TOP_TRI) {
+      const int r = top_row(k), c = top_col(k);
+      if (c < 10) { t.v[k][0] = 20 + r; t.v[k][1] = c; t.v[k][2] = 30 + r; t.v[k][3] = 10 + c; }
+      else { t.v[k][0] = r; t.v[k][1] = 40 + 2 * (c - 10); t.v[k][2] = 10 + r; t.v[k][3] = 41 + 2 * (c - 10); }
+    } else if (k < TOP_USED) { t.v[k][0] = 46 + (k - TOP_TRI); t.v[k][1] = 53; t.v[k][2] = 52; t.v[k][3] = 52; }
+    else { t.v[k][0] = 52; t.v[k][1] = 52; t.v[k][2] = 52; t.v[k][3] = 52; }
+  }
+  return t;
+}
+static __device__ __constant__ EntryTab c_entry_tab = make_entry_tab();
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -178,9 +200,10 @@ __device__ __forceinline__ double xchg_pull_sum(const BAXchg& X, int idx, double
 // (EnergyFunctionalStructs.cpp:L88-114) turns resF into res_toZeroF, and the accumulation is AccumulatedTopHessian::addPoint<2> +
 // AccumulatedSCHessian::addPoint(p, shiftPriorToZero = false) with priorF * idepthFixPriorMargFac (EnergyFunctional.cpp:L678-742).
 // phases A-C for one chunk of one window (W / it may live in kernel-parameter space or in global memory)
-template <int P, bool MARG>
-__device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it, FusedSmem<P>& S, const int chunk) {
+template <int P, int LPR, bool MARG>
+__device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it, FusedSmem<P, LPR>& S, const int chunk) {
   constexpr int LOGP = (P == 32) ? 5 : 4;
+  constexpr int NH = FusedSmem<P, LPR>::NH;
   const int nf = W.nf, N = W.N, mp = W.mp;
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
@@ -198,14 +221,15 @@ __device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it,
   for (int i = tid; i < nf * 4; i += nthreads) cp_async16(&S.dT[i >> 2][(i & 3) * 2], &A->adTdiag[h * nf + (i >> 2)][(i & 3) * 2]);
   asm volatile("cp.async.commit_group;" ::: "memory");
 
-  // ---------------------------------------------------------------- phase A: one thread = one point-residual
+  float e_sum = 0.f, rs_step2 = 0.f, rs_nid = 0.f, rs_cnt = 0.f;
+  int n_in = 0, n_oob = 0, n_outl = 0;
+  if constexpr (LPR == 1) {
+  // ---------------------------------------------------------------- phase A (LPR = 1): one thread = one point-residual
   const int r = tid >> LOGP, pl = tid & (P - 1);  // r-th target frame other than h
   const int t = r + (r >= h ? 1 : 0);
   const bool slot_ok = r < nf - 1;
-  float e_sum = 0.f, rs_step2 = 0.f, rs_nid = 0.f, rs_cnt = 0.f;
-  int n_in = 0, n_oob = 0, n_outl = 0;
-  if ((warp << 5 >> LOGP) < nf - 1) {  // warp-uniform: this warp owns at least one pair
-    const int tc = slot_ok ? t : (h == 0 ? 1 : 0);  // idle half-warps shadow a valid pair (loads stay in bounds, nothing is written)
+  {  // every warp runs the phase (no thread-dependent branch around the shuffles: ptxas then emits plain SHFL, not WARPSYNC-wrapped ones)
+    const int tc = slot_ok ? t : (h == 0 ? 1 : 0);  // lanes without a pair shadow a valid one (loads stay in bounds, nothing is written)
     if (slot_ok) {  // the pair's fp32 adjoints: fetched by the lanes that use them (no block barrier before phase A's tail)
       if (pl < 16) *reinterpret_cast<float4*>(&S.adH[t][pl * 4]) = __ldg(reinterpret_cast<const float4*>(&A->adHostF[h * nf + t][pl * 4]));
       if (pl < 2) *reinterpret_cast<float4*>(&S.adT[t][pl * 4]) = __ldg(reinterpret_cast<const float4*>(&A->adTdiagF[h * nf + t][pl * 4]));
@@ -249,15 +273,25 @@ __device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it,
       float b = po1.w - (it.xc[0] * po0.z + it.xc[1] * po0.w + it.xc[2] * po1.x + it.xc[3] * po1.y);
       int ngood = 0;
 #pragma unroll
-      for (int tt = 0; tt < MAXF; tt++) {
-        if (tt >= nf || tt == h) continue;
-        const int cs = tt * mp + p;
-        if (__ldg(W.c_st + cs) != RES_IN) continue;
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8));
-        const float4 a1 = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8) + 1);
-        const float* xa = it.xAd[h * nf + tt];
-        b -= xa[0] * a0.x + xa[1] * a0.y + xa[2] * a0.z + xa[3] * a0.w + xa[4] * a1.x + xa[5] * a1.y + xa[6] * a1.z + xa[7] * a1.w;
-        ngood++;
+      for (int t4 = 0; t4 < MAXF; t4 += 4) {  // the loads of 4 targets are issued before any is used (2 memory round trips, not one per target)
+        int stc[4];
+        float4 a0[4], a1[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int cs = min(t4 + u, nf - 1) * mp + p;
+          stc[u] = __ldg(W.c_st + cs);
+          a0[u] = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8));
+          a1[u] = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8) + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int tt = t4 + u;
+          const bool good = tt < nf && tt != h && stc[u] == RES_IN;
+          const float* xa = it.xAd[h * nf + min(tt, nf - 1)];
+          const float dot = xa[0] * a0[u].x + xa[1] * a0[u].y + xa[2] * a0[u].z + xa[3] * a0[u].w + xa[4] * a1[u].x + xa[5] * a1[u].y + xa[6] * a1[u].z + xa[7] * a1[u].w;
+          b -= good ? dot : 0.f;
+          ngood += good;
+        }
       }
       const float step = ngood > 0 ? -b * po1.z : 0.f;
       idepth = idb + step;
@@ -444,8 +478,304 @@ __device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it,
     if (slot_ok) {  // lane L of the pair's group now holds entries [(96/P) L, (96/P)(L+1))
       constexpr int PER = 96 / P;
 #pragma unroll
-      for (int k = 0; k < PER; k++) S.pair[t][PER * pl + k] = v[k];
+      for (int k = 0; k < PER; k++) S.pair[t][0][PER * pl + k] = v[k];
     }
+  }
+  } else {
+  // ---------------------------------------------------------------- phase A (LPR = 4): 4 lanes per point-residual, 2 pattern pixels each.
+  // The latency-oriented variant for ONE window: the per-residual chain is ~2.5x shorter and the CTA has 4x the warps, at the price of
+  // redundant per-residual scalar work in the 4 lanes.  A (host, target) pair = 16 points x 4 lanes = 2 warps.
+  static_assert(LPR == 1 || P == 16, "LPR = 4 is written for chunks of 16 points");
+  const int r = tid >> 6;                                 // r-th target frame other than h (warp-uniform)
+  const int pl = (tid & 63) >> 2, q = tid & 3;            // point of the chunk, lane of the residual
+  const int half = (tid >> 5) & 1;                        // which of the pair's two warps
+  const bool pair_ok = r < nf - 1;                        // warps beyond the window's pairs shadow a valid pair and write nothing
+  const int t = pair_ok ? r + (r >= h ? 1 : 0) : (h == 0 ? 1 : 0);
+  {
+    const bool valid = pair_ok && pl < ch_count;
+    const int p = ch_start + min(pl, ch_count - 1);
+    const int slot = t * mp + p;
+    const float* pc = it.precalc[h * nf + t];
+    const float fx = it.calib[0], fy = it.calib[1], cx = it.calib[2], cy = it.calib[3];
+    const float fxi = it.calib[4], fyi = it.calib[5];
+    const float TH = fmaxf(it.TH[h], it.TH[t]);
+    const float wM3 = (float)(W.w - 3), hM3 = (float)(W.h - 3);
+    const float4* __restrict__ img = W.img[t];
+    const int iw = W.w;
+    const float huber = W.huberTH, oth = W.outlierTHSum;
+
+    // ---- direct loads (all independent: one memory round trip); rows 2q, 2q+1 of the pair's fp32 adjoint for the Schur vector
+    int st = valid ? (int)__ldg(W.st_in + slot) : RES_NONE;
+    float en_old = __ldg(W.en_in + slot);
+    bool masked = true;
+    if constexpr (MARG) {
+      masked = valid && __ldg(W.marg_mask + p) != 0;
+      st = (masked && st != RES_NONE) ? RES_IN : RES_NONE;
+      en_old = 0.f;
+    }
+    const float2 uv = __ldg(W.uv + p);
+    const float2 col = __ldg(reinterpret_cast<const float2*>(W.color + (size_t)p * 8) + q);
+    const float2 wgt = __ldg(reinterpret_cast<const float2*>(W.weights + (size_t)p * 8) + q);
+    float4 ah[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) ah[u] = __ldg(reinterpret_cast<const float4*>(&A->adHostF[h * nf + t][q * 16]) + u);
+    const float2 at2 = __ldg(reinterpret_cast<const float2*>(&A->adTdiagF[h * nf + t][q * 2]));
+    float idepth, idz;
+    if (it.have_x) {  // fused resubstituteFPt + point step, as in the LPR = 1 path (every lane of the point recomputes the same step)
+      const float4 po0 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8));
+      const float4 po1 = __ldg(reinterpret_cast<const float4*>(W.c_pout + (size_t)p * 8) + 1);
+      const float idb = __ldg(W.idepth_backup + p);
+      float b = po1.w - (it.xc[0] * po0.z + it.xc[1] * po0.w + it.xc[2] * po1.x + it.xc[3] * po1.y);
+      int ngood = 0;
+#pragma unroll
+      for (int t4 = 0; t4 < MAXF; t4 += 4) {
+        int stc[4];
+        float4 a0[4], a1[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int cs = min(t4 + u, nf - 1) * mp + p;
+          stc[u] = __ldg(W.c_st + cs);
+          a0[u] = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8));
+          a1[u] = __ldg(reinterpret_cast<const float4*>(W.c_jpjd + (size_t)cs * 8) + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int tt = t4 + u;
+          const bool good = tt < nf && tt != h && stc[u] == RES_IN;
+          const float* xa = it.xAd[h * nf + min(tt, nf - 1)];
+          const float dot = xa[0] * a0[u].x + xa[1] * a0[u].y + xa[2] * a0[u].z + xa[3] * a0[u].w + xa[4] * a1[u].x + xa[5] * a1[u].y + xa[6] * a1[u].z + xa[7] * a1[u].w;
+          b -= good ? dot : 0.f;
+          ngood += good;
+        }
+      }
+      const float step = ngood > 0 ? -b * po1.z : 0.f;
+      idepth = idb + step;
+      idz = idepth;
+      if (r == 0 && q == 0 && valid) {
+        W.step[p] = step;
+        W.idepth_out[p] = idepth;
+        rs_step2 = step * step; rs_nid = fabsf(idb); rs_cnt = 1.f;
+      }
+    } else {
+      idepth = __ldg(W.idepth + p);
+      idz = __ldg(W.idepth_zero + p);
+    }
+    if (r == 0 && q == 0 && valid) { S.id[pl] = idepth; S.idz[pl] = idz; }
+    bool live = (st != RES_NONE) && (st != RES_OOB);
+
+    // ---- centre pixel at the FEJ point (every lane)
+    const float Kl0 = (uv.x - cx) * fxi, Kl1 = (uv.y - cy) * fyi;
+    const float q2 = pc[18] * Kl0 + pc[19] * Kl1 + pc[20] + pc[23] * idz;
+    const float drescale = 1.0f / q2;
+    const float new_idepth = idz * drescale;
+    const float cu = (pc[12] * Kl0 + pc[13] * Kl1 + pc[14] + pc[21] * idz) * drescale;
+    const float cv = (pc[15] * Kl0 + pc[16] * Kl1 + pc[17] + pc[22] * idz) * drescale;
+    const float cKu = cu * fx + cx, cKv = cv * fy + cy;
+    live = live && (drescale > 0.f) && cKu > 1.1f && cKv > 1.1f && cKu < wM3 && cKv < hM3;
+
+    // ---- this lane's two pattern pixels (2q, 2q+1) at the current state
+    float Ku[2], Kv[2];
+#pragma unroll
+    for (int jj = 0; jj < 2; jj++) {
+      const float pu = uv.x + (float)c_pattern[2 * q + jj][0], pv = uv.y + (float)c_pattern[2 * q + jj][1];
+      const float r2 = pc[6] * pu + pc[7] * pv + pc[8] + pc[11] * idepth;
+      Ku[jj] = (pc[0] * pu + pc[1] * pv + pc[2] + pc[9] * idepth) / r2;
+      Kv[jj] = (pc[3] * pu + pc[4] * pv + pc[5] + pc[10] * idepth) / r2;
+      live = live && Ku[jj] > 1.1f && Kv[jj] > 1.1f && Ku[jj] < wM3 && Kv[jj] < hM3;
+    }
+    {  // all 8 pixels of the residual must project inside: AND over the 4 lanes
+      const unsigned bal = __ballot_sync(0xffffffffu, live);
+      live = ((bal >> (lane & ~3)) & 0xfu) == 0xfu;
+    }
+    float x[10], y[10], ddx = 0.f, ddy = 0.f, jpx = 0.f, jpy = 0.f, dp6 = 0.f, dp7 = 0.f;
+    if constexpr (MARG) {
+      if (live) {
+        geo_jac(pc, Kl0, Kl1, cu, cv, drescale, new_idepth, fx, fy, fxi, fyi, x, y, ddx, ddy);
+        const float* dp = W.marg->adHTdelta[h * nf + t];
+        const float* cD = W.marg->cDelta;
+        const float dlt = idepth - idz;
+        jpx = (x[4] * dp[0] + x[5] * dp[1] + x[6] * dp[2] + x[7] * dp[3] + x[8] * dp[4] + x[9] * dp[5]) +
+              (x[0] * cD[0] + x[1] * cD[1] + x[2] * cD[2] + x[3] * cD[3]) + ddx * dlt;
+        jpy = (y[4] * dp[0] + y[5] * dp[1] + y[6] * dp[2] + y[7] * dp[3] + y[8] * dp[4] + y[9] * dp[5]) +
+              (y[0] * cD[0] + y[1] * cD[1] + y[2] * cD[2] + y[3] * cD[3]) + ddy * dlt;
+        dp6 = dp[6]; dp7 = dp[7];
+      }
+    }
+
+    // ---- the lane's 2 x 4 taps, residuals, partial sums
+    float sv[17];  // JI00 JI10 JI11 JabJI00 JabJI01 JabJI10 JabJI11 Jab00 Jab01 Jab11 JIr0 JIr1 Jabr0 Jabr1 rr | energy wJI2
+#pragma unroll
+    for (int k = 0; k < 17; k++) sv[k] = 0.f;
+    float rtz[2] = {0.f, 0.f};
+    bool fin = true;
+    if (live) {
+      const bool zA = W.zeroA != 0, zB = W.zeroB != 0;
+      float4 tap[2][4];
+#pragma unroll
+      for (int jj = 0; jj < 2; jj++) {
+        const int ix = (int)Ku[jj], iy = (int)Kv[jj];
+        const float4* bp = img + (size_t)iy * iw + ix;
+        tap[jj][0] = __ldg(bp); tap[jj][1] = __ldg(bp + 1); tap[jj][2] = __ldg(bp + iw); tap[jj][3] = __ldg(bp + iw + 1);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 2; jj++) {
+        const int ix = (int)Ku[jj], iy = (int)Kv[jj];
+        const float dx = Ku[jj] - ix, dy = Kv[jj] - iy, dxdy = dx * dy;
+        const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+        const float h0 = w11 * tap[jj][3].x + w10 * tap[jj][2].x + w01 * tap[jj][1].x + w00 * tap[jj][0].x;
+        const float h1 = w11 * tap[jj][3].y + w10 * tap[jj][2].y + w01 * tap[jj][1].y + w00 * tap[jj][0].y;
+        const float h2 = w11 * tap[jj][3].z + w10 * tap[jj][2].z + w01 * tap[jj][1].z + w00 * tap[jj][0].z;
+        fin = fin && isfinite(h0);
+        const float cj = jj ? col.y : col.x, wj = jj ? wgt.y : wgt.x;
+        const float residual = h0 - (pc[24] * cj + pc[25]);
+        const float drdA = cj - pc[26];
+        float w = sqrtf(oth / (oth + (h1 * h1 + h2 * h2)));
+        w = 0.5f * (w + wj);
+        const float ar = fabsf(residual);
+        float hw = ar < huber ? 1.f : huber / ar;
+        sv[15] += w * w * hw * residual * residual * (2.f - hw);
+        if (hw < 1.f) hw = sqrtf(hw);
+        hw = hw * w;
+        const float gx = h1 * hw, gy = h2 * hw;
+        const float resF = residual * hw;
+        const float ja = drdA * hw, jb = hw;
+        const float jaF = zA ? 0.f : ja, jbF = zB ? 0.f : jb;
+        float ra = resF;
+        if constexpr (MARG) { ra = (((resF - gx * jpx) - gy * jpy) - jaF * dp6) - jbF * dp7; rtz[jj] = ra; }
+        sv[0] += gx * gx; sv[2] += gy * gy; sv[1] += gx * gy;
+        sv[3] += ja * gx; sv[4] += ja * gy; sv[5] += jb * gx; sv[6] += jb * gy;
+        sv[7] += ja * ja; sv[8] += ja * jb; sv[9] += jb * jb;
+        sv[10] += ra * gx; sv[11] += ra * gy; sv[12] += ra * jaF; sv[13] += ra * jbF; sv[14] += ra * ra;
+        sv[16] += hw * hw * (gx * gx + gy * gy);
+      }
+    }
+    {  // every sample finite, and the sums of the residual's 8 pixels in all 4 lanes (butterfly over the lane bits 0, 1)
+      const unsigned bal = __ballot_sync(0xffffffffu, fin);
+      live = live && (((bal >> (lane & ~3)) & 0xfu) == 0xfu);
+#pragma unroll
+      for (int k = 0; k < 17; k++) {
+        sv[k] += __shfl_xor_sync(0xffffffffu, sv[k], 1);
+        sv[k] += __shfl_xor_sync(0xffffffffu, sv[k], 2);
+      }
+    }
+    PixSums s = {sv[0], sv[1], sv[2], sv[3], sv[4], sv[5], sv[6], sv[7], sv[8], sv[9], sv[10], sv[11], sv[12], sv[13], sv[14]};
+    const float energy = sv[15], wJI2 = sv[16];
+
+    // ---- classification and per-residual outputs (identical in the 4 lanes; lane 0 writes)
+    int newState;
+    float newEnergy;
+    if (st == RES_NONE) { newState = RES_NONE; newEnergy = 0.f; }
+    else if (!live) { newState = RES_OOB; newEnergy = en_old; }
+    else if (energy > TH || wJI2 < 2.f) { newState = RES_OUTLIER; newEnergy = TH; }
+    else { newState = RES_IN; newEnergy = energy; }
+    const bool in = (newState == RES_IN);
+    if (st != RES_NONE && q == 0) {
+      e_sum = newEnergy;
+      n_in = in; n_oob = (newState == RES_OOB); n_outl = (newState == RES_OUTLIER);
+    }
+    if constexpr (MARG) {
+      if (masked) *reinterpret_cast<float2*>(W.marg_rtz + (size_t)slot * 8 + 2 * q) = in ? make_float2(rtz[0], rtz[1]) : make_float2(0.f, 0.f);
+    }
+    if (valid && masked && q == 0) {
+      W.st_new[slot] = (uint8_t)newState;
+      W.en_new[slot] = newEnergy;
+      W.en_wo[slot] = (st == RES_NONE || !live) ? -1.f : energy;
+      const size_t plane = (size_t)MAXF * mp;
+      W.cpt[slot] = cKu; W.cpt[plane + slot] = cKv; W.cpt[2 * plane + slot] = new_idepth;
+    }
+
+    // ---- takeDataF, per-point terms, Schur-vector rows (split over the lanes)
+    float jp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Hdd = 0.f, bd = 0.f, Hcd0 = 0.f, Hcd1 = 0.f, Hcd2 = 0.f, Hcd3 = 0.f;
+    if (in) {
+      if constexpr (!MARG) geo_jac(pc, Kl0, Kl1, cu, cv, drescale, new_idepth, fx, fy, fxi, fyi, x, y, ddx, ddy);
+      const float J0 = s.JI00 * ddx + s.JI10 * ddy, J1 = s.JI10 * ddx + s.JI11 * ddy;
+#pragma unroll
+      for (int k = 0; k < 6; k++) jp[k] = x[4 + k] * J0 + y[4 + k] * J1;
+      jp[6] = s.JabJI00 * ddx + s.JabJI01 * ddy; jp[7] = s.JabJI10 * ddx + s.JabJI11 * ddy;
+      Hdd = J0 * ddx + J1 * ddy;
+      bd = s.JIr0 * ddx + s.JIr1 * ddy;
+      Hcd0 = x[0] * J0 + y[0] * J1; Hcd1 = x[1] * J0 + y[1] * J1; Hcd2 = x[2] * J0 + y[2] * J1; Hcd3 = x[3] * J0 + y[3] * J1;
+      if (valid && q == 0) {
+        float4* gj = reinterpret_cast<float4*>(W.jpjd + (size_t)slot * 8);
+        gj[0] = make_float4(jp[0], jp[1], jp[2], jp[3]);
+        gj[1] = make_float4(jp[4], jp[5], jp[6], jp[7]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 10; k++) { x[k] = 0.f; y[k] = 0.f; }
+      s = PixSums{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    }
+    {  // lane q: rows 2q, 2q+1 of adHost * JpJdF and of the (diagonal) adTarget product; lanes 1..3 also carry the per-point scalars
+      const float r0 = ah[0].x * jp[0] + ah[0].y * jp[1] + ah[0].z * jp[2] + ah[0].w * jp[3] + ah[1].x * jp[4] + ah[1].y * jp[5] + ah[1].z * jp[6] + ah[1].w * jp[7];
+      const float r1 = ah[2].x * jp[0] + ah[2].y * jp[1] + ah[2].z * jp[2] + ah[2].w * jp[3] + ah[3].x * jp[4] + ah[3].y * jp[5] + ah[3].z * jp[6] + ah[3].w * jp[7];
+      const float j0 = (q == 0) ? jp[0] : (q == 1) ? jp[2] : (q == 2) ? jp[4] : jp[6];
+      const float j1 = (q == 0) ? jp[1] : (q == 1) ? jp[3] : (q == 2) ? jp[5] : jp[7];
+      if (pair_ok) {
+        S.rec[t][2 * q][pl] = r0; S.rec[t][2 * q + 1][pl] = r1;
+        S.Wv[pl][4 + 8 * t + 2 * q] = at2.x * j0; S.Wv[pl][4 + 8 * t + 2 * q + 1] = at2.y * j1;
+      }
+      const float e0 = (q == 0) ? Hdd : (q == 1) ? Hcd0 : (q == 2) ? Hcd2 : (in ? 1.f : 0.f);
+      const float e1 = (q == 0) ? bd : (q == 1) ? Hcd1 : (q == 2) ? Hcd3 : 0.f;
+      const int k0 = (q == 0) ? 8 : (q == 1) ? 10 : (q == 2) ? 12 : 14;
+      if (pair_ok) { S.rec[t][k0][pl] = e0; S.rec[t][k0 + 1][pl] = e1; }
+    }
+
+    // ---- the pair's 13x13 block, rows split over the 4 lanes: lane q forms rows q, q+4, q+8 of the 10 geometric rows (all columns from the
+    // row group's first column on: compile-time register indices; the few sub-diagonal products are discarded) and lane 2 carries the 6
+    // (a, b, r) entries; then a transposing butterfly over the warp's 8 points (16 + 8 + 4 exchanges) leaves 4 values per lane
+    float v[32];
+    {
+      const float alq[3] = {s.JI00 * ((q == 0) ? x[0] : (q == 1) ? x[1] : (q == 2) ? x[2] : x[3]) + s.JI10 * ((q == 0) ? y[0] : (q == 1) ? y[1] : (q == 2) ? y[2] : y[3]),
+                            s.JI00 * ((q == 0) ? x[4] : (q == 1) ? x[5] : (q == 2) ? x[6] : x[7]) + s.JI10 * ((q == 0) ? y[4] : (q == 1) ? y[5] : (q == 2) ? y[6] : y[7]),
+                            s.JI00 * ((q == 0) ? x[8] : (q == 1) ? x[9] : 0.f) + s.JI10 * ((q == 0) ? y[8] : (q == 1) ? y[9] : 0.f)};
+      const float beq[3] = {s.JI10 * ((q == 0) ? x[0] : (q == 1) ? x[1] : (q == 2) ? x[2] : x[3]) + s.JI11 * ((q == 0) ? y[0] : (q == 1) ? y[1] : (q == 2) ? y[2] : y[3]),
+                            s.JI10 * ((q == 0) ? x[4] : (q == 1) ? x[5] : (q == 2) ? x[6] : x[7]) + s.JI11 * ((q == 0) ? y[4] : (q == 1) ? y[5] : (q == 2) ? y[6] : y[7]),
+                            s.JI10 * ((q == 0) ? x[8] : (q == 1) ? x[9] : 0.f) + s.JI11 * ((q == 0) ? y[8] : (q == 1) ? y[9] : 0.f)};
+      const float xq[3] = {(q == 0) ? x[0] : (q == 1) ? x[1] : (q == 2) ? x[2] : x[3], (q == 0) ? x[4] : (q == 1) ? x[5] : (q == 2) ? x[6] : x[7],
+                           (q == 0) ? x[8] : (q == 1) ? x[9] : 0.f};
+      const float yq[3] = {(q == 0) ? y[0] : (q == 1) ? y[1] : (q == 2) ? y[2] : y[3], (q == 0) ? y[4] : (q == 1) ? y[5] : (q == 2) ? y[6] : y[7],
+                           (q == 0) ? y[8] : (q == 1) ? y[9] : 0.f};
+      // column c of a row: c < 10: al x[c] + be y[c];  c = 10, 11: x_r JabJI(c-10,0) + y_r JabJI(c-10,1);  c = 12: x_r JIr0 + y_r JIr1
+      int o = 0;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+#pragma unroll
+        for (int c = 4 * j; c < 13; c++) {
+          float val;
+          if (c < 10) val = alq[j] * x[c] + beq[j] * y[c];
+          else if (c == 10) val = xq[j] * s.JabJI00 + yq[j] * s.JabJI01;
+          else if (c == 11) val = xq[j] * s.JabJI10 + yq[j] * s.JabJI11;
+          else val = xq[j] * s.JIr0 + yq[j] * s.JIr1;
+          v[o++] = val;   // o: 0..12 (rows 0-3), 13..21 (rows 4-7), 22..26 (rows 8-9)
+        }
+      }
+      if (q == 2) { v[22] = s.Jab00; v[23] = s.Jab01; v[24] = s.Jabr0; v[25] = s.Jab11; v[26] = s.Jabr1; }   // lanes 2, 3 have no third row:
+      v[27] = (q == 2) ? s.rr : 0.f;                                                                             // lane 2 carries the bottom block
+      if (q == 3) { v[22] = v[23] = v[24] = v[25] = v[26] = 0.f; }
+      v[28] = v[29] = v[30] = v[31] = 0.f;
+    }
+    static_for<0, 3>([&](auto sc) {
+      constexpr int st2 = decltype(sc)::value, hstep = 16 >> st2, m = 16 >> st2;   // lane bits 4, 3, 2 = the warp's 8 points
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int k = 0; k < hstep; k++) v[k] = (up ? v[k + hstep] : v[k]) + __shfl_xor_sync(0xffffffffu, up ? v[k] : v[k + hstep], m);
+    });
+    if (pair_ok) {  // lane (point-in-warp w8, q) holds positions 4 w8 + {0..3} of lane class q: position -> (row, column) -> packed index
+      const int w8 = (lane >> 2) & 7;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int pos = 4 * w8 + k;
+        int idx = -1;
+        if (pos < 13) { const int rr = q, c = pos; if (c >= rr) idx = top_off(rr) + c - rr; }
+        else if (pos < 22) { const int rr = q + 4, c = pos - 13 + 4; if (c >= rr) idx = top_off(rr) + c - rr; }
+        else if (pos < 28) {
+          if (q < 2) { const int rr = q + 8, c = pos - 22 + 8; if (pos < 27 && c >= rr) idx = top_off(rr) + c - rr; }
+          else if (q == 2) idx = TOP_TRI + (pos - 22);
+        }
+        if (idx >= 0) S.pair[t][half][idx] = v[k];
+      }
+    }
+  }
   }
   {  // counters: warp sums
     float es = e_sum, fin = (float)n_in, foob = (float)n_oob, fout = (float)n_outl;
@@ -512,7 +842,7 @@ __device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it,
     const int colc = (c < 8) ? 4 + c : (c < 12 ? c - 8 : 12);
     double m = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) m += S.AhD[tt][i * 8 + k] * (double)h13f(S.pair[tt], 4 + k, colc);
+    for (int k = 0; k < 8; k++) m += S.AhD[tt][i * 8 + k] * (double)h13f<NH>(S.pair[tt], 4 + k, colc);
     S.G[tt][rr] = m;
   }
   __syncthreads();
@@ -533,11 +863,11 @@ __device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it,
       const int tt = e / PART_SLOT, q = e - tt * PART_SLOT;
       double val;
       if (tt != h) {
-        const float* B = S.pair[tt];
+        const float (*B)[96] = S.pair[tt];
         if (q < 64) { const int i = q >> 3, j = q & 7; val = S.G[tt][i * 13 + j] * S.dT[tt][j]; }                               // H[h,t] = (Ah P) At^T
-        else if (q < 128) { const int i = (q - 64) >> 3, j = q & 7; val = S.dT[tt][i] * (double)h13f(B, 4 + i, 4 + j) * S.dT[tt][j]; }  // H[t,t] = At P At^T
-        else if (q < 160) { const int i = (q - 128) >> 2, c = q & 3; val = S.dT[tt][i] * (double)h13f(B, 4 + i, c); }           // H[t,C] = At Q
-        else { const int i = q - 160; val = S.dT[tt][i] * (double)h13f(B, 4 + i, 12); }                                          // b[t] = At p
+        else if (q < 128) { const int i = (q - 64) >> 3, j = q & 7; val = S.dT[tt][i] * (double)h13f<NH>(B, 4 + i, 4 + j) * S.dT[tt][j]; }  // H[t,t] = At P At^T
+        else if (q < 160) { const int i = (q - 128) >> 2, c = q & 3; val = S.dT[tt][i] * (double)h13f<NH>(B, 4 + i, c); }           // H[t,C] = At Q
+        else { const int i = q - 160; val = S.dT[tt][i] * (double)h13f<NH>(B, 4 + i, 12); }                                          // b[t] = At p
       } else {
         if (q < 64) continue;  // H[h,h] goes to the diagonal slot below
         val = 0.0;
@@ -561,7 +891,7 @@ __device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it,
     if (tid < 20) {  // H[C,C] (4x4) and b[C]
       const int i = tid / 5, j = tid - i * 5;
       double val = 0.0;
-      for (int t2 = 0; t2 < nf; t2++) if (t2 != h) val += (double)h13f(S.pair[t2], i, j < 4 ? j : 12);
+      for (int t2 = 0; t2 < nf; t2++) if (t2 != h) val += (double)h13f<NH>(S.pair[t2], i, j < 4 ? j : 12);
       out[PART_CC + (j < 4 ? i * 4 + j : 16 + i)] = val;
     } else if (tid >= 32 && tid < 40) {
       const int k = tid - 32;
@@ -574,8 +904,8 @@ __device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it,
 }
 
 // phases D / E for one window: the work is split over `ncta` CTAs, this one acting as CTA `vcta`
-template <int P>
-__device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P>& S, bool ok, const int vcta, const int ncta) {
+template <int P, int LPR>
+__device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR>& S, bool ok, const int vcta, const int ncta) {
   const int nf = W.nf, N = W.N, mp = W.mp;
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
@@ -586,25 +916,29 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P>& S,
   const bool xch = W.xc.nranks > 1;
   const double* __restrict__ part = W.part;
 
-  // ---------------------------------------------------------------- phase D: H_top / b_top / counters, a warp per result entry
-  // item list: [unordered frame pairs a<b: 64 entries each][diagonal blocks: nf x 64][H[.,C]: nf x 32][b: nf x 8][CC 16][bC 4][misc 8]
+  // ---------------------------------------------------------------- phase D: H_top / b_top / counters, 8 lanes per result entry
+  // item list: [unordered frame pairs a<b: 64 entries each][diagonal blocks: nf x 64][H[.,C]: nf x 32][b: nf x 8][CC 16][bC 4][counters 7]
+  // One pass over the items: (number of 8-lane groups in the grid) ~ (number of items), every lane sums <= 17 chunk partials whose loads
+  // are all in flight together (batches of 8), then a 3-step butterfly.  Fixed order => bit-reproducible.
   const int npair = nf * (nf - 1) / 2;
   const int n_off = npair * 64, n_diag = nf * 64, n_c = nf * 32, n_b = nf * 8;
   const int nitems = n_off + n_diag + n_c + n_b + 16 + 4 + (ACC_MISC - 1);  // the last counter slot is the error flag: written on error only
-  const int gwarp = vcta * nwarps + warp, gstride = ncta * nwarps;
+  const int grp = tid >> 3, gl = tid & 7, groups_per_cta = nthreads >> 3;
   const int nch = W.nchunks;
   for (int pass = 0; pass < (xch ? 2 : 1); pass++) {
-    for (int item = gwarp; item < nitems; item += gstride) {
+    for (int base = vcta * groups_per_cta; base < nitems; base += ncta * groups_per_cta) {  // CTA-uniform trip count (shuffles below)
+      const int item = base + grp;
+      const bool act = item < nitems;
       // decode: up to two (offset, chunk range) segments and up to two destinations
-      int off0 = 0, lo0 = 0, hi0 = nch, off1 = -1, lo1 = 0, hi1 = 0, d0, d1 = -1;
-      int e = item;
+      int off0 = 0, lo0 = 0, hi0 = act ? nch : 0, off1 = 0, lo1 = 0, hi1 = 0, d0 = 0, d1 = -1;
+      int e = act ? item : nitems - 1;
       if (e < n_off) {
         const int q = e >> 6, ij = e & 63, i = ij >> 3, j = ij & 7;
         int a = 0, rem = q;
         while (rem >= nf - 1 - a) { rem -= nf - 1 - a; a++; }
         const int b = a + 1 + rem;
-        off0 = b * PART_SLOT + i * 8 + j; lo0 = W.chunk_beg[a]; hi0 = W.chunk_beg[a + 1];
-        off1 = a * PART_SLOT + j * 8 + i; lo1 = W.chunk_beg[b]; hi1 = W.chunk_beg[b + 1];
+        off0 = b * PART_SLOT + i * 8 + j; lo0 = W.chunk_beg[a]; hi0 = act ? W.chunk_beg[a + 1] : lo0;
+        off1 = a * PART_SLOT + j * 8 + i; lo1 = W.chunk_beg[b]; hi1 = act ? W.chunk_beg[b + 1] : lo1;
         d0 = (4 + 8 * a + i) * N + 4 + 8 * b + j; d1 = (4 + 8 * b + j) * N + 4 + 8 * a + i;
       } else if ((e -= n_off) < n_diag) {
         const int a = e >> 6, ij = e & 63;
@@ -627,16 +961,26 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P>& S,
       }
       if (pass == 0) {
         double sum = 0.0;
-        for (int c = lo0 + lane; c < hi0; c += 32) sum += __ldcg(part + (size_t)c * PART_STRIDE + off0);
-        if (off1 >= 0)
-          for (int c = lo1 + lane; c < hi1; c += 32) sum += __ldcg(part + (size_t)c * PART_STRIDE + off1);
+#pragma unroll 1
+        for (int seg = 0; seg < 2; seg++) {
+          const int lo = seg ? lo1 : lo0, hi = seg ? hi1 : hi0;
+          const double* __restrict__ src = part + (seg ? off1 : off0);
+          for (int c0 = lo + gl; c0 < hi; c0 += 64) {
+            double v[8];
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
-        if (lane == 0) {
+            for (int u = 0; u < 8; u++) v[u] = (c0 + 8 * u < hi) ? __ldcg(src + (size_t)(c0 + 8 * u) * PART_STRIDE) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) sum += v[u];
+          }
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        if (gl == 0 && act) {
           if (xch) { R[d0] = sum; xchg_push(W.xc, d0, sum); }
           else { R[d0] = sum; if (d1 >= 0) R[d1] = sum; if (RH) { RH[d0] = sum; if (d1 >= 0) RH[d1] = sum; } }
         }
-      } else if (lane == 0) {
+      } else if (gl == 0 && act) {
         const double sum = xchg_pull_sum(W.xc, d0, R[d0], ok);
         R[d0] = sum; if (d1 >= 0) R[d1] = sum;
         if (RH) { RH[d0] = sum; if (d1 >= 0) RH[d1] = sum; }
@@ -644,46 +988,74 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P>& S,
     }
   }
 
-  // ---------------------------------------------------------------- phase E: [H_sc | b_sc] = sum_p HdiF w_p w_p^T, one CTA per 4x4 tile
+  // ---------------------------------------------------------------- phase E: [H_sc | b_sc] = sum_p HdiF w_p w_p^T as 4x4 tiles over ALL points
+  // of the window: a CTA takes tiles vcta, vcta + ncta (both in ONE pass over the points when the grid has fewer CTAs than tiles)
   {
     const int T = W.T, npts = W.npts;
-    for (int tile = vcta; tile < W.ntiles; tile += ncta) {
-      int ti = 0, rem = tile;
-      while (rem >= T - ti) { rem -= T - ti; ti++; }
-      const int tj = ti + rem;
-      float a[4][4];
+    for (int tile0 = vcta; tile0 < W.ntiles; tile0 += 2 * ncta) {
+      const int tile1 = tile0 + ncta;
+      const bool two = tile1 < W.ntiles;
+      int ti0 = 0, rem = tile0;
+      while (rem >= T - ti0) { rem -= T - ti0; ti0++; }
+      const int tj0 = ti0 + rem;
+      int ti1 = 0;
+      rem = two ? tile1 : tile0;
+      while (rem >= T - ti1) { rem -= T - ti1; ti1++; }
+      const int tj1 = ti1 + rem;
+      float a[2][4][4];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int q = 0; q < 2; q++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) a[i][j] = 0.f;
-      const float4* __restrict__ wi_p = W.wg + (size_t)ti * mp;
-      const float4* __restrict__ wj_p = W.wg + (size_t)tj * mp;
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) a[q][i][j] = 0.f;
+      const float4* __restrict__ wi0 = W.wg + (size_t)ti0 * mp;
+      const float4* __restrict__ wj0 = W.wg + (size_t)tj0 * mp;
+      const float4* __restrict__ wi1 = W.wg + (size_t)ti1 * mp;
+      const float4* __restrict__ wj1 = W.wg + (size_t)tj1 * mp;
 #pragma unroll 4
       for (int p = tid; p < npts; p += nthreads) {
         const float sc = __ldcg(W.hdig + p);
-        const float4 wi = __ldcg(wi_p + p), wj = __ldcg(wj_p + p);
+        const float4 wi = __ldcg(wi0 + p), wj = __ldcg(wj0 + p);
         const float si[4] = {sc * wi.x, sc * wi.y, sc * wi.z, sc * wi.w};
         const float vj[4] = {wj.x, wj.y, wj.z, wj.w};
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) a[i][j] += si[i] * vj[j];
-      }
-      // per-thread fp32 sums over <= npts / nthreads points, then fp64: warp butterfly, cross-warp through shared memory
+          for (int j = 0; j < 4; j++) a[0][i][j] += si[i] * vj[j];
+        if (two) {  // CTA-uniform
+          const float4 xi = __ldcg(wi1 + p), xj = __ldcg(wj1 + p);
+          const float ti[4] = {sc * xi.x, sc * xi.y, sc * xi.z, sc * xi.w};
+          const float uj[4] = {xj.x, xj.y, xj.z, xj.w};
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+          for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          double d = (double)a[i][j];
-#pragma unroll
-          for (int m = 16; m >= 1; m >>= 1) d += __shfl_xor_sync(0xffffffffu, d, m);
-          if (lane == 0) S.red[warp][i * 4 + j] = d;
+            for (int j = 0; j < 4; j++) a[1][i][j] += ti[i] * uj[j];
         }
+      }
+      // per-thread fp32 sums over <= npts / nthreads points, then fp64: transposing warp butterfly (31 exchanges for the 32 values: lane L
+      // ends with the warp's sum of value L), cross-warp through shared memory
+      {
+        double d[32];
+#pragma unroll
+        for (int qq = 0; qq < 2; qq++)
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) d[qq * 16 + i * 4 + j] = (double)a[qq][i][j];
+        static_for<0, 5>([&](auto sc) {
+          constexpr int st2 = decltype(sc)::value, hstep = 16 >> st2, m = 16 >> st2;
+          const bool up = (lane & m) != 0;
+#pragma unroll
+          for (int k = 0; k < hstep; k++) d[k] = (up ? d[k + hstep] : d[k]) + __shfl_xor_sync(0xffffffffu, up ? d[k] : d[k + hstep], m);
+        });
+        S.red[warp][lane] = d[0];   // lane L: value index 16 b4 + 8 b3 + 4 b2 + 2 b1 + b0 = L
+      }
       __syncthreads();
-      if (tid < 16) {
+      if (tid < 32 && (tid < 16 || two)) {
         double d = 0.0;
         for (int wv = 0; wv < nwarps; wv++) d += S.red[wv][tid];
-        const int idx = nH + tile * 16 + tid;
+        const int idx = nH + (tid < 16 ? tile0 : tile1) * 16 + (tid & 15);
         if (xch) {
           xchg_push(W.xc, idx, d);
           d = xchg_pull_sum(W.xc, idx, d, ok);
@@ -694,7 +1066,7 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P>& S,
       __syncthreads();
     }
   }
-  if (!ok && lane == 0) {  // barrier / peer timeout: poison the error slot of the counters (checked by the host)
+  if (!__syncthreads_and(ok) && tid == 0) {  // barrier / peer timeout seen by any thread: raise the error slot of the counters (checked by the host)
     R[nH + W.ntiles * 16 + 7] = 1.0;
     if (RH) RH[nH + W.ntiles * 16 + 7] = 1.0;
   }
@@ -704,36 +1076,41 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P>& S,
 // residuals are re-linearised from scratch (PointFrameResidual::resetOOB; FullSystem.cpp:L826-838), EFResidual::fixLinearizationF
 // (EnergyFunctionalStructs.cpp:L88-114) turns resF into res_toZeroF, and the accumulation is AccumulatedTopHessian::addPoint<2> +
 // AccumulatedSCHessian::addPoint(p, shiftPriorToZero = false) with priorF * idepthFixPriorMargFac (EnergyFunctional.cpp:L678-742).
+// Two configurations: chunk_points = 16 -> (P = 16, LPR = 4): 448 threads, 4 lanes per residual (the latency-oriented default for ONE window);
+//                     chunk_points = 32 -> (P = 32, LPR = 1): 224 threads, one thread per residual (fewest instructions: batches / large windows)
+template <int P> struct FusedCfgOf { static constexpr int LPR = (P == 16) ? 4 : 1, TPB = (P == 16) ? 448 : 224; };
+
 template <int P, bool MARG>
-__global__ void __launch_bounds__(P == 32 ? 224 : 128, P == 32 ? 2 : 4)
+__global__ void __launch_bounds__(FusedCfgOf<P>::TPB, 1)
     ba_fused_kernel(const __grid_constant__ BAWinDev W, const __grid_constant__ BAIter it) {
+  constexpr int LPR = FusedCfgOf<P>::LPR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FusedSmem<P>& S = *reinterpret_cast<FusedSmem<P>*>(smem_raw);
+  FusedSmem<P, LPR>& S = *reinterpret_cast<FusedSmem<P, LPR>*>(smem_raw);
 #pragma unroll 1
-  for (int chunk = blockIdx.x; chunk < W.nchunks; chunk += gridDim.x) fused_chunk<P, MARG>(W, it, S, chunk);
+  for (int chunk = blockIdx.x; chunk < W.nchunks; chunk += gridDim.x) fused_chunk<P, LPR, MARG>(W, it, S, chunk);
   const bool ok = grid_barrier(W.bar, W.bar_target);  // every chunk of the window is done
-  fused_reduce<P>(W, S, ok, blockIdx.x, gridDim.x);
+  fused_reduce<P, LPR>(W, S, ok, blockIdx.x, gridDim.x);
 }
 
 // Batched variant: B independent windows in ONE launch.  Descriptors and per-iteration tables come from global memory;
 // work items = (window, chunk) pairs dealt round-robin to the resident CTAs; after the grid barrier every window's reduction is spread
 // over all CTAs, rotated per window so that the Schur tiles of different windows land on different CTAs.
 template <int P>
-__global__ void __launch_bounds__(P == 32 ? 224 : 128, P == 32 ? 2 : 4)
+__global__ void __launch_bounds__(FusedCfgOf<P>::TPB, P == 32 ? 2 : 1)
     ba_fused_batch_kernel(const BAWinDev* __restrict__ gW, const BAIter* __restrict__ gIt, const __grid_constant__ BABatchHdr hdr) {
+  constexpr int LPR = FusedCfgOf<P>::LPR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FusedSmem<P>& S = *reinterpret_cast<FusedSmem<P>*>(smem_raw);
+  FusedSmem<P, LPR>& S = *reinterpret_cast<FusedSmem<P, LPR>*>(smem_raw);
 #pragma unroll 1
   for (int item = blockIdx.x; item < hdr.total; item += gridDim.x) {
     int w = 0;
     while (w + 1 < hdr.B && item >= hdr.prefix[w + 1]) w++;
-    fused_chunk<P, false>(gW[w], gIt[w], S, item - hdr.prefix[w]);
+    fused_chunk<P, LPR, false>(gW[w], gIt[w], S, item - hdr.prefix[w]);
   }
   const bool ok = grid_barrier(hdr.bar, hdr.bar_target);
 #pragma unroll 1
-  for (int w = 0; w < hdr.B; w++) fused_reduce<P>(gW[w], S, ok, (int)((blockIdx.x + (unsigned)w * 41u) % gridDim.x), gridDim.x);
+  for (int w = 0; w < hdr.B; w++) fused_reduce<P, LPR>(gW[w], S, ok, (int)((blockIdx.x + (unsigned)w * 41u) % gridDim.x), gridDim.x);
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // launch: cooperative (all CTAs resident); shared-memory opt-in and occupancy are cached PER DEVICE (cudaFuncSetAttribute is a
@@ -745,12 +1122,12 @@ static std::mutex g_cfg_mutex;
 template <int P, bool MARG>
 static cudaError_t launch_cfg(BAWinDev& W, const BAIter& it, cudaStream_t s, unsigned* bar_count) {
   static FusedCfg cfg[64];
-  constexpr int TPB = (P == 32) ? 224 : 128;
+  constexpr int TPB = FusedCfgOf<P>::TPB;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  const int smem = (int)sizeof(FusedSmem<P>);
-  const int threads = min(TPB, max(64, ((P * (W.nf - 1)) + 31) & ~31));
+  const int smem = (int)sizeof(FusedSmem<P, FusedCfgOf<P>::LPR>);
+  const int threads = TPB;  // fixed block size: the summation orders of phases D / E depend on it, and batched launches must reproduce single ones bit for bit
   int max_ctas;
   {
     std::lock_guard<std::mutex> lk(g_cfg_mutex);
@@ -778,12 +1155,13 @@ static cudaError_t launch_cfg(BAWinDev& W, const BAIter& it, cudaStream_t s, uns
 template <int P>
 static cudaError_t launch_batch_cfg(const BAWinDev* gW, const BAIter* gIt, BABatchHdr& hdr, int max_nf, cudaStream_t s, unsigned* bar_count) {
   static FusedCfg cfg[64];
-  constexpr int TPB = (P == 32) ? 224 : 128;
+  constexpr int TPB = FusedCfgOf<P>::TPB;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  const int smem = (int)sizeof(FusedSmem<P>);
-  const int threads = min(TPB, max(64, ((P * (max_nf - 1)) + 31) & ~31));
+  const int smem = (int)sizeof(FusedSmem<P, FusedCfgOf<P>::LPR>);
+  const int threads = TPB;
+  (void)max_nf;
   int max_ctas;
   {
     std::lock_guard<std::mutex> lk(g_cfg_mutex);

@@ -12,6 +12,7 @@
 #include "inv3.h"
 #include "ip_trace.h"
 #include "ct_depth.h"
+#include <cuda.h>
 #include <unordered_map>
 #include <algorithm>
 #include <cstring>
@@ -498,6 +499,233 @@ __global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// ct_track_cluster_kernel — the same trackNewestCoarse state machine on ONE THREAD-BLOCK CLUSTER (sm_90+ hardware feature):
+//   * the CTAs of the cluster exchange their fp64 partials through DISTRIBUTED SHARED MEMORY (st.shared::cluster into every peer's
+//     slot) and meet at the hardware cluster barrier (barrier.cluster.arrive/wait): no global-memory partials, no atomics, no spinning
+//     on an L2 counter — the per-evaluation synchronisation of the 39-CTA grid version (~4 us) shrinks to a few hundred ns;
+//   * pyramid levels whose float4 plane fits in shared memory (80x60 at 640x480: 76.8 KB; 64x64 at 512^2; 40x30) are staged ONCE per
+//     level by TMA (cp.async.bulk.tensor.2d, multicast to every CTA of the cluster, completion on an mbarrier) and every Levenberg-
+//     Marquardt evaluation of that level gathers its 4 taps per point from shared memory instead of L2;
+//   * the block reduction of the 53 sums per point is a transposing butterfly (62 shuffles per warp instead of 265).
+// Every CTA folds the cluster's partials in rank order and advances the same scalar state machine: identical decisions everywhere.
+// A sequential LM chain is latency-bound: fewer, closer SMs with a hardware barrier beat a chip-wide software barrier.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int CTC_THREADS = 512;
+constexpr int CTC_MAXC = 16;                 // CTAs per cluster (8 portable, 16 with the non-portable opt-in)
+constexpr int CTC_PLANE_BYTES = 80 * 1024;   // largest level plane staged in shared memory
+struct alignas(64) CTMaps { CUtensorMap lvl[CT_L]; };   // level planes as 2-D tensors of 16-byte texels (encoded as pairs of fp64)
+
+struct alignas(128) CTCSmem {
+  unsigned char plane[CTC_PLANE_BYTES];      // TMA destination: the staged level, row-major float4
+  double xch[2][CTC_MAXC][CT_NRED + 3];      // [parity][source CTA][sum]: written by every CTA of the cluster through DSMEM
+  float red[CTC_THREADS / 32][64];           // per-warp sums (transposed butterfly output)
+  double s_sum[CT_NRED + 3];
+  CTLM S;
+  unsigned long long mbar;                   // TMA completion barrier
+};
+
+__device__ __forceinline__ unsigned ctc_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned ctc_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void ctc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned ctc_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// one reference point against a plane in SHARED memory (same arithmetic as ct_eval_point; the taps come from the staged copy)
+template <bool SMEM>
+__device__ __forceinline__ void ctc_eval_accumulate(const CTParams& P, int i, const float* __restrict__ pc_u, const float* __restrict__ pc_v,
+                                                    const float* __restrict__ pc_id, const float* __restrict__ pc_col, const float4* __restrict__ img,
+                                                    const float4* plane_s, float v[CT_NRED]) {
+  const float id = pc_id[i], x = pc_u[i], y = pc_v[i];
+  const float p0 = P.RKi[0] * x + P.RKi[1] * y + P.RKi[2] + P.t[0] * id;
+  const float p1 = P.RKi[3] * x + P.RKi[4] * y + P.RKi[5] + P.t[1] * id;
+  const float p2 = P.RKi[6] * x + P.RKi[7] * y + P.RKi[8] + P.t[2] * id;
+  const float u = p0 / p2, vv = p1 / p2;
+  const float Ku = P.fx * u + P.cx, Kv = P.fy * vv + P.cy;
+  const float new_idepth = id / p2;
+  if (P.lvl == 0 && (i & 31) == 0) {  // flow indicators (CoarseTracker.cpp:L416-447)
+    const float k0 = P.Ki[0] * x + P.Ki[1] * y + P.Ki[2], k1 = P.Ki[3] * x + P.Ki[4] * y + P.Ki[5], k2 = P.Ki[6] * x + P.Ki[7] * y + P.Ki[8];
+    const float T0 = k0 + P.t[0] * id, T1 = k1 + P.t[1] * id, T2 = k2 + P.t[2] * id;
+    const float M0 = k0 - P.t[0] * id, M1 = k1 - P.t[1] * id, M2 = k2 - P.t[2] * id;
+    const float q0 = P.RKi[0] * x + P.RKi[1] * y + P.RKi[2] - P.t[0] * id;
+    const float q1 = P.RKi[3] * x + P.RKi[4] * y + P.RKi[5] - P.t[1] * id;
+    const float q2 = P.RKi[6] * x + P.RKi[7] * y + P.RKi[8] - P.t[2] * id;
+    const float KuT = P.fx * (T0 / T2) + P.cx, KvT = P.fy * (T1 / T2) + P.cy;
+    const float KuT2 = P.fx * (M0 / M2) + P.cx, KvT2 = P.fy * (M1 / M2) + P.cy;
+    const float Ku3 = P.fx * (q0 / q2) + P.cx, Kv3 = P.fy * (q1 / q2) + P.cy;
+    v[49] += (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y) + (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
+    v[50] += (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y) + (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
+    v[51] += 2.f;
+  }
+  if (Ku > 2.f && Kv > 2.f && Ku < (float)(P.w - 3) && Kv < (float)(P.h - 3) && new_idepth > 0.f) {
+    const int ix = (int)Ku, iy = (int)Kv;
+    const float dx = Ku - ix, dy = Kv - iy, dxdy = dx * dy;
+    float4 tl, tr, bl, br;
+    if constexpr (SMEM) {
+      const float4* bp = plane_s + iy * P.w + ix;
+      tl = bp[0]; tr = bp[1]; bl = bp[P.w]; br = bp[P.w + 1];
+    } else {
+      const float4* bp = img + (size_t)iy * P.w + ix;
+      tl = __ldg(bp); tr = __ldg(bp + 1); bl = __ldg(bp + P.w); br = __ldg(bp + P.w + 1);
+    }
+    const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+    const float h0 = w11 * br.x + w10 * bl.x + w01 * tr.x + w00 * tl.x;
+    const float h1 = w11 * br.y + w10 * bl.y + w01 * tr.y + w00 * tl.y;
+    const float h2 = w11 * br.z + w10 * bl.z + w01 * tr.z + w00 * tl.z;
+    if (isfinite(h0)) {
+      const float refColor = pc_col[i];
+      const float residual = h0 - (P.affa * refColor + P.affb);
+      const float ar = fabsf(residual);
+      const float hw = ar < P.huber ? 1.f : P.huber / ar;
+      if (ar > P.cutoff) {
+        v[45] += P.maxEnergy; v[46] += 1.f; v[47] += 1.f;
+      } else {
+        v[45] += hw * residual * residual * (2.f - hw); v[46] += 1.f; v[48] += 1.f;
+        const float gx = h1 * P.fx, gy = h2 * P.fy;
+        float J[9];
+        J[0] = new_idepth * gx;
+        J[1] = new_idepth * gy;
+        J[2] = 0.f - new_idepth * (u * gx + vv * gy);
+        J[3] = 0.f - ((u * vv) * gx + gy * (1.f + vv * vv));
+        J[4] = (u * vv) * gy + gx * (1.f + u * u);
+        J[5] = u * gy - vv * gx;
+        J[6] = P.a_gs * (P.b0 - refColor);
+        J[7] = -1.f;
+        J[8] = residual;
+        int e = 0;
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          const float Jw = J[r] * hw;
+#pragma unroll
+          for (int c = r; c < 9; c++) v[e++] += Jw * J[c];
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CTC_THREADS, 1) ct_track_cluster_kernel(const __grid_constant__ CTTrack T, const __grid_constant__ CTMaps maps) {
+  extern __shared__ __align__(128) unsigned char ctc_raw[];
+  CTCSmem& M = *reinterpret_cast<CTCSmem*>(ctc_raw);
+  CTLM& S = M.S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned rank = ctc_rank(), NC = ctc_size();
+  int par = 0, staged_lvl = -1;
+  unsigned mphase = 0;
+  if (tid == 0) {
+    for (int i = 0; i < 9; i++) S.R[i] = T.R0[i];
+    for (int i = 0; i < 3; i++) S.t[i] = T.t0[i];
+    S.a = T.a0; S.b = T.b0;
+    for (int i = 0; i < 5; i++) S.lastResiduals[i] = __longlong_as_double(0x7ff8000000000000ll);  // NAN
+    for (int i = 0; i < 3; i++) S.flow[i] = 1000;
+    S.haveRepeated = 0; S.iterations = 0; S.evaluations = 0; S.done = 0; S.good = 0; S.status = 0; S.cur = 0;
+    S.lvl = T.coarsest;
+    ct_begin_level(T, S);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ctc_smem_u32(&M.mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  ctc_cluster_sync();  // every CTA's mbarrier exists before the first multicast copy can signal it
+  while (!S.done) {
+    const int l = S.lvl;
+    // ---- level change: stage the plane with TMA if it fits (one multicast copy issued by CTA 0 lands in every CTA's shared memory)
+    const bool fits = (size_t)T.w[l] * T.h[l] * sizeof(float4) <= (size_t)CTC_PLANE_BYTES;
+    if (fits && staged_lvl != l) {
+      const unsigned bytes = (unsigned)(T.w[l] * T.h[l] * sizeof(float4));
+      if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ctc_smem_u32(&M.mbar)), "r"(bytes) : "memory");
+      ctc_cluster_sync();  // all barriers armed (and nobody still reads the previous level's plane)
+      if (rank == 0 && tid == 0) {
+        const unsigned short mask = (unsigned short)((1u << NC) - 1u);
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+                ctc_smem_u32(M.plane)),
+            "l"(&maps.lvl[l]), "r"(ctc_smem_u32(&M.mbar)), "r"(0), "r"(0), "h"(mask)
+            : "memory");
+      }
+      {  // wait for the bytes (try_wait suspends the thread between probes)
+        const unsigned mb = ctc_smem_u32(&M.mbar);
+        unsigned done = 0;
+        while (!done)
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mb), "r"(mphase) : "memory");
+      }
+      mphase ^= 1u;
+      staged_lvl = l;
+    }
+    // ---- one evaluation: calcRes + calcGSSSE at the requested pose
+    CTParams P;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { P.RKi[i] = S.RKi[i]; P.Ki[i] = T.Ki[l][i]; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) P.t[i] = S.tf[i];
+    P.fx = T.fx[l]; P.fy = T.fy[l]; P.cx = T.cx[l]; P.cy = T.cy[l];
+    P.affa = S.affLL[0]; P.affb = S.affLL[1]; P.a_gs = S.affLL[0]; P.b0 = (float)T.ref_b;
+    P.cutoff = S.cutoff; P.huber = T.huber; P.maxEnergy = 2 * T.huber * S.cutoff - T.huber * T.huber;
+    P.w = T.w[l]; P.h = T.h[l]; P.n = T.n[l]; P.lvl = l; P.want_gs = 1;
+    float v[64];
+#pragma unroll
+    for (int k = 0; k < 64; k++) v[k] = 0.f;
+    const int stride = (int)NC * CTC_THREADS;
+    if (fits) {
+      for (int i = (int)rank * CTC_THREADS + tid; i < P.n; i += stride)
+        ctc_eval_accumulate<true>(P, i, T.u[l], T.v[l], T.id[l], T.col[l], T.img[l], reinterpret_cast<const float4*>(M.plane), v);
+    } else {
+      for (int i = (int)rank * CTC_THREADS + tid; i < P.n; i += stride)
+        ctc_eval_accumulate<false>(P, i, T.u[l], T.v[l], T.id[l], T.col[l], T.img[l], nullptr, v);
+    }
+    // ---- warp: transposing butterfly, lane L ends with the warp sums of entries 2L, 2L+1
+    {
+      static_assert(CT_NRED <= 64, "");
+#pragma unroll
+      for (int st2 = 0; st2 < 5; st2++) {
+        const int hstep = 32 >> st2, m = 16 >> st2;
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int k = 0; k < 32; k++)
+          if (k < hstep) v[k] = (up ? v[k + hstep] : v[k]) + __shfl_xor_sync(0xffffffffu, up ? v[k] : v[k + hstep], m);
+      }
+      // entry index of v[k] in lane L: 32 b4 + 16 b3 + 8 b2 + 4 b1 + 2 b0 + k = 2 * bitrev-free L' ... = 2 L + k with L's bits in natural order
+      M.red[warp][2 * lane] = v[0];
+      M.red[warp][2 * lane + 1] = v[1];
+    }
+    __syncthreads();
+    // ---- CTA: fp64 sum over the warps, pushed into EVERY CTA's exchange slot through distributed shared memory
+    if (tid < CT_NRED) {
+      double sm = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < CTC_THREADS / 32; wv++) sm += (double)M.red[wv][tid];
+      const unsigned local = ctc_smem_u32(&M.xch[par][rank][tid]);
+      for (unsigned c = 0; c < NC; c++) {
+        unsigned remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(c));
+        asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(sm) : "memory");
+      }
+    }
+    ctc_cluster_sync();  // release / acquire at cluster scope: every CTA's partials are visible in every CTA's shared memory
+    if (tid < CT_NRED) {
+      double sm = 0.0;
+      for (unsigned c = 0; c < NC; c++) sm += M.xch[par][c][tid];  // rank order: bit-identical in every CTA
+      M.s_sum[tid] = sm;
+    }
+    par ^= 1;
+    __syncthreads();
+    ct_finish_parallel(M.s_sum, S.res[S.cur ^ 1], S.H[S.cur ^ 1], S.bb[S.cur ^ 1], tid);
+    __syncthreads();
+    if (tid == 0) ct_advance(T, S);
+    __syncthreads();
+  }
+  ctc_cluster_sync();  // nobody leaves while a peer may still write into its shared memory
+  if (rank == 0 && tid == 0) {
+    double* o = T.out;
+    for (int i = 0; i < 9; i++) o[i] = S.R[i];
+    for (int i = 0; i < 3; i++) o[9 + i] = S.t[i];
+    o[12] = S.a; o[13] = S.b;
+    for (int i = 0; i < 5; i++) o[14 + i] = S.lastResiduals[i];
+    for (int i = 0; i < 3; i++) o[19 + i] = S.flow[i];
+    o[22] = S.good; o[23] = S.iterations; o[24] = S.evaluations; o[25] = S.status;
+  }
+}
+
 __global__ void ct_repack_kernel(const float* __restrict__ src, float4* __restrict__ dst, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
@@ -555,6 +783,8 @@ struct dmv_ct {
   float* h_ip = nullptr;
   int ip_cap = 0;
   float huber = 9.f;
+  int cluster_size = 0;        // CTAs of ct_track_cluster_kernel's cluster (0 = not probed yet, -1 = unavailable: grid version)
+  CTMaps* maps = nullptr;      // TMA descriptors of the level planes (host copy; passed as a kernel parameter)
   long long launches = 0;
   float last_ms[4] = {0, 0, 0, 0};
 };
@@ -633,6 +863,7 @@ int dmv_ct_destroy(dmv_ct* c) {
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
   if (c->stream) cudaStreamDestroy(c->stream);
+  delete c->maps;
   delete c;
   return DMV_OK;
 }
@@ -761,6 +992,34 @@ int dmv_ct_calc_res_gs(dmv_ct* c, int l, const float RKi[9], const float t[3], c
   return DMV_OK;
 }
 
+// TMA descriptors of the level planes: a w x h plane of float4 texels = a 2-D tensor of (2w) x h fp64 elements (the widest element type a
+// tensor map knows; 16-byte texels = pairs), one box = the whole plane.  Only levels that fit CTC_PLANE_BYTES are ever copied.
+static int ct_make_tensor_maps(dmv_ct* c) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return set_error(DMV_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  }
+  if (!c->maps) c->maps = new CTMaps();
+  std::memset(c->maps, 0, sizeof(CTMaps));
+  for (int l = 0; l < c->cfg.levels; l++) {
+    const size_t bytes = (size_t)c->w[l] * c->h[l] * sizeof(float4);
+    if (bytes > (size_t)CTC_PLANE_BYTES || 2 * c->w[l] > 256 || c->h[l] > 256) continue;   // never staged (box limits: 256 elements per dimension)
+    const cuuint64_t gdim[2] = {(cuuint64_t)(2 * c->w[l]), (cuuint64_t)c->h[l]};
+    const cuuint64_t gstride[1] = {(cuuint64_t)c->w[l] * sizeof(float4)};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * c->w[l]), (cuuint32_t)c->h[l]};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = reinterpret_cast<EncodeFn>(fn)(&c->maps->lvl[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, c->d_img[l], gdim, gstride, box, estr,
+                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(DMV_ERR_CUDA, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+  }
+  return DMV_OK;
+}
+
 // CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:L539-770, visual-only branch) in one persistent launch
 int dmv_ct_track(dmv_ct* c, const dmv_ct_track_args* in, dmv_ct_track_result* out) {
   if (!c || !in || !out) return set_error(DMV_ERR_INVALID, "null argument");
@@ -782,7 +1041,6 @@ int dmv_ct_track(dmv_ct* c, const dmv_ct_track_args* in, dmv_ct_track_result* ou
   T.G = (maxn + CT_THREADS - 1) / CT_THREADS;
   int dev_sms = 0;
   CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device));
-  if (T.G > dev_sms) return set_error(DMV_ERR_INVALID, "%d reference points need %d co-resident CTAs, the device has %d SMs: use dmv_ct_calc_res_gs", maxn, T.G, dev_sms);
   for (int i = 0; i < 9; i++) T.R0[i] = in->R[i];
   for (int i = 0; i < 3; i++) T.t0[i] = in->t[i];
   T.a0 = in->a; T.b0 = in->b; T.ref_a = in->ref_a; T.ref_b = in->ref_b;
@@ -790,9 +1048,38 @@ int dmv_ct_track(dmv_ct* c, const dmv_ct_track_args* in, dmv_ct_track_result* ou
   T.huber = c->huber; T.cutoffTH = in->coarseCutoffTH; T.affModeA = in->affineOptModeA; T.affModeB = in->affineOptModeB;
   for (int i = 0; i < 5; i++) T.minRes[i] = in->minResForAbort[i];
   T.partial = c->d_partial; T.bar = c->d_bar; T.out = c->h_out;
-  CK(cudaMemsetAsync(c->d_bar, 0, sizeof(unsigned int), c->stream));
-  void* args[] = {&T};
-  CK(cudaLaunchCooperativeKernel((void*)ct_track_kernel, dim3(T.G), dim3(CT_THREADS), args, 0, c->stream));  // co-residency of all CTAs guaranteed
+  if (c->cluster_size == 0) {  // probe once: the largest cluster the device schedules for this kernel (16 needs the non-portable opt-in)
+    c->cluster_size = -1;
+    const char* env = getenv("DMV_CT_GRID");   // A/B switch: DMV_CT_GRID=1 keeps the chip-wide cooperative-grid version
+    if (!(env && atoi(env) != 0) && ct_make_tensor_maps(c) == DMV_OK) {
+      CK(cudaFuncSetAttribute(ct_track_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CTCSmem)));
+      cudaFuncSetAttribute(ct_track_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaGetLastError();
+      for (int nc : {16, 8, 4}) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(nc); cfg.blockDim = dim3(CTC_THREADS); cfg.dynamicSmemBytes = sizeof(CTCSmem); cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, ct_track_cluster_kernel, &cfg) == cudaSuccess && ncl >= 1) { c->cluster_size = nc; break; }
+        cudaGetLastError();
+      }
+    }
+  }
+  if (c->cluster_size > 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(c->cluster_size); cfg.blockDim = dim3(CTC_THREADS); cfg.dynamicSmemBytes = sizeof(CTCSmem); cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = c->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, ct_track_cluster_kernel, T, *c->maps));
+  } else {
+    if (T.G > dev_sms) return set_error(DMV_ERR_INVALID, "%d reference points need %d co-resident CTAs, the device has %d SMs: use dmv_ct_calc_res_gs", maxn, T.G, dev_sms);
+    CK(cudaMemsetAsync(c->d_bar, 0, sizeof(unsigned int), c->stream));
+    void* args[] = {&T};
+    CK(cudaLaunchCooperativeKernel((void*)ct_track_kernel, dim3(T.G), dim3(CT_THREADS), args, 0, c->stream));  // co-residency of all CTAs guaranteed
+  }
   c->launches++;
   CK(cudaStreamSynchronize(c->stream));
   c->staging_busy = false;

@@ -200,7 +200,7 @@ double orc_win_override_new_states(OrcWin* o, const int32_t* newState, int* chan
         nch++;
       }
     }
-    E += r.state_NewEnergy;
+    E += (r.state_NewState == RS_OOB) ? r.state_energy : r.state_NewEnergy;  // OOB exits return the old energy and leave state_NewEnergy alone
   }
   if (changed) *changed = nch;
   if (unfixable) *unfixable = nbad;
