@@ -37,6 +37,7 @@ int dmv_ba_fill_descriptor(dmv_ba* b) {
   // linearisation has been committed, the committed outputs ARE the input states (OOB stays OOB, its energy is returned)
   W.st_in = b->have_committed ? b->d_st_new[c2] : b->d_st_in;
   W.en_in = b->have_committed ? b->d_en_new[c2] : b->d_en_in;
+  W.en_wo_newest_host = b->h_en_newest;
   W.st_new = b->d_st_new[t]; W.en_new = b->d_en_new[t]; W.en_wo = b->d_en_wo[t]; W.cpt = b->d_cpt[t]; W.jpjd = b->d_jpjd[t]; W.pout = b->d_pout[t];
   W.c_st = b->d_st_new[c2]; W.c_jpjd = b->d_jpjd[c2]; W.c_pout = b->d_pout[c2];
   W.step = b->d_step;
@@ -147,6 +148,7 @@ static int ba_allocate(dmv_ba* b, const dmv_ba_config* cfg) {
   std::memset(b->h_up, 0, sizeof(HostUpload));
   b->scratch_floats = std::max((size_t)mp * 8 * MF, npx * 3);
   CK(cudaMallocHost(&b->h_scratch, sizeof(float) * b->scratch_floats));
+  CK(cudaMallocHost(&b->h_en_newest, sizeof(float) * mp));
   for (int f = 0; f < MF; f++) b->slots[f] = f;
   return DMV_OK;
 }
@@ -165,7 +167,7 @@ int dmv_ba_destroy(dmv_ba* b) {
   }
   cudaFree(b->d_step); cudaFree(b->d_resub_sums); cudaFree(b->d_flush);
   cudaFree(b->d_part); cudaFree(b->d_wg); cudaFree(b->d_hdig); cudaFree(b->d_hdi_solve); cudaFree(b->d_bar);
-  cudaFreeHost(b->h_up); cudaFreeHost(b->h_adj); cudaFreeHost(b->h_scratch);
+  cudaFreeHost(b->h_up); cudaFreeHost(b->h_adj); cudaFreeHost(b->h_scratch); cudaFreeHost(b->h_en_newest);
   for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   if (b->nccl_comm) dmv::nccl_destroy(b->nccl_comm);
   cudaFree(b->d_act); cudaFreeHost(b->h_act);
@@ -268,6 +270,7 @@ int dmv_ba_set_points(dmv_ba* b, int npts, const int32_t* host, const float* u, 
   else CK(cudaMemset(b->d_priorF, 0, sizeof(float) * npts));
   b->nres = 0;
   b->hdi_solve_n = 0;
+  b->en_newest_valid = false;
   b->have_tentative = b->have_committed = false;
   return DMV_OK;
 }
@@ -367,6 +370,7 @@ static int enqueue_linearize(dmv_ba* b) {
   HostUpload& U = *b->h_up;
   if (b->timing) CK(cudaEventRecord(b->ev[0], b->stream));
   CK(launch_fused_kernel(U.win, U.it, false, b->stream, &b->bar_count));  // whole linearisation: residuals -> H_top, b_top, [H_sc | b_sc]
+  b->en_newest_valid = true;
   b->launches += 1;
   if (b->timing) CK(cudaEventRecord(b->ev[1], b->stream));
   {
@@ -632,6 +636,7 @@ int dmv_ba_marginalize_points(dmv_ba* b, const dmv_ba_marg_args* a) {
   BAWinDev& W = b->h_up->win;
   W.result = b->d_marg_result;
   W.result_host = nullptr;
+  W.en_wo_newest_host = nullptr;
   W.marg = b->d_marg; W.marg_mask = b->d_marg_mask; W.marg_rtz = b->d_marg_rtz;
   CK(launch_fused_kernel(W, b->h_up->it, true, b->stream, &b->bar_count));
   b->launches += 1;
@@ -710,11 +715,16 @@ int dmv_ba_get_target_energies(dmv_ba* b, int target, float* out, int cap, int* 
   if (!b->have_tentative && !b->have_committed) return set_error(DMV_ERR_STATE, "linearize first");
   CK(cudaSetDevice(b->device));
   const int k = b->have_tentative ? b->tent : 1 - b->tent;
-  int rc = fetch_f(b, b->d_en_wo[k] + (size_t)target * b->mp, b->npts);
-  if (rc != DMV_OK) return rc;
+  const float* src = b->h_scratch;
+  if (target == b->nf - 1 && b->en_newest_valid) {
+    src = b->h_en_newest;   // the kernel streamed these into pinned host memory itself; every launch is followed by a stream synchronisation
+  } else {
+    int rc = fetch_f(b, b->d_en_wo[k] + (size_t)target * b->mp, b->npts);
+    if (rc != DMV_OK) return rc;
+  }
   int c = 0;
   for (int p = 0; p < b->npts && c < cap; p++)
-    if (b->h_st_in[(size_t)target * b->mp + p] != RES_NONE && b->h_scratch[p] >= 0.f) out[c++] = b->h_scratch[p];
+    if (b->h_st_in[(size_t)target * b->mp + p] != RES_NONE && src[p] >= 0.f) out[c++] = src[p];
   *n = c;
   return DMV_OK;
 }

@@ -107,6 +107,7 @@ int dmv_ba_batch_gn_step(dmv_ba_batch* B, const double* const* x, const dmv_ba_s
   for (int i = 0; i < n; i++) {
     dmv_ba* b = B->h[i];
     b->launches += (i == 0);
+    b->en_newest_valid = true;
     int rc = dmv_ba_finish_linearize(b, out ? out + i : nullptr, sums3 ? sums3 + 3 * i : nullptr);
     b->h_up->it.have_x = 0;
     if (rc != DMV_OK) return rc;

@@ -32,9 +32,11 @@ int dmv_ba_bench_device(dmv_ba* b, const double* x, int iters, int flush_l2, flo
     CK(cudaEventRecord(e[3 * i], b->stream));
     CK(launch_fused_kernel(U.win, U.it, false, b->stream, &b->bar_count));
     CK(cudaEventRecord(e[3 * i + 1], b->stream));
-    rc = dmv_ba_enqueue_exchange(b);
-    if (rc != DMV_OK) return rc;
-    CK(cudaEventRecord(e[3 * i + 2], b->stream));
+    if (b->nccl_comm && !b->xchg_on) {  // a separate all-reduce follows the kernel: the step ends behind it
+      rc = dmv_ba_enqueue_exchange(b);
+      if (rc != DMV_OK) return rc;
+      CK(cudaEventRecord(e[3 * i + 2], b->stream));
+    }
     b->launches += 1;
   }
   CK(cudaGetLastError());
@@ -42,8 +44,9 @@ int dmv_ba_bench_device(dmv_ba* b, const double* x, int iters, int flush_l2, flo
   double tot = 0, pk = 0;
   for (int i = 0; i < iters; i++) {
     float a = 0, c = 0;
-    cudaEventElapsedTime(&a, e[3 * i], e[3 * i + 2]);
     cudaEventElapsedTime(&c, e[3 * i], e[3 * i + 1]);
+    if (b->nccl_comm && !b->xchg_on) cudaEventElapsedTime(&a, e[3 * i], e[3 * i + 2]);
+    else a = c;  // the step IS the kernel (the peer exchange, if any, happens inside it)
     tot += a; pk += c;
   }
   for (auto& ev : e) cudaEventDestroy(ev);

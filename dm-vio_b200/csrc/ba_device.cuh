@@ -85,6 +85,7 @@ struct BAWinDev {
   uint8_t* st_new;           // tentative outputs of this linearisation
   float* en_new;
   float* en_wo;
+  float* en_wo_newest_host;  // pinned host mirror of en_wo for target frame nf-1 (setNewFrameEnergyTH's percentile input), or nullptr
   float* cpt;                // 3 planes [k][slot]
   float* jpjd;               // [slot][8]
   float* pout;               // [p][8]: Hdd bd Hcd[4] HdiF bdSum

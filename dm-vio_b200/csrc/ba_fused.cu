@@ -415,7 +415,9 @@ __device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it,
     if (valid && masked) {
       W.st_new[slot] = (uint8_t)newState;
       W.en_new[slot] = newEnergy;
-      W.en_wo[slot] = (st == RES_NONE || !live) ? -1.f : energy;
+      const float ewo = (st == RES_NONE || !live) ? -1.f : energy;
+      W.en_wo[slot] = ewo;
+      if (tc == nf - 1 && W.en_wo_newest_host) W.en_wo_newest_host[p] = ewo;  // zero-copy: the host's percentile needs no D2H call
       const size_t plane = (size_t)MAXF * mp;
       W.cpt[slot] = cKu; W.cpt[plane + slot] = cKv; W.cpt[2 * plane + slot] = new_idepth;
     }
@@ -679,7 +681,9 @@ __device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it,
     if (valid && masked && q == 0) {
       W.st_new[slot] = (uint8_t)newState;
       W.en_new[slot] = newEnergy;
-      W.en_wo[slot] = (st == RES_NONE || !live) ? -1.f : energy;
+      const float ewo = (st == RES_NONE || !live) ? -1.f : energy;
+      W.en_wo[slot] = ewo;
+      if (t == nf - 1 && W.en_wo_newest_host) W.en_wo_newest_host[p] = ewo;  // zero-copy: the host's percentile needs no D2H call
       const size_t plane = (size_t)MAXF * mp;
       W.cpt[slot] = cKu; W.cpt[plane + slot] = cKv; W.cpt[2 * plane + slot] = new_idepth;
     }
@@ -916,14 +920,14 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR
   const bool xch = W.xc.nranks > 1;
   const double* __restrict__ part = W.part;
 
-  // ---------------------------------------------------------------- phase D: H_top / b_top / counters, 8 lanes per result entry
+  // ---------------------------------------------------------------- phase D: H_top / b_top / counters, 16 lanes per result entry
   // item list: [unordered frame pairs a<b: 64 entries each][diagonal blocks: nf x 64][H[.,C]: nf x 32][b: nf x 8][CC 16][bC 4][counters 7]
-  // One pass over the items: (number of 8-lane groups in the grid) ~ (number of items), every lane sums <= 17 chunk partials whose loads
-  // are all in flight together (batches of 8), then a 3-step butterfly.  Fixed order => bit-reproducible.
+  // Usually one pass over the items (16-lane groups in the grid >= items), every lane sums <= 12 chunk partials per segment whose loads
+  // are all in flight together, then a 4-step butterfly.  Fixed order => bit-reproducible.
   const int npair = nf * (nf - 1) / 2;
   const int n_off = npair * 64, n_diag = nf * 64, n_c = nf * 32, n_b = nf * 8;
   const int nitems = n_off + n_diag + n_c + n_b + 16 + 4 + (ACC_MISC - 1);  // the last counter slot is the error flag: written on error only
-  const int grp = tid >> 3, gl = tid & 7, groups_per_cta = nthreads >> 3;
+  const int grp = tid >> 4, gl = tid & 15, groups_per_cta = nthreads >> 4;
   const int nch = W.nchunks;
   for (int pass = 0; pass < (xch ? 2 : 1); pass++) {
     for (int base = vcta * groups_per_cta; base < nitems; base += ncta * groups_per_cta) {  // CTA-uniform trip count (shuffles below)
@@ -965,14 +969,15 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR
         for (int seg = 0; seg < 2; seg++) {
           const int lo = seg ? lo1 : lo0, hi = seg ? hi1 : hi0;
           const double* __restrict__ src = part + (seg ? off1 : off0);
-          for (int c0 = lo + gl; c0 < hi; c0 += 64) {
-            double v[8];
+          for (int c0 = lo + gl; c0 < hi; c0 += 192) {
+            double v[12];
 #pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = (c0 + 8 * u < hi) ? __ldcg(src + (size_t)(c0 + 8 * u) * PART_STRIDE) : 0.0;
+            for (int u = 0; u < 12; u++) v[u] = (c0 + 16 * u < hi) ? __ldcg(src + (size_t)(c0 + 16 * u) * PART_STRIDE) : 0.0;
 #pragma unroll
-            for (int u = 0; u < 8; u++) sum += v[u];
+            for (int u = 0; u < 12; u++) sum += v[u];
           }
         }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 8);
         sum += __shfl_xor_sync(0xffffffffu, sum, 4);
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);

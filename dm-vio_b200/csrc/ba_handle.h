@@ -64,6 +64,8 @@ struct dmv_ba {
   BAAdj* h_adj = nullptr;
   double* h_result[2] = {nullptr, nullptr};
   float* h_scratch = nullptr;  // max(mp*8, w*h*3) floats
+  float* h_en_newest = nullptr; // [mp] en_wo of the residuals targeting the newest frame, written by the kernel itself (zero-copy)
+  bool en_newest_valid = false; // h_en_newest belongs to the most recent linearisation
   size_t scratch_floats = 0;
   // host bookkeeping
   int host_start[MAXF + 1];

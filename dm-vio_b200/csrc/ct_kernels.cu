@@ -213,6 +213,8 @@ struct CTLM {  // the scalar state of trackNewestCoarse, one copy per CTA (share
   float RKi[9], tf[3], affLL[2], cutoff;  // operands of the pending evaluation
   float lambda, rep;
   int lvl, iteration, phase, haveRepeated, iterations, evaluations, done, good, status;
+  double A[64], rhs[8], Lf[64], Df[8], incraw[8];   // the damped 8x8 system of the pending LM step, its LDL^T factors, its solution
+  int need_solve;
 };
 enum { CT_PH_INIT = 0, CT_PH_LM = 1 };
 
@@ -239,44 +241,9 @@ __device__ __forceinline__ void ct_se3_exp_mul(const double xi[6], const double 
     to[i] = E[i * 3] * t[0] + E[i * 3 + 1] * t[1] + E[i * 3 + 2] * t[2] + et[i];
   }
 }
-// Hl.ldlt().solve(-b) for the 8x8 system (L639-665), plain LDL^T fully unrolled so that everything stays in registers.  A parameter
-// that is not optimised (setting_affineOptModeA/B < 0: the reference solves the 6x6 / 7x7 sub-system) is padded with an identity
-// row/column and a zero right-hand side: the extra terms are exact zeros, the other components come out bit-identical.
-__device__ __forceinline__ void ct_ldlt_solve8(const double* A, const double* b, double* x) {
-  double L[8][8], D[8], y[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    double dj = A[j * 8 + j];
-#pragma unroll
-    for (int k = 0; k < 8; k++) if (k < j) dj -= L[j][k] * L[j][k] * D[k];
-    D[j] = dj;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      if (i > j) {
-        double sm = A[i * 8 + j];
-#pragma unroll
-        for (int k = 0; k < 8; k++) if (k < j) sm -= L[i][k] * L[j][k] * D[k];
-        L[i][j] = dj != 0.0 ? sm / dj : 0.0;
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    double sm = b[i];
-#pragma unroll
-    for (int k = 0; k < 8; k++) if (k < i) sm -= L[i][k] * y[k];
-    y[i] = sm;
-  }
-#pragma unroll
-  for (int i = 0; i < 8; i++) y[i] = D[i] != 0.0 ? y[i] / D[i] : 0.0;
-#pragma unroll
-  for (int i = 7; i >= 0; i--) {
-    double sm = y[i];
-#pragma unroll
-    for (int k = 0; k < 8; k++) if (k > i) sm -= L[k][i] * x[k];
-    x[i] = sm;
-  }
-}
+// Hl.ldlt().solve(-b) for the 8x8 system (L639-665): plain LDL^T (ct_factor_warp / ct_propose_post below).  A parameter that is not
+// optimised (setting_affineOptModeA/B < 0: the reference solves the 6x6 / 7x7 sub-system) is padded with an identity row/column and a zero
+// right-hand side: the extra terms are exact zeros, the other components come out bit-identical.
 // operands of calcRes for a pose (CoarseTracker.cpp:L377-379): RKi = R.cast<float>() * Ki[lvl], t.cast<float>(), affLL.cast<float>()
 __device__ __forceinline__ void ct_request(const CTTrack& T, CTLM& S, const double R[9], const double t[3], double a, double b) {
   float Rf[9];
@@ -322,13 +289,14 @@ __device__ void ct_begin_level(const CTTrack& T, CTLM& S) {
   S.phase = CT_PH_INIT;
   ct_request(T, S, S.R, S.t, S.a, S.b);
 }
-// one LM trial step from the current linearisation (L605-683)
-__device__ void ct_propose(const CTTrack& T, CTLM& S) {
+// one LM trial step from the current linearisation (L605-683), in three parts: lane 0 sets up the damped system, the WARP factorises it
+// (row i of L in lane i: the 8^3/3 multiply-adds and the 28 divisions of the scalar version collapse to 8 dependent column steps), lane 0
+// substitutes and updates the pose.  Every element sees the same operations in the same order as the scalar LDL^T: bit-identical result.
+__device__ void ct_propose_pre(const CTTrack& T, CTLM& S) {
   S.iterations++;
   const double* Hc = S.H[S.cur];
   const double* bc = S.bb[S.cur];
   const bool fixA = T.affModeA < 0, fixB = T.affModeB < 0;
-  double A[64], rhs[8], inc[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const bool fi = (i == 6 && fixA) || (i == 7 && fixB);
@@ -337,11 +305,58 @@ __device__ void ct_propose(const CTTrack& T, CTLM& S) {
       const bool fj = (j == 6 && fixA) || (j == 7 && fixB);
       double vv = Hc[i * 8 + j];
       if (i == j) vv *= (1 + S.lambda);
-      A[i * 8 + j] = (fi || fj) ? ((i == j) ? 1.0 : 0.0) : vv;
+      S.A[i * 8 + j] = (fi || fj) ? ((i == j) ? 1.0 : 0.0) : vv;
     }
-    rhs[i] = fi ? 0.0 : -bc[i];
+    S.rhs[i] = fi ? 0.0 : -bc[i];
   }
-  ct_ldlt_solve8(A, rhs, inc);
+  S.need_solve = 1;
+}
+// LDL^T of S.A by one warp (all 32 lanes execute; lane i & 7 mirrors row i, lanes 0..7 write)
+__device__ __forceinline__ void ct_factor_warp(CTLM& S) {
+  const int lane = threadIdx.x & 31, i = lane & 7;
+  double Ai[8], Li[8], D[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { Ai[k] = S.A[i * 8 + k]; Li[k] = 0.0; }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    double sm = Ai[j];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k < j) {
+        const double Ljk = __shfl_sync(0xffffffffu, Li[k], j);   // row j's entry (lane j's own row when i == j)
+        sm -= Li[k] * Ljk * D[k];
+      }
+    const double dj = __shfl_sync(0xffffffffu, sm, j);
+    D[j] = dj;
+    if (i > j) Li[j] = dj != 0.0 ? sm / dj : 0.0;
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) S.Lf[i * 8 + k] = Li[k];
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) S.Df[k] = D[k];
+    }
+  }
+}
+__device__ void ct_propose_post(const CTTrack& T, CTLM& S) {
+  double y[8], inc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    double sm = S.rhs[i];
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < i) sm -= S.Lf[i * 8 + k] * y[k];
+    y[i] = sm;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) y[i] = S.Df[i] != 0.0 ? y[i] / S.Df[i] : 0.0;
+#pragma unroll
+  for (int i = 7; i >= 0; i--) {
+    double sm = y[i];
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k > i) sm -= S.Lf[k * 8 + i] * inc[k];
+    inc[i] = sm;
+  }
   float extrapFac = 1;
   const float lambdaExtrapolationLimit = 0.001f;
   if (S.lambda < lambdaExtrapolationLimit) extrapFac = sqrtf(sqrtf(lambdaExtrapolationLimit / S.lambda));
@@ -365,8 +380,11 @@ __device__ void ct_propose(const CTTrack& T, CTLM& S) {
 #pragma unroll
   for (int i = 0; i < 8; i++) S.inc[i] = inc[i];
   S.phase = CT_PH_LM;
+  S.need_solve = 0;
   ct_request(T, S, S.Rn, S.tn, S.an, S.bn);
 }
+// the scalar state machine step, executed by warp 0 of every CTA
+__device__ __forceinline__ void ct_advance_warp(const CTTrack& T, CTLM& S);
 __device__ void ct_end_level(const CTTrack& T, CTLM& S) {  // L722-745
   const int lvl = S.lvl;
   const double* resOld = S.res[S.cur];
@@ -401,7 +419,7 @@ __device__ void ct_advance(const CTTrack& T, CTLM& S) {
     S.lambda = 0.01f;
     S.iteration = 0;
     if (S.iteration >= maxIterations[S.lvl]) { ct_end_level(T, S); return; }
-    ct_propose(T, S);
+    ct_propose_pre(T, S);
     return;
   }
   // CT_PH_LM: accept / reject (L686-716)
@@ -422,7 +440,17 @@ __device__ void ct_advance(const CTTrack& T, CTLM& S) {
   incNorm = sqrt(incNorm);
   S.iteration++;
   if (!(incNorm > 1e-3) || S.iteration >= maxIterations[S.lvl]) { ct_end_level(T, S); return; }
-  ct_propose(T, S);
+  ct_propose_pre(T, S);
+}
+__device__ __forceinline__ void ct_advance_warp(const CTTrack& T, CTLM& S) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) ct_advance(T, S);
+  __syncwarp();
+  if (S.need_solve) {  // warp-uniform (shared memory)
+    ct_factor_warp(S);
+    __syncwarp();
+    if (lane == 0) ct_propose_post(T, S);
+  }
 }
 
 __global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_constant__ CTTrack T) {
@@ -440,7 +468,7 @@ __global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_const
     S.a = T.a0; S.b = T.b0;
     for (int i = 0; i < 5; i++) S.lastResiduals[i] = __longlong_as_double(0x7ff8000000000000ll);  // NAN
     for (int i = 0; i < 3; i++) S.flow[i] = 1000;
-    S.haveRepeated = 0; S.iterations = 0; S.evaluations = 0; S.done = 0; S.good = 0; S.status = 0; S.cur = 0;
+    S.haveRepeated = 0; S.iterations = 0; S.evaluations = 0; S.done = 0; S.good = 0; S.status = 0; S.cur = 0; S.need_solve = 0;
     S.lvl = T.coarsest;
     ct_begin_level(T, S);
   }
@@ -484,7 +512,7 @@ __global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_const
     __syncthreads();
     ct_finish_parallel(s_sum, S.res[S.cur ^ 1], S.H[S.cur ^ 1], S.bb[S.cur ^ 1], tid);
     __syncthreads();
-    if (tid == 0) ct_advance(T, S);
+    if (tid < 32) ct_advance_warp(T, S);
     __syncthreads();
   }
   if (blockIdx.x == 0 && tid == 0) {
@@ -619,7 +647,7 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) ct_track_cluster_kernel(const 
     S.a = T.a0; S.b = T.b0;
     for (int i = 0; i < 5; i++) S.lastResiduals[i] = __longlong_as_double(0x7ff8000000000000ll);  // NAN
     for (int i = 0; i < 3; i++) S.flow[i] = 1000;
-    S.haveRepeated = 0; S.iterations = 0; S.evaluations = 0; S.done = 0; S.good = 0; S.status = 0; S.cur = 0;
+    S.haveRepeated = 0; S.iterations = 0; S.evaluations = 0; S.done = 0; S.good = 0; S.status = 0; S.cur = 0; S.need_solve = 0;
     S.lvl = T.coarsest;
     ct_begin_level(T, S);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ctc_smem_u32(&M.mbar)) : "memory");
@@ -667,9 +695,11 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) ct_track_cluster_kernel(const 
     for (int k = 0; k < 64; k++) v[k] = 0.f;
     const int stride = (int)NC * CTC_THREADS;
     if (fits) {
+#pragma unroll 2
       for (int i = (int)rank * CTC_THREADS + tid; i < P.n; i += stride)
         ctc_eval_accumulate<true>(P, i, T.u[l], T.v[l], T.id[l], T.col[l], T.img[l], reinterpret_cast<const float4*>(M.plane), v);
     } else {
+#pragma unroll 2
       for (int i = (int)rank * CTC_THREADS + tid; i < P.n; i += stride)
         ctc_eval_accumulate<false>(P, i, T.u[l], T.v[l], T.id[l], T.col[l], T.img[l], nullptr, v);
     }
@@ -711,7 +741,7 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) ct_track_cluster_kernel(const 
     __syncthreads();
     ct_finish_parallel(M.s_sum, S.res[S.cur ^ 1], S.H[S.cur ^ 1], S.bb[S.cur ^ 1], tid);
     __syncthreads();
-    if (tid == 0) ct_advance(T, S);
+    if (tid < 32) ct_advance_warp(T, S);
     __syncthreads();
   }
   ctc_cluster_sync();  // nobody leaves while a peer may still write into its shared memory

@@ -59,19 +59,18 @@ def test_marginalize_points_parity(capi, orc, synth, cfg, frac, P):
     in_set = np.isin(W["res_point"], pts)
     assert not g["isLinearized"][~in_set].any()
     assert np.all(g["rtz"][g["isLinearized"] == 0] == 0)
-    if len(mism) == 0:
-        np.testing.assert_array_equal(g["ngood"], o["ngood"])
-        assert g["resInM"] == o["resInM"]
+    assert len(mism) == 0, "a threshold tie on a seeded case: the system comparison below must never be skipped (pick another seed)"
+    np.testing.assert_array_equal(g["ngood"], o["ngood"])
+    assert g["resInM"] == o["resInM"]
     # ---- res_toZeroF per residual
     scale = np.abs(o["rtz"][both]).max()
     err = np.abs(g["rtz"][both] - o["rtz"][both])
     assert err.max() <= 2e-3 * scale + 1e-4, err.max()
     assert np.median(err) <= 2e-5 * scale
     # ---- the marginalisation system
-    if len(mism) == 0:
-        assert rel(g["M"], o["M"]) < 1e-5 and rel(g["Msc"], o["Msc"]) < 1e-5
-        assert rel(g["H"], o["H"]) < 1e-5
-        assert rel(g["Mb"], o["Mb"]) < 2e-4 and rel(g["Mbsc"], o["Mbsc"]) < 2e-4 and rel(g["b"], o["b"]) < 2e-4
+    assert rel(g["M"], o["M"]) < 1e-5 and rel(g["Msc"], o["Msc"]) < 1e-5
+    assert rel(g["H"], o["H"]) < 1e-5
+    assert rel(g["Mb"], o["Mb"]) < 2e-4 and rel(g["Mbsc"], o["Mbsc"]) < 2e-4 and rel(g["b"], o["b"]) < 2e-4
     assert np.allclose(g["M"], g["M"].T) and np.allclose(g["Msc"], g["Msc"].T, rtol=1e-12, atol=0)
     ba.close()
 

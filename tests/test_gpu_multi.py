@@ -57,6 +57,14 @@ def _worker(rank, world, port, cfg, mode, q):
     ba.apply_res()
     a = ba.accumulate()
     out.append((r["energy"], r["n_in"], a["HA"].copy(), a["bA"].copy(), a["Hsc"].copy(), a["bsc"].copy()))
+    # sharded point marginalisation: every rank marginalises ITS share of the flagged points, the partial M / Msc are summed in the launch
+    from oracle import orc as _orc
+    ow = _orc.Window(W)
+    flagged = np.arange(0, len(W["host"]), 3)
+    keep = np.nonzero((np.arange(len(W["host"])) % world) == rank)[0]            # dmvio_b200.sharding.shard_points
+    local = np.nonzero(np.isin(keep, flagged))[0].astype(np.int32)
+    g = ba.marginalize_points(local, ow.adHTdeltaF(), ow.calib()["cDeltaF"])
+    marg = (g["M"].copy(), g["Msc"].copy(), g["Mb"].copy(), g["Mbsc"].copy(), g["resInM"])
     # a few fused GN steps: exercises the parity double-buffering of the inbox
     HL, bL = hm.prior_system(W)
     ba.backup_points()
@@ -67,7 +75,7 @@ def _worker(rank, world, port, cfg, mode, q):
         a = ba.accumulate()
         ba.backup_points()
     out.append((r["energy"], r["n_in"], a["HA"].copy(), a["bA"].copy(), a["Hsc"].copy(), a["bsc"].copy()))
-    q.put((rank, out + [states]))
+    q.put((rank, out + [states, marg]))
     dist.barrier()
     ba.close()
     dist.destroy_process_group()
@@ -108,6 +116,14 @@ def test_sharded_exchange(orc, synth, world, mode):
     assert unfixable == 0
     ow.apply_res()
     a = ow.accumulate(1)
+    # sharded marginalisation: identical on every rank, equal to the unsharded oracle's marginalizePointsF of the same points
+    for rk in range(1, world):
+        for x, y in zip(res[0][3][:4], res[rk][3][:4]):
+            np.testing.assert_array_equal(x, y)
+    om = orc.Window(W).marginalize(np.arange(0, len(W["host"]), 3).astype(np.int32), precision=1)
+    M, Msc, Mb, Mbsc, nM = res[0][3]
+    assert nM == om["resInM"]
+    assert rel(M, om["M"]) < 1e-5 and rel(Msc, om["Msc"]) < 1e-5 and rel(Mb, om["Mb"]) < 2e-4 and rel(Mbsc, om["Mbsc"]) < 2e-4
     e0, n0, HA, bA, Hsc, bsc = res[0][0]
     assert abs(e0 - E) <= 2e-5 * abs(E)
     assert rel(HA, a["HA"]) < 1e-5 and rel(Hsc, a["Hsc"]) < 1e-5
