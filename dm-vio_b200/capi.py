@@ -113,14 +113,14 @@ class CTConfig(C.Structure):
 # every symbol declared in include/dmvio_b200.h (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "dmv_last_error", "dmv_version", "dmv_device_count",
-    "dmv_ba_create", "dmv_ba_destroy", "dmv_ba_set_params", "dmv_ba_default_params", "dmv_ba_upload_frame", "dmv_ba_upload_image",
+    "dmv_ba_create", "dmv_ba_destroy", "dmv_ba_set_params", "dmv_ba_default_params", "dmv_ba_upload_frame", "dmv_ba_upload_image", "dmv_ba_adopt_frame",
     "dmv_ba_set_window", "dmv_ba_set_points", "dmv_ba_set_residuals", "dmv_ba_set_adjoints", "dmv_ba_set_state", "dmv_ba_linearize",
     "dmv_ba_get_residual_outputs", "dmv_ba_get_target_energies", "dmv_ba_apply_res", "dmv_ba_accumulate", "dmv_ba_get_point_outputs", "dmv_ba_get_solve_HdiF",
     "dmv_ba_resubstitute", "dmv_ba_backup_points", "dmv_ba_restore_points", "dmv_ba_get_idepth", "dmv_ba_gn_step", "dmv_nccl_unique_id",
     "dmv_ba_comm_init", "dmv_ba_activate_points", "dmv_ba_marginalize_points", "dmv_ba_drop_residuals", "dmv_ba_reset_oob", "dmv_ba_p2p_export", "dmv_ba_p2p_import", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e",
     "dmv_ba_batch_create", "dmv_ba_batch_destroy", "dmv_ba_batch_gn_step", "dmv_ba_batch_set_timing", "dmv_ba_batch_last_kernel_ms", "dmv_ba_batch_bench",
     "dmv_ct_create", "dmv_ct_destroy", "dmv_ct_set_K", "dmv_ct_set_ref", "dmv_ct_make_coarse_depth", "dmv_ct_get_ref", "dmv_ct_upload_new", "dmv_ct_upload_new_image", "dmv_ct_set_huber",
-    "dmv_ct_calc_res_gs", "dmv_ct_track", "dmv_ip_default_settings", "dmv_ct_init_points", "dmv_ct_trace_points", "dmv_ct_set_timing", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count",
+    "dmv_ct_calc_res_gs", "dmv_ct_track", "dmv_ip_default_settings", "dmv_ct_init_points", "dmv_ct_trace_points", "dmv_ct_trace_points_multi", "dmv_ct_set_timing", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count",
 ]
 
 
@@ -169,6 +169,7 @@ def lib():
         L.dmv_ba_bench_e2e.argtypes = [vp, vp, C.POINTER(BAState), C.c_int, C.POINTER(C.c_double)]
         L.dmv_ba_io_bytes.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         L.dmv_ba_get_solve_HdiF.argtypes = [vp, f32p]
+        L.dmv_ba_adopt_frame.argtypes = [vp, C.c_int, vp]
         L.dmv_ba_batch_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
         L.dmv_ba_batch_destroy.argtypes = [vp]
         L.dmv_ba_batch_gn_step.argtypes = [vp, vp, vp, vp, vp]
@@ -187,6 +188,7 @@ def lib():
         L.dmv_ct_calc_res_gs.argtypes = [vp, C.c_int, f32p, f32p, f32p, C.c_float, C.c_float, C.c_int, f64p, f64p, f64p, C.POINTER(C.c_int)]
         L.dmv_ct_init_points.argtypes = [vp, C.c_int, i32p, i32p, f32p, f32p, f32p, f32p, i32p]
         L.dmv_ct_trace_points.argtypes = [vp, C.POINTER(IPPoints), f32p, f32p, f32p, vp]
+        L.dmv_ct_trace_points_multi.argtypes = [vp, C.c_int, vp, f32p, vp]
         L.dmv_ct_set_timing.argtypes = [vp, C.c_int]
         L.dmv_ct_last_timing.argtypes = [vp, f32p]
         L.dmv_ct_kernel_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
@@ -239,6 +241,10 @@ class BA:
 
     def upload_image(self, slot, img):
         check(self.L.dmv_ba_upload_image(self.h, slot, _c(img, np.float32).reshape(-1)))
+
+    def adopt_frame(self, slot, ct):
+        """level-0 plane of the frame resident in the coarse-tracker handle `ct` (capi.CT), device to device"""
+        check(self.L.dmv_ba_adopt_frame(self.h, slot, ct.h))
 
     def set_window(self, nf, slots=None):
         s = _c(slots, np.int32)
@@ -508,6 +514,28 @@ class CT:
         Q = dict(P)
         Q.update(out)
         return Q
+
+    def trace_points_multi(self, sets):
+        """sets = [(P, KRKi, Kt, aff), ...]: the immature points of several host keyframes in ONE launch (dmv_ct_trace_points_multi);
+        returns the list of updated dicts."""
+        ns = len(sets)
+        arr = (IPPoints * ns)()
+        keeps, outs = [], []
+        tab = np.zeros((ns, 14), np.float32)
+        for k, (P, KRKi, Kt, aff) in enumerate(sets):
+            keep = {q: _c(P[q], np.float32) for q in ("u", "v", "color", "weights", "gradH", "energyTH")}
+            out = {"idepth_min": np.array(P["idepth_min"], np.float32, copy=True), "idepth_max": np.array(P["idepth_max"], np.float32, copy=True),
+                   "quality": np.array(P["quality"], np.float32, copy=True), "status": np.array(P["status"], np.int32, copy=True),
+                   "lastTraceUV": np.array(P["lastTraceUV"], np.float32, copy=True), "lastTracePixelInterval": np.array(P["lastTracePixelInterval"], np.float32, copy=True)}
+            arr[k] = IPPoints(len(P["u"]), *[a.ctypes.data for a in (keep["u"], keep["v"], keep["color"], keep["weights"], keep["gradH"], keep["energyTH"], out["idepth_min"],
+                                                                      out["idepth_max"], out["quality"], out["status"], out["lastTraceUV"], out["lastTracePixelInterval"])])
+            tab[k, :9] = np.asarray(KRKi, np.float32).reshape(-1); tab[k, 9:12] = Kt; tab[k, 12:14] = aff
+            keeps.append(keep); outs.append(out)
+        check(self.L.dmv_ct_trace_points_multi(self.h, ns, C.addressof(arr), tab.reshape(-1), None))
+        res = []
+        for (P, _, _, _), out in zip(sets, outs):
+            Q = dict(P); Q.update(out); res.append(Q)
+        return res
 
     def set_timing(self, enable=True):
         check(self.L.dmv_ct_set_timing(self.h, int(enable)))

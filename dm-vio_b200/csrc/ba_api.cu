@@ -213,6 +213,27 @@ int dmv_ba_upload_image(dmv_ba* b, int slot, const float* image) {
   return DMV_OK;
 }
 
+// FrameHessian::dI of a frame that is ALREADY resident in a coarse-tracker handle (uploaded once when the frame arrived, pyramid built on
+// the device): the BA slot takes a device-to-device copy of its level-0 plane (same float4 texel layout) — no second H2D, no second
+// makeImages.  Stream-ordered behind whatever the tracker handle still has in flight.
+extern "C" int dmv_ct_level0_plane(dmv_ct* c, const void** plane, int* w, int* h, int* device, cudaStream_t* stream);
+int dmv_ba_adopt_frame(dmv_ba* b, int slot, dmv_ct* ct) {
+  if (!b || !ct || slot < 0 || slot >= b->cfg.max_frames) return set_error(DMV_ERR_INVALID, "bad slot/handle");
+  const void* plane = nullptr;
+  int w = 0, h = 0, dev = 0;
+  cudaStream_t cs = nullptr;
+  int rc = dmv_ct_level0_plane(ct, &plane, &w, &h, &dev, &cs);
+  if (rc != DMV_OK) return rc;
+  if (w != b->cfg.w || h != b->cfg.h) return set_error(DMV_ERR_INVALID, "image size mismatch (%dx%d vs %dx%d)", w, h, b->cfg.w, b->cfg.h);
+  if (dev != b->device) return set_error(DMV_ERR_INVALID, "the tracker handle lives on device %d, the BA handle on %d", dev, b->device);
+  CK(cudaSetDevice(b->device));
+  CK(cudaEventRecord(b->ev[0], cs));                 // the tracker's upload + pyramid kernels
+  CK(cudaStreamWaitEvent(b->stream, b->ev[0], 0));
+  CK(cudaMemcpyAsync(b->d_img[slot], plane, sizeof(float4) * (size_t)w * h, cudaMemcpyDeviceToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return DMV_OK;
+}
+
 int dmv_ba_set_window(dmv_ba* b, int nf, const int* slots) {
   if (!b || nf < 2 || nf > b->cfg.max_frames) return set_error(DMV_ERR_INVALID, "nf out of range");
   for (int f = 0; f < nf; f++) {

@@ -213,52 +213,18 @@ struct CTLM {  // the scalar state of trackNewestCoarse, one copy per CTA (share
   float RKi[9], tf[3], affLL[2], cutoff;  // operands of the pending evaluation
   float lambda, rep;
   int lvl, iteration, phase, haveRepeated, iterations, evaluations, done, good, status;
-  double A[64], rhs[8], Lf[64], Df[8], incraw[8];   // the damped 8x8 system of the pending LM step, its LDL^T factors, its solution
-  int need_solve;
+  double A[64], rhs[8], Lf[64], Df[8], incs[8], EV[18];   // the damped 8x8 system of the pending LM step, its LDL^T factors, its solution
+  int need_solve, need_request;   // need_request: 1 = evaluate at (R, t, a, b), 2 = at the candidate (Rn, tn, an, bn) = exp(incs) * (R, t)
 };
 enum { CT_PH_INIT = 0, CT_PH_LM = 1 };
 
-__device__ __forceinline__ void ct_se3_exp_mul(const double xi[6], const double R[9], const double t[3], double Ro[9], double to[3]) {
-  // SE3::exp(xi) * (R,t)   (Sophus: tangent = (translation, rotation), left increment)
-  const double wx = xi[3], wy = xi[4], wz = xi[5];
-  const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
-  const double W[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
-  double W2[9];
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) W2[i * 3 + j] = W[i * 3] * W[j] + W[i * 3 + 1] * W[3 + j] + W[i * 3 + 2] * W[6 + j];
-  double ca, cb, cc;
-  if (th < 1e-8) { ca = 1.0 - th2 / 6.0; cb = 0.5 - th2 / 24.0; cc = 1.0 / 6.0 - th2 / 120.0; }
-  else { ca = sin(th) / th; cb = (1.0 - cos(th)) / th2; cc = (th - sin(th)) / (th2 * th); }
-  double E[9], V[9], et[3];
-  for (int i = 0; i < 9; i++) {
-    const double I = (i % 4 == 0) ? 1.0 : 0.0;
-    E[i] = I + ca * W[i] + cb * W2[i];
-    V[i] = I + cb * W[i] + cc * W2[i];
-  }
-  for (int i = 0; i < 3; i++) et[i] = V[i * 3] * xi[0] + V[i * 3 + 1] * xi[1] + V[i * 3 + 2] * xi[2];
-  for (int i = 0; i < 3; i++) {
-    for (int j = 0; j < 3; j++) Ro[i * 3 + j] = E[i * 3] * R[j] + E[i * 3 + 1] * R[3 + j] + E[i * 3 + 2] * R[6 + j];
-    to[i] = E[i * 3] * t[0] + E[i * 3 + 1] * t[1] + E[i * 3 + 2] * t[2] + et[i];
-  }
-}
 // Hl.ldlt().solve(-b) for the 8x8 system (L639-665): plain LDL^T (ct_factor_warp / ct_propose_post below).  A parameter that is not
 // optimised (setting_affineOptModeA/B < 0: the reference solves the 6x6 / 7x7 sub-system) is padded with an identity row/column and a zero
 // right-hand side: the extra terms are exact zeros, the other components come out bit-identical.
 // operands of calcRes for a pose (CoarseTracker.cpp:L377-379): RKi = R.cast<float>() * Ki[lvl], t.cast<float>(), affLL.cast<float>()
 __device__ __forceinline__ void ct_request(const CTTrack& T, CTLM& S, const double R[9], const double t[3], double a, double b) {
-  float Rf[9];
-  for (int i = 0; i < 9; i++) Rf[i] = (float)R[i];
-  const float* Ki = T.Ki[S.lvl];
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) S.RKi[i * 3 + j] = Rf[i * 3] * Ki[j] + Rf[i * 3 + 1] * Ki[3 + j] + Rf[i * 3 + 2] * Ki[6 + j];
-  for (int i = 0; i < 3; i++) S.tf[i] = (float)t[i];
-  float eF = T.ref_exposure, eT = T.new_exposure;  // AffLight::fromToVecExposure (util/NumType.h:L174-186)
-  if (eF == 0 || eT == 0) eT = eF = 1;
-  const double aa = exp(a - T.ref_a) * eT / eF;
-  S.affLL[0] = (float)aa;
-  S.affLL[1] = (float)(b - aa * T.ref_b);
-  S.cutoff = T.cutoffTH * S.rep;
-  S.evaluations++;
+  (void)T; (void)R; (void)t; (void)a; (void)b;
+  S.need_request = 1;   // evaluate at the current pose: the warp forms the operands (ct_pose_request_warp)
 }
 // Vec6 of calcRes (L508-516) and H, b of calcGSSSE (L341-355) from the 53 folded sums, one output per thread (tid < 78)
 __device__ __forceinline__ void ct_finish_parallel(const double* o, double* res6, double* H, double* b, int tid) {
@@ -292,24 +258,27 @@ __device__ void ct_begin_level(const CTTrack& T, CTLM& S) {
 // one LM trial step from the current linearisation (L605-683), in three parts: lane 0 sets up the damped system, the WARP factorises it
 // (row i of L in lane i: the 8^3/3 multiply-adds and the 28 divisions of the scalar version collapse to 8 dependent column steps), lane 0
 // substitutes and updates the pose.  Every element sees the same operations in the same order as the scalar LDL^T: bit-identical result.
-__device__ void ct_propose_pre(const CTTrack& T, CTLM& S) {
+__device__ void ct_propose_pre(const CTTrack& T, CTLM& S) {  // lane 0: bookkeeping only; the damped system is built by the warp (ct_build_system_warp)
   S.iterations++;
+  S.need_solve = 1;
+}
+__device__ __forceinline__ void ct_build_system_warp(const CTTrack& T, CTLM& S) {
+  const int lane = threadIdx.x & 31;
   const double* Hc = S.H[S.cur];
   const double* bc = S.bb[S.cur];
   const bool fixA = T.affModeA < 0, fixB = T.affModeB < 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const bool fi = (i == 6 && fixA) || (i == 7 && fixB);
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const bool fj = (j == 6 && fixA) || (j == 7 && fixB);
-      double vv = Hc[i * 8 + j];
-      if (i == j) vv *= (1 + S.lambda);
-      S.A[i * 8 + j] = (fi || fj) ? ((i == j) ? 1.0 : 0.0) : vv;
-    }
-    S.rhs[i] = fi ? 0.0 : -bc[i];
+  for (int e = lane; e < 64; e += 32) {
+    const int i = e >> 3, j = e & 7;
+    const bool fi = (i == 6 && fixA) || (i == 7 && fixB), fj = (j == 6 && fixA) || (j == 7 && fixB);
+    double vv = Hc[e];
+    if (i == j) vv *= (1 + S.lambda);
+    S.A[e] = (fi || fj) ? ((i == j) ? 1.0 : 0.0) : vv;
   }
-  S.need_solve = 1;
+  if (lane < 8) {
+    const bool fi = (lane == 6 && fixA) || (lane == 7 && fixB);
+    S.rhs[lane] = fi ? 0.0 : -bc[lane];
+  }
 }
 // LDL^T of S.A by one warp (all 32 lanes execute; lane i & 7 mirrors row i, lanes 0..7 write)
 __device__ __forceinline__ void ct_factor_warp(CTLM& S) {
@@ -374,14 +343,64 @@ __device__ void ct_propose_post(const CTTrack& T, CTLM& S) {
 #pragma unroll
     for (int i = 0; i < 8; i++) incScaled[i] = 0;
   }
-  ct_se3_exp_mul(incScaled, S.R, S.t, S.Rn, S.tn);
+#pragma unroll
+  for (int i = 0; i < 8; i++) { S.incs[i] = incScaled[i]; S.inc[i] = inc[i]; }
   S.an = S.a + incScaled[6];
   S.bn = S.b + incScaled[7];
-#pragma unroll
-  for (int i = 0; i < 8; i++) S.inc[i] = inc[i];
   S.phase = CT_PH_LM;
   S.need_solve = 0;
-  ct_request(T, S, S.Rn, S.tn, S.an, S.bn);
+  S.need_request = 2;   // evaluate at the candidate exp(incs) * (R, t)
+}
+// SE3::exp(incs) * (R, t) -> (Rn, tn) and the operands of the next calcRes, spread over the lanes of warp 0: every output element is formed
+// by exactly the expression of the scalar code (ct_se3_exp_mul / ct_request), only by a different lane.
+__device__ __forceinline__ void ct_pose_request_warp(const CTTrack& T, CTLM& S, const bool from_candidate) {
+  const int lane = threadIdx.x & 31;
+  if (from_candidate) {
+    const double* xi = S.incs;
+    const double wx = xi[3], wy = xi[4], wz = xi[5];
+    const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
+    double ca, cb, cc;
+    if (th < 1e-8) { ca = 1.0 - th2 / 6.0; cb = 0.5 - th2 / 24.0; cc = 1.0 / 6.0 - th2 / 120.0; }
+    else { double sn, cs; sincos(th, &sn, &cs); ca = sn / th; cb = (1.0 - cs) / th2; cc = (th - sn) / (th2 * th); }
+    const double W[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+    if (lane < 18) {  // lanes 0..8: E = I + ca W + cb W^2, lanes 9..17: V = I + cb W + cc W^2
+      const int e = lane % 9, i = e / 3, j = e - 3 * i;
+      const double w2 = W[i * 3] * W[j] + W[i * 3 + 1] * W[3 + j] + W[i * 3 + 2] * W[6 + j];
+      const double I = (e % 4 == 0) ? 1.0 : 0.0;
+      S.EV[lane] = (lane < 9) ? I + ca * W[e] + cb * w2 : I + cb * W[e] + cc * w2;
+    }
+    __syncwarp();
+    const double* E = S.EV;
+    const double* V = S.EV + 9;
+    if (lane < 9) {
+      const int i = lane / 3, j = lane - 3 * i;
+      S.Rn[lane] = E[i * 3] * S.R[j] + E[i * 3 + 1] * S.R[3 + j] + E[i * 3 + 2] * S.R[6 + j];
+    } else if (lane < 12) {
+      const int i = lane - 9;
+      const double et = V[i * 3] * xi[0] + V[i * 3 + 1] * xi[1] + V[i * 3 + 2] * xi[2];
+      S.tn[i] = E[i * 3] * S.t[0] + E[i * 3 + 1] * S.t[1] + E[i * 3 + 2] * S.t[2] + et;
+    }
+    __syncwarp();
+  }
+  // operands of calcRes (CoarseTracker.cpp:L377-379): RKi = R.cast<float>() * Ki[lvl], t.cast<float>(), affLL.cast<float>()
+  const double* R = from_candidate ? S.Rn : S.R;
+  const double* t = from_candidate ? S.tn : S.t;
+  const double a = from_candidate ? S.an : S.a, b = from_candidate ? S.bn : S.b;
+  if (lane < 9) {
+    const int i = lane / 3, j = lane - 3 * i;
+    const float* Ki = T.Ki[S.lvl];
+    S.RKi[lane] = (float)R[i * 3] * Ki[j] + (float)R[i * 3 + 1] * Ki[3 + j] + (float)R[i * 3 + 2] * Ki[6 + j];
+  } else if (lane < 12) {
+    S.tf[lane - 9] = (float)t[lane - 9];
+  } else if (lane == 12) {
+    float eF = T.ref_exposure, eT = T.new_exposure;  // AffLight::fromToVecExposure (util/NumType.h:L174-186)
+    if (eF == 0 || eT == 0) eT = eF = 1;
+    const double aa = exp(a - T.ref_a) * eT / eF;
+    S.affLL[0] = (float)aa;
+    S.affLL[1] = (float)(b - aa * T.ref_b);
+    S.cutoff = T.cutoffTH * S.rep;
+    S.evaluations++;
+  }
 }
 // the scalar state machine step, executed by warp 0 of every CTA
 __device__ __forceinline__ void ct_advance_warp(const CTTrack& T, CTLM& S);
@@ -444,13 +463,17 @@ __device__ void ct_advance(const CTTrack& T, CTLM& S) {
 }
 __device__ __forceinline__ void ct_advance_warp(const CTTrack& T, CTLM& S) {
   const int lane = threadIdx.x & 31;
-  if (lane == 0) ct_advance(T, S);
+  if (lane == 0) { S.need_request = 0; ct_advance(T, S); }
   __syncwarp();
   if (S.need_solve) {  // warp-uniform (shared memory)
+    ct_build_system_warp(T, S);
+    __syncwarp();
     ct_factor_warp(S);
     __syncwarp();
     if (lane == 0) ct_propose_post(T, S);
+    __syncwarp();
   }
+  if (S.need_request) ct_pose_request_warp(T, S, S.need_request == 2);
 }
 
 __global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_constant__ CTTrack T) {
@@ -472,6 +495,8 @@ __global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_const
     S.lvl = T.coarsest;
     ct_begin_level(T, S);
   }
+  __syncthreads();
+  if (tid < 32) ct_pose_request_warp(T, S, false);
   __syncthreads();
   while (!S.done) {
     // ---- one evaluation: calcRes + calcGSSSE at the requested pose
@@ -540,6 +565,7 @@ __global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_const
 // A sequential LM chain is latency-bound: fewer, closer SMs with a hardware barrier beat a chip-wide software barrier.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int CTC_THREADS = 512;
+constexpr int CTC_SLOTS = 2;                // reference points per thread kept in registers (2 x 16 x 512 = 16384 points per level)
 constexpr int CTC_MAXC = 16;                 // CTAs per cluster (8 portable, 16 with the non-portable opt-in)
 constexpr int CTC_PLANE_BYTES = 80 * 1024;   // largest level plane staged in shared memory
 struct alignas(64) CTMaps { CUtensorMap lvl[CT_L]; };   // level planes as 2-D tensors of 16-byte texels (encoded as pairs of fp64)
@@ -562,10 +588,8 @@ __device__ __forceinline__ unsigned ctc_smem_u32(const void* p) { return (unsign
 
 // one reference point against a plane in SHARED memory (same arithmetic as ct_eval_point; the taps come from the staged copy)
 template <bool SMEM>
-__device__ __forceinline__ void ctc_eval_accumulate(const CTParams& P, int i, const float* __restrict__ pc_u, const float* __restrict__ pc_v,
-                                                    const float* __restrict__ pc_id, const float* __restrict__ pc_col, const float4* __restrict__ img,
-                                                    const float4* plane_s, float v[CT_NRED]) {
-  const float id = pc_id[i], x = pc_u[i], y = pc_v[i];
+__device__ __forceinline__ void ctc_eval_accumulate(const CTParams& P, int i, const float x, const float y, const float id, const float refColor,
+                                                    const float4* __restrict__ img, const float4* plane_s, float v[CT_NRED]) {
   const float p0 = P.RKi[0] * x + P.RKi[1] * y + P.RKi[2] + P.t[0] * id;
   const float p1 = P.RKi[3] * x + P.RKi[4] * y + P.RKi[5] + P.t[1] * id;
   const float p2 = P.RKi[6] * x + P.RKi[7] * y + P.RKi[8] + P.t[2] * id;
@@ -602,7 +626,6 @@ __device__ __forceinline__ void ctc_eval_accumulate(const CTParams& P, int i, co
     const float h1 = w11 * br.y + w10 * bl.y + w01 * tr.y + w00 * tl.y;
     const float h2 = w11 * br.z + w10 * bl.z + w01 * tr.z + w00 * tl.z;
     if (isfinite(h0)) {
-      const float refColor = pc_col[i];
       const float residual = h0 - (P.affa * refColor + P.affb);
       const float ar = fabsf(residual);
       const float hw = ar < P.huber ? 1.f : P.huber / ar;
@@ -639,8 +662,9 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) ct_track_cluster_kernel(const 
   CTLM& S = M.S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned rank = ctc_rank(), NC = ctc_size();
-  int par = 0, staged_lvl = -1;
+  int par = 0, staged_lvl = -1, cached_lvl = -1;
   unsigned mphase = 0;
+  float4 pts[CTC_SLOTS];
   if (tid == 0) {
     for (int i = 0; i < 9; i++) S.R[i] = T.R0[i];
     for (int i = 0; i < 3; i++) S.t[i] = T.t0[i];
@@ -653,6 +677,8 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) ct_track_cluster_kernel(const 
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ctc_smem_u32(&M.mbar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+  if (tid < 32) ct_pose_request_warp(T, S, false);
   __syncthreads();
   ctc_cluster_sync();  // every CTA's mbarrier exists before the first multicast copy can signal it
   while (!S.done) {
@@ -693,15 +719,26 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) ct_track_cluster_kernel(const 
     float v[64];
 #pragma unroll
     for (int k = 0; k < 64; k++) v[k] = 0.f;
-    const int stride = (int)NC * CTC_THREADS;
-    if (fits) {
-#pragma unroll 2
-      for (int i = (int)rank * CTC_THREADS + tid; i < P.n; i += stride)
-        ctc_eval_accumulate<true>(P, i, T.u[l], T.v[l], T.id[l], T.col[l], T.img[l], reinterpret_cast<const float4*>(M.plane), v);
-    } else {
-#pragma unroll 2
-      for (int i = (int)rank * CTC_THREADS + tid; i < P.n; i += stride)
-        ctc_eval_accumulate<false>(P, i, T.u[l], T.v[l], T.id[l], T.col[l], T.img[l], nullptr, v);
+    const int stride = (int)NC * CTC_THREADS, first = (int)rank * CTC_THREADS + tid;
+    if (cached_lvl != l) {  // the level's reference points of this thread stay in registers for all evaluations of the level
+#pragma unroll
+      for (int k = 0; k < CTC_SLOTS; k++) {
+        const int i = first + k * stride;
+        if (i < P.n) { pts[k] = make_float4(__ldg(T.u[l] + i), __ldg(T.v[l] + i), __ldg(T.id[l] + i), __ldg(T.col[l] + i)); }
+      }
+      cached_lvl = l;
+    }
+#pragma unroll
+    for (int k = 0; k < CTC_SLOTS; k++) {
+      const int i = first + k * stride;
+      if (i < P.n) {
+        if (fits) ctc_eval_accumulate<true>(P, i, pts[k].x, pts[k].y, pts[k].z, pts[k].w, T.img[l], reinterpret_cast<const float4*>(M.plane), v);
+        else ctc_eval_accumulate<false>(P, i, pts[k].x, pts[k].y, pts[k].z, pts[k].w, T.img[l], nullptr, v);
+      }
+    }
+    for (int i = first + CTC_SLOTS * stride; i < P.n; i += stride) {  // more points than register slots: stream the rest
+      if (fits) ctc_eval_accumulate<true>(P, i, __ldg(T.u[l] + i), __ldg(T.v[l] + i), __ldg(T.id[l] + i), __ldg(T.col[l] + i), T.img[l], reinterpret_cast<const float4*>(M.plane), v);
+      else ctc_eval_accumulate<false>(P, i, __ldg(T.u[l] + i), __ldg(T.v[l] + i), __ldg(T.id[l] + i), __ldg(T.col[l] + i), T.img[l], nullptr, v);
     }
     // ---- warp: transposing butterfly, lane L ends with the warp sums of entries 2L, 2L+1
     {
@@ -1151,8 +1188,8 @@ int dmv_ct_make_coarse_depth(dmv_ct* c, int n, const float* Ku, const float* Kv,
     if (c->d_ip) cudaFree(c->d_ip);
     if (c->h_ip) cudaFreeHost(c->h_ip);
     c->ip_cap = std::max(n, 2048);
-    CK(cudaMalloc(&c->d_ip, sizeof(float) * 30 * c->ip_cap));
-    CK(cudaMallocHost(&c->h_ip, sizeof(float) * 30 * c->ip_cap));
+    CK(cudaMalloc(&c->d_ip, sizeof(float) * ((size_t)31 * c->ip_cap + 14 * 64)));
+    CK(cudaMallocHost(&c->h_ip, sizeof(float) * ((size_t)31 * c->ip_cap + 14 * 64)));
   }
   if (c->staging_busy) { CK(cudaStreamSynchronize(c->stream)); c->staging_busy = false; }
   const size_t cap = c->ip_cap;
@@ -1219,8 +1256,8 @@ int dmv_ct_init_points(dmv_ct* c, int n, const int32_t* u, const int32_t* v, flo
     if (c->d_ip) cudaFree(c->d_ip);
     if (c->h_ip) cudaFreeHost(c->h_ip);
     c->ip_cap = std::max(n, 2048);
-    CK(cudaMalloc(&c->d_ip, sizeof(float) * 30 * c->ip_cap));
-    CK(cudaMallocHost(&c->h_ip, sizeof(float) * 30 * c->ip_cap));
+    CK(cudaMalloc(&c->d_ip, sizeof(float) * ((size_t)31 * c->ip_cap + 14 * 64)));
+    CK(cudaMallocHost(&c->h_ip, sizeof(float) * ((size_t)31 * c->ip_cap + 14 * 64)));
   }
   if (c->staging_busy) { CK(cudaStreamSynchronize(c->stream)); c->staging_busy = false; }
   const size_t cap = c->ip_cap;
@@ -1245,39 +1282,57 @@ int dmv_ct_init_points(dmv_ct* c, int n, const int32_t* u, const int32_t* v, flo
   return DMV_OK;
 }
 
-// one host frame's immature points traced against the resident newest frame (ip_trace.cu)
-int dmv_ct_trace_points(dmv_ct* c, const dmv_ip_points* p, const float KRKi[9], const float Kt[3], const float aff[2], const dmv_ip_settings* settings) {
-  if (!c || !p || !KRKi || !Kt || !aff) return set_error(DMV_ERR_INVALID, "null argument");
-  if (p->n < 0 || (p->n > 0 && (!p->u || !p->v || !p->color8 || !p->weights8 || !p->gradH4 || !p->energyTH || !p->idepth_min || !p->idepth_max || !p->quality ||
-                                !p->lastTraceStatus || !p->lastTraceUV2 || !p->lastTracePixelInterval)))
-    return set_error(DMV_ERR_INVALID, "incomplete dmv_ip_points");
-  if (p->n == 0) return DMV_OK;
+// immature points of SEVERAL host frames traced against the resident newest frame in ONE launch (ip_trace.cu): FullSystem::traceNewCoarse's
+// loop over the window's keyframes (FullSystem.cpp:L554-575) collapsed into one upload, one kernel, one download
+int dmv_ct_trace_points_multi(dmv_ct* c, int nsets, const dmv_ip_points* sets, const float* tables14, const dmv_ip_settings* settings) {
+  if (!c || nsets < 0 || (nsets > 0 && (!sets || !tables14))) return set_error(DMV_ERR_INVALID, "null argument");
+  int n = 0;
+  for (int k = 0; k < nsets; k++) {
+    const dmv_ip_points* p = &sets[k];
+    if (p->n < 0 || (p->n > 0 && (!p->u || !p->v || !p->color8 || !p->weights8 || !p->gradH4 || !p->energyTH || !p->idepth_min || !p->idepth_max || !p->quality ||
+                                  !p->lastTraceStatus || !p->lastTraceUV2 || !p->lastTracePixelInterval)))
+      return set_error(DMV_ERR_INVALID, "incomplete dmv_ip_points (set %d)", k);
+    n += p->n;
+  }
+  if (n == 0) return DMV_OK;
   CK(cudaSetDevice(c->device));
-  const int n = p->n;
-  if (n > c->ip_cap) {  // device + pinned staging: 23 read-only floats and 7 in/out words per point
+  const int words = 31;   // 23 read-only floats, 7 in/out words and the set index per point
+  if (n > c->ip_cap) {
     if (c->d_ip) cudaFree(c->d_ip);
     if (c->h_ip) cudaFreeHost(c->h_ip);
     c->ip_cap = std::max(n, 2048);
-    CK(cudaMalloc(&c->d_ip, sizeof(float) * 30 * c->ip_cap));
-    CK(cudaMallocHost(&c->h_ip, sizeof(float) * 30 * c->ip_cap));
+    CK(cudaMalloc(&c->d_ip, sizeof(float) * ((size_t)words * c->ip_cap + 14 * 64)));
+    CK(cudaMallocHost(&c->h_ip, sizeof(float) * ((size_t)words * c->ip_cap + 14 * 64)));
   }
+  if (nsets > 64) return set_error(DMV_ERR_INVALID, "at most 64 host frames per call");
   if (c->staging_busy) { CK(cudaStreamSynchronize(c->stream)); c->staging_busy = false; }
   const size_t cap = c->ip_cap;
   float* hb = c->h_ip;
-  // layout (floats): u | v | color*8 | weights*8 | gradH*4 | energyTH | idmin | idmax | quality | status(int) | uv*2 | interval
+  // layout (floats): u | v | color*8 | weights*8 | gradH*4 | energyTH | idmin | idmax | quality | status(int) | uv*2 | interval | set(int) | tables
   const size_t o_u = 0, o_v = cap, o_col = 2 * cap, o_wgt = 10 * cap, o_g = 18 * cap, o_eth = 22 * cap, o_min = 23 * cap, o_max = 24 * cap, o_q = 25 * cap,
-               o_st = 26 * cap, o_uv = 27 * cap, o_iv = 29 * cap;
-  std::memcpy(hb + o_u, p->u, 4 * n); std::memcpy(hb + o_v, p->v, 4 * n);
-  std::memcpy(hb + o_col, p->color8, 32 * (size_t)n); std::memcpy(hb + o_wgt, p->weights8, 32 * (size_t)n);
-  std::memcpy(hb + o_g, p->gradH4, 16 * (size_t)n); std::memcpy(hb + o_eth, p->energyTH, 4 * n);
-  std::memcpy(hb + o_min, p->idepth_min, 4 * n); std::memcpy(hb + o_max, p->idepth_max, 4 * n); std::memcpy(hb + o_q, p->quality, 4 * n);
-  std::memcpy(hb + o_st, p->lastTraceStatus, 4 * n); std::memcpy(hb + o_uv, p->lastTraceUV2, 8 * (size_t)n); std::memcpy(hb + o_iv, p->lastTracePixelInterval, 4 * n);
-  CK(cudaMemcpyAsync(c->d_ip, hb, sizeof(float) * 30 * cap, cudaMemcpyHostToDevice, c->stream));
+               o_st = 26 * cap, o_uv = 27 * cap, o_iv = 29 * cap, o_set = 30 * cap, o_tab = 31 * cap;
+  size_t at = 0;
+  for (int k = 0; k < nsets; k++) {
+    const dmv_ip_points* p = &sets[k];
+    const size_t m = (size_t)p->n;
+    if (m == 0) continue;
+    std::memcpy(hb + o_u + at, p->u, 4 * m); std::memcpy(hb + o_v + at, p->v, 4 * m);
+    std::memcpy(hb + o_col + 8 * at, p->color8, 32 * m); std::memcpy(hb + o_wgt + 8 * at, p->weights8, 32 * m);
+    std::memcpy(hb + o_g + 4 * at, p->gradH4, 16 * m); std::memcpy(hb + o_eth + at, p->energyTH, 4 * m);
+    std::memcpy(hb + o_min + at, p->idepth_min, 4 * m); std::memcpy(hb + o_max + at, p->idepth_max, 4 * m); std::memcpy(hb + o_q + at, p->quality, 4 * m);
+    std::memcpy(hb + o_st + at, p->lastTraceStatus, 4 * m); std::memcpy(hb + o_uv + 2 * at, p->lastTraceUV2, 8 * m); std::memcpy(hb + o_iv + at, p->lastTracePixelInterval, 4 * m);
+    int* setp = reinterpret_cast<int*>(hb + o_set + at);
+    for (size_t q = 0; q < m; q++) setp[q] = k;
+    at += m;
+  }
+  std::memcpy(hb + o_tab, tables14, sizeof(float) * 14 * (size_t)nsets);
+  CK(cudaMemcpyAsync(c->d_ip, hb, sizeof(float) * ((size_t)words * cap + 14 * (size_t)nsets), cudaMemcpyHostToDevice, c->stream));
   IPTraceArgs A;
+  std::memset(&A, 0, sizeof(A));
   A.n = n; A.w = c->w[0]; A.h = c->h[0];
-  std::memcpy(A.KRKi, KRKi, sizeof(A.KRKi)); std::memcpy(A.Kt, Kt, sizeof(A.Kt)); std::memcpy(A.aff, aff, sizeof(A.aff));
   if (settings) A.s = *settings; else dmv_ip_default_settings(&A.s);
   float* d = c->d_ip;
+  A.tab = d + o_tab; A.set_of = reinterpret_cast<const int*>(d + o_set);
   A.u = d + o_u; A.v = d + o_v; A.color = d + o_col; A.weights = d + o_wgt; A.gradH = d + o_g; A.energyTH = d + o_eth;
   A.idepth_min = d + o_min; A.idepth_max = d + o_max; A.quality = d + o_q; A.status = reinterpret_cast<int*>(d + o_st); A.uv = d + o_uv; A.interval = d + o_iv;
   A.img = c->d_img[0];
@@ -1286,8 +1341,30 @@ int dmv_ct_trace_points(dmv_ct* c, const dmv_ip_points* p, const float KRKi[9], 
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(hb + o_min, d + o_min, sizeof(float) * 7 * cap, cudaMemcpyDeviceToHost, c->stream));  // the 7 in/out words per point
   CK(cudaStreamSynchronize(c->stream));
-  std::memcpy(p->idepth_min, hb + o_min, 4 * n); std::memcpy(p->idepth_max, hb + o_max, 4 * n); std::memcpy(p->quality, hb + o_q, 4 * n);
-  std::memcpy(p->lastTraceStatus, hb + o_st, 4 * n); std::memcpy(p->lastTraceUV2, hb + o_uv, 8 * (size_t)n); std::memcpy(p->lastTracePixelInterval, hb + o_iv, 4 * n);
+  at = 0;
+  for (int k = 0; k < nsets; k++) {
+    const dmv_ip_points* p = &sets[k];
+    const size_t m = (size_t)p->n;
+    if (m == 0) continue;
+    std::memcpy(p->idepth_min, hb + o_min + at, 4 * m); std::memcpy(p->idepth_max, hb + o_max + at, 4 * m); std::memcpy(p->quality, hb + o_q + at, 4 * m);
+    std::memcpy(p->lastTraceStatus, hb + o_st + at, 4 * m); std::memcpy(p->lastTraceUV2, hb + o_uv + 2 * at, 8 * m); std::memcpy(p->lastTracePixelInterval, hb + o_iv + at, 4 * m);
+    at += m;
+  }
+  return DMV_OK;
+}
+
+// one host frame's immature points traced against the resident newest frame
+int dmv_ct_trace_points(dmv_ct* c, const dmv_ip_points* p, const float KRKi[9], const float Kt[3], const float aff[2], const dmv_ip_settings* settings) {
+  if (!c || !p || !KRKi || !Kt || !aff) return set_error(DMV_ERR_INVALID, "null argument");
+  float tab[14];
+  std::memcpy(tab, KRKi, 36); std::memcpy(tab + 9, Kt, 12); std::memcpy(tab + 12, aff, 8);
+  return dmv_ct_trace_points_multi(c, 1, p, tab, settings);
+}
+
+// library-internal: the resident level-0 float4 plane of the coarse-tracker handle (dmv_ba_adopt_frame copies it device-to-device)
+__attribute__((visibility("hidden"))) int dmv_ct_level0_plane(dmv_ct* c, const void** plane, int* w, int* h, int* device, cudaStream_t* stream) {
+  if (!c) return set_error(DMV_ERR_INVALID, "null handle");
+  *plane = c->d_img[0]; *w = c->w[0]; *h = c->h[0]; *device = c->device; *stream = c->stream;
   return DMV_OK;
 }
 

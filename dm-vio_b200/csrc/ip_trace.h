@@ -5,7 +5,9 @@
 namespace dmv {
 struct IPTraceArgs {
   int n, w, h;
-  float KRKi[9], Kt[3], aff[2];
+  float KRKi[9], Kt[3], aff[2];   // one host frame (tab == nullptr)
+  const float* tab;               // several host frames in one launch: [set][14] = KRKi 9 | Kt 3 | aff 2, and set_of[point]
+  const int* set_of;
   dmv_ip_settings s;
   const float *u, *v, *color, *weights, *gradH, *energyTH;
   float *idepth_min, *idepth_max, *quality;

@@ -133,7 +133,7 @@ bool CoarseTracker::eval(int lvl, const SE3& refToNew, AffLight aff_g2l, float c
 bool CoarseTracker::trackNewestCoarse(SE3& lastToNew_out, AffLight& aff_g2l_out, int coarsestLvl, const double minResForAbort[5]) {
   // CoarseTracker.cpp:L539-770, visual-only branch.  calcRes and calcGSSSE are one launch: every evaluation returns the
   // residual statistics AND the Gauss-Newton system at that pose; H,b are adopted only when the step is accepted.
-  if (useDeviceLM) {
+  if (useDeviceLM && !computeCoarseUpdate) {  // a host consumer needs H, b on the host every iteration: host loop
     dmv_ct_track_args in;
     for (int i = 0; i < 9; i++) in.R[i] = lastToNew_out.R[i];
     for (int i = 0; i < 3; i++) in.t[i] = lastToNew_out.t[i];
@@ -181,35 +181,43 @@ bool CoarseTracker::trackNewestCoarse(SE3& lastToNew_out, AffLight& aff_g2l_out,
       for (int i = 0; i < 8; i++) Hl[i * 8 + i] *= (1 + lambda);
       float extrapFac = 1;
       if (lambda < lambdaExtrapolationLimit) extrapFac = sqrt(sqrt(lambdaExtrapolationLimit / lambda));
-      double inc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      {
-        // Vec8 inc = Hl.ldlt().solve(-b) with the fixed-a / fixed-b variants (L639-665)
-        int map[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-        int n = 8;
-        const bool fixA = s.setting_affineOptModeA < 0, fixB = s.setting_affineOptModeB < 0;
-        if (fixA && fixB) n = 6;
-        else if (!fixA && fixB) n = 7;
-        else if (fixA && !fixB) { n = 7; map[6] = 7; }
-        double A[64], rhs[8], x[8];
-        for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) A[i * n + j] = Hl[map[i] * 8 + map[j]]; rhs[i] = -b[map[i]]; }
-        ldlt_solve(n, A, rhs, x);
-        for (int i = 0; i < n; i++) inc[map[i]] = x[i];
-      }
-      for (int i = 0; i < 8; i++) inc[i] *= extrapFac;
-      double incScaled[8];
-      for (int i = 0; i < 8; i++) incScaled[i] = inc[i];
-      incScaled[6] *= SCALE_A;
-      incScaled[7] *= SCALE_B;
-      double ssum = 0;
-      for (int i = 0; i < 8; i++) ssum += incScaled[i];
-      if (!std::isfinite(ssum)) for (int i = 0; i < 8; i++) incScaled[i] = 0;
-      const SE3 refToNew_new = SE3::exp(incScaled) * refToNew_current;
+      SE3 refToNew_new;
       AffLight aff_g2l_new = aff_g2l_current;
-      aff_g2l_new.a += incScaled[6];
-      aff_g2l_new.b += incScaled[7];
       double incNorm = 0;
-      for (int i = 0; i < 8; i++) incNorm += inc[i] * inc[i];
-      incNorm = std::sqrt(incNorm);
+      if (computeCoarseUpdate) {  // CoarseTracker.cpp:L616-637: the IMU integration forms the step from the photometric H, b
+        double incA = 0, incB = 0;
+        refToNew_new = computeCoarseUpdate(Hl, b, extrapFac, lambda, incA, incB, incNorm);
+        aff_g2l_new.a += incA;
+        aff_g2l_new.b += incB;
+      } else {
+        double inc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        {
+          // Vec8 inc = Hl.ldlt().solve(-b) with the fixed-a / fixed-b variants (L639-665)
+          int map[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+          int n = 8;
+          const bool fixA = s.setting_affineOptModeA < 0, fixB = s.setting_affineOptModeB < 0;
+          if (fixA && fixB) n = 6;
+          else if (!fixA && fixB) n = 7;
+          else if (fixA && !fixB) { n = 7; map[6] = 7; }
+          double A[64], rhs[8], x[8];
+          for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) A[i * n + j] = Hl[map[i] * 8 + map[j]]; rhs[i] = -b[map[i]]; }
+          ldlt_solve(n, A, rhs, x);
+          for (int i = 0; i < n; i++) inc[map[i]] = x[i];
+        }
+        for (int i = 0; i < 8; i++) inc[i] *= extrapFac;
+        double incScaled[8];
+        for (int i = 0; i < 8; i++) incScaled[i] = inc[i];
+        incScaled[6] *= SCALE_A;
+        incScaled[7] *= SCALE_B;
+        double ssum = 0;
+        for (int i = 0; i < 8; i++) ssum += incScaled[i];
+        if (!std::isfinite(ssum)) for (int i = 0; i < 8; i++) incScaled[i] = 0;
+        refToNew_new = SE3::exp(incScaled) * refToNew_current;
+        aff_g2l_new.a += incScaled[6];
+        aff_g2l_new.b += incScaled[7];
+        for (int i = 0; i < 8; i++) incNorm += inc[i] * inc[i];
+        incNorm = std::sqrt(incNorm);
+      }
       double resNew[6];
       if (!eval(lvl, refToNew_new, aff_g2l_new, s.setting_coarseCutoffTH * levelCutoffRepeat, true, resNew, Hn, bn)) return false;
       const bool accept = (resNew[0] / resNew[1]) < (resOld[0] / resOld[1]);
@@ -219,6 +227,7 @@ bool CoarseTracker::trackNewestCoarse(SE3& lastToNew_out, AffLight& aff_g2l_out,
         for (int i = 0; i < 6; i++) resOld[i] = resNew[i];
         aff_g2l_current = aff_g2l_new;
         refToNew_current = refToNew_new;
+        if (acceptCoarseUpdate) acceptCoarseUpdate();
         lambda *= 0.5;
       } else {
         lambda *= 4;

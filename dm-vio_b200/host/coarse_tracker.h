@@ -39,6 +39,12 @@ class CoarseTracker {
   // true (default): the whole LM loop runs on the device in one persistent launch (dmv_ct_track); false: the loop below on the host,
   // one fused calcRes+calcGSSSE launch per evaluation (dmv_ct_calc_res_gs)
   bool useDeviceLM = true;
+  // Downstream consumer of the 8x8 system: the slot of dmvio::IMUIntegration::computeCoarseUpdate (IMU/IMUIntegration.hpp:L106-107,
+  // called from CoarseTracker.cpp:L616-637 when setting_useIMU): gets H (8x8 row-major), b, extrapFac, lambda; returns the new refToNew and writes
+  // the affine increments and the increment norm.  When set, trackNewestCoarse runs its LM loop on the host (one fused calcRes + calcGSSSE launch
+  // per evaluation) and calls this instead of the 8x8 LDL^T; acceptCoarseUpdate is called on every accepted step (L700).
+  std::function<SE3(const double H[64], const double b[8], float extrapFac, float lambda, double& incA, double& incB, double& incNorm)> computeCoarseUpdate;
+  std::function<void()> acceptCoarseUpdate;
   double lastResiduals[5];
   double lastFlowIndicators[3];
   int pc_n[DMV_MAX_PYR_LEVELS];

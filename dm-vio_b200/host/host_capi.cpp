@@ -61,6 +61,15 @@ int dmvh_window_set_residuals(void* p, int n, const int32_t* point, const int32_
   static_cast<WindowBA*>(p)->insertResiduals(n, point, target);
   return 0;
 }
+void dmvh_window_set_ba_update_hook(void* p, dmvh_ba_update_cb cb, void* user) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  if (!cb) { W->computeBAUpdate = nullptr; return; }
+  W->computeBAUpdate = [cb, user](const std::vector<double>& H, const std::vector<double>& b, double lambda, int nFrames, const std::vector<double>& HNoLambda) {
+    std::vector<double> x(b.size());
+    cb(H.data(), b.data(), lambda, nFrames, HNoLambda.data(), x.data(), user);
+    return x;
+  };
+}
 int dmvh_window_prepare(void* p) {
   WindowBA* W = static_cast<WindowBA*>(p);
   if (!W->makeIDX()) return -1;

@@ -18,6 +18,9 @@ int dmvh_window_set_points(void* win, int n, const int32_t* host, const float* u
 int dmvh_window_set_points_carry(void* win, int n, const int32_t* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
                                  const float* color8, const float* weights8, const uint8_t* hasDepthPrior, const int32_t* carry_from);
 int dmvh_window_set_residuals(void* win, int n, const int32_t* point, const int32_t* target);
+/* installs WindowBA::computeBAUpdate (the slot of BAGTSAMIntegration::computeBAUpdate): cb(H N*N, b N, lambda, nFrames, HNoLambda N*N, x_out N, user); NULL removes it */
+typedef void (*dmvh_ba_update_cb)(const double* H, const double* b, double lambda, int nFrames, const double* HNoLambda, double* x_out, void* user);
+void dmvh_window_set_ba_update_hook(void* win, dmvh_ba_update_cb cb, void* user);
 int dmvh_window_prepare(void* win); /* makeIDX + setAdjointsF + setPrecalcValues */
 double dmvh_window_linearize(void* win, int fix);
 void dmvh_window_apply(void* win);

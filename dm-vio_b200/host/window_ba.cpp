@@ -547,15 +547,20 @@ void WindowBA::solveSystemF(int iteration, double lambda) {
   lastbS = bFinal;
   for (int i = 0; i < N; i++) HFinal[(size_t)i * N + i] *= (1 + lambda);
   for (size_t i = 0; i < (size_t)N * N; i++) HFinal[i] -= last_Hsc[i] * (1.0 / (1 + lambda));
-  std::vector<double> SVecI(N), Hs((size_t)N * N), bs(N), xs(N);
-  for (int i = 0; i < N; i++) SVecI[i] = 1.0 / std::sqrt(HFinal[(size_t)i * N + i] + 10);
-  for (int i = 0; i < N; i++) {
-    for (int j = 0; j < N; j++) Hs[(size_t)i * N + j] = SVecI[i] * HFinal[(size_t)i * N + j] * SVecI[j];
-    bs[i] = SVecI[i] * bFinal[i];
+  if (computeBAUpdate) {  // EnergyFunctional.cpp:L958-968: the host consumer (GTSAM + IMU factors in DM-VIO) solves; same H / b / x conventions
+    lastX = computeBAUpdate(HFinal, bFinal, lambda, n, lastHS);
+    if ((int)lastX.size() != N) { err_ = "computeBAUpdate returned a vector of the wrong size"; lastX.assign(N, 0.0); }
+  } else {
+    std::vector<double> SVecI(N), Hs((size_t)N * N), bs(N), xs(N);
+    for (int i = 0; i < N; i++) SVecI[i] = 1.0 / std::sqrt(HFinal[(size_t)i * N + i] + 10);
+    for (int i = 0; i < N; i++) {
+      for (int j = 0; j < N; j++) Hs[(size_t)i * N + j] = SVecI[i] * HFinal[(size_t)i * N + j] * SVecI[j];
+      bs[i] = SVecI[i] * bFinal[i];
+    }
+    ldlt_solve(N, Hs.data(), bs.data(), xs.data());
+    lastX.resize(N);
+    for (int i = 0; i < N; i++) lastX[i] = SVecI[i] * xs[i];
   }
-  ldlt_solve(N, Hs.data(), bs.data(), xs.data());
-  lastX.resize(N);
-  for (int i = 0; i < N; i++) lastX[i] = SVecI[i] * xs[i];
   if (iteration >= 2 && s.setting_orthogonalizeXLater) {  // L980-984: project x off the 7 gauge directions (6 pose + 1 scale)
     std::vector<SE3> evalPT(n);
     for (int h = 0; h < n; h++) evalPT[h] = frameHessians[h].worldToCam_evalPT;
@@ -637,6 +642,7 @@ int WindowBA::optimize(int mnumOptIts, std::vector<double>* energyLog, bool fini
     if (newEnergy + newEnergyL + newEnergyM < lastEnergy + lastEnergyL + lastEnergyM) {
       applyRes_Reductor();
       lastEnergy = newEnergy; lastEnergyL = newEnergyL; lastEnergyM = newEnergyM;
+      if (acceptBAUpdate) acceptBAUpdate(lastEnergy);
       lambda *= 0.25;
       lambda = std::max(lambda, minLambda);
     } else {

@@ -10,6 +10,7 @@
 #pragma once
 #include "../../include/dmvio_b200.h"
 #include "se3.h"
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -95,6 +96,13 @@ class WindowBA {
   std::vector<PointFrameResidual> activeResiduals;
   std::vector<double> HM, bM;                  // marginalisation prior (EnergyFunctional::HM / bM), N*N / N
   std::vector<double> lastHS, lastbS, lastX;   // EnergyFunctional.h:L113-116
+  // Downstream consumer of the reduced system: the slot of dmvio::BAGTSAMIntegration::computeBAUpdate (BAGTSAMIntegration.h:L189-190,
+  // called from EnergyFunctional.cpp:L958-968 when setting_useGTSAMIntegration): gets the lambda-damped Schur-reduced H (N*N row-major, DSO
+  // ordering [C4 | per frame trans3 rot3 a b]), b, lambda and the undamped H; returns x (N).  Unset = the no-GTSAM branch (Jacobi-preconditioned
+  // LDL^T, EnergyFunctional.cpp:L971-973).  IMU / GTSAM code stays on the host and plugs in here.
+  std::function<std::vector<double>(const std::vector<double>& H, const std::vector<double>& b, double lambda, int nFrames, const std::vector<double>& HNoLambda)>
+      computeBAUpdate;
+  std::function<void(double energy)> acceptBAUpdate;   // BAGTSAMIntegration::acceptBAUpdate (FullSystemOptimize.cpp:L571)
   int resInA = 0;
   double lastEnergyTotal = 0;
 

@@ -75,6 +75,11 @@ void dmv_ba_default_params(dmv_ba_params* p);
 int dmv_ba_upload_frame(dmv_ba* ba, int slot, const float* dI_aos3);
 /* Same, but builds [I,dx,dy] on the device from the raw float image (FrameHessian::makeImages, HessianBlocks.cpp:L128-191, level 0). */
 int dmv_ba_upload_image(dmv_ba* ba, int slot, const float* image_wh);
+/* Same frame, no second upload: the level-0 [I,dx,dy] plane is copied device-to-device from the coarse-tracker handle in which the frame is
+ * resident (dmv_ct_upload_new_image when it arrived; same device).  The reference shares one FrameHessian::dIp between tracker and mapper
+ * (HessianBlocks.h:L122-123); here the frame crosses PCIe once and makeImages runs once. */
+struct dmv_ct;
+int dmv_ba_adopt_frame(dmv_ba* ba, int slot, struct dmv_ct* ct);
 
 /* EnergyFunctional::makeIDX (EnergyFunctional.cpp:L998-1016): window frame index -> image slot */
 int dmv_ba_set_window(dmv_ba* ba, int nf, const int* slots);
@@ -350,6 +355,9 @@ int dmv_ct_init_points(dmv_ct* ct, int n, const int32_t* u, const int32_t* v, fl
 /* hostToFrame_KRKi (row-major 3x3), hostToFrame_Kt, hostToFrame_affine exactly as traceNewCoarse computes them (FullSystem.cpp:L557-561).
  * settings may be NULL (defaults). */
 int dmv_ct_trace_points(dmv_ct* ct, const dmv_ip_points* pts, const float KRKi[9], const float Kt[3], const float aff[2], const dmv_ip_settings* settings);
+/* The same for the immature points of SEVERAL host keyframes at once (the whole loop of FullSystem::traceNewCoarse, FullSystem.cpp:L554-575):
+ * sets[k] = the points hosted by keyframe k, tables14 = per host [KRKi 9 | Kt 3 | aff 2]; one upload, one launch, one download. */
+int dmv_ct_trace_points_multi(dmv_ct* ct, int nsets, const dmv_ip_points* sets, const float* tables14, const dmv_ip_settings* settings);
 
 /* enable/disable the CUDA-event timing of dmv_ct_calc_res_gs (off by default); dmv_ct_last_timing()[0] = kernel milliseconds */
 int dmv_ct_set_timing(dmv_ct* ct, int enable);

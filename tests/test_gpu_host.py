@@ -247,3 +247,35 @@ def test_keyframe_turnover_flow(hostapi, orc, synth):
     st2, _, _ = hw.states()
     assert st2.shape[0] == nf - 1
     hw.close()
+
+
+def test_ba_adopts_the_frame_resident_in_the_tracker_handle(orc, synth):
+    """a frame crosses PCIe once.  dmv_ba_adopt_frame (device-to-device copy of the level-0 plane the coarse-tracker handle built
+    when the frame arrived) gives bit-identical BA results to uploading the image to the BA handle a second time."""
+    import dmvio_b200.capi as capi
+    W = synth.make_window(nf=3, npts=400, seed=23)
+    ow = orc.Window(W)
+
+    def load(ba):
+        ba.set_window(W["nf"])
+        ba.set_points(W["host"], W["u"], W["v"], W["idepth"], W["idepth_zero"], W["color"], W["weights"])
+        ba.set_residuals(W["res_point"], W["res_target"])
+        ba.set_adjoints(*ow.adjoints())
+        ba.set_state(ow.calib()["k8"], ow.precalc(), ow.frame_tables()["frameEnergyTH"])
+        r = ba.linearize(); ba.apply_res()
+        return r, ba.accumulate()
+
+    ba1 = capi.BA(W["w"], W["h"], max_frames=3, max_points=len(W["host"]))
+    for k in range(3):
+        ba1.upload_image(k, W["images"][k])
+    ct = capi.CT(W["w"], W["h"], synth.pyr_levels(W["w"], W["h"]), max_points=1024)
+    ba2 = capi.BA(W["w"], W["h"], max_frames=3, max_points=len(W["host"]))
+    for k in range(3):
+        ct.upload_new_image(W["images"][k])   # the tracker receives the frame (H2D + device pyramid) ...
+        ba2.adopt_frame(k, ct)                # ... the mapper takes its level-0 plane from there
+    r1, a1 = load(ba1)
+    r2, a2 = load(ba2)
+    assert r1["energy"] == r2["energy"] and r1["n_in"] == r2["n_in"]
+    for k in ("HA", "bA", "Hsc", "bsc"):
+        np.testing.assert_array_equal(a1[k], a2[k])
+    ba1.close(); ba2.close(); ct.close()

@@ -63,6 +63,29 @@ def test_trace_device_pyramid_and_edge_cases(capi, orc, synth):
     g.close()
 
 
+def test_trace_multi_host_equals_per_host(capi, orc, synth):
+    """dmv_ct_trace_points_multi: the points of all host keyframes in one launch == one call per host (the loop of traceNewCoarse), bit for bit"""
+    import dmvio_b200.hostmath as hm
+    W = synth.make_window(nf=5, npts=10, seed=6, trans=0.05, rot=0.01)
+    w, h = W["w"], W["h"]
+    rng = np.random.default_rng(1)
+    new = 4
+    sets = []
+    for host, n in zip(range(4), (700, 1, 1300, 257)):
+        u, v = rng.integers(10, w - 10, n), rng.integers(10, h - 10, n)
+        sets.append((orc.ip_init(W["dI"][host], w, h, u, v),) + tuple(hm.trace_tables(W, host, new)))
+    g = capi.CT(w, h, synth.pyr_levels(w, h), max_points=1024)
+    g.upload_new(0, W["dI"][new])
+    one = [g.trace_points(*s_) for s_ in sets]
+    allq = g.trace_points_multi(sets)
+    for a, b, s_ in zip(one, allq, sets):
+        ref = orc.ip_trace(s_[0], W["dI"][new], w, h, *s_[1:])
+        for k in orc.IP_STATE_KEYS:
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+            np.testing.assert_array_equal(b[k], ref[k], err_msg=k)
+    g.close()
+
+
 def test_init_points_bit_exact(capi, orc, synth):
     """dmv_ct_init_points == ImmaturePoint constructor: colours, weights, gradH, energyTH equal to the oracle bit for bit."""
     W = synth.make_window(nf=2, npts=10, seed=4)

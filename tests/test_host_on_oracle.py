@@ -346,3 +346,37 @@ def test_insert_points_on_older_host_keeps_the_other_points_statistics(hostapi, 
     s2 = hw.point_stats()
     assert np.all(s2["numGoodResiduals"] == 0) and np.all(s2["maxRelBaseline"] == 0)
     hw.close()
+
+
+def test_compute_ba_update_hook_receives_the_reference_conventions(hostapi, orc, synth):
+    """SURVEY §8b consumer contract: WindowBA::computeBAUpdate is the slot of BAGTSAMIntegration::computeBAUpdate(H, b, lambda, frames, HNoLambda) -> x.
+    A hook that solves H x = b like the no-GTSAM branch (Jacobi-preconditioned) must reproduce the built-in path; H must be the lambda-damped
+    Schur-reduced system in DSO ordering, HNoLambda the undamped one."""
+    import ctypes as C
+    W = synth.make_window(nf=4, npts=300, seed=19)
+    ref = hostapi.WindowBA(W); n_ref, log_ref = ref.optimize(4); st_ref, _, _ = ref.states(); ref.close()
+    calls = []
+
+    CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+    def cb(H, b, lam, nframes, H0, x, user):
+        N = 8 * nframes + 4
+        Hm = np.ctypeslib.as_array(H, (N, N)).copy(); bm = np.ctypeslib.as_array(b, (N,)).copy(); H0m = np.ctypeslib.as_array(H0, (N, N)).copy()
+        calls.append((lam, N, np.abs(Hm - Hm.T).max() / np.abs(Hm).max(), np.linalg.eigvalsh(0.5 * (H0m + H0m.T)).min()))
+        sv = 1.0 / np.sqrt(np.diag(Hm) + 10)
+        xs = sv * np.linalg.solve(sv[:, None] * Hm * sv[None, :], sv * bm)
+        for i in range(N):
+            x[i] = xs[i]
+
+    hook = CB(cb)
+    hw = hostapi.WindowBA(W)
+    hw.L.dmvh_window_set_ba_update_hook.argtypes = [C.c_void_p, CB, C.c_void_p]
+    hw.L.dmvh_window_set_ba_update_hook(hw.h, hook, None)
+    n_h, log_h = hw.optimize(4)
+    st_h, _, _ = hw.states()
+    hw.close()
+    assert n_h == n_ref and len(calls) == n_h
+    assert all(c[1] == 8 * 4 + 4 and c[2] < 1e-9 for c in calls)          # N, symmetric
+    assert calls[0][0] == pytest.approx(1e-5)                               # first lambda
+    np.testing.assert_allclose(log_h, log_ref, rtol=2e-5)   # numpy's LU vs the adapter's pivoted LDL^T on a system conditioned ~1e7
+    assert np.abs(st_h - st_ref).max() < 2e-6
