@@ -475,6 +475,68 @@ def batched_roofline(B, steps, warmup, chunk, local_rank, peak):
     return out
 
 
+def config5_stream(D, rank, world, local_rank):
+    """BASELINE config 5: TUM-VI-shaped 512x512 stream, 10 GN iterations per keyframe, IMU factors stubbed (host LDL^T); every rank runs an
+    independent replica (the path does not shard below a window: 'replicas only'), keyframes/s add up."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_stream
+    r = bench_stream.run_stream(keyframes=14, its=10, cpu_keyframes=(3 if (rank == 0 and world == 1) else 0), size=512, device=local_rank)
+    rates = D.gather(r["gpu_keyframes_per_s"])
+    if rank != 0:
+        return None
+    out = {"workload": "512x512 stream, 7 KF window, 2000 pts, exactly 10 GN iterations per keyframe, one replica per GPU", "scaling": "replicas",
+           "keyframes_per_s": float(sum(rates)), "keyframes_per_s_per_gpu": [float(x) for x in rates], "gpu_ms_per_keyframe": r["gpu_ms_per_keyframe"],
+           "gn_iterations_per_keyframe": r["gpu_gn_iterations_per_keyframe"], "timed_gpu": r["timed_gpu"]}
+    if world == 1:
+        out.update(cpu_keyframes_per_s=r["cpu_keyframes_per_s"], cpu_threads=r["cpu_threads"], timed_cpu=r["timed_cpu"])
+    return out
+
+
+def coarse_record(local_rank, peak):
+    """BASELINE config 2: CoarseTracker 5-level alignment of a 640x480 pair (one cluster launch per frame) + its roofline (64 B per point and
+    evaluation: SURVEY.md section 8d) + the single-threaded CPU oracle (the reference's tracker is single-threaded)."""
+    import dmvio_b200.hostapi as hostapi
+    import dmvio_b200.synth as synth
+    from oracle import orc
+    out = {}
+    for levels in (5, 0):
+        T = synth.make_tracking_pair(seed=4321, levels=levels)
+        L = T["levels"]
+        g = hostapi.CoarseTracker(T["w"], T["h"], T["K"], L, device=local_rank)
+        counts = g.set_ref_device(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["img_ref"])
+        g.set_new_image(T["img_new"])
+        R0, t0 = np.eye(3), np.zeros(3)
+        for _ in range(5):
+            r = g.track(R0, t0, 0.0, 0.0)
+        n = 200
+        tw = time.perf_counter()
+        for _ in range(n):
+            r = g.track(R0, t0, 0.0, 0.0)
+        ms = (time.perf_counter() - tw) / n * 1e3
+        tw = time.perf_counter()
+        for _ in range(n):
+            g.set_new_image(T["img_new"]); g.track(R0, t0, 0.0, 0.0)
+        ms_frame = (time.perf_counter() - tw) / n * 1e3
+        ev = r["evaluations"]
+        # point-evaluations per frame: every evaluation of a level touches all its reference points
+        pe = float(r.get("point_evaluations", 0)) or float(ev) * float(np.mean(counts))
+        ct = orc.CoarseTracker(T["w"], T["h"], T["K"], levels)
+        ct.make_coarse_depth(T["Ku"], T["Kv"], T["new_idepth"], T["HdiF"], T["pyr_ref"])
+        ct.set_new_frame(T["pyr_new"])
+        tw = time.perf_counter()
+        for _ in range(3):
+            ct.track(np.eye(3), np.zeros(3), 0.0, 0.0)
+        cpu_ms = (time.perf_counter() - tw) / 3 * 1e3
+        key = f"L{L}"
+        out[key] = {"levels": L, "ref_points_per_level": [int(c) for c in counts], "track_only_ms": ms, "frame_ms_incl_h2d_and_pyramid": ms_frame, "evaluations": int(ev),
+                    "us_per_evaluation": ms * 1e3 / max(1, ev), "cpu_oracle_track_ms_1_thread": cpu_ms, "speedup_track_only": cpu_ms / ms,
+                    "roofline": {"bound": "hbm", "kernel": "ct_track_cluster_kernel", "algorithmic_bytes": 64.0 * pe, "achieved": 64.0 * pe / (ms * 1e-3) / 1e9, "peak": peak,
+                                 "unit": "GB/s", "frac": 64.0 * pe / (ms * 1e-3) / 1e9 / peak,
+                                 "note": "a sequential LM chain of ~%d dependent evaluations of <= 10 k points each: latency-bound by construction (DESIGN.md section 5)" % ev}}
+        g.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -544,6 +606,10 @@ def main():
                                          "ms_per_step": mx["ms_iter"], "e2e_value": mx["e2e_value"], "unit": UNIT, "steps": side_steps, "parity": px,
                                          "roofline_frac": algorithmic_bytes(Cx.nres_local, 8000, NF) / (mx["ms_kernel"] * 1e-3) / 1e9 / peak}
             Cx.close()
+            try:
+                extras["config2_coarse"] = coarse_record(local_rank, peak)
+            except Exception as e:
+                extras["config2_coarse"] = {"error": str(e)[:300]}
             if args.batch > 0:
                 try:
                     tw0 = time.perf_counter()
@@ -552,6 +618,14 @@ def main():
                 except Exception as e:
                     extras["roofline_batched"] = {"error": str(e)[:300]}
 
+    if not args.no_extras:
+        try:
+            c5 = config5_stream(D, rank, world, local_rank)
+        except Exception as e:
+            c5 = {"error": str(e)[:300]}
+            D.gather(0.0) if world > 1 and "gather" not in str(e) else None
+        if rank == 0:
+            extras["config5_stream"] = c5
     clocks = sampler.stop() if rank == 0 else None
     traffic, traffic_src = ncu_traffic()
     ach = balg / (m["ms_kernel"] * 1e-3) / 1e9

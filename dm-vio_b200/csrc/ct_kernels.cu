@@ -214,6 +214,7 @@ struct CTLM {  // the scalar state of trackNewestCoarse, one copy per CTA (share
   float lambda, rep;
   int lvl, iteration, phase, haveRepeated, iterations, evaluations, done, good, status;
   double A[64], rhs[8], Lf[64], Df[8], incs[8], EV[18];   // the damped 8x8 system of the pending LM step, its LDL^T factors, its solution
+  double pevals;                  // sum over the evaluations of the level's reference-point count (measurement: algorithmic bytes = 64 B each)
   int need_solve, need_request;   // need_request: 1 = evaluate at (R, t, a, b), 2 = at the candidate (Rn, tn, an, bn) = exp(incs) * (R, t)
 };
 enum { CT_PH_INIT = 0, CT_PH_LM = 1 };
@@ -400,6 +401,7 @@ __device__ __forceinline__ void ct_pose_request_warp(const CTTrack& T, CTLM& S, 
     S.affLL[1] = (float)(b - aa * T.ref_b);
     S.cutoff = T.cutoffTH * S.rep;
     S.evaluations++;
+    S.pevals += (double)T.n[S.lvl];
   }
 }
 // the scalar state machine step, executed by warp 0 of every CTA
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_const
     S.a = T.a0; S.b = T.b0;
     for (int i = 0; i < 5; i++) S.lastResiduals[i] = __longlong_as_double(0x7ff8000000000000ll);  // NAN
     for (int i = 0; i < 3; i++) S.flow[i] = 1000;
-    S.haveRepeated = 0; S.iterations = 0; S.evaluations = 0; S.done = 0; S.good = 0; S.status = 0; S.cur = 0; S.need_solve = 0;
+    S.haveRepeated = 0; S.iterations = 0; S.evaluations = 0; S.done = 0; S.good = 0; S.status = 0; S.cur = 0; S.need_solve = 0; S.pevals = 0;
     S.lvl = T.coarsest;
     ct_begin_level(T, S);
   }
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(CT_THREADS) ct_track_kernel(const __grid_const
     o[12] = ok ? S.a : T.a0; o[13] = ok ? S.b : T.b0;
     for (int i = 0; i < 5; i++) o[14 + i] = S.lastResiduals[i];
     for (int i = 0; i < 3; i++) o[19 + i] = S.flow[i];
-    o[22] = S.good; o[23] = S.iterations; o[24] = S.evaluations; o[25] = S.status;
+    o[22] = S.good; o[23] = S.iterations; o[24] = S.evaluations; o[25] = S.status; o[26] = S.pevals;
   }
 }
 
@@ -671,7 +673,7 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) ct_track_cluster_kernel(const 
     S.a = T.a0; S.b = T.b0;
     for (int i = 0; i < 5; i++) S.lastResiduals[i] = __longlong_as_double(0x7ff8000000000000ll);  // NAN
     for (int i = 0; i < 3; i++) S.flow[i] = 1000;
-    S.haveRepeated = 0; S.iterations = 0; S.evaluations = 0; S.done = 0; S.good = 0; S.status = 0; S.cur = 0; S.need_solve = 0;
+    S.haveRepeated = 0; S.iterations = 0; S.evaluations = 0; S.done = 0; S.good = 0; S.status = 0; S.cur = 0; S.need_solve = 0; S.pevals = 0;
     S.lvl = T.coarsest;
     ct_begin_level(T, S);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ctc_smem_u32(&M.mbar)) : "memory");
@@ -789,7 +791,7 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) ct_track_cluster_kernel(const 
     o[12] = S.a; o[13] = S.b;
     for (int i = 0; i < 5; i++) o[14 + i] = S.lastResiduals[i];
     for (int i = 0; i < 3; i++) o[19 + i] = S.flow[i];
-    o[22] = S.good; o[23] = S.iterations; o[24] = S.evaluations; o[25] = S.status;
+    o[22] = S.good; o[23] = S.iterations; o[24] = S.evaluations; o[25] = S.status; o[26] = S.pevals;
   }
 }
 
@@ -1376,6 +1378,12 @@ int dmv_ct_set_timing(dmv_ct* c, int enable) {
 int dmv_ct_last_timing(dmv_ct* c, float ms[4]) {
   if (!c || !ms) return set_error(DMV_ERR_INVALID, "null argument");
   for (int i = 0; i < 4; i++) ms[i] = c->last_ms[i];
+  return DMV_OK;
+}
+// instrumentation: reference points evaluated by the last dmv_ct_track, summed over its calcRes / calcGSSSE evaluations
+int dmv_ct_last_point_evaluations(dmv_ct* c, double* n) {
+  if (!c || !n) return set_error(DMV_ERR_INVALID, "null argument");
+  *n = c->h_out[26];
   return DMV_OK;
 }
 int dmv_ct_kernel_launch_count(dmv_ct* c, long long* n) {

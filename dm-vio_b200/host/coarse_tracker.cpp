@@ -149,6 +149,7 @@ bool CoarseTracker::trackNewestCoarse(SE3& lastToNew_out, AffLight& aff_g2l_out,
     for (int i = 0; i < 3; i++) lastFlowIndicators[i] = r.flowIndicators[i];
     iterations = r.iterations;
     evaluations = r.evaluations;
+    dmv_ct_last_point_evaluations(ct_, &pointEvaluations);
     if (r.status != 0) return false;  // aborted inside the level loop: outputs untouched, like the reference's early return
     for (int i = 0; i < 9; i++) lastToNew_out.R[i] = r.R[i];
     for (int i = 0; i < 3; i++) lastToNew_out.t[i] = r.t[i];

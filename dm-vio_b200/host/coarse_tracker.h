@@ -50,6 +50,7 @@ class CoarseTracker {
   int pc_n[DMV_MAX_PYR_LEVELS];
   int iterations = 0;       // LM iterations of the last trackNewestCoarse
   long long evaluations = 0;  // fused calcRes+GS launches of the last trackNewestCoarse
+  double pointEvaluations = 0;  // reference points evaluated, summed over the evaluations (device LM loop only; measurement)
   // reference point cloud of a level (for tests)
   std::vector<float> pc_u[DMV_MAX_PYR_LEVELS], pc_v[DMV_MAX_PYR_LEVELS], pc_idepth[DMV_MAX_PYR_LEVELS], pc_color[DMV_MAX_PYR_LEVELS];
 

@@ -1,4 +1,5 @@
 #include "host_capi.h"
+#include <string>
 #include "coarse_tracker.h"
 #include "window_ba.h"
 #include "marg_frame.h"
@@ -69,6 +70,17 @@ void dmvh_window_set_ba_update_hook(void* p, dmvh_ba_update_cb cb, void* user) {
     cb(H.data(), b.data(), lambda, nFrames, HNoLambda.data(), x.data(), user);
     return x;
   };
+}
+int dmvh_window_set_setting(void* p, const char* name, double value) {
+  Settings& s = static_cast<WindowBA*>(p)->s;
+  const std::string n(name);
+  if (n == "minOptIterations") s.setting_minOptIterations = (int)value;
+  else if (n == "thOptIterations") s.setting_thOptIterations = (float)value;
+  else if (n == "margWeightFac") s.setting_margWeightFac = (float)value;
+  else if (n == "huberTH") s.setting_huberTH = (float)value;
+  else if (n == "minIdepthH_marg") s.setting_minIdepthH_marg = (float)value;
+  else return -1;
+  return 0;
 }
 int dmvh_window_prepare(void* p) {
   WindowBA* W = static_cast<WindowBA*>(p);
@@ -195,6 +207,7 @@ int dmvh_ct_set_ref_device(void* p, int n, const float* Ku, const float* Kv, con
   return static_cast<CoarseTracker*>(p)->setCoarseTrackingRefOnDevice(n, Ku, Kv, nid, HdiF, ref_image, a, ref_exposure) ? 0 : -1;
 }
 void dmvh_ct_set_device_lm(void* p, int on) { static_cast<CoarseTracker*>(p)->useDeviceLM = on != 0; }
+double dmvh_ct_point_evaluations(void* p) { return static_cast<CoarseTracker*>(p)->pointEvaluations; }
 int dmvh_ct_track(void* p, double R[9], double t[3], double* a, double* b, int coarsestLvl, const double minRes[5], double lastRes[5], double flow[3],
                   int* iterations, long long* evaluations) {
   CoarseTracker* C = static_cast<CoarseTracker*>(p);

@@ -21,6 +21,8 @@ int dmvh_window_set_residuals(void* win, int n, const int32_t* point, const int3
 /* installs WindowBA::computeBAUpdate (the slot of BAGTSAMIntegration::computeBAUpdate): cb(H N*N, b N, lambda, nFrames, HNoLambda N*N, x_out N, user); NULL removes it */
 typedef void (*dmvh_ba_update_cb)(const double* H, const double* b, double lambda, int nFrames, const double* HNoLambda, double* x_out, void* user);
 void dmvh_window_set_ba_update_hook(void* win, dmvh_ba_update_cb cb, void* user);
+/* WindowBA::s.<name> = value for the settings the optimisation loop reads (minOptIterations, thOptIterations, margWeightFac, ...); 0 ok, -1 unknown */
+int dmvh_window_set_setting(void* win, const char* name, double value);
 int dmvh_window_prepare(void* win); /* makeIDX + setAdjointsF + setPrecalcValues */
 double dmvh_window_linearize(void* win, int fix);
 void dmvh_window_apply(void* win);
@@ -57,7 +59,8 @@ int dmvh_ct_pc_n(void* ct, int lvl);
 int dmvh_ct_set_new_image(void* ct, const float* image, float exposure);
 int dmvh_ct_set_ref_device(void* ct, int n, const float* Ku, const float* Kv, const float* new_idepth, const float* HdiF, const float* ref_image_wh,
                            double ref_a, double ref_b, float ref_exposure); /* makeCoarseDepthL0 on the device */
-void dmvh_ct_set_device_lm(void* ct, int on); /* 1 (default): LM loop on the device (dmv_ct_track); 0: host loop */
+void dmvh_ct_set_device_lm(void* ct, int on);
+double dmvh_ct_point_evaluations(void* ct); /* CoarseTracker::pointEvaluations of the last track (measurement) */ /* 1 (default): LM loop on the device (dmv_ct_track); 0: host loop */
 int dmvh_ct_track(void* ct, double R[9], double t[3], double* a, double* b, int coarsestLvl, const double minResForAbort[5],
                   double lastResiduals[5], double flow[3], int* iterations, long long* evaluations);
 #ifdef __cplusplus

@@ -262,5 +262,7 @@ class CoarseTracker:
         mr = np.full(5, np.nan) if minRes is None else _c(minRes, np.float64)
         good = self.L.dmvh_ct_track(self.h, R, t, C.byref(ca), C.byref(cb), self.levels - 1 if coarsest is None else coarsest, mr, lastRes, flow,
                                     C.byref(its), C.byref(ev))
+        self.L.dmvh_ct_point_evaluations.restype = C.c_double
+        self.L.dmvh_ct_point_evaluations.argtypes = [C.c_void_p]
         return dict(good=bool(good), R=R.reshape(3, 3), t=t, a=ca.value, b=cb.value, lastResiduals=lastRes, flow=flow, iterations=its.value,
-                    evaluations=ev.value)
+                    evaluations=ev.value, point_evaluations=self.L.dmvh_ct_point_evaluations(self.h))

@@ -363,6 +363,7 @@ int dmv_ct_trace_points_multi(dmv_ct* ct, int nsets, const dmv_ip_points* sets, 
 int dmv_ct_set_timing(dmv_ct* ct, int enable);
 int dmv_ct_last_timing(dmv_ct* ct, float ms[4]);
 int dmv_ct_kernel_launch_count(dmv_ct* ct, long long* n);
+int dmv_ct_last_point_evaluations(dmv_ct* ct, double* n);   /* sum over the last dmv_ct_track's evaluations of the level's reference-point count */
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ struct dmv_ba {
   dmv_ba_config cfg;
   std::vector<std::vector<float>> slot_dI;  // per image slot: level-0 [I, dx, dy] AoS
   std::vector<int> slots;                   // window frame -> slot
-  bool have_tentative = false, have_committed = false, have_adj = false;
+  bool have_tentative = false, have_committed = false, have_adj = false, have_state = false;
   ReducedSystem sys;                        // system of the committed linearisation
   std::vector<float> hdi_solve;             // EFPoint::HdiF at the last dmv_ba_accumulate
 };
@@ -86,8 +86,9 @@ int dmv_ba_upload_image(dmv_ba* b, int slot, const float* image) {
 int dmv_ba_set_window(dmv_ba* b, int nf, const int* slots) {
   if (nf < 2 || nf > b->cfg.max_frames) return fail(DMV_ERR_INVALID, "bad window size");
   b->W.frames.assign(nf, Frame());
-  b->slots.assign(slots, slots + nf);
-  for (int f = 0; f < nf; f++) b->W.frames[f].dI = b->slot_dI[slots[f]].data();
+  b->slots.resize(nf);
+  for (int f = 0; f < nf; f++) b->slots[f] = slots ? slots[f] : f;   // NULL = identity, like the CUDA library
+  for (int f = 0; f < nf; f++) b->W.frames[f].dI = b->slot_dI[b->slots[f]].data();
   b->W.points.clear(); b->W.residuals.clear();
   b->have_tentative = b->have_committed = b->have_adj = false;
   return DMV_OK;
@@ -178,6 +179,7 @@ int dmv_ba_gn_step(dmv_ba* b, const double* x, const dmv_ba_state* st, dmv_ba_li
     }
   }
   take_state(b, st);
+  b->have_state = true;
   const double E = W.linearizeAll(false, nullptr, false);
   if (out) {
     out->energy = E; out->n_in = out->n_oob = out->n_outlier = 0;
@@ -188,6 +190,43 @@ int dmv_ba_gn_step(dmv_ba* b, const double* x, const dmv_ba_state* st, dmv_ba_li
   }
   if (sums) { sums[0] = s3[0]; sums[1] = s3[1]; sums[2] = s3[2]; }
   b->have_tentative = true;
+  return DMV_OK;
+}
+int dmv_ba_set_state(dmv_ba* b, const dmv_ba_state* st) {
+  if (!b || !st) return fail(DMV_ERR_INVALID, "null argument");
+  take_state(b, st);
+  b->have_state = true;
+  return DMV_OK;
+}
+int dmv_ba_linearize(dmv_ba* b, dmv_ba_lin_result* out) {
+  if (!b) return fail(DMV_ERR_INVALID, "null argument");
+  if (!b->have_adj || !b->have_state) return fail(DMV_ERR_STATE, "dmv_ba_set_adjoints + dmv_ba_set_state first");
+  Window& W = b->W;
+  const double E = W.linearizeAll(false, nullptr, false);
+  if (out) {
+    out->energy = E; out->n_in = out->n_oob = out->n_outlier = 0;
+    for (const Residual& r : W.residuals) {
+      if (r.dropped) continue;
+      out->n_in += r.state_NewState == RS_IN; out->n_oob += r.state_NewState == RS_OOB; out->n_outlier += r.state_NewState == RS_OUTLIER;
+    }
+  }
+  b->have_tentative = true;
+  return DMV_OK;
+}
+int dmv_ba_resubstitute(dmv_ba* b, const double* x, float* step_out, int apply, double sums[3]) {
+  if (!b || !x) return fail(DMV_ERR_INVALID, "null argument");
+  if (!b->have_committed) return fail(DMV_ERR_STATE, "no committed linearisation to resubstitute");
+  Window& W = b->W;
+  VecX xv(x, x + 8 * W.nf() + CPARS);
+  W.resubstitute(xv);
+  double s3[3] = {0, 0, 0};
+  for (size_t i = 0; i < W.points.size(); i++) {
+    Point& p = W.points[i];
+    if (step_out) step_out[i] = p.step;
+    s3[0] += (double)p.step * p.step; s3[1] += std::fabs(p.idepth_backup); s3[2] += 1;
+    if (apply) { p.idepth = p.idepth_backup + p.step; p.idepth_zero = p.idepth; }
+  }
+  if (sums) { sums[0] = s3[0]; sums[1] = s3[1]; sums[2] = s3[2]; }
   return DMV_OK;
 }
 int dmv_ba_apply_res(dmv_ba* b) {
@@ -388,6 +427,7 @@ int dmv_ct_calc_res_gs(dmv_ct* c, int lvl, const float RKi[9], const float t[3],
   }
   return DMV_OK;
 }
+int dmv_ct_last_point_evaluations(dmv_ct*, double* n) { *n = 0; return DMV_OK; }
 int dmv_ct_track(dmv_ct* c, const dmv_ct_track_args* in, dmv_ct_track_result* out) {
   CoarseTracker& ct = c->ct;
   ct.lastRef_aff_g2l.a = in->ref_a; ct.lastRef_aff_g2l.b = in->ref_b;

@@ -46,6 +46,17 @@
 
 using namespace dso;
 
+// Drop-in build (oracle/ref_build.sh dropin): the hot-path members are REPLACED at link time by oracle/dropin_stubs.cpp, which forwards them
+// to the CUDA library through include/dmvio_b200.h.  The stubs cache device copies keyed by object; the harness rewrites frames in place
+// (the reference allocates new ones), so it announces that here.  No-ops in the plain reference build.
+#ifdef DMV_DROPIN
+extern "C" { void dropin_invalidate(); void dropin_set_calib(void* hcalib); void dropin_release(const void* owner); }
+#else
+static inline void dropin_invalidate() {}
+static inline void dropin_set_calib(void*) {}
+static inline void dropin_release(const void*) {}
+#endif
+
 // ---- link-time leftovers of translation units that are NOT compiled (FullSystem.cpp, IOWrapper): never executed
 namespace dso {
 int PointHessian::instanceCounter = 0;  // FullSystem.cpp:L66-68
@@ -109,6 +120,7 @@ RefWin* ref_win_create(int w, int h, int nf, const double calib_value_scaled[4],
 
 void ref_win_destroy(RefWin* W) {
   if (!W) return;
+  dropin_release(W->ef);
   // tear down in the reference's ownership order (residuals -> EF mirrors -> points -> frames)
   for (PointFrameResidual* r : W->residuals) { if (r->efResidual) { delete r->efResidual; r->efResidual = 0; } }
   for (PointHessian* p : W->points) { if (p->efPoint) { delete p->efPoint; p->efPoint = 0; } }
@@ -382,6 +394,7 @@ static void out_vec(const VecX& v, double* out) { if (out) for (int i = 0; i < v
 
 // the accumulate half of EnergyFunctional::solveSystemF (EnergyFunctional.cpp:L853-860)
 void ref_win_accumulate(RefWin* W, int, double* HA, double* bA, double* HL, double* bL, double* Hsc, double* bsc, int* resInA) {
+  dropin_set_calib(W->Hcalib);
   MatXX HA_top, HL_top, H_sc;
   VecX bA_top, bL_top, b_sc;
   W->ef->accumulateAF_MT(HA_top, bA_top, multiThreading);
@@ -450,6 +463,7 @@ void ref_win_orthogonalize(RefWin* W, double* x) {
 // EnergyFunctional::solveSystemF (EnergyFunctional.cpp:L841-996), no-GTSAM branch, including resubstituteF_MT
 void ref_win_solve(RefWin* W, int iteration, double lambda, int, double* x_out, double* HFinal, double* bFinal) {
   fill_nullspaces(W);  // FullSystem::solveSystem (FullSystemOptimize.cpp:L655-661) refreshes them before every solve
+  dropin_set_calib(W->Hcalib);
   W->ef->solveSystemF(iteration, lambda, W->Hcalib);
   out_vec(W->ef->lastX, x_out);
   out_mat(W->ef->lastHS, HFinal);
@@ -463,6 +477,7 @@ void ref_win_solve(RefWin* W, int iteration, double lambda, int, double* x_out, 
 double ref_win_hot_iteration(RefWin* W, const double* x, int) {
   EnergyFunctional* ef = W->ef;
   const int N = W->nf * 8 + CPARS;
+  dropin_set_calib(W->Hcalib);
   // FullSystem::backupState (FullSystemOptimize.cpp:L322-370)
   W->Hcalib->value_backup = W->Hcalib->value;
   for (FrameHessian* fh : W->frames) fh->state_backup = fh->get_state();
@@ -681,6 +696,7 @@ RefCT* ref_ct_create(int w, int h, const double K[4]) {
 
 void ref_ct_destroy(RefCT* C) {
   if (!C) return;
+  dropin_release(C->ct);
   for (PointFrameResidual* r : C->residuals) { delete r->efResidual; r->efResidual = 0; }
   for (PointHessian* p : C->points) { delete p->efPoint; p->efPoint = 0; }
   free_frame(C->host);  // deletes its pointHessians and their residuals
@@ -719,6 +735,7 @@ int ref_ct_make_coarse_depth(RefCT* C, int n, const float* Ku, const float* Kv, 
   fhs.push_back(C->host);
   fhs.push_back(C->lastRef);
   C->ct->setCoarseTrackingRef(fhs);
+  dropin_invalidate();
   return C->ct->pc_n[0];
 }
 
@@ -739,6 +756,7 @@ void ref_ct_set_new_frame(RefCT* C, const float* dIp_concat, float ref_exposure,
   C->lastRef->ab_exposure = ref_exposure;
   C->ct->lastRef_aff_g2l = AffLight(ref_a, ref_b);
   C->ct->newFrame = C->newFrame;
+  dropin_invalidate();
 }
 
 void ref_ct_get_K(RefCT* C, int lvl, float* k4, int* wh) {

@@ -45,7 +45,18 @@ def main():
     ap.add_argument("--its", type=int, default=10)
     ap.add_argument("--cpu-keyframes", type=int, default=6)
     ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--device", type=int, default=0)
     args = ap.parse_args()
+    print(json.dumps(run_stream(args.keyframes, args.its, args.cpu_keyframes, args.size, args.device)))
+
+
+def run_stream(keyframes=40, its=10, cpu_keyframes=6, size=512, device=0):
+    """BASELINE config 5 as written: EXACTLY `its` GN iterations per keyframe on both sides (setting_minOptIterations = setting_maxOptIterations =
+    its, MainSettings.cpp:L195-196).  cpu_keyframes = 0 skips the CPU arm (replicas at N > 1)."""
+    class A:
+        pass
+    args = A()
+    args.keyframes, args.its, args.cpu_keyframes, args.size = keyframes, its, cpu_keyframes, size
     import dmvio_b200.hostapi as hostapi
     import dmvio_b200.synth as synth
     from oracle import orc
@@ -55,7 +66,9 @@ def main():
     S = synth.make_window(nf=total, npts=400 * total, w=args.size, h=args.size, seed=77, hosts="all", state_noise=1e-3)
     L = hostapi.lib()
     c = lambda a, t: np.ascontiguousarray(a, t)
-    win = L.dmvh_window_create(S["w"], S["h"], 8, NPTS, 0, c(S["K"], np.float64))
+    win = L.dmvh_window_create(S["w"], S["h"], 8, NPTS, device, c(S["K"], np.float64))
+    L.dmvh_window_set_setting.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    assert L.dmvh_window_set_setting(win, b"minOptIterations", float(args.its)) == 0   # no early break: its iterations per keyframe, as the config says
 
     def add_frame(W, k):
         rc = L.dmvh_window_add_frame(win, c(W["images"][k], np.float32).reshape(-1), 1, c(W["R_eval"][k], np.float64).reshape(-1), c(W["t_eval"][k], np.float64),
@@ -84,19 +97,19 @@ def main():
     cpu_t = []
     for s in range(min(args.cpu_keyframes, args.keyframes)):
         W = sub_window(S, s, NFW, NPTS, np.random.default_rng(7)) if s == 0 else sub_window(S, s, NFW, NPTS, rng)
-        ow = orc.Window(W, nthreads=6)
+        ow = orc.Window(W, nthreads=6, settings={"minOptIterations": args.its})
         t0 = time.perf_counter()
         n_o, log_o = ow.optimize(args.its, precision=0)
         cpu_t.append(time.perf_counter() - t0)
-    g = float(np.median(gpu_t[2:])); cpu = float(np.median(cpu_t))
+    g = float(np.median(gpu_t[2:])); cpu = float(np.median(cpu_t)) if cpu_t else float("nan")
     out = {"metric": "BA keyframes/s (7 KF window, 2000 pts, %dx%d, %d GN its/KF, IMU factors stubbed)" % (args.size, args.size, args.its),
            "gpu_ms_per_keyframe": g * 1e3, "gpu_keyframes_per_s": 1.0 / g, "gpu_gn_iterations_per_keyframe": float(np.mean(gpu_its)),
            "cpu_oracle_ms_per_keyframe": cpu * 1e3, "cpu_keyframes_per_s": 1.0 / cpu, "cpu_threads": 6, "speedup": cpu / g,
            "residuals_per_window": int(len(W["res_point"])), "energy_first_last_of_last_keyframe": [float(v) for v in energies[-1]],
            "timed_gpu": "drop oldest + H2D new image + device [I,dx,dy] + points/residuals upload + adjoints + optimize() (fused GN steps, host LDLT solves)",
            "timed_cpu": "oracle optimize() only (window construction excluded), 6 worker threads"}
-    print(json.dumps(out))
     L.dmvh_window_destroy(win)
+    return out
 
 
 if __name__ == "__main__":
