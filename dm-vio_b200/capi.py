@@ -110,6 +110,20 @@ class CTConfig(C.Structure):
     _fields_ = [("w", C.c_int), ("h", C.c_int), ("levels", C.c_int), ("max_points", C.c_int), ("device", C.c_int)]
 
 
+class CIEvalArgs(C.Structure):
+    _fields_ = [("level", C.c_int), ("RKi", C.c_float * 9), ("t_d", C.c_double * 3), ("t_log", C.c_double * 3), ("r2new_aff", C.c_float * 2),
+                ("huberTH", C.c_float), ("alphaK", C.c_float), ("alphaW", C.c_float), ("couplingWeight", C.c_float),
+                ("weightZeroPriorX", C.c_double), ("weightZeroPriorY", C.c_double),
+                ("idepth_new", C.c_void_p), ("isGood", C.c_void_p), ("energy2", C.c_void_p), ("iR", C.c_void_p),
+                ("isGood_new", C.c_void_p), ("energy_new2", C.c_void_p), ("maxstep", C.c_void_p), ("lastHessian_new", C.c_void_p),
+                ("JbBuffer_new10", C.c_void_p)]
+
+
+class CIEvalResult(C.Structure):
+    _fields_ = [("H", C.c_float * 64), ("b", C.c_float * 8), ("Hsc", C.c_float * 64), ("bsc", C.c_float * 8), ("res3", C.c_float * 3),
+                ("alphaOpt", C.c_float), ("n_good_new", C.c_int)]
+
+
 # every symbol declared in include/dmvio_b200.h (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "dmv_last_error", "dmv_version", "dmv_device_count",
@@ -120,6 +134,7 @@ SYMBOLS = [
     "dmv_ba_comm_init", "dmv_ba_activate_points", "dmv_ba_marginalize_points", "dmv_ba_drop_residuals", "dmv_ba_reset_oob", "dmv_ba_p2p_export", "dmv_ba_p2p_import", "dmv_ba_last_timing", "dmv_ba_bench_device", "dmv_ba_kernel_launch_count", "dmv_ba_io_bytes", "dmv_ba_set_timing", "dmv_ba_bench_e2e",
     "dmv_ba_batch_create", "dmv_ba_batch_destroy", "dmv_ba_batch_gn_step", "dmv_ba_batch_set_timing", "dmv_ba_batch_last_kernel_ms", "dmv_ba_batch_bench",
     "dmv_ct_create", "dmv_ct_destroy", "dmv_ct_set_K", "dmv_ct_set_ref", "dmv_ct_make_coarse_depth", "dmv_ct_get_ref", "dmv_ct_upload_new", "dmv_ct_upload_new_image", "dmv_ct_set_huber",
+    "dmv_ci_create", "dmv_ci_destroy", "dmv_ci_set_K", "dmv_ci_upload_first", "dmv_ci_upload_new", "dmv_ci_set_points", "dmv_ci_calc_res_and_gs", "dmv_ci_kernel_launch_count",
     "dmv_ct_calc_res_gs", "dmv_ct_track", "dmv_ip_default_settings", "dmv_ct_init_points", "dmv_ct_trace_points", "dmv_ct_trace_points_multi", "dmv_ct_set_timing", "dmv_ct_last_timing", "dmv_ct_kernel_launch_count", "dmv_ct_last_point_evaluations",
 ]
 
@@ -193,6 +208,14 @@ def lib():
         L.dmv_ct_last_timing.argtypes = [vp, f32p]
         L.dmv_ct_kernel_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
         L.dmv_ct_last_point_evaluations.argtypes = [vp, C.POINTER(C.c_double)]
+        L.dmv_ci_create.argtypes = [C.POINTER(CTConfig), C.POINTER(vp)]
+        L.dmv_ci_destroy.argtypes = [vp]
+        L.dmv_ci_set_K.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.dmv_ci_upload_first.argtypes = [vp, C.c_int, vp]
+        L.dmv_ci_upload_new.argtypes = [vp, C.c_int, vp]
+        L.dmv_ci_set_points.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+        L.dmv_ci_calc_res_and_gs.argtypes = [vp, C.POINTER(CIEvalArgs), C.POINTER(CIEvalResult)]
+        L.dmv_ci_kernel_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
         _LIB = L
     return _LIB
 
@@ -550,3 +573,60 @@ class CT:
         n = C.c_longlong(0)
         check(self.L.dmv_ct_kernel_launch_count(self.h, C.byref(n)))
         return n.value
+
+
+class CI:
+    """CoarseInitializer::calcResAndGS on the device (include/dmvio_b200.h, dmv_ci_*)"""
+
+    def __init__(self, w, h, levels, max_points=16384, device=0):
+        self.L = lib()
+        cfg = CTConfig(w, h, levels, max_points, device)   # dmv_ci_config has the same layout
+        self.h = vp()
+        check(self.L.dmv_ci_create(C.byref(cfg), C.byref(self.h)))
+        self.levels = levels
+
+    def close(self):
+        if self.h:
+            self.L.dmv_ci_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_K(self, lvl, fx, fy, cx, cy):
+        check(self.L.dmv_ci_set_K(self.h, lvl, C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy)))
+
+    def upload_first(self, lvl, dIp):
+        check(self.L.dmv_ci_upload_first(self.h, lvl, _p(_c(dIp, np.float32).reshape(-1))))
+
+    def upload_new(self, lvl, dIp):
+        check(self.L.dmv_ci_upload_new(self.h, lvl, _p(_c(dIp, np.float32).reshape(-1))))
+
+    def set_points(self, lvl, u, v, outlierTH):
+        check(self.L.dmv_ci_set_points(self.h, lvl, len(u), _p(_c(u, np.float32)), _p(_c(v, np.float32)), _p(_c(outlierTH, np.float32))))
+        self._n = getattr(self, "_n", {})
+        self._n[lvl] = len(u)
+
+    def calc_res_and_gs(self, lvl, RKi, t, t_log, r2new_aff, idepth_new, isGood, energy2, iR, huberTH=9.0, alphaK=2.5 * 2.5, alphaW=150.0 * 150.0,
+                        couplingWeight=1.0, wzpx=0.0, wzpy=0.0):
+        n = self._n[lvl]
+        a = CIEvalArgs()
+        a.level = lvl
+        a.RKi[:] = [float(x) for x in np.asarray(RKi, np.float32).reshape(-1)]
+        a.t_d[:] = [float(x) for x in t]
+        a.t_log[:] = [float(x) for x in t_log]
+        a.r2new_aff[:] = [float(np.float32(x)) for x in r2new_aff]
+        a.huberTH, a.alphaK, a.alphaW, a.couplingWeight, a.weightZeroPriorX, a.weightZeroPriorY = huberTH, alphaK, alphaW, couplingWeight, wzpx, wzpy
+        ins = [_c(idepth_new, np.float32), _c(isGood, np.uint8), _c(energy2, np.float32).reshape(-1), _c(iR, np.float32)]
+        a.idepth_new, a.isGood, a.energy2, a.iR = [x.ctypes.data for x in ins]
+        o = dict(isGood_new=np.zeros(n, np.uint8), energy_new=np.zeros((n, 2), np.float32), maxstep=np.zeros(n, np.float32),
+                 lastHessian_new=np.zeros(n, np.float32), Jb=np.zeros((n, 10), np.float32))
+        a.isGood_new, a.energy_new2, a.maxstep, a.lastHessian_new, a.JbBuffer_new10 = [o[k].ctypes.data for k in ("isGood_new", "energy_new", "maxstep", "lastHessian_new", "Jb")]
+        r = CIEvalResult()
+        check(self.L.dmv_ci_calc_res_and_gs(self.h, C.byref(a), C.byref(r)))
+        o.update(H=np.array(r.H, np.float32).reshape(8, 8), b=np.array(r.b, np.float32), Hsc=np.array(r.Hsc, np.float32).reshape(8, 8),
+                 bsc=np.array(r.bsc, np.float32), res=np.array(r.res3, np.float32), alphaOpt=float(r.alphaOpt), n_good_new=int(r.n_good_new))
+        return o

@@ -169,12 +169,18 @@ __device__ __forceinline__ void xchg_push(const BAXchg& X, int idx, double v) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
   }
 }
-__device__ __forceinline__ double xchg_pull_sum(const BAXchg& X, int idx, double mine, bool& ok) {
+// Both pull variants are WARP-COLLECTIVE with warp-uniform spin loops (votes decide when to leave): lanes of one warp never wait on
+// different conditions, so the warp is converged at the __syncthreads() that follow (an aligned barrier executed by a diverged warp counts
+// the warp twice: premature release or "warp illegal instruction").
+constexpr long long XCHG_SPIN_LIMIT = 400000000ll;  // ~0.2 s of SM clocks: peer lost
+
+// lane-per-entry: every lane with active == true owns entry idx and polls the nranks - 1 packets of it
+__device__ __forceinline__ double xchg_pull_sum_lanes(const BAXchg& X, int idx, double mine, bool active, bool& ok) {
   const uint4* base = X.inbox[X.rank] + (size_t)((X.seq & 1u) * XCHG_MAXR) * X.pitch + idx;
   uint4 pk[XCHG_MAXR];
-  unsigned pending = ((1u << X.nranks) - 1u) & ~(1u << X.rank);
+  unsigned pending = active ? (((1u << X.nranks) - 1u) & ~(1u << X.rank)) : 0u;
   const long long t0 = clock64();
-  while (pending) {
+  while (__any_sync(0xffffffffu, pending != 0u)) {
 #pragma unroll
     for (int r = 0; r < XCHG_MAXR; r++)
       if ((pending >> r) & 1u) {
@@ -184,14 +190,39 @@ __device__ __forceinline__ double xchg_pull_sum(const BAXchg& X, int idx, double
 #pragma unroll
     for (int r = 0; r < XCHG_MAXR; r++)
       if (((pending >> r) & 1u) && pk[r].y == X.seq && pk[r].w == X.seq) pending &= ~(1u << r);
-    if (pending && clock64() - t0 > 400000000ll) { ok = false; return mine; }  // ~0.2 s: peer lost
+    if (__any_sync(0xffffffffu, clock64() - t0 > XCHG_SPIN_LIMIT)) break;
   }
+  if (pending) { ok = false; return mine; }
   double s = 0.0;
 #pragma unroll
   for (int r = 0; r < XCHG_MAXR; r++) {
     if (r >= X.nranks) break;
     s += (r == X.rank) ? mine : __longlong_as_double((long long)(((unsigned long long)pk[r].z << 32) | pk[r].x));
   }
+  return active ? s : mine;
+}
+
+// 16-lane group per entry (phase D): lane gl of the group polls the packet of rank gl, all ranks in flight at once; `mine` is the value of
+// lane gl == 0.  Returns the rank-ordered sum in every lane of the group.
+__device__ __forceinline__ double xchg_pull_sum_group(const BAXchg& X, int idx, double mine, bool active, bool& ok) {
+  const int lane = threadIdx.x & 31, gl = lane & 15;
+  const bool poll = active && gl < X.nranks && gl != X.rank;
+  const uint4* src = X.inbox[X.rank] + (size_t)((X.seq & 1u) * XCHG_MAXR + (poll ? gl : 0)) * X.pitch + idx;
+  uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+  bool pending = poll;
+  const long long t0 = clock64();
+  while (__any_sync(0xffffffffu, pending)) {
+    if (pending) {
+      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "l"(src) : "memory");
+      pending = !(pk.y == X.seq && pk.w == X.seq);
+    }
+    if (__any_sync(0xffffffffu, clock64() - t0 > XCHG_SPIN_LIMIT)) break;
+  }
+  if (__any_sync(0xffffffffu, pending)) ok = false;
+  const double own = __shfl_sync(0xffffffffu, mine, lane & 16);
+  const double v = (gl == X.rank) ? own : (poll ? __longlong_as_double((long long)(((unsigned long long)pk.z << 32) | pk.x)) : 0.0);
+  double s = 0.0;
+  for (int r = 0; r < X.nranks; r++) s += __shfl_sync(0xffffffffu, v, (lane & 16) | r);  // rank order: bit-identical on every rank
   return s;
 }
 
@@ -929,7 +960,9 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR
   const int nitems = n_off + n_diag + n_c + n_b + 16 + 4 + (ACC_MISC - 1);  // the last counter slot is the error flag: written on error only
   const int grp = tid >> 4, gl = tid & 15, groups_per_cta = nthreads >> 4;
   const int nch = W.nchunks;
-  for (int pass = 0; pass < (xch ? 2 : 1); pass++) {
+  // with the peer exchange on: pass 0 (sum + push) -> phase E (Gram tiles + push) -> pass 1 (pull) -> phase E pull: the NVLink round trip of
+  // the H_top entries overlaps the Gram computation
+  auto phase_d = [&](const int pass) {
     for (int base = vcta * groups_per_cta; base < nitems; base += ncta * groups_per_cta) {  // CTA-uniform trip count (shuffles below)
       const int item = base + grp;
       const bool act = item < nitems;
@@ -985,13 +1018,16 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR
           if (xch) { R[d0] = sum; xchg_push(W.xc, d0, sum); }
           else { R[d0] = sum; if (d1 >= 0) R[d1] = sum; if (RH) { RH[d0] = sum; if (d1 >= 0) RH[d1] = sum; } }
         }
-      } else if (gl == 0 && act) {
-        const double sum = xchg_pull_sum(W.xc, d0, R[d0], ok);
-        R[d0] = sum; if (d1 >= 0) R[d1] = sum;
-        if (RH) { RH[d0] = sum; if (d1 >= 0) RH[d1] = sum; }
+      } else {  // warp-collective: both 16-lane groups of the warp wait together
+        const double sum = xchg_pull_sum_group(W.xc, d0, (gl == 0 && act) ? R[d0] : 0.0, act, ok);
+        if (gl == 0 && act) {
+          R[d0] = sum; if (d1 >= 0) R[d1] = sum;
+          if (RH) { RH[d0] = sum; if (d1 >= 0) RH[d1] = sum; }
+        }
       }
     }
-  }
+    };
+  phase_d(0);
 
   // ---------------------------------------------------------------- phase E: [H_sc | b_sc] = sum_p HdiF w_p w_p^T as 4x4 tiles over ALL points
   // of the window: a CTA takes tiles vcta, vcta + ncta (both in ONE pass over the points when the grid has fewer CTAs than tiles)
@@ -1057,18 +1093,33 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR
         S.red[warp][lane] = d[0];   // lane L: value index 16 b4 + 8 b3 + 4 b2 + 2 b1 + b0 = L
       }
       __syncthreads();
-      if (tid < 32 && (tid < 16 || two)) {
+      if (tid < 32) {  // the whole first warp (the exchange below is warp-collective)
+        const bool own = tid < 16 || two;
         double d = 0.0;
         for (int wv = 0; wv < nwarps; wv++) d += S.red[wv][tid];
         const int idx = nH + (tid < 16 ? tile0 : tile1) * 16 + (tid & 15);
-        if (xch) {
-          xchg_push(W.xc, idx, d);
-          d = xchg_pull_sum(W.xc, idx, d, ok);
+        if (own) {
+          R[idx] = d;
+          if (xch) xchg_push(W.xc, idx, d);
+          else if (RH) RH[idx] = d;
         }
-        R[idx] = d;
-        if (RH) RH[idx] = d;
       }
       __syncthreads();
+    }
+  }
+  if (xch) {
+    phase_d(1);
+    if (tid < 32) {  // pull of the Gram tiles: same (tile, lane) ownership as above, so R[idx] is this lane's own earlier store
+      for (int tile0 = vcta; tile0 < W.ntiles; tile0 += 2 * ncta) {
+        const int tile1 = tile0 + ncta;
+        const bool own = tid < 16 || tile1 < W.ntiles;
+        const int idx = nH + (tid < 16 ? tile0 : tile1) * 16 + (tid & 15);
+        const double d = xchg_pull_sum_lanes(W.xc, idx, own ? R[idx] : 0.0, own, ok);
+        if (own) {
+          R[idx] = d;
+          if (RH) RH[idx] = d;
+        }
+      }
     }
   }
   if (!__syncthreads_and(ok) && tid == 0) {  // barrier / peer timeout seen by any thread: raise the error slot of the counters (checked by the host)

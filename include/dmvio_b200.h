@@ -365,6 +365,60 @@ int dmv_ct_last_timing(dmv_ct* ct, float ms[4]);
 int dmv_ct_kernel_launch_count(dmv_ct* ct, long long* n);
 int dmv_ct_last_point_evaluations(dmv_ct* ct, double* n);   /* sum over the last dmv_ct_track's evaluations of the level's reference-point count */
 
+/* ------------------------------------------------------------------------------------------------
+ * Coarse-initialiser handle  ==  the GPU side of CoarseInitializer::calcResAndGS (FullSystem/CoarseInitializer.{h,cpp})
+ * The rest of CoarseInitializer::trackFrame (doStep, applyStep, optReg, propagateUp/Down, the 8x8 solve; L85-281, L650-965) is scalar
+ * per-point host code that runs once per sequence and stays with the caller: it owns the Pnt arrays and passes their live fields per call.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dmv_ci dmv_ci;
+typedef struct dmv_ci_config {
+  int w, h;
+  int levels;      /* pyrLevelsUsed */
+  int max_points;  /* capacity of points[lvl] (numPoints[0] is the largest) */
+  int device;
+} dmv_ci_config;
+int dmv_ci_create(const dmv_ci_config* cfg, dmv_ci** out);
+int dmv_ci_destroy(dmv_ci* ci);
+/* CoarseInitializer::makeK (CoarseInitializer.cpp:L967-999) */
+int dmv_ci_set_K(dmv_ci* ci, int level, float fx, float fy, float cx, float cy);
+/* firstFrame->dIp[level] / newFrame->dIp[level] (w_l*h_l*3 floats AoS) */
+int dmv_ci_upload_first(dmv_ci* ci, int level, const float* dIp_aos3);
+int dmv_ci_upload_new(dmv_ci* ci, int level, const float* dIp_aos3);
+/* the constant fields of points[level] (Pnt::u, v, outlierTH; CoarseInitializer.h:L44-82), set by setFirst (L804-889) */
+int dmv_ci_set_points(dmv_ci* ci, int level, int n, const float* u, const float* v, const float* outlierTH);
+
+typedef struct dmv_ci_eval_args {
+  int level;
+  float RKi[9];          /* (refToNew.rotationMatrix() * Ki[lvl]).cast<float>(), row-major (L341) */
+  double t_d[3];         /* refToNew.translation() */
+  double t_log[3];       /* refToNew.log().head<3>() (L601) */
+  float r2new_aff[2];    /* exp(refToNew_aff.a), refToNew_aff.b (L343) */
+  float huberTH;         /* setting_huberTH */
+  float alphaK, alphaW, couplingWeight;             /* CoarseInitializer members (CoarseInitializer.h:L107-111) */
+  double weightZeroPriorX, weightZeroPriorY;        /* setting_weightZeroPriorDSOInitX / Y (L606-611) */
+  /* live per-point fields of points[level], n entries (n as given to dmv_ci_set_points) */
+  const float* idepth_new;
+  const uint8_t* isGood;
+  const float* energy2;   /* Pnt::energy, 2 per point */
+  const float* iR;
+  /* per-point results (any may be NULL): Pnt::isGood_new, energy_new (2 per point), maxstep, lastHessian_new and the JbBuffer_new rows
+   * (10 per point) as L562-586 leave them.  maxstep / lastHessian_new / JbBuffer_new are meaningful for isGood_new points only. */
+  uint8_t* isGood_new;
+  float* energy_new2;
+  float* maxstep;
+  float* lastHessian_new;
+  float* JbBuffer_new10;
+} dmv_ci_eval_args;
+typedef struct dmv_ci_eval_result {
+  float H[64], b[8], Hsc[64], bsc[8];   /* H_out, b_out, H_out_sc, b_out_sc (row-major) */
+  float res3[3];                        /* Vec3f(E.A, alphaEnergy, E.num) */
+  float alphaOpt;
+  int n_good_new;
+} dmv_ci_eval_result;
+/* CoarseInitializer::calcResAndGS (CoarseInitializer.cpp:L333-625) as ONE launch */
+int dmv_ci_calc_res_and_gs(dmv_ci* ci, const dmv_ci_eval_args* args, dmv_ci_eval_result* out);
+int dmv_ci_kernel_launch_count(dmv_ci* ci, long long* n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,7 @@
 //   CoarseTracker::calcRes / calcGSSSE            (FullSystem/CoarseTracker.cpp:L299-517)  -> dmv_ct_calc_res_gs
 //   EnergyFunctional::accumulateAF_MT / accumulateSCF_MT  (OptimizationBackend/EnergyFunctional.cpp:L201-265) -> dmv_ba_linearize + dmv_ba_accumulate
 //   EnergyFunctional::resubstituteF_MT            (EnergyFunctional.cpp:L267-289)          -> dmv_ba_resubstitute
+//   CoarseInitializer::calcResAndGS               (FullSystem/CoarseInitializer.cpp:L333-625) -> dmv_ci_calc_res_and_gs
 // A maintainer keeps the handles as members (EnergyFunctional::gpu, CoarseTracker::gpu); here they live in side tables keyed by `this`.
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +28,7 @@
 #define protected public
 #include "FullSystem/FullSystem.h"
 #include "FullSystem/CoarseTracker.h"
+#include "FullSystem/CoarseInitializer.h"
 #include "OptimizationBackend/EnergyFunctional.h"
 #include "OptimizationBackend/EnergyFunctionalStructs.h"
 #include "util/globalCalib.h"
@@ -59,6 +61,12 @@ struct BaState {
   int nFrames = 0;
 };
 std::map<const dso::EnergyFunctional*, BaState> g_ba;
+
+struct CiState {
+  dmv_ci* ci = nullptr;
+  unsigned long long gen = 0;
+};
+std::map<const dso::CoarseInitializer*, CiState> g_ci;
 }  // namespace
 
 extern "C" void dropin_invalidate() { g_generation++; }
@@ -66,6 +74,8 @@ extern "C" void dropin_set_calib(void* hcalib) { g_calib = static_cast<dso::Cali
 extern "C" void dropin_release(const void* owner) {
   auto a = g_ct.find(static_cast<const dso::CoarseTracker*>(owner));
   if (a != g_ct.end()) { dmv_ct_destroy(a->second.ct); g_ct.erase(a); }
+  auto c = g_ci.find(static_cast<const dso::CoarseInitializer*>(owner));
+  if (c != g_ci.end()) { dmv_ci_destroy(c->second.ci); g_ci.erase(c); }
   auto b = g_ba.find(static_cast<const dso::EnergyFunctional*>(owner));
   if (b != g_ba.end()) { dmv_ba_destroy(b->second.ba); g_ba.erase(b); }
 }
@@ -115,6 +125,68 @@ void CoarseTracker::calcGSSSE(int lvl, Mat88& H_out, Vec8& b_out, const SE3&, Af
     b_out[i] = s.b[i];
     for (int j = 0; j < 8; j++) H_out(i, j) = s.H[i * 8 + j];
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------- coarse initialiser
+Vec3f CoarseInitializer::calcResAndGS(int lvl, Mat88f& H_out, Vec8f& b_out, Mat88f& H_out_sc, Vec8f& b_out_sc, const SE3& refToNew, AffLight refToNew_aff,
+                                      bool plot) {
+  (void)plot;
+  CiState& s = g_ci[this];
+  if (!s.ci) {
+    int maxn = 1;
+    for (int l = 0; l < pyrLevelsUsed; l++) maxn = std::max(maxn, numPoints[l]);
+    dmv_ci_config cfg{w[0], h[0], pyrLevelsUsed, maxn, 0};
+    DMV_CHECK(dmv_ci_create(&cfg, &s.ci));
+  }
+  if (s.gen != g_generation) {   // frames and the constant point fields, as setFirst / trackFrame hold them
+    for (int l = 0; l < pyrLevelsUsed; l++) {
+      DMV_CHECK(dmv_ci_set_K(s.ci, l, (float)fx[l], (float)fy[l], (float)cx[l], (float)cy[l]));
+      DMV_CHECK(dmv_ci_upload_first(s.ci, l, reinterpret_cast<const float*>(firstFrame->dIp[l])));
+      DMV_CHECK(dmv_ci_upload_new(s.ci, l, reinterpret_cast<const float*>(newFrame->dIp[l])));
+      const int n = numPoints[l];
+      std::vector<float> u(n), v(n), th(n);
+      for (int i = 0; i < n; i++) { u[i] = points[l][i].u; v[i] = points[l][i].v; th[i] = points[l][i].outlierTH; }
+      DMV_CHECK(dmv_ci_set_points(s.ci, l, n, u.data(), v.data(), th.data()));
+    }
+    s.gen = g_generation;
+  }
+  const int n = numPoints[lvl];
+  Pnt* pts = points[lvl];
+  std::vector<float> idn(n), en((size_t)2 * n), iR(n), en_new((size_t)2 * n), mstep(n), lastH(n), jb((size_t)10 * n);
+  std::vector<uint8_t> good(n), good_new(n);
+  for (int i = 0; i < n; i++) { idn[i] = pts[i].idepth_new; good[i] = pts[i].isGood; en[2 * i] = pts[i].energy[0]; en[2 * i + 1] = pts[i].energy[1]; iR[i] = pts[i].iR; }
+  dmv_ci_eval_args a;
+  std::memset(&a, 0, sizeof(a));
+  a.level = lvl;
+  const Mat33f RKi = (refToNew.rotationMatrix() * Ki[lvl]).cast<float>();
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) a.RKi[3 * i + j] = RKi(i, j);
+  const Vec6 lg = refToNew.log();
+  for (int i = 0; i < 3; i++) { a.t_d[i] = refToNew.translation()[i]; a.t_log[i] = lg[i]; }
+  const Eigen::Vector2f r2new_aff((float)std::exp(refToNew_aff.a), (float)refToNew_aff.b);
+  a.r2new_aff[0] = r2new_aff[0]; a.r2new_aff[1] = r2new_aff[1];
+  a.huberTH = setting_huberTH; a.alphaK = alphaK; a.alphaW = alphaW; a.couplingWeight = couplingWeight;
+  a.weightZeroPriorX = setting_weightZeroPriorDSOInitX; a.weightZeroPriorY = setting_weightZeroPriorDSOInitY;
+  a.idepth_new = idn.data(); a.isGood = good.data(); a.energy2 = en.data(); a.iR = iR.data();
+  a.isGood_new = good_new.data(); a.energy_new2 = en_new.data(); a.maxstep = mstep.data(); a.lastHessian_new = lastH.data(); a.JbBuffer_new10 = jb.data();
+  dmv_ci_eval_result r;
+  DMV_CHECK(dmv_ci_calc_res_and_gs(s.ci, &a, &r));
+  for (int i = 0; i < n; i++) {   // what processPointsForReduce and the Schur pass leave in the Pnt array / JbBuffer_new (L369-586)
+    Pnt& p = pts[i];
+    p.isGood_new = good_new[i] != 0;
+    p.energy_new[0] = en_new[2 * i]; p.energy_new[1] = en_new[2 * i + 1];
+    if (p.isGood) p.maxstep = mstep[i]; else p.maxstep = 1e10;
+    if (p.isGood_new) {
+      p.lastHessian_new = lastH[i];
+      for (int k = 0; k < 10; k++) JbBuffer_new[i][k] = jb[(size_t)10 * i + k];
+    }
+  }
+  for (int i = 0; i < 8; i++) {
+    b_out[i] = r.b[i]; b_out_sc[i] = r.bsc[i];
+    for (int j = 0; j < 8; j++) { H_out(i, j) = r.H[i * 8 + j]; H_out_sc(i, j) = r.Hsc[i * 8 + j]; }
+  }
+  return Vec3f(r.res3[0], r.res3[1], r.res3[2]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------- energy functional

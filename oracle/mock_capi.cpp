@@ -11,6 +11,7 @@
 #include "../include/dmvio_b200.h"
 #include "orc_ba.h"
 #include "orc_coarse.h"
+#include "orc_init.h"
 
 #include <cstdarg>
 #include <cstdio>
@@ -28,6 +29,11 @@ struct dmv_ba {
   bool have_tentative = false, have_committed = false, have_adj = false, have_state = false;
   ReducedSystem sys;                        // system of the committed linearisation
   std::vector<float> hdi_solve;             // EFPoint::HdiF at the last dmv_ba_accumulate
+};
+struct dmv_ci {
+  CoarseInit ci;
+  dmv_ci_config cfg;
+  std::vector<std::vector<float>> first, next;   // level planes [I, dx, dy] AoS
 };
 struct dmv_ct {
   CoarseTracker ct;
@@ -452,5 +458,75 @@ int dmv_ct_track(dmv_ct* c, const dmv_ct_track_args* in, dmv_ct_track_result* ou
   out->trackingGood = good ? 1 : 0; out->iterations = its; out->evaluations = 0; out->status = aborted ? 2 : 0;
   return DMV_OK;
 }
+
+
+// ---- CoarseInitializer::calcResAndGS (dmv_ci_*) on the restatement oracle/orc_init.cpp
+int dmv_ci_create(const dmv_ci_config* cfg, dmv_ci** out) {
+  if (!cfg || !out || cfg->levels < 1 || cfg->levels > PYR_LEVELS) return fail(DMV_ERR_INVALID, "bad dmv_ci_config");
+  dmv_ci* c = new dmv_ci();
+  c->cfg = *cfg;
+  c->ci.levels = cfg->levels;
+  c->first.resize(cfg->levels); c->next.resize(cfg->levels);
+  for (int l = 0; l < cfg->levels; l++) { c->ci.w[l] = cfg->w >> l; c->ci.h[l] = cfg->h >> l; }
+  *out = c;
+  return DMV_OK;
+}
+int dmv_ci_destroy(dmv_ci* c) { delete c; return DMV_OK; }
+int dmv_ci_set_K(dmv_ci* c, int l, float fx, float fy, float cx, float cy) {
+  c->ci.fx[l] = fx; c->ci.fy[l] = fy; c->ci.cx[l] = cx; c->ci.cy[l] = cy;
+  return DMV_OK;
+}
+int dmv_ci_upload_first(dmv_ci* c, int l, const float* dIp) {
+  c->first[l].assign(dIp, dIp + (size_t)3 * c->ci.w[l] * c->ci.h[l]);
+  c->ci.dIFirst[l] = c->first[l].data();
+  return DMV_OK;
+}
+int dmv_ci_upload_new(dmv_ci* c, int l, const float* dIp) {
+  c->next[l].assign(dIp, dIp + (size_t)3 * c->ci.w[l] * c->ci.h[l]);
+  c->ci.dINew[l] = c->next[l].data();
+  return DMV_OK;
+}
+int dmv_ci_set_points(dmv_ci* c, int l, int n, const float* u, const float* v, const float* outlierTH) {
+  c->ci.points[l].assign(n, InitPnt());
+  for (int i = 0; i < n; i++) { InitPnt& p = c->ci.points[l][i]; p.u = u[i]; p.v = v[i]; p.outlierTH = outlierTH[i]; }
+  if ((int)c->ci.JbBuffer_new.size() < n) { c->ci.JbBuffer.assign(n, std::array<float, 10>()); c->ci.JbBuffer_new.assign(n, std::array<float, 10>()); }
+  return DMV_OK;
+}
+int dmv_ci_calc_res_and_gs(dmv_ci* c, const dmv_ci_eval_args* a, dmv_ci_eval_result* r) {
+  const int l = a->level, n = (int)c->ci.points[l].size();
+  if (!c->ci.dIFirst[l] || !c->ci.dINew[l] || n < 1) return fail(DMV_ERR_STATE, "frames / points first");
+  for (int i = 0; i < n; i++) {
+    InitPnt& p = c->ci.points[l][i];
+    p.idepth_new = a->idepth_new[i]; p.isGood = a->isGood[i] != 0; p.energy[0] = a->energy2[2 * i]; p.energy[1] = a->energy2[2 * i + 1]; p.iR = a->iR[i];
+  }
+  CoarseInit& ci = c->ci;
+  ci.s.huberTH = a->huberTH; ci.alphaK = a->alphaK; ci.alphaW = a->alphaW; ci.couplingWeight = a->couplingWeight;
+  ci.weightZeroPriorDSOInitX = a->weightZeroPriorX; ci.weightZeroPriorDSOInitY = a->weightZeroPriorY;
+  // the restatement takes a pose and forms R * Ki itself: hand it the identity rotation and the given product as "Ki"
+  for (int i = 0; i < 9; i++) ci.Ki[l].d[i] = a->RKi[i];
+  SE3 T;
+  for (int i = 0; i < 3; i++) T.t[i] = a->t_d[i];
+  AffLight aff;
+  aff.a = std::log((double)a->r2new_aff[0]); aff.b = a->r2new_aff[1];
+  InitSystem sys;
+  ci.calcResAndGS(l, sys, T, aff, r->res3);
+  std::memcpy(r->H, sys.H, sizeof(sys.H)); std::memcpy(r->b, sys.b, sizeof(sys.b));
+  std::memcpy(r->Hsc, sys.Hsc, sizeof(sys.Hsc)); std::memcpy(r->bsc, sys.bsc, sizeof(sys.bsc));
+  const double tsq = a->t_d[0] * a->t_d[0] + a->t_d[1] * a->t_d[1] + a->t_d[2] * a->t_d[2];
+  r->alphaOpt = (ci.alphaW * (float)(tsq * n) > ci.alphaK * n) ? 0.f : ci.alphaW;
+  for (int k = 0; k < 3; k++) r->b[k] += (float)(a->t_log[k] - a->t_d[k]) * r->alphaOpt * n;   // log of the real pose vs the pure translation used above
+  r->n_good_new = 0;
+  for (int i = 0; i < n; i++) {
+    const InitPnt& p = ci.points[l][i];
+    r->n_good_new += p.isGood_new;
+    if (a->isGood_new) a->isGood_new[i] = p.isGood_new;
+    if (a->energy_new2) { a->energy_new2[2 * i] = p.energy_new[0]; a->energy_new2[2 * i + 1] = p.energy_new[1]; }
+    if (a->maxstep) a->maxstep[i] = p.maxstep;
+    if (a->lastHessian_new) a->lastHessian_new[i] = p.lastHessian_new;
+    if (a->JbBuffer_new10) for (int k = 0; k < 10; k++) a->JbBuffer_new10[10 * i + k] = p.isGood_new ? ci.JbBuffer_new[i][k] : 0.f;
+  }
+  return DMV_OK;
+}
+int dmv_ci_kernel_launch_count(dmv_ci*, long long* n) { *n = 0; return DMV_OK; }
 
 }  // extern "C"

@@ -501,6 +501,31 @@ class CoarseInit:
         self._f("calc")(self.hd, lvl, np.ascontiguousarray(R, np.float64).reshape(-1), np.ascontiguousarray(t, np.float64), float(a), float(b), H, bb, Hsc, bsc, res)
         return dict(H=H.reshape(8, 8), b=bb, Hsc=Hsc.reshape(8, 8), bsc=bsc, res=res)
 
+    def static_fields(self, lvl):
+        """u, v, outlierTH of points[lvl] (restatement only)"""
+        n = self._f("npts")(self.hd, lvl)
+        u, v, th = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        f = self.L.orc_ci_get_static
+        f.argtypes = [C.c_void_p, C.c_int, f32p, f32p, f32p]
+        f(self.hd, lvl, u, v, th)
+        return u, v, th
+
+    def jb(self, lvl):
+        """JbBuffer_new rows of the last calc() on this level (restatement only)"""
+        n = self._f("npts")(self.hd, lvl)
+        o = np.zeros((n, 10), np.float32)
+        f = self.L.orc_ci_get_jb
+        f.argtypes = [C.c_void_p, C.c_int, f32p]
+        f(self.hd, lvl, o.reshape(-1))
+        return o
+
+    def K(self, lvl):
+        k4, wh = np.zeros(4), np.zeros(2, np.int32)
+        f = self.L.orc_ci_get_K
+        f.argtypes = [C.c_void_p, C.c_int, f64p, i32p]
+        f(self.hd, lvl, k4, wh)
+        return k4, wh
+
     def points(self, lvl):
         n = self._f("npts")(self.hd, lvl)
         o = np.zeros((n, 12), np.float32)

@@ -592,6 +592,23 @@ void orc_ci_get_points(OrcCI* o, int lvl, float* out12) {
     q[7] = p.lastHessian; q[8] = p.lastHessian_new; q[9] = p.maxstep; q[10] = p.isGood ? 1.f : 0.f; q[11] = p.isGood_new ? 1.f : 0.f;
   }
 }
+// constant per-point fields u, v, outlierTH and the JbBuffer_new rows of the last calcResAndGS (10 per point): inputs / expected outputs of the
+// CUDA kernel's parity test (tests/test_gpu_init.py)
+void orc_ci_get_static(OrcCI* o, int lvl, float* u, float* v, float* outlierTH) {
+  for (size_t i = 0; i < o->ci.points[lvl].size(); i++) {
+    const orc::InitPnt& p = o->ci.points[lvl][i];
+    u[i] = p.u; v[i] = p.v; outlierTH[i] = p.outlierTH;
+  }
+}
+void orc_ci_get_K(OrcCI* o, int lvl, double* k4, int* wh) {
+  k4[0] = o->ci.fx[lvl]; k4[1] = o->ci.fy[lvl]; k4[2] = o->ci.cx[lvl]; k4[3] = o->ci.cy[lvl];
+  wh[0] = o->ci.w[lvl]; wh[1] = o->ci.h[lvl];
+}
+void orc_ci_get_jb(OrcCI* o, int lvl, float* out10) {
+  const size_t n = o->ci.points[lvl].size();
+  for (size_t i = 0; i < n && i < o->ci.JbBuffer_new.size(); i++)
+    for (int k = 0; k < 10; k++) out10[10 * i + k] = o->ci.JbBuffer_new[i][k];
+}
 // sets idepth, idepth_new, iR, lastHessian, isGood (5 floats per point) — lets the tests start from arbitrary states
 void orc_ci_set_points(OrcCI* o, int lvl, const float* in5) {
   for (size_t i = 0; i < o->ci.points[lvl].size(); i++) {

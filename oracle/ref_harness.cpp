@@ -898,6 +898,7 @@ RefCI* ref_ci_create(int w, int h, const double K[4]) {
 }
 void ref_ci_destroy(RefCI* C) {
   if (!C) return;
+  dropin_release(C->ci);
   delete C->ci;
   free_frame(C->first);
   free_frame(C->cur);
@@ -948,6 +949,7 @@ void ref_ci_set_first(RefCI* C, const float* dIp_concat, float exposure, const i
   ci->alphaW = 150 * 150;
   ci->regWeight = 0.8;
   ci->couplingWeight = 1;
+  dropin_invalidate();
 }
 void ref_ci_set_new(RefCI* C, const float* dIp_concat, float exposure) {
   free_frame(C->cur);
@@ -955,6 +957,7 @@ void ref_ci_set_new(RefCI* C, const float* dIp_concat, float exposure) {
   load_pyramid(C->cur, dIp_concat);
   C->cur->ab_exposure = exposure;
   C->ci->newFrame = C->cur;
+  dropin_invalidate();
 }
 void ref_ci_calc(RefCI* C, int lvl, const double R[9], const double t[3], double a, double b, float* H64, float* b8, float* Hsc64, float* bsc8, float* res3) {
   Mat88f H, Hsc; Vec8f bb, bsc;

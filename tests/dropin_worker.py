@@ -11,8 +11,9 @@ import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 
 BA_CASES = {
     "c1": dict(nf=4, npts=300, seed=7),
@@ -74,9 +75,42 @@ def run_ct(ref, synth, name):
     return out
 
 
+CI_CASES = {"few": (50, 45, 35, 25), "many": (3000, 900, 300, 100)}
+
+
+def run_ci(ref, synth, name):
+    """the reference's own CoarseInitializer::trackFrame (pyramid loop, LM, depth steps, regularisation, propagation, snapping) over six frames;
+    in the drop-in build every calcResAndGS inside it is served by dmv_ci_calc_res_and_gs"""
+    from helpers import init_points
+    frames = [synth.make_tracking_pair(seed=77, trans=0.02 * k, rot=0.004 * k) for k in (1, 2, 3)]
+    T = frames[0]
+    w, h, L = T["w"], T["h"], T["levels"]
+    pts = init_points(np.random.default_rng(6), w, h, L, CI_CASES[name])
+    rc = ref.CoarseInit(w, h, T["K"])
+    rc.set_first(T["pyr_ref"], 1.0, pts)
+    rc.set_new(T["pyr_new"], 1.2)
+    out = {"levels": np.int64(L)}
+    R, t = synth.se3_exp(np.array([0.004, -0.003, 0.002, 0.002, -0.001, 0.0015]))
+    for lvl in range(L):
+        s = rc.calc(lvl, R, t, np.log(1.2), 0.3)                            # CoarseInitializer::calcResAndGS directly
+        for k in ("H", "b", "Hsc", "bsc", "res"):
+            out[f"calc_{lvl}_{k}"] = s[k]
+        p = rc.points(lvl)
+        out[f"calc_{lvl}_good"], out[f"calc_{lvl}_energy"] = p["isGood_new"], p["energy_new0"]
+    rc.set_first(T["pyr_ref"], 1.0, pts)
+    for k, F in enumerate(frames + frames[::-1]):
+        tr = rc.track(F["pyr_new"], 1.0 + 0.05 * k)
+        out[f"trk_{k}_state"] = np.array([tr["ok"], tr["snapped"], tr["snappedAt"], tr["frameID"]], np.int64)
+        out[f"trk_{k}_R"], out[f"trk_{k}_t"], out[f"trk_{k}_ab"] = tr["R"], tr["t"], np.array([tr["a"], tr["b"]])
+    p0 = rc.points(0)
+    out["final_isGood"], out["final_idepth"] = p0["isGood"], p0["idepth"]
+    del rc
+    return out
+
+
 def run_case(ref, synth, case):
     kind, name = case.split(":")
-    return run_ba(ref, synth, name) if kind == "ba" else run_ct(ref, synth, name)
+    return {"ba": run_ba, "ct": run_ct, "ci": run_ci}[kind](ref, synth, name)
 
 
 if __name__ == "__main__":

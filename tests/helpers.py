@@ -41,3 +41,32 @@ def activation_case(synth, orc, seed=9, nf=5, n=2000, **kw):
     bad = rng.random(n) < 0.03            # a few hopeless intervals: far from the truth
     P["idepth_min"][bad] *= 3; P["idepth_max"][bad] *= 3
     return W, host, P
+
+
+def init_points(rng, w, h, levels, counts):
+    """points per level the way CoarseInitializer::setFirst lays them out (integer pixel + 0.1 inside the pattern margin, row-major order), with
+    brute-force 10 nearest neighbours and the nearest parent one level up (CoarseInitializer::makeNN's outputs, without its kd-tree)"""
+    pts = []
+    for l in range(levels):
+        wl, hl = w >> l, h >> l
+        n = counts[l]
+        x = rng.integers(3, wl - 4, 4 * n); y = rng.integers(3, hl - 4, 4 * n)
+        xy = np.unique(np.stack([y, x], 1), axis=0)                       # row-major order, no duplicates
+        xy = xy[np.sort(rng.choice(len(xy), min(n, len(xy)), replace=False))]
+        pts.append(dict(u=(xy[:, 1] + 0.1).astype(np.float32), v=(xy[:, 0] + 0.1).astype(np.float32), type=np.ones(len(xy), np.float32)))
+    for l in range(levels):
+        p = pts[l]
+        P = np.stack([p["u"], p["v"]], 1).astype(np.float64)
+        d = ((P[:, None, :] - P[None, :, :]) ** 2).sum(-1)
+        np.fill_diagonal(d, np.inf)
+        k = min(10, len(P) - 1)
+        nb = np.full((len(P), 10), -1, np.int32)
+        nb[:, :k] = np.argsort(d, axis=1, kind="stable")[:, :k]
+        p["neighbours"] = nb
+        if l + 1 < levels:
+            Q = np.stack([pts[l + 1]["u"], pts[l + 1]["v"]], 1).astype(np.float64)
+            dq = ((0.5 * P[:, None, :] - Q[None, :, :]) ** 2).sum(-1)
+            p["parent"] = np.argmin(dq, axis=1).astype(np.int32)
+        else:
+            p["parent"] = np.full(len(P), -1, np.int32)
+    return pts

@@ -1,5 +1,6 @@
 """Drop-in proof: the REFERENCE's own translation units, compiled from /root/reference, linked with oracle/dropin_stubs.cpp so
-that its hot-path members (CoarseTracker::calcRes / calcGSSSE, EnergyFunctional::accumulateAF_MT / accumulateSCF_MT / resubstituteF_MT) forward to
+that its hot-path members (CoarseTracker::calcRes / calcGSSSE, EnergyFunctional::accumulateAF_MT / accumulateSCF_MT / resubstituteF_MT,
+CoarseInitializer::calcResAndGS) forward to
 the C ABI of include/dmvio_b200.h (oracle/ref_build.sh dropin -> oracle/_ref/libdso_ref_dropin.so).  Everything around those members — the object
 graph, PointFrameResidual::linearize, EnergyFunctional::solveSystemF with its dense solve, CoarseTracker::trackNewestCoarse with its LM loop — is
 the reference's unmodified code.  The same harness calls run against the unmodified oracle/_ref/libdso_ref.so in this process and against the
@@ -60,8 +61,9 @@ def _check_ba(d, r):
     # oracle-precision-1 check and tests/test_gpu_ba.py)
     for k, tol in (("acc_HA", 3e-6), ("acc_Hsc", 3e-6), ("acc_bA", 1e-4), ("acc_bsc", 1e-4)):
         assert _rel(d[k], r[k]) < tol, (k, _rel(d[k], r[k]))
-    for k in ("pt_Hdd", "pt_bd", "pt_Hcd", "pt_HdiF", "pt_bdSumF"):
-        assert _rel(d[k], r[k]) < 2e-5, (k, _rel(d[k], r[k]))
+    for k in ("pt_Hdd", "pt_bd", "pt_Hcd", "pt_HdiF", "pt_bdSumF"):   # per-point fp32 sums: the bounds of tests/test_gpu_ba.py
+        np.testing.assert_allclose(d[k], r[k], rtol=2e-3, atol=2e-4 * np.abs(r[k]).max(), err_msg=k)
+        assert _rel(d[k], r[k]) < 2e-4, (k, _rel(d[k], r[k]))
     # solveSystemF (the reference's code on both sides) on top of the replaced accumulators, then the replaced resubstituteF_MT.
     # The reduced system is ill-conditioned (gauge directions): the solution amplifies the accumulators' 1e-7 differences
     assert _rel(d["HS"], r["HS"]) < 3e-6 and _rel(d["bS"], r["bS"]) < 1e-4
@@ -76,8 +78,9 @@ def _check_ct(d, r):
     for l in range(L):
         for ci in range(2):
             np.testing.assert_allclose(d[f"res_{l}_{ci}"], r[f"res_{l}_{ci}"], rtol=2e-5, atol=1e-6)   # calcRes Vec6 (counts equal, energies fp32 sums)
+            # the bounds of tests/test_gpu_coarse.py: H 2e-5, b 2e-4 (b is a sum of signed terms)
             np.testing.assert_allclose(d[f"H_{l}_{ci}"], r[f"H_{l}_{ci}"], rtol=0, atol=2e-5 * np.nanmax(np.abs(r[f"H_{l}_{ci}"]), initial=0) + 1e-30, equal_nan=True)
-            np.testing.assert_allclose(d[f"b_{l}_{ci}"], r[f"b_{l}_{ci}"], rtol=0, atol=2e-5 * np.nanmax(np.abs(r[f"b_{l}_{ci}"]), initial=0) + 1e-30, equal_nan=True)
+            np.testing.assert_allclose(d[f"b_{l}_{ci}"], r[f"b_{l}_{ci}"], rtol=0, atol=2e-4 * np.nanmax(np.abs(r[f"b_{l}_{ci}"]), initial=0) + 1e-30, equal_nan=True)
     # the reference's own trackNewestCoarse loop, every evaluation served by the stubs
     assert int(d["good"]) == int(r["good"])
     np.testing.assert_allclose(d["R"], r["R"], rtol=0, atol=2e-6)
@@ -85,6 +88,31 @@ def _check_ct(d, r):
     np.testing.assert_allclose(d["ab"], r["ab"], rtol=0, atol=2e-4)
     np.testing.assert_allclose(d["lastResiduals"], r["lastResiduals"], rtol=2e-4, equal_nan=True)
     np.testing.assert_allclose(d["flow"], r["flow"], rtol=2e-3, atol=1e-4)
+
+
+def _check_ci(d, r):
+    L = int(r["levels"])
+    for lvl in range(L):
+        same = d[f"calc_{lvl}_good"] == r[f"calc_{lvl}_good"]
+        assert same.mean() > 0.995
+        np.testing.assert_allclose(d[f"calc_{lvl}_energy"][same], r[f"calc_{lvl}_energy"][same], rtol=5e-5, atol=1e-5)
+        if same.all():
+            for k, tol in (("H", 5e-5), ("Hsc", 5e-5), ("b", 5e-4), ("bsc", 5e-4)):
+                assert _rel(d[f"calc_{lvl}_{k}"], r[f"calc_{lvl}_{k}"]) < tol, (lvl, k, _rel(d[f"calc_{lvl}_{k}"], r[f"calc_{lvl}_{k}"]))
+            np.testing.assert_allclose(d[f"calc_{lvl}_res"], r[f"calc_{lvl}_res"], rtol=5e-5)
+    # the reference's own trackFrame on top: same decisions (ok / snapped / snappedAt / frameID), same poses to float accumulation order
+    for k in range(6):
+        np.testing.assert_array_equal(d[f"trk_{k}_state"], r[f"trk_{k}_state"], err_msg=f"frame {k}")
+        np.testing.assert_allclose(d[f"trk_{k}_R"], r[f"trk_{k}_R"], rtol=0, atol=5e-5)
+        np.testing.assert_allclose(d[f"trk_{k}_t"], r[f"trk_{k}_t"], rtol=0, atol=5e-4 * max(1e-2, np.abs(r[f"trk_{k}_t"]).max()))
+        np.testing.assert_allclose(d[f"trk_{k}_ab"], r[f"trk_{k}_ab"], rtol=0, atol=2e-3)
+    assert r["trk_5_state"][1] == 1   # the initialiser snapped
+    same = d["final_isGood"] == r["final_isGood"]
+    assert same.mean() > 0.99
+    assert np.median(np.abs(d["final_idepth"][same] - r["final_idepth"][same]) / np.abs(r["final_idepth"][same])) < 2e-4
+
+
+_CHECK = {"ba": _check_ba, "ct": _check_ct, "ci": _check_ci}
 
 
 @pytest.fixture(scope="module")
@@ -104,14 +132,14 @@ def ref_results():
     return get
 
 
-@pytest.mark.parametrize("case", ["ba:c1", "ba:states", "ct:small"])
+@pytest.mark.parametrize("case", ["ba:c1", "ba:states", "ct:small", "ci:many"])
 def test_dropin_on_cpu_stand_in(ref_results, tmp_path, case):
     d, r = _run_dropin(case, tmp_path, mock=True), ref_results(case)
-    (_check_ba if case.startswith("ba") else _check_ct)(d, r)
+    _CHECK[case.split(":")[0]](d, r)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["ba:c1", "ba:c3", "ba:states", "ct:small", "ct:vga"])
+@pytest.mark.parametrize("case", ["ba:c1", "ba:c3", "ba:states", "ct:small", "ct:vga", "ci:many"])
 def test_dropin_on_cuda_library(ref_results, tmp_path, case):
     d, r = _run_dropin(case, tmp_path, mock=False), ref_results(case)
-    (_check_ba if case.startswith("ba") else _check_ct)(d, r)
+    _CHECK[case.split(":")[0]](d, r)

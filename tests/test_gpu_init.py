@@ -1,0 +1,94 @@
+"""CoarseInitializer::calcResAndGS on the device (dm-vio_b200/csrc/ci_kernels.cu through dmv_ci_*) against the CPU oracle
+(oracle/orc_init.cpp, pinned bit-exact per point against the reference's compiled CoarseInitializer.cpp by tests/test_ref_pin.py).
+Per-point results: fp32 with a different contraction (FMA) than the CPU build -> 2e-5 relative; point verdicts must agree except for exact ties
+of the outlier threshold; the summed 8x8 systems agree to float summation order (the reference's own multi-threaded sums are not reproducible
+beyond that, tests/test_ref_pin.py::test_coarse_initializer_matches_reference[many_points])."""
+import numpy as np
+import pytest
+
+from helpers import init_points, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _se3_log_translation(R, t):
+    """first three entries of Sophus::SE3::log(): V^-1 t"""
+    R = np.asarray(R, np.float64); t = np.asarray(t, np.float64)
+    th = np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1))
+    if th < 1e-10:
+        return t.copy()
+    w = th / (2 * np.sin(th)) * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    V = np.eye(3) + (1 - np.cos(th)) / th ** 2 * W + (th - np.sin(th)) / th ** 3 * (W @ W)
+    return np.linalg.solve(V, t)
+
+
+@pytest.mark.parametrize("counts", [(48, 40, 30, 20), (3000, 900, 300, 100)], ids=["few_points", "many_points"])
+def test_calc_res_and_gs_parity(orc, synth, counts):
+    import dmvio_b200.capi as capi
+    T = synth.make_tracking_pair(seed=77, trans=0.02, rot=0.005)
+    w, h, L = T["w"], T["h"], T["levels"]
+    rng = np.random.default_rng(5)
+    pts = init_points(rng, w, h, L, counts)
+    oc = orc.CoarseInit(w, h, T["K"])
+    assert oc.levels == L
+    oc.set_first(T["pyr_ref"], 1.0, pts)
+    oc.set_new(T["pyr_new"], 1.2)
+    g = capi.CI(w, h, L, max_points=max(counts) + 8)
+    for l in range(L):
+        k4, wh = oc.K(l)
+        g.set_K(l, *[float(x) for x in k4])
+        g.upload_first(l, T["pyr_ref"][l])
+        g.upload_new(l, T["pyr_new"][l])
+        u, v, th = oc.static_fields(l)
+        g.set_points(l, u, v, th)
+    R, t = synth.se3_exp(np.array([0.004, -0.003, 0.002, 0.002, -0.001, 0.0015]))
+    inc = np.array([1e-3, -2e-3, 5e-4, 1e-3, 2e-3, -1e-3, 0.0, 0.0], np.float32)
+    checked_bad = 0
+    for lvl in range(L - 1, -1, -1):
+        n = len(pts[lvl]["u"])
+        # three states of the level: fresh (idepth 1), a small motion, and after applyStep + a depth step (doStep) with some points bad
+        for step, (RR, tt, a, b) in enumerate(((np.eye(3), np.zeros(3), 0.0, 0.0), (R, t, np.log(1.2), 0.3), (R, t, np.log(1.2), 0.3))):
+            if step == 2:
+                oc.apply_step(lvl)
+                oc.do_step(lvl, 0.1, inc)
+            p_in = oc.points(lvl)                                   # the live fields the caller passes (before this evaluation)
+            so = oc.calc(lvl, RR, tt, a, b)
+            p_out, jb_o = oc.points(lvl), oc.jb(lvl)
+            k4, _ = oc.K(lvl)
+            K = np.array([[k4[0], 0, k4[2]], [0, k4[1], k4[3]], [0, 0, 1.0]])
+            RKi = (np.asarray(RR, np.float64) @ np.linalg.inv(K)).astype(np.float32)
+            sg = g.calc_res_and_gs(lvl, RKi, tt, _se3_log_translation(RR, tt), (np.float32(np.exp(a)), np.float32(b)), p_in["idepth_new"],
+                                   p_in["isGood"].astype(np.uint8), np.stack([p_in["energy0"], p_in["energy1"]], 1), p_in["iR"])
+            good_o, good_g = p_out["isGood_new"].astype(bool), sg["isGood_new"].astype(bool)
+            flips = np.nonzero(good_o != good_g)[0]
+            assert len(flips) <= max(1, n // 500), (lvl, step, len(flips))   # threshold ties only
+            both = good_o & good_g
+            assert both.sum() > 0.5 * n
+            checked_bad += int((~good_o).sum())
+            np.testing.assert_allclose(sg["energy_new"][both, 0], p_out["energy_new0"][both], rtol=2e-5, atol=1e-6)
+            np.testing.assert_allclose(sg["energy_new"][:, 1][good_o == good_g], p_out["energy_new1"][good_o == good_g], rtol=2e-5, atol=1e-7)
+            np.testing.assert_allclose(sg["energy_new"][~good_g & ~good_o, 0], p_out["energy_new0"][~good_g & ~good_o], rtol=0, atol=0)
+            np.testing.assert_allclose(sg["maxstep"][both], p_out["maxstep"][both], rtol=2e-5)
+            np.testing.assert_allclose(sg["lastHessian_new"][both], p_out["lastHessian_new"][both], rtol=5e-5, atol=1e-6)
+            scale = np.abs(jb_o[both]).max(axis=0) + 1e-12
+            assert (np.abs(sg["Jb"][both] - jb_o[both]) / scale).max() < 5e-5
+            if len(flips) == 0:
+                for k, tol in (("H", 2e-5), ("Hsc", 2e-5), ("b", 2e-4), ("bsc", 2e-4)):
+                    assert rel(sg[k], so[k]) < tol, (lvl, step, k, rel(sg[k], so[k]))
+                np.testing.assert_allclose(sg["res"], so["res"], rtol=2e-5)
+                assert sg["n_good_new"] == int(good_o.sum())
+            assert np.abs(sg["H"] - sg["H"].T).max() == 0
+    assert checked_bad > 0   # the not-good branch (energy carried over, no contribution) was exercised
+    g.close()
+
+
+def test_init_handle_errors(synth):
+    import dmvio_b200.capi as capi
+    g = capi.CI(64, 48, 2, max_points=16)
+    with pytest.raises(capi.DmvError):
+        g.set_points(0, np.zeros(17, np.float32), np.zeros(17, np.float32), np.zeros(17, np.float32))   # over capacity
+    g.set_points(0, np.full(4, 10.1, np.float32), np.full(4, 10.1, np.float32), np.full(4, 100.0, np.float32))
+    with pytest.raises(capi.DmvError):   # no K / frames yet
+        g.calc_res_and_gs(0, np.eye(3), np.zeros(3), np.zeros(3), (1.0, 0.0), np.ones(4), np.ones(4), np.zeros((4, 2)), np.ones(4))
+    g.close()
