@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(CI_THREADS) ci_res_gs_kernel(const __grid_cons
           J[8] = hw * residual;
           dd = dxI * dxdd + dyI * dydd;
           const float mx = dxdd * P.fx, my = dydd * P.fy;
-          mstep = 1.0f / sqrtf(mx * mx + my * my);
+          mstep = fminf(1e10f, 1.0f / sqrtf(mx * mx + my * my));   // `if (maxstep < point->maxstep)` from 1e10 (L371, L447-448)
         }
       }
     }

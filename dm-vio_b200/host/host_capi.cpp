@@ -71,6 +71,19 @@ void dmvh_window_set_ba_update_hook(void* p, dmvh_ba_update_cb cb, void* user) {
     return x;
   };
 }
+int dmvh_window_set_sharding(void* p, int rank, int nranks, dmvh_allgather_cb cb, void* user) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  if (cb) W->allgather = [cb, user](const void* send, void* recv, size_t bytes) { cb(send, recv, bytes, user); };
+  else W->allgather = nullptr;
+  return W->setSharding(rank, nranks) ? 0 : -1;
+}
+int dmvh_window_p2p_setup(void* p) { return static_cast<WindowBA*>(p)->p2pSetup() ? 0 : -1; }
+int dmvh_window_comm_init(void* p, const void* uid) { return static_cast<WindowBA*>(p)->commInit(uid) ? 0 : -1; }
+int dmvh_window_get_idepths(void* p, float* idepth) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  W->getIdepths(idepth);
+  return W->error().empty() ? 0 : -1;
+}
 int dmvh_window_set_setting(void* p, const char* name, double value) {
   Settings& s = static_cast<WindowBA*>(p)->s;
   const std::string n(name);

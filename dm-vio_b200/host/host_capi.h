@@ -1,6 +1,7 @@
 /* C glue over the C++ host adapters (WindowBA, CoarseTracker) so that the Python tests and bench can drive them through
  * ctypes.  Not part of the drop-in boundary (that is include/dmvio_b200.h); a C++ host links the classes directly. */
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -21,6 +22,13 @@ int dmvh_window_set_residuals(void* win, int n, const int32_t* point, const int3
 /* installs WindowBA::computeBAUpdate (the slot of BAGTSAMIntegration::computeBAUpdate): cb(H N*N, b N, lambda, nFrames, HNoLambda N*N, x_out N, user); NULL removes it */
 typedef void (*dmvh_ba_update_cb)(const double* H, const double* b, double lambda, int nFrames, const double* HNoLambda, double* x_out, void* user);
 void dmvh_window_set_ba_update_hook(void* win, dmvh_ba_update_cb cb, void* user);
+/* multi-GPU: WindowBA::setSharding + the application's host allgather (send `bytes`, receive nranks*bytes in rank order); call before
+ * dmvh_window_prepare.  dmvh_window_p2p_setup / dmvh_window_comm_init choose the device-side exchange (NVLink peer memory / NCCL). */
+typedef void (*dmvh_allgather_cb)(const void* send, void* recv_all, size_t bytes, void* user);
+int dmvh_window_set_sharding(void* win, int rank, int nranks, dmvh_allgather_cb cb, void* user);
+int dmvh_window_p2p_setup(void* win);
+int dmvh_window_comm_init(void* win, const void* nccl_unique_id128);
+int dmvh_window_get_idepths(void* win, float* idepth);
 /* WindowBA::s.<name> = value for the settings the optimisation loop reads (minOptIterations, thOptIterations, margWeightFac, ...); 0 ok, -1 unknown */
 int dmvh_window_set_setting(void* win, const char* name, double value);
 int dmvh_window_prepare(void* win); /* makeIDX + setAdjointsF + setPrecalcValues */

@@ -120,7 +120,7 @@ bool WindowBA::marginalizeFrame(int idx) {
     const int nr = (int)activeResiduals.size(), np = (int)points.size();
     std::vector<int32_t> ns(nr);
     std::vector<float> ne(nr);
-    if (nr > 0 && dmv_ba_get_residual_outputs(ba_, ns.data(), ne.data(), nullptr, nullptr, nullptr) == DMV_OK) {
+    if (nr > 0 && fetchResidualOutputs(ns.data(), ne.data(), nullptr, nullptr)) {
       int w = 0;
       for (int i = 0; i < nr; i++)
         if (activeResiduals[i].target != idx) { rkeep[w].state_state = ns[i]; rkeep[w].state_energy = ne[i]; w++; }
@@ -170,7 +170,7 @@ void WindowBA::insertResiduals(int n, const int* point, const int* target) {
 bool WindowBA::makeIDX() {
   err_.clear();  // per-call status: an earlier, already reported failure must not fail this call
   if (!ba_) return false;
-  const int n = nf(), np = (int)points.size(), nr = (int)activeResiduals.size();
+  const int n = nf(), np = (int)points.size();
   std::vector<int> slots(n);
   for (int f = 0; f < n; f++) slots[f] = frameHessians[f].slot;
   if (dmv_ba_set_window(ba_, n, slots.data()) != DMV_OK) return fail("dmv_ba_set_window");
@@ -178,19 +178,30 @@ bool WindowBA::makeIDX() {
   prm.huberTH = s.setting_huberTH; prm.outlierTHSumComponent = s.setting_outlierTHSumComponent;
   prm.affineOptModeA = s.setting_affineOptModeA; prm.affineOptModeB = s.setting_affineOptModeB;
   dmv_ba_set_params(ba_, &prm);
-  std::vector<int32_t> host(np);
-  std::vector<float> u(np), v(np), id(np), idz(np), col((size_t)np * 8), wgt((size_t)np * 8), prior(np);
-  for (int i = 0; i < np; i++) {
-    const PointHessian& p = points[i];
+  // the share of every rank (round robin over the point index keeps the per-host-frame load even; one rank = everything)
+  pts_of_rank_.assign(nranks_, std::vector<int>());
+  local_of_point_.assign(np, 0);
+  for (int i = 0; i < np; i++) { std::vector<int>& l = pts_of_rank_[i % nranks_]; local_of_point_[i] = (int)l.size(); l.push_back(i); }
+  rebuildResidualMaps();
+  const std::vector<int>& mine = pts_of_rank_[rank_];
+  const std::vector<int>& mres = res_of_rank_[rank_];
+  const int lp = (int)mine.size(), lr = (int)mres.size();
+  std::vector<int32_t> host(lp);
+  std::vector<float> u(lp), v(lp), id(lp), idz(lp), col((size_t)lp * 8), wgt((size_t)lp * 8), prior(lp);
+  for (int i = 0; i < lp; i++) {
+    const PointHessian& p = points[mine[i]];
     host[i] = p.host; u[i] = p.u; v[i] = p.v; id[i] = p.idepth; idz[i] = p.idepth_zero; prior[i] = p.priorF;
     for (int k = 0; k < 8; k++) { col[(size_t)8 * i + k] = p.color[k]; wgt[(size_t)8 * i + k] = p.weights[k]; }
   }
-  if (dmv_ba_set_points(ba_, np, host.data(), u.data(), v.data(), id.data(), idz.data(), col.data(), wgt.data(), prior.data()) != DMV_OK)
+  if (dmv_ba_set_points(ba_, lp, host.data(), u.data(), v.data(), id.data(), idz.data(), col.data(), wgt.data(), prior.data()) != DMV_OK)
     return fail("dmv_ba_set_points");
-  std::vector<int32_t> rp(nr), rt(nr), rs(nr);
-  std::vector<float> re(nr);
-  for (int i = 0; i < nr; i++) { rp[i] = activeResiduals[i].point; rt[i] = activeResiduals[i].target; rs[i] = activeResiduals[i].state_state; re[i] = activeResiduals[i].state_energy; }
-  if (dmv_ba_set_residuals(ba_, nr, rp.data(), rt.data(), rs.data(), re.data()) != DMV_OK) return fail("dmv_ba_set_residuals");
+  std::vector<int32_t> rp(lr), rt(lr), rs(lr);
+  std::vector<float> re(lr);
+  for (int i = 0; i < lr; i++) {
+    const PointFrameResidual& r = activeResiduals[mres[i]];
+    rp[i] = local_of_point_[r.point]; rt[i] = r.target; rs[i] = r.state_state; re[i] = r.state_energy;
+  }
+  if (dmv_ba_set_residuals(ba_, lr, rp.data(), rt.data(), rs.data(), re.data()) != DMV_OK) return fail("dmv_ba_set_residuals");
   const int N = 8 * n + CPARS;
   if ((int)HM.size() != N * N) { HM.assign((size_t)N * N, 0.0); bM.assign(N, 0.0); }
   have_pending_x_ = false;
@@ -304,12 +315,12 @@ int WindowBA::marginalizePointsF(const std::vector<int>& toMargIn, const std::ve
   // PointHessian::idepth_hessian is written by AccumulatedSCHessian::addPoint only (AccumulatedSCHessian.cpp:L42-50), i.e. during the LAST
   // solveSystemF — not by the tail's linearizeAll(true): use the HdiF cached there (no solve yet: idepth_hessian = 0, candidates are dropped)
   std::vector<float> HdiF(np, 0.f);
-  if (np > 0 && solved_since_makeIDX_ && dmv_ba_get_solve_HdiF(ba_, HdiF.data()) != DMV_OK) { fail("dmv_ba_get_solve_HdiF"); return -1; }
+  if (np > 0 && solved_since_makeIDX_ && !fetchPointFloats(1, HdiF.data())) { fail("dmv_ba_get_solve_HdiF"); return -1; }
   {  // the residual states live on the device (applyRes_Reductor commits there): pull them for the re-upload below
     const int nr = (int)activeResiduals.size();
     std::vector<int32_t> ns(nr);
     std::vector<float> ne(nr);
-    if (nr > 0 && dmv_ba_get_residual_outputs(ba_, ns.data(), ne.data(), nullptr, nullptr, nullptr) == DMV_OK)
+    if (nr > 0 && fetchResidualOutputs(ns.data(), ne.data(), nullptr, nullptr))
       for (int i = 0; i < nr; i++) { activeResiduals[i].state_state = ns[i]; activeResiduals[i].state_energy = ne[i]; }
   }
   std::vector<int32_t> toMarg;
@@ -326,7 +337,10 @@ int WindowBA::marginalizePointsF(const std::vector<int>& toMargIn, const std::ve
     const std::vector<float> ad = adHTdeltaF();
     std::vector<double> M((size_t)N * N), Mb(N), Msc((size_t)N * N), Mbsc(N);
     dmv_ba_marg_args a;
-    a.n = (int32_t)toMarg.size(); a.point = toMarg.data(); a.adHTdeltaF = ad.data();
+    // sharded: every rank marginalises ITS flagged points (possibly none); M / Msc come back summed over the ranks
+    std::vector<int32_t> toMargLocal;
+    for (int32_t i : toMarg) if (i % nranks_ == rank_) toMargLocal.push_back(local_of_point_[i]);
+    a.n = (int32_t)toMargLocal.size(); a.point = toMargLocal.data(); a.adHTdeltaF = ad.data();
     for (int i = 0; i < 4; i++) a.cDeltaF[i] = (float)Hcalib.value_minus_value_zero[i];
     a.idepthFixPriorMargFac = s.setting_idepthFixPriorMargFac;
     a.M = M.data(); a.Mb = Mb.data(); a.Msc = Msc.data(); a.Mbsc = Mbsc.data();
@@ -415,7 +429,9 @@ double WindowBA::linearizeAll(bool fixLinearization) {
   }
   lastRemovedResiduals.assign(toRemove.begin(), toRemove.end());
   if (!toRemove.empty()) {
-    if (dmv_ba_drop_residuals(ba_, (int)toRemove.size(), toRemove.data()) != DMV_OK) { fail("dmv_ba_drop_residuals"); return NAN; }
+    std::vector<int32_t> dropLocal;   // the device holds this rank's residuals only
+    for (int i : toRemove) if (activeResiduals[i].point % nranks_ == rank_) dropLocal.push_back(local_of_res_[i]);
+    if (!dropLocal.empty() && dmv_ba_drop_residuals(ba_, (int)dropLocal.size(), dropLocal.data()) != DMV_OK) { fail("dmv_ba_drop_residuals"); return NAN; }
     std::vector<char> gone(nr, 0);
     for (int i : toRemove) {
       gone[i] = 1;
@@ -428,6 +444,7 @@ double WindowBA::linearizeAll(bool fixLinearization) {
     for (int i = 0; i < nr; i++)
       if (!gone[i]) activeResiduals[w++] = activeResiduals[i];
     activeResiduals.resize(w);
+    rebuildResidualMaps();   // the device kept the relative order of the remaining residuals: the same rule gives the same local indices
   }
   return r.energy;
 }
@@ -476,7 +493,16 @@ void WindowBA::flagPointsForRemoval(const std::vector<int>& flaggedFrames, std::
 void WindowBA::setNewFrameEnergyTH() {  // FullSystemOptimize.cpp:L96-149 (no IMU cap)
   std::vector<float> allResVec(points.size() + 1);
   int n = 0;
-  if (dmv_ba_get_target_energies(ba_, nf() - 1, allResVec.data(), (int)allResVec.size(), &n) != DMV_OK) { fail("dmv_ba_get_target_energies"); return; }
+  if (nranks_ == 1) {
+    if (dmv_ba_get_target_energies(ba_, nf() - 1, allResVec.data(), (int)allResVec.size(), &n) != DMV_OK) { fail("dmv_ba_get_target_energies"); return; }
+  } else {  // the percentile is over the residuals of ALL ranks: gather state_NewEnergyWithOutlier, keep the evaluated ones that target the newest frame
+    const int nr = (int)activeResiduals.size();
+    std::vector<float> nw(nr);
+    if (nr > 0 && !fetchResidualOutputs(nullptr, nullptr, nw.data(), nullptr)) { fail("dmv_ba_get_residual_outputs"); return; }
+    allResVec.resize(nr + 1);
+    for (int i = 0; i < nr; i++)
+      if (activeResiduals[i].target == nf() - 1 && nw[i] >= 0) allResVec[n++] = nw[i];
+  }
   FrameHessian& newFrame = frameHessians.back();
   if (n == 0) { newFrame.frameEnergyTH = 12 * 12 * patternNum; return; }
   allResVec.resize(n);
@@ -669,14 +695,88 @@ void WindowBA::syncResidualStates() {
   const int nr = (int)activeResiduals.size();
   std::vector<int32_t> ns(nr);
   std::vector<float> ne(nr), nw(nr), cp((size_t)nr * 3);
-  if (dmv_ba_get_residual_outputs(ba_, ns.data(), ne.data(), nw.data(), cp.data(), nullptr) != DMV_OK) { fail("dmv_ba_get_residual_outputs"); return; }
+  if (!fetchResidualOutputs(ns.data(), ne.data(), nw.data(), cp.data())) { fail("dmv_ba_get_residual_outputs"); return; }
   for (int i = 0; i < nr; i++) {
     PointFrameResidual& r = activeResiduals[i];
     r.state_NewState = ns[i]; r.state_NewEnergy = ne[i]; r.state_NewEnergyWithOutlier = nw[i];
     for (int k = 0; k < 3; k++) r.centerProjectedTo[k] = cp[(size_t)3 * i + k];
   }
 }
-void WindowBA::getIdepths(float* idepth) { dmv_ba_get_idepth(ba_, idepth, nullptr); }
+void WindowBA::getIdepths(float* idepth) { fetchPointFloats(0, idepth); }
+
+// ---- sharding
+void WindowBA::rebuildResidualMaps() {
+  const int nr = (int)activeResiduals.size();
+  res_of_rank_.assign(nranks_, std::vector<int>());
+  local_of_res_.assign(nr, 0);
+  for (int i = 0; i < nr; i++) { std::vector<int>& l = res_of_rank_[activeResiduals[i].point % nranks_]; local_of_res_[i] = (int)l.size(); l.push_back(i); }
+}
+bool WindowBA::setSharding(int rank, int nranks) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail("setSharding: bad rank / nranks");
+  rank_ = rank; nranks_ = nranks;
+  return true;
+}
+bool WindowBA::p2pExport(void* h64) { return dmv_ba_p2p_export(ba_, h64) == DMV_OK || fail("dmv_ba_p2p_export"); }
+bool WindowBA::p2pImport(const void* handles) { return dmv_ba_p2p_import(ba_, nranks_, rank_, handles) == DMV_OK || fail("dmv_ba_p2p_import"); }
+bool WindowBA::p2pSetup() {
+  if (nranks_ == 1) return true;
+  if (!allgather) return fail("sharded WindowBA needs the allgather callback");
+  unsigned char mine[64];
+  std::vector<unsigned char> all((size_t)64 * nranks_);
+  if (!p2pExport(mine)) return false;
+  allgather(mine, all.data(), 64);
+  return p2pImport(all.data());
+}
+bool WindowBA::commInit(const void* uid) { return dmv_ba_comm_init(ba_, nranks_, rank_, uid) == DMV_OK || fail("dmv_ba_comm_init"); }
+
+// every rank contributes its rows (local order), padded to the largest share; the result is scattered to global indices
+template <class T> bool WindowBA::gatherRows(const std::vector<std::vector<int>>& of_rank, const T* local, int width, T* global) {
+  if (nranks_ == 1) {
+    const std::vector<int>& l = of_rank[0];
+    for (size_t i = 0; i < l.size(); i++) for (int k = 0; k < width; k++) global[(size_t)l[i] * width + k] = local[i * width + k];
+    return true;
+  }
+  if (!allgather) return fail("sharded WindowBA needs the allgather callback");
+  size_t mx = 0;
+  for (const std::vector<int>& l : of_rank) mx = std::max(mx, l.size());
+  if (mx == 0) return true;
+  std::vector<T> send(mx * width, T(0)), recv(mx * width * nranks_);
+  std::copy(local, local + of_rank[rank_].size() * width, send.begin());
+  allgather(send.data(), recv.data(), sizeof(T) * mx * width);
+  for (int r = 0; r < nranks_; r++) {
+    const std::vector<int>& l = of_rank[r];
+    const T* src = recv.data() + (size_t)r * mx * width;
+    for (size_t i = 0; i < l.size(); i++) for (int k = 0; k < width; k++) global[(size_t)l[i] * width + k] = src[i * width + k];
+  }
+  return true;
+}
+
+bool WindowBA::fetchResidualOutputs(int32_t* newState, float* newEnergy, float* newEnergyWithOutlier, float* cpt3) {
+  if (res_of_rank_.empty()) return false;
+  const int lr = (int)res_of_rank_[rank_].size();
+  std::vector<int32_t> ns(lr);
+  std::vector<float> ne(lr), nw(lr), cp((size_t)lr * 3);
+  if (lr > 0 && dmv_ba_get_residual_outputs(ba_, newState ? ns.data() : nullptr, newEnergy ? ne.data() : nullptr, newEnergyWithOutlier ? nw.data() : nullptr,
+                                             cpt3 ? cp.data() : nullptr, nullptr) != DMV_OK)
+    return false;
+  bool ok = true;
+  if (newState) ok = gatherRows(res_of_rank_, ns.data(), 1, newState) && ok;
+  if (newEnergy) ok = gatherRows(res_of_rank_, ne.data(), 1, newEnergy) && ok;
+  if (newEnergyWithOutlier) ok = gatherRows(res_of_rank_, nw.data(), 1, newEnergyWithOutlier) && ok;
+  if (cpt3) ok = gatherRows(res_of_rank_, cp.data(), 3, cpt3) && ok;
+  return ok;
+}
+
+bool WindowBA::fetchPointFloats(int what, float* out) {
+  if (pts_of_rank_.empty()) return false;
+  const int lp = (int)pts_of_rank_[rank_].size();
+  std::vector<float> loc(lp);
+  if (lp > 0) {
+    const int rc = what == 0 ? dmv_ba_get_idepth(ba_, loc.data(), nullptr) : dmv_ba_get_solve_HdiF(ba_, loc.data());
+    if (rc != DMV_OK) return false;
+  }
+  return gatherRows(pts_of_rank_, loc.data(), 1, out);
+}
 void WindowBA::getFrameStates(double* st) const {
   for (int f = 0; f < nf(); f++) for (int i = 0; i < 10; i++) st[10 * f + i] = frameHessians[f].state[i];
 }

@@ -157,6 +157,22 @@ class WindowBA {
   std::vector<float> adHTdeltaF() const;   // EnergyFunctional::setDeltaF (EnergyFunctional.cpp:L175-187), [h + t*nf][8]
   int resInM = 0;
 
+  // ---- multi-GPU: one WindowBA per rank / GPU.  Every rank holds the WHOLE window on the host (frames, point and residual
+  // lists, priors: small) and uploads only its share of the points (index % nranks == rank) with their residuals; the linearised system,
+  // energies and counters are summed over the ranks inside the launch (peer memory or NCCL, dmv_ba_p2p_* / dmv_ba_comm_init), so every rank
+  // takes the identical LM decisions and steps.  Per-point / per-residual results live on the owning rank's device; where the host logic needs
+  // them for ALL points (setNewFrameEnergyTH's percentile, flagPointsForRemoval, residual removal, depth read-back) the adapter gathers them
+  // with `allgather`, supplied by the application's host communicator (MPI_Allgather / torch.distributed / ...): send `bytes` bytes, receive
+  // nranks * bytes in rank order.  Call setSharding before makeIDX; the exchange set-up calls forward to the C ABI.
+  std::function<void(const void* send, void* recv_all, size_t bytes)> allgather;
+  bool setSharding(int rank, int nranks);
+  bool p2pExport(void* ipc_handle64);                      // dmv_ba_p2p_export
+  bool p2pImport(const void* ipc_handles);                 // dmv_ba_p2p_import(nranks, rank, handles)
+  bool commInit(const void* nccl_unique_id);               // dmv_ba_comm_init (NCCL fallback)
+  bool p2pSetup();                                         // export -> allgather of the 64-byte handles -> import
+  int rank() const { return rank_; }
+  int nranks() const { return nranks_; }
+
   // ---- results
   void syncResidualStates();           // pulls state_NewState / energies / centerProjectedTo of the last linearisation from the device
   void getIdepths(float* idepth);      // current device depths
@@ -180,6 +196,15 @@ class WindowBA {
   std::vector<double> pending_x_;
   double step_sums_[3] = {0, 0, 0};
   bool solved_since_makeIDX_ = false;  // dmv_ba_get_solve_HdiF is valid
+  // sharding: global index of every local point / residual, per rank (the same lists on every rank)
+  int rank_ = 0, nranks_ = 1;
+  std::vector<std::vector<int>> pts_of_rank_, res_of_rank_;
+  std::vector<int> local_of_point_, local_of_res_;   // global -> local index on the owning rank
+  void rebuildResidualMaps();
+  // device read-backs in GLOBAL indexing (gathered over the ranks when sharded); any pointer may be null
+  bool fetchResidualOutputs(int32_t* newState, float* newEnergy, float* newEnergyWithOutlier, float* cpt3);
+  bool fetchPointFloats(int what, float* out);   // 0: idepth, 1: HdiF of the last solve
+  template <class T> bool gatherRows(const std::vector<std::vector<int>>& of_rank, const T* local, int width, T* global);
   float canbreak_frames_[4] = {0, 0, 0, 0};
 };
 

@@ -46,6 +46,9 @@ def _bind(L):
         L.dmvh_window_set_points_carry.argtypes = [vp, C.c_int, i32p, f32p, f32p, f32p, f32p, f32p, f32p, vp, i32p]
         L.dmvh_window_set_residuals.argtypes = [vp, C.c_int, i32p, i32p]
         L.dmvh_window_prepare.argtypes = [vp]
+        L.dmvh_window_set_sharding.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+        L.dmvh_window_p2p_setup.argtypes = [vp]
+        L.dmvh_window_comm_init.argtypes = [vp, vp]
         L.dmvh_window_linearize.restype = C.c_double
         L.dmvh_window_linearize.argtypes = [vp, C.c_int]
         L.dmvh_window_apply.argtypes = [vp]
@@ -96,10 +99,15 @@ def marginalize_frame_hm(HM, bM, nframes, idx, prior8, delta_prior8):
     return H[:n * n].reshape(n, n).copy(), b[:n].copy()
 
 
+ALLGATHER_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
 class WindowBA:
     """dmvio_b200::WindowBA loaded from a synth.make_window() dict."""
 
-    def __init__(self, W, device=0, use_device_pyramid=False):
+    def __init__(self, W, device=0, use_device_pyramid=False, shard=None):
+        """shard (multi-GPU, one WindowBA per rank): dict(rank, nranks, allgather=f(bytes) -> bytes of all ranks in rank order,
+        exchange="p2p" | "nccl", uid=NCCL unique id for "nccl").  Every rank passes the SAME window."""
         self.L = lib()
         self.nf, self.npts, self.nres = W["nf"], len(W["host"]), len(W["res_point"])
         self.N = 8 * self.nf + 4
@@ -113,6 +121,18 @@ class WindowBA:
         self.L.dmvh_window_set_points(self.h, self.npts, _c(W["host"], np.int32), _c(W["u"], np.float32), _c(W["v"], np.float32), _c(W["idepth"], np.float32),
                                       _c(W["idepth_zero"], np.float32), _c(W["color"], np.float32).reshape(-1), _c(W["weights"], np.float32).reshape(-1), None)
         self.L.dmvh_window_set_residuals(self.h, len(W["res_point"]), _c(W["res_point"], np.int32), _c(W["res_target"], np.int32))
+        if shard is not None:
+            ag = shard["allgather"]
+
+            def _cb(send, recv, nbytes, user):
+                allb = ag(C.string_at(send, nbytes))
+                C.memmove(recv, allb, len(allb))
+            self._ag_cb = ALLGATHER_CB(_cb)   # keep alive as long as the window
+            if self.L.dmvh_window_set_sharding(self.h, int(shard["rank"]), int(shard["nranks"]), C.cast(self._ag_cb, vp), None) != 0:
+                raise capi.DmvError(self.L.dmvh_window_error(self.h).decode())
+            rc = self.L.dmvh_window_comm_init(self.h, shard["uid"]) if shard.get("exchange", "p2p") == "nccl" else self.L.dmvh_window_p2p_setup(self.h)
+            if rc != 0:
+                raise capi.DmvError(self.L.dmvh_window_error(self.h).decode())
         if self.L.dmvh_window_prepare(self.h) != 0:
             raise capi.DmvError(self.L.dmvh_window_error(self.h).decode())
 

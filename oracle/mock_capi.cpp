@@ -235,6 +235,10 @@ int dmv_ba_resubstitute(dmv_ba* b, const double* x, float* step_out, int apply, 
   if (sums) { sums[0] = s3[0]; sums[1] = s3[1]; sums[2] = s3[2]; }
   return DMV_OK;
 }
+// the CPU stand-in has no ranks: the exchange set-up entry points exist for the adapter's link, and refuse
+int dmv_ba_p2p_export(dmv_ba*, void*) { return fail(DMV_ERR_STATE, "host-logic mock: no multi-GPU exchange"); }
+int dmv_ba_p2p_import(dmv_ba*, int, int, const void*) { return fail(DMV_ERR_STATE, "host-logic mock: no multi-GPU exchange"); }
+int dmv_ba_comm_init(dmv_ba*, int, int, const void*) { return fail(DMV_ERR_STATE, "host-logic mock: no multi-GPU exchange"); }
 int dmv_ba_apply_res(dmv_ba* b) {
   if (!b->have_tentative) return fail(DMV_ERR_STATE, "no tentative linearisation to commit");
   b->W.applyResAll();

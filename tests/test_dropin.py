@@ -95,7 +95,7 @@ def _check_ci(d, r):
     for lvl in range(L):
         same = d[f"calc_{lvl}_good"] == r[f"calc_{lvl}_good"]
         assert same.mean() > 0.995
-        np.testing.assert_allclose(d[f"calc_{lvl}_energy"][same], r[f"calc_{lvl}_energy"][same], rtol=5e-5, atol=1e-5)
+        np.testing.assert_allclose(d[f"calc_{lvl}_energy"][same], r[f"calc_{lvl}_energy"][same], rtol=3e-4, atol=1e-5)   # squares of differences of O(100) intensities
         if same.all():
             for k, tol in (("H", 5e-5), ("Hsc", 5e-5), ("b", 5e-4), ("bsc", 5e-4)):
                 assert _rel(d[f"calc_{lvl}_{k}"], r[f"calc_{lvl}_{k}"]) < tol, (lvl, k, _rel(d[f"calc_{lvl}_{k}"], r[f"calc_{lvl}_{k}"]))
