@@ -41,7 +41,7 @@ int dmv_ba_fill_descriptor(dmv_ba* b) {
   W.st_new = b->d_st_new[t]; W.en_new = b->d_en_new[t]; W.en_wo = b->d_en_wo[t]; W.cpt = b->d_cpt[t]; W.jpjd = b->d_jpjd[t]; W.pout = b->d_pout[t];
   W.c_st = b->d_st_new[c2]; W.c_jpjd = b->d_jpjd[c2]; W.c_pout = b->d_pout[c2];
   W.step = b->d_step;
-  W.part = b->d_part; W.wg = b->d_wg; W.hdig = b->d_hdig;
+  W.part = b->d_part; W.gpart = b->d_gpart;
   W.bar = b->d_bar;
   W.result = b->d_result[t];
   W.result_host = nullptr;
@@ -140,8 +140,7 @@ static int ba_allocate(dmv_ba* b, const dmv_ba_config* cfg) {
   CK(cudaMalloc(&b->d_step, sizeof(float) * mp));
   CK(cudaMemset(b->d_step, 0, sizeof(float) * mp));
   CK(cudaMalloc(&b->d_part, sizeof(double) * PART_STRIDE * (size_t)b->max_chunks));
-  CK(cudaMalloc(&b->d_wg, sizeof(float4) * (size_t)maxT0 * mp));
-  CK(cudaMalloc(&b->d_hdig, sizeof(float) * mp));
+  CK(cudaMalloc(&b->d_gpart, sizeof(float) * dmv::GP_STRIDE * (size_t)b->max_chunks));
   CK(cudaMalloc(&b->d_hdi_solve, sizeof(float) * mp));
   CK(cudaMalloc(&b->d_bar, sizeof(unsigned int)));
   CK(cudaMemset(b->d_bar, 0, sizeof(unsigned int)));
@@ -169,7 +168,7 @@ int dmv_ba_destroy(dmv_ba* b) {
     cudaFree(b->d_pout[k]); cudaFree(b->d_result[k]); cudaFreeHost(b->h_result[k]);
   }
   cudaFree(b->d_step); cudaFree(b->d_resub_sums); cudaFree(b->d_flush);
-  cudaFree(b->d_part); cudaFree(b->d_wg); cudaFree(b->d_hdig); cudaFree(b->d_hdi_solve); cudaFree(b->d_bar);
+  cudaFree(b->d_part); cudaFree(b->d_gpart); cudaFree(b->d_hdi_solve); cudaFree(b->d_bar);
   cudaFreeHost(b->h_up); cudaFreeHost(b->h_adj); cudaFreeHost(b->h_scratch); cudaFreeHost(b->h_en_newest);
   for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   if (b->nccl_comm) dmv::nccl_destroy(b->nccl_comm);
@@ -391,6 +390,8 @@ static int enqueue_linearize(dmv_ba* b) {
   double* hres = b->h_result[b->tent];
   hres[(size_t)b->N * b->N + b->N + (size_t)b->ntiles * 16 + (ACC_MISC - 1)] = 0.0;  // error flag: written by the device on a timeout only
   if (zero_copy) b->h_up->win.result_host = hres;
+  else  // the NCCL all-reduce sums the device copy of the slot: it must not carry a stale value (e.g. from a window of another size)
+    CK(cudaMemsetAsync(b->d_result[b->tent] + (size_t)b->N * b->N + b->N + (size_t)b->ntiles * 16 + (ACC_MISC - 1), 0, sizeof(double), b->stream));
   HostUpload& U = *b->h_up;
   if (b->timing) CK(cudaEventRecord(b->ev[0], b->stream));
   CK(launch_fused_kernel(U.win, U.it, false, b->stream, &b->bar_count));  // whole linearisation: residuals -> H_top, b_top, [H_sc | b_sc]
@@ -662,6 +663,7 @@ int dmv_ba_marginalize_points(dmv_ba* b, const dmv_ba_marg_args* a) {
   W.result_host = nullptr;
   W.en_wo_newest_host = nullptr;
   W.marg = b->d_marg; W.marg_mask = b->d_marg_mask; W.marg_rtz = b->d_marg_rtz;
+  CK(cudaMemsetAsync(b->d_marg_result + nres_d - 1, 0, sizeof(double), b->stream));   // error slot: written by the device on a timeout only
   CK(launch_fused_kernel(W, b->h_up->it, true, b->stream, &b->bar_count));
   b->launches += 1;
   if (b->nccl_comm && !b->xchg_on) {
@@ -678,6 +680,8 @@ int dmv_ba_marginalize_points(dmv_ba* b, const dmv_ba_marg_args* a) {
   }
   CK(cudaStreamSynchronize(b->stream));
   b->have_tentative = false;  // the tentative buffers now hold the flagged points' re-linearisation only
+  if (b->h_marg_result[nres_d - 1] != 0.0)
+    return set_error(DMV_ERR_TIMEOUT, "grid barrier / peer exchange timed out inside ba_fused_kernel (marginalisation launch)");
   unpack_system(b, b->h_marg_result, a->M, a->Mb, a->Msc, a->Mbsc, nullptr);
   if (a->resInM) *a->resInM = (int)b->h_marg_result[(size_t)N * N + N + (size_t)b->ntiles * 16 + 1];
   std::vector<int> good(b->mp, 0);

@@ -69,10 +69,10 @@ def test_calc_res_and_gs_parity(orc, synth, counts):
             np.testing.assert_allclose(sg["energy_new"][both, 0], p_out["energy_new0"][both], rtol=2e-4, atol=1e-5)   # squares of differences of O(100) intensities
             np.testing.assert_allclose(sg["energy_new"][:, 1][good_o == good_g], p_out["energy_new1"][good_o == good_g], rtol=2e-5, atol=1e-7)
             np.testing.assert_allclose(sg["energy_new"][~good_g & ~good_o, 0], p_out["energy_new0"][~good_g & ~good_o], rtol=0, atol=0)
-            np.testing.assert_allclose(sg["maxstep"][both], p_out["maxstep"][both], rtol=5e-5)
-            np.testing.assert_allclose(sg["lastHessian_new"][both], p_out["lastHessian_new"][both], rtol=5e-5, atol=1e-6)
+            np.testing.assert_allclose(sg["maxstep"][both], p_out["maxstep"][both], rtol=2e-4)
+            np.testing.assert_allclose(sg["lastHessian_new"][both], p_out["lastHessian_new"][both], rtol=3e-4, atol=1e-6)
             scale = np.abs(jb_o[both]).max(axis=0) + 1e-12
-            assert (np.abs(sg["Jb"][both] - jb_o[both]) / scale).max() < 5e-5
+            assert (np.abs(sg["Jb"][both] - jb_o[both]) / scale).max() < 2e-4
             if len(flips) == 0:
                 for k, tol in (("H", 2e-5), ("Hsc", 2e-5), ("b", 2e-4), ("bsc", 2e-4)):
                     assert rel(sg[k], so[k]) < tol, (lvl, step, k, rel(sg[k], so[k]))

@@ -128,3 +128,91 @@ def test_sharded_exchange(orc, synth, world, mode):
     assert abs(e0 - E) <= 2e-5 * abs(E)
     assert rel(HA, a["HA"]) < 1e-5 and rel(Hsc, a["Hsc"]) < 1e-5
     assert rel(bA, a["bA"]) < 1e-4 and rel(bsc, a["bsc"]) < 1e-4
+
+
+def _flow(hw, nf):
+    """the makeKeyFrame sequence on the adapter (as tests/test_gpu_host.py::test_keyframe_turnover_flow)"""
+    out = {}
+    n1, log1 = hw.optimize(4)
+    E_tail, removed = hw.finish_optimize()
+    marg, drop = hw.flag_points([0])
+    g = hw.marginalize_points(marg, drop)
+    m = hw.marginalize_frame(0)
+    n2, log2 = hw.optimize(3)
+    st, idd, th = hw.states()
+    out.update(n1=n1, log1=log1, E_tail=E_tail, removed=removed, marg=marg, drop=drop, resInM=g["resInM"], HM=m["HM"], bM=m["bM"], nres=m["nres"],
+               n2=n2, log2=log2, st=st, idepth=idd, th=th)
+    return out
+
+
+def _worker_window(rank, world, port, cfg, mode, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch
+    import torch.distributed as dist
+    import dmvio_b200.capi as capi
+    import dmvio_b200.hostapi as hostapi
+    import dmvio_b200.synth as synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def allgather(data):   # the application's host communicator (here gloo)
+        t = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return b"".join(o.numpy().tobytes() for o in outs)
+
+    W = synth.make_window(**cfg)
+    shard = dict(rank=rank, nranks=world, allgather=allgather, exchange=mode)
+    if mode == "nccl":
+        uid = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        shard["uid"] = uid[0]
+    hw = hostapi.WindowBA(W, device=rank, shard=shard)
+    out = _flow(hw, W["nf"])
+    q.put((rank, out))
+    dist.barrier()
+    hw.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,mode", [(2, "p2p"), (2, "nccl"), (4, "p2p")])
+def test_window_ba_sharded(synth, world, mode):
+    """The C++ adapter in sharded mode (WindowBA::setSharding): every rank runs the SAME host logic on the all-reduced system; per-point read-backs
+    are gathered through the application's host allgather.  The whole makeKeyFrame flow (optimize, tail with residual removal, flagPointsForRemoval,
+    marginalizePointsF, marginalizeFrame, optimize again) must take the same decisions as the unsharded adapter and end in the same state."""
+    import dmvio_b200.capi as capi
+    import dmvio_b200.hostapi as hostapi
+    if capi.lib().dmv_device_count() < world:
+        pytest.skip(f"needs {world} GPUs (run with gpurun --gpus {world})")
+    import torch.multiprocessing as mp
+    cfg = dict(nf=6, npts=500 + world, seed=31, state_noise=1e-3, hosts="all")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_window, args=(r, world, port, cfg, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = _flow(hostapi.WindowBA(synth.make_window(**cfg)), cfg["nf"])
+    for rk in range(world):
+        o = res[rk]
+        # identical host decisions on every rank and the unsharded adapter
+        assert (o["n1"], o["n2"], o["resInM"], o["nres"]) == (ref["n1"], ref["n2"], ref["resInM"], ref["nres"])
+        np.testing.assert_array_equal(o["marg"], ref["marg"]); np.testing.assert_array_equal(o["drop"], ref["drop"])
+        np.testing.assert_array_equal(o["removed"], ref["removed"])
+        np.testing.assert_allclose(o["log1"], ref["log1"], rtol=3e-4)
+        np.testing.assert_allclose(o["log2"], ref["log2"], rtol=3e-4)
+        assert abs(o["E_tail"] - ref["E_tail"]) <= 3e-4 * abs(ref["E_tail"])
+        assert rel(o["HM"], ref["HM"]) < 1e-4 and rel(o["bM"], ref["bM"]) < 1e-3
+        assert np.abs(o["st"] - ref["st"]).max() < 2e-5
+        np.testing.assert_allclose(o["idepth"], ref["idepth"], rtol=2e-3, atol=2e-4)
+        np.testing.assert_allclose(o["th"], ref["th"], rtol=2e-3)
+    for rk in range(1, world):   # the ranks agree bit for bit (same all-reduced system, same host arithmetic)
+        np.testing.assert_array_equal(res[rk]["st"], res[0]["st"])
+        np.testing.assert_array_equal(res[rk]["HM"], res[0]["HM"])
+        np.testing.assert_array_equal(res[rk]["idepth"], res[0]["idepth"])

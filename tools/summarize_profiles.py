@@ -68,10 +68,33 @@ def reports(prefix):
                     if k in h:
                         f.write(f"| {k} | {r[h.index(k)]} | {units[h.index(k)]} |\n")
                 f.write("\n")
-        # hottest source lines by stall samples
-        src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda"], capture_output=True, text=True).stdout
-        if src.strip():
-            open(f"{prefix}_{name}_source.csv", "w").write(src)
+        # where the time goes: warp-stall samples and executed instructions between consecutive block barriers of the SASS (phase boundaries)
+        sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+        rows = [r for r in csv.reader(sass.splitlines())]
+        hi = next((i for i, r in enumerate(rows) if "# Samples" in r), None)
+        if hi is not None:
+            h2, data = rows[hi], [r for r in rows[hi + 1:] if len(r) == len(rows[hi])]
+            iS, iI, isrc = h2.index("# Samples"), h2.index("Instructions Executed"), h2.index("Source")
+            stall = [c for c in h2 if c.startswith("stall_") and "Not Issued" not in c]
+            tot, toti = sum(int(r[iS]) for r in data) or 1, sum(int(r[iI]) for r in data) or 1
+            with open(f"{prefix}_{name}_summary.md", "a") as f:
+                f.write(f"### segments between block barriers ({tot} warp-stall samples, {toti} warp instructions; first kernel of the report)\n\n")
+                f.write("| SASS index | ends at | samples | share | instructions share | top stall reasons |\n|---|---|---|---|---|---|\n")
+                acc = acci = 0
+                agg = collections.Counter()
+                for k, r in enumerate(data):
+                    acc += int(r[iS]); acci += int(r[iI])
+                    for c in stall:
+                        agg[c] += int(r[h2.index(c)] or 0)
+                    src = r[isrc].strip()
+                    if src.startswith("BAR.") or "ATOMG" in src or src.startswith("EXIT"):
+                        top = ", ".join(f"{c[6:]} {100 * v / max(1, sum(agg.values())):.0f}%" for c, v in agg.most_common(3))
+                        f.write(f"| {k} | `{src[:40]}` | {acc} | {100 * acc / tot:.1f}% | {100 * acci / toti:.1f}% | {top} |\n")
+                        acc = acci = 0
+                        agg = collections.Counter()
+                    if src.startswith("EXIT") and k > len(data) // 2:
+                        break
+                f.write("\n")
 
 
 def main():
@@ -81,9 +104,8 @@ def main():
     prefix = os.path.join(P, rnd + tag)
     launches(prefix)
     reports(prefix)
-    for f in ("bench1.json", "bench_ref.json", "pytest_gpu.log", "gpu.txt", "bench2.json", "bench_n2.json", "bench_n4.json", "bench_n8.json"):
-        if os.path.exists(os.path.join(G, f)):
-            shutil.copy(os.path.join(G, f), prefix + "_" + f)
+    for f in sorted(glob.glob(os.path.join(G, "ev_*.json")) + glob.glob(os.path.join(G, "ev_pytest*.log")) + glob.glob(os.path.join(G, "scale_*.json"))):
+        shutil.copy(f, prefix + "_" + os.path.basename(f)[3:] if os.path.basename(f).startswith("ev_") else prefix + "_" + os.path.basename(f))
 
 
 if __name__ == "__main__":
