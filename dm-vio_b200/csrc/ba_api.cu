@@ -41,7 +41,7 @@ int dmv_ba_fill_descriptor(dmv_ba* b) {
   W.st_new = b->d_st_new[t]; W.en_new = b->d_en_new[t]; W.en_wo = b->d_en_wo[t]; W.cpt = b->d_cpt[t]; W.jpjd = b->d_jpjd[t]; W.pout = b->d_pout[t];
   W.c_st = b->d_st_new[c2]; W.c_jpjd = b->d_jpjd[c2]; W.c_pout = b->d_pout[c2];
   W.step = b->d_step;
-  W.part = b->d_part; W.gpart = b->d_gpart;
+  W.part = b->d_part; W.wg = b->d_wg; W.hdig = b->d_hdig;
   W.bar = b->d_bar;
   W.result = b->d_result[t];
   W.result_host = nullptr;
@@ -140,7 +140,8 @@ static int ba_allocate(dmv_ba* b, const dmv_ba_config* cfg) {
   CK(cudaMalloc(&b->d_step, sizeof(float) * mp));
   CK(cudaMemset(b->d_step, 0, sizeof(float) * mp));
   CK(cudaMalloc(&b->d_part, sizeof(double) * PART_STRIDE * (size_t)b->max_chunks));
-  CK(cudaMalloc(&b->d_gpart, sizeof(float) * dmv::GP_STRIDE * (size_t)b->max_chunks));
+  CK(cudaMalloc(&b->d_wg, sizeof(float4) * (size_t)maxT0 * mp));
+  CK(cudaMalloc(&b->d_hdig, sizeof(float) * mp));
   CK(cudaMalloc(&b->d_hdi_solve, sizeof(float) * mp));
   CK(cudaMalloc(&b->d_bar, sizeof(unsigned int)));
   CK(cudaMemset(b->d_bar, 0, sizeof(unsigned int)));
@@ -168,7 +169,7 @@ int dmv_ba_destroy(dmv_ba* b) {
     cudaFree(b->d_pout[k]); cudaFree(b->d_result[k]); cudaFreeHost(b->h_result[k]);
   }
   cudaFree(b->d_step); cudaFree(b->d_resub_sums); cudaFree(b->d_flush);
-  cudaFree(b->d_part); cudaFree(b->d_gpart); cudaFree(b->d_hdi_solve); cudaFree(b->d_bar);
+  cudaFree(b->d_part); cudaFree(b->d_wg); cudaFree(b->d_hdig); cudaFree(b->d_hdi_solve); cudaFree(b->d_bar);
   cudaFreeHost(b->h_up); cudaFreeHost(b->h_adj); cudaFreeHost(b->h_scratch); cudaFreeHost(b->h_en_newest);
   for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   if (b->nccl_comm) dmv::nccl_destroy(b->nccl_comm);

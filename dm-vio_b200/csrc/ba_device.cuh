@@ -25,8 +25,6 @@ constexpr int PART_SLOT = 168;
 constexpr int PART_CC = MAXF * PART_SLOT;
 constexpr int PART_MISC = PART_CC + 20;
 constexpr int PART_STRIDE = PART_MISC + ACC_MISC;
-constexpr int GP_MAXT = (8 * MAXF + 4 + 1 + 3) / 4;                 // 4-column groups of [C | frames | b]
-constexpr int GP_STRIDE = GP_MAXT * (GP_MAXT + 1) / 2 * 16;     // floats per chunk
 
 // per-iteration parameter block
 struct BAIter {
@@ -98,7 +96,8 @@ struct BAWinDev {
   float* step;               // [p]
   // scratch of one launch (never read by the host)
   double* part;              // [chunk][PART_STRIDE] partial blobs
-  float* gpart;              // [chunk][GP_STRIDE] per-chunk partial of sum_p HdiF w_p w_p^T: ntiles 4x4 tiles of 16 floats
+  float4* wg;                // [4-column group][mp] Schur vectors w_p, transposed
+  float* hdig;               // [p] HdiF
   unsigned int* bar;         // grid-barrier arrival counter (monotonic)
   unsigned int bar_target;   // arrivals expected once every CTA of THIS launch has arrived
   double* result;            // H_top N*N | b_top N | Schur tiles ntiles*16 | ACC_MISC tail

@@ -12,15 +12,15 @@
 //            projection, 8 pattern pixels x 4 float4 taps, Huber, classification; per-residual outputs; JpJdF; the residual's 91
 //            AccumulatorApprox entries (MatrixAccumulators.h:L754-915) summed over the pair's lanes -> shared memory
 //   phase B  per point: Hdd / bd / Hcd, HdiF, bdSum (AccumulatedSCHessian.cpp:L36-58) and its Schur vector in ABSOLUTE frame
-//            coordinates w_p = [Hcd | sum_t adHost JpJdF_t | adTarget JpJdF_t ... | bdSum]  (shared memory)
+//            coordinates w_p = [Hcd | sum_t adHost JpJdF_t | adTarget JpJdF_t ... | bdSum]  -> global (transposed for phase E)
 //   phase C  the chunk's pair blocks pushed through the adjoints IN THE CTA (fp64): contributions to H[h,h], H[h,t], H[t,t], H[.,C], b
-//            are written to the chunk's partial blob with plain coalesced stores — no atomics, no accumulators to zero; and the chunk's
-//            share of the Schur complement [H_sc | b_sc] = sum_p HdiF w_p w_p^T as 4x4 tiles (replaces the nf^3 accD blocks and their
-//            stitch) -> the chunk's Gram partial
+//            are written to the chunk's partial blob with plain coalesced stores — no atomics, no accumulators to zero
 //   -------- grid barrier (cooperative launch; every CTA is resident) --------
-//   phase D  every final entry of H_top / b_top / [H_sc | b_sc] = fixed-order fp64 sum of the chunk partials that touch it: 16 lanes per entry
-//   every result entry has exactly one producing lane group, which also streams it into the caller's pinned host buffer and, on a sharded
-//   window, exchanges it with the peer GPUs (LL packets over NVLink peer memory, bounded warp-uniform spin).
+//   phase D  every final entry of H_top / b_top = fixed-order fp64 sum of the chunk partials that touch it: a warp per entry
+//   phase E  Schur complement [H_sc | b_sc] = sum_p HdiF w_p w_p^T as 4x4 tiles, one CTA per tile over ALL points (replaces the nf^3
+//            accD blocks and their stitch)
+//   every result entry has exactly one producing warp, which also streams it into the caller's pinned host buffer and, on a sharded
+//   window, exchanges it with the peer GPUs (LL packets over NVLink peer memory, bounded spin).
 // Results are bit-reproducible run to run (no atomics anywhere on the data path).
 #include "ba_common.cuh"
 #include <mutex>
@@ -108,6 +108,7 @@ struct FusedSmem {
   float hdi[P];
   float id[P], idz[P];
   float misc[16][8];           // per warp: energy, n_in, n_oob, n_outlier, step^2, |idepth_backup|, count
+  double red[16][32];          // phase E: per-warp partials of up to two 4x4 tiles
 };
 
 // operand indices of entry k of the pair block: entry = ops[a] * ops[b] + ops[c] * ops[d]   (LPR = 4 path; same arithmetic as top_entry<K>)
@@ -168,10 +169,38 @@ __device__ __forceinline__ void xchg_push(const BAXchg& X, int idx, double v) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
   }
 }
-// The pull is WARP-COLLECTIVE with a warp-uniform spin loop (votes decide when to leave): lanes of one warp never wait on
+// Both pull variants are WARP-COLLECTIVE with warp-uniform spin loops (votes decide when to leave): lanes of one warp never wait on
 // different conditions, so the warp is converged at the __syncthreads() that follow (an aligned barrier executed by a diverged warp counts
 // the warp twice: premature release or "warp illegal instruction").
 constexpr long long XCHG_SPIN_LIMIT = 400000000ll;  // ~0.2 s of SM clocks: peer lost
+
+// lane-per-entry: every lane with active == true owns entry idx and polls the nranks - 1 packets of it
+__device__ __forceinline__ double xchg_pull_sum_lanes(const BAXchg& X, int idx, double mine, bool active, bool& ok) {
+  const uint4* base = X.inbox[X.rank] + (size_t)((X.seq & 1u) * XCHG_MAXR) * X.pitch + idx;
+  uint4 pk[XCHG_MAXR];
+  unsigned pending = active ? (((1u << X.nranks) - 1u) & ~(1u << X.rank)) : 0u;
+  const long long t0 = clock64();
+  while (__any_sync(0xffffffffu, pending != 0u)) {
+#pragma unroll
+    for (int r = 0; r < XCHG_MAXR; r++)
+      if ((pending >> r) & 1u) {
+        const uint4* src = base + (size_t)r * X.pitch;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[r].x), "=r"(pk[r].y), "=r"(pk[r].z), "=r"(pk[r].w) : "l"(src) : "memory");
+      }
+#pragma unroll
+    for (int r = 0; r < XCHG_MAXR; r++)
+      if (((pending >> r) & 1u) && pk[r].y == X.seq && pk[r].w == X.seq) pending &= ~(1u << r);
+    if (__any_sync(0xffffffffu, clock64() - t0 > XCHG_SPIN_LIMIT)) break;
+  }
+  if (pending) { ok = false; return mine; }
+  double s = 0.0;
+#pragma unroll
+  for (int r = 0; r < XCHG_MAXR; r++) {
+    if (r >= X.nranks) break;
+    s += (r == X.rank) ? mine : __longlong_as_double((long long)(((unsigned long long)pk[r].z << 32) | pk[r].x));
+  }
+  return active ? s : mine;
+}
 
 // 16-lane group per entry (phase D): lane gl of the group polls the packet of rank gl, all ranks in flight at once; `mine` is the value of
 // lane gl == 0.  Returns the rank-ordered sum in every lane of the group.
@@ -853,46 +882,14 @@ __device__ __forceinline__ void fused_chunk(const BAWinDev& W, const BAIter& it,
   }
   __syncthreads();
 
-  // ---- the chunk's share of [H_sc | b_sc] = sum_p HdiF w_p w_p^T (AccumulatedSCHessian.cpp:L62-76), 4x4 tiles over the 4-column groups of
-  // w = [C | frames | b]: two lanes per tile (one half of the chunk's points each; fp32, <= P/2 terms), combined by one shuffle, written as the
-  // chunk's Gram partial.  Phase D sums the partials of all chunks in fp64 in a fixed order.
+  // ---- Schur vectors -> global, transposed ([4-column group][point] float4) so that phase E reads them coalesced
   {
-    const int T = W.T, nt2 = 2 * W.ntiles;
-    float* __restrict__ gout = W.gpart + (size_t)chunk * GP_STRIDE;
-    for (int e0 = warp * 32; e0 < nt2; e0 += nthreads) {  // warp-uniform trip count (shuffle below)
-      const int e = e0 + lane;
-      const bool act = e < nt2;
-      const int tile = act ? (e >> 1) : 0, half = e & 1;
-      int ti = 0, rem = tile;
-      while (rem >= T - ti) { rem -= T - ti; ti++; }
-      const int tj = ti + rem;
-      float a[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) a[i][j] = 0.f;
-      const int p0 = half * (P / 2), p1 = min(ch_count, p0 + P / 2);
-      for (int pl2 = p0; pl2 < p1; pl2++) {
-        const float sc = S.hdi[pl2];
-        const float4 wi = *reinterpret_cast<const float4*>(&S.Wv[pl2][4 * ti]);
-        const float4 wj = *reinterpret_cast<const float4*>(&S.Wv[pl2][4 * tj]);
-        const float si[4] = {sc * wi.x, sc * wi.y, sc * wi.z, sc * wi.w};
-        const float vj[4] = {wj.x, wj.y, wj.z, wj.w};
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 4; j++) a[i][j] += si[i] * vj[j];
-      }
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) a[i][j] += __shfl_xor_sync(0xffffffffu, a[i][j], 1);
-      if (act && half == 0) {
-        float4* o = reinterpret_cast<float4*>(gout + (size_t)tile * 16);
-#pragma unroll
-        for (int i = 0; i < 4; i++) o[i] = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
-      }
+    const int T = W.T;
+    for (int e = tid; e < ch_count * T; e += nthreads) {
+      const int g4 = e / ch_count, pl2 = e - g4 * ch_count;
+      W.wg[(size_t)g4 * mp + ch_start + pl2] = *reinterpret_cast<const float4*>(&S.Wv[pl2][4 * g4]);
     }
+    if (tid < ch_count) W.hdig[ch_start + tid] = S.hdi[tid];
   }
   // ---- phase C, second half: the chunk's contributions in absolute coordinates -> partial blob (AccumulatedTopHessian.cpp:L270-286)
   {
@@ -960,13 +957,11 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR
   // are all in flight together, then a 4-step butterfly.  Fixed order => bit-reproducible.
   const int npair = nf * (nf - 1) / 2;
   const int n_off = npair * 64, n_diag = nf * 64, n_c = nf * 32, n_b = nf * 8;
-  const int n_top = n_off + n_diag + n_c + n_b + 16 + 4 + (ACC_MISC - 1);  // the last counter slot is the error flag: written on error only
-  const int n_gram = W.ntiles * 16;                                        // [H_sc | b_sc] tiles: sums of the per-chunk Gram partials over ALL chunks
-  const int nitems = n_top + n_gram;
+  const int nitems = n_off + n_diag + n_c + n_b + 16 + 4 + (ACC_MISC - 1);  // the last counter slot is the error flag: written on error only
   const int grp = tid >> 4, gl = tid & 15, groups_per_cta = nthreads >> 4;
   const int nch = W.nchunks;
-  // with the peer exchange on: pass 0 (sum + push of every entry this CTA owns) -> pass 1 (pull): the packets of the first entries travel
-  // while the later ones are still being summed
+  // with the peer exchange on: pass 0 (sum + push) -> phase E (Gram tiles + push) -> pass 1 (pull) -> phase E pull: the NVLink round trip of
+  // the H_top entries overlaps the Gram computation
   auto phase_d = [&](const int pass) {
     for (int base = vcta * groups_per_cta; base < nitems; base += ncta * groups_per_cta) {  // CTA-uniform trip count (shuffles below)
       const int item = base + grp;
@@ -974,10 +969,7 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR
       // decode: up to two (offset, chunk range) segments and up to two destinations
       int off0 = 0, lo0 = 0, hi0 = act ? nch : 0, off1 = 0, lo1 = 0, hi1 = 0, d0 = 0, d1 = -1;
       int e = act ? item : nitems - 1;
-      const bool gram = e >= n_top;   // warp-uniform except in the one warp that straddles the boundary
-      if (gram) {
-        off0 = e - n_top; d0 = nH + off0;
-      } else if (e < n_off) {
+      if (e < n_off) {
         const int q = e >> 6, ij = e & 63, i = ij >> 3, j = ij & 7;
         int a = 0, rem = q;
         while (rem >= nf - 1 - a) { rem -= nf - 1 - a; a++; }
@@ -1009,24 +1001,13 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR
 #pragma unroll 1
         for (int seg = 0; seg < 2; seg++) {
           const int lo = seg ? lo1 : lo0, hi = seg ? hi1 : hi0;
-          if (gram) {
-            const float* __restrict__ src = W.gpart + off0;
-            for (int c0 = lo + gl; c0 < hi; c0 += 192) {
-              float v[12];
+          const double* __restrict__ src = part + (seg ? off1 : off0);
+          for (int c0 = lo + gl; c0 < hi; c0 += 192) {
+            double v[12];
 #pragma unroll
-              for (int u = 0; u < 12; u++) v[u] = (c0 + 16 * u < hi) ? __ldcg(src + (size_t)(c0 + 16 * u) * GP_STRIDE) : 0.f;
+            for (int u = 0; u < 12; u++) v[u] = (c0 + 16 * u < hi) ? __ldcg(src + (size_t)(c0 + 16 * u) * PART_STRIDE) : 0.0;
 #pragma unroll
-              for (int u = 0; u < 12; u++) sum += (double)v[u];
-            }
-          } else {
-            const double* __restrict__ src = part + (seg ? off1 : off0);
-            for (int c0 = lo + gl; c0 < hi; c0 += 192) {
-              double v[12];
-#pragma unroll
-              for (int u = 0; u < 12; u++) v[u] = (c0 + 16 * u < hi) ? __ldcg(src + (size_t)(c0 + 16 * u) * PART_STRIDE) : 0.0;
-#pragma unroll
-              for (int u = 0; u < 12; u++) sum += v[u];
-            }
+            for (int u = 0; u < 12; u++) sum += v[u];
           }
         }
         sum += __shfl_xor_sync(0xffffffffu, sum, 8);
@@ -1048,7 +1029,99 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR
     };
   phase_d(0);
 
-  if (xch) phase_d(1);
+  // ---------------------------------------------------------------- phase E: [H_sc | b_sc] = sum_p HdiF w_p w_p^T as 4x4 tiles over ALL points
+  // of the window: a CTA takes tiles vcta, vcta + ncta (both in ONE pass over the points when the grid has fewer CTAs than tiles)
+  {
+    const int T = W.T, npts = W.npts;
+    for (int tile0 = vcta; tile0 < W.ntiles; tile0 += 2 * ncta) {
+      const int tile1 = tile0 + ncta;
+      const bool two = tile1 < W.ntiles;
+      int ti0 = 0, rem = tile0;
+      while (rem >= T - ti0) { rem -= T - ti0; ti0++; }
+      const int tj0 = ti0 + rem;
+      int ti1 = 0;
+      rem = two ? tile1 : tile0;
+      while (rem >= T - ti1) { rem -= T - ti1; ti1++; }
+      const int tj1 = ti1 + rem;
+      float a[2][4][4];
+#pragma unroll
+      for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) a[q][i][j] = 0.f;
+      const float4* __restrict__ wi0 = W.wg + (size_t)ti0 * mp;
+      const float4* __restrict__ wj0 = W.wg + (size_t)tj0 * mp;
+      const float4* __restrict__ wi1 = W.wg + (size_t)ti1 * mp;
+      const float4* __restrict__ wj1 = W.wg + (size_t)tj1 * mp;
+#pragma unroll 4
+      for (int p = tid; p < npts; p += nthreads) {
+        const float sc = __ldcg(W.hdig + p);
+        const float4 wi = __ldcg(wi0 + p), wj = __ldcg(wj0 + p);
+        const float si[4] = {sc * wi.x, sc * wi.y, sc * wi.z, sc * wi.w};
+        const float vj[4] = {wj.x, wj.y, wj.z, wj.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) a[0][i][j] += si[i] * vj[j];
+        if (two) {  // CTA-uniform
+          const float4 xi = __ldcg(wi1 + p), xj = __ldcg(wj1 + p);
+          const float ti[4] = {sc * xi.x, sc * xi.y, sc * xi.z, sc * xi.w};
+          const float uj[4] = {xj.x, xj.y, xj.z, xj.w};
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) a[1][i][j] += ti[i] * uj[j];
+        }
+      }
+      // per-thread fp32 sums over <= npts / nthreads points, then fp64: transposing warp butterfly (31 exchanges for the 32 values: lane L
+      // ends with the warp's sum of value L), cross-warp through shared memory
+      {
+        double d[32];
+#pragma unroll
+        for (int qq = 0; qq < 2; qq++)
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) d[qq * 16 + i * 4 + j] = (double)a[qq][i][j];
+        static_for<0, 5>([&](auto sc) {
+          constexpr int st2 = decltype(sc)::value, hstep = 16 >> st2, m = 16 >> st2;
+          const bool up = (lane & m) != 0;
+#pragma unroll
+          for (int k = 0; k < hstep; k++) d[k] = (up ? d[k + hstep] : d[k]) + __shfl_xor_sync(0xffffffffu, up ? d[k] : d[k + hstep], m);
+        });
+        S.red[warp][lane] = d[0];   // lane L: value index 16 b4 + 8 b3 + 4 b2 + 2 b1 + b0 = L
+      }
+      __syncthreads();
+      if (tid < 32) {  // the whole first warp (the exchange below is warp-collective)
+        const bool own = tid < 16 || two;
+        double d = 0.0;
+        for (int wv = 0; wv < nwarps; wv++) d += S.red[wv][tid];
+        const int idx = nH + (tid < 16 ? tile0 : tile1) * 16 + (tid & 15);
+        if (own) {
+          R[idx] = d;
+          if (xch) xchg_push(W.xc, idx, d);
+          else if (RH) RH[idx] = d;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (xch) {
+    phase_d(1);
+    if (tid < 32) {  // pull of the Gram tiles: same (tile, lane) ownership as above, so R[idx] is this lane's own earlier store
+      for (int tile0 = vcta; tile0 < W.ntiles; tile0 += 2 * ncta) {
+        const int tile1 = tile0 + ncta;
+        const bool own = tid < 16 || tile1 < W.ntiles;
+        const int idx = nH + (tid < 16 ? tile0 : tile1) * 16 + (tid & 15);
+        const double d = xchg_pull_sum_lanes(W.xc, idx, own ? R[idx] : 0.0, own, ok);
+        if (own) {
+          R[idx] = d;
+          if (RH) RH[idx] = d;
+        }
+      }
+    }
+  }
   if (!__syncthreads_and(ok) && tid == 0) {  // barrier / peer timeout seen by any thread: raise the error slot of the counters (checked by the host)
     R[nH + W.ntiles * 16 + 7] = 1.0;
     if (RH) RH[nH + W.ntiles * 16 + 7] = 1.0;

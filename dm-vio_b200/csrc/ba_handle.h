@@ -50,7 +50,8 @@ struct dmv_ba {
   double* d_result[2] = {nullptr, nullptr};
   float* d_step = nullptr;
   double* d_part = nullptr;        // [max_chunks][PART_STRIDE] per-chunk partial blobs (scratch of one launch)
-  float* d_gpart = nullptr;        // [max_chunks][GP_STRIDE] per-chunk Gram partials (scratch)
+  float4* d_wg = nullptr;          // [WG_GROUPS][mp] Schur vectors, transposed (scratch)
+  float* d_hdig = nullptr;         // [mp] HdiF (scratch)
   float* d_hdi_solve = nullptr;    // [mp] HdiF of the linearisation the last dmv_ba_accumulate returned (PointHessian::idepth_hessian)
   int hdi_solve_n = 0;
   unsigned int* d_bar = nullptr;   // grid-barrier arrival counter
