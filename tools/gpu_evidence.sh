@@ -16,5 +16,5 @@ timeout 200 python tools/bench_trace.py > $O/ev_bench_trace.json 2> $O/ev_bench_
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > $O/ev_ncu_launches.log 2>&1; tail -1 $O/ev_ncu_launches.log | cut -c1-200
 # one full capture per hot kernel
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ba_fused_kernel -s 40 -c 1 -f -o $O/prof_ba_fused python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-extras > $O/ev_ncu_ba_fused.log 2>&1; tail -1 $O/ev_ncu_ba_fused.log | cut -c1-200
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:ba_fused_batch_kernel -s 10 -c 1 -f -o $O/prof_ba_fused_batch python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras --chunk 32 --batch 16 > $O/ev_ncu_ba_batch.log 2>&1; tail -1 $O/ev_ncu_ba_batch.log | cut -c1-200
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ba_fused_batch_kernel -s 10 -c 1 -f -o $O/prof_ba_fused_batch python bench.py --steps 10 --warmup 3 --no-cpu-baseline --chunk 32 --batch 16 > $O/ev_ncu_ba_batch.log 2>&1; tail -1 $O/ev_ncu_ba_batch.log | cut -c1-200
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:ct_track_cluster -s 3 -c 1 -f -o $O/prof_ct_track_cluster python tools/bench_coarse.py --frames 3 --cpu-frames 1 > $O/ev_ncu_ct.log 2>&1; tail -1 $O/ev_ncu_ct.log | cut -c1-200
