@@ -72,10 +72,11 @@ inline void jacobiEigenSym(std::vector<double> A, int k, std::vector<double>& w,
 }
 }  // namespace detail
 
-// x (size 8 nf + 4) is projected onto the orthogonal complement of span(ns); the singular values of the normalised nullspace matrix are
-// the square roots of the eigenvalues of its 7 x 7 Gram matrix
-inline void orthogonalizeX(std::vector<double>& x, std::vector<std::vector<double>> ns, double solverModeDelta) {
-  const int k = (int)ns.size(), N = (int)x.size();
+// Orthonormal basis of span(ns) restricted to the singular directions above solverModeDelta * max: the columns u_a = N v_a / sigma_a of the
+// normalised nullspace matrix (sigma^2, v from the 7 x 7 Gram matrix).  It depends on the frames' evaluation points only, which do not
+// move during FullSystem::optimize: built once per window state and reused by every solve (gaugeProject).
+inline std::vector<std::vector<double>> gaugeBasis(std::vector<std::vector<double>> ns, double solverModeDelta) {
+  const int k = (int)ns.size(), N = k ? (int)ns[0].size() : 0;
   for (std::vector<double>& v : ns) {
     double nrm = 0;
     for (double e : v) nrm += e * e;
@@ -88,16 +89,30 @@ inline void orthogonalizeX(std::vector<double>& x, std::vector<std::vector<doubl
   detail::jacobiEigenSym(G, k, w, V);
   double maxSv = 0;
   for (int a = 0; a < k; a++) maxSv = std::max(maxSv, std::sqrt(std::max(0.0, w[a])));
-  std::vector<double> proj(N, 0.0), u(N);
+  std::vector<std::vector<double>> U;
   for (int a = 0; a < k; a++) {
     const double sv = std::sqrt(std::max(0.0, w[a]));
     if (!(sv > solverModeDelta * maxSv)) continue;
+    std::vector<double> u(N);
     for (int i = 0; i < N; i++) { double d = 0; for (int b = 0; b < k; b++) d += ns[b][i] * V[(size_t)b * k + a]; u[i] = d / sv; }
+    U.push_back(std::move(u));
+  }
+  return U;
+}
+inline void gaugeProject(std::vector<double>& x, const std::vector<std::vector<double>>& U) {
+  const int N = (int)x.size();
+  std::vector<double> proj(N, 0.0);
+  for (const std::vector<double>& u : U) {
     double ux = 0;
     for (int i = 0; i < N; i++) ux += u[i] * x[i];
     for (int i = 0; i < N; i++) proj[i] += u[i] * ux;
   }
   for (int i = 0; i < N; i++) x[i] -= proj[i];
+}
+// x (size 8 nf + 4) is projected onto the orthogonal complement of span(ns); the singular values of the normalised nullspace matrix are
+// the square roots of the eigenvalues of its 7 x 7 Gram matrix
+inline void orthogonalizeX(std::vector<double>& x, std::vector<std::vector<double>> ns, double solverModeDelta) {
+  gaugeProject(x, gaugeBasis(std::move(ns), solverModeDelta));
 }
 
 }  // namespace dmvio_b200

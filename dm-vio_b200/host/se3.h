@@ -87,20 +87,29 @@ struct SE3 {
 };
 
 // Plain LDL^T solve of a symmetric positive (semi-)definite system; n x n row-major.  (Eigen's ldlt() pivots; rounding only.)
+// dot product with four independent partial sums: the reduced systems are small (N <= 68), so the solve is bound by the latency of the
+// dependent adds of a plain loop, not by flops
+inline double dot4(const double* a, const double* b, int n) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  int k = 0;
+  for (; k + 3 < n; k += 4) { s0 += a[k] * b[k]; s1 += a[k + 1] * b[k + 1]; s2 += a[k + 2] * b[k + 2]; s3 += a[k + 3] * b[k + 3]; }
+  for (; k < n; k++) s0 += a[k] * b[k];
+  return (s0 + s1) + (s2 + s3);
+}
+
+// x = A^-1 b by LDL^T without pivoting (A symmetric positive definite after the Jacobi scaling of the caller), row-major
 inline void ldlt_solve(int n, const double* A, const double* b, double* x) {
-  std::vector<double> L((size_t)n * n, 0.0), D(n, 0.0), y(n);
+  std::vector<double> L((size_t)n * n, 0.0), D(n, 0.0), y(n), w(n);
   for (int j = 0; j < n; j++) {
-    double dj = A[(size_t)j * n + j];
-    for (int k = 0; k < j; k++) dj -= L[(size_t)j * n + k] * L[(size_t)j * n + k] * D[k];
+    double* Lj = &L[(size_t)j * n];
+    for (int k = 0; k < j; k++) w[k] = Lj[k] * D[k];
+    const double dj = A[(size_t)j * n + j] - dot4(Lj, w.data(), j);
     D[j] = dj;
-    L[(size_t)j * n + j] = 1.0;
-    for (int i = j + 1; i < n; i++) {
-      double s = A[(size_t)i * n + j];
-      for (int k = 0; k < j; k++) s -= L[(size_t)i * n + k] * L[(size_t)j * n + k] * D[k];
-      L[(size_t)i * n + j] = dj != 0.0 ? s / dj : 0.0;
-    }
+    Lj[j] = 1.0;
+    const double inv = dj != 0.0 ? 1.0 / dj : 0.0;
+    for (int i = j + 1; i < n; i++) L[(size_t)i * n + j] = (A[(size_t)i * n + j] - dot4(&L[(size_t)i * n], w.data(), j)) * inv;
   }
-  for (int i = 0; i < n; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[(size_t)i * n + k] * y[k]; y[i] = s; }
+  for (int i = 0; i < n; i++) y[i] = b[i] - dot4(&L[(size_t)i * n], y.data(), i);
   for (int i = 0; i < n; i++) y[i] = D[i] != 0.0 ? y[i] / D[i] : 0.0;
   for (int i = n - 1; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < n; k++) s -= L[(size_t)k * n + i] * x[k]; x[i] = s; }
 }

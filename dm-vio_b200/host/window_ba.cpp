@@ -588,9 +588,20 @@ void WindowBA::solveSystemF(int iteration, double lambda) {
     for (int i = 0; i < N; i++) lastX[i] = SVecI[i] * xs[i];
   }
   if (iteration >= 2 && s.setting_orthogonalizeXLater) {  // L980-984: project x off the 7 gauge directions (6 pose + 1 scale)
-    std::vector<SE3> evalPT(n);
-    for (int h = 0; h < n; h++) evalPT[h] = frameHessians[h].worldToCam_evalPT;
-    orthogonalizeX(lastX, windowNullspaces(evalPT, SCALE_XI_TRANS, SCALE_XI_ROT), s.setting_solverModeDelta);
+    // the nullspaces depend on the evaluation points only (fixed during optimize): basis cached, keyed by the evaluation points themselves
+    std::vector<double> key((size_t)12 * n);
+    for (int h = 0; h < n; h++) {
+      const SE3& T = frameHessians[h].worldToCam_evalPT;
+      for (int i = 0; i < 9; i++) key[(size_t)12 * h + i] = T.R[i];
+      for (int i = 0; i < 3; i++) key[(size_t)12 * h + 9 + i] = T.t[i];
+    }
+    if (key != gauge_key_) {
+      std::vector<SE3> evalPT(n);
+      for (int h = 0; h < n; h++) evalPT[h] = frameHessians[h].worldToCam_evalPT;
+      gauge_U_ = gaugeBasis(windowNullspaces(evalPT, SCALE_XI_TRANS, SCALE_XI_ROT), s.setting_solverModeDelta);
+      gauge_key_.swap(key);
+    }
+    gaugeProject(lastX, gauge_U_);
   }
   // resubstituteF_MT (EnergyFunctional.cpp:L267-289): frame / calib steps here, the per-point half is fused into the next linearizeAll
   for (int i = 0; i < 4; i++) Hcalib.step[i] = -lastX[i];

@@ -206,6 +206,8 @@ class WindowBA {
   bool fetchPointFloats(int what, float* out);   // 0: idepth, 1: HdiF of the last solve
   template <class T> bool gatherRows(const std::vector<std::vector<int>>& of_rank, const T* local, int width, T* global);
   float canbreak_frames_[4] = {0, 0, 0, 0};
+  std::vector<double> gauge_key_;                 // evaluation points the cached gauge basis belongs to
+  std::vector<std::vector<double>> gauge_U_;      // orthonormal basis of the 7 gauge directions (host/nullspace.h: gaugeBasis)
 };
 
 }  // namespace dmvio_b200
