@@ -8,7 +8,7 @@ timeout 1500 python -m pytest tests -m gpu -q > $O/ev_pytest_gpu.log 2>&1; echo 
 grep -n "passed\|failed\|^FAILED\|^ERROR\|pytest rc" $O/ev_pytest_gpu.log | cut -c1-300 | tail -20
 timeout 600 python bench.py > $O/ev_bench_default.json 2> $O/ev_bench_default.err; cut -c1-400 $O/ev_bench_default.json; tail -2 $O/ev_bench_default.err | cut -c1-200
 timeout 600 python bench.py --impl reference > $O/ev_bench_reference.json 2> $O/ev_bench_reference.err; cut -c1-400 $O/ev_bench_reference.json
-timeout 300 python bench.py --steps 300 --warmup 20 --no-cpu-baseline --no-extras --chunk 32 --batch 16 > $O/ev_bench_chunk32_batch16.json 2> $O/ev_bench_chunk32_batch16.err; cut -c1-300 $O/ev_bench_chunk32_batch16.json
+timeout 300 python bench.py --steps 300 --warmup 20 --no-cpu-baseline --chunk 32 --batch 16 > $O/ev_bench_chunk32_batch16.json 2> $O/ev_bench_chunk32_batch16.err; cut -c1-300 $O/ev_bench_chunk32_batch16.json
 timeout 200 python tools/bench_coarse.py --frames 300 > $O/ev_bench_coarse.json 2> $O/ev_bench_coarse.err; cut -c1-500 $O/ev_bench_coarse.json
 timeout 200 python tools/bench_trace.py > $O/ev_bench_trace.json 2> $O/ev_bench_trace.err; cut -c1-300 $O/ev_bench_trace.json
 [ "$1" = "quick" ] && exit 0
