@@ -486,7 +486,8 @@ def config5_stream(D, rank, world, local_rank):
         return None
     out = {"workload": "512x512 stream, 7 KF window, 2000 pts, exactly 10 GN iterations per keyframe, one replica per GPU", "scaling": "replicas",
            "keyframes_per_s": float(sum(rates)), "keyframes_per_s_per_gpu": [float(x) for x in rates], "gpu_ms_per_keyframe": r["gpu_ms_per_keyframe"],
-           "gn_iterations_per_keyframe": r["gpu_gn_iterations_per_keyframe"], "timed_gpu": r["timed_gpu"]}
+           "gn_iterations_per_keyframe": r["gpu_gn_iterations_per_keyframe"], "timed_gpu": r["timed_gpu"],
+           "gpu_ms_setup_per_keyframe": r.get("gpu_ms_setup_per_keyframe"), "gpu_us_per_iteration": r.get("gpu_us_per_iteration")}
     if world == 1:
         out.update(cpu_keyframes_per_s=r["cpu_keyframes_per_s"], cpu_threads=r["cpu_threads"], timed_cpu=r["timed_cpu"])
     return out

@@ -84,6 +84,10 @@ int dmvh_window_get_idepths(void* p, float* idepth) {
   W->getIdepths(idepth);
   return W->error().empty() ? 0 : -1;
 }
+void dmvh_window_profile(void* p, double out5[5], int reset) {
+  WindowBA* W = static_cast<WindowBA*>(p);
+  for (int i = 0; i < 5; i++) { out5[i] = W->profile_us[i]; if (reset) W->profile_us[i] = 0; }
+}
 int dmvh_window_set_setting(void* p, const char* name, double value) {
   Settings& s = static_cast<WindowBA*>(p)->s;
   const std::string n(name);

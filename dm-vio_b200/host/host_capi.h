@@ -29,6 +29,8 @@ int dmvh_window_set_sharding(void* win, int rank, int nranks, dmvh_allgather_cb 
 int dmvh_window_p2p_setup(void* win);
 int dmvh_window_comm_init(void* win, const void* nccl_unique_id128);
 int dmvh_window_get_idepths(void* win, float* idepth);
+/* WindowBA::profile_us: microseconds spent in [solve, state step + tables, linearize, prior energies] and the iteration count */
+void dmvh_window_profile(void* win, double out5[5], int reset);
 /* WindowBA::s.<name> = value for the settings the optimisation loop reads (minOptIterations, thOptIterations, margWeightFac, ...); 0 ok, -1 unknown */
 int dmvh_window_set_setting(void* win, const char* name, double value);
 int dmvh_window_prepare(void* win); /* makeIDX + setAdjointsF + setPrecalcValues */

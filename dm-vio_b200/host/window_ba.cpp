@@ -4,6 +4,7 @@
 #include "nullspace.h"
 #include "../csrc/inv3.h"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 
@@ -663,14 +664,22 @@ int WindowBA::optimize(int mnumOptIts, std::vector<double>* energyLog, bool fini
   double lambda = 1e-5;
   const double minLambda = 1e-5;
   int numIterations = 0;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
   for (int iteration = 0; iteration < mnumOptIts; iteration++) {
+    const auto t0 = now();
     backupState();
     solveSystemF(iteration, lambda);
+    const auto t1 = now();
     doStepFromBackup();
+    const auto t2 = now();
     const double newEnergy = linearizeAll(false);
+    const auto t3 = now();
     if (!std::isfinite(newEnergy) && !err_.empty()) return numIterations;
     const double newEnergyL = calcLEnergyF_MT();
     const double newEnergyM = calcMEnergyF();
+    const auto t4 = now();
+    profile_us[0] += us(t0, t1); profile_us[1] += us(t1, t2); profile_us[2] += us(t2, t3); profile_us[3] += us(t3, t4); profile_us[4] += 1;
     // doStepFromBackup's return value (L311-314), now that the device reported sum |idepth_backup|
     const float sumNID = step_sums_[2] > 0 ? (float)(step_sums_[1] / step_sums_[2]) : 0.f;
     bool canbreak = sqrtf(canbreak_frames_[0]) < 0.0005 * s.setting_thOptIterations && sqrtf(canbreak_frames_[1]) < 0.00005 * s.setting_thOptIterations &&

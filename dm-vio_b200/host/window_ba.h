@@ -105,6 +105,9 @@ class WindowBA {
   std::function<void(double energy)> acceptBAUpdate;   // BAGTSAMIntegration::acceptBAUpdate (FullSystemOptimize.cpp:L571)
   int resInA = 0;
   double lastEnergyTotal = 0;
+  // wall-clock microseconds accumulated over the LM iterations of optimize(): [backup + solveSystemF, doStepFromBackup (states + precalc tables),
+  // linearizeAll (upload of the tables, fused launch, sync), calcLEnergy + calcMEnergy, #iterations]; reset by the caller
+  double profile_us[5] = {0, 0, 0, 0, 0};
 
   // ---- construction (EnergyFunctional::insertFrame / insertPoint / insertResidual + FrameHessian::makeImages on the device)
   int insertFrame(const float* image_wh, const SE3& worldToCam_evalPT, const double state[10], const double state_zero[10], float ab_exposure,

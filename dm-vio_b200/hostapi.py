@@ -46,6 +46,8 @@ def _bind(L):
         L.dmvh_window_set_points_carry.argtypes = [vp, C.c_int, i32p, f32p, f32p, f32p, f32p, f32p, f32p, vp, i32p]
         L.dmvh_window_set_residuals.argtypes = [vp, C.c_int, i32p, i32p]
         L.dmvh_window_prepare.argtypes = [vp]
+        L.dmvh_window_profile.argtypes = [vp, f64p, C.c_int]
+        L.dmvh_window_profile.restype = None
         L.dmvh_window_set_sharding.argtypes = [vp, C.c_int, C.c_int, vp, vp]
         L.dmvh_window_p2p_setup.argtypes = [vp]
         L.dmvh_window_comm_init.argtypes = [vp, vp]
@@ -146,6 +148,13 @@ class WindowBA:
             self.close()
         except Exception:
             pass
+
+    def profile(self, reset=True):
+        """per-iteration wall-clock split of optimize()'s LM loop, microseconds: dict(solve, step, linearize, energies, iterations)"""
+        o = np.zeros(5)
+        self.L.dmvh_window_profile(self.h, o, int(reset))
+        n = max(1.0, o[4])
+        return dict(solve=o[0] / n, step_and_tables=o[1] / n, linearize=o[2] / n, prior_energies=o[3] / n, iterations=int(o[4]))
 
     def tables(self):
         pc = np.zeros((self.nf * self.nf, 32), np.float32); a = np.zeros((self.nf * self.nf, 8, 8)); b = np.zeros((self.nf * self.nf, 8, 8))

@@ -79,7 +79,7 @@ def run_stream(keyframes=40, its=10, cpu_keyframes=6, size=512, device=0):
     for k in range(NFW - 1):
         add_frame(W0, k)
     log = np.zeros(64)
-    gpu_t, gpu_its, energies = [], [], []
+    gpu_t, gpu_its, energies, setup_t = [], [], [], []
     for s in range(args.keyframes):
         W = sub_window(S, s, NFW, NPTS, rng)
         t0 = time.perf_counter()
@@ -90,8 +90,10 @@ def run_stream(keyframes=40, its=10, cpu_keyframes=6, size=512, device=0):
                                  c(W["idepth_zero"], np.float32), c(W["color"], np.float32).reshape(-1), c(W["weights"], np.float32).reshape(-1), None)
         L.dmvh_window_set_residuals(win, len(W["res_point"]), c(W["res_point"], np.int32), c(W["res_target"], np.int32))
         assert L.dmvh_window_prepare(win) == 0, L.dmvh_window_error(win)
+        t1 = time.perf_counter()
         n = L.dmvh_window_optimize(win, args.its, log, 64)
         gpu_t.append(time.perf_counter() - t0)
+        setup_t.append(t1 - t0)
         gpu_its.append(n)
         energies.append(log[log >= 0][[0, -1]].copy())
     cpu_t = []
@@ -108,6 +110,12 @@ def run_stream(keyframes=40, its=10, cpu_keyframes=6, size=512, device=0):
            "residuals_per_window": int(len(W["res_point"])), "energy_first_last_of_last_keyframe": [float(v) for v in energies[-1]],
            "timed_gpu": "drop oldest + H2D new image + device [I,dx,dy] + points/residuals upload + adjoints + optimize() (fused GN steps, host LDLT solves)",
            "timed_cpu": "oracle optimize() only (window construction excluded), 6 worker threads"}
+    prof = np.zeros(5)
+    L.dmvh_window_profile(win, prof, 1)
+    nit = max(1.0, prof[4])
+    out["gpu_ms_setup_per_keyframe"] = float(np.median(setup_t[2:])) * 1e3   # drop oldest + H2D + device [I,dx,dy] + point / residual upload + adjoints
+    out["gpu_us_per_iteration"] = {"host_solve": prof[0] / nit, "host_state_step_and_tables": prof[1] / nit, "linearize_launch_and_sync": prof[2] / nit,
+                                   "host_prior_energies": prof[3] / nit}
     L.dmvh_window_destroy(win)
     return out
 

@@ -6,6 +6,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > $O/ev_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/ev_pytest_gpu.log
 grep -n "passed\|failed\|^FAILED\|^ERROR\|pytest rc" $O/ev_pytest_gpu.log | cut -c1-300 | tail -20
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/ev_smoke.log 2>&1; echo "smoke rc=$?" >> $O/ev_smoke.log; tail -4 $O/ev_smoke.log | cut -c1-250
 timeout 600 python bench.py > $O/ev_bench_default.json 2> $O/ev_bench_default.err; cut -c1-400 $O/ev_bench_default.json; tail -2 $O/ev_bench_default.err | cut -c1-200
 timeout 600 python bench.py --impl reference > $O/ev_bench_reference.json 2> $O/ev_bench_reference.err; cut -c1-400 $O/ev_bench_reference.json
 timeout 300 python bench.py --steps 300 --warmup 20 --no-cpu-baseline --chunk 32 --batch 16 > $O/ev_bench_chunk32_batch16.json 2> $O/ev_bench_chunk32_batch16.err; cut -c1-300 $O/ev_bench_chunk32_batch16.json
