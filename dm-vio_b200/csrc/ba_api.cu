@@ -149,7 +149,7 @@ static int ba_allocate(dmv_ba* b, const dmv_ba_config* cfg) {
   CK(cudaMallocHost(&b->h_up, sizeof(HostUpload)));
   CK(cudaMallocHost(&b->h_adj, sizeof(BAAdj)));
   std::memset(b->h_up, 0, sizeof(HostUpload));
-  b->scratch_floats = std::max((size_t)mp * 8 * MF, npx * 3);
+  b->scratch_floats = std::max((size_t)mp * std::max(8 * MF, 21), npx * 3);   // 21 floats per point: the staged upload of dmv_ba_set_points
   CK(cudaMallocHost(&b->h_scratch, sizeof(float) * b->scratch_floats));
   CK(cudaMallocHost(&b->h_en_newest, sizeof(float) * mp));
   for (int f = 0; f < MF; f++) b->slots[f] = f;
@@ -280,18 +280,26 @@ int dmv_ba_set_points(dmv_ba* b, int npts, const int32_t* host, const float* u, 
     b->nchunks = c;
   }
   if (b->nchunks > b->max_chunks) return set_error(DMV_ERR_INVALID, "too many chunks");
-  float* s = b->h_scratch;
-  for (int i = 0; i < npts; i++) { s[2 * i] = u[i]; s[2 * i + 1] = v[i]; }
-  CK(cudaMemcpyAsync(b->d_uv, s, sizeof(float2) * npts, cudaMemcpyHostToDevice, b->stream));
-  CK(cudaStreamSynchronize(b->stream));
+  // one pinned staging block, the copies queued back to back, ONE synchronisation (was: seven blocking copies from pageable memory)
+  float* s = b->h_scratch;   // >= 8 * MAXF * mp floats
+  const size_t n = (size_t)npts;
+  float *s_uv = s, *s_id = s + 2 * n, *s_idz = s + 3 * n, *s_col = s + 4 * n, *s_w = s + 12 * n, *s_pr = s + 20 * n;
+  for (int i = 0; i < npts; i++) { s_uv[2 * i] = u[i]; s_uv[2 * i + 1] = v[i]; }
+  std::memcpy(s_id, idepth, sizeof(float) * n);
+  if (idepth_zero) std::memcpy(s_idz, idepth_zero, sizeof(float) * n);
+  std::memcpy(s_col, color8, sizeof(float) * 8 * n);
+  std::memcpy(s_w, weights8, sizeof(float) * 8 * n);
+  if (priorF) std::memcpy(s_pr, priorF, sizeof(float) * n);
   b->id_cur = b->id_bak = 0;
-  CK(cudaMemcpy(b->d_idepth[0], idepth, sizeof(float) * npts, cudaMemcpyHostToDevice));
   b->zero_alias = (idepth_zero == nullptr);
-  if (idepth_zero) CK(cudaMemcpy(b->d_idepth_zero, idepth_zero, sizeof(float) * npts, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(b->d_color, color8, sizeof(float) * 8 * npts, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(b->d_weights, weights8, sizeof(float) * 8 * npts, cudaMemcpyHostToDevice));
-  if (priorF) CK(cudaMemcpy(b->d_priorF, priorF, sizeof(float) * npts, cudaMemcpyHostToDevice));
-  else CK(cudaMemset(b->d_priorF, 0, sizeof(float) * npts));
+  CK(cudaMemcpyAsync(b->d_uv, s_uv, sizeof(float2) * n, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemcpyAsync(b->d_idepth[0], s_id, sizeof(float) * n, cudaMemcpyHostToDevice, b->stream));
+  if (idepth_zero) CK(cudaMemcpyAsync(b->d_idepth_zero, s_idz, sizeof(float) * n, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemcpyAsync(b->d_color, s_col, sizeof(float) * 8 * n, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemcpyAsync(b->d_weights, s_w, sizeof(float) * 8 * n, cudaMemcpyHostToDevice, b->stream));
+  if (priorF) CK(cudaMemcpyAsync(b->d_priorF, s_pr, sizeof(float) * n, cudaMemcpyHostToDevice, b->stream));
+  else CK(cudaMemsetAsync(b->d_priorF, 0, sizeof(float) * n, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
   b->nres = 0;
   b->hdi_solve_n = 0;
   b->en_newest_valid = false;
@@ -323,9 +331,10 @@ int dmv_ba_set_residuals(dmv_ba* b, int nres, const int32_t* point, const int32_
   b->st_in_clean = true;
   for (int i = 0; i < nres; i++)
     if (b->h_st_in[b->res_slot[i]] != RES_IN || b->h_en_in[b->res_slot[i]] != 0.f) { b->st_in_clean = false; break; }
-  CK(cudaMemcpy(b->d_st_in, b->h_st_in.data(), ns, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(b->d_en_in, b->h_en_in.data(), ns * sizeof(float), cudaMemcpyHostToDevice));
-  for (int k = 0; k < 2; k++) CK(cudaMemset(b->d_st_new[k], 0xff, ns));
+  CK(cudaMemcpyAsync(b->d_st_in, b->h_st_in.data(), ns, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemcpyAsync(b->d_en_in, b->h_en_in.data(), ns * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+  for (int k = 0; k < 2; k++) CK(cudaMemsetAsync(b->d_st_new[k], 0xff, ns, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
   b->have_tentative = b->have_committed = false;
   return DMV_OK;
 }
