@@ -73,8 +73,10 @@ int dmv_ba_batch_gn_step(dmv_ba_batch* B, const double* const* x, const dmv_ba_s
   std::memset(&hdr, 0, sizeof(hdr));
   hdr.B = n;
   B->max_nf = 2;
+  B->P = B->h[0]->P;   // with chunk_points = 0 a handle picks its shape per window: the batch needs ONE shape
   for (int i = 0; i < n; i++) {
     dmv_ba* b = B->h[i];
+    if (b->P != B->P) return set_error(DMV_ERR_STATE, "window %d uses %d-point chunks, window 0 %d: create the handles of a batch with an explicit chunk_points", i, b->P, B->P);
     if (!st[i]) return set_error(DMV_ERR_INVALID, "state %d is null", i);
     if (b->npts < 1) return set_error(DMV_ERR_STATE, "window %d: points not set", i);
     if (!b->have_adj) return set_error(DMV_ERR_STATE, "window %d: dmv_ba_set_adjoints first", i);

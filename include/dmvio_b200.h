@@ -54,7 +54,7 @@ typedef struct dmv_ba_config {
   int max_frames;     /* <= DMV_MAX_FRAMES */
   int max_points;     /* capacity of the active point set */
   int device;         /* CUDA device ordinal */
-  int chunk_points;   /* points per thread block: 16 or 32; 0 = default (16) */
+  int chunk_points;   /* points per thread block: 16 or 32; 0 = chosen per window (16 up to 16 x #SMs points, i.e. one wave; 32 beyond) */
 } dmv_ba_config;
 
 /* util/settings.cpp values read by the kernels (constant during a run) */
