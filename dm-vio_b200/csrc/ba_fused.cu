@@ -1205,11 +1205,6 @@ static cudaError_t launch_cfg(BAWinDev& W, const BAIter& it, cudaStream_t s, uns
   const int grid = min(W.nchunks, max_ctas);
   *bar_count += (unsigned)grid;   // monotonic arrival counter: every CTA of this launch adds one
   W.bar_target = *bar_count;
-  static const bool noncoop = [] { const char* e = getenv("DMV_BA_NONCOOP"); return e && atoi(e) != 0; }();   // experiment: plain launch (co-residency not guaranteed)
-  if (noncoop) {
-    ba_fused_kernel<P, MARG><<<grid, threads, smem, s>>>(W, it);
-    return cudaGetLastError();
-  }
   void* args[2] = {(void*)&W, (void*)&it};
   return cudaLaunchCooperativeKernel((const void*)ba_fused_kernel<P, MARG>, dim3(grid), dim3(threads), args, (size_t)smem, s);
 }
