@@ -1075,23 +1075,24 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR
             for (int j = 0; j < 4; j++) a[1][i][j] += ti[i] * uj[j];
         }
       }
-      // per-thread fp32 sums over <= npts / nthreads points, then fp64: transposing warp butterfly (31 exchanges for the 32 values: lane L
-      // ends with the warp's sum of value L), cross-warp through shared memory
+      // per-thread fp32 sums over <= npts / nthreads points; transposing warp butterfly in fp32 (31 exchanges for the 32 values: lane L ends with
+      // the warp's sum of value L over its <= 160 points; half the instructions of the fp64 form, and this straight-line code is fetched
+      // once per CTA, where instruction fetch is the stall), then fp64 across the warps in a fixed order through shared memory
       {
-        double d[32];
+        float d[32];
 #pragma unroll
         for (int qq = 0; qq < 2; qq++)
 #pragma unroll
           for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) d[qq * 16 + i * 4 + j] = (double)a[qq][i][j];
+            for (int j = 0; j < 4; j++) d[qq * 16 + i * 4 + j] = a[qq][i][j];
         static_for<0, 5>([&](auto sc) {
           constexpr int st2 = decltype(sc)::value, hstep = 16 >> st2, m = 16 >> st2;
           const bool up = (lane & m) != 0;
 #pragma unroll
           for (int k = 0; k < hstep; k++) d[k] = (up ? d[k + hstep] : d[k]) + __shfl_xor_sync(0xffffffffu, up ? d[k] : d[k + hstep], m);
         });
-        S.red[warp][lane] = d[0];   // lane L: value index 16 b4 + 8 b3 + 4 b2 + 2 b1 + b0 = L
+        S.red[warp][lane] = (double)d[0];   // lane L: value index 16 b4 + 8 b3 + 4 b2 + 2 b1 + b0 = L
       }
       __syncthreads();
       if (tid < 32) {  // the whole first warp (the exchange below is warp-collective)
