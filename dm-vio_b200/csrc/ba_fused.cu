@@ -1028,22 +1028,15 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR
       }
     }
     };
+  phase_d(0);
+
   // ---------------------------------------------------------------- phase E: [H_sc | b_sc] = sum_p HdiF w_p w_p^T as 4x4 tiles over ALL points
-  // of the window: a CTA takes tiles vcta, vcta + ncta (both in ONE pass over the points when the grid has fewer CTAs than tiles).
-  // Phases D and E are INTERLEAVED across the warps: behind the grid barrier every warp of the CTA would otherwise run the same
-  // never-fetched straight-line code in lockstep and all of them stall on the same instruction-cache misses; even warps do D then E, odd
-  // warps E then D, so that the two code regions are fetched concurrently and each warp finds one of them warm.
+  // of the window: a CTA takes tiles vcta, vcta + ncta (both in ONE pass over the points when the grid has fewer CTAs than tiles)
   {
     const int T = W.T, npts = W.npts;
-    const bool d_first = (warp & 1) == 0;
-    for (int it = 0, tile0 = vcta; it == 0 || tile0 < W.ntiles; it++, tile0 += 2 * ncta) {
-      const bool have = tile0 < W.ntiles;   // CTA-uniform
+    for (int tile0 = vcta; tile0 < W.ntiles; tile0 += 2 * ncta) {
       const int tile1 = tile0 + ncta;
       const bool two = tile1 < W.ntiles;
-#pragma unroll 1
-      for (int half = 0; half < 2; half++) {
-        if (it == 0 && ((half == 0) == d_first)) phase_d(0);
-        if (!(have && ((half == 1) == d_first))) continue;
       int ti0 = 0, rem = tile0;
       while (rem >= T - ti0) { rem -= T - ti0; ti0++; }
       const int tj0 = ti0 + rem;
@@ -1101,8 +1094,6 @@ __device__ __forceinline__ void fused_reduce(const BAWinDev& W, FusedSmem<P, LPR
         });
         S.red[warp][lane] = (double)d[0];   // lane L: value index 16 b4 + 8 b3 + 4 b2 + 2 b1 + b0 = L
       }
-      }
-      if (!have) break;
       __syncthreads();
       if (tid < 32) {  // the whole first warp (the exchange below is warp-collective)
         const bool own = tid < 16 || two;
