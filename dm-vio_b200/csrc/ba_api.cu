@@ -8,7 +8,7 @@
 
 using namespace dmv;
 
-// all-reduce of the stitched result blob across ranks: fused into the stitch kernel when the peer-memory exchange is on
+// all-reduce of the result blob across ranks: done inside ba_fused_kernel when the peer-memory exchange is on
 // (fill_descriptor/next_exchange hand it the inbox table), otherwise one ncclAllReduce behind it
 int dmv_ba_enqueue_exchange(dmv_ba* b) {
   if (b->xchg_on) return DMV_OK;
@@ -53,7 +53,7 @@ int dmv_ba_fill_descriptor(dmv_ba* b) {
   return DMV_OK;
 }
 
-// every stitch launch of a sharded handle is one exchange: number it (all ranks launch the same sequence of stitches)
+// every launch of a sharded handle is one exchange: number it (all ranks make the same sequence of launches)
 void dmv_ba_next_exchange(dmv_ba* b) {
   if (!b->xchg_on) return;
   b->xchg_seq++;
@@ -582,7 +582,7 @@ static void unpack_system(const dmv_ba* b, const double* r, double* H_A, double*
       for (int c = 0; c < 4; c++) H_A[(size_t)c * N + i] = H_A[(size_t)i * N + c];
   }
   if (b_A) std::memcpy(b_A, r + (size_t)N * N, sizeof(double) * N);
-  const double* sc = r + (size_t)N * N + N;  // raw upper-triangular 4x4 Gram tiles of [H_sc | b_sc] (ba_point.cu, phase C)
+  const double* sc = r + (size_t)N * N + N;  // raw upper-triangular 4x4 Gram tiles of [H_sc | b_sc] (ba_fused.cu, phase E)
   auto gram = [&](int rr, int cc) {
     if (cc < N && rr > cc) std::swap(rr, cc);
     const int ti = rr >> 2, tj = cc >> 2;

@@ -45,7 +45,7 @@ struct BAAdj {
   double adTdiag[MAXF * MAXF][8];
 };
 
-// peer-memory exchange fused into ba_stitch_kernel.  Inbox of one rank (cudaMalloc + CUDA IPC):
+// peer-memory exchange inside ba_fused_kernel.  Inbox of one rank (cudaMalloc + CUDA IPC):
 // [2 parities][XCHG_MAXR source ranks][pitch] 16-byte packets {value.lo, seq, value.hi, seq}  ("LL" packets: flag travels with the data)
 constexpr int XCHG_MAXR = 8;
 struct BAXchg {
@@ -54,7 +54,7 @@ struct BAXchg {
   uint4* inbox[XCHG_MAXR];            // rank r's inbox as mapped in THIS process ([rank] = own)
 };
 
-// tables of a marginalisation launch (dmv_ba_marginalize_points -> ba_point_kernel<.., MARG = true>); device memory, never read in production
+// tables of a marginalisation launch (dmv_ba_marginalize_points -> ba_fused_kernel<.., MARG = true>); device memory, never read in production
 struct BAMarg {
   float adHTdelta[MAXF * MAXF][8];  // [h*nf + t]: (state - state_zero)_h^T adHostF + (..)_t^T adTargetF  (EnergyFunctional.cpp:L175-198)
   float cDelta[4];                  // calibration value - value_zero (scaled), as float

@@ -95,7 +95,7 @@ struct dmv_ba {
   float* d_act = nullptr;      // point-activation staging (dmv_ba_activate_points)
   float* h_act = nullptr;
   int act_cap = 0;
-  // peer-memory exchange (fused into ba_stitch_kernel)
+  // peer-memory exchange (inside ba_fused_kernel)
   void* xchg_own = nullptr;                 // this rank's inbox (cudaMalloc, exported through CUDA IPC)
   void* xchg_map[XCHG_MAXR] = {nullptr};    // every rank's inbox as mapped here ([rank] == xchg_own)
   int xchg_pitch = 0;

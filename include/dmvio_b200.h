@@ -112,7 +112,7 @@ int dmv_ba_set_state(dmv_ba* ba, const dmv_ba_state* st);
 
 /* FullSystem::linearizeAll(false) (FullSystemOptimize.cpp:L150-218) fused with the *tentative* accumulateAF/SCF of the
  * next solveSystemF: evaluates every active residual at the current state, reduces the per-pair 13x13 blocks, the
- * per-point Hdd/bd/Hcd and the Schur complement, and stitches the dense system on the device.
+ * per-point Hdd/bd/Hcd and the Schur complement, and assembles the dense system on the device (one launch).
  * Nothing becomes visible to dmv_ba_accumulate / dmv_ba_resubstitute until dmv_ba_apply_res().
  * out: energy = sum of PointFrameResidual::linearize() return values (stats[0]); n_in = #residuals with state_NewState==IN. */
 typedef struct dmv_ba_lin_result {
@@ -217,16 +217,17 @@ typedef struct dmv_ba_marg_args {
 int dmv_ba_marginalize_points(dmv_ba* ba, const dmv_ba_marg_args* a);
 
 /* Multi-GPU: points are sharded over ranks, images/tables replicated.  After dmv_ba_comm_init every
- * dmv_ba_linearize all-reduces the stitched system (and energy/counters) over NCCL so all ranks hold identical H,b.
+ * dmv_ba_linearize / dmv_ba_gn_step / dmv_ba_marginalize_points all-reduces the system (and energy / counters) over NCCL so that all ranks
+ * hold identical H,b; every rank must make the same sequence of these calls (dmv_ba_marginalize_points with its own flagged points, possibly none).
  * nccl_unique_id: 128 bytes from ncclGetUniqueId() on rank 0, distributed by the caller. */
 int dmv_nccl_unique_id(void* id128);
 int dmv_ba_comm_init(dmv_ba* ba, int nranks, int rank, const void* nccl_unique_id);
 
 /* The same exchange without NCCL, over NVLink/NVSwitch peer memory (CUDA IPC, one process per GPU of one node, <= 8 ranks):
  * every rank exports its inbox (64-byte cudaIpcMemHandle_t), the caller all-gathers the handles (any transport: MPI,
- * torch.distributed, a file) and every rank imports all of them.  From then on the all-reduce is FUSED INTO THE STITCH KERNEL:
- * each stitch CTA pushes the entries it produced to every peer as 16-byte flag-carrying packets, waits for the peers' packets of
- * the same entries and adds them in rank order (bit-identical H,b on all ranks; no extra launch, no fence round trip).
+ * torch.distributed, a file) and every rank imports all of them.  From then on the all-reduce happens INSIDE THE LINEARISATION KERNEL:
+ * the lanes that produce a result entry push it to every peer as a 16-byte flag-carrying packet, later wait (bounded: DMV_ERR_TIMEOUT) for the
+ * peers' packets of the same entry and add them in rank order (bit-identical H,b on all ranks; no extra launch, no fence round trip).
  * Takes precedence over a NCCL communicator if both are set; nranks = 1 in dmv_ba_p2p_import switches it off again.
  * No reference counterpart (the reference is single-node CPU). */
 int dmv_ba_p2p_export(dmv_ba* ba, void* ipc_handle64);
