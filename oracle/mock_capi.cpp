@@ -21,7 +21,15 @@
 
 using namespace orc;
 
+// Multi-rank emulation for the CPU tier: the CUDA library sums the linearised system over the ranks inside the launch; here the test
+// installs a host all-reduce (sum over ranks of a double buffer, e.g. torch.distributed / gloo) and the stand-in calls it at the same places.
+typedef void (*mock_allreduce_cb)(double* buf, int n, void* user);
+static mock_allreduce_cb g_allreduce = nullptr;
+static void* g_allreduce_user = nullptr;
+extern "C" void mock_set_allreduce(mock_allreduce_cb cb, void* user) { g_allreduce = cb; g_allreduce_user = user; }
+
 struct dmv_ba {
+  int nranks = 1;
   Window W;
   dmv_ba_config cfg;
   std::vector<std::vector<float>> slot_dI;  // per image slot: level-0 [I, dx, dy] AoS
@@ -40,6 +48,35 @@ struct dmv_ct {
   std::vector<std::vector<float>> pyr;  // pyramid of the frame uploaded last
 };
 
+static void mock_allreduce(dmv_ba* b, std::vector<double>& v) {
+  if (b->nranks > 1 && g_allreduce) g_allreduce(v.data(), (int)v.size(), g_allreduce_user);
+}
+// energy + counters of a linearisation, summed over the ranks like the counters slot of the CUDA library's result blob
+static void mock_reduce_lin(dmv_ba* b, double& E, dmv_ba_lin_result* out, double s3[3]) {
+  if (b->nranks <= 1) return;
+  std::vector<double> v = {E, out ? (double)out->n_in : 0.0, out ? (double)out->n_oob : 0.0, out ? (double)out->n_outlier : 0.0, s3 ? s3[0] : 0.0, s3 ? s3[1] : 0.0, s3 ? s3[2] : 0.0};
+  mock_allreduce(b, v);
+  E = v[0];
+  if (out) { out->energy = v[0]; out->n_in = (int)v[1]; out->n_oob = (int)v[2]; out->n_outlier = (int)v[3]; }
+  if (s3) { s3[0] = v[4]; s3[1] = v[5]; s3[2] = v[6]; }
+}
+static void mock_reduce_system(dmv_ba* b, ReducedSystem& sys) {
+  if (b->nranks <= 1) return;
+  const int N = sys.N;
+  std::vector<double> v;
+  v.insert(v.end(), sys.HA.d.begin(), sys.HA.d.end());
+  v.insert(v.end(), sys.bA.begin(), sys.bA.end());
+  v.insert(v.end(), sys.Hsc.d.begin(), sys.Hsc.d.end());
+  v.insert(v.end(), sys.bsc.begin(), sys.bsc.end());
+  v.push_back((double)sys.resInA);
+  mock_allreduce(b, v);
+  size_t o = 0;
+  std::copy(v.begin() + o, v.begin() + o + (size_t)N * N, sys.HA.d.begin()); o += (size_t)N * N;
+  std::copy(v.begin() + o, v.begin() + o + N, sys.bA.begin()); o += N;
+  std::copy(v.begin() + o, v.begin() + o + (size_t)N * N, sys.Hsc.d.begin()); o += (size_t)N * N;
+  std::copy(v.begin() + o, v.begin() + o + N, sys.bsc.begin()); o += N;
+  sys.resInA = (int)v[o];
+}
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -194,6 +231,12 @@ int dmv_ba_gn_step(dmv_ba* b, const double* x, const dmv_ba_state* st, dmv_ba_li
       out->n_in += r.state_NewState == RS_IN; out->n_oob += r.state_NewState == RS_OOB; out->n_outlier += r.state_NewState == RS_OUTLIER;
     }
   }
+  {
+    double Er = E;
+    dmv_ba_lin_result tmp;
+    if (!out) { tmp.energy = E; tmp.n_in = tmp.n_oob = tmp.n_outlier = 0; }
+    mock_reduce_lin(b, Er, out ? out : &tmp, s3);
+  }
   if (sums) { sums[0] = s3[0]; sums[1] = s3[1]; sums[2] = s3[2]; }
   b->have_tentative = true;
   return DMV_OK;
@@ -216,6 +259,12 @@ int dmv_ba_linearize(dmv_ba* b, dmv_ba_lin_result* out) {
       out->n_in += r.state_NewState == RS_IN; out->n_oob += r.state_NewState == RS_OOB; out->n_outlier += r.state_NewState == RS_OUTLIER;
     }
   }
+  {
+    double Er = E;
+    dmv_ba_lin_result tmp;
+    tmp.energy = E; tmp.n_in = tmp.n_oob = tmp.n_outlier = 0;
+    mock_reduce_lin(b, Er, out ? out : &tmp, nullptr);
+  }
   b->have_tentative = true;
   return DMV_OK;
 }
@@ -236,13 +285,27 @@ int dmv_ba_resubstitute(dmv_ba* b, const double* x, float* step_out, int apply, 
   return DMV_OK;
 }
 // the CPU stand-in has no ranks: the exchange set-up entry points exist for the adapter's link, and refuse
-int dmv_ba_p2p_export(dmv_ba*, void*) { return fail(DMV_ERR_STATE, "host-logic mock: no multi-GPU exchange"); }
-int dmv_ba_p2p_import(dmv_ba*, int, int, const void*) { return fail(DMV_ERR_STATE, "host-logic mock: no multi-GPU exchange"); }
-int dmv_ba_comm_init(dmv_ba*, int, int, const void*) { return fail(DMV_ERR_STATE, "host-logic mock: no multi-GPU exchange"); }
+int dmv_ba_p2p_export(dmv_ba*, void* h64) {
+  if (!g_allreduce) return fail(DMV_ERR_STATE, "host-logic mock: no multi-rank exchange (mock_set_allreduce first)");
+  std::memset(h64, 0, 64);
+  return DMV_OK;
+}
+int dmv_ba_p2p_import(dmv_ba* b, int nranks, int, const void*) {
+  if (!g_allreduce) return fail(DMV_ERR_STATE, "host-logic mock: no multi-rank exchange (mock_set_allreduce first)");
+  b->nranks = nranks;
+  return DMV_OK;
+}
+int dmv_ba_comm_init(dmv_ba* b, int nranks, int, const void*) {
+  if (!g_allreduce) return fail(DMV_ERR_STATE, "host-logic mock: no multi-rank exchange (mock_set_allreduce first)");
+  b->nranks = nranks;
+  return DMV_OK;
+}
+
 int dmv_ba_apply_res(dmv_ba* b) {
   if (!b->have_tentative) return fail(DMV_ERR_STATE, "no tentative linearisation to commit");
   b->W.applyResAll();
   b->W.accumulate(b->sys, 1);  // the device accumulates while it linearises: the committed system belongs to the committed state
+  mock_reduce_system(b, b->sys);
   b->have_committed = true; b->have_tentative = false;
   return DMV_OK;
 }
@@ -350,6 +413,7 @@ int dmv_ba_marginalize_points(dmv_ba* b, const dmv_ba_marg_args* a) {
   std::vector<int> good = W.fixLinearization(pts);
   ReducedSystem sys;
   W.marginalizePoints(pts, 1, sys);
+  mock_reduce_system(b, sys);
   if (a->M) std::memcpy(a->M, sys.HA.d.data(), sizeof(double) * N * N);
   if (a->Mb) std::memcpy(a->Mb, sys.bA.data(), sizeof(double) * N);
   if (a->Msc) std::memcpy(a->Msc, sys.Hsc.d.data(), sizeof(double) * N * N);

@@ -149,3 +149,88 @@ def test_shard_edge_cases(synth):
             assert S["res_point"].max() < len(S["host"])
     np.testing.assert_array_equal(seen, 1)
     assert shard_window(W, 0, 1) is W
+
+
+def _worker_adapter(rank, world, port, cfg, q):
+    """one rank of the sharded C++ adapter on the CPU stand-in of the C ABI; the stand-in's system all-reduce and the adapter's allgather
+    both go through gloo"""
+    import ctypes as C
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import dmvio_b200.hostapi as hostapi
+    import dmvio_b200.synth as synth
+    from test_gpu_multi import _flow
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L = C.CDLL(os.path.join(root, "oracle", "libhost_on_oracle.so"))
+    hostapi._L = hostapi._bind(L)
+
+    CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.c_void_p)
+
+    def _allreduce(buf, n, user):
+        a = np.ctypeslib.as_array(buf, shape=(n,))
+        t = torch.from_numpy(a.copy())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        a[:] = t.numpy()
+    cb = CB(_allreduce)
+    L.mock_set_allreduce.argtypes = [CB, C.c_void_p]
+    L.mock_set_allreduce(cb, None)
+
+    def allgather(data):
+        t = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return b"".join(o.numpy().tobytes() for o in outs)
+
+    W = synth.make_window(**cfg)
+    hw = hostapi.WindowBA(W, shard=dict(rank=rank, nranks=world, allgather=allgather, exchange="p2p"))
+    out = _flow(hw, W["nf"])
+    q.put((rank, out))
+    dist.barrier()
+    hw.close()
+    dist.destroy_process_group()
+
+
+def test_sharded_adapter_flow_matches_unsharded(orc, synth):
+    """WindowBA::setSharding on the CPU: two ranks run the whole makeKeyFrame flow (optimize, tail with residual removal, flagPointsForRemoval,
+    marginalizePointsF, marginalizeFrame, optimize again) on their shares; the stand-in of the C ABI sums the systems over the ranks where the
+    CUDA library does it inside the launch.  Same decisions and state as the unsharded adapter; the ranks agree bit for bit."""
+    import ctypes as C
+    import subprocess
+    import dmvio_b200.hostapi as hostapi
+    from test_gpu_multi import _flow
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "oracle"), "libhost_on_oracle.so"])
+    world = 2
+    cfg = dict(nf=5, npts=301, seed=31, state_noise=1e-3, hosts="all", w=160, h=120)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_adapter, args=(r, world, port, cfg, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    saved = hostapi._L
+    hostapi._L = hostapi._bind(C.CDLL(os.path.join(root, "oracle", "libhost_on_oracle.so")))
+    try:
+        ref = _flow(hostapi.WindowBA(synth.make_window(**cfg)), cfg["nf"])
+    finally:
+        hostapi._L = saved
+    for rk in range(world):
+        o = res[rk]
+        assert (o["n1"], o["n2"], o["resInM"], o["nres"]) == (ref["n1"], ref["n2"], ref["resInM"], ref["nres"])
+        np.testing.assert_array_equal(o["marg"], ref["marg"]); np.testing.assert_array_equal(o["drop"], ref["drop"])
+        np.testing.assert_array_equal(o["removed"], ref["removed"])
+        np.testing.assert_allclose(o["log1"], ref["log1"], rtol=1e-9)     # fp64 sums in another order only
+        np.testing.assert_allclose(o["log2"], ref["log2"], rtol=1e-8)
+        assert rel(o["HM"], ref["HM"]) < 1e-9 and rel(o["bM"], ref["bM"]) < 1e-8
+        assert np.abs(o["st"] - ref["st"]).max() < 1e-9
+        np.testing.assert_allclose(o["idepth"], ref["idepth"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(res[1]["st"], res[0]["st"])
+    np.testing.assert_array_equal(res[1]["idepth"], res[0]["idepth"])
