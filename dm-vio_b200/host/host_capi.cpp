@@ -1,6 +1,7 @@
 #include "host_capi.h"
 #include <string>
 #include "coarse_tracker.h"
+#include "coarse_initializer.h"
 #include "window_ba.h"
 #include "marg_frame.h"
 #include "nullspace.h"
@@ -241,4 +242,60 @@ int dmvh_ct_track(void* p, double R[9], double t[3], double* a, double* b, int c
   return good ? 1 : 0;
 }
 
+
+// ---- CoarseInitializer adapter
+void* dmvh_ci_create(int w, int h, int levels, int max_points, int device, const double cvs[4]) {
+  CoarseInitializer* C = new CoarseInitializer(w, h, levels, max_points, device);
+  CalibHessian H;
+  initCalib(H, cvs);
+  C->makeK(H);
+  return C;
+}
+void dmvh_ci_destroy(void* p) { delete static_cast<CoarseInitializer*>(p); }
+const char* dmvh_ci_error(void* p) { return static_cast<CoarseInitializer*>(p)->error().c_str(); }
+// points of all levels concatenated (n[l] per level): u, v, my_type, parent, neighbours (10 per point); dIp: the first frame's pyramid, concatenated
+int dmvh_ci_set_first(void* p, const float* dIp, float exposure, const int32_t* n, const float* u, const float* v, const float* type, const int32_t* parent,
+                      const int32_t* neighbours10) {
+  CoarseInitializer* C = static_cast<CoarseInitializer*>(p);
+  if (!C->ok()) return -1;
+  const float* lv[DMV_MAX_PYR_LEVELS];
+  size_t off = 0, q = 0;
+  for (int l = 0; l < C->levels(); l++) {
+    lv[l] = dIp + off;
+    off += (size_t)(C->width(l) * C->height(l)) * 3;
+    C->points[l].assign(n[l], Pnt());
+    for (int i = 0; i < n[l]; i++, q++) {
+      Pnt& pt = C->points[l][i];
+      pt.u = u[q]; pt.v = v[q]; pt.my_type = type[q]; pt.parent = parent[q];
+      for (int k = 0; k < 10; k++) pt.neighbours[k] = neighbours10[10 * q + k];
+    }
+  }
+  return C->setFirst(lv, exposure) ? 0 : -1;
+}
+// CoarseInitializer::trackFrame; out: R[9] t[3] (thisToNext), ab[2], state[3] = snapped, snappedAt, frameID; returns its bool (or -1 on error)
+int dmvh_ci_track(void* p, const float* dIp, float exposure, double* R9, double* t3, double* ab2, int32_t* state3) {
+  CoarseInitializer* C = static_cast<CoarseInitializer*>(p);
+  const float* lv[DMV_MAX_PYR_LEVELS];
+  size_t off = 0;
+  for (int l = 0; l < C->levels(); l++) { lv[l] = dIp + off; off += (size_t)(C->width(l) * C->height(l)) * 3; }
+  const bool ok = C->trackFrame(lv, exposure);
+  if (!C->error().empty()) return -1;
+  for (int i = 0; i < 9; i++) R9[i] = C->thisToNext.R[i];
+  for (int i = 0; i < 3; i++) t3[i] = C->thisToNext.t[i];
+  ab2[0] = C->thisToNext_aff.a; ab2[1] = C->thisToNext_aff.b;
+  state3[0] = C->snapped ? 1 : 0; state3[1] = C->snappedAt; state3[2] = C->frameID;
+  return ok ? 1 : 0;
+}
+int dmvh_ci_npts(void* p, int lvl) { return (int)static_cast<CoarseInitializer*>(p)->points[lvl].size(); }
+// per-point state, 12 floats: idepth idepth_new iR energy0 energy1 energy_new0 energy_new1 lastHessian lastHessian_new maxstep isGood isGood_new
+void dmvh_ci_get_points(void* p, int lvl, float* out12) {
+  const std::vector<Pnt>& pts = static_cast<CoarseInitializer*>(p)->points[lvl];
+  for (size_t i = 0; i < pts.size(); i++) {
+    const Pnt& q = pts[i];
+    float* o = out12 + 12 * i;
+    o[0] = q.idepth; o[1] = q.idepth_new; o[2] = q.iR; o[3] = q.energy[0]; o[4] = q.energy[1]; o[5] = q.energy_new[0]; o[6] = q.energy_new[1];
+    o[7] = q.lastHessian; o[8] = q.lastHessian_new; o[9] = q.maxstep; o[10] = q.isGood ? 1.f : 0.f; o[11] = q.isGood_new ? 1.f : 0.f;
+  }
+}
+long long dmvh_ci_evaluations(void* p) { return static_cast<CoarseInitializer*>(p)->evaluations; }
 }  // extern "C"

@@ -73,6 +73,18 @@ void dmvh_ct_set_device_lm(void* ct, int on);
 double dmvh_ct_point_evaluations(void* ct); /* CoarseTracker::pointEvaluations of the last track (measurement) */ /* 1 (default): LM loop on the device (dmv_ct_track); 0: host loop */
 int dmvh_ct_track(void* ct, double R[9], double t[3], double* a, double* b, int coarsestLvl, const double minResForAbort[5],
                   double lastResiduals[5], double flow[3], int* iterations, long long* evaluations);
+
+/* CoarseInitializer adapter (host/coarse_initializer.h): trackFrame on the host, calcResAndGS on the device */
+void* dmvh_ci_create(int w, int h, int levels, int max_points, int device, const double calib_value_scaled[4]);
+void dmvh_ci_destroy(void* ci);
+const char* dmvh_ci_error(void* ci);
+int dmvh_ci_set_first(void* ci, const float* dIp_concat, float exposure, const int32_t* n_per_level, const float* u, const float* v, const float* type,
+                      const int32_t* parent, const int32_t* neighbours10);
+int dmvh_ci_track(void* ci, const float* dIp_concat, float exposure, double* R9, double* t3, double* ab2, int32_t* state3);
+int dmvh_ci_npts(void* ci, int lvl);
+void dmvh_ci_get_points(void* ci, int lvl, float* out12);
+long long dmvh_ci_evaluations(void* ci);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,17 @@ def _bind(L):
         L.dmvh_window_energy_L.argtypes = [vp]
         L.dmvh_window_energy_M.restype = C.c_double
         L.dmvh_window_energy_M.argtypes = [vp]
+        L.dmvh_ci_create.restype = vp
+        L.dmvh_ci_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64p]
+        L.dmvh_ci_destroy.argtypes = [vp]
+        L.dmvh_ci_error.restype = C.c_char_p
+        L.dmvh_ci_error.argtypes = [vp]
+        L.dmvh_ci_set_first.argtypes = [vp, f32p, C.c_float, i32p, f32p, f32p, f32p, i32p, i32p]
+        L.dmvh_ci_track.argtypes = [vp, f32p, C.c_float, f64p, f64p, f64p, i32p]
+        L.dmvh_ci_npts.argtypes = [vp, C.c_int]
+        L.dmvh_ci_get_points.argtypes = [vp, C.c_int, f32p]
+        L.dmvh_ci_evaluations.restype = C.c_longlong
+        L.dmvh_ci_evaluations.argtypes = [vp]
         L.dmvh_ct_create.restype = vp
         L.dmvh_ct_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64p]
         L.dmvh_ct_destroy.argtypes = [vp]
@@ -295,3 +306,52 @@ class CoarseTracker:
         self.L.dmvh_ct_point_evaluations.argtypes = [C.c_void_p]
         return dict(good=bool(good), R=R.reshape(3, 3), t=t, a=ca.value, b=cb.value, lastResiduals=lastRes, flow=flow, iterations=its.value,
                     evaluations=ev.value, point_evaluations=self.L.dmvh_ct_point_evaluations(self.h))
+
+
+class CoarseInit:
+    """dmvio_b200::CoarseInitializer (host/coarse_initializer.h): trackFrame on the host, calcResAndGS on the device.  Points of all levels,
+    parents and neighbour lists are inputs (the pixel selector and the kd-tree are not part of the path)."""
+
+    def __init__(self, w, h, K, levels, max_points=16384, device=0):
+        self.L = lib()
+        self.levels = levels
+        self.h = self.L.dmvh_ci_create(w, h, levels, max_points, device, _c(K, np.float64))
+
+    def close(self):
+        if self.h:
+            self.L.dmvh_ci_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _concat(pyr):
+        return np.ascontiguousarray(np.concatenate([np.asarray(p, np.float32).reshape(-1) for p in pyr]))
+
+    def set_first(self, pyr, exposure, pts):
+        """pts: list per level of dict(u, v, type, parent, neighbours (n, 10))"""
+        n = np.array([len(p["u"]) for p in pts], np.int32)
+        cat = lambda k, t: np.ascontiguousarray(np.concatenate([np.asarray(p[k], t).reshape(-1) for p in pts]))
+        rc = self.L.dmvh_ci_set_first(self.h, self._concat(pyr[:self.levels]), float(exposure), n, cat("u", np.float32), cat("v", np.float32),
+                                      cat("type", np.float32), cat("parent", np.int32), cat("neighbours", np.int32))
+        if rc != 0:
+            raise capi.DmvError(self.L.dmvh_ci_error(self.h).decode())
+
+    def track(self, pyr, exposure):
+        R, t, ab, st = np.zeros(9), np.zeros(3), np.zeros(2), np.zeros(3, np.int32)
+        ok = self.L.dmvh_ci_track(self.h, self._concat(pyr[:self.levels]), float(exposure), R, t, ab, st)
+        if ok < 0:
+            raise capi.DmvError(self.L.dmvh_ci_error(self.h).decode())
+        return dict(ok=bool(ok), R=R.reshape(3, 3), t=t, a=ab[0], b=ab[1], snapped=bool(st[0]), snappedAt=int(st[1]), frameID=int(st[2]),
+                    evaluations=int(self.L.dmvh_ci_evaluations(self.h)))
+
+    def points(self, lvl):
+        n = self.L.dmvh_ci_npts(self.h, lvl)
+        o = np.zeros((n, 12), np.float32)
+        self.L.dmvh_ci_get_points(self.h, lvl, o.reshape(-1))
+        keys = ("idepth", "idepth_new", "iR", "energy0", "energy1", "energy_new0", "energy_new1", "lastHessian", "lastHessian_new", "maxstep", "isGood", "isGood_new")
+        return {k: o[:, i].copy() for i, k in enumerate(keys)}

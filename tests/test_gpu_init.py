@@ -92,3 +92,29 @@ def test_init_handle_errors(synth):
     with pytest.raises(capi.DmvError):   # no K / frames yet
         g.calc_res_and_gs(0, np.eye(3), np.zeros(3), np.zeros(3), (1.0, 0.0), np.ones(4), np.ones(4), np.zeros((4, 2)), np.ones(4))
     g.close()
+
+
+def test_initializer_adapter_track_frames(orc, synth):
+    """dmvio_b200::CoarseInitializer (C++ adapter: trackFrame's loop on the host, calcResAndGS on the device) over six frames vs the oracle's
+    trackFrame: same ok / snapped / snappedAt / frameID decisions, poses and depths to float accumulation order."""
+    import dmvio_b200.hostapi as hostapi
+    frames = [synth.make_tracking_pair(seed=77, trans=0.02 * k, rot=0.004 * k) for k in (1, 2, 3)]
+    T = frames[0]
+    w, h, L = T["w"], T["h"], T["levels"]
+    pts = init_points(np.random.default_rng(6), w, h, L, (3000, 900, 300, 100))
+    oc = orc.CoarseInit(w, h, T["K"])
+    oc.set_first(T["pyr_ref"], 1.0, pts)
+    g = hostapi.CoarseInit(w, h, T["K"], L, max_points=3008)
+    g.set_first(T["pyr_ref"], 1.0, pts)
+    for k, F in enumerate(frames + frames[::-1]):
+        to, tg = oc.track(F["pyr_new"], 1.0 + 0.05 * k), g.track(F["pyr_new"], 1.0 + 0.05 * k)
+        assert (tg["ok"], tg["snapped"], tg["snappedAt"], tg["frameID"]) == (to["ok"], to["snapped"], to["snappedAt"], to["frameID"]), k
+        np.testing.assert_allclose(tg["R"], to["R"], rtol=0, atol=5e-5)
+        np.testing.assert_allclose(tg["t"], to["t"], rtol=0, atol=5e-4 * max(1e-2, np.abs(to["t"]).max()))
+        assert abs(tg["a"] - to["a"]) < 1e-6 and abs(tg["b"] - to["b"]) < 2e-3
+        po, pg = oc.points(0), g.points(0)
+        same = po["isGood"] == pg["isGood"]
+        assert same.mean() > 0.99
+        assert np.median(np.abs(pg["idepth"][same] - po["idepth"][same]) / np.abs(po["idepth"][same])) < 2e-4
+    assert tg["snapped"] and tg["evaluations"] > 50
+    g.close()

@@ -380,3 +380,31 @@ def test_compute_ba_update_hook_receives_the_reference_conventions(hostapi, orc,
     assert calls[0][0] == pytest.approx(1e-5)                               # first lambda
     np.testing.assert_allclose(log_h, log_ref, rtol=2e-5)   # numpy's LU vs the adapter's pivoted LDL^T on a system conditioned ~1e7
     assert np.abs(st_h - st_ref).max() < 2e-6
+
+
+def test_coarse_initializer_adapter_matches_oracle(hostapi, orc, synth):
+    """dmvio_b200::CoarseInitializer::trackFrame (host loop over the pyramid, LM control, doStep / applyStep / optReg / propagateUp / Down /
+    resetPoints) on the CPU stand-in of dmv_ci_calc_res_and_gs vs the oracle's trackFrame (pinned to the reference's compiled code): same
+    decisions over six frames, poses and depths to float accumulation order."""
+    from helpers import init_points
+    frames = [synth.make_tracking_pair(seed=77, trans=0.02 * k, rot=0.004 * k) for k in (1, 2, 3)]
+    T = frames[0]
+    w, h, L = T["w"], T["h"], T["levels"]
+    pts = init_points(np.random.default_rng(6), w, h, L, (3000, 900, 300, 100))
+    oc = orc.CoarseInit(w, h, T["K"])
+    assert oc.levels == L
+    oc.set_first(T["pyr_ref"], 1.0, pts)
+    g = hostapi.CoarseInit(w, h, T["K"], L, max_points=3008)
+    g.set_first(T["pyr_ref"], 1.0, pts)
+    for k, F in enumerate(frames + frames[::-1]):
+        to, tg = oc.track(F["pyr_new"], 1.0 + 0.05 * k), g.track(F["pyr_new"], 1.0 + 0.05 * k)
+        assert (tg["ok"], tg["snapped"], tg["snappedAt"], tg["frameID"]) == (to["ok"], to["snapped"], to["snappedAt"], to["frameID"]), k
+        np.testing.assert_allclose(tg["R"], to["R"], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(tg["t"], to["t"], rtol=0, atol=2e-4 * max(1e-2, np.abs(to["t"]).max()))
+        assert abs(tg["a"] - to["a"]) < 1e-6 and abs(tg["b"] - to["b"]) < 1e-4
+        po, pg = oc.points(0), g.points(0)
+        same = po["isGood"] == pg["isGood"]
+        assert same.mean() > 0.995
+        assert np.median(np.abs(pg["idepth"][same] - po["idepth"][same]) / np.abs(po["idepth"][same])) < 1e-4
+    assert tg["snapped"] and tg["evaluations"] > 50
+    g.close()
